@@ -1,0 +1,111 @@
+/*
+ * vslam_b200.h -- C-ABI of the B200-native stereo-VO + sliding-window-BA hot path.
+ *
+ * Drop-in boundary for shangzhouye/stereo-visual-slam.  The reference has no FFI or
+ * plugin registry: its boundary is the C++ signatures of visual_odometry.hpp / optimization.hpp.
+ * The C++ host layer in stereo-visual-slam_b200/host/ keeps those signatures and calls the entry
+ * points below; every entry point cites the reference code it replaces.  Plain pointers and sizes
+ * only -- no torch, OpenCV, Eigen or Sophus types cross this line.
+ *
+ * Conventions
+ *   - every call returns an int status (VSLAM_OK == 0, negative = error) and never throws;
+ *   - `*_dev` entry points take DEVICE pointers, enqueue on the context's stream and return without
+ *     synchronising; all other entry points take HOST pointers and are synchronous on return;
+ *   - one context = one device + one stream; a context is not thread-safe;
+ *   - there is no CPU fallback: without a usable sm_100-class device vslam_ctx_create fails.
+ */
+#ifndef VSLAM_B200_H
+#define VSLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSLAM_ABI_VERSION 1
+
+/* status codes (reference convention: 0 ok / -1 image missing, visual_odometry.cpp:53-57,73-77) */
+enum {
+    VSLAM_OK = 0,
+    VSLAM_E_INVALID = -1,   /* null pointer / bad size (the reference's "-1: could not open or find the image") */
+    VSLAM_E_CAPACITY = -2,  /* input exceeds the capacity the context was created with */
+    VSLAM_E_CUDA = -3,      /* CUDA runtime error; see vslam_last_error() */
+    VSLAM_E_NODEVICE = -4,  /* no CUDA device / not an sm_100-class device */
+    VSLAM_E_NUMERIC = -5,   /* linear solve failed on every LM trial etc. */
+    VSLAM_E_OVERFLOW = -6   /* a device-side work list overflowed (raise the capacity) */
+};
+
+typedef struct vslam_ctx vslam_ctx;
+
+/* POD mirror of cv::KeyPoint (28 bytes: pt.x, pt.y, size, angle, response, octave, class_id). */
+typedef struct vslam_keypoint {
+    float x, y;
+    float size;
+    float angle;
+    float response;
+    int32_t octave;
+    int32_t class_id;
+} vslam_keypoint;
+
+/* POD mirror of cv::DMatch (16 bytes). distance holds an integer 0..256 as float. */
+typedef struct vslam_dmatch {
+    int32_t queryIdx;
+    int32_t trainIdx;
+    int32_t imgIdx;
+    float distance;
+} vslam_dmatch;
+
+/* Capacities fixed at context creation; all device memory is owned by the context. */
+typedef struct vslam_config {
+    int32_t device;        /* CUDA device ordinal */
+    int32_t max_images;    /* images per batch (a stereo pair is 2 images) */
+    int32_t max_width;     /* level-0 width  */
+    int32_t max_height;    /* level-0 height */
+    int32_t max_keypoints; /* per image (nfeatures upper bound) */
+    int32_t max_ba_poses;
+    int32_t max_ba_points;
+    int32_t max_ba_obs;
+} vslam_config;
+
+int vslam_abi_version(void);
+const char* vslam_status_string(int status);
+/* last CUDA error text seen by this context (empty string if none) */
+const char* vslam_last_error(const vslam_ctx* ctx);
+
+int vslam_ctx_create(const vslam_config* cfg, vslam_ctx** out);
+void vslam_ctx_destroy(vslam_ctx* ctx);
+/* run on a caller-owned stream (a cudaStream_t, e.g. torch's current stream); NULL = context's own */
+int vslam_ctx_set_stream(vslam_ctx* ctx, void* cuda_stream);
+int vslam_ctx_synchronize(vslam_ctx* ctx);
+/* number of kernels this context has launched since creation (for bench.py's gpu_launches) */
+int64_t vslam_ctx_launch_count(const vslam_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * K10  brute-force Hamming matching + mutual cross-check + distance gate.
+ * Replaces cv::BFMatcher(NORM_HAMMING, crossCheck=true)::match and the gate of VO::feature_matching
+ * (visual_odometry.cpp:24,33 and :219-251).  query = descriptors_1, train = descriptors_2, rows are
+ * 32-byte ORB descriptors.  Output is ordered by ascending queryIdx, imgIdx = 0.
+ *   cross_check != 0 : strict mutual nearest neighbour, first minimum wins ties (cv2 4.13 semantics)
+ *   gate_rel >= 0    : keep distance <= max(gate_rel * min_distance, gate_abs)
+ *                      (reference: gate_rel = 2.0, gate_abs = 30.0 * frame_gap); gate_rel < 0 = no gate
+ * nq == 0 or nt == 0 yields *n_out = 0 (the reference dereferences an empty range there: UB).
+ * nq, nt <= 65535.  `out` must hold min(nq, nt) entries when cross_check, nq otherwise.
+ * ---------------------------------------------------------------------------------------------- */
+int vslam_match_hamming(vslam_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt,
+                        int cross_check, double gate_rel, double gate_abs,
+                        vslam_dmatch* out, int* n_out);
+
+/* Device-resident batched form.  Pair b matches rows d_query + b*q_stride_rows*32 (d_nq[b] rows) against
+ * d_train + b*t_stride_rows*32 (d_nt[b] rows); counts are read on the device (no host sync).  Matches
+ * of pair b are written to d_out + b*out_stride, their number to d_n_out[b]. */
+int vslam_match_hamming_batch_dev(vslam_ctx* ctx, const uint8_t* d_query, const int32_t* d_nq, int q_stride_rows,
+                                  const uint8_t* d_train, const int32_t* d_nt, int t_stride_rows,
+                                  int batch, int max_rows, int cross_check, double gate_rel, double gate_abs,
+                                  vslam_dmatch* d_out, int out_stride, int32_t* d_n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSLAM_B200_H */

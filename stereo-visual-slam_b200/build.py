@@ -1,0 +1,74 @@
+"""In-tree native build of libvslam_b200.so (sm_100a only; nvcc cross-compiles without a GPU).
+
+    python stereo-visual-slam_b200/build.py [--force] [--verbose]
+
+Objects go to stereo-visual-slam_b200/build/, the shared library next to this file so that it travels
+to the GPU box with the repo snapshot.  Static cudart (nvcc default): the library shares the primary
+context -- and therefore streams and device pointers -- with torch in the same process.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libvslam_b200.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+# -fmad=false: the bit-exact float stages (Harris, fastAtan2, rBRIEF rotation, blur tail) must not be
+# contracted; fused operations are written explicitly with fmaf()/fma() where the CPU path fuses.
+CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+NO_FMAD = {"orb.cu"}  # everything else (fp64 BA, triangulation) may contract
+
+
+def _newer(src: str, dst: str, extra=()) -> bool:
+    if not os.path.exists(dst):
+        return True
+    t = os.path.getmtime(dst)
+    return any(os.path.getmtime(p) > t for p in (src, *extra))
+
+
+def build_native(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(BUILD, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
+    headers.append(os.path.join(HERE, "..", "include", "vslam_b200.h"))
+    objs = []
+    procs = []
+    for f in sorted(os.listdir(CSRC)):
+        if not f.endswith(".cu"):
+            continue
+        src = os.path.join(CSRC, f)
+        obj = os.path.join(BUILD, f[:-3] + ".o")
+        objs.append(obj)
+        if force or _newer(src, obj, headers):
+            cmd = [NVCC, *ARCH, *CFLAGS, *(["-fmad=false"] if f in NO_FMAD else []), "-c", src, "-o", obj]
+            if verbose:
+                cmd.insert(1, "-Xptxas")
+                cmd.insert(2, "-v")
+                print(" ".join(cmd))
+            procs.append((f, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for f, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"[build] {f} FAILED\n{out}\n")
+        elif verbose or out.strip():
+            sys.stderr.write(f"[build] {f}\n{out}\n")
+    if failed:
+        raise RuntimeError("nvcc failed")
+    if force or procs or not os.path.exists(LIB):
+        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout)
+            raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_native(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

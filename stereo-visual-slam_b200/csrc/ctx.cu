@@ -1,0 +1,82 @@
+// Context lifetime, status strings and stream plumbing for the C-ABI in include/vslam_b200.h.
+#include "common.cuh"
+
+#include <stdlib.h>
+
+extern "C" int vslam_abi_version(void) { return VSLAM_ABI_VERSION; }
+
+extern "C" const char* vslam_status_string(int status) {
+    switch (status) {
+        case VSLAM_OK: return "ok";
+        case VSLAM_E_INVALID: return "invalid argument";
+        case VSLAM_E_CAPACITY: return "capacity exceeded";
+        case VSLAM_E_CUDA: return "CUDA error";
+        case VSLAM_E_NODEVICE: return "no sm_100-class CUDA device";
+        case VSLAM_E_NUMERIC: return "numeric failure";
+        case VSLAM_E_OVERFLOW: return "device work list overflow";
+        default: return "unknown status";
+    }
+}
+
+extern "C" const char* vslam_last_error(const vslam_ctx* ctx) { return ctx ? ctx->err : ""; }
+
+extern "C" int vslam_ctx_create(const vslam_config* cfg, vslam_ctx** out) {
+    if (!cfg || !out) return VSLAM_E_INVALID;
+    *out = nullptr;
+    if (cfg->max_images < 0 || cfg->max_width < 0 || cfg->max_height < 0 || cfg->max_keypoints < 0 ||
+        cfg->max_keypoints > 65535)
+        return VSLAM_E_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+        cudaGetLastError();
+        return VSLAM_E_NODEVICE;  // no CPU fallback by design
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return VSLAM_E_NODEVICE;
+    if (prop.major != 10) return VSLAM_E_NODEVICE;  // the only code in this library is sm_100a SASS
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return VSLAM_E_NODEVICE;
+
+    vslam_ctx* ctx = (vslam_ctx*)calloc(1, sizeof(vslam_ctx));
+    if (!ctx) return VSLAM_E_INVALID;
+    ctx->cfg = *cfg;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        free(ctx);
+        return VSLAM_E_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    int st = vslam_match_init(ctx);
+    if (st == VSLAM_OK) st = vslam_orb_init(ctx);
+    if (st == VSLAM_OK) st = vslam_ba_init(ctx);
+    if (st != VSLAM_OK) {
+        vslam_ctx_destroy(ctx);
+        return st;
+    }
+    *out = ctx;
+    return VSLAM_OK;
+}
+
+extern "C" void vslam_ctx_destroy(vslam_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStreamSynchronize(ctx->stream);
+    vslam_ba_free(ctx);
+    vslam_orb_free(ctx);
+    vslam_match_free(ctx);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    free(ctx);
+}
+
+extern "C" int vslam_ctx_set_stream(vslam_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return VSLAM_E_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return VSLAM_OK;
+}
+
+extern "C" int vslam_ctx_synchronize(vslam_ctx* ctx) {
+    if (!ctx) return VSLAM_E_INVALID;
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VSLAM_OK;
+}
+
+extern "C" int64_t vslam_ctx_launch_count(const vslam_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -1,0 +1,275 @@
+// K10: brute-force Hamming matching with mutual cross-check and the reference's distance gate.
+//
+// Replaces cv::BFMatcher(NORM_HAMMING, crossCheck=true)::match + the gate loop of VO::feature_matching
+// (/root/reference/src/stereo_visual_slam_main/visual_odometry.cpp:24,33,219-251).
+//
+// Kernel 1 (hamming_argmin): the Nq x Nt distance matrix is computed ONCE, tile by tile, and reduced both
+// ways in the same pass: forward  fw[i] = min_j (D[i][j] << 16 | j)   (per-thread running min, query in registers)
+//                        backward bw[j] = min_i (D[i][j] << 16 | i)   (redux.sync.min across the warp + smem atomicMin)
+// Packing distance above the index makes "first minimum wins ties" a plain unsigned min.
+// Train descriptors are staged into shared memory with cp.async (LDGSTS) 16-byte copies and read back as
+// warp-wide broadcasts; query descriptors live in registers (2 per thread, 128-bit loads).
+// Kernel 2 (crosscheck_gate_compact): one CTA per pair: mutual test, min distance, gate, ordered compaction.
+#include "common.cuh"
+
+#include <cuda_pipeline.h>
+
+#define MT_THREADS 128
+#define MT_QPT 2                        // queries per thread
+#define MT_TILE_Q (MT_THREADS * MT_QPT) // 256 queries per CTA
+#define MT_TILE_T 128                   // trains per CTA
+#define CC_THREADS 1024
+
+struct MatchState {
+    uint32_t* d_keys;  // [pairs][2][max_rows]  fw then bw packed keys
+    uint8_t* d_q;      // staging for the host-buffer entry point
+    uint8_t* d_t;
+    vslam_dmatch* d_out;
+    int32_t* d_cnt;  // nq, nt, n_out
+    int max_pairs;
+    int max_rows;
+    vslam_dmatch* h_out;  // pinned
+    int32_t* h_cnt;       // pinned
+};
+
+__device__ __forceinline__ uint32_t hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+    uint32_t d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z);
+    d += __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x);
+    d += __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z);
+    d += __popc(a1.w ^ b1.w);
+    return d;
+}
+
+__global__ void __launch_bounds__(MT_THREADS)
+hamming_argmin_kernel(const uint8_t* __restrict__ query, const int32_t* __restrict__ d_nq, int q_stride_rows,
+                      const uint8_t* __restrict__ train, const int32_t* __restrict__ d_nt, int t_stride_rows,
+                      uint32_t* __restrict__ keys, int max_rows) {
+    const int pair = blockIdx.z;
+    const int nq = d_nq[pair];
+    const int nt = d_nt[pair];
+    const int q0 = blockIdx.x * MT_TILE_Q;
+    const int t0 = blockIdx.y * MT_TILE_T;
+    if (q0 >= nq || t0 >= nt) return;
+
+    __shared__ uint4 s_t[MT_TILE_T * 2];
+    __shared__ uint32_t s_bw[MT_TILE_T];
+
+    const uint4* tq = reinterpret_cast<const uint4*>(query + (size_t)pair * q_stride_rows * 32);
+    const uint4* tt = reinterpret_cast<const uint4*>(train + (size_t)pair * t_stride_rows * 32);
+    const int tile_n = min(MT_TILE_T, nt - t0);
+
+    // stage the train tile: tile_n*2 16-byte chunks, coalesced, asynchronous
+    for (int c = threadIdx.x; c < tile_n * 2; c += MT_THREADS)
+        __pipeline_memcpy_async(&s_t[c], &tt[(size_t)t0 * 2 + c], 16);
+    __pipeline_commit();
+    for (int j = threadIdx.x; j < MT_TILE_T; j += MT_THREADS) s_bw[j] = 0xFFFFFFFFu;
+
+    // queries of this thread: rows q0 + tid and q0 + tid + MT_THREADS (coalesced 32-byte rows)
+    uint4 qa[MT_QPT][2];
+    int qi[MT_QPT];
+    bool qv[MT_QPT];
+#pragma unroll
+    for (int r = 0; r < MT_QPT; ++r) {
+        qi[r] = q0 + threadIdx.x + r * MT_THREADS;
+        qv[r] = qi[r] < nq;
+        if (qv[r]) {
+            qa[r][0] = __ldg(&tq[(size_t)qi[r] * 2]);
+            qa[r][1] = __ldg(&tq[(size_t)qi[r] * 2 + 1]);
+        } else {
+            qa[r][0] = make_uint4(0, 0, 0, 0);
+            qa[r][1] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    uint32_t best[MT_QPT];
+#pragma unroll
+    for (int r = 0; r < MT_QPT; ++r) best[r] = 0xFFFFFFFFu;
+
+    __pipeline_wait_prior(0);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+#pragma unroll 4
+    for (int j = 0; j < tile_n; ++j) {
+        const uint4 b0 = s_t[2 * j];
+        const uint4 b1 = s_t[2 * j + 1];
+        uint32_t kb = 0xFFFFFFFFu;
+#pragma unroll
+        for (int r = 0; r < MT_QPT; ++r) {
+            const uint32_t d = hamming256(qa[r][0], qa[r][1], b0, b1);
+            const uint32_t kf = (d << 16) | (uint32_t)(t0 + j);
+            best[r] = min(best[r], qv[r] ? kf : 0xFFFFFFFFu);
+            const uint32_t kq = qv[r] ? ((d << 16) | (uint32_t)qi[r]) : 0xFFFFFFFFu;
+            kb = min(kb, kq);
+        }
+        kb = __reduce_min_sync(0xFFFFFFFFu, kb);
+        if (lane == 0) atomicMin(&s_bw[j], kb);
+    }
+    __syncthreads();
+
+    uint32_t* fw = keys + (size_t)pair * 2 * max_rows;
+    uint32_t* bw = fw + max_rows;
+#pragma unroll
+    for (int r = 0; r < MT_QPT; ++r)
+        if (qv[r]) atomicMin(&fw[qi[r]], best[r]);
+    for (int j = threadIdx.x; j < tile_n; j += MT_THREADS) atomicMin(&bw[t0 + j], s_bw[j]);
+}
+
+__global__ void __launch_bounds__(CC_THREADS)
+crosscheck_gate_compact_kernel(const int32_t* __restrict__ d_nq, const int32_t* __restrict__ d_nt,
+                               const uint32_t* __restrict__ keys, int max_rows, int cross_check, double gate_rel,
+                               double gate_abs, vslam_dmatch* __restrict__ out, int out_stride,
+                               int32_t* __restrict__ n_out) {
+    const int pair = blockIdx.x;
+    const int nq = d_nq[pair];
+    const int nt = d_nt[pair];
+    const uint32_t* fw = keys + (size_t)pair * 2 * max_rows;
+    const uint32_t* bw = fw + max_rows;
+    vslam_dmatch* o = out + (size_t)pair * out_stride;
+
+    __shared__ uint32_t s_warp[CC_THREADS / 32];
+    __shared__ uint32_t s_min;
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        s_min = 0xFFFFFFFFu;
+        s_base = 0;
+    }
+    __syncthreads();
+    if (nq <= 0 || nt <= 0) {
+        if (tid == 0) n_out[pair] = 0;
+        return;
+    }
+
+    // phase 1: smallest distance among the (mutual) matches
+    uint32_t dmin = 0xFFFFFFFFu;
+    for (int i = tid; i < nq; i += CC_THREADS) {
+        const uint32_t k = fw[i];
+        const uint32_t j = k & 0xFFFFu;
+        const bool ok = !cross_check || ((bw[j] & 0xFFFFu) == (uint32_t)i);
+        if (ok) dmin = min(dmin, k >> 16);
+    }
+    dmin = __reduce_min_sync(0xFFFFFFFFu, dmin);
+    if (lane == 0) atomicMin(&s_min, dmin);
+    __syncthreads();
+    const uint32_t min_d = s_min;
+    double thr = 1e300;
+    if (gate_rel >= 0.0 && min_d != 0xFFFFFFFFu) thr = fmax(gate_rel * (double)(float)min_d, gate_abs);
+
+    // phase 2: ordered compaction (ascending queryIdx)
+    for (int i0 = 0; i0 < nq; i0 += CC_THREADS) {
+        const int i = i0 + tid;
+        bool keep = false;
+        uint32_t k = 0, j = 0;
+        if (i < nq) {
+            k = fw[i];
+            j = k & 0xFFFFu;
+            keep = !cross_check || ((bw[j] & 0xFFFFu) == (uint32_t)i);
+            keep = keep && ((double)(float)(k >> 16) <= thr);
+        }
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t wsum = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < CC_THREADS / 32; ++w) {
+            const uint32_t c = s_warp[w];
+            wsum += (w < warp) ? c : 0;
+            total += c;
+        }
+        if (keep) {
+            const int pos = s_base + (int)wsum + __popc(bal & ((1u << lane) - 1));
+            vslam_dmatch m;
+            m.queryIdx = i;
+            m.trainIdx = (int)j;
+            m.imgIdx = 0;
+            m.distance = (float)(k >> 16);
+            o[pos] = m;
+        }
+        __syncthreads();
+        if (tid == 0) s_base += (int)total;
+        __syncthreads();
+    }
+    if (tid == 0) n_out[pair] = s_base;
+}
+
+int vslam_match_init(vslam_ctx* ctx) {
+    MatchState* m = (MatchState*)calloc(1, sizeof(MatchState));
+    if (!m) return VSLAM_E_INVALID;
+    ctx->match = m;
+    m->max_pairs = ctx->cfg.max_images > 0 ? ctx->cfg.max_images : 1;
+    m->max_rows = ctx->cfg.max_keypoints > 0 ? ctx->cfg.max_keypoints : 1;
+    const size_t rows = (size_t)m->max_rows;
+    VSLAM_CUDA(ctx, cudaMalloc(&m->d_keys, (size_t)m->max_pairs * 2 * rows * sizeof(uint32_t)));
+    VSLAM_CUDA(ctx, cudaMalloc(&m->d_q, rows * 32));
+    VSLAM_CUDA(ctx, cudaMalloc(&m->d_t, rows * 32));
+    VSLAM_CUDA(ctx, cudaMalloc(&m->d_out, rows * sizeof(vslam_dmatch)));
+    VSLAM_CUDA(ctx, cudaMalloc(&m->d_cnt, 4 * sizeof(int32_t)));
+    VSLAM_CUDA(ctx, cudaMallocHost(&m->h_out, rows * sizeof(vslam_dmatch)));
+    VSLAM_CUDA(ctx, cudaMallocHost(&m->h_cnt, 4 * sizeof(int32_t)));
+    return VSLAM_OK;
+}
+
+void vslam_match_free(vslam_ctx* ctx) {
+    MatchState* m = ctx->match;
+    if (!m) return;
+    cudaFree(m->d_keys);
+    cudaFree(m->d_q);
+    cudaFree(m->d_t);
+    cudaFree(m->d_out);
+    cudaFree(m->d_cnt);
+    cudaFreeHost(m->h_out);
+    cudaFreeHost(m->h_cnt);
+    free(m);
+    ctx->match = nullptr;
+}
+
+extern "C" int vslam_match_hamming_batch_dev(vslam_ctx* ctx, const uint8_t* d_query, const int32_t* d_nq,
+                                             int q_stride_rows, const uint8_t* d_train, const int32_t* d_nt,
+                                             int t_stride_rows, int batch, int max_rows, int cross_check,
+                                             double gate_rel, double gate_abs, vslam_dmatch* d_out, int out_stride,
+                                             int32_t* d_n_out) {
+    if (!ctx || !d_query || !d_train || !d_nq || !d_nt || !d_out || !d_n_out) return VSLAM_E_INVALID;
+    if (batch <= 0 || max_rows <= 0) return VSLAM_E_INVALID;
+    MatchState* m = ctx->match;
+    if (batch > m->max_pairs || max_rows > m->max_rows || max_rows > 65535) return VSLAM_E_CAPACITY;
+    if (((uintptr_t)d_query | (uintptr_t)d_train) & 15) return VSLAM_E_INVALID;
+    VSLAM_CUDA(ctx, cudaMemsetAsync(m->d_keys, 0xFF, (size_t)batch * 2 * m->max_rows * sizeof(uint32_t), ctx->stream));
+    dim3 grid(ceil_div(max_rows, MT_TILE_Q), ceil_div(max_rows, MT_TILE_T), batch);
+    hamming_argmin_kernel<<<grid, MT_THREADS, 0, ctx->stream>>>(d_query, d_nq, q_stride_rows, d_train, d_nt,
+                                                                t_stride_rows, m->d_keys, m->max_rows);
+    VSLAM_LAUNCH_CHECK(ctx, "hamming_argmin_kernel");
+    crosscheck_gate_compact_kernel<<<batch, CC_THREADS, 0, ctx->stream>>>(
+        d_nq, d_nt, m->d_keys, m->max_rows, cross_check, gate_rel, gate_abs, d_out, out_stride, d_n_out);
+    VSLAM_LAUNCH_CHECK(ctx, "crosscheck_gate_compact_kernel");
+    return VSLAM_OK;
+}
+
+extern "C" int vslam_match_hamming(vslam_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt,
+                                   int cross_check, double gate_rel, double gate_abs, vslam_dmatch* out,
+                                   int* n_out) {
+    if (!ctx || !n_out || nq < 0 || nt < 0) return VSLAM_E_INVALID;
+    *n_out = 0;
+    if (nq == 0 || nt == 0) return VSLAM_OK;
+    if (!query || !train || !out) return VSLAM_E_INVALID;
+    MatchState* m = ctx->match;
+    if (nq > m->max_rows || nt > m->max_rows) return VSLAM_E_CAPACITY;
+    cudaStream_t s = ctx->stream;
+    m->h_cnt[0] = nq;
+    m->h_cnt[1] = nt;
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(m->d_cnt, m->h_cnt, 2 * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(m->d_q, query, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(m->d_t, train, (size_t)nt * 32, cudaMemcpyHostToDevice, s));
+    int st = vslam_match_hamming_batch_dev(ctx, m->d_q, m->d_cnt, m->max_rows, m->d_t, m->d_cnt + 1, m->max_rows, 1,
+                                           nq > nt ? nq : nt, cross_check, gate_rel, gate_abs, m->d_out, m->max_rows,
+                                           m->d_cnt + 2);
+    if (st != VSLAM_OK) return st;
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(m->h_cnt + 2, m->d_cnt + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(s));
+    const int n = m->h_cnt[2];
+    if (n > 0) {
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(out, m->d_out, (size_t)n * sizeof(vslam_dmatch), cudaMemcpyDeviceToHost, s));
+        VSLAM_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    *n_out = n;
+    return VSLAM_OK;
+}

@@ -1,0 +1,142 @@
+"""ctypes binding of include/vslam_b200.h -- the only way Python reaches the CUDA path.
+
+There is no fallback: if libvslam_b200.so is missing or no B200 is visible, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvslam_b200.so")
+
+VSLAM_OK = 0
+STATUS = {0: "VSLAM_OK", -1: "VSLAM_E_INVALID", -2: "VSLAM_E_CAPACITY", -3: "VSLAM_E_CUDA",
+          -4: "VSLAM_E_NODEVICE", -5: "VSLAM_E_NUMERIC", -6: "VSLAM_E_OVERFLOW"}
+
+
+class VslamError(RuntimeError):
+    def __init__(self, status: int, where: str, detail: str = ""):
+        self.status = status
+        super().__init__(f"{where}: {STATUS.get(status, status)} {detail}".strip())
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_images", C.c_int32), ("max_width", C.c_int32),
+                ("max_height", C.c_int32), ("max_keypoints", C.c_int32), ("max_ba_poses", C.c_int32),
+                ("max_ba_points", C.c_int32), ("max_ba_obs", C.c_int32)]
+
+
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                           ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+assert KEYPOINT_DTYPE.itemsize == 28 and DMATCH_DTYPE.itemsize == 16
+
+_lib = None
+
+_vp, _i, _d, _f, _i64 = C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_int64
+_pi = C.POINTER(C.c_int)
+
+# name -> (restype, argtypes); must list every symbol include/vslam_b200.h declares
+SIGNATURES = {
+    "vslam_abi_version": (_i, []),
+    "vslam_status_string": (C.c_char_p, [_i]),
+    "vslam_last_error": (C.c_char_p, [_vp]),
+    "vslam_ctx_create": (_i, [C.POINTER(Config), C.POINTER(_vp)]),
+    "vslam_ctx_destroy": (None, [_vp]),
+    "vslam_ctx_set_stream": (_i, [_vp, _vp]),
+    "vslam_ctx_synchronize": (_i, [_vp]),
+    "vslam_ctx_launch_count": (_i64, [_vp]),
+    "vslam_match_hamming": (_i, [_vp, _vp, _i, _vp, _i, _i, _d, _d, _vp, _pi]),
+    "vslam_match_hamming_batch_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _d, _d, _vp, _i, _vp]),
+}
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _ptr(a):
+    """host numpy array, torch CUDA tensor, or int -> void*"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(a.data_ptr())  # torch tensor
+
+
+class Context:
+    """Owns a vslam_ctx (device memory, stream).  Mirrors the role of the reference's VO object's
+    cv::Ptr<ORB>/cv::Ptr<BFMatcher> members (visual_odometry.cpp:20-35): created once, reused per frame."""
+
+    def __init__(self, device: int = 0, max_images: int = 2, max_width: int = 1241, max_height: int = 376,
+                 max_keypoints: int = 4096, max_ba_poses: int = 64, max_ba_points: int = 32768,
+                 max_ba_obs: int = 262144):
+        self.lib = load_library()
+        self.cfg = Config(device, max_images, max_width, max_height, max_keypoints, max_ba_poses,
+                          max_ba_points, max_ba_obs)
+        h = C.c_void_p()
+        st = self.lib.vslam_ctx_create(C.byref(self.cfg), C.byref(h))
+        if st != VSLAM_OK:
+            raise VslamError(st, "vslam_ctx_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vslam_ctx_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def check(self, st: int, where: str):
+        if st != VSLAM_OK:
+            raise VslamError(st, where, self.lib.vslam_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream_handle: int | None):
+        self.check(self.lib.vslam_ctx_set_stream(self.h, C.c_void_p(cuda_stream_handle or 0)), "set_stream")
+
+    def synchronize(self):
+        self.check(self.lib.vslam_ctx_synchronize(self.h), "synchronize")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.vslam_ctx_launch_count(self.h))
+
+    # ---- K10 --------------------------------------------------------------------------------
+    def match_hamming(self, query: np.ndarray, train: np.ndarray, cross_check: bool = True,
+                      gate_rel: float = -1.0, gate_abs: float = 0.0) -> np.ndarray:
+        """cv::BFMatcher(NORM_HAMMING, crossCheck)::match + optional VO::feature_matching gate.
+        Returns a DMATCH_DTYPE array ordered by queryIdx."""
+        q = np.ascontiguousarray(query, dtype=np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(train, dtype=np.uint8).reshape(-1, 32)
+        out = np.zeros(max(len(q), 1), dtype=DMATCH_DTYPE)
+        n = C.c_int(0)
+        st = self.lib.vslam_match_hamming(self.h, _ptr(q), len(q), _ptr(t), len(t), int(cross_check),
+                                          float(gate_rel), float(gate_abs), _ptr(out), C.byref(n))
+        self.check(st, "vslam_match_hamming")
+        return out[:n.value].copy()
+
+    def match_hamming_batch_dev(self, d_query, d_nq, q_stride_rows, d_train, d_nt, t_stride_rows, batch, max_rows,
+                                cross_check, gate_rel, gate_abs, d_out, out_stride, d_n_out):
+        st = self.lib.vslam_match_hamming_batch_dev(self.h, _ptr(d_query), _ptr(d_nq), q_stride_rows, _ptr(d_train),
+                                                    _ptr(d_nt), t_stride_rows, batch, max_rows, int(cross_check),
+                                                    float(gate_rel), float(gate_abs), _ptr(d_out), out_stride,
+                                                    _ptr(d_n_out))
+        self.check(st, "vslam_match_hamming_batch_dev")
