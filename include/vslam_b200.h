@@ -105,6 +105,40 @@ int vslam_match_hamming_batch_dev(vslam_ctx* ctx, const uint8_t* d_query, const 
                                   int batch, int max_rows, int cross_check, double gate_rel, double gate_abs,
                                   vslam_dmatch* d_out, int out_stride, int32_t* d_n_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * K1-K9  ORB feature detection: pyramid + FAST-9 + NMS + Harris ranking + ANMS + orientation + rBRIEF.
+ * Replaces detector_->detect / adaptive_non_maximal_suppresion / descriptor_->compute inside
+ * VO::feature_detection (visual_odometry.cpp:70-94; ORB::create(3000) at :22,:31; ANMS :96-157).
+ * Bit-exact against cv2 4.13.0 cv::ORB (8 levels, scale 1.2, edge 31, HARRIS_SCORE, patch 31, FAST 20).
+ *   nfeatures  : cv::ORB nfeatures (reference: 3000)
+ *   anms_keep  : ANMS target (reference: 500); <= 0 disables ANMS.  As in the reference, ANMS is a
+ *                no-op when fewer than anms_keep keypoints were detected, and keeps radius ties.
+ *   anms_c     : robustness coefficient (reference: 1.11f)
+ * Output order is canonical: octave ascending, response descending, then y, x (what cv::ORB::compute's
+ * stable by-octave regrouping yields from the response-sorted ANMS list).  Because cv::ORB keeps
+ * response ties, up to a few more than nfeatures keypoints can be returned; image i's keypoints
+ * start at kp_out + i*cap and desc_out + i*cap*32 where cap = vslam_orb_keypoint_capacity(ctx).
+ * Returns VSLAM_E_INVALID for a null image (the reference's -1, visual_odometry.cpp:73-77).
+ * ---------------------------------------------------------------------------------------------- */
+int vslam_orb_keypoint_capacity(const vslam_ctx* ctx);
+int vslam_orb_detect_compute(vslam_ctx* ctx, const uint8_t* image, int width, int height, int row_pitch,
+                             int nfeatures, int anms_keep, float anms_c,
+                             vslam_keypoint* kp_out, uint8_t* desc_out, int32_t* n_out);
+int vslam_orb_detect_compute_batch(vslam_ctx* ctx, const uint8_t* images, int n_images, int width, int height,
+                                   int row_pitch, long long image_stride, int nfeatures, int anms_keep,
+                                   float anms_c, vslam_keypoint* kp_out, uint8_t* desc_out, int32_t* n_out);
+/* device-resident form: images, outputs and counts stay in HBM; asynchronous on the context stream */
+int vslam_orb_detect_compute_batch_dev(vslam_ctx* ctx, const uint8_t* d_images, int n_images, int width,
+                                       int height, int row_pitch, long long image_stride, int nfeatures,
+                                       int anms_keep, float anms_c, vslam_keypoint* d_kp, uint8_t* d_desc,
+                                       int32_t* d_n);
+/* synchronise and report VSLAM_E_OVERFLOW if any of the last n_images raised a work-list overflow */
+int vslam_orb_last_flags(vslam_ctx* ctx, int n_images);
+/* test tap: intermediate state of image `img` after the last ORB call (any output pointer may be NULL).
+ * cand_xy_score receives pairs {x | y << 16, FAST score} in arbitrary order. */
+int vslam_orb_debug_read(vslam_ctx* ctx, int img, int level, uint8_t* level_pixels, uint8_t* blurred_pixels,
+                         int* w_out, int* h_out, uint32_t* cand_xy_score, int cand_cap, int* n_cand);
+
 #ifdef __cplusplus
 }
 #endif

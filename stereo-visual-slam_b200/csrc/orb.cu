@@ -1,4 +1,1056 @@
-// placeholder until the ORB kernels land
+// K1-K9: bit-exact ORB (oriented FAST + rotated BRIEF) on the GPU, batched over images.
+//
+// Replaces the arithmetic behind VO::feature_detection
+// (/root/reference/src/stereo_visual_slam_main/visual_odometry.cpp:70-94): detector_->detect (:80, ORB with
+// nfeatures = 3000, :22/:31), adaptive_non_maximal_suppresion (:82, :96-157) and descriptor_->compute (:85).
+// The arithmetic itself lives in OpenCV (cv::ORB, un-vendored); the bit-exact specification followed here is
+// SURVEY.md §A.1 as re-validated by oracle/orb_restate.py against cv2 4.13.0.
+//
+// Pipeline (every kernel covers ALL images of the batch; nothing returns to the host in between):
+//   resize_level_kernel x7   K1  INTER_LINEAR_EXACT chain, 8.8 fixed point, coefficient tables from the host
+//   fast_kernel              K2  FAST-9/16 (t=20) score + 3x3 NMS + 31-px border filter, tile = 64x32 in smem,
+//                                candidate list + per-(image,level) 256-bin score histogram
+//   harris_select_kernel     K3-K5 one CTA per (level,image): histogram cut (retainBest 2N, ties kept), Harris
+//                                response (7x7, no FMA), bitonic sort by (response desc, y, x), retainBest N
+//   blur_kernel              K8  7x7 sigma-2 float32 separable blur with cv2's exact fused/unfused op order
+//   anms_kernel (optional)   K7  the reference's own ANMS
+//   describe_kernel          K6+K9 one warp per keypoint: intensity-centroid angle, fastAtan2, 256 rBRIEF tests
+// This file is compiled with -fmad=false; fused operations are explicit fmaf() where cv2's AVX2 path fuses.
 #include "common.cuh"
-int vslam_orb_init(vslam_ctx* ctx) { (void)ctx; return VSLAM_OK; }
-void vslam_orb_free(vslam_ctx* ctx) { (void)ctx; }
+
+#include <math.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#define ORB_NL VSLAM_NLEVELS
+#define ORB_EDGE 31
+#define FAST_T 20
+#define TILE_W 64
+#define TILE_H 32
+#define FAST_THREADS 256
+#define SORT_CAP 8192
+#define HS_THREADS 1024
+#define DESC_WARPS 8
+
+struct OrbLevel {
+    int w, h, pitch;
+    int off;  // byte offset of the plane inside one image's slab (pyramid and blurred pyramid share the layout)
+    int tiles_x, tiles_y, tile_begin;
+    int cand_off, cand_cap;  // candidate-list region (entries) inside one image's candidate slab
+    int xtab_off, ytab_off;  // resize coefficient tables (entries)
+    float scale, inv_scale;
+};
+
+struct OrbGeom {
+    OrbLevel lv[ORB_NL];
+    int total_tiles;
+    int img_slab;   // bytes per image in the pyramid / blurred slabs
+    int cand_slab;  // candidate entries per image
+    int w, h;
+};
+
+struct OrbQuota {
+    int n[ORB_NL];
+};
+
+// Level 0 is read in place from the caller's buffers (left images first, then right images).
+struct ImgSrc {
+    const uint8_t* base[2];
+    long long img_stride;  // bytes between consecutive images of one base
+    int pitch;             // bytes between rows
+    int per_base;          // images per base pointer
+};
+
+struct ImgCounters {
+    uint32_t hist[ORB_NL][256];
+    uint32_t cand_cnt[ORB_NL];
+    uint32_t sel_cnt[ORB_NL];
+    uint32_t n_keep;  // ANMS output count
+    uint32_t flags;   // bit0: candidate list overflow, bit1: sort overflow, bit2: keypoint capacity overflow
+    uint32_t pad[2];
+};
+
+struct OrbState {
+    OrbGeom geom;
+    bool geom_valid;
+    uint8_t* d_pyr;
+    uint8_t* d_blur;
+    uint32_t* d_tab;      // resize tables
+    uint2* d_cand;        // {x | y << 16, score}
+    uint2* d_sel;         // [img][level][SORT_CAP] {x | y << 16, response bits}
+    ImgCounters* d_cnt;
+    uint32_t* d_keep;     // ANMS keep list [img][kp_cap]
+    double* d_rad;        // ANMS radii [img][kp_cap]
+    int8_t* d_pattern;    // 256 x 4
+    // staging for the host-buffer entry point
+    uint8_t* d_in;
+    int in_pitch;
+    vslam_keypoint* d_kp;
+    uint8_t* d_desc;
+    int32_t* d_n;
+    vslam_keypoint* h_kp;
+    uint8_t* h_desc;
+    int32_t* h_n;
+    ImgCounters* h_cnt;
+    int max_images, kp_cap;
+    size_t slab_cap, cand_cap_total;
+    int tab_cap;
+};
+
+static const int8_t h_orb_pattern[256 * 4] = {
+#include "orb_pattern.inc"
+};
+
+// float(pow(double(1.2f), l)), l = 0..7 (cv::ORB getScale; verified against oracle/orb_restate.level_scales)
+static const float h_scales[ORB_NL] = {0x1.0p+0f,        0x1.333334p+0f, 0x1.70a3d8p+0f, 0x1.ba5e38p+0f,
+                                       0x1.096bbcp+1f, 0x1.3e814ap+1f, 0x1.7e34c0p+1f, 0x1.caa5b4p+1f};
+
+__device__ __forceinline__ const uint8_t* level_ptr(const ImgSrc& src, const uint8_t* slab, const OrbGeom& g, int img,
+                                                    int l, int& pitch) {
+    if (l == 0) {
+        pitch = src.pitch;
+        const bool second = img >= src.per_base;
+        return (second ? src.base[1] : src.base[0]) + (long long)(second ? img - src.per_base : img) * src.img_stride;
+    }
+    pitch = g.lv[l].pitch;
+    return slab + (size_t)img * g.img_slab + g.lv[l].off;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1  resize INTER_LINEAR_EXACT: out = (c0y*(c0x*s00 + c1x*s01) + c1y*(c0x*s10 + c1x*s11) + 32768) >> 16
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+resize_level_kernel(ImgSrc src, uint8_t* __restrict__ pyr, const uint32_t* __restrict__ tab, const __grid_constant__ OrbGeom g, int l) {
+    const int img = blockIdx.z;
+    const OrbLevel& L = g.lv[l];
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= L.w || y >= L.h) return;
+    int sp;
+    const uint8_t* s = level_ptr(src, pyr, g, img, l - 1, sp);
+    const int sw = g.lv[l - 1].w, sh = g.lv[l - 1].h;
+    const uint32_t tx = __ldg(&tab[L.xtab_off + x]);
+    const uint32_t ty = __ldg(&tab[L.ytab_off + y]);
+    const int ox = tx >> 16, c1x = tx & 0xFFFF, c0x = 256 - c1x;
+    const int oy = ty >> 16, c1y = ty & 0xFFFF, c0y = 256 - c1y;
+    const int ox1 = min(ox + 1, sw - 1), oy1 = min(oy + 1, sh - 1);
+    const uint8_t* r0 = s + (size_t)oy * sp;
+    const uint8_t* r1 = s + (size_t)oy1 * sp;
+    const int h0 = c0x * (int)r0[ox] + c1x * (int)r0[ox1];
+    const int h1 = c0x * (int)r1[ox] + c1x * (int)r1[ox1];
+    const int v = (c0y * h0 + c1y * h1 + 32768) >> 16;
+    pyr[(size_t)img * g.img_slab + L.off + (size_t)y * L.pitch + x] = (uint8_t)v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2  FAST-9/16 + NMS + border filter
+// ------------------------------------------------------------------------------------------------------------
+#define SI_W (TILE_W + 8)
+#define SI_H (TILE_H + 8)
+#define SS_W (TILE_W + 2)
+#define SS_H (TILE_H + 2)
+#define FAST_OUT_CAP 640
+
+__device__ __forceinline__ bool has_arc9(uint32_t m16) {
+    uint32_t x = m16 | (m16 << 16);
+    uint32_t a = x & (x >> 1);
+    a &= a >> 2;
+    a &= a >> 4;
+    a &= x >> 8;
+    return (a & 0xFFFFu) != 0;
+}
+
+__global__ void __launch_bounds__(FAST_THREADS)
+fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g, uint2* __restrict__ cand,
+            ImgCounters* __restrict__ cnt) {
+    __shared__ uint8_t s_img[SI_H * SI_W];
+    __shared__ uint8_t s_score[SS_H * SS_W];
+    __shared__ uint16_t s_list[SS_H * SS_W];
+    __shared__ uint2 s_out[FAST_OUT_CAP];
+    __shared__ uint32_t s_hist[256];
+    __shared__ int s_n1, s_nout, s_base;
+
+    const int img = blockIdx.y;
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < ORB_NL; ++i)
+        if ((int)blockIdx.x >= g.lv[i].tile_begin) l = i;
+    const OrbLevel& L = g.lv[l];
+    const int t = blockIdx.x - L.tile_begin;
+    const int tx0 = (t % L.tiles_x) * TILE_W, ty0 = (t / L.tiles_x) * TILE_H;
+    int pitch;
+    const uint8_t* im = level_ptr(src, pyr, g, img, l, pitch);
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < SI_H * SI_W; i += FAST_THREADS) {
+        const int r = i / SI_W, c = i - r * SI_W;
+        const int gy = ty0 - 4 + r, gx = tx0 - 4 + c;
+        uint8_t v = 0;
+        if (gx >= 0 && gx < L.w && gy >= 0 && gy < L.h) v = im[(size_t)gy * pitch + gx];
+        s_img[i] = v;
+    }
+    for (int i = tid; i < SS_H * SS_W; i += FAST_THREADS) s_score[i] = 0;
+    s_hist[tid] = 0;  // FAST_THREADS == 256
+    if (tid == 0) {
+        s_n1 = 0;
+        s_nout = 0;
+    }
+    __syncthreads();
+
+    // phase 1: compass pre-test (any 9-arc contains two adjacent compass pixels)
+    for (int i = tid; i < SS_H * SS_W; i += FAST_THREADS) {
+        const int sy = i / SS_W, sx = i - sy * SS_W;
+        const int gy = ty0 - 1 + sy, gx = tx0 - 1 + sx;
+        if (gx < 3 || gx >= L.w - 3 || gy < 3 || gy >= L.h - 3) continue;
+        const uint8_t* c = &s_img[(sy + 3) * SI_W + sx + 3];
+        const int v = c[0];
+        const int hi = v + FAST_T, lo = v - FAST_T;
+        const int p0 = c[3 * SI_W], p4 = c[3], p8 = c[-3 * SI_W], p12 = c[-3];
+        const uint32_t d = (p0 > hi) | ((p4 > hi) << 1) | ((p8 > hi) << 2) | ((p12 > hi) << 3);
+        const uint32_t b = (p0 < lo) | ((p4 < lo) << 1) | ((p8 < lo) << 2) | ((p12 < lo) << 3);
+        const uint32_t dd = d & ((d >> 1) | (d << 3));
+        const uint32_t bb = b & ((b >> 1) | (b << 3));
+        if ((dd | bb) & 0xF) s_list[atomicAdd(&s_n1, 1)] = (uint16_t)i;
+    }
+    __syncthreads();
+
+    // phase 2: full segment test and corner score on the survivors
+    const int n1 = s_n1;
+    for (int e = tid; e < n1; e += FAST_THREADS) {
+        const int i = s_list[e];
+        const int sy = i / SS_W, sx = i - sy * SS_W;
+        const uint8_t* c = &s_img[(sy + 3) * SI_W + sx + 3];
+        const int v = c[0];
+        int d[16];
+        d[0] = v - c[3 * SI_W];
+        d[1] = v - c[3 * SI_W + 1];
+        d[2] = v - c[2 * SI_W + 2];
+        d[3] = v - c[1 * SI_W + 3];
+        d[4] = v - c[3];
+        d[5] = v - c[-1 * SI_W + 3];
+        d[6] = v - c[-2 * SI_W + 2];
+        d[7] = v - c[-3 * SI_W + 1];
+        d[8] = v - c[-3 * SI_W];
+        d[9] = v - c[-3 * SI_W - 1];
+        d[10] = v - c[-2 * SI_W - 2];
+        d[11] = v - c[-1 * SI_W - 3];
+        d[12] = v - c[-3];
+        d[13] = v - c[1 * SI_W - 3];
+        d[14] = v - c[2 * SI_W - 2];
+        d[15] = v - c[3 * SI_W - 1];
+        uint32_t mb = 0, md = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            mb |= (uint32_t)(d[k] > FAST_T) << k;
+            md |= (uint32_t)(d[k] < -FAST_T) << k;
+        }
+        if (!(has_arc9(mb) || has_arc9(md))) continue;
+        // best = max over the 16 arcs of max(min(d), -max(d)); sliding min/max by doubling
+        int mn[16], mx[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            mn[k] = min(d[k], d[(k + 1) & 15]);
+            mx[k] = max(d[k], d[(k + 1) & 15]);
+        }
+        int mn2[16], mx2[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            mn2[k] = min(mn[k], mn[(k + 2) & 15]);
+            mx2[k] = max(mx[k], mx[(k + 2) & 15]);
+        }
+        // max_k max(a_k, -b_k) == max(max_k a_k, -min_k b_k).  The negation is kept OUT of the min/max chain on
+        // purpose: ptxas 12.9 -O3 for sm_100a miscompiles max(x, -y) when it folds the negation into
+        // VIMNMX3/VIADDMNMX (reproduced standalone: tools/scratch/t_fast2.cu gives 51 instead of 22).
+        int besta = -1000, bmin = 1000;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int a = min(min(mn2[k], mn2[(k + 4) & 15]), d[(k + 8) & 15]);
+            const int b = max(max(mx2[k], mx2[(k + 4) & 15]), d[(k + 8) & 15]);
+            besta = max(besta, a);
+            bmin = min(bmin, b);
+        }
+        int nb = 0 - bmin;
+        asm volatile("" : "+r"(nb));
+        const int best = max(besta, nb);
+        s_score[i] = (uint8_t)(best - 1);  // best > 20 here, <= 255
+    }
+    __syncthreads();
+
+    // phase 3: 3x3 NMS (strictly greater), border filter, emit
+    for (int i = tid; i < TILE_W * TILE_H; i += FAST_THREADS) {
+        const int sy = i / TILE_W + 1, sx = i % TILE_W + 1;
+        const uint8_t* sc = &s_score[sy * SS_W + sx];
+        const int s = sc[0];
+        if (s == 0) continue;
+        if (sc[-1] >= s || sc[1] >= s || sc[-SS_W - 1] >= s || sc[-SS_W] >= s || sc[-SS_W + 1] >= s ||
+            sc[SS_W - 1] >= s || sc[SS_W] >= s || sc[SS_W + 1] >= s)
+            continue;
+        const int gy = ty0 - 1 + sy, gx = tx0 - 1 + sx;
+        if (gx < ORB_EDGE || gx >= L.w - ORB_EDGE || gy < ORB_EDGE || gy >= L.h - ORB_EDGE) continue;
+        const int pos = atomicAdd(&s_nout, 1);
+        if (pos < FAST_OUT_CAP) s_out[pos] = make_uint2((uint32_t)gx | ((uint32_t)gy << 16), (uint32_t)s);
+        atomicAdd(&s_hist[s], 1u);
+    }
+    __syncthreads();
+    const int nout = min(s_nout, FAST_OUT_CAP);  // a 64x32 tile holds at most 512 strict 3x3 maxima
+    if (nout == 0) return;
+    ImgCounters* C = &cnt[img];
+    if (tid == 0) s_base = (int)atomicAdd(&C->cand_cnt[l], (uint32_t)nout);
+    __syncthreads();
+    const int base = s_base;
+    uint2* dst = cand + (size_t)img * g.cand_slab + L.cand_off;
+    for (int i = tid; i < nout; i += FAST_THREADS) {
+        if (base + i < L.cand_cap) dst[base + i] = s_out[i];
+    }
+    if (tid == 0 && base + nout > L.cand_cap) atomicOr(&C->flags, 1u);
+    if (s_hist[tid]) atomicAdd(&C->hist[l][tid], s_hist[tid]);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3-K5  per (level, image): histogram cut, Harris, sort, retainBest
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_desc_key(float f) {
+    uint32_t b = __float_as_uint(f);
+    b ^= (b >> 31) ? 0xFFFFFFFFu : 0x80000000u;  // monotone increasing
+    return ~b;                                    // ascending key == descending response
+}
+
+__global__ void __launch_bounds__(HS_THREADS)
+harris_select_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g, const __grid_constant__ OrbQuota quota,
+                     const uint2* __restrict__ cand, ImgCounters* __restrict__ cnt, uint2* __restrict__ sel) {
+    extern __shared__ unsigned long long s_key[];  // SORT_CAP
+    __shared__ uint32_t s_h[256];
+    __shared__ uint8_t s_patch[HS_THREADS / 32][96];
+    __shared__ int s_cut, s_n, s_kept;
+
+    const int l = blockIdx.x, img = blockIdx.y;
+    const OrbLevel& L = g.lv[l];
+    ImgCounters* C = &cnt[img];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = quota.n[l];
+    const int nc = min((int)C->cand_cnt[l], L.cand_cap);
+    if (tid < 256) s_h[tid] = C->hist[l][tid];
+    if (tid == 0) {
+        s_cut = 0;
+        s_n = 0;
+        s_kept = 0;
+    }
+    __syncthreads();
+    if (N <= 0 || nc == 0) {
+        if (tid == 0) C->sel_cnt[l] = 0;
+        return;
+    }
+    // retainBest(2N) on integer FAST scores: cut = value of the 2N-th largest (ties kept)
+    if (tid < 256) {
+        uint32_t ge = 0;
+        for (int v = tid; v < 256; ++v) ge += s_h[v];
+        if (ge >= (uint32_t)(2 * N)) atomicMax(&s_cut, tid);
+    }
+    __syncthreads();
+    const uint32_t cut = (uint32_t)s_cut;
+    const uint2* cl = cand + (size_t)img * g.cand_slab + L.cand_off;
+    for (int i = tid; i < nc; i += HS_THREADS) {
+        const uint2 c = cl[i];
+        if (c.y >= cut) {
+            const int pos = atomicAdd(&s_n, 1);
+            if (pos < SORT_CAP) s_key[pos] = c.x;
+        }
+    }
+    __syncthreads();
+    int n = s_n;
+    if (n > SORT_CAP) {
+        if (tid == 0) atomicOr(&C->flags, 2u);
+        n = SORT_CAP;
+    }
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+
+    // Harris response, one warp per candidate (orb.cpp HarrisResponses: blockSize 7, k = 0.04)
+    int pitch;
+    const uint8_t* im = level_ptr(src, pyr, g, img, l, pitch);
+    for (int e = warp; e < n; e += HS_THREADS / 32) {
+        const uint32_t xy = (uint32_t)s_key[e];
+        const int x = xy & 0xFFFF, y = xy >> 16;
+        uint8_t* P = s_patch[warp];
+        for (int i = lane; i < 81; i += 32) {
+            const int r = i / 9, c = i - r * 9;
+            P[i] = im[(size_t)(y - 4 + r) * pitch + (x - 4 + c)];
+        }
+        __syncwarp();
+        int a = 0, b = 0, c = 0;
+        for (int i = lane; i < 49; i += 32) {
+            const int r = i / 7, q = i - r * 7;
+            const uint8_t* p = &P[(r + 1) * 9 + q + 1];
+            const int ix = ((int)p[1] - (int)p[-1]) * 2 + ((int)p[-9 + 1] - (int)p[-9 - 1]) + ((int)p[9 + 1] - (int)p[9 - 1]);
+            const int iy = ((int)p[9] - (int)p[-9]) * 2 + ((int)p[9 - 1] - (int)p[-9 - 1]) + ((int)p[9 + 1] - (int)p[-9 + 1]);
+            a += ix * ix;
+            b += iy * iy;
+            c += ix * iy;
+        }
+        a = __reduce_add_sync(0xFFFFFFFFu, a);
+        b = __reduce_add_sync(0xFFFFFFFFu, b);
+        c = __reduce_add_sync(0xFFFFFFFFu, c);
+        if (lane == 0) {
+            const float af = (float)a, bf = (float)b, cf = (float)c;
+            const float s4 = 0x1.bb9da2p-52f;  // ((s*s)*s)*s, s = 1.f/(4*7*255.f)
+            const float kk = 0x1.47ae14p-5f;   // 0.04f
+            const float t1 = __fmul_rn(af, bf);
+            const float t2 = __fmul_rn(cf, cf);
+            const float sm = __fadd_rn(af, bf);
+            const float t4 = __fmul_rn(__fmul_rn(kk, sm), sm);
+            const float resp = __fmul_rn(__fsub_rn(__fsub_rn(t1, t2), t4), s4);
+            s_key[e] = ((unsigned long long)float_desc_key(resp) << 32) | xy;
+        }
+        __syncwarp();
+    }
+    for (int i = n + tid; i < n2; i += HS_THREADS) s_key[i] = 0xFFFFFFFFFFFFFFFFull;
+    __syncthreads();
+
+    // bitonic sort ascending
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n2; i += HS_THREADS) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const unsigned long long A = s_key[i], B = s_key[p];
+                    const bool up = (i & k) == 0;
+                    if ((A > B) == up) {
+                        s_key[i] = B;
+                        s_key[p] = A;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // retainBest(N) on the Harris response, ties with the N-th kept
+    if (n > N) {
+        const uint32_t cut_hi = (uint32_t)(s_key[N - 1] >> 32);
+        for (int i = tid; i < n; i += HS_THREADS) {
+            const bool in = (uint32_t)(s_key[i] >> 32) <= cut_hi;
+            const bool nxt = (i + 1 < n) ? ((uint32_t)(s_key[i + 1] >> 32) <= cut_hi) : false;
+            if (in && !nxt) s_kept = i + 1;
+        }
+    } else if (tid == 0) {
+        s_kept = n;
+    }
+    __syncthreads();
+    const int kept = s_kept;
+    uint2* so = sel + ((size_t)img * ORB_NL + l) * SORT_CAP;
+    for (int i = tid; i < kept; i += HS_THREADS) {
+        const unsigned long long K = s_key[i];
+        uint32_t b = ~(uint32_t)(K >> 32);
+        b ^= (b >> 31) ? 0x80000000u : 0xFFFFFFFFu;  // inverse of the monotone map
+        so[i] = make_uint2((uint32_t)K, b);
+    }
+    if (tid == 0) C->sel_cnt[l] = (uint32_t)kept;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K8  descriptor blur (see oracle/orb_restate.blur7 for how the op order was pinned against cv2)
+// ------------------------------------------------------------------------------------------------------------
+#define BI_W (TILE_W + 6)
+#define BI_H (TILE_H + 6)
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+    if (p < 0) p = -p;
+    if (p >= n) p = 2 * n - 2 - p;
+    return p;
+}
+
+__global__ void __launch_bounds__(256)
+blur_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, const __grid_constant__ OrbGeom g) {
+    __shared__ uint8_t s_in[BI_H * BI_W];
+    __shared__ float s_row[BI_H * TILE_W];
+    const float k0 = 0x1.1f5f62p-4f, k1 = 0x1.0c70fcp-3f, k2 = 0x1.869472p-3f, k3 = 0x1.ba95c0p-3f;
+
+    const int img = blockIdx.y;
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < ORB_NL; ++i)
+        if ((int)blockIdx.x >= g.lv[i].tile_begin) l = i;
+    const OrbLevel& L = g.lv[l];
+    const int t = blockIdx.x - L.tile_begin;
+    const int tx0 = (t % L.tiles_x) * TILE_W, ty0 = (t / L.tiles_x) * TILE_H;
+    int pitch;
+    const uint8_t* im = level_ptr(src, pyr, g, img, l, pitch);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < BI_H * BI_W; i += 256) {
+        const int r = i / BI_W, c = i - r * BI_W;
+        const int gy = reflect101(min(ty0 - 3 + r, L.h + 2), L.h);
+        const int gx = reflect101(min(tx0 - 3 + c, L.w + 2), L.w);
+        s_in[i] = im[(size_t)gy * pitch + gx];
+    }
+    __syncthreads();
+    const int tail = (L.w / 32) * 32;  // cv2's AVX2 row filter: 32-wide fused body, unfused scalar tail
+    for (int i = tid; i < BI_H * TILE_W; i += 256) {
+        const int r = i / TILE_W, c = i - r * TILE_W;
+        const uint8_t* p = &s_in[r * BI_W + c];
+        const float v0 = (float)p[0], v1 = (float)p[1], v2 = (float)p[2], v3 = (float)p[3], v4 = (float)p[4],
+                    v5 = (float)p[5], v6 = (float)p[6];
+        float acc = __fmul_rn(k0, v0);
+        if (tx0 + c < tail) {
+            acc = fmaf(k1, v1, acc);
+            acc = fmaf(k2, v2, acc);
+            acc = fmaf(k3, v3, acc);
+            acc = fmaf(k2, v4, acc);
+            acc = fmaf(k1, v5, acc);
+            acc = fmaf(k0, v6, acc);
+        } else {
+            acc = __fadd_rn(acc, __fmul_rn(k1, v1));
+            acc = __fadd_rn(acc, __fmul_rn(k2, v2));
+            acc = __fadd_rn(acc, __fmul_rn(k3, v3));
+            acc = __fadd_rn(acc, __fmul_rn(k2, v4));
+            acc = __fadd_rn(acc, __fmul_rn(k1, v5));
+            acc = __fadd_rn(acc, __fmul_rn(k0, v6));
+        }
+        s_row[i] = acc;
+    }
+    __syncthreads();
+    uint8_t* out = blur + (size_t)img * g.img_slab + L.off;
+    for (int i = tid; i < TILE_H * TILE_W; i += 256) {
+        const int r = i / TILE_W, c = i - r * TILE_W;
+        const int gy = ty0 + r, gx = tx0 + c;
+        if (gy >= L.h || gx >= L.w) continue;
+        const float* p = &s_row[(r + 3) * TILE_W + c];
+        float acc = __fmul_rn(k3, p[0]);
+        acc = fmaf(__fadd_rn(p[TILE_W], p[-TILE_W]), k2, acc);
+        acc = fmaf(__fadd_rn(p[2 * TILE_W], p[-2 * TILE_W]), k1, acc);
+        acc = fmaf(__fadd_rn(p[3 * TILE_W], p[-3 * TILE_W]), k0, acc);
+        int v = __float2int_rn(acc);
+        v = max(0, min(255, v));
+        out[(size_t)gy * L.pitch + gx] = (uint8_t)v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// helpers shared by ANMS and describe: locate keypoint g of an image in the per-level selections
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int locate_level(const uint32_t* sel_cnt, int gidx, int& j) {
+    int l = 0, base = 0;
+#pragma unroll
+    for (int i = 0; i < ORB_NL; ++i) {
+        const int c = (int)sel_cnt[i];
+        if (gidx >= base + c) {
+            base += c;
+            l = i + 1;
+        }
+    }
+    // l is the first level whose cumulative end exceeds gidx
+    j = gidx - base;
+    return l;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K7  ANMS (the reference's own code, visual_odometry.cpp:96-157), one CTA per image.
+//   radius_i = min over {j : response_j > response_i * 1.11f} of sqrt((double)dx*dx + (double)dy*dy), dx,dy float32
+//   keep radius_i >= (num-th largest radius); output order = canonical order (what cv::ORB::compute's stable
+//   by-octave regrouping produces from the response-sorted list)
+// ------------------------------------------------------------------------------------------------------------
+#define ANMS_THREADS 1024
+
+__global__ void __launch_bounds__(ANMS_THREADS)
+anms_kernel(const __grid_constant__ OrbGeom g, const uint2* __restrict__ sel, ImgCounters* __restrict__ cnt, int kp_cap, int num,
+            float c_robust, double* __restrict__ rad, uint32_t* __restrict__ keep) {
+    extern __shared__ unsigned long long s_sort[];  // n2 doubles (as ordered bits)
+    __shared__ uint32_t s_warp[ANMS_THREADS / 32];
+    __shared__ int s_base;
+    const int img = blockIdx.x;
+    ImgCounters* C = &cnt[img];
+    const int tid = threadIdx.x;
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < ORB_NL; ++i) n += (int)C->sel_cnt[i];
+    if (n > kp_cap) n = kp_cap;
+    uint32_t* kp_keep = keep + (size_t)img * kp_cap;
+    if (n < num) {  // reference: no-op when fewer than num keypoints (visual_odometry.cpp:100)
+        for (int i = tid; i < n; i += ANMS_THREADS) kp_keep[i] = i;
+        if (tid == 0) C->n_keep = n;
+        return;
+    }
+    double* R = rad + (size_t)img * kp_cap;
+    const uint2* S = sel + (size_t)img * ORB_NL * SORT_CAP;
+    for (int i = tid; i < n; i += ANMS_THREADS) {
+        int j;
+        const int l = locate_level(C->sel_cnt, i, j);
+        const uint2 e = S[(size_t)l * SORT_CAP + j];
+        const float sc = g.lv[l].scale;
+        const float xi = __fmul_rn((float)(e.x & 0xFFFF), sc), yi = __fmul_rn((float)(e.x >> 16), sc);
+        const float thr = __fmul_rn(__uint_as_float(e.y), c_robust);
+        double best = 1.7976931348623157e308;
+        for (int l2 = 0; l2 < ORB_NL; ++l2) {
+            const int c2 = (int)C->sel_cnt[l2];
+            const float sc2 = g.lv[l2].scale;
+            const uint2* S2 = S + (size_t)l2 * SORT_CAP;
+            for (int q = 0; q < c2; ++q) {
+                const uint2 f = S2[q];
+                if (!(__uint_as_float(f.y) > thr)) break;  // per-level lists are response-descending
+                const float dx = __fsub_rn(xi, __fmul_rn((float)(f.x & 0xFFFF), sc2));
+                const float dy = __fsub_rn(yi, __fmul_rn((float)(f.x >> 16), sc2));
+                const double d = sqrt(__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)));
+                best = fmin(best, d);
+            }
+        }
+        R[i] = best;
+    }
+    __syncthreads();
+    // num-th largest radius by bitonic sort (descending) of the (positive) doubles
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (int i = tid; i < n2; i += ANMS_THREADS)
+        s_sort[i] = i < n ? ~(unsigned long long)__double_as_longlong(R[i]) : 0xFFFFFFFFFFFFFFFFull;
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n2; i += ANMS_THREADS) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const unsigned long long A = s_sort[i], B = s_sort[p];
+                    const bool up = (i & k) == 0;
+                    if ((A > B) == up) {
+                        s_sort[i] = B;
+                        s_sort[p] = A;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const double final_radius = __longlong_as_double((long long)~s_sort[num - 1]);
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += ANMS_THREADS) {
+        const int i = i0 + tid;
+        const bool k = i < n && R[i] >= final_radius;
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, k);
+        if ((tid & 31) == 0) s_warp[tid >> 5] = __popc(bal);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (int w = 0; w < ANMS_THREADS / 32; ++w) {
+            const uint32_t c = s_warp[w];
+            before += (w < (tid >> 5)) ? c : 0;
+            total += c;
+        }
+        if (k) kp_keep[s_base + before + __popc(bal & ((1u << (tid & 31)) - 1))] = i;
+        __syncthreads();
+        if (tid == 0) s_base += total;
+        __syncthreads();
+    }
+    if (tid == 0) C->n_keep = s_base;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K6 + K9  orientation and rotated BRIEF, one warp per keypoint
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float p1 = 0x1.ca44dep+5f, p3 = -0x1.2aaddcp+4f, p5 = 0x1.1d3f7ep+3f, p7 = -0x1.4515b2p+1f;
+    const float eps = 0x1.0p-52f;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+__global__ void __launch_bounds__(DESC_WARPS * 32)
+describe_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, const __grid_constant__ OrbGeom g,
+                const uint2* __restrict__ sel, ImgCounters* __restrict__ cnt, const uint32_t* __restrict__ keep,
+                int use_keep, const int8_t* __restrict__ pattern, int kp_cap, vslam_keypoint* __restrict__ kp_out,
+                uint8_t* __restrict__ desc_out, int32_t* __restrict__ n_out) {
+    const int img = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
+    ImgCounters* C = &cnt[img];
+    int total = 0;
+#pragma unroll
+    for (int i = 0; i < ORB_NL; ++i) total += (int)C->sel_cnt[i];
+    if (total > kp_cap) {
+        if (k == 0 && lane == 0) atomicOr(&C->flags, 4u);
+        total = kp_cap;
+    }
+    const int n = use_keep ? (int)C->n_keep : total;
+    if (k == 0 && lane == 0) n_out[img] = n;
+    if (k >= n) return;
+    const int gi = use_keep ? (int)keep[(size_t)img * kp_cap + k] : k;
+    int j;
+    const int l = locate_level(C->sel_cnt, gi, j);
+    const uint2 e = sel[((size_t)img * ORB_NL + l) * SORT_CAP + j];
+    const int x = e.x & 0xFFFF, y = e.x >> 16;
+    const OrbLevel& L = g.lv[l];
+
+    // intensity centroid over the radius-15 disc (orb.cpp ICAngles); lanes run along u, rows along v
+    int pitch;
+    const uint8_t* im = level_ptr(src, pyr, g, img, l, pitch);
+    const int u = lane - 15;
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int au = abs(u);
+        const uint8_t* c = im + (size_t)y * pitch + x + u;
+#pragma unroll
+        for (int v = -15; v <= 15; ++v) {
+            if (au <= c_umax[v < 0 ? -v : v]) {
+                const int val = c[(long long)v * pitch];
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+    }
+    m10 = __reduce_add_sync(0xFFFFFFFFu, m10);
+    m01 = __reduce_add_sync(0xFFFFFFFFu, m01);
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    const float ptx = __fmul_rn((float)x, L.scale), pty = __fmul_rn((float)y, L.scale);
+    vslam_keypoint* ko = kp_out + (size_t)img * kp_cap + k;
+    if (lane < 7) {
+        uint32_t w;
+        switch (lane) {
+            case 0: w = __float_as_uint(ptx); break;
+            case 1: w = __float_as_uint(pty); break;
+            case 2: w = __float_as_uint(__fmul_rn(31.f, L.scale)); break;
+            case 3: w = __float_as_uint(angle); break;
+            case 4: w = e.y; break;
+            case 5: w = (uint32_t)l; break;
+            default: w = 0xFFFFFFFFu; break;  // class_id = -1
+        }
+        reinterpret_cast<uint32_t*>(ko)[lane] = w;
+    }
+
+    // rotated BRIEF on the blurred level (orb.cpp computeOrbDescriptors, WTA_K = 2); lane = output byte
+    const uint8_t* bl = blur + (size_t)img * g.img_slab + L.off;
+    const int cx = __float2int_rn(__fmul_rn(ptx, L.inv_scale));
+    const int cy = __float2int_rn(__fmul_rn(pty, L.inv_scale));
+    const float th = __fmul_rn(angle, 0x1.1df46ap-6f);  // (float)(CV_PI/180)
+    const float a = (float)cos((double)th), b = (float)sin((double)th);
+    const uint8_t* center = bl + (size_t)cy * L.pitch + cx;
+    const char4* pat = reinterpret_cast<const char4*>(pattern) + lane * 8;
+    uint32_t byte = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const char4 p0 = __ldg(&pat[t]);  // (x0, y0, x1, y1) of test 8*lane + t
+        const float x0 = (float)p0.x, y0 = (float)p0.y, x1 = (float)p0.z, y1 = (float)p0.w;
+        const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int t0 = center[(long long)iy0 * L.pitch + ix0];
+        const int t1 = center[(long long)iy1 * L.pitch + ix1];
+        byte |= (uint32_t)(t0 < t1) << t;
+    }
+    desc_out[((size_t)img * kp_cap + k) * 32 + lane] = (uint8_t)byte;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side: geometry, lifetime, orchestration
+// ------------------------------------------------------------------------------------------------------------
+static inline int cv_round_f(float v) { return (int)lrintf(v); }  // round-half-even like cvRound
+
+// cv::ORB per-level feature quotas (orb.cpp detectAndCompute -> computeKeyPoints), float32 arithmetic
+static void orb_quotas(int nfeatures, OrbQuota* q) {
+    const float factor = (float)(1.0 / (double)1.2f);
+    float nd = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)ORB_NL));
+    int sum = 0;
+    for (int l = 0; l < ORB_NL - 1; ++l) {
+        q->n[l] = (int)lrint((double)nd);
+        sum += q->n[l];
+        nd *= factor;
+    }
+    q->n[ORB_NL - 1] = nfeatures - sum > 0 ? nfeatures - sum : 0;
+}
+
+// cv::resize(INTER_LINEAR_EXACT) coefficient tables: entry = (src offset << 16) | c1, c0 = 256 - c1
+static void resize_table(int dst, int srcn, uint32_t* out) {
+    const double scale = 1.0 / ((double)dst / (double)srcn);
+    for (int v = 0; v < dst; ++v) {
+        const double f = scale * (v + 0.5) - 0.5;
+        int i = (int)floor(f);
+        int c1 = 0;
+        if (i < 0) {
+            i = 0;
+        } else if (i >= srcn - 1) {
+            i = srcn - 1;
+        } else {
+            c1 = (int)lrint((f - i) * 256.0);
+        }
+        out[v] = ((uint32_t)i << 16) | (uint32_t)c1;
+    }
+}
+
+static int orb_set_geometry(vslam_ctx* ctx, int w, int h) {
+    OrbState* o = ctx->orb;
+    if (o->geom_valid && o->geom.w == w && o->geom.h == h) return VSLAM_OK;
+    OrbGeom g;
+    memset(&g, 0, sizeof(g));
+    g.w = w;
+    g.h = h;
+    int off = 0, tiles = 0, cand = 0, tab = 0;
+    for (int l = 0; l < ORB_NL; ++l) {
+        OrbLevel& L = g.lv[l];
+        L.scale = h_scales[l];
+        L.inv_scale = 1.f / L.scale;
+        L.w = cv_round_f((float)w / L.scale);
+        L.h = cv_round_f((float)h / L.scale);
+        if (L.w < 2 * ORB_EDGE + 8 || L.h < 2 * ORB_EDGE + 8) return VSLAM_E_INVALID;  // image too small for 8 levels
+        L.pitch = (L.w + 15) & ~15;
+        L.off = off;
+        off += L.pitch * L.h;
+        off = (off + 255) & ~255;
+        L.tiles_x = ceil_div(L.w, TILE_W);
+        L.tiles_y = ceil_div(L.h, TILE_H);
+        L.tile_begin = tiles;
+        tiles += L.tiles_x * L.tiles_y;
+        L.cand_off = cand;
+        L.cand_cap = (L.w * L.h) / 12 + 64;
+        cand += L.cand_cap;
+        L.xtab_off = tab;
+        tab += L.w;
+        L.ytab_off = tab;
+        tab += L.h;
+    }
+    g.total_tiles = tiles;
+    g.img_slab = off;
+    g.cand_slab = cand;
+    if ((size_t)off > o->slab_cap || (size_t)cand > o->cand_cap_total || tab > o->tab_cap) return VSLAM_E_CAPACITY;
+    std::vector<uint32_t> t((size_t)tab, 0);
+    for (int l = 1; l < ORB_NL; ++l) {
+        resize_table(g.lv[l].w, g.lv[l - 1].w, &t[g.lv[l].xtab_off]);
+        resize_table(g.lv[l].h, g.lv[l - 1].h, &t[g.lv[l].ytab_off]);
+    }
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VSLAM_CUDA(ctx, cudaMemcpy(o->d_tab, t.data(), (size_t)tab * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    o->geom = g;
+    o->geom_valid = true;
+    return VSLAM_OK;
+}
+
+int vslam_orb_init(vslam_ctx* ctx) {
+    OrbState* o = (OrbState*)calloc(1, sizeof(OrbState));
+    if (!o) return VSLAM_E_INVALID;
+    ctx->orb = o;
+    const vslam_config& c = ctx->cfg;
+    o->max_images = c.max_images;
+    o->kp_cap = c.max_keypoints;
+    if (c.max_images <= 0 || c.max_width <= 0 || c.max_height <= 0 || c.max_keypoints <= 0) return VSLAM_OK;  // ORB disabled
+    // capacity for the largest geometry: sum over levels of pitch*h < 3.4 * w*h (+ alignment)
+    const size_t wh = (size_t)((c.max_width + 15) & ~15) * c.max_height;
+    o->slab_cap = (size_t)(wh * 3.4) + 8 * 256 + 4096;
+    o->cand_cap_total = (size_t)(wh * 3.4 / 12) + 8 * 64 + 1024;
+    o->tab_cap = (int)((c.max_width + c.max_height) * 6.2) + 64;
+    o->in_pitch = (c.max_width + 15) & ~15;
+    const size_t ni = (size_t)c.max_images;
+    VSLAM_CUDA(ctx, cudaMalloc(&o->d_pyr, ni * o->slab_cap));
+    VSLAM_CUDA(ctx, cudaMalloc(&o->d_blur, ni * o->slab_cap));
+    VSLAM_CUDA(ctx, cudaMalloc(&o->d_tab, (size_t)o->tab_cap * sizeof(uint32_t)));
+    VSLAM_CUDA(ctx, cudaMalloc(&o->d_cand, ni * o->cand_cap_total * sizeof(uint2)));
+    VSLAM_CUDA(ctx, cudaMalloc(&o->d_sel, ni * ORB_NL * SORT_CAP * sizeof(uint2)));
+    VSLAM_CUDA(ctx, cudaMalloc(&o->d_cnt, ni * sizeof(ImgCounters)));
+    VSLAM_CUDA(ctx, cudaMalloc(&o->d_keep, ni * o->kp_cap * sizeof(uint32_t)));
+    VSLAM_CUDA(ctx, cudaMalloc(&o->d_rad, ni * o->kp_cap * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&o->d_pattern, 1024));
+    VSLAM_CUDA(ctx, cudaMemcpy(o->d_pattern, h_orb_pattern, 1024, cudaMemcpyHostToDevice));
+    VSLAM_CUDA(ctx, cudaMalloc(&o->d_in, ni * (size_t)o->in_pitch * c.max_height));
+    VSLAM_CUDA(ctx, cudaMalloc(&o->d_kp, ni * o->kp_cap * sizeof(vslam_keypoint)));
+    VSLAM_CUDA(ctx, cudaMalloc(&o->d_desc, ni * o->kp_cap * 32));
+    VSLAM_CUDA(ctx, cudaMalloc(&o->d_n, ni * sizeof(int32_t)));
+    VSLAM_CUDA(ctx, cudaMallocHost(&o->h_kp, ni * o->kp_cap * sizeof(vslam_keypoint)));
+    VSLAM_CUDA(ctx, cudaMallocHost(&o->h_desc, ni * o->kp_cap * 32));
+    VSLAM_CUDA(ctx, cudaMallocHost(&o->h_n, ni * sizeof(int32_t)));
+    VSLAM_CUDA(ctx, cudaMallocHost(&o->h_cnt, ni * sizeof(ImgCounters)));
+    VSLAM_CUDA(ctx, cudaFuncSetAttribute(harris_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SORT_CAP * (int)sizeof(unsigned long long)));
+    VSLAM_CUDA(ctx, cudaFuncSetAttribute(anms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    return VSLAM_OK;
+}
+
+void vslam_orb_free(vslam_ctx* ctx) {
+    OrbState* o = ctx->orb;
+    if (!o) return;
+    cudaFree(o->d_pyr);
+    cudaFree(o->d_blur);
+    cudaFree(o->d_tab);
+    cudaFree(o->d_cand);
+    cudaFree(o->d_sel);
+    cudaFree(o->d_cnt);
+    cudaFree(o->d_keep);
+    cudaFree(o->d_rad);
+    cudaFree(o->d_pattern);
+    cudaFree(o->d_in);
+    cudaFree(o->d_kp);
+    cudaFree(o->d_desc);
+    cudaFree(o->d_n);
+    cudaFreeHost(o->h_kp);
+    cudaFreeHost(o->h_desc);
+    cudaFreeHost(o->h_n);
+    cudaFreeHost(o->h_cnt);
+    free(o);
+    ctx->orb = nullptr;
+}
+
+// Enqueue the whole ORB pipeline for n_img images on the context stream (no host synchronisation).
+static int orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h, int nfeatures, int anms_keep,
+                       float anms_c, vslam_keypoint* d_kp, uint8_t* d_desc, int32_t* d_n) {
+    OrbState* o = ctx->orb;
+    if (!o || !o->d_pyr) return VSLAM_E_CAPACITY;
+    if (n_img <= 0 || n_img > o->max_images) return VSLAM_E_CAPACITY;
+    if (w > ctx->cfg.max_width || h > ctx->cfg.max_height) return VSLAM_E_CAPACITY;
+    if (w >= 65536 || h >= 65536) return VSLAM_E_CAPACITY;
+    if (nfeatures <= 0 || nfeatures > o->kp_cap) return VSLAM_E_CAPACITY;
+    int st = orb_set_geometry(ctx, w, h);
+    if (st != VSLAM_OK) return st;
+    const OrbGeom& g = o->geom;
+    OrbQuota q;
+    orb_quotas(nfeatures, &q);
+    cudaStream_t s = ctx->stream;
+    VSLAM_CUDA(ctx, cudaMemsetAsync(o->d_cnt, 0, (size_t)n_img * sizeof(ImgCounters), s));
+    for (int l = 1; l < ORB_NL; ++l) {
+        dim3 grid(ceil_div(g.lv[l].w, 32), ceil_div(g.lv[l].h, 8), n_img);
+        resize_level_kernel<<<grid, dim3(32, 8), 0, s>>>(src, o->d_pyr, o->d_tab, g, l);
+        VSLAM_LAUNCH_CHECK(ctx, "resize_level_kernel");
+    }
+    fast_kernel<<<dim3(g.total_tiles, n_img), FAST_THREADS, 0, s>>>(src, o->d_pyr, g, o->d_cand, o->d_cnt);
+    VSLAM_LAUNCH_CHECK(ctx, "fast_kernel");
+    harris_select_kernel<<<dim3(ORB_NL, n_img), HS_THREADS, SORT_CAP * sizeof(unsigned long long), s>>>(
+        src, o->d_pyr, g, q, o->d_cand, o->d_cnt, o->d_sel);
+    VSLAM_LAUNCH_CHECK(ctx, "harris_select_kernel");
+    blur_kernel<<<dim3(g.total_tiles, n_img), 256, 0, s>>>(src, o->d_pyr, o->d_blur, g);
+    VSLAM_LAUNCH_CHECK(ctx, "blur_kernel");
+    const int use_keep = anms_keep > 0 ? 1 : 0;
+    if (use_keep) {
+        int n2 = 1;
+        while (n2 < o->kp_cap) n2 <<= 1;
+        if ((size_t)n2 * 8 > 65536) return VSLAM_E_CAPACITY;
+        anms_kernel<<<n_img, ANMS_THREADS, (size_t)n2 * 8, s>>>(g, o->d_sel, o->d_cnt, o->kp_cap, anms_keep, anms_c,
+                                                               o->d_rad, o->d_keep);
+        VSLAM_LAUNCH_CHECK(ctx, "anms_kernel");
+    }
+    describe_kernel<<<dim3(ceil_div(o->kp_cap, DESC_WARPS), n_img), DESC_WARPS * 32, 0, s>>>(
+        src, o->d_pyr, o->d_blur, g, o->d_sel, o->d_cnt, o->d_keep, use_keep, o->d_pattern, o->kp_cap, d_kp, d_desc,
+        d_n);
+    VSLAM_LAUNCH_CHECK(ctx, "describe_kernel");
+    return VSLAM_OK;
+}
+
+extern "C" int vslam_orb_keypoint_capacity(const vslam_ctx* ctx) { return ctx && ctx->orb ? ctx->orb->kp_cap : 0; }
+
+extern "C" int vslam_orb_detect_compute_batch_dev(vslam_ctx* ctx, const uint8_t* d_images, int n_images, int width,
+                                                  int height, int row_pitch, long long image_stride, int nfeatures,
+                                                  int anms_keep, float anms_c, vslam_keypoint* d_kp, uint8_t* d_desc,
+                                                  int32_t* d_n) {
+    if (!ctx || !d_images || !d_kp || !d_desc || !d_n) return VSLAM_E_INVALID;
+    if (width <= 0 || height <= 0 || row_pitch < width) return VSLAM_E_INVALID;
+    ImgSrc src;
+    src.base[0] = d_images;
+    src.base[1] = d_images;
+    src.img_stride = image_stride;
+    src.pitch = row_pitch;
+    src.per_base = n_images > 0 ? n_images : 1;
+    return orb_enqueue(ctx, src, n_images, width, height, nfeatures, anms_keep, anms_c, d_kp, d_desc, d_n);
+}
+
+// flags raised by the kernels (bit0 candidate overflow, bit1 sort overflow, bit2 keypoint capacity)
+static int orb_check_flags(vslam_ctx* ctx, int n_img) {
+    OrbState* o = ctx->orb;
+    for (int i = 0; i < n_img; ++i) {
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(&o->h_cnt[i].flags, &o->d_cnt[i].flags, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                        ctx->stream));
+    }
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n_img; ++i)
+        if (o->h_cnt[i].flags) return VSLAM_E_OVERFLOW;
+    return VSLAM_OK;
+}
+
+extern "C" int vslam_orb_last_flags(vslam_ctx* ctx, int n_images) {
+    if (!ctx || !ctx->orb) return VSLAM_E_INVALID;
+    return orb_check_flags(ctx, n_images);
+}
+
+extern "C" int vslam_orb_detect_compute_batch(vslam_ctx* ctx, const uint8_t* images, int n_images, int width,
+                                              int height, int row_pitch, long long image_stride, int nfeatures,
+                                              int anms_keep, float anms_c, vslam_keypoint* kp_out, uint8_t* desc_out,
+                                              int32_t* n_out) {
+    if (!ctx || !n_out) return VSLAM_E_INVALID;
+    if (!images) return VSLAM_E_INVALID;  // reference: "Could not open or find the image" -> -1 (vo.cpp:73-77)
+    if (!kp_out || !desc_out) return VSLAM_E_INVALID;
+    OrbState* o = ctx->orb;
+    if (!o || !o->d_in) return VSLAM_E_CAPACITY;
+    if (n_images <= 0 || n_images > o->max_images) return VSLAM_E_CAPACITY;
+    if (width <= 0 || height <= 0 || row_pitch < width) return VSLAM_E_INVALID;
+    if (width > ctx->cfg.max_width || height > ctx->cfg.max_height) return VSLAM_E_CAPACITY;
+    cudaStream_t s = ctx->stream;
+    const size_t dstride = (size_t)o->in_pitch * height;
+    for (int i = 0; i < n_images; ++i)
+        VSLAM_CUDA(ctx, cudaMemcpy2DAsync(o->d_in + i * dstride, o->in_pitch, images + (size_t)i * image_stride,
+                                          row_pitch, width, height, cudaMemcpyHostToDevice, s));
+    ImgSrc src;
+    src.base[0] = o->d_in;
+    src.base[1] = o->d_in;
+    src.img_stride = (long long)dstride;
+    src.pitch = o->in_pitch;
+    src.per_base = n_images;
+    int st = orb_enqueue(ctx, src, n_images, width, height, nfeatures, anms_keep, anms_c, o->d_kp, o->d_desc, o->d_n);
+    if (st != VSLAM_OK) return st;
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(o->h_n, o->d_n, n_images * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    st = orb_check_flags(ctx, n_images);  // synchronises
+    if (st != VSLAM_OK) return st;
+    for (int i = 0; i < n_images; ++i) {
+        const int n = o->h_n[i];
+        n_out[i] = n;
+        if (n <= 0) continue;
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(kp_out + (size_t)i * o->kp_cap, o->d_kp + (size_t)i * o->kp_cap,
+                                        (size_t)n * sizeof(vslam_keypoint), cudaMemcpyDeviceToHost, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(desc_out + (size_t)i * o->kp_cap * 32, o->d_desc + (size_t)i * o->kp_cap * 32,
+                                        (size_t)n * 32, cudaMemcpyDeviceToHost, s));
+    }
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(s));
+    return VSLAM_OK;
+}
+
+extern "C" int vslam_orb_detect_compute(vslam_ctx* ctx, const uint8_t* image, int width, int height, int row_pitch,
+                                        int nfeatures, int anms_keep, float anms_c, vslam_keypoint* kp_out,
+                                        uint8_t* desc_out, int32_t* n_out) {
+    return vslam_orb_detect_compute_batch(ctx, image, 1, width, height, row_pitch, 0, nfeatures, anms_keep, anms_c,
+                                          kp_out, desc_out, n_out);
+}
+
+// test/debug taps: copy intermediate device state of image `img` to host buffers (any may be NULL)
+extern "C" int vslam_orb_debug_read(vslam_ctx* ctx, int img, int level, uint8_t* level_pixels, uint8_t* blurred_pixels,
+                                    int* w_out, int* h_out, uint32_t* cand_xy_score, int cand_cap, int* n_cand) {
+    if (!ctx || !ctx->orb || !ctx->orb->geom_valid) return VSLAM_E_INVALID;
+    OrbState* o = ctx->orb;
+    if (img < 0 || img >= o->max_images || level < 0 || level >= ORB_NL) return VSLAM_E_INVALID;
+    const OrbLevel& L = o->geom.lv[level];
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (w_out) *w_out = L.w;
+    if (h_out) *h_out = L.h;
+    if (level_pixels && level > 0)
+        VSLAM_CUDA(ctx, cudaMemcpy2D(level_pixels, L.w, o->d_pyr + (size_t)img * o->geom.img_slab + L.off, L.pitch, L.w,
+                                     L.h, cudaMemcpyDeviceToHost));
+    if (blurred_pixels)
+        VSLAM_CUDA(ctx, cudaMemcpy2D(blurred_pixels, L.w, o->d_blur + (size_t)img * o->geom.img_slab + L.off, L.pitch,
+                                     L.w, L.h, cudaMemcpyDeviceToHost));
+    if (n_cand) {
+        ImgCounters c;
+        VSLAM_CUDA(ctx, cudaMemcpy(&c, &o->d_cnt[img], sizeof(c), cudaMemcpyDeviceToHost));
+        int n = (int)c.cand_cnt[level];
+        if (n > L.cand_cap) n = L.cand_cap;
+        *n_cand = n;
+        if (cand_xy_score) {
+            if (n > cand_cap) n = cand_cap;
+            VSLAM_CUDA(ctx, cudaMemcpy(cand_xy_score, o->d_cand + (size_t)img * o->geom.cand_slab + L.cand_off,
+                                       (size_t)n * sizeof(uint2), cudaMemcpyDeviceToHost));
+        }
+    }
+    return VSLAM_OK;
+}

@@ -50,6 +50,12 @@ SIGNATURES = {
     "vslam_ctx_synchronize": (_i, [_vp]),
     "vslam_ctx_launch_count": (_i64, [_vp]),
     "vslam_match_hamming": (_i, [_vp, _vp, _i, _vp, _i, _i, _d, _d, _vp, _pi]),
+    "vslam_orb_keypoint_capacity": (_i, [_vp]),
+    "vslam_orb_detect_compute": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "vslam_orb_detect_compute_batch": (_i, [_vp, _vp, _i, _i, _i, _i, C.c_longlong, _i, _i, _f, _vp, _vp, _vp]),
+    "vslam_orb_detect_compute_batch_dev": (_i, [_vp, _vp, _i, _i, _i, _i, C.c_longlong, _i, _i, _f, _vp, _vp, _vp]),
+    "vslam_orb_last_flags": (_i, [_vp, _i]),
+    "vslam_orb_debug_read": (_i, [_vp, _i, _i, _vp, _vp, _pi, _pi, _vp, _i, _pi]),
     "vslam_match_hamming_batch_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _d, _d, _vp, _i, _vp]),
 }
 
@@ -140,3 +146,50 @@ class Context:
                                                     float(gate_rel), float(gate_abs), _ptr(d_out), out_stride,
                                                     _ptr(d_n_out))
         self.check(st, "vslam_match_hamming_batch_dev")
+
+    # ---- K1-K9 ------------------------------------------------------------------------------
+    @property
+    def kp_cap(self) -> int:
+        return int(self.lib.vslam_orb_keypoint_capacity(self.h))
+
+    def orb_detect_compute(self, images, nfeatures: int = 3000, anms_keep: int = 500, anms_c: float = 1.11):
+        """VO::feature_detection on one image (H x W u8) or a batch (B x H x W u8), host buffers.
+        Returns a list of (keypoints KEYPOINT_DTYPE[n], descriptors u8[n,32]) -- one per image."""
+        if images is None:
+            raise VslamError(-1, "vslam_orb_detect_compute", "Could not open or find the image")
+        imgs = np.ascontiguousarray(images, dtype=np.uint8)
+        single = imgs.ndim == 2
+        if single:
+            imgs = imgs[None]
+        b, h, w = imgs.shape
+        cap = self.kp_cap
+        kp = np.zeros((b, cap), dtype=KEYPOINT_DTYPE)
+        desc = np.zeros((b, cap, 32), dtype=np.uint8)
+        n = np.zeros(b, dtype=np.int32)
+        st = self.lib.vslam_orb_detect_compute_batch(self.h, _ptr(imgs), b, w, h, w, h * w, int(nfeatures),
+                                                     int(anms_keep), float(anms_c), _ptr(kp), _ptr(desc), _ptr(n))
+        self.check(st, "vslam_orb_detect_compute_batch")
+        out = [(kp[i, :n[i]].copy(), desc[i, :n[i]].copy()) for i in range(b)]
+        return out[0] if single else out
+
+    def orb_detect_compute_batch_dev(self, d_images, n_images, w, h, pitch, img_stride, nfeatures, anms_keep, anms_c,
+                                     d_kp, d_desc, d_n):
+        st = self.lib.vslam_orb_detect_compute_batch_dev(self.h, _ptr(d_images), n_images, w, h, pitch, img_stride,
+                                                         int(nfeatures), int(anms_keep), float(anms_c), _ptr(d_kp),
+                                                         _ptr(d_desc), _ptr(d_n))
+        self.check(st, "vslam_orb_detect_compute_batch_dev")
+
+    def orb_last_flags(self, n_images: int):
+        self.check(self.lib.vslam_orb_last_flags(self.h, n_images), "vslam_orb_last_flags")
+
+    def orb_debug_level(self, img: int, level: int, want_cand: bool = True):
+        """(level pixels or None for level 0, blurred pixels, candidates[n,2] u32) of the last ORB call."""
+        w, hh, nc = C.c_int(0), C.c_int(0), C.c_int(0)
+        self.check(self.lib.vslam_orb_debug_read(self.h, img, level, None, None, C.byref(w), C.byref(hh), None, 0,
+                                                 C.byref(nc)), "vslam_orb_debug_read")
+        lv = np.zeros((hh.value, w.value), dtype=np.uint8)
+        bl = np.zeros((hh.value, w.value), dtype=np.uint8)
+        cand = np.zeros((max(nc.value, 1), 2), dtype=np.uint32)
+        self.check(self.lib.vslam_orb_debug_read(self.h, img, level, _ptr(lv), _ptr(bl), C.byref(w), C.byref(hh),
+                                                 _ptr(cand), nc.value, C.byref(nc)), "vslam_orb_debug_read")
+        return (lv if level > 0 else None), bl, cand[:nc.value]
