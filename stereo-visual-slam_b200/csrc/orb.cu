@@ -528,16 +528,20 @@ blur_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ b
 // helpers shared by ANMS and describe: locate keypoint g of an image in the per-level selections
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int locate_level(const uint32_t* sel_cnt, int gidx, int& j) {
-    int l = 0, base = 0;
+    int l = ORB_NL - 1, base = 0;
+    bool found = false;
 #pragma unroll
     for (int i = 0; i < ORB_NL; ++i) {
         const int c = (int)sel_cnt[i];
-        if (gidx >= base + c) {
-            base += c;
-            l = i + 1;
+        if (!found) {
+            if (gidx < base + c) {
+                found = true;
+                l = i;
+            } else if (i < ORB_NL - 1) {
+                base += c;
+            }
         }
     }
-    // l is the first level whose cumulative end exceeds gidx
     j = gidx - base;
     return l;
 }
