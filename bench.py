@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- stereo frames/sec of the B200-native frontend (detect + match + triangulate), BASELINE.json metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs B] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of B synthetic 1241x376 stereo pairs at 2000 ORB keypoints
+(BASELINE.json configs[1], batched): ORB on every left and right image, L<->R brute-force Hamming matching with
+cross-check + the reference's distance gate, per-match DLT triangulation with the depth gates.
+  value  : whole-job stereo frames/s with the images already resident in HBM (CUDA events on the launching stream,
+           max over ranks); two input sets are alternated so a step's inputs are not L2-resident from the last step.
+  e2e    : the same metric through the host-buffer C-ABI call (pinned host images in, all results out, H2D and D2H
+           copies inside the timed region).
+  roofline / cpu_baseline / clocks / gpu_launches as the driver contract asks.
+Under torchrun (N > 1) every rank runs its own batch (frames are independent: weak scaling, no collective on the
+data path); timing is bracketed by barrier + synchronize and reduced with MAX over ranks.
+`--impl reference` times the reference's own CPU path for the same workload: live cv2 4.13.0 (cv::ORB, cv::BFMatcher,
+cv::triangulatePoints -- the OpenCV calls the reference makes) wrapped by the oracle, on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, NFEAT = 1241, 376, 2000
+METRIC = "stereo_frames_per_sec"
+UNIT = "stereo frames/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_batch(pkg, n_pairs: int, seed0: int):
+    """n_pairs distinct synthetic stereo pairs are expensive to synthesise on the host; 8 base pairs are generated and
+    cyclically rolled by whole rows so that every image of the batch is a different array with the same statistics."""
+    base = [pkg.synth.synth_pair(seed0 + s)[:2] for s in range(8)]
+    L = np.empty((n_pairs, H, W), np.uint8)
+    R = np.empty((n_pairs, H, W), np.uint8)
+    for i in range(n_pairs):
+        l, r = base[i % 8]
+        sh = (i // 8) * 7
+        L[i] = np.roll(l, sh, axis=0)
+        R[i] = np.roll(r, sh, axis=0)
+    return L, R
+
+
+def cv2_frontend(cv2, V, left, right, P1, P2, nfeat=NFEAT):
+    """The reference CPU path for one stereo pair (oracle wrappers over the OpenCV calls the reference makes)."""
+    orb = cv2.ORB_create(nfeat)
+    kl, dl = orb.detectAndCompute(left, None)
+    kr, dr = orb.detectAndCompute(right, None)
+    m = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match(dl, dr)
+    if not m:
+        return 0
+    dist = np.array([x.distance for x in m])
+    keep = dist <= max(2.0 * dist.min(), 30.0)
+    xl = np.array([kl[x.queryIdx].pt for x, k in zip(m, keep) if k], np.float64).T
+    xr = np.array([kr[x.trainIdx].pt for x, k in zip(m, keep) if k], np.float64).T
+    X = cv2.triangulatePoints(P1, P2, xl, xr)
+    z = X[2] / X[3]
+    return int(((z > 10) & (z < 400)).sum())
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import cv2
+    import vslam_b200_loader
+    pkg = vslam_b200_loader.pkg
+    from oracle import vo_restate as V
+    ncores = os.cpu_count() or 1
+    cv2.setNumThreads(ncores)
+    s = pkg.synth
+    P1, P2 = V.stereo_projection_matrices(s.FX, s.FY, s.CX, s.CY, s.BASELINE_M)
+    sample = 4  # stereo pairs per step: a bounded sample of the batch workload
+    L, R = make_batch(pkg, sample, 0)
+    for _ in range(max(args.warmup, 1)):
+        cv2_frontend(cv2, V, L[0], R[0], P1, P2)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for i in range(sample):
+            cv2_frontend(cv2, V, L[i], R[i], P1, P2)
+    dt = time.perf_counter() - t0
+    fps = args.steps * sample / dt
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[1]: 1241x376 synthetic stereo pairs, 2000 ORB kp, detect+match+triangulate",
+                       "pairs_per_step": sample},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": ncores, "kind": "reference",
+                             "sample": f"{sample} stereo pairs/step x {args.steps} steps; live cv2 {cv2.__version__} "
+                                       "(cv::ORB(2000) detectAndCompute x2, BFMatcher crossCheck + gate, "
+                                       "triangulatePoints) = the OpenCV calls of the reference's VO path, "
+                                       f"cv2.setNumThreads({ncores})"},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def algorithmic_bytes(n_images: int, n_pairs: int, n_kp: float, n_match: float):
+    """ALGORITHMIC bytes per launch for each kernel, for a batch of n_images / n_pairs."""
+    lv = [(1241, 376), (1034, 313), (862, 261), (718, 218), (598, 181), (499, 151), (416, 126), (346, 105)]
+    px = [w * h for w, h in lv]
+    tot = sum(px)
+    return {
+        # one launch per level l>=1: read level l-1, write level l  (sum over the 7 launches / 7 = per-launch average)
+        "resize_level_kernel": n_images * (sum(px[:-1]) + sum(px[1:])) / 7.0,
+        "fast_kernel": n_images * tot,                      # every pyramid pixel read once (+ small candidate list)
+        "blur_kernel": n_images * 2 * tot,                  # read + write every pyramid pixel
+        "harris_select_kernel": n_images * (2 * n_kp * (81 + 8) + n_kp * 8),   # 9x9 patch per candidate + lists
+        "describe_kernel": n_images * n_kp * (749 + 512 + 28 + 32),            # IC disc + 512 samples + outputs
+        "hamming_argmin_kernel": n_pairs * (2 * n_kp * 32 + 2 * n_kp * 4),     # both descriptor sets + fw/bw keys
+        "crosscheck_gate_compact_kernel": n_pairs * (2 * n_kp * 4 + n_match * 16),
+        "triangulate_kernel": n_pairs * n_match * (16 + 2 * 28 + 12 + 1),
+    }
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import vslam_b200_loader
+    pkg = vslam_b200_loader.pkg
+    from oracle import vo_restate as V  # only for P1/P2 construction helpers and the cpu_baseline leg
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.pairs
+    cap = 2304
+    ctx = pkg.Context(device=local_rank, max_images=2 * B, max_keypoints=cap)
+    stream = torch.cuda.Stream(device=dev)
+    ctx.set_stream(stream.cuda_stream)
+    s = pkg.synth
+    P1, P2 = V.stereo_projection_matrices(s.FX, s.FY, s.CX, s.CY, s.BASELINE_M)
+
+    # two alternating input sets (2 x 2B x 466 KB > L2 for B >= 64), pinned on the host for the e2e leg
+    sets = []
+    for k in range(2):
+        L, R = make_batch(pkg, B, 100 * rank + 17 * k)
+        hl = torch.from_numpy(L).pin_memory()
+        hr = torch.from_numpy(R).pin_memory()
+        sets.append((hl, hr, hl.to(dev), hr.to(dev)))
+    d_kp = torch.zeros((2 * B, cap, 7), dtype=torch.int32, device=dev)
+    d_desc = torch.zeros((2 * B, cap, 32), dtype=torch.uint8, device=dev)
+    d_nkp = torch.zeros(2 * B, dtype=torch.int32, device=dev)
+    d_m = torch.zeros((B, cap, 4), dtype=torch.int32, device=dev)
+    d_nm = torch.zeros(B, dtype=torch.int32, device=dev)
+    d_xyz = torch.zeros((B, cap, 3), dtype=torch.float32, device=dev)
+    d_fl = torch.zeros((B, cap), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_dev(i):
+        _, _, dl, dr = sets[i & 1]
+        ctx.stereo_frontend_dev(dl, dr, B, W, H, W, W * H, P1, P2, None, d_kp, d_desc, d_nkp, d_m, d_nm, d_xyz, d_fl,
+                                nfeatures=NFEAT)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing (value) -------------------------------------------------------------
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            step_dev(i)
+    ctx.orb_last_flags(2 * B)  # synchronises; raises on a work-list overflow
+    n_kp_mean = float(d_nkp.float().mean())
+    n_m_mean = float(d_nm.float().mean())
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ctx.timing_enable(True)
+    launches0 = ctx.launch_count
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        flush.fill_(1)  # evict the previous step's lines; enqueued before the start event
+        e0.record(stream)
+        for i in range(args.steps):
+            step_dev(i)
+        e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    ktimes = ctx.timing_read()
+    ctx.timing_enable(False)
+    clk = clocks.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # ---- end-to-end through the host-buffer C-ABI call (e2e) -------------------------------------------
+    out = ctx.alloc_frontend_outputs(B)
+    keep_alive = []
+    for k, v in list(out.items()):  # pinned result buffers (structured dtypes go through a byte view)
+        tt = torch.from_numpy(v.view(np.uint8).reshape(-1)).pin_memory()
+        keep_alive.append(tt)
+        out[k] = tt.numpy().view(v.dtype).reshape(v.shape)
+    h2d = 2 * B * W * H
+    d2h = sum(v.nbytes for v in out.values())
+    for i in range(min(args.warmup, 3)):
+        ctx.stereo_frontend(sets[i & 1][0], sets[i & 1][1], P1, P2, nfeatures=NFEAT, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        ctx.stereo_frontend(sets[i & 1][0], sets[i & 1][1], P1, P2, nfeatures=NFEAT, out=out)  # synchronous
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(t.item())
+    matches_e2e = int(out["n_matches"].sum())
+    usable = int(sum(int((out["flags"][i, :out["n_matches"][i]] & 1).sum()) for i in range(B)))
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------
+    peak, peak_src = _peaks()
+    alg = algorithmic_bytes(2 * B, B, n_kp_mean, n_m_mean)
+    share = {k: v[0] for k, v in ktimes.items()}
+    tot_k = sum(share.values()) or 1.0
+    top = max(share, key=share.get)
+    avg_ms = ktimes[top][0] / ktimes[top][1]
+    achieved = alg.get(top, 0.0) / (avg_ms * 1e-3) / 1e9
+    roof = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg_ms,
+            "algorithmic_bytes_per_launch": alg.get(top, 0.0),
+            "kernel_time_share": {k: round(v / tot_k, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
+            "note": "per-kernel CUDA-event times measured live over the timed region; see DESIGN.md §4 for the bytes"}
+    # Hamming kernel: the north star asks for its HBM fraction; it is POPC-pipe bound by construction
+    if "hamming_argmin_kernel" in ktimes:
+        hm = ktimes["hamming_argmin_kernel"][0] / ktimes["hamming_argmin_kernel"][1]
+        roof["hamming"] = {"hbm_GBps": alg["hamming_argmin_kernel"] / (hm * 1e-3) / 1e9,
+                           "hbm_frac": alg["hamming_argmin_kernel"] / (hm * 1e-3) / 1e9 / peak,
+                           "popc_Tops": B * n_kp_mean * n_kp_mean * 8 / (hm * 1e-3) / 1e12,
+                           "popc_pipe_peak_Tops": 148 * 16 * (clk["sm_mhz"] or 1965.0) * 1e6 / 1e12,
+                           "avg_launch_ms": hm}
+
+    # ---- CPU baseline beside it (bounded sample, all host threads) ----------------------------------------
+    import cv2
+    ncores = os.cpu_count() or 1
+    cv2.setNumThreads(ncores)
+    Ls, Rs = sets[0][0].numpy(), sets[0][1].numpy()
+    cv2_frontend(cv2, V, Ls[0], Rs[0], P1, P2)
+    n_cpu, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < args.cpu_seconds and n_cpu < B:
+        cv2_frontend(cv2, V, Ls[n_cpu], Rs[n_cpu], P1, P2)
+        n_cpu += 1
+    cpu_fps = n_cpu / (time.perf_counter() - t0)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[1] batched: 1241x376 synthetic stereo pairs, 2000 ORB kp, "
+                                   "detect(L,R)+BF-Hamming cross-check match+DLT triangulate",
+                       "pairs_per_step_per_gpu": B, "nfeatures": NFEAT, "anms": "off (configs[1])",
+                       "l2": "two alternating input sets + 256 MiB flush before the timed region; per-step working "
+                             "set (inputs+pyramids+blurred) ~%.0f MB > 126 MB L2" % (2 * B * 3.7),
+                       "mean_keypoints_per_image": n_kp_mean, "mean_matches_per_pair": n_m_mean,
+                       "parallelism": f"frames sharded over {world} GPU(s), no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "matches_per_step": matches_e2e, "usable_points_per_step": usable},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
+            "cpu_baseline": {"value": cpu_fps, "unit": UNIT, "cores": ncores, "kind": "port",
+                             "sample": f"{n_cpu} stereo pairs of the same batch through the oracle's cv2 "
+                                       f"{cv2.__version__} path (ORB(2000) x2, BFMatcher crossCheck + gate, "
+                                       f"triangulatePoints), cv2.setNumThreads({ncores})"}}
+    if args.ba:
+        try:
+            line["ba"] = bench_ba(ctx, pkg, args)
+        except Exception as ex:  # the BA numbers are secondary; never lose the headline line
+            line["ba"] = {"error": repr(ex)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def bench_ba(ctx, pkg, args):
+    """BA LM-iterations/s on configs[2]'s window (K=10, L=5000) -- filled in once the BA kernels exist."""
+    if not hasattr(ctx, "ba_optimize"):
+        return {"unavailable": "BA kernels not built yet"}
+    return pkg.bench_ba(ctx, args) if hasattr(pkg, "bench_ba") else {"unavailable": "no bench hook"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=128, help="stereo pairs per step per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-ba", dest="ba", action="store_false")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -82,6 +82,14 @@ int vslam_ctx_synchronize(vslam_ctx* ctx);
 /* number of kernels this context has launched since creation (for bench.py's gpu_launches) */
 int64_t vslam_ctx_launch_count(const vslam_ctx* ctx);
 
+/* Optional per-launch timing: when enabled every kernel launch of this context is bracketed by CUDA
+ * events on the launching stream; vslam_ctx_timing_read synchronises and returns the accumulated device
+ * time and launch count of kernel `id` (0 <= id < vslam_kernel_count()) since the last enable. */
+int vslam_kernel_count(void);
+const char* vslam_kernel_name(int id);
+int vslam_ctx_timing_enable(vslam_ctx* ctx, int on);
+int vslam_ctx_timing_read(vslam_ctx* ctx, int id, double* total_ms, int64_t* launches);
+
 /* ------------------------------------------------------------------------------------------------
  * K10  brute-force Hamming matching + mutual cross-check + distance gate.
  * Replaces cv::BFMatcher(NORM_HAMMING, crossCheck=true)::match and the gate of VO::feature_matching
@@ -138,6 +146,47 @@ int vslam_orb_last_flags(vslam_ctx* ctx, int n_images);
  * cand_xy_score receives pairs {x | y << 16, FAST score} in arbitrary order. */
 int vslam_orb_debug_read(vslam_ctx* ctx, int img, int level, uint8_t* level_pixels, uint8_t* blurred_pixels,
                          int* w_out, int* h_out, uint32_t* cand_xy_score, int cand_cap, int* n_cand);
+
+/* ------------------------------------------------------------------------------------------------
+ * K11  per-match triangulation (DLT) with the reference's depth gates.
+ * Takes the role of VO::disparity_map + Frame::find_3d + VO::set_ref_3d_position
+ * (visual_odometry.cpp:159-217, types_def.cpp:9-18) in sparse-stereo form; arithmetic oracle is
+ * cv::triangulatePoints.  xl / xr are n x 2 float32 pixel coordinates, P1 / P2 row-major 3x4
+ * projection matrices, T_c_w a row-major 3x4 [R|t] (NULL = identity).  xyz_world (n x 3 float32) is
+ * T_c_w^-1 * p for EVERY input (no compaction); flags bit0 = usable (10 < Z < 400, visual_odometry.cpp:194),
+ * bit1 = reliable depth (Z < 40, visual_odometry.cpp:201), Z measured in the left camera frame.
+ * ---------------------------------------------------------------------------------------------- */
+int vslam_triangulate(vslam_ctx* ctx, const float* xl, const float* xr, int n, const double* P1, const double* P2,
+                      const double* T_c_w, float* xyz_world, uint8_t* flags);
+/* device form over match lists: pair b triangulates d_matches[b*match_stride + i], i < d_n_matches[b], between
+ * d_kp_left[b*kp_stride + queryIdx] and d_kp_right[b*kp_stride + trainIdx]; P1/P2 are HOST pointers (passed by
+ * value to the kernel), d_T_c_w is batch x 12 doubles on the device or NULL. */
+int vslam_triangulate_matches_batch_dev(vslam_ctx* ctx, const vslam_keypoint* d_kp_left,
+                                        const vslam_keypoint* d_kp_right, int kp_stride,
+                                        const vslam_dmatch* d_matches, const int32_t* d_n_matches, int match_stride,
+                                        int batch, const double* P1, const double* P2, const double* d_T_c_w,
+                                        float* d_xyz, uint8_t* d_flags);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched stereo frontend = the north star's "detect + match + triangulate" on n_pairs stereo pairs:
+ * vslam_orb_detect_compute on every left and right image, VO::feature_matching (left = query,
+ * right = train; gate_rel / gate_abs as in vslam_match_hamming) and vslam_triangulate per match.
+ * Strides: cap = vslam_orb_keypoint_capacity(ctx).  kp [2*n_pairs][cap] and desc [2*n_pairs][cap][32]
+ * hold the left images first, then the right images; n_kp [2*n_pairs]; matches [n_pairs][cap];
+ * n_matches [n_pairs]; xyz [n_pairs][cap][3]; flags [n_pairs][cap].
+ * The _dev form takes device pointers (P1/P2 stay host pointers) and does not synchronise.
+ * ---------------------------------------------------------------------------------------------- */
+int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_pairs, int width,
+                                int height, int row_pitch, long long image_stride, int nfeatures, int anms_keep,
+                                float anms_c, double gate_rel, double gate_abs, const double* P1, const double* P2,
+                                const double* T_c_w, vslam_keypoint* kp, uint8_t* desc, int32_t* n_kp,
+                                vslam_dmatch* matches, int32_t* n_matches, float* xyz, uint8_t* flags);
+int vslam_stereo_frontend_batch_dev(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_right, int n_pairs,
+                                    int width, int height, int row_pitch, long long image_stride, int nfeatures,
+                                    int anms_keep, float anms_c, double gate_rel, double gate_abs, const double* P1,
+                                    const double* P2, const double* d_T_c_w, vslam_keypoint* d_kp, uint8_t* d_desc,
+                                    int32_t* d_n_kp, vslam_dmatch* d_matches, int32_t* d_n_matches, float* d_xyz,
+                                    uint8_t* d_flags);
 
 #ifdef __cplusplus
 }

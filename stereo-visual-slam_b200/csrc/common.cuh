@@ -14,6 +14,18 @@
 struct OrbState;   // orb.cu
 struct MatchState; // match.cu
 struct BaState;    // ba.cu
+struct FrontState; // frontend.cu
+
+// kernel ids for the optional per-launch CUDA-event timing (vslam_ctx_timing_*)
+enum {
+    VK_RESIZE = 0, VK_FAST, VK_HARRIS_SELECT, VK_BLUR, VK_ANMS, VK_DESCRIBE, VK_HAMMING_ARGMIN, VK_CROSSCHECK,
+    VK_TRIANGULATE, VK_BA_BUILD, VK_BA_SOLVE, VK_BA_UPDATE, VK_BA_MISC, VK_PNP, VK_COUNT
+};
+#define VSLAM_TIMING_CAP 16384
+struct TimingRec {
+    int id;
+    cudaEvent_t a, b;
+};
 
 struct vslam_ctx {
     vslam_config cfg;
@@ -22,9 +34,15 @@ struct vslam_ctx {
     int64_t launches;
     char err[256];
     int num_sms;
+    int timing_on;
+    int n_trec, n_trec_alloc;
+    TimingRec* trec;
+    double t_ms[VK_COUNT];
+    int64_t t_launches[VK_COUNT];
     OrbState* orb;
     MatchState* match;
     BaState* ba;
+    FrontState* front;
 };
 
 static inline int vslam_set_cuda_error(vslam_ctx* ctx, cudaError_t e, const char* where) {
@@ -45,7 +63,38 @@ static inline int vslam_set_cuda_error(vslam_ctx* ctx, cudaError_t e, const char
         if (e__ != cudaSuccess) return vslam_set_cuda_error((ctx), e__, (name)); \
     } while (0)
 
+// bracket a launch with events on the context stream when timing is enabled
+static inline void vslam_time_begin(vslam_ctx* ctx, int id) {
+    if (!ctx->timing_on || ctx->n_trec >= VSLAM_TIMING_CAP) return;
+    TimingRec* r = &ctx->trec[ctx->n_trec];
+    if (ctx->n_trec >= ctx->n_trec_alloc) {
+        cudaEventCreate(&r->a);
+        cudaEventCreate(&r->b);
+        ctx->n_trec_alloc = ctx->n_trec + 1;
+    }
+    r->id = id;
+    cudaEventRecord(r->a, ctx->stream);
+}
+static inline void vslam_time_end(vslam_ctx* ctx) {
+    if (!ctx->timing_on || ctx->n_trec >= VSLAM_TIMING_CAP) return;
+    cudaEventRecord(ctx->trec[ctx->n_trec].b, ctx->stream);
+    ctx->n_trec++;
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Level 0 is read in place from the caller's buffers (left images first, then right images).
+struct ImgSrc {
+    const uint8_t* base[2];
+    long long img_stride;  // bytes between consecutive images of one base
+    int pitch;             // bytes between rows
+    int per_base;          // images per base pointer
+};
+
+// internal cross-module entry points
+int vslam_orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h, int nfeatures, int anms_keep,
+                      float anms_c, vslam_keypoint* d_kp, uint8_t* d_desc, int32_t* d_n);
+int vslam_orb_check_flags(vslam_ctx* ctx, int n_img);  // synchronises the stream
 
 // sub-module lifetime hooks (each .cu owns its state)
 int vslam_match_init(vslam_ctx* ctx);
@@ -54,3 +103,5 @@ int vslam_orb_init(vslam_ctx* ctx);
 void vslam_orb_free(vslam_ctx* ctx);
 int vslam_ba_init(vslam_ctx* ctx);
 void vslam_ba_free(vslam_ctx* ctx);
+int vslam_front_init(vslam_ctx* ctx);
+void vslam_front_free(vslam_ctx* ctx);

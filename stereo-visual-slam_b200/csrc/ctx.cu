@@ -45,9 +45,12 @@ extern "C" int vslam_ctx_create(const vslam_config* cfg, vslam_ctx** out) {
         return VSLAM_E_CUDA;
     }
     ctx->stream = ctx->own_stream;
-    int st = vslam_match_init(ctx);
+    ctx->trec = (TimingRec*)calloc(VSLAM_TIMING_CAP, sizeof(TimingRec));
+    int st = ctx->trec ? VSLAM_OK : VSLAM_E_INVALID;
+    if (st == VSLAM_OK) st = vslam_match_init(ctx);
     if (st == VSLAM_OK) st = vslam_orb_init(ctx);
     if (st == VSLAM_OK) st = vslam_ba_init(ctx);
+    if (st == VSLAM_OK) st = vslam_front_init(ctx);
     if (st != VSLAM_OK) {
         vslam_ctx_destroy(ctx);
         return st;
@@ -60,9 +63,17 @@ extern "C" void vslam_ctx_destroy(vslam_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
+    vslam_front_free(ctx);
     vslam_ba_free(ctx);
     vslam_orb_free(ctx);
     vslam_match_free(ctx);
+    if (ctx->trec) {
+        for (int i = 0; i < ctx->n_trec_alloc; ++i) {
+            cudaEventDestroy(ctx->trec[i].a);
+            cudaEventDestroy(ctx->trec[i].b);
+        }
+        free(ctx->trec);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     free(ctx);
 }
@@ -80,3 +91,43 @@ extern "C" int vslam_ctx_synchronize(vslam_ctx* ctx) {
 }
 
 extern "C" int64_t vslam_ctx_launch_count(const vslam_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- optional per-launch timing (CUDA events on the launching stream) -------------------------------------
+static const char* const k_kernel_names[VK_COUNT] = {
+    "resize_level_kernel", "fast_kernel", "harris_select_kernel", "blur_kernel", "anms_kernel", "describe_kernel",
+    "hamming_argmin_kernel", "crosscheck_gate_compact_kernel", "triangulate_kernel", "ba_build_kernel",
+    "ba_solve_kernel", "ba_update_kernel", "ba_misc_kernel", "pnp_kernel"};
+
+extern "C" int vslam_kernel_count(void) { return VK_COUNT; }
+extern "C" const char* vslam_kernel_name(int id) { return id >= 0 && id < VK_COUNT ? k_kernel_names[id] : ""; }
+
+extern "C" int vslam_ctx_timing_enable(vslam_ctx* ctx, int on) {
+    if (!ctx) return VSLAM_E_INVALID;
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->timing_on = on ? 1 : 0;
+    ctx->n_trec = 0;
+    for (int i = 0; i < VK_COUNT; ++i) {
+        ctx->t_ms[i] = 0;
+        ctx->t_launches[i] = 0;
+    }
+    return VSLAM_OK;
+}
+
+// synchronise, fold the pending event pairs into per-kernel totals and report kernel `id`
+extern "C" int vslam_ctx_timing_read(vslam_ctx* ctx, int id, double* total_ms, int64_t* launches) {
+    if (!ctx || id < 0 || id >= VK_COUNT) return VSLAM_E_INVALID;
+    if (ctx->n_trec > 0) {
+        VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < ctx->n_trec; ++i) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ctx->trec[i].a, ctx->trec[i].b) == cudaSuccess) {
+                ctx->t_ms[ctx->trec[i].id] += ms;
+                ctx->t_launches[ctx->trec[i].id]++;
+            }
+        }
+        ctx->n_trec = 0;
+    }
+    if (total_ms) *total_ms = ctx->t_ms[id];
+    if (launches) *launches = ctx->t_launches[id];
+    return VSLAM_OK;
+}

@@ -1,0 +1,322 @@
+// K11 (per-match DLT triangulation + depth gates) and the batched stereo frontend
+// (ORB on left and right images -> L<->R Hamming matching -> triangulation), all device-resident.
+//
+// Role in the reference: VO::disparity_map + Frame::find_3d + VO::set_ref_3d_position
+// (/root/reference/src/stereo_visual_slam_main/visual_odometry.cpp:159-217, types_def.cpp:9-18) turn the keypoints of a
+// frame into world points with the gates 10 < Z < 400 (usable) and Z < 40 (reliable depth).  The reference gets Z from
+// a dense SGBM disparity; the north star replaces that with sparse stereo: ORB on both images, the reference's own
+// feature_matching (cross-check + distance gate, visual_odometry.cpp:219-251) between left and right descriptors and a
+// per-match DLT whose arithmetic oracle is cv::triangulatePoints (SVD of the 4x4 system; one-sided Jacobi here, the
+// scheme OpenCV's JacobiSVD uses).  fp64 throughout; world = T_c_w^-1 * p narrowed to float32 like cv::Point3f.
+#include "common.cuh"
+
+#include <stdlib.h>
+
+struct FrontState {
+    // host-buffer staging for vslam_stereo_frontend_batch / vslam_triangulate
+    uint8_t* d_img;  // [2 * pairs][h][pitch] left images first, then right
+    int pitch;
+    vslam_keypoint* d_kp;
+    uint8_t* d_desc;
+    int32_t* d_nkp;
+    vslam_dmatch* d_match;
+    int32_t* d_nmatch;
+    float* d_xyz;
+    uint8_t* d_flags;
+    double* d_cam;   // P1 (12) P2 (12)
+    double* d_pose;  // [pairs][12]
+    float* d_xl;     // vslam_triangulate staging
+    float* d_xr;
+    int max_pairs, kp_cap;
+};
+
+struct Cam24 {
+    double p[24];
+};
+
+// One-sided (Hestenes) Jacobi SVD of the 4x4 DLT matrix; returns the right singular vector of the smallest
+// singular value.  Fully unrolled so A and V stay in registers.
+__device__ __forceinline__ void dlt_null_vector(double A[4][4], double X[4]) {
+    double V[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        bool changed = false;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int j = i + 1; j < 4; ++j) {
+                double a = 0, b = 0, p = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    a += A[k][i] * A[k][i];
+                    b += A[k][j] * A[k][j];
+                    p += A[k][i] * A[k][j];
+                }
+                if (fabs(p) <= 2.220446049250313e-16 * sqrt(a * b)) continue;
+                changed = true;
+                p *= 2;
+                const double beta = a - b, gamma = hypot(p, beta);
+                double c, s;
+                if (beta < 0) {
+                    const double delta = (gamma - beta) * 0.5;
+                    s = sqrt(delta / gamma);
+                    c = p / (gamma * s * 2);
+                } else {
+                    c = sqrt((gamma + beta) / (gamma * 2));
+                    s = p / (gamma * c * 2);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double t0 = c * A[k][i] + s * A[k][j], t1 = -s * A[k][i] + c * A[k][j];
+                    A[k][i] = t0;
+                    A[k][j] = t1;
+                    const double v0 = c * V[k][i] + s * V[k][j], v1 = -s * V[k][i] + c * V[k][j];
+                    V[k][i] = v0;
+                    V[k][j] = v1;
+                }
+            }
+        }
+        if (!changed) break;
+    }
+    double best = 1e300;
+    int bi = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        double n = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) n += A[k][j] * A[k][j];
+        if (n < best) {
+            best = n;
+            bi = j;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) X[k] = bi == 0 ? V[k][0] : bi == 1 ? V[k][1] : bi == 2 ? V[k][2] : V[k][3];
+}
+
+__device__ __forceinline__ void triangulate_one(float xlx, float xly, float xrx, float xry, const double* P1,
+                                                const double* P2, const double* T, float* xyz, uint8_t* flags) {
+    double A[4][4];
+    const double xl = xlx, yl = xly, xr = xrx, yr = xry;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        A[0][k] = xl * P1[8 + k] - P1[k];
+        A[1][k] = yl * P1[8 + k] - P1[4 + k];
+        A[2][k] = xr * P2[8 + k] - P2[k];
+        A[3][k] = yr * P2[8 + k] - P2[4 + k];
+    }
+    double X[4];
+    dlt_null_vector(A, X);
+    const double iw = 1.0 / X[3];
+    const double px = X[0] * iw, py = X[1] * iw, pz = X[2] * iw;
+    // set_ref_3d_position gates (visual_odometry.cpp:194,201)
+    const bool usable = pz > 10.0 && pz < 400.0;
+    const bool reliable = usable && pz < 40.0;
+    // world = T_c_w^-1 * p = R^T (p - t)   (types_def.cpp:17)
+    double wx = px, wy = py, wz = pz;
+    if (T) {
+        const double dx = px - T[3], dy = py - T[7], dz = pz - T[11];
+        wx = T[0] * dx + T[4] * dy + T[8] * dz;
+        wy = T[1] * dx + T[5] * dy + T[9] * dz;
+        wz = T[2] * dx + T[6] * dy + T[10] * dz;
+    }
+    xyz[0] = (float)wx;
+    xyz[1] = (float)wy;
+    xyz[2] = (float)wz;
+    *flags = (uint8_t)((usable ? 1 : 0) | (reliable ? 2 : 0));
+}
+
+__global__ void __launch_bounds__(128)
+triangulate_matches_kernel(const vslam_keypoint* __restrict__ kp_left, const vslam_keypoint* __restrict__ kp_right,
+                           int kp_stride, const vslam_dmatch* __restrict__ matches,
+                           const int32_t* __restrict__ n_matches, int match_stride, const Cam24 cam,
+                           const double* __restrict__ poses, float* __restrict__ xyz, uint8_t* __restrict__ flags) {
+    const int pair = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_matches[pair]) return;
+    const vslam_dmatch m = matches[(size_t)pair * match_stride + i];
+    const vslam_keypoint* kl = kp_left + (size_t)pair * kp_stride + m.queryIdx;
+    const vslam_keypoint* kr = kp_right + (size_t)pair * kp_stride + m.trainIdx;
+    triangulate_one(kl->x, kl->y, kr->x, kr->y, cam.p, cam.p + 12, poses ? poses + 12 * pair : nullptr,
+                    xyz + ((size_t)pair * match_stride + i) * 3, flags + (size_t)pair * match_stride + i);
+}
+
+__global__ void __launch_bounds__(128)
+triangulate_points_kernel(const float* __restrict__ xl, const float* __restrict__ xr, int n, const Cam24 cam,
+                          const double* __restrict__ pose, float* __restrict__ xyz, uint8_t* __restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    triangulate_one(xl[2 * i], xl[2 * i + 1], xr[2 * i], xr[2 * i + 1], cam.p, cam.p + 12, pose, xyz + 3 * i, flags + i);
+}
+
+int vslam_front_init(vslam_ctx* ctx) {
+    FrontState* f = (FrontState*)calloc(1, sizeof(FrontState));
+    if (!f) return VSLAM_E_INVALID;
+    ctx->front = f;
+    const vslam_config& c = ctx->cfg;
+    f->max_pairs = c.max_images / 2;
+    f->kp_cap = c.max_keypoints;
+    if (c.max_images <= 0 || c.max_width <= 0 || c.max_height <= 0 || c.max_keypoints <= 0) return VSLAM_OK;
+    const size_t ni = (size_t)c.max_images, np = (size_t)(f->max_pairs > 0 ? f->max_pairs : 1), cap = (size_t)f->kp_cap;
+    f->pitch = (c.max_width + 15) & ~15;
+    VSLAM_CUDA(ctx, cudaMalloc(&f->d_img, ni * f->pitch * c.max_height));
+    VSLAM_CUDA(ctx, cudaMalloc(&f->d_kp, ni * cap * sizeof(vslam_keypoint)));
+    VSLAM_CUDA(ctx, cudaMalloc(&f->d_desc, ni * cap * 32));
+    VSLAM_CUDA(ctx, cudaMalloc(&f->d_nkp, ni * sizeof(int32_t)));
+    VSLAM_CUDA(ctx, cudaMalloc(&f->d_match, np * cap * sizeof(vslam_dmatch)));
+    VSLAM_CUDA(ctx, cudaMalloc(&f->d_nmatch, np * sizeof(int32_t)));
+    VSLAM_CUDA(ctx, cudaMalloc(&f->d_xyz, np * cap * 3 * sizeof(float)));
+    VSLAM_CUDA(ctx, cudaMalloc(&f->d_flags, np * cap));
+    VSLAM_CUDA(ctx, cudaMalloc(&f->d_pose, np * 12 * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&f->d_xl, cap * 2 * sizeof(float)));
+    VSLAM_CUDA(ctx, cudaMalloc(&f->d_xr, cap * 2 * sizeof(float)));
+    return VSLAM_OK;
+}
+
+void vslam_front_free(vslam_ctx* ctx) {
+    FrontState* f = ctx->front;
+    if (!f) return;
+    cudaFree(f->d_img);
+    cudaFree(f->d_kp);
+    cudaFree(f->d_desc);
+    cudaFree(f->d_nkp);
+    cudaFree(f->d_match);
+    cudaFree(f->d_nmatch);
+    cudaFree(f->d_xyz);
+    cudaFree(f->d_flags);
+    cudaFree(f->d_pose);
+    cudaFree(f->d_xl);
+    cudaFree(f->d_xr);
+    free(f);
+    ctx->front = nullptr;
+}
+
+extern "C" int vslam_triangulate(vslam_ctx* ctx, const float* xl, const float* xr, int n, const double* P1,
+                                 const double* P2, const double* T_c_w, float* xyz_world, uint8_t* flags) {
+    if (!ctx || n < 0 || !P1 || !P2) return VSLAM_E_INVALID;
+    if (n == 0) return VSLAM_OK;
+    if (!xl || !xr || !xyz_world || !flags) return VSLAM_E_INVALID;
+    FrontState* f = ctx->front;
+    if (!f || !f->d_xl || n > f->kp_cap) return VSLAM_E_CAPACITY;
+    cudaStream_t s = ctx->stream;
+    Cam24 cam;
+    memcpy(cam.p, P1, 96);
+    memcpy(cam.p + 12, P2, 96);
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(f->d_xl, xl, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(f->d_xr, xr, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    if (T_c_w) VSLAM_CUDA(ctx, cudaMemcpyAsync(f->d_pose, T_c_w, 96, cudaMemcpyHostToDevice, s));
+    vslam_time_begin(ctx, VK_TRIANGULATE);
+    triangulate_points_kernel<<<ceil_div(n, 128), 128, 0, s>>>(f->d_xl, f->d_xr, n, cam, T_c_w ? f->d_pose : nullptr,
+                                                              f->d_xyz, f->d_flags);
+    vslam_time_end(ctx);
+    VSLAM_LAUNCH_CHECK(ctx, "triangulate_points_kernel");
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(xyz_world, f->d_xyz, (size_t)n * 12, cudaMemcpyDeviceToHost, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(flags, f->d_flags, (size_t)n, cudaMemcpyDeviceToHost, s));
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(s));
+    return VSLAM_OK;
+}
+
+extern "C" int vslam_triangulate_matches_batch_dev(vslam_ctx* ctx, const vslam_keypoint* d_kp_left,
+                                                   const vslam_keypoint* d_kp_right, int kp_stride,
+                                                   const vslam_dmatch* d_matches, const int32_t* d_n_matches,
+                                                   int match_stride, int batch, const double* P1, const double* P2,
+                                                   const double* d_T_c_w, float* d_xyz, uint8_t* d_flags) {
+    if (!ctx || !d_kp_left || !d_kp_right || !d_matches || !d_n_matches || !P1 || !P2 || !d_xyz || !d_flags)
+        return VSLAM_E_INVALID;
+    if (batch <= 0 || match_stride <= 0) return VSLAM_E_INVALID;
+    Cam24 cam;
+    memcpy(cam.p, P1, 96);
+    memcpy(cam.p + 12, P2, 96);
+    dim3 grid(ceil_div(match_stride, 128), batch);
+    vslam_time_begin(ctx, VK_TRIANGULATE);
+    triangulate_matches_kernel<<<grid, 128, 0, ctx->stream>>>(d_kp_left, d_kp_right, kp_stride, d_matches, d_n_matches,
+                                                             match_stride, cam, d_T_c_w, d_xyz, d_flags);
+    vslam_time_end(ctx);
+    VSLAM_LAUNCH_CHECK(ctx, "triangulate_matches_kernel");
+    return VSLAM_OK;
+}
+
+// ORB(left) + ORB(right) + feature_matching(left -> right) + triangulation, everything enqueued on the stream.
+extern "C" int vslam_stereo_frontend_batch_dev(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_right,
+                                               int n_pairs, int width, int height, int row_pitch,
+                                               long long image_stride, int nfeatures, int anms_keep, float anms_c,
+                                               double gate_rel, double gate_abs, const double* P1, const double* P2,
+                                               const double* d_T_c_w, vslam_keypoint* d_kp, uint8_t* d_desc,
+                                               int32_t* d_n_kp, vslam_dmatch* d_matches, int32_t* d_n_matches,
+                                               float* d_xyz, uint8_t* d_flags) {
+    if (!ctx || !d_left || !d_right || !P1 || !P2 || !d_kp || !d_desc || !d_n_kp || !d_matches || !d_n_matches ||
+        !d_xyz || !d_flags)
+        return VSLAM_E_INVALID;
+    if (n_pairs <= 0 || width <= 0 || height <= 0 || row_pitch < width) return VSLAM_E_INVALID;
+    if (2 * n_pairs > ctx->cfg.max_images) return VSLAM_E_CAPACITY;
+    const int cap = ctx->cfg.max_keypoints;
+    ImgSrc src;
+    src.base[0] = d_left;
+    src.base[1] = d_right;
+    src.img_stride = image_stride;
+    src.pitch = row_pitch;
+    src.per_base = n_pairs;
+    int st = vslam_orb_enqueue(ctx, src, 2 * n_pairs, width, height, nfeatures, anms_keep, anms_c, d_kp, d_desc, d_n_kp);
+    if (st != VSLAM_OK) return st;
+    // query = left descriptors (images 0..n_pairs-1), train = right descriptors (images n_pairs..2*n_pairs-1)
+    st = vslam_match_hamming_batch_dev(ctx, d_desc, d_n_kp, cap, d_desc + (size_t)n_pairs * cap * 32, d_n_kp + n_pairs,
+                                       cap, n_pairs, cap, 1, gate_rel, gate_abs, d_matches, cap, d_n_matches);
+    if (st != VSLAM_OK) return st;
+    return vslam_triangulate_matches_batch_dev(ctx, d_kp, d_kp + (size_t)n_pairs * cap, cap, d_matches, d_n_matches, cap,
+                                               n_pairs, P1, P2, d_T_c_w, d_xyz, d_flags);
+}
+
+// Host-buffer form (the call a user of the library makes): images come from host memory (pinned memory makes the
+// copies asynchronous DMA), results are copied back, one synchronisation at the end.  Outputs use the same strides as
+// the device form (cap = vslam_orb_keypoint_capacity(ctx)): kp [2*n_pairs][cap], desc [2*n_pairs][cap][32],
+// n_kp [2*n_pairs], matches [n_pairs][cap], n_matches [n_pairs], xyz [n_pairs][cap][3], flags [n_pairs][cap].
+extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_pairs,
+                                           int width, int height, int row_pitch, long long image_stride, int nfeatures,
+                                           int anms_keep, float anms_c, double gate_rel, double gate_abs,
+                                           const double* P1, const double* P2, const double* T_c_w,
+                                           vslam_keypoint* kp, uint8_t* desc, int32_t* n_kp, vslam_dmatch* matches,
+                                           int32_t* n_matches, float* xyz, uint8_t* flags) {
+    if (!ctx || !n_kp || !n_matches) return VSLAM_E_INVALID;
+    if (!left || !right) return VSLAM_E_INVALID;  // reference: -1 "Could not open or find the image"
+    if (!P1 || !P2 || !kp || !desc || !matches || !xyz || !flags) return VSLAM_E_INVALID;
+    FrontState* f = ctx->front;
+    if (!f || !f->d_img) return VSLAM_E_CAPACITY;
+    if (n_pairs <= 0 || n_pairs > f->max_pairs) return VSLAM_E_CAPACITY;
+    if (width <= 0 || height <= 0 || row_pitch < width) return VSLAM_E_INVALID;
+    if (width > ctx->cfg.max_width || height > ctx->cfg.max_height) return VSLAM_E_CAPACITY;
+    cudaStream_t s = ctx->stream;
+    const size_t dstride = (size_t)f->pitch * height;
+    uint8_t* dl = f->d_img;
+    uint8_t* dr = f->d_img + (size_t)n_pairs * dstride;
+    if (image_stride == (long long)row_pitch * height) {
+        VSLAM_CUDA(ctx, cudaMemcpy2DAsync(dl, f->pitch, left, row_pitch, width, (size_t)height * n_pairs,
+                                          cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpy2DAsync(dr, f->pitch, right, row_pitch, width, (size_t)height * n_pairs,
+                                          cudaMemcpyHostToDevice, s));
+    } else {
+        for (int i = 0; i < n_pairs; ++i) {
+            VSLAM_CUDA(ctx, cudaMemcpy2DAsync(dl + i * dstride, f->pitch, left + (size_t)i * image_stride, row_pitch,
+                                              width, height, cudaMemcpyHostToDevice, s));
+            VSLAM_CUDA(ctx, cudaMemcpy2DAsync(dr + i * dstride, f->pitch, right + (size_t)i * image_stride, row_pitch,
+                                              width, height, cudaMemcpyHostToDevice, s));
+        }
+    }
+    if (T_c_w) VSLAM_CUDA(ctx, cudaMemcpyAsync(f->d_pose, T_c_w, (size_t)n_pairs * 96, cudaMemcpyHostToDevice, s));
+    int st = vslam_stereo_frontend_batch_dev(ctx, dl, dr, n_pairs, width, height, f->pitch, (long long)dstride,
+                                             nfeatures, anms_keep, anms_c, gate_rel, gate_abs, P1, P2,
+                                             T_c_w ? f->d_pose : nullptr, f->d_kp, f->d_desc, f->d_nkp, f->d_match,
+                                             f->d_nmatch, f->d_xyz, f->d_flags);
+    if (st != VSLAM_OK) return st;
+    const size_t cap = (size_t)f->kp_cap, ni = 2 * (size_t)n_pairs, np = (size_t)n_pairs;
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(kp, f->d_kp, ni * cap * sizeof(vslam_keypoint), cudaMemcpyDeviceToHost, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(desc, f->d_desc, ni * cap * 32, cudaMemcpyDeviceToHost, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(n_kp, f->d_nkp, ni * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(matches, f->d_match, np * cap * sizeof(vslam_dmatch), cudaMemcpyDeviceToHost, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(n_matches, f->d_nmatch, np * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(xyz, f->d_xyz, np * cap * 12, cudaMemcpyDeviceToHost, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(flags, f->d_flags, np * cap, cudaMemcpyDeviceToHost, s));
+    return vslam_orb_check_flags(ctx, (int)ni);  // synchronises; VSLAM_E_OVERFLOW if a work list overflowed
+}

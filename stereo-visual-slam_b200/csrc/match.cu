@@ -235,11 +235,15 @@ extern "C" int vslam_match_hamming_batch_dev(vslam_ctx* ctx, const uint8_t* d_qu
     if (((uintptr_t)d_query | (uintptr_t)d_train) & 15) return VSLAM_E_INVALID;
     VSLAM_CUDA(ctx, cudaMemsetAsync(m->d_keys, 0xFF, (size_t)batch * 2 * m->max_rows * sizeof(uint32_t), ctx->stream));
     dim3 grid(ceil_div(max_rows, MT_TILE_Q), ceil_div(max_rows, MT_TILE_T), batch);
+    vslam_time_begin(ctx, VK_HAMMING_ARGMIN);
     hamming_argmin_kernel<<<grid, MT_THREADS, 0, ctx->stream>>>(d_query, d_nq, q_stride_rows, d_train, d_nt,
                                                                 t_stride_rows, m->d_keys, m->max_rows);
+    vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "hamming_argmin_kernel");
+    vslam_time_begin(ctx, VK_CROSSCHECK);
     crosscheck_gate_compact_kernel<<<batch, CC_THREADS, 0, ctx->stream>>>(
         d_nq, d_nt, m->d_keys, m->max_rows, cross_check, gate_rel, gate_abs, d_out, out_stride, d_n_out);
+    vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "crosscheck_gate_compact_kernel");
     return VSLAM_OK;
 }

@@ -54,14 +54,6 @@ struct OrbQuota {
     int n[ORB_NL];
 };
 
-// Level 0 is read in place from the caller's buffers (left images first, then right images).
-struct ImgSrc {
-    const uint8_t* base[2];
-    long long img_stride;  // bytes between consecutive images of one base
-    int pitch;             // bytes between rows
-    int per_base;          // images per base pointer
-};
-
 struct ImgCounters {
     uint32_t hist[ORB_NL][256];
     uint32_t cand_cnt[ORB_NL];
@@ -902,7 +894,7 @@ void vslam_orb_free(vslam_ctx* ctx) {
 }
 
 // Enqueue the whole ORB pipeline for n_img images on the context stream (no host synchronisation).
-static int orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h, int nfeatures, int anms_keep,
+int vslam_orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h, int nfeatures, int anms_keep,
                        float anms_c, vslam_keypoint* d_kp, uint8_t* d_desc, int32_t* d_n) {
     OrbState* o = ctx->orb;
     if (!o || !o->d_pyr) return VSLAM_E_CAPACITY;
@@ -919,28 +911,40 @@ static int orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int 
     VSLAM_CUDA(ctx, cudaMemsetAsync(o->d_cnt, 0, (size_t)n_img * sizeof(ImgCounters), s));
     for (int l = 1; l < ORB_NL; ++l) {
         dim3 grid(ceil_div(g.lv[l].w, 32), ceil_div(g.lv[l].h, 8), n_img);
+        vslam_time_begin(ctx, VK_RESIZE);
         resize_level_kernel<<<grid, dim3(32, 8), 0, s>>>(src, o->d_pyr, o->d_tab, g, l);
+        vslam_time_end(ctx);
         VSLAM_LAUNCH_CHECK(ctx, "resize_level_kernel");
     }
+    vslam_time_begin(ctx, VK_FAST);
     fast_kernel<<<dim3(g.total_tiles, n_img), FAST_THREADS, 0, s>>>(src, o->d_pyr, g, o->d_cand, o->d_cnt);
+    vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "fast_kernel");
+    vslam_time_begin(ctx, VK_HARRIS_SELECT);
     harris_select_kernel<<<dim3(ORB_NL, n_img), HS_THREADS, SORT_CAP * sizeof(unsigned long long), s>>>(
         src, o->d_pyr, g, q, o->d_cand, o->d_cnt, o->d_sel);
+    vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "harris_select_kernel");
+    vslam_time_begin(ctx, VK_BLUR);
     blur_kernel<<<dim3(g.total_tiles, n_img), 256, 0, s>>>(src, o->d_pyr, o->d_blur, g);
+    vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "blur_kernel");
     const int use_keep = anms_keep > 0 ? 1 : 0;
     if (use_keep) {
         int n2 = 1;
         while (n2 < o->kp_cap) n2 <<= 1;
         if ((size_t)n2 * 8 > 65536) return VSLAM_E_CAPACITY;
+        vslam_time_begin(ctx, VK_ANMS);
         anms_kernel<<<n_img, ANMS_THREADS, (size_t)n2 * 8, s>>>(g, o->d_sel, o->d_cnt, o->kp_cap, anms_keep, anms_c,
                                                                o->d_rad, o->d_keep);
+        vslam_time_end(ctx);
         VSLAM_LAUNCH_CHECK(ctx, "anms_kernel");
     }
+    vslam_time_begin(ctx, VK_DESCRIBE);
     describe_kernel<<<dim3(ceil_div(o->kp_cap, DESC_WARPS), n_img), DESC_WARPS * 32, 0, s>>>(
         src, o->d_pyr, o->d_blur, g, o->d_sel, o->d_cnt, o->d_keep, use_keep, o->d_pattern, o->kp_cap, d_kp, d_desc,
         d_n);
+    vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "describe_kernel");
     return VSLAM_OK;
 }
@@ -959,11 +963,11 @@ extern "C" int vslam_orb_detect_compute_batch_dev(vslam_ctx* ctx, const uint8_t*
     src.img_stride = image_stride;
     src.pitch = row_pitch;
     src.per_base = n_images > 0 ? n_images : 1;
-    return orb_enqueue(ctx, src, n_images, width, height, nfeatures, anms_keep, anms_c, d_kp, d_desc, d_n);
+    return vslam_orb_enqueue(ctx, src, n_images, width, height, nfeatures, anms_keep, anms_c, d_kp, d_desc, d_n);
 }
 
 // flags raised by the kernels (bit0 candidate overflow, bit1 sort overflow, bit2 keypoint capacity)
-static int orb_check_flags(vslam_ctx* ctx, int n_img) {
+int vslam_orb_check_flags(vslam_ctx* ctx, int n_img) {
     OrbState* o = ctx->orb;
     for (int i = 0; i < n_img; ++i) {
         VSLAM_CUDA(ctx, cudaMemcpyAsync(&o->h_cnt[i].flags, &o->d_cnt[i].flags, sizeof(uint32_t), cudaMemcpyDeviceToHost,
@@ -977,7 +981,7 @@ static int orb_check_flags(vslam_ctx* ctx, int n_img) {
 
 extern "C" int vslam_orb_last_flags(vslam_ctx* ctx, int n_images) {
     if (!ctx || !ctx->orb) return VSLAM_E_INVALID;
-    return orb_check_flags(ctx, n_images);
+    return vslam_orb_check_flags(ctx, n_images);
 }
 
 extern "C" int vslam_orb_detect_compute_batch(vslam_ctx* ctx, const uint8_t* images, int n_images, int width,
@@ -1003,10 +1007,10 @@ extern "C" int vslam_orb_detect_compute_batch(vslam_ctx* ctx, const uint8_t* ima
     src.img_stride = (long long)dstride;
     src.pitch = o->in_pitch;
     src.per_base = n_images;
-    int st = orb_enqueue(ctx, src, n_images, width, height, nfeatures, anms_keep, anms_c, o->d_kp, o->d_desc, o->d_n);
+    int st = vslam_orb_enqueue(ctx, src, n_images, width, height, nfeatures, anms_keep, anms_c, o->d_kp, o->d_desc, o->d_n);
     if (st != VSLAM_OK) return st;
     VSLAM_CUDA(ctx, cudaMemcpyAsync(o->h_n, o->d_n, n_images * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    st = orb_check_flags(ctx, n_images);  // synchronises
+    st = vslam_orb_check_flags(ctx, n_images);  // synchronises
     if (st != VSLAM_OK) return st;
     for (int i = 0; i < n_images; ++i) {
         const int n = o->h_n[i];

@@ -49,6 +49,10 @@ SIGNATURES = {
     "vslam_ctx_set_stream": (_i, [_vp, _vp]),
     "vslam_ctx_synchronize": (_i, [_vp]),
     "vslam_ctx_launch_count": (_i64, [_vp]),
+    "vslam_kernel_count": (_i, []),
+    "vslam_kernel_name": (C.c_char_p, [_i]),
+    "vslam_ctx_timing_enable": (_i, [_vp, _i]),
+    "vslam_ctx_timing_read": (_i, [_vp, _i, C.POINTER(_d), C.POINTER(_i64)]),
     "vslam_match_hamming": (_i, [_vp, _vp, _i, _vp, _i, _i, _d, _d, _vp, _pi]),
     "vslam_orb_keypoint_capacity": (_i, [_vp]),
     "vslam_orb_detect_compute": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
@@ -56,6 +60,12 @@ SIGNATURES = {
     "vslam_orb_detect_compute_batch_dev": (_i, [_vp, _vp, _i, _i, _i, _i, C.c_longlong, _i, _i, _f, _vp, _vp, _vp]),
     "vslam_orb_last_flags": (_i, [_vp, _i]),
     "vslam_orb_debug_read": (_i, [_vp, _i, _i, _vp, _vp, _pi, _pi, _vp, _i, _pi]),
+    "vslam_triangulate": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "vslam_triangulate_matches_batch_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "vslam_stereo_frontend_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_longlong, _i, _i, _f, _d, _d, _vp, _vp, _vp,
+                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vslam_stereo_frontend_batch_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_longlong, _i, _i, _f, _d, _d, _vp, _vp,
+                                             _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vslam_match_hamming_batch_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _d, _d, _vp, _i, _vp]),
 }
 
@@ -125,6 +135,19 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.vslam_ctx_launch_count(self.h))
 
+    def timing_enable(self, on: bool = True):
+        self.check(self.lib.vslam_ctx_timing_enable(self.h, int(on)), "timing_enable")
+
+    def timing_read(self) -> dict:
+        """{kernel name: (total device ms, launches)} since timing_enable (CUDA events on the launching stream)."""
+        out = {}
+        for i in range(self.lib.vslam_kernel_count()):
+            ms, n = C.c_double(0), C.c_int64(0)
+            self.check(self.lib.vslam_ctx_timing_read(self.h, i, C.byref(ms), C.byref(n)), "timing_read")
+            if n.value:
+                out[self.lib.vslam_kernel_name(i).decode()] = (ms.value, n.value)
+        return out
+
     # ---- K10 --------------------------------------------------------------------------------
     def match_hamming(self, query: np.ndarray, train: np.ndarray, cross_check: bool = True,
                       gate_rel: float = -1.0, gate_abs: float = 0.0) -> np.ndarray:
@@ -193,3 +216,61 @@ class Context:
         self.check(self.lib.vslam_orb_debug_read(self.h, img, level, _ptr(lv), _ptr(bl), C.byref(w), C.byref(hh),
                                                  _ptr(cand), nc.value, C.byref(nc)), "vslam_orb_debug_read")
         return (lv if level > 0 else None), bl, cand[:nc.value]
+
+    # ---- K11 + frontend ---------------------------------------------------------------------
+    def triangulate(self, xl, xr, P1, P2, T_c_w=None):
+        """(xyz_world float32 [n,3], flags u8 [n]) -- see vslam_triangulate."""
+        xl = np.ascontiguousarray(xl, dtype=np.float32).reshape(-1, 2)
+        xr = np.ascontiguousarray(xr, dtype=np.float32).reshape(-1, 2)
+        P1 = np.ascontiguousarray(P1, dtype=np.float64).reshape(12)
+        P2 = np.ascontiguousarray(P2, dtype=np.float64).reshape(12)
+        T = None if T_c_w is None else np.ascontiguousarray(T_c_w, dtype=np.float64).reshape(12)
+        n = len(xl)
+        xyz = np.zeros((max(n, 1), 3), dtype=np.float32)
+        fl = np.zeros(max(n, 1), dtype=np.uint8)
+        st = self.lib.vslam_triangulate(self.h, _ptr(xl), _ptr(xr), n, _ptr(P1), _ptr(P2), _ptr(T), _ptr(xyz), _ptr(fl))
+        self.check(st, "vslam_triangulate")
+        return xyz[:n], fl[:n]
+
+    def stereo_frontend(self, left, right, P1, P2, T_c_w=None, nfeatures=2000, anms_keep=0, anms_c=1.11,
+                        gate_rel=2.0, gate_abs=30.0, out=None):
+        """Host-buffer batched frontend.  left/right: [B,H,W] u8 numpy arrays or pinned torch tensors.
+        Returns a dict of full-stride numpy arrays (see include/vslam_b200.h) plus per-pair views."""
+        is_np = isinstance(left, np.ndarray)
+        if is_np:
+            left = np.ascontiguousarray(left, dtype=np.uint8)
+            right = np.ascontiguousarray(right, dtype=np.uint8)
+        b, h, w = left.shape
+        cap = self.kp_cap
+        if out is None:
+            out = self.alloc_frontend_outputs(b)
+        P1 = np.ascontiguousarray(P1, dtype=np.float64).reshape(12)
+        P2 = np.ascontiguousarray(P2, dtype=np.float64).reshape(12)
+        T = None if T_c_w is None else np.ascontiguousarray(T_c_w, dtype=np.float64).reshape(b, 12)
+        st = self.lib.vslam_stereo_frontend_batch(
+            self.h, _ptr(left), _ptr(right), b, w, h, w, h * w, int(nfeatures), int(anms_keep), float(anms_c),
+            float(gate_rel), float(gate_abs), _ptr(P1), _ptr(P2), _ptr(T), _ptr(out["kp"]), _ptr(out["desc"]),
+            _ptr(out["n_kp"]), _ptr(out["matches"]), _ptr(out["n_matches"]), _ptr(out["xyz"]), _ptr(out["flags"]))
+        self.check(st, "vslam_stereo_frontend_batch")
+        return out
+
+    def alloc_frontend_outputs(self, n_pairs: int):
+        cap = self.kp_cap
+        return dict(kp=np.zeros((2 * n_pairs, cap), dtype=KEYPOINT_DTYPE),
+                    desc=np.zeros((2 * n_pairs, cap, 32), dtype=np.uint8),
+                    n_kp=np.zeros(2 * n_pairs, dtype=np.int32),
+                    matches=np.zeros((n_pairs, cap), dtype=DMATCH_DTYPE),
+                    n_matches=np.zeros(n_pairs, dtype=np.int32),
+                    xyz=np.zeros((n_pairs, cap, 3), dtype=np.float32),
+                    flags=np.zeros((n_pairs, cap), dtype=np.uint8))
+
+    def stereo_frontend_dev(self, d_left, d_right, n_pairs, w, h, pitch, img_stride, P1, P2, d_T, d_kp, d_desc, d_n_kp,
+                            d_matches, d_n_matches, d_xyz, d_flags, nfeatures=2000, anms_keep=0, anms_c=1.11,
+                            gate_rel=2.0, gate_abs=30.0):
+        P1 = np.ascontiguousarray(P1, dtype=np.float64).reshape(12)
+        P2 = np.ascontiguousarray(P2, dtype=np.float64).reshape(12)
+        st = self.lib.vslam_stereo_frontend_batch_dev(
+            self.h, _ptr(d_left), _ptr(d_right), n_pairs, w, h, pitch, img_stride, int(nfeatures), int(anms_keep),
+            float(anms_c), float(gate_rel), float(gate_abs), _ptr(P1), _ptr(P2), _ptr(d_T), _ptr(d_kp), _ptr(d_desc),
+            _ptr(d_n_kp), _ptr(d_matches), _ptr(d_n_matches), _ptr(d_xyz), _ptr(d_flags))
+        self.check(st, "vslam_stereo_frontend_batch_dev")

@@ -1,0 +1,100 @@
+"""GPU parity: K11 triangulation and the batched stereo frontend (detect + match + triangulate) vs the oracle."""
+import numpy as np
+import pytest
+
+from oracle import orb_restate as R
+from oracle import vo_restate as V
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-4  # north star: poses / landmarks within 1e-4 relative
+
+
+def _cams(pkg):
+    s = pkg.synth
+    return V.stereo_projection_matrices(s.FX, s.FY, s.CX, s.CY, s.BASELINE_M)
+
+
+def test_triangulate_vs_cv2_and_oracle(pkg, gpu_ctx):
+    import cv2
+    rng = np.random.default_rng(0)
+    P1, P2 = _cams(pkg)
+    n = 3000
+    xl = np.stack([rng.uniform(50, 1200, n), rng.uniform(20, 350, n)], 1).astype(np.float32)
+    disp = rng.uniform(0.8, 90, n).astype(np.float32)     # Z from 4.6 m to 515 m: both gates exercised
+    xr = xl.copy()
+    xr[:, 0] -= disp
+    xr[:, 1] += rng.normal(0, 0.5, n).astype(np.float32)  # imperfect epipolar alignment
+    T = np.hstack([pkg.synth.se3_exp(np.array([0.3, -0.1, 2.0, 0.02, -0.3, 0.01]))[0],
+                   np.array([[0.5], [-0.2], [3.0]])])
+    xyz, fl = gpu_ctx.triangulate(xl, xr, P1, P2, T)
+    X = cv2.triangulatePoints(P1, P2, xl.T.astype(np.float64), xr.T.astype(np.float64))
+    pc = (X[:3] / X[3]).T
+    ref_w, usable, reliable = V.depth_gates(pc, T)
+    assert np.allclose(V.triangulate_dlt(xl.astype(np.float64), xr.astype(np.float64), P1, P2), pc, rtol=1e-7, atol=1e-8)
+    err = np.abs(xyz.astype(np.float64) - ref_w.astype(np.float64)).max(axis=1) / np.linalg.norm(ref_w, axis=1)
+    assert err.max() < REL_TOL, err.max()
+    # gates are exact except for depths within float rounding of a threshold
+    z = pc[:, 2]
+    safe = (np.abs(z - 10) > 1e-6) & (np.abs(z - 40) > 1e-6) & (np.abs(z - 400) > 1e-6)
+    assert np.array_equal((fl & 1).astype(bool)[safe], usable[safe])
+    assert np.array_equal((fl & 2).astype(bool)[safe], reliable[safe])
+    assert usable.sum() > 100 and reliable.sum() > 100 and (~usable).sum() > 100
+    # identity pose: world == camera frame
+    xyz0, _ = gpu_ctx.triangulate(xl, xr, P1, P2, None)
+    err0 = np.abs(xyz0 - pc.astype(np.float32)).max(axis=1) / np.linalg.norm(pc, axis=1)
+    assert err0.max() < REL_TOL
+
+
+def test_triangulate_empty(pkg, gpu_ctx):
+    P1, P2 = _cams(pkg)
+    xyz, fl = gpu_ctx.triangulate(np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32), P1, P2)
+    assert xyz.shape == (0, 3) and fl.shape == (0,)
+
+
+def _oracle_frontend(L, Rimg, pattern, P1, P2, nfeat):
+    import cv2
+    kl, dl = R.orb_detect_and_compute(L, nfeat, pattern)
+    kr, dr = R.orb_detect_and_compute(Rimg, nfeat, pattern)
+    qi, ti, d = V.bf_match_crosscheck(dl, dr)
+    qi, ti, d = V.match_gate(qi, ti, d, 1.0)
+    X = cv2.triangulatePoints(P1, P2, kl["pt"][qi].T.astype(np.float64), kr["pt"][ti].T.astype(np.float64))
+    pc = (X[:3] / X[3]).T
+    return kl, dl, kr, dr, qi, ti, d, pc
+
+
+@pytest.mark.parametrize("seeds", [(0, 1, 2), (7,)])
+def test_stereo_frontend_batch(pkg, gpu_ctx, pattern, seeds):
+    P1, P2 = _cams(pkg)
+    pairs = [pkg.synth.synth_pair(s) for s in seeds]
+    left = np.stack([p[0] for p in pairs]); right = np.stack([p[1] for p in pairs])
+    out = gpu_ctx.stereo_frontend(left, right, P1, P2, nfeatures=2000)
+    b = len(seeds)
+    for i in range(b):
+        kl, dl, kr, dr, qi, ti, d, pc = _oracle_frontend(left[i], right[i], pattern, P1, P2, 2000)
+        nl, nr, nm = out["n_kp"][i], out["n_kp"][b + i], out["n_matches"][i]
+        assert nl == len(dl) and nr == len(dr)                      # keypoint counts bit-exact
+        assert np.array_equal(out["desc"][i, :nl], dl) and np.array_equal(out["desc"][b + i, :nr], dr)
+        assert np.array_equal(out["kp"]["x"][i, :nl], kl["pt"][:, 0])
+        m = out["matches"][i, :nm]
+        assert nm == len(qi)
+        assert np.array_equal(m["queryIdx"], qi) and np.array_equal(m["trainIdx"], ti)   # match indices bit-exact
+        assert np.array_equal(m["distance"], d.astype(np.float32))
+        xyz = out["xyz"][i, :nm].astype(np.float64)
+        ok = np.abs(pc[:, 2]) < 1e4     # DLT of (near-)zero disparity matches is ill-conditioned on both sides
+        err = np.abs(xyz[ok] - pc[ok]).max(axis=1) / np.linalg.norm(pc[ok], axis=1)
+        assert err.max() < REL_TOL
+        # synthetic ground truth: band disparities are integers in 4..80 px -> depths 5..103 m, so roughly half of
+        # the bands fall below the reference's 10 m "usable" gate; check the flags against the true band depth
+        flags = out["flags"][i, :nm]
+        dtrue = pairs[i][2][np.rint(kl["pt"][qi][:, 1]).astype(int).clip(0, 375)]
+        ztrue = pkg.synth.FX * pkg.synth.BASELINE_M / dtrue
+        correct = np.abs(xyz[:, 2] - ztrue) / ztrue < 0.05          # matches that found the true correspondence
+        assert correct.sum() > 0.5 * nm
+        zc = ztrue[correct]
+        clear = (np.abs(zc - 10) > 1) & (np.abs(zc - 40) > 2)       # away from the gate thresholds
+        assert np.array_equal((flags[correct] & 1).astype(bool)[clear], (zc > 10)[clear])
+        assert np.array_equal((flags[correct] & 2).astype(bool)[clear], ((zc > 10) & (zc < 40))[clear])
+        ref_usable = (pc[:, 2] > 10) & (pc[:, 2] < 400)
+        safe = (np.abs(pc[:, 2] - 10) > 1e-6) & (np.abs(pc[:, 2] - 40) > 1e-6) & (np.abs(pc[:, 2] - 400) > 1e-6)
+        assert np.array_equal((flags & 1).astype(bool)[safe], ref_usable[safe])

@@ -1,8 +1,14 @@
 #!/bin/bash
-# One gpurun visit: GPU parity tests + micro benches.  Output lands in gpurun_out/.
+# One gpurun visit: GPU parity tests + smoke + bench (+ optional ncu launch list).  Output lands in gpurun_out/.
 mkdir -p gpurun_out
+rm -f gpurun_out/extra.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -30 gpurun_out/pytest_gpu.log
-for s in "$@"; do timeout 600 python $s >> gpurun_out/extra.log 2>&1; done
-[ -f gpurun_out/extra.log ] && tail -40 gpurun_out/extra.log
+tail -25 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log; tail -5 gpurun_out/smoke.log
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
+if [ "$1" == "ncu" ]; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --pairs 32 --cpu-seconds 1 > gpurun_out/ncu_bench.log 2>&1
+  echo "ncu rc=$?"; tail -3 gpurun_out/launches.csv
+fi
+exit 0
