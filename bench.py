@@ -187,7 +187,8 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     B = args.pairs
     cap = 2304
-    ctx = pkg.Context(device=local_rank, max_images=2 * B, max_keypoints=cap)
+    ctx = pkg.Context(device=local_rank, max_images=2 * B, max_keypoints=cap, max_ba_poses=64, max_ba_points=32768,
+                      max_ba_obs=262144)
     stream = torch.cuda.Stream(device=dev)
     ctx.set_stream(stream.cuda_stream)
     s = pkg.synth
@@ -343,10 +344,36 @@ def run_ours(args, rank, world, local_rank):
 
 
 def bench_ba(ctx, pkg, args):
-    """BA LM-iterations/s on configs[2]'s window (K=10, L=5000) -- filled in once the BA kernels exist."""
-    if not hasattr(ctx, "ba_optimize"):
-        return {"unavailable": "BA kernels not built yet"}
-    return pkg.bench_ba(ctx, args) if hasattr(pkg, "bench_ba") else {"unavailable": "no bench hook"}
+    """Secondary metric of BASELINE.json: BA LM-iterations/s on configs[2] (K=10, L=5000) and configs[4]
+    (K=50, L=20000, 100k observations), through the host-buffer C-ABI call (e2e) and kernel-only (CUDA events),
+    next to the single-thread C oracle (g2o's default build has no OpenMP)."""
+    from oracle import ba_oracle
+    out = {}
+    for name, (seed, nk, nl, nobs, nit) in {"cfg3_K10_L5000": (42, 10, 5000, None, 10),
+                                            "cfg5_K50_L20000_obs100k": (43, 50, 20000, 100000, 10)}.items():
+        p = pkg.synth.synth_ba_problem(seed, nk, nl, n_obs_exact=nobs)
+        a = (p["poses"], p["points"], p["obs_pose"], p["obs_point"], p["obs_uv"], p["K"])
+        for _ in range(2):
+            r = ctx.ba_optimize(*a, num_iterations=nit)
+        ctx.timing_enable(True)
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = ctx.ba_optimize(*a, num_iterations=nit)
+        dt = (time.perf_counter() - t0) / reps
+        kt = ctx.timing_read().get("ba_lm_kernel", (0.0, 1))
+        ctx.timing_enable(False)
+        kms = kt[0] / max(kt[1], 1)
+        t0 = time.perf_counter()
+        o = ba_oracle.optimize(*a, num_iterations=nit)
+        dt_cpu = time.perf_counter() - t0
+        rel = float(np.abs(r["poses"] - o["poses"]).max() / np.abs(o["poses"]).max())
+        out[name] = {"observations": int(len(p["obs_pose"])), "lm_iterations": r["iterations"], "lm_trials": r["trials"],
+                     "e2e_iters_per_s": r["iterations"] / dt, "kernel_iters_per_s": r["iterations"] / (kms * 1e-3),
+                     "kernel_ms": kms, "e2e_ms": dt * 1e3,
+                     "cpu_oracle_iters_per_s": o["iterations"] / dt_cpu, "cpu_cores": 1,
+                     "pose_rel_err_vs_oracle": rel, "chi2": [r["chi2_initial"], r["chi2_final"]]}
+    return out
 
 
 def main():

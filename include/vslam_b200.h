@@ -188,6 +188,50 @@ int vslam_stereo_frontend_batch_dev(vslam_ctx* ctx, const uint8_t* d_left, const
                                     int32_t* d_n_kp, vslam_dmatch* d_matches, int32_t* d_n_matches, float* d_xyz,
                                     uint8_t* d_flags);
 
+/* ------------------------------------------------------------------------------------------------
+ * K13-K16  sliding-window bundle adjustment: Levenberg-Marquardt with Schur complement and Huber kernel.
+ * Replaces the arithmetic of optimize_map (optimization.cpp:103-288) and optimize_pose_only
+ * (optimization.cpp:290-436): g2o's OptimizationAlgorithmLevenberg + BlockSolver<6,3> driving the
+ * reference's VertexPose / VertexXYZ / EdgeProjection / PoseOnlyEdgeProjection (optimization.cpp:26-101),
+ * followed by the adaptive chi2 relabel loop (optimization.cpp:224-266 / 382-424).
+ *   poses        n_poses x 12 doubles, row-major 3x4 [R|t] of T_c_w, updated in place (no vertex is fixed)
+ *   points       n_points x 3 doubles (Landmark::pt_3d_ widened), updated in place unless pose_only
+ *   obs_*        one entry per graph edge in INSERTION order: pose index, point index, measured pixel
+ *   Kmat         row-major 3x3 intrinsics
+ *   chi2_per_obs (optional, n_obs) edge->chi2() as the relabel loop sees it
+ *   point_inlier (optional, n_points, in/out) Landmark::is_inlier after relabelling; the LAST edge of a
+ *                landmark in insertion order decides (the reference iterates a pointer-keyed std::map,
+ *                optimization.cpp:156,254-266); points without edges keep the value passed in
+ * The caller applies if_update_map / if_update_landmark (optimization.cpp:272-287) by choosing what to
+ * copy back.  The selection of edges (is_inlier / reliable_depth_, optimization.cpp:160,334) is the
+ * caller's graph-building job, as in the reference.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vslam_ba_options {
+    double huber_delta;    /* 5.991 (optimization.cpp:154,205) */
+    double chi2_threshold; /* 5.991 initial relabel threshold */
+    int32_t num_iterations; /* optimizer.optimize(num_ite) */
+    int32_t pose_only;     /* 0 = optimize_map, 1 = optimize_pose_only */
+    int32_t max_trials;    /* g2o maxTrialsAfterFailure, 10 */
+    int32_t reserved;
+    double tau;            /* g2o initial-lambda factor, 1e-5 */
+} vslam_ba_options;
+
+typedef struct vslam_ba_result {
+    int32_t iterations;    /* outer LM iterations executed */
+    int32_t trials;        /* LM trials = linear solves */
+    int32_t accepted;
+    int32_t reserved;
+    double chi2_initial, chi2_final; /* robustified */
+    double lambda_final;
+    double chi2_threshold; /* after the adaptive doubling */
+    int32_t n_inlier_obs, n_outlier_obs;
+} vslam_ba_result;
+
+int vslam_ba_optimize(vslam_ctx* ctx, int n_poses, double* poses, int n_points, double* points, int n_obs,
+                      const int32_t* obs_pose, const int32_t* obs_point, const double* obs_uv, const double* Kmat,
+                      const vslam_ba_options* opt, vslam_ba_result* res, double* chi2_per_obs,
+                      uint8_t* point_inlier);
+
 #ifdef __cplusplus
 }
 #endif

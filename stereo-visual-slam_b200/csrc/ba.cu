@@ -1,4 +1,857 @@
-// placeholder until the BA kernels land
+// K13-K16: sliding-window bundle adjustment, the whole Levenberg-Marquardt optimisation in ONE persistent
+// cooperative kernel (grid.sync between phases, LM control flow evaluated redundantly by every thread).
+//
+// Replaces optimize_map / optimize_pose_only (/root/reference/src/stereo_visual_slam_main/optimization.cpp:103-288,
+// 290-436) together with the g2o machinery they run (OptimizationAlgorithmLevenberg + BlockSolver<6,3> with Schur
+// complement + Huber kernel; un-vendored, restated in SURVEY.md §3.4/§A.5 and in oracle/ba_oracle.c) and the reference's
+// own vertex/edge callbacks (optimization.cpp:26-101).  fp64 throughout; same control flow, same lambda schedule, same
+// accept/reject rule as the oracle -- only summation order differs (documented tolerance 1e-4 relative on poses).
+//
+// Data layout: observations are sorted by landmark on the host (stable counting sort, O(n_obs) index marshalling), so
+// one thread owns one landmark: its 3x3 Hll block, bl and its Schur products never need atomics.  Pose blocks
+// (Hpp, bp) are accumulated in shared memory per CTA and flushed with fp64 atomics; the reduced camera system S
+// (6K x 6K) is accumulated per CTA in shared memory and reduced deterministically through a partial buffer when it
+// fits (6K <= 96), with global fp64 atomics otherwise.  The dense SPD solve (K15) runs in one CTA, in shared memory
+// when 6K <= 160.  The phase functions are also exposed one by one (vslam_ba_phase_*) for the multi-GPU path, where
+// the host inserts one all-reduce of [S, b, chi2] per LM trial between them.
 #include "common.cuh"
-int vslam_ba_init(vslam_ctx* ctx) { (void)ctx; return VSLAM_OK; }
-void vslam_ba_free(vslam_ctx* ctx) { (void)ctx; }
+
+#include <cooperative_groups.h>
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include <vector>
+
+namespace cg = cooperative_groups;
+
+#define BA_THREADS 256
+#define BA_SMEM_S_MAX 96     // reduced system accumulated in shared memory per CTA up to this dimension
+#define BA_SMEM_CHOL_MAX 160 // Cholesky in shared memory up to this dimension
+
+struct BaScalars {
+    double chi_cur;                    // robust chi2 at the linearisation point (accumulated by BUILD)
+    double chi_trial[2];               // alternating slots, see header comment of ba_lm_kernel
+    double scale[2];
+    unsigned long long maxdiag_bits;   // max |diag| as ordered bits (positive doubles order like integers)
+    int solve_ok[2];
+    int cnt_le[6];                     // relabel: #obs with chi2 <= th * 2^r
+    // results
+    int iterations, trials, accepted;
+    double chi2_initial, chi2_final, lambda_final, chi2_threshold;
+    int n_inlier_obs, n_outlier_obs;
+    int pad;
+};
+
+struct BaParams {
+    int K, L, n_obs, pose_only, num_iterations, max_trials;
+    double delta, tau, chi2_th;
+    double Kc[9];
+    int n;                 // 6K
+    int use_smem_S;        // per-CTA shared-memory S + deterministic reduce
+    int n_cta;             // grid size (partials)
+    int shard_L0, shard_L1;  // landmark range owned by this rank (multi-GPU); [0, L) on one GPU
+    double* poses;         // [2][K][12]
+    double* points;        // [2][L][3]
+    const int* obs_pose;   // sorted by landmark
+    const int* obs_point;
+    const double* obs_uv;  // [n_obs][2]
+    const int* obs_orig;   // original (insertion-order) index of sorted observation i
+    const int* lm_start;   // [L+1]
+    double* err;           // [n_obs][2]  the edges' _error (last computed, trial or not -- as in g2o)
+    double* Hpl;           // [n_obs][18]
+    double* Hll;           // [L][9]
+    double* bl;            // [L][3]
+    double* Dinv;          // [L][9]
+    double* Hpp;           // [K][36]
+    double* bp;            // [6K]
+    double* S;             // [n][n]
+    double* bs;            // [n]
+    double* x;             // [n + 3L]
+    double* S_part;        // [n_cta][n*n + n]
+    BaScalars* sc;
+    double* chi2_out;      // [n_obs] original order
+    uint8_t* inlier_out;   // [L]
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// small fp64 helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void se3_exp_dev(const double* xi, double* R, double* t) {
+    const double u0 = xi[0], u1 = xi[1], u2 = xi[2], w0 = xi[3], w1 = xi[4], w2 = xi[5];
+    const double th2 = w0 * w0 + w1 * w1 + w2 * w2;
+    const double th = sqrt(th2);
+    double imag, real;
+    if (th < 1e-10) {
+        const double th4 = th2 * th2;
+        imag = 0.5 - th2 / 48.0 + th4 / 3840.0;
+        real = 1.0 - th2 / 8.0 + th4 / 384.0;
+    } else {
+        double sh, ch;
+        sincos(0.5 * th, &sh, &ch);
+        imag = sh / th;
+        real = ch;
+    }
+    const double qx = imag * w0, qy = imag * w1, qz = imag * w2, qw = real;
+    R[0] = 1 - 2 * (qy * qy + qz * qz); R[1] = 2 * (qx * qy - qz * qw);     R[2] = 2 * (qx * qz + qy * qw);
+    R[3] = 2 * (qx * qy + qz * qw);     R[4] = 1 - 2 * (qx * qx + qz * qz); R[5] = 2 * (qy * qz - qx * qw);
+    R[6] = 2 * (qx * qz - qy * qw);     R[7] = 2 * (qy * qz + qx * qw);     R[8] = 1 - 2 * (qx * qx + qy * qy);
+    double V[9];
+    if (th < 1e-10) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) V[i] = R[i];
+    } else {
+        double s, c;
+        sincos(th, &s, &c);
+        const double a = (1 - c) / th2, b = (th - s) / (th2 * th);
+        // Omega = hat(w), Omega^2 = w w^T - |w|^2 I
+        V[0] = 1 + b * (w0 * w0 - th2); V[1] = -a * w2 + b * w0 * w1;   V[2] = a * w1 + b * w0 * w2;
+        V[3] = a * w2 + b * w0 * w1;    V[4] = 1 + b * (w1 * w1 - th2); V[5] = -a * w0 + b * w1 * w2;
+        V[6] = -a * w1 + b * w0 * w2;   V[7] = a * w0 + b * w1 * w2;    V[8] = 1 + b * (w2 * w2 - th2);
+    }
+    t[0] = V[0] * u0 + V[1] * u1 + V[2] * u2;
+    t[1] = V[3] * u0 + V[4] * u1 + V[5] * u2;
+    t[2] = V[6] * u0 + V[7] * u1 + V[8] * u2;
+}
+
+__device__ __forceinline__ void huber_dev(double e2, double delta, double& rho0, double& rho1) {
+    const double dsqr = delta * delta;
+    if (e2 <= dsqr) {
+        rho0 = e2;
+        rho1 = 1.0;
+    } else {
+        const double s = sqrt(e2);
+        rho0 = 2 * s * delta - dsqr;
+        rho1 = delta / s;
+    }
+}
+
+// e = z - pi(K (T p)); returns camera-frame point
+__device__ __forceinline__ void residual_dev(const double* T, const double* p, const double* Kc, double u, double v,
+                                             double& e0, double& e1, double* pc) {
+    pc[0] = T[0] * p[0] + T[1] * p[1] + T[2] * p[2] + T[3];
+    pc[1] = T[4] * p[0] + T[5] * p[1] + T[6] * p[2] + T[7];
+    pc[2] = T[8] * p[0] + T[9] * p[1] + T[10] * p[2] + T[11];
+    const double q0 = Kc[0] * pc[0] + Kc[1] * pc[1] + Kc[2] * pc[2];
+    const double q1 = Kc[3] * pc[0] + Kc[4] * pc[1] + Kc[5] * pc[2];
+    const double q2 = Kc[6] * pc[0] + Kc[7] * pc[1] + Kc[8] * pc[2];
+    e0 = u - q0 / q2;
+    e1 = v - q1 / q2;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// phases (grid-wide; called either from the persistent kernel or one kernel per phase)
+// ---------------------------------------------------------------------------------------------------------------
+// ZERO: clear the accumulators BUILD adds into
+__device__ void ba_phase_zero(const BaParams& P, int gtid, int gsize) {
+    for (int i = gtid; i < P.K * 36; i += gsize) P.Hpp[i] = 0.0;
+    for (int i = gtid; i < P.n; i += gsize) P.bp[i] = 0.0;
+    if (gtid == 0) {
+        P.sc->chi_cur = 0.0;
+        P.sc->maxdiag_bits = 0ull;
+    }
+}
+
+// BUILD: computeActiveErrors + activeRobustChi2 + buildSystem (K13), one thread per landmark
+__device__ void ba_phase_build(const BaParams& P, int cur, double* smem, int gtid, int gsize) {
+    // shared partial pose blocks: Hpp [K][36] then bp [6K]
+    double* sHpp = smem;
+    double* sbp = smem + P.K * 36;
+    for (int i = threadIdx.x; i < P.K * 42; i += blockDim.x) smem[i] = 0.0;
+    __syncthreads();
+    const double* poses = P.poses + (size_t)cur * P.K * 12;
+    const double* points = P.points + (size_t)cur * P.L * 3;
+    const double fx = P.Kc[0], fy = P.Kc[4];
+    double chi = 0.0, mdiag = 0.0;
+    for (int l = P.shard_L0 + gtid; l < P.shard_L1; l += gsize) {
+        const int o0 = P.lm_start[l], o1 = P.lm_start[l + 1];
+        double hll[6] = {0, 0, 0, 0, 0, 0};  // upper triangle 00 01 02 11 12 22
+        double b3[3] = {0, 0, 0};
+        const double p[3] = {points[3 * l], points[3 * l + 1], points[3 * l + 2]};
+        for (int i = o0; i < o1; ++i) {
+            const int k = P.obs_pose[i];
+            const double* T = poses + 12 * k;
+            double pc[3], e0, e1;
+            residual_dev(T, p, P.Kc, P.obs_uv[2 * i], P.obs_uv[2 * i + 1], e0, e1, pc);
+            P.err[2 * i] = e0;
+            P.err[2 * i + 1] = e1;
+            double r0, w;
+            huber_dev(e0 * e0 + e1 * e1, P.delta, r0, w);
+            chi += r0;
+            const double X = pc[0], Y = pc[1], Z = pc[2];
+            double A[12];
+            if (!P.pose_only) {  // optimization.cpp:52-73
+                const double Zinv = 1.0 / (Z + 1e-18), Zinv2 = Zinv * Zinv;
+                A[0] = -fx * Zinv; A[1] = 0; A[2] = fx * X * Zinv2; A[3] = fx * X * Y * Zinv2;
+                A[4] = -fx - fx * X * X * Zinv2; A[5] = fx * Y * Zinv;
+                A[6] = 0; A[7] = -fy * Zinv; A[8] = fy * Y * Zinv2; A[9] = fy + fy * Y * Y * Zinv2;
+                A[10] = -fy * X * Y * Zinv2; A[11] = -fy * X * Zinv;
+            } else {             // optimization.cpp:84-101
+                const double Z2 = Z * Z;
+                A[0] = -fx / Z; A[1] = 0; A[2] = fx * X / Z2; A[3] = fx * X * Y / Z2; A[4] = -fx - fx * X * X / Z2;
+                A[5] = fx * Y / Z;
+                A[6] = 0; A[7] = -fy / Z; A[8] = fy * Y / (Z * Z); A[9] = fy + fy * Y * Y / Z2; A[10] = -fy * X * Y / Z2;
+                A[11] = -fy * X / Z;
+            }
+            const double om0 = -w * e0, om1 = -w * e1;
+            double* hk = sHpp + 36 * k;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                atomicAdd(&sbp[6 * k + a], A[a] * om0 + A[6 + a] * om1);
+#pragma unroll
+                for (int b = 0; b < 6; ++b) atomicAdd(&hk[a * 6 + b], w * (A[a] * A[b] + A[6 + a] * A[6 + b]));
+            }
+            if (!P.pose_only) {
+                double B[6];
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) B[r * 3 + c] = A[r * 6] * T[c] + A[r * 6 + 1] * T[4 + c] + A[r * 6 + 2] * T[8 + c];
+                b3[0] += B[0] * om0 + B[3] * om1;
+                b3[1] += B[1] * om0 + B[4] * om1;
+                b3[2] += B[2] * om0 + B[5] * om1;
+                hll[0] += w * (B[0] * B[0] + B[3] * B[3]);
+                hll[1] += w * (B[0] * B[1] + B[3] * B[4]);
+                hll[2] += w * (B[0] * B[2] + B[3] * B[5]);
+                hll[3] += w * (B[1] * B[1] + B[4] * B[4]);
+                hll[4] += w * (B[1] * B[2] + B[4] * B[5]);
+                hll[5] += w * (B[2] * B[2] + B[5] * B[5]);
+                double* hp = P.Hpl + 18 * (size_t)i;
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) hp[a * 3 + c] = w * (A[a] * B[c] + A[6 + a] * B[3 + c]);
+            }
+        }
+        if (!P.pose_only) {
+            double* H = P.Hll + 9 * (size_t)l;
+            H[0] = hll[0]; H[1] = hll[1]; H[2] = hll[2];
+            H[3] = hll[1]; H[4] = hll[3]; H[5] = hll[4];
+            H[6] = hll[2]; H[7] = hll[4]; H[8] = hll[5];
+            P.bl[3 * l] = b3[0]; P.bl[3 * l + 1] = b3[1]; P.bl[3 * l + 2] = b3[2];
+            if (o1 > o0) mdiag = fmax(mdiag, fmax(fabs(hll[0]), fmax(fabs(hll[3]), fabs(hll[5]))));
+        }
+    }
+    chi = warp_sum(chi);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mdiag = fmax(mdiag, __shfl_xor_sync(0xFFFFFFFFu, mdiag, o));
+    if ((threadIdx.x & 31) == 0) {
+        if (chi != 0.0) atomicAdd(&P.sc->chi_cur, chi);
+        if (mdiag > 0.0) atomicMax(&P.sc->maxdiag_bits, (unsigned long long)__double_as_longlong(mdiag));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P.K * 36; i += blockDim.x)
+        if (sHpp[i] != 0.0) atomicAdd(&P.Hpp[i], sHpp[i]);
+    for (int i = threadIdx.x; i < P.n; i += blockDim.x)
+        if (sbp[i] != 0.0) atomicAdd(&P.bp[i], sbp[i]);
+    __syncthreads();
+}
+
+// SCHUR_INIT: S = Hpp (+ lambda on the diagonal), bs = bp; clear this trial's accumulator slots
+__device__ void ba_phase_schur_init(const BaParams& P, double lambda, int slot, int add_hpp, int gtid, int gsize) {
+    const int n = P.n;
+    for (int i = gtid; i < n * n; i += gsize) {
+        const int r = i / n, c = i - r * n;
+        double v = 0.0;
+        if (add_hpp && r / 6 == c / 6) v = P.Hpp[(r / 6) * 36 + (r % 6) * 6 + (c % 6)];
+        if (add_hpp && r == c) v += lambda;
+        P.S[i] = v;
+    }
+    for (int i = gtid; i < n; i += gsize) P.bs[i] = add_hpp ? P.bp[i] : 0.0;
+    if (gtid == 0) {
+        P.sc->chi_trial[slot] = 0.0;
+        P.sc->scale[slot] = 0.0;
+        P.sc->solve_ok[slot] = 0;
+    }
+}
+
+// SCHUR (K14): per landmark Dinv = (Hll + lambda I)^-1, S -= Hpl Dinv Hpl^T (upper block triangle), bs -= Hpl Dinv bl
+__device__ void ba_phase_schur(const BaParams& P, double lambda, double* smem, int gtid, int gsize) {
+    if (P.pose_only) return;
+    const int n = P.n;
+    double* sS = smem;           // [n*n] when use_smem_S
+    double* sb = smem + n * n;   // [n]
+    if (P.use_smem_S) {
+        for (int i = threadIdx.x; i < n * n + n; i += blockDim.x) smem[i] = 0.0;
+        __syncthreads();
+    }
+    for (int l = P.shard_L0 + gtid; l < P.shard_L1; l += gsize) {
+        const int o0 = P.lm_start[l], o1 = P.lm_start[l + 1];
+        double* Di = P.Dinv + 9 * (size_t)l;
+        if (o1 == o0) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) Di[q] = 0.0;
+            continue;
+        }
+        const double* H = P.Hll + 9 * (size_t)l;
+        const double m0 = H[0] + lambda, m1 = H[1], m2 = H[2], m4 = H[4] + lambda, m5 = H[5], m8 = H[8] + lambda;
+        const double c0 = m4 * m8 - m5 * m5, c1 = m5 * m2 - m1 * m8, c2 = m1 * m5 - m4 * m2;
+        const double id = 1.0 / (m0 * c0 + m1 * c1 + m2 * c2);
+        double d[9];
+        d[0] = c0 * id; d[1] = c1 * id; d[2] = c2 * id;
+        d[3] = d[1];    d[4] = (m0 * m8 - m2 * m2) * id; d[5] = (m2 * m1 - m0 * m5) * id;
+        d[6] = d[2];    d[7] = d[5];                     d[8] = (m0 * m4 - m1 * m1) * id;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) Di[q] = d[q];
+        const double b0 = P.bl[3 * l], b1 = P.bl[3 * l + 1], b2 = P.bl[3 * l + 2];
+        const double db0 = d[0] * b0 + d[1] * b1 + d[2] * b2, db1 = d[3] * b0 + d[4] * b1 + d[5] * b2,
+                     db2 = d[6] * b0 + d[7] * b1 + d[8] * b2;
+        for (int i = o0; i < o1; ++i) {
+            const int ki = P.obs_pose[i];
+            const double* Bi = P.Hpl + 18 * (size_t)i;
+            double BD[18];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                const double x0 = Bi[a * 3], x1 = Bi[a * 3 + 1], x2 = Bi[a * 3 + 2];
+                BD[a * 3] = x0 * d[0] + x1 * d[3] + x2 * d[6];
+                BD[a * 3 + 1] = x0 * d[1] + x1 * d[4] + x2 * d[7];
+                BD[a * 3 + 2] = x0 * d[2] + x1 * d[5] + x2 * d[8];
+                const double vb = x0 * db0 + x1 * db1 + x2 * db2;
+                if (P.use_smem_S) atomicAdd(&sb[6 * ki + a], -vb);
+                else atomicAdd(&P.bs[6 * ki + a], -vb);
+            }
+            for (int j = o0; j < o1; ++j) {
+                const int kj = P.obs_pose[j];
+                if (kj < ki) continue;  // upper block triangle only (as g2o); the solver mirrors it
+                const double* Bj = P.Hpl + 18 * (size_t)j;
+                double* dst = (P.use_smem_S ? sS : P.S) + (size_t)(6 * ki) * n + 6 * kj;
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int b = 0; b < 6; ++b) {
+                        if (ki == kj && b < a) continue;  // diagonal blocks: upper triangle only
+                        const double v = BD[a * 3] * Bj[b * 3] + BD[a * 3 + 1] * Bj[b * 3 + 1] + BD[a * 3 + 2] * Bj[b * 3 + 2];
+                        atomicAdd(&dst[a * n + b], -v);
+                    }
+            }
+        }
+    }
+    if (P.use_smem_S) {
+        __syncthreads();
+        double* part = P.S_part + (size_t)blockIdx.x * (n * n + n);
+        for (int i = threadIdx.x; i < n * n + n; i += blockDim.x) part[i] = smem[i];
+        __syncthreads();
+    }
+}
+
+// SCHUR_REDUCE: deterministic sum of the per-CTA partials into S / bs (shared-memory path only)
+__device__ void ba_phase_schur_reduce(const BaParams& P, int gtid, int gsize) {
+    if (P.pose_only || !P.use_smem_S) return;
+    const int n = P.n, tot = n * n + n;
+    for (int i = gtid; i < tot; i += gsize) {
+        double s = 0.0;
+        for (int c = 0; c < P.n_cta; ++c) s += P.S_part[(size_t)c * tot + i];
+        if (i < n * n) P.S[i] += s;
+        else P.bs[i - n * n] += s;
+    }
+}
+
+// triangular solves U^T y = b, U x = y by one CTA (column-oriented, parallel over the trailing entries).
+// M holds the factor: either U itself (scaled = 1) or the un-normalised rows of the grid-wide LDL^T variant
+// (scaled = 0: U[j][c] = M[j][c] / sqrt(M[j][j]), U[j][j] = sqrt(M[j][j])).
+__device__ void ba_tri_solve_cta(const BaParams& P, const double* M, int scaled, double* work) {
+    const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
+    double* y = work;  // n doubles (shared or global)
+    for (int i = tid; i < n; i += nt) y[i] = P.bs[i];
+    __syncthreads();
+    for (int i = 0; i < n; ++i) {  // forward: y_i /= U_ii; y_k -= U_ik y_i (k > i)
+        const double dii = M[i * n + i];
+        const double uii = scaled ? dii : sqrt(dii);
+        const double yi = y[i] / uii;
+        __syncthreads();
+        if (tid == 0) y[i] = yi;
+        const double f = scaled ? yi : yi / uii;
+        for (int k = i + 1 + tid; k < n; k += nt) y[k] -= M[i * n + k] * f;
+        __syncthreads();
+    }
+    for (int i = n - 1; i >= 0; --i) {  // backward: x_i = (y_i - sum_{k>i} U_ik x_k) / U_ii
+        const double dii = M[i * n + i];
+        const double uii = scaled ? dii : sqrt(dii);
+        double part = 0.0;
+        for (int k = i + 1 + tid; k < n; k += nt) part += M[i * n + k] * y[k];
+        part = warp_sum(part);
+        __shared__ double s_part[BA_THREADS / 32];
+        if ((tid & 31) == 0) s_part[tid >> 5] = part;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < nt / 32; ++w) t += s_part[w];
+            if (!scaled) t /= uii;
+            y[i] = (y[i] - t) / uii;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += nt) P.x[i] = y[i];
+    __syncthreads();
+}
+
+// SOLVE (K15), small systems: dense Cholesky S = U^T U of the upper-stored SPD system in shared memory, one CTA
+__device__ void ba_phase_solve_cta(const BaParams& P, int slot, double* smem) {
+    if (blockIdx.x != 0) return;
+    const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
+    __shared__ int s_fail;
+    __shared__ double s_d;
+    double* M = smem;  // n*n doubles, then n doubles of work space
+    if (tid == 0) s_fail = 0;
+    for (int i = tid; i < n * n; i += nt) M[i] = P.S[i];
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+        if (tid == 0) {
+            const double d = M[j * n + j];
+            if (!(d > 0.0) || !isfinite(d)) s_fail = 1;
+            s_d = sqrt(d);
+        }
+        __syncthreads();
+        if (s_fail) break;
+        const double dj = s_d;
+        for (int c = j + tid; c < n; c += nt) M[j * n + c] = (c == j) ? dj : M[j * n + c] / dj;  // row j of U
+        __syncthreads();
+        const int m = n - j - 1;  // trailing update: M[r][c] -= U[j][r] * U[j][c] for j < r <= c
+        for (int e = tid; e < m * m; e += nt) {
+            const int r = j + 1 + e / m, c = j + 1 + e % m;
+            if (c >= r) M[r * n + c] -= M[j * n + r] * M[j * n + c];
+        }
+        __syncthreads();
+    }
+    const int fail = s_fail;
+    if (!fail) ba_tri_solve_cta(P, M, 1, M + n * n);
+    if (tid == 0) P.sc->solve_ok[slot] = fail ? 0 : 1;
+}
+
+// SOLVE (K15), large systems (6K > 160): grid-wide right-looking LDL^T on S in L2, one grid.sync per column,
+// followed by the triangular solves in CTA 0.  Row j is final after step j-1, so no in-place scaling is needed.
+__device__ void ba_phase_solve_grid(const BaParams& P, int slot, cg::grid_group& grid, int gtid, int gsize) {
+    const int n = P.n;
+    int fail = 0;
+    for (int j = 0; j < n - 1; ++j) {
+        const double d = P.S[j * n + j];
+        if (!(d > 0.0) || !isfinite(d)) {
+            fail = 1;  // uniform: every thread reads the same value after the previous grid.sync
+            break;
+        }
+        const double inv = 1.0 / d;
+        const int m = n - j - 1;
+        for (int e = gtid; e < m * m; e += gsize) {
+            const int r = j + 1 + e / m, c = j + 1 + e % m;
+            if (c >= r) P.S[r * n + c] -= P.S[j * n + r] * P.S[j * n + c] * inv;
+        }
+        grid.sync();
+    }
+    if (!fail) {
+        const double d = P.S[(n - 1) * n + n - 1];
+        if (!(d > 0.0) || !isfinite(d)) fail = 1;
+    }
+    if (!fail && blockIdx.x == 0) ba_tri_solve_cta(P, P.S, 0, P.x + P.n + 3 * (size_t)P.L);  // work space behind x
+    if (gtid == 0) P.sc->solve_ok[slot] = fail ? 0 : 1;
+}
+
+// UPDATE (K16): landmark back-substitution, trial estimate = oplus(current, x), computeScale partial sums
+__device__ void ba_phase_update(const BaParams& P, int cur, double lambda, int slot, int gtid, int gsize) {
+    const int n = P.n;
+    if (!P.sc->solve_ok[slot]) return;
+    const double* poses = P.poses + (size_t)cur * P.K * 12;
+    double* tposes = P.poses + (size_t)(1 - cur) * P.K * 12;
+    const double* points = P.points + (size_t)cur * P.L * 3;
+    double* tpoints = P.points + (size_t)(1 - cur) * P.L * 3;
+    double scale = 0.0;
+    if (gtid < P.K && P.shard_L0 == 0) {  // poses are replicated; rank 0's shard accounts for their scale term
+        const int k = gtid;
+        const double* xi = P.x + 6 * k;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) scale += xi[a] * (lambda * xi[a] + P.bp[6 * k + a]);
+    }
+    if (gtid < P.K) {
+        const int k = gtid;
+        double dR[9], dt[3];
+        se3_exp_dev(P.x + 6 * k, dR, dt);
+        const double* T = poses + 12 * k;
+        double* Tn = tposes + 12 * k;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Tn[r * 4 + c] = dR[r * 3] * T[c] + dR[r * 3 + 1] * T[4 + c] + dR[r * 3 + 2] * T[8 + c];
+            Tn[r * 4 + 3] = dR[r * 3] * T[3] + dR[r * 3 + 1] * T[7] + dR[r * 3 + 2] * T[11] + dt[r];
+        }
+    }
+    if (!P.pose_only) {
+        for (int l = P.shard_L0 + gtid; l < P.shard_L1; l += gsize) {
+            const int o0 = P.lm_start[l], o1 = P.lm_start[l + 1];
+            double c0 = P.bl[3 * l], c1 = P.bl[3 * l + 1], c2 = P.bl[3 * l + 2];
+            for (int i = o0; i < o1; ++i) {
+                const double* Bi = P.Hpl + 18 * (size_t)i;
+                const double* xp = P.x + 6 * P.obs_pose[i];
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    c0 -= Bi[a * 3] * xp[a];
+                    c1 -= Bi[a * 3 + 1] * xp[a];
+                    c2 -= Bi[a * 3 + 2] * xp[a];
+                }
+            }
+            const double* d = P.Dinv + 9 * (size_t)l;
+            const double x0 = d[0] * c0 + d[1] * c1 + d[2] * c2, x1 = d[3] * c0 + d[4] * c1 + d[5] * c2,
+                         x2 = d[6] * c0 + d[7] * c1 + d[8] * c2;
+            P.x[n + 3 * l] = x0; P.x[n + 3 * l + 1] = x1; P.x[n + 3 * l + 2] = x2;
+            tpoints[3 * l] = points[3 * l] + x0;
+            tpoints[3 * l + 1] = points[3 * l + 1] + x1;
+            tpoints[3 * l + 2] = points[3 * l + 2] + x2;
+            scale += x0 * (lambda * x0 + P.bl[3 * l]) + x1 * (lambda * x1 + P.bl[3 * l + 1]) + x2 * (lambda * x2 + P.bl[3 * l + 2]);
+        }
+    }
+    scale = warp_sum(scale);
+    if ((threadIdx.x & 31) == 0 && scale != 0.0) atomicAdd(&P.sc->scale[slot], scale);
+}
+
+// TRIAL_ERR: computeActiveErrors + activeRobustChi2 at the trial estimate (the edges' _error is overwritten, as in g2o)
+__device__ void ba_phase_trial_err(const BaParams& P, int cur, int slot, int gtid, int gsize) {
+    if (!P.sc->solve_ok[slot]) return;
+    const double* tposes = P.poses + (size_t)(1 - cur) * P.K * 12;
+    const double* tpoints = P.pose_only ? P.points + (size_t)cur * P.L * 3 : P.points + (size_t)(1 - cur) * P.L * 3;
+    double chi = 0.0;
+    const int i0 = P.lm_start[P.shard_L0], i1 = P.lm_start[P.shard_L1];
+    for (int i = i0 + gtid; i < i1; i += gsize) {
+        double pc[3], e0, e1, r0, w;
+        residual_dev(tposes + 12 * P.obs_pose[i], tpoints + 3 * P.obs_point[i], P.Kc, P.obs_uv[2 * i], P.obs_uv[2 * i + 1],
+                     e0, e1, pc);
+        P.err[2 * i] = e0;
+        P.err[2 * i + 1] = e1;
+        huber_dev(e0 * e0 + e1 * e1, P.delta, r0, w);
+        chi += r0;
+    }
+    chi = warp_sum(chi);
+    if ((threadIdx.x & 31) == 0 && chi != 0.0) atomicAdd(&P.sc->chi_trial[slot], chi);
+}
+
+// RELABEL counts: #edges with chi2 <= th * 2^r for r = 0..5 in one pass (optimization.cpp:224-252)
+__device__ void ba_phase_relabel_count(const BaParams& P, int gtid, int gsize) {
+    int c[6] = {0, 0, 0, 0, 0, 0};
+    const int i0 = P.lm_start[P.shard_L0], i1 = P.lm_start[P.shard_L1];
+    for (int i = i0 + gtid; i < i1; i += gsize) {
+        const double chi = P.err[2 * i] * P.err[2 * i] + P.err[2 * i + 1] * P.err[2 * i + 1];
+        double th = P.chi2_th;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            c[r] += !(chi > th);
+            th *= 2;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        c[r] = __reduce_add_sync(0xFFFFFFFFu, c[r]);
+        if ((threadIdx.x & 31) == 0 && c[r]) atomicAdd(&P.sc->cnt_le[r], c[r]);
+    }
+}
+
+__device__ double ba_relabel_threshold(const BaParams& P, int total_obs, int* n_in) {
+    double th = P.chi2_th;
+    int r = 0;
+    for (; r < 5; ++r) {
+        const double ratio = P.sc->cnt_le[r] / (double)total_obs;
+        if (ratio > 0.5) break;
+        th *= 2;
+    }
+    *n_in = P.sc->cnt_le[r];
+    return th;
+}
+
+// RELABEL apply: per-edge chi2 (insertion order) and Landmark::is_inlier = verdict of the landmark's LAST edge
+__device__ void ba_phase_relabel_apply(const BaParams& P, double th, int gtid, int gsize) {
+    for (int l = P.shard_L0 + gtid; l < P.shard_L1; l += gsize) {
+        const int o0 = P.lm_start[l], o1 = P.lm_start[l + 1];
+        for (int i = o0; i < o1; ++i) {
+            const double chi = P.err[2 * i] * P.err[2 * i] + P.err[2 * i + 1] * P.err[2 * i + 1];
+            if (P.chi2_out) P.chi2_out[P.obs_orig[i]] = chi;
+            if (i == o1 - 1 && P.inlier_out) P.inlier_out[l] = chi > th ? 0 : 1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the persistent single-GPU kernel: optimizer.optimize(num_ite) + relabel in one launch
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BA_THREADS)
+ba_lm_kernel(const __grid_constant__ BaParams P) {
+    extern __shared__ double smem[];
+    cg::grid_group grid = cg::this_grid();
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    BaScalars* sc = P.sc;
+
+    // every thread carries an identical copy of the LM state (all inputs are read after a grid.sync)
+    int cur = 0, trials = 0, accepted = 0, it = 0;
+    double lambda = 0.0, ni = 2.0, chi_first = 0.0, chi_last = 0.0;
+
+    if (gtid == 0) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) sc->cnt_le[r] = 0;
+    }
+    for (it = 0; it < P.num_iterations; ++it) {
+        ba_phase_zero(P, gtid, gsize);
+        grid.sync();
+        ba_phase_build(P, cur, smem, gtid, gsize);
+        grid.sync();
+        double currentChi = sc->chi_cur;
+        if (it == 0) {
+            chi_first = currentChi;
+            __shared__ double s_md;
+            if (threadIdx.x == 0) {
+                double md = __longlong_as_double((long long)sc->maxdiag_bits);
+                for (int i = 0; i < P.n; ++i) md = fmax(md, fabs(P.Hpp[(i / 6) * 36 + (i % 6) * 7]));
+                s_md = md;
+            }
+            __syncthreads();
+            lambda = P.tau * s_md;  // computeLambdaInit: tau * max |diagonal| over poses and landmarks
+            ni = 2.0;
+        }
+        double rho = 0.0;
+        int qmax = 0;
+        do {
+            const int slot = trials & 1;
+            ba_phase_schur_init(P, lambda, slot, 1, gtid, gsize);
+            grid.sync();
+            ba_phase_schur(P, lambda, smem, gtid, gsize);
+            grid.sync();
+            ba_phase_schur_reduce(P, gtid, gsize);
+            grid.sync();
+            if (P.n <= BA_SMEM_CHOL_MAX) ba_phase_solve_cta(P, slot, smem);
+            else ba_phase_solve_grid(P, slot, grid, gtid, gsize);
+            grid.sync();
+            ba_phase_update(P, cur, lambda, slot, gtid, gsize);
+            grid.sync();
+            ba_phase_trial_err(P, cur, slot, gtid, gsize);
+            grid.sync();
+            const int ok2 = sc->solve_ok[slot];
+            const double tempChi = ok2 ? sc->chi_trial[slot] : DBL_MAX;
+            const double scale = (ok2 ? sc->scale[slot] : 0.0) + 1e-3;
+            rho = (currentChi - tempChi) / scale;
+            if (rho > 0 && isfinite(tempChi)) {
+                double alpha = 1. - pow(2 * rho - 1, 3);
+                alpha = fmin(alpha, 2. / 3.);
+                lambda *= fmax(1. / 3., alpha);
+                ni = 2;
+                currentChi = tempChi;
+                cur = 1 - cur;  // discardTop(): the trial estimate becomes the estimate
+                if (P.pose_only) {
+                    // points are not touched in pose-only mode: both buffers hold the same values
+                }
+                accepted++;
+            } else {
+                lambda *= ni;
+                ni *= 2;  // pop(): keep `cur`; the edges' errors stay at the trial values, as in g2o
+            }
+            qmax++;
+            trials++;
+        } while (rho < 0 && qmax < P.max_trials);
+        chi_last = currentChi;
+        if (qmax == P.max_trials || rho == 0) {
+            it++;
+            break;
+        }
+    }
+    if (P.num_iterations <= 0) {
+        ba_phase_zero(P, gtid, gsize);
+        grid.sync();
+        ba_phase_build(P, cur, smem, gtid, gsize);
+        grid.sync();
+        chi_first = chi_last = sc->chi_cur;
+    }
+    // relabel
+    grid.sync();
+    ba_phase_relabel_count(P, gtid, gsize);
+    grid.sync();
+    int n_in = 0;
+    const double th = ba_relabel_threshold(P, P.n_obs, &n_in);
+    ba_phase_relabel_apply(P, th, gtid, gsize);
+    // the accepted estimate must end up in buffer 0
+    if (cur == 1) {
+        for (int i = gtid; i < P.K * 12; i += gsize) P.poses[i] = P.poses[P.K * 12 + i];
+        if (!P.pose_only)
+            for (int i = gtid; i < P.L * 3; i += gsize) P.points[i] = P.points[(size_t)P.L * 3 + i];
+    }
+    if (gtid == 0) {
+        sc->iterations = it;
+        sc->trials = trials;
+        sc->accepted = accepted;
+        sc->chi2_initial = chi_first;
+        sc->chi2_final = chi_last;
+        sc->lambda_final = lambda;
+        sc->chi2_threshold = th;
+        sc->n_inlier_obs = n_in;
+        sc->n_outlier_obs = P.n_obs - n_in;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+struct BaState {
+    int maxK, maxL, maxObs, n_cta, smem_bytes;
+    double *d_poses, *d_points, *d_uv, *d_err, *d_Hpl, *d_Hll, *d_bl, *d_Dinv, *d_Hpp, *d_bp, *d_S, *d_bs, *d_x, *d_Spart;
+    double* d_chi2;
+    int *d_obs_pose, *d_obs_point, *d_obs_orig, *d_lm_start;
+    uint8_t* d_inlier;
+    BaScalars* d_sc;
+    BaScalars* h_sc;  // pinned
+};
+
+// shared memory of one CTA: max(pose partials K*42, per-CTA S n*n+n, in-shared-memory Cholesky n*n+n) doubles
+static int ba_smem_bytes(int K) {
+    const size_t n = 6 * (size_t)K;
+    size_t need = (size_t)K * 42;
+    if (n <= BA_SMEM_CHOL_MAX && n * n + n > need) need = n * n + n;
+    return (int)(need * sizeof(double));
+}
+
+int vslam_ba_init(vslam_ctx* ctx) {
+    BaState* b = (BaState*)calloc(1, sizeof(BaState));
+    if (!b) return VSLAM_E_INVALID;
+    ctx->ba = b;
+    const vslam_config& c = ctx->cfg;
+    b->maxK = c.max_ba_poses;
+    b->maxL = c.max_ba_points;
+    b->maxObs = c.max_ba_obs;
+    if (b->maxK <= 0 || b->maxL <= 0 || b->maxObs <= 0) return VSLAM_OK;  // BA disabled
+    const size_t K = b->maxK, L = b->maxL, O = b->maxObs, n = 6 * K;
+    b->n_cta = ctx->num_sms;
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_poses, 2 * K * 12 * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_points, 2 * L * 3 * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_uv, O * 2 * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_err, O * 2 * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_Hpl, O * 18 * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_Hll, L * 9 * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_bl, L * 3 * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_Dinv, L * 9 * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_Hpp, K * 36 * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_bp, n * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_S, n * n * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_bs, n * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_x, (2 * n + 3 * L) * sizeof(double)));
+    const size_t ns = n < BA_SMEM_S_MAX ? n : BA_SMEM_S_MAX;
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_Spart, (size_t)b->n_cta * (ns * ns + ns) * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_chi2, O * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_obs_pose, O * sizeof(int)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_obs_point, O * sizeof(int)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_obs_orig, O * sizeof(int)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_lm_start, (L + 1) * sizeof(int)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_inlier, L));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_sc, sizeof(BaScalars)));
+    VSLAM_CUDA(ctx, cudaMallocHost(&b->h_sc, sizeof(BaScalars)));
+    // dynamic shared memory is sized per call from the actual K (ba_smem_bytes); opt in to the largest case here
+    b->smem_bytes = 0;
+    for (size_t k = 1; k <= K; ++k) {
+        const int need = ba_smem_bytes((int)k);
+        if (need > b->smem_bytes) b->smem_bytes = need;
+    }
+    if (b->smem_bytes > 227 * 1024) return VSLAM_E_CAPACITY;
+    VSLAM_CUDA(ctx, cudaFuncSetAttribute(ba_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
+    return VSLAM_OK;
+}
+
+void vslam_ba_free(vslam_ctx* ctx) {
+    BaState* b = ctx->ba;
+    if (!b) return;
+    cudaFree(b->d_poses); cudaFree(b->d_points); cudaFree(b->d_uv); cudaFree(b->d_err); cudaFree(b->d_Hpl);
+    cudaFree(b->d_Hll); cudaFree(b->d_bl); cudaFree(b->d_Dinv); cudaFree(b->d_Hpp); cudaFree(b->d_bp); cudaFree(b->d_S);
+    cudaFree(b->d_bs); cudaFree(b->d_x); cudaFree(b->d_Spart); cudaFree(b->d_chi2); cudaFree(b->d_obs_pose);
+    cudaFree(b->d_obs_point); cudaFree(b->d_obs_orig); cudaFree(b->d_lm_start); cudaFree(b->d_inlier); cudaFree(b->d_sc);
+    cudaFreeHost(b->h_sc);
+    free(b);
+    ctx->ba = nullptr;
+}
+
+extern "C" int vslam_ba_optimize(vslam_ctx* ctx, int n_poses, double* poses, int n_points, double* points, int n_obs,
+                                 const int32_t* obs_pose, const int32_t* obs_point, const double* obs_uv,
+                                 const double* Kmat, const vslam_ba_options* opt, vslam_ba_result* res,
+                                 double* chi2_per_obs, uint8_t* point_inlier) {
+    if (!ctx || !poses || !Kmat || !opt || n_poses <= 0 || n_points < 0 || n_obs < 0) return VSLAM_E_INVALID;
+    if (n_obs > 0 && (!obs_pose || !obs_point || !obs_uv)) return VSLAM_E_INVALID;
+    if (n_points > 0 && !points) return VSLAM_E_INVALID;
+    BaState* b = ctx->ba;
+    if (!b || !b->d_poses) return VSLAM_E_CAPACITY;
+    if (n_poses > b->maxK || n_points > b->maxL || n_obs > b->maxObs) return VSLAM_E_CAPACITY;
+    const int K = n_poses, L = n_points > 0 ? n_points : 1;
+    // marshal: stable counting sort of the observations by landmark (index bookkeeping only)
+    std::vector<int> lm_start(L + 1, 0), op(n_obs > 0 ? n_obs : 1), ol(n_obs > 0 ? n_obs : 1), oo(n_obs > 0 ? n_obs : 1);
+    std::vector<double> uv(2 * (size_t)(n_obs > 0 ? n_obs : 1));
+    for (int i = 0; i < n_obs; ++i) {
+        if (obs_point[i] < 0 || obs_point[i] >= n_points || obs_pose[i] < 0 || obs_pose[i] >= K) return VSLAM_E_INVALID;
+        lm_start[obs_point[i] + 1]++;
+    }
+    for (int l = 0; l < L; ++l) lm_start[l + 1] += lm_start[l];
+    {
+        std::vector<int> fill(lm_start.begin(), lm_start.end() - 1);
+        for (int i = 0; i < n_obs; ++i) {
+            const int d = fill[obs_point[i]]++;
+            op[d] = obs_pose[i];
+            ol[d] = obs_point[i];
+            oo[d] = i;
+            uv[2 * d] = obs_uv[2 * i];
+            uv[2 * d + 1] = obs_uv[2 * i + 1];
+        }
+    }
+    cudaStream_t s = ctx->stream;
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_poses, poses, (size_t)K * 96, cudaMemcpyHostToDevice, s));
+    if (n_points > 0) {
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_points, points, (size_t)n_points * 24, cudaMemcpyHostToDevice, s));
+        // pose-only mode never writes the trial points: keep both buffers equal
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_points + (size_t)L * 3, points, (size_t)n_points * 24, cudaMemcpyHostToDevice, s));
+    }
+    if (n_obs > 0) {
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_pose, op.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_point, ol.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_orig, oo.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_uv, uv.data(), (size_t)n_obs * 16, cudaMemcpyHostToDevice, s));
+    }
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_lm_start, lm_start.data(), (size_t)(L + 1) * 4, cudaMemcpyHostToDevice, s));
+    if (point_inlier && n_points > 0)
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_inlier, point_inlier, (size_t)n_points, cudaMemcpyHostToDevice, s));
+
+    BaParams P;
+    memset(&P, 0, sizeof(P));
+    P.K = K; P.L = n_points; P.n_obs = n_obs; P.pose_only = opt->pose_only ? 1 : 0;
+    P.num_iterations = opt->num_iterations; P.max_trials = opt->max_trials > 0 ? opt->max_trials : 10;
+    P.delta = opt->huber_delta; P.tau = opt->tau > 0 ? opt->tau : 1e-5; P.chi2_th = opt->chi2_threshold;
+    memcpy(P.Kc, Kmat, 72);
+    P.n = 6 * K;
+    P.use_smem_S = (!P.pose_only && P.n <= BA_SMEM_S_MAX) ? 1 : 0;
+    P.n_cta = b->n_cta;
+    P.shard_L0 = 0; P.shard_L1 = n_points;
+    P.poses = b->d_poses; P.points = b->d_points; P.obs_pose = b->d_obs_pose; P.obs_point = b->d_obs_point;
+    P.obs_uv = b->d_uv; P.obs_orig = b->d_obs_orig; P.lm_start = b->d_lm_start; P.err = b->d_err; P.Hpl = b->d_Hpl;
+    P.Hll = b->d_Hll; P.bl = b->d_bl; P.Dinv = b->d_Dinv; P.Hpp = b->d_Hpp; P.bp = b->d_bp; P.S = b->d_S; P.bs = b->d_bs;
+    P.x = b->d_x; P.S_part = b->d_Spart; P.sc = b->d_sc; P.chi2_out = b->d_chi2; P.inlier_out = b->d_inlier;
+    // points buffer 1 lives at offset L*3 (L = max(n_points,1)); the kernel indexes with P.L
+    if (n_points > 0 && L != n_points) return VSLAM_E_INVALID;
+
+    void* args[] = {(void*)&P};
+    vslam_time_begin(ctx, VK_BA_BUILD);
+    VSLAM_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)ba_lm_kernel, dim3(b->n_cta), dim3(BA_THREADS), args,
+                                                (size_t)ba_smem_bytes(K), s));
+    vslam_time_end(ctx);
+    VSLAM_LAUNCH_CHECK(ctx, "ba_lm_kernel");
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->h_sc, b->d_sc, sizeof(BaScalars), cudaMemcpyDeviceToHost, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(poses, b->d_poses, (size_t)K * 96, cudaMemcpyDeviceToHost, s));
+    if (n_points > 0 && !P.pose_only)
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(points, b->d_points, (size_t)n_points * 24, cudaMemcpyDeviceToHost, s));
+    if (chi2_per_obs && n_obs > 0)
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(chi2_per_obs, b->d_chi2, (size_t)n_obs * 8, cudaMemcpyDeviceToHost, s));
+    if (point_inlier && n_points > 0)
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(point_inlier, b->d_inlier, (size_t)n_points, cudaMemcpyDeviceToHost, s));
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(s));
+    if (res) {
+        res->iterations = b->h_sc->iterations;
+        res->trials = b->h_sc->trials;
+        res->accepted = b->h_sc->accepted;
+        res->chi2_initial = b->h_sc->chi2_initial;
+        res->chi2_final = b->h_sc->chi2_final;
+        res->lambda_final = b->h_sc->lambda_final;
+        res->chi2_threshold = b->h_sc->chi2_threshold;
+        res->n_inlier_obs = b->h_sc->n_inlier_obs;
+        res->n_outlier_obs = b->h_sc->n_outlier_obs;
+    }
+    return VSLAM_OK;
+}

@@ -95,7 +95,7 @@ extern "C" int64_t vslam_ctx_launch_count(const vslam_ctx* ctx) { return ctx ? c
 // ---- optional per-launch timing (CUDA events on the launching stream) -------------------------------------
 static const char* const k_kernel_names[VK_COUNT] = {
     "resize_level_kernel", "fast_kernel", "harris_select_kernel", "blur_kernel", "anms_kernel", "describe_kernel",
-    "hamming_argmin_kernel", "crosscheck_gate_compact_kernel", "triangulate_kernel", "ba_build_kernel",
+    "hamming_argmin_kernel", "crosscheck_gate_compact_kernel", "triangulate_kernel", "ba_lm_kernel",
     "ba_solve_kernel", "ba_update_kernel", "ba_misc_kernel", "pnp_kernel"};
 
 extern "C" int vslam_kernel_count(void) { return VK_COUNT; }

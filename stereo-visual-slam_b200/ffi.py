@@ -29,6 +29,17 @@ class Config(C.Structure):
                 ("max_ba_points", C.c_int32), ("max_ba_obs", C.c_int32)]
 
 
+class BaOptions(C.Structure):
+    _fields_ = [("huber_delta", C.c_double), ("chi2_threshold", C.c_double), ("num_iterations", C.c_int32),
+                ("pose_only", C.c_int32), ("max_trials", C.c_int32), ("reserved", C.c_int32), ("tau", C.c_double)]
+
+
+class BaResult(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("trials", C.c_int32), ("accepted", C.c_int32), ("reserved", C.c_int32),
+                ("chi2_initial", C.c_double), ("chi2_final", C.c_double), ("lambda_final", C.c_double),
+                ("chi2_threshold", C.c_double), ("n_inlier_obs", C.c_int32), ("n_outlier_obs", C.c_int32)]
+
+
 KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
                            ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
@@ -66,6 +77,8 @@ SIGNATURES = {
                                          _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vslam_stereo_frontend_batch_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_longlong, _i, _i, _f, _d, _d, _vp, _vp,
                                              _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vslam_ba_optimize": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, C.POINTER(BaOptions),
+                               C.POINTER(BaResult), _vp, _vp]),
     "vslam_match_hamming_batch_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _d, _d, _vp, _i, _vp]),
 }
 
@@ -274,3 +287,26 @@ class Context:
             float(anms_c), float(gate_rel), float(gate_abs), _ptr(P1), _ptr(P2), _ptr(d_T), _ptr(d_kp), _ptr(d_desc),
             _ptr(d_n_kp), _ptr(d_matches), _ptr(d_n_matches), _ptr(d_xyz), _ptr(d_flags))
         self.check(st, "vslam_stereo_frontend_batch_dev")
+
+    # ---- K13-K16 ----------------------------------------------------------------------------
+    def ba_optimize(self, poses, points, obs_pose, obs_point, obs_uv, K, num_iterations=10, pose_only=False,
+                    huber_delta=5.991, chi2_th=5.991, max_trials=10, tau=1e-5, point_inlier=None):
+        """optimize_map / optimize_pose_only arithmetic (inputs are not modified).  Returns a dict."""
+        poses = np.array(poses, dtype=np.float64, order="C").reshape(-1, 12).copy()
+        points = np.array(points, dtype=np.float64, order="C").reshape(-1, 3).copy()
+        op = np.ascontiguousarray(obs_pose, dtype=np.int32)
+        ol = np.ascontiguousarray(obs_point, dtype=np.int32)
+        uv = np.ascontiguousarray(obs_uv, dtype=np.float64).reshape(-1, 2)
+        Kc = np.ascontiguousarray(K, dtype=np.float64).reshape(9)
+        opt = BaOptions(huber_delta, chi2_th, int(num_iterations), int(pose_only), int(max_trials), 0, tau)
+        res = BaResult()
+        chi2 = np.zeros(max(len(op), 1), dtype=np.float64)
+        inl = (np.ones(max(len(points), 1), dtype=np.uint8) if point_inlier is None
+               else np.ascontiguousarray(point_inlier, dtype=np.uint8).copy())
+        st = self.lib.vslam_ba_optimize(self.h, len(poses), _ptr(poses), len(points), _ptr(points), len(op), _ptr(op),
+                                        _ptr(ol), _ptr(uv), _ptr(Kc), C.byref(opt), C.byref(res), _ptr(chi2), _ptr(inl))
+        self.check(st, "vslam_ba_optimize")
+        return dict(poses=poses, points=points, chi2_per_obs=chi2[:len(op)], point_inlier=inl[:len(points)].astype(bool),
+                    iterations=res.iterations, trials=res.trials, accepted=res.accepted,
+                    chi2_initial=res.chi2_initial, chi2_final=res.chi2_final, lambda_final=res.lambda_final,
+                    chi2_threshold=res.chi2_threshold, n_inlier_obs=res.n_inlier_obs, n_outlier_obs=res.n_outlier_obs)
