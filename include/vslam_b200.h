@@ -232,6 +232,27 @@ int vslam_ba_optimize(vslam_ctx* ctx, int n_poses, double* poses, int n_points, 
                       const vslam_ba_options* opt, vslam_ba_result* res, double* chi2_per_obs,
                       uint8_t* point_inlier);
 
+/* ------------------------------------------------------------------------------------------------
+ * K12  PnP-RANSAC + inlier refit.
+ * Replaces cv::solvePnPRansac(pts3d, pts2d, K, noDist, rvec, tvec, false, 100, 4.0, 0.99, inliers) in
+ * VO::motion_estimation (visual_odometry.cpp:253-314, call at :277).  xyz: n x 3 float32 world points
+ * (Landmark::pt_3d_), uv: n x 2 float32 pixels, Kmat row-major 3x3 (no distortion).  Outputs: rvec
+ * (Rodrigues) and tvec as cv::solvePnPRansac returns them, optionally the same pose as a 3x4 [R|t]
+ * (T_c_w, may be NULL), and the ascending inlier index list.  The pose is the Gauss-Newton optimum of
+ * the reprojection error over the inliers of the best hypothesis (what OpenCV returns);
+ * all `iters` hypotheses are scored (no confidence-based early exit), so on inputs with a clear
+ * consensus the inlier set and pose equal cv2's.  n < 6 yields *n_inliers = 0.
+ * ---------------------------------------------------------------------------------------------- */
+int vslam_pnp_ransac(vslam_ctx* ctx, const float* xyz, const float* uv, int n, const double* Kmat, int iters,
+                     float reproj_err, double confidence, double* rvec, double* tvec, double* T_c_w,
+                     int32_t* inliers, int32_t* n_inliers);
+
+/* K7 stand-alone: VO::adaptive_non_maximal_suppresion (visual_odometry.cpp:96-157) on caller keypoints.
+ * keep_idx receives the indices (ascending, into `keypoints`) of the survivors: radius >= num-th largest
+ * radius, ties kept; identity when n < num (visual_odometry.cpp:100). */
+int vslam_anms(vslam_ctx* ctx, const vslam_keypoint* keypoints, int n, int num, float c_robust,
+               int32_t* keep_idx, int32_t* n_keep);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@ struct OrbState;   // orb.cu
 struct MatchState; // match.cu
 struct BaState;    // ba.cu
 struct FrontState; // frontend.cu
+struct PnpState;   // pnp.cu
 
 // kernel ids for the optional per-launch CUDA-event timing (vslam_ctx_timing_*)
 enum {
@@ -43,6 +44,7 @@ struct vslam_ctx {
     MatchState* match;
     BaState* ba;
     FrontState* front;
+    PnpState* pnp;
 };
 
 static inline int vslam_set_cuda_error(vslam_ctx* ctx, cudaError_t e, const char* where) {
@@ -105,3 +107,5 @@ int vslam_ba_init(vslam_ctx* ctx);
 void vslam_ba_free(vslam_ctx* ctx);
 int vslam_front_init(vslam_ctx* ctx);
 void vslam_front_free(vslam_ctx* ctx);
+int vslam_pnp_init(vslam_ctx* ctx);
+void vslam_pnp_free(vslam_ctx* ctx);

@@ -51,6 +51,7 @@ extern "C" int vslam_ctx_create(const vslam_config* cfg, vslam_ctx** out) {
     if (st == VSLAM_OK) st = vslam_orb_init(ctx);
     if (st == VSLAM_OK) st = vslam_ba_init(ctx);
     if (st == VSLAM_OK) st = vslam_front_init(ctx);
+    if (st == VSLAM_OK) st = vslam_pnp_init(ctx);
     if (st != VSLAM_OK) {
         vslam_ctx_destroy(ctx);
         return st;
@@ -63,6 +64,7 @@ extern "C" void vslam_ctx_destroy(vslam_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
+    vslam_pnp_free(ctx);
     vslam_front_free(ctx);
     vslam_ba_free(ctx);
     vslam_orb_free(ctx);

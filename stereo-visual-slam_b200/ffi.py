@@ -79,6 +79,8 @@ SIGNATURES = {
                                              _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vslam_ba_optimize": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, C.POINTER(BaOptions),
                                C.POINTER(BaResult), _vp, _vp]),
+    "vslam_pnp_ransac": (_i, [_vp, _vp, _vp, _i, _vp, _i, _f, _d, _vp, _vp, _vp, _vp, _pi]),
+    "vslam_anms": (_i, [_vp, _vp, _i, _i, _f, _vp, _pi]),
     "vslam_match_hamming_batch_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _d, _d, _vp, _i, _vp]),
 }
 
@@ -310,3 +312,25 @@ class Context:
                     iterations=res.iterations, trials=res.trials, accepted=res.accepted,
                     chi2_initial=res.chi2_initial, chi2_final=res.chi2_final, lambda_final=res.lambda_final,
                     chi2_threshold=res.chi2_threshold, n_inlier_obs=res.n_inlier_obs, n_outlier_obs=res.n_outlier_obs)
+
+    # ---- K12 / K7 ---------------------------------------------------------------------------
+    def pnp_ransac(self, xyz, uv, K, iters=100, reproj_err=4.0, confidence=0.99):
+        """cv::solvePnPRansac arithmetic.  Returns dict(rvec, tvec, T_c_w (3x4), inliers int32[])."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+        Kc = np.ascontiguousarray(K, dtype=np.float64).reshape(9)
+        rvec, tvec, T = np.zeros(3), np.zeros(3), np.zeros(12)
+        inl = np.zeros(max(len(xyz), 1), dtype=np.int32)
+        n = C.c_int(0)
+        st = self.lib.vslam_pnp_ransac(self.h, _ptr(xyz), _ptr(uv), len(xyz), _ptr(Kc), int(iters), float(reproj_err),
+                                       float(confidence), _ptr(rvec), _ptr(tvec), _ptr(T), _ptr(inl), C.byref(n))
+        self.check(st, "vslam_pnp_ransac")
+        return dict(rvec=rvec, tvec=tvec, T_c_w=T.reshape(3, 4), inliers=inl[:n.value].copy())
+
+    def anms(self, keypoints, num=500, c_robust=1.11):
+        kp = np.ascontiguousarray(keypoints, dtype=KEYPOINT_DTYPE)
+        keep = np.zeros(max(len(kp), 1), dtype=np.int32)
+        n = C.c_int(0)
+        st = self.lib.vslam_anms(self.h, _ptr(kp), len(kp), int(num), float(c_robust), _ptr(keep), C.byref(n))
+        self.check(st, "vslam_anms")
+        return keep[:n.value].copy()
