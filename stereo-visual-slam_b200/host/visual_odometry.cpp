@@ -1,0 +1,388 @@
+// VO front end: the reference's stage methods and state machine
+// (/root/reference/src/stereo_visual_slam_main/visual_odometry.cpp:20-706) over the CUDA library.
+// Compute stages (feature_detection, adaptive_non_maximal_suppresion, feature_matching, disparity_map,
+// motion_estimation) are one C-ABI call each; everything else is the host bookkeeping the reference does, expressed
+// with index maps instead of its O(N*M) scans where the result is identical.
+#include <stereo_visual_slam_main/visual_odometry.hpp>
+
+#include <algorithm>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <stdexcept>
+#include <unordered_map>
+
+#include "../../include/vslam_b200.h"
+
+namespace vslam {
+
+namespace {
+const int kMaxW = 1920, kMaxH = 1200, kMaxKp = 8192;
+
+void check(int st, const char* what) {
+    if (st != VSLAM_OK) throw std::runtime_error(std::string(what) + ": " + vslam_status_string(st));
+}
+}  // namespace
+
+void VO::create_context() {
+    vslam_config cfg;
+    cfg.device = 0;
+    cfg.max_images = 2;
+    cfg.max_width = kMaxW;
+    cfg.max_height = kMaxH;
+    cfg.max_keypoints = kMaxKp;
+    cfg.max_ba_poses = 16;
+    cfg.max_ba_points = 65536;
+    cfg.max_ba_obs = 262144;
+    check(vslam_ctx_create(&cfg, &ctx_), "vslam_ctx_create");  // throws without a B200: there is no CPU path
+    set_optimization_context(ctx_);
+}
+
+VO::VO(ros::NodeHandle& nh, Map& map) : my_map_(map), my_visual_(nh) {
+    create_context();
+    nh.getParam("/if_rviz", if_rviz_);
+}
+
+VO::VO(std::string dataset, ros::NodeHandle& nh, Map& map) : my_map_(map), my_visual_(nh) {
+    dataset_ = dataset;
+    create_context();
+    nh.getParam("/if_rviz", if_rviz_);
+}
+
+VO::~VO() {
+    if (optimization_context() == ctx_) set_optimization_context(nullptr);
+    vslam_ctx_destroy(ctx_);
+}
+
+// ---- I/O -------------------------------------------------------------------------------------------------------
+static bool read_pgm(const std::string& path, cv::Mat& img) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    std::string magic;
+    int w = 0, h = 0, maxv = 0;
+    f >> magic >> w >> h >> maxv;
+    if (magic != "P5" || w <= 0 || h <= 0 || maxv != 255) return false;
+    f.get();
+    img.create(h, w, cv::CV_8U);
+    f.read(reinterpret_cast<char*>(img.data), (std::streamsize)w * h);
+    return (bool)f;
+}
+
+int VO::read_img(int id, cv::Mat& left_img, cv::Mat& right_img) {
+    if (image_source_) return image_source_(id, left_img, right_img);
+    char name[16];
+    std::snprintf(name, sizeof(name), "%06d", id);
+    const bool ok = read_pgm(dataset_ + "image_0/" + name + ".pgm", left_img) &&
+                    read_pgm(dataset_ + "image_1/" + name + ".pgm", right_img);
+    if (!ok || !left_img.data) {
+        std::cout << "Could not open or find the image" << std::endl;
+        return -1;
+    }
+    return 0;
+}
+
+// ---- compute stages --------------------------------------------------------------------------------------------
+int VO::feature_detection(const cv::Mat& img, std::vector<cv::KeyPoint>& keypoints, cv::Mat& descriptors) {
+    if (!img.data) {
+        std::cout << "Could not open or find the image" << std::endl;
+        return -1;
+    }
+    const int cap = vslam_orb_keypoint_capacity(ctx_);
+    std::vector<cv::KeyPoint> kp(cap);
+    cv::Mat desc(cap, 32, cv::CV_8U);
+    int32_t n = 0;
+    const int st = vslam_orb_detect_compute(ctx_, img.data, img.cols, img.rows, (int)img.step, detector_nfeatures_,
+                                            anms_keep_, 1.11f, reinterpret_cast<vslam_keypoint*>(kp.data()), desc.data, &n);
+    if (st == VSLAM_E_INVALID) return -1;
+    check(st, "vslam_orb_detect_compute");
+    kp.resize(n);
+    keypoints.swap(kp);
+    descriptors = cv::Mat(n, 32, cv::CV_8U);  // owning N x 32 matrix, rows are handed out as views (Feature::descriptor_)
+    if (n > 0) std::memcpy(descriptors.data, desc.data, (size_t)n * 32);
+    return 0;
+}
+
+void VO::adaptive_non_maximal_suppresion(std::vector<cv::KeyPoint>& keypoints, const int num) {
+    if ((int)keypoints.size() < num) return;
+    std::vector<int32_t> keep(keypoints.size());
+    int32_t n = 0;
+    check(vslam_anms(ctx_, reinterpret_cast<const vslam_keypoint*>(keypoints.data()), (int)keypoints.size(), num, 1.11f,
+                     keep.data(), &n),
+          "vslam_anms");
+    std::vector<cv::KeyPoint> out;
+    out.reserve(n);
+    for (int i = 0; i < n; ++i) out.push_back(keypoints[keep[i]]);
+    // the reference returns the survivors in descending-response order (it sorts before suppressing)
+    std::stable_sort(out.begin(), out.end(), [](const cv::KeyPoint& a, const cv::KeyPoint& b) { return a.response > b.response; });
+    keypoints.swap(out);
+}
+
+int VO::feature_matching(const cv::Mat& descriptors_1, const cv::Mat& descriptors_2,
+                         std::vector<cv::DMatch>& feature_matches) {
+    feature_matches.clear();
+    const int nq = descriptors_1.rows, nt = descriptors_2.rows;
+    if (nq == 0 || nt == 0) return 0;  // the reference dereferences an empty range here (UB); we return no matches
+    const double frame_gap = frame_current_.frame_id_ - frame_last_.frame_id_;
+    std::vector<cv::DMatch> out(std::min(nq, nt));
+    int n = 0;
+    check(vslam_match_hamming(ctx_, descriptors_1.data, nq, descriptors_2.data, nt, 1, 2.0, 30.0 * frame_gap,
+                              reinterpret_cast<vslam_dmatch*>(out.data()), &n),
+          "vslam_match_hamming");
+    out.resize(n);
+    feature_matches.swap(out);
+    return 0;
+}
+
+int VO::disparity_map(const Frame& frame, cv::Mat& disparity) {
+    const cv::Mat& L = frame.left_img_;
+    const cv::Mat& R = frame.right_img_;
+    if (!L.data || !R.data) return -1;
+    const int cap = vslam_orb_keypoint_capacity(ctx_);
+    std::vector<vslam_keypoint> kp(2 * (size_t)cap);
+    std::vector<uint8_t> desc(2 * (size_t)cap * 32), flags(cap);
+    std::vector<vslam_dmatch> matches(cap);
+    std::vector<float> xyz(3 * (size_t)cap);
+    int32_t n_kp[2] = {0, 0}, n_m = 0;
+    // rectified pair: P1 = K [I|0], P2 = K [I|(-b,0,0)]
+    const double P1[12] = {frame.fx_, 0, frame.cx_, 0, 0, frame.fy_, frame.cy_, 0, 0, 0, 1, 0};
+    const double P2[12] = {frame.fx_, 0, frame.cx_, -frame.fx_ * frame.b_, 0, frame.fy_, frame.cy_, 0, 0, 0, 1, 0};
+    check(vslam_stereo_frontend_batch(ctx_, L.data, R.data, 1, L.cols, L.rows, (int)L.step, (long long)L.step * L.rows,
+                                      detector_nfeatures_, anms_keep_, 1.11f, 2.0, 30.0, P1, P2, nullptr, kp.data(),
+                                      desc.data(), n_kp, matches.data(), &n_m, xyz.data(), flags.data()),
+          "vslam_stereo_frontend_batch");
+    disparity.create(L.rows, L.cols, cv::CV_32F);
+    disparity.setTo(-1.0);  // "no depth", as SGBM's invalid value after the /16 conversion
+    for (int i = 0; i < n_m; ++i) {
+        const vslam_keypoint& k = kp[matches[i].queryIdx];
+        const float Z = xyz[3 * i + 2];
+        if (!(Z > 0)) continue;
+        disparity.at<float>((int)k.y, (int)k.x) = (float)(frame.fx_ * frame.b_ / Z);
+    }
+    return 0;
+}
+
+std::vector<bool> VO::set_ref_3d_position(std::vector<cv::Point3f>& pts_3d, std::vector<cv::KeyPoint>& keypoints,
+                                          cv::Mat& descriptors, Frame& frame) {
+    pts_3d.clear();
+    std::vector<cv::KeyPoint> kept_kp;
+    std::vector<int> kept_rows;
+    std::vector<bool> reliable_depth;
+    for (size_t i = 0; i < keypoints.size(); ++i) {
+        Eigen::Vector3d rel;
+        const Eigen::Vector3d w = frame.find_3d(keypoints[i], rel);
+        if (rel(2) > 10 && rel(2) < 400) {  // usable depth (visual_odometry.cpp:194)
+            pts_3d.push_back(cv::Point3f((float)w(0), (float)w(1), (float)w(2)));
+            kept_kp.push_back(keypoints[i]);
+            kept_rows.push_back((int)i);
+            reliable_depth.push_back(rel(2) < 40);  // visual_odometry.cpp:201
+        }
+    }
+    cv::Mat filtered((int)kept_rows.size(), 32, cv::CV_8U);
+    for (size_t r = 0; r < kept_rows.size(); ++r) std::memcpy(filtered.ptr<uint8_t>((int)r), descriptors.ptr<uint8_t>(kept_rows[r]), 32);
+    descriptors = filtered;
+    keypoints.swap(kept_kp);
+    return reliable_depth;
+}
+
+void VO::motion_estimation(Frame& frame) {
+    const size_t n = frame.features_.size();
+    std::vector<float> xyz(3 * n), uv(2 * n);
+    for (size_t i = 0; i < n; ++i) {
+        const int landmark_id = frame.features_[i].landmark_id_;
+        if (landmark_id == -1) std::cout << "No landmark associated!" << std::endl;
+        const cv::Point3f& p = my_map_.landmarks_.at(landmark_id).pt_3d_;  // throws like the reference
+        xyz[3 * i] = p.x; xyz[3 * i + 1] = p.y; xyz[3 * i + 2] = p.z;
+        uv[2 * i] = frame.features_[i].keypoint_.pt.x;
+        uv[2 * i + 1] = frame.features_[i].keypoint_.pt.y;
+    }
+    const double K[9] = {frame.fx_, 0, frame.cx_, 0, frame.fy_, frame.cy_, 0, 0, 1};
+    double rvec[3] = {0, 0, 0}, tvec[3] = {0, 0, 0}, T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    std::vector<int32_t> inliers(n ? n : 1);
+    int32_t n_inl = 0;
+    check(vslam_pnp_ransac(ctx_, xyz.data(), uv.data(), (int)n, K, 100, 4.0f, 0.99, rvec, tvec, T, inliers.data(), &n_inl),
+          "vslam_pnp_ransac");
+    num_inliers_ = n_inl;
+    if (n_inl > 0) {
+        Eigen::Matrix3d R;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) R(r, c) = T[r * 4 + c];
+        T_c_w_ = SE3(R, Eigen::Vector3d(T[3], T[7], T[11]));
+    } else {
+        T_c_w_ = SE3();  // cv::solvePnPRansac leaves rvec/tvec empty on failure; the reference then reads zeros
+    }
+    for (int i = 0; i < n_inl; ++i) frame.features_[inliers[i]].is_inlier = true;
+    frame.features_.erase(std::remove_if(frame.features_.begin(), frame.features_.end(),
+                                         [](const Feature& f) { return !f.is_inlier; }),
+                          frame.features_.end());
+}
+
+// ---- state machine ---------------------------------------------------------------------------------------------
+bool VO::check_motion_estimation() {
+    if (num_inliers_ < 10) {
+        std::cout << "Frame id: " << frame_last_.frame_id_ << " and " << frame_current_.frame_id_ << std::endl;
+        std::cout << "Rejected - inliers not enough: " << num_inliers_ << std::endl;
+        return false;
+    }
+    const double frame_gap = frame_current_.frame_id_ - frame_last_.frame_id_;
+    const double motion = T_c_l_.log().norm();
+    if (motion > 5.0 * frame_gap) {
+        std::cout << "Frame id: " << frame_last_.frame_id_ << " and " << frame_current_.frame_id_ << std::endl;
+        std::cout << "Rejected - motion is too large: " << motion << std::endl;
+        return false;
+    }
+    return true;
+}
+
+bool VO::insert_key_frame(bool check_ok, std::vector<cv::Point3f>& pts_3d, std::vector<cv::KeyPoint>& keypoints,
+                          cv::Mat& descriptors) {
+    // keyframe unless tracking is comfortable (>= 80 inliers and little yaw -- signed test, as the reference) or rejected
+    if ((num_inliers_ >= 80 && T_c_l_.angleY() < 0.03) || !check_ok) return false;
+
+    frame_current_.is_keyframe_ = true;
+    frame_current_.keyframe_id_ = curr_keyframe_id_;
+    for (Feature& f : frame_current_.features_) {
+        Landmark& lm = my_map_.landmarks_.at(f.landmark_id_);
+        lm.observed_times_++;
+        lm.observations_.push_back(Observation(frame_current_.keyframe_id_, f.feature_id_));
+    }
+
+    disparity_map(frame_current_, frame_current_.disparity_);
+    std::vector<bool> reliable_depth = set_ref_3d_position(pts_3d, keypoints, descriptors, frame_current_);
+
+    // which detected keypoints are already tracked features?  (the reference compares pt.x / pt.y exactly in a nested
+    // loop, visual_odometry.cpp:385-401; a hash of the bit patterns gives the same answer in O(N))
+    auto key = [](const cv::Point2f& p) {
+        uint32_t a, b;
+        std::memcpy(&a, &p.x, 4);
+        std::memcpy(&b, &p.y, 4);
+        return ((uint64_t)a << 32) | b;
+    };
+    std::unordered_multimap<uint64_t, size_t> tracked;
+    for (size_t j = 0; j < frame_current_.features_.size(); ++j) tracked.emplace(key(frame_current_.features_[j].keypoint_.pt), j);
+
+    int feature_id = (int)frame_current_.features_.size();
+    for (size_t i = 0; i < keypoints.size(); ++i) {
+        bool exist = false;
+        auto range = tracked.equal_range(key(keypoints[i].pt));
+        for (auto it = range.first; it != range.second; ++it) {
+            exist = true;
+            Landmark& lm = my_map_.landmarks_.at(frame_current_.features_[it->second].landmark_id_);
+            if (!lm.reliable_depth_ && reliable_depth[i]) {  // upgrade an unreliable depth
+                lm.pt_3d_ = pts_3d[i];
+                lm.reliable_depth_ = true;
+            }
+        }
+        if (!exist) {
+            Feature f(feature_id, frame_current_.frame_id_, keypoints[i], descriptors.row((int)i));
+            f.landmark_id_ = curr_landmark_id_;
+            frame_current_.features_.push_back(f);
+            tracked.emplace(key(keypoints[i].pt), frame_current_.features_.size() - 1);  // later duplicates see it, as in the reference
+            my_map_.insert_landmark(Landmark(curr_landmark_id_, pts_3d[i], descriptors.row((int)i), reliable_depth[i],
+                                             Observation(frame_current_.keyframe_id_, feature_id)));
+            curr_landmark_id_++;
+            feature_id++;
+        }
+    }
+    curr_keyframe_id_++;
+    my_map_.insert_keyframe(frame_current_);
+    return true;
+}
+
+void VO::move_frame() { frame_last_ = frame_current_; }
+
+void VO::write_pose(const Frame& frame) { my_map_.write_pose(frame); }
+
+bool VO::initialization() {
+    frame_last_ = Frame();
+    if (read_img(0, frame_last_.left_img_, frame_last_.right_img_) != 0) return false;
+    frame_last_.frame_id_ = 0;
+
+    std::vector<cv::KeyPoint> keypoints;
+    cv::Mat descriptors;
+    std::vector<cv::Point3f> pts_3d;
+    if (feature_detection(frame_last_.left_img_, keypoints, descriptors) != 0) return false;
+    disparity_map(frame_last_, frame_last_.disparity_);
+    std::vector<bool> reliable_depth = set_ref_3d_position(pts_3d, keypoints, descriptors, frame_last_);
+
+    for (size_t i = 0; i < keypoints.size(); ++i) {
+        Feature f((int)i, 0, keypoints[i], descriptors.row((int)i));
+        f.landmark_id_ = curr_landmark_id_;
+        frame_last_.features_.push_back(f);
+        my_map_.insert_landmark(Landmark(curr_landmark_id_, pts_3d[i], descriptors.row((int)i), reliable_depth[i], Observation(0, (int)i)));
+        curr_landmark_id_++;
+    }
+    frame_last_.fill_frame(SE3(), true, curr_keyframe_id_);
+    curr_keyframe_id_++;
+    my_map_.insert_keyframe(frame_last_);
+    return true;
+}
+
+bool VO::tracking(bool& if_insert_keyframe) {
+    frame_current_ = Frame();
+    // pick up the BA-optimised pose of the last keyframe
+    if (frame_last_.is_keyframe_) {
+        auto it = my_map_.keyframes_.find(frame_last_.keyframe_id_);
+        if (it != my_map_.keyframes_.end()) frame_last_ = it->second;
+    }
+    if (read_img(seq_, frame_current_.left_img_, frame_current_.right_img_) != 0) {
+        seq_++;
+        return false;
+    }
+    frame_current_.frame_id_ = seq_;
+
+    std::vector<cv::KeyPoint> keypoints;
+    cv::Mat descriptors;
+    feature_detection(frame_current_.left_img_, keypoints, descriptors);
+
+    // descriptors of the last frame's features, gathered into one matrix
+    cv::Mat descriptors_last((int)frame_last_.features_.size(), 32, cv::CV_8U);
+    for (size_t i = 0; i < frame_last_.features_.size(); ++i)
+        std::memcpy(descriptors_last.ptr<uint8_t>((int)i), frame_last_.features_[i].descriptor_.data, 32);
+    std::vector<cv::DMatch> matches;
+    feature_matching(descriptors_last, descriptors, matches);  // query = last frame, train = current frame
+
+    for (size_t i = 0; i < matches.size(); ++i) {
+        Feature f((int)i, seq_, keypoints[matches[i].trainIdx], descriptors.row(matches[i].trainIdx));
+        f.landmark_id_ = frame_last_.features_[matches[i].queryIdx].landmark_id_;
+        frame_current_.features_.push_back(f);
+    }
+
+    motion_estimation(frame_current_);
+    frame_current_.T_c_w_ = T_c_w_;
+    T_c_l_ = frame_current_.T_c_w_ * frame_last_.T_c_w_.inverse();
+
+    const bool ok = check_motion_estimation();
+    std::vector<cv::Point3f> pts_3d;
+    if_insert_keyframe = insert_key_frame(ok, pts_3d, keypoints, descriptors);
+    if (ok) move_frame();
+    seq_++;
+    return ok;
+}
+
+bool VO::pipeline(bool& if_insert_keyframe) {
+    switch (state_) {
+        case Init:
+            if (initialization()) {
+                state_ = Track;
+            } else if (++num_lost_ > 10) {
+                state_ = Lost;
+            }
+            break;
+        case Track:
+            if (tracking(if_insert_keyframe)) {
+                num_lost_ = 0;
+            } else if (++num_lost_ > 10) {
+                state_ = Lost;
+            }
+            break;
+        case Lost:
+            std::cout << "VO IS LOST" << std::endl;
+            return false;
+        default:
+            std::cout << "Invalid state" << std::endl;
+            return false;
+    }
+    return true;
+}
+
+}  // namespace vslam

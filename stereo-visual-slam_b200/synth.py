@@ -196,3 +196,40 @@ def synth_ba_problem(seed: int, n_kf: int, n_lm: int, obs_per_lm=(2, 6), n_obs_e
     uv = np.array(uv).astype(np.float32).astype(np.float64)
     return dict(K=K, poses=poses0, points=pts0, obs_pose=np.array(op, dtype=np.int32),
                 obs_point=np.array(ol, dtype=np.int32), obs_uv=uv, poses_gt=poses_gt, points_gt=pts)
+
+
+def synth_sequence(seed: int, n_frames: int, w: int = W, h: int = H):
+    """Stereo sequence of a camera translating along +x past 8 fronto-parallel bands (piecewise-planar scene).
+
+    Band disparities are multiples of 4 px in [8, 40] (Z = fx*b/d in [10.3, 51.5] m, inside the reference's usable
+    depth gate) and the camera moves b/4 per frame, so every image is an exact integer crop of one canvas: a world
+    point of band d at left column x in frame 0 sits at x - i*d/4 in frame i and at x - i*d/4 - d in the right image.
+    Returns (lefts, rights, T_w_c translations [n,3]); rotation is identity throughout.
+    """
+    rng = np.random.default_rng(seed + 77)
+    n_band = 8
+    disp = 4 * rng.integers(2, 11, size=n_band)
+    max_shift = int(disp.max()) * (n_frames // 4 + 2)
+    canvas = synth_canvas(seed, w + 200 + max_shift, h, n_rect=400 + max_shift // 3)
+    edges = np.linspace(0, h, n_band + 1).astype(int)
+    lefts, rights = [], []
+    for i in range(n_frames):
+        L = np.empty((h, w), np.uint8)
+        R = np.empty((h, w), np.uint8)
+        for bnd in range(n_band):
+            d = int(disp[bnd])
+            y0, y1 = edges[bnd], edges[bnd + 1]
+            off = 100 + (i * d) // 4
+            L[y0:y1] = canvas[y0:y1, off:off + w]
+            R[y0:y1] = canvas[y0:y1, off + d:off + d + w]
+        lefts.append(L)
+        rights.append(R)
+    t = np.zeros((n_frames, 3))
+    t[:, 0] = np.arange(n_frames) * BASELINE_M / 4.0
+    return lefts, rights, t, disp
+
+
+def write_pgm(path: str, img: np.ndarray):
+    with open(path, "wb") as f:
+        f.write(b"P5\n%d %d\n255\n" % (img.shape[1], img.shape[0]))
+        f.write(np.ascontiguousarray(img, dtype=np.uint8).tobytes())
