@@ -118,3 +118,14 @@ def test_edge_cases(pkg, ba_ctx):
     with pytest.raises(pkg.VslamError) as e:
         ba_ctx.ba_optimize(p["poses"], p["points"], p["obs_pose"], bad, p["obs_uv"], p["K"])
     assert e.value.status == -1
+
+
+def test_golden_ba(pkg, ba_ctx):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ba_seed11_K5_L120_it10.npz"))
+    p = pkg.synth.synth_ba_problem(11, 5, 120, outlier_frac=0.05)
+    r = ba_ctx.ba_optimize(p["poses"], p["points"], p["obs_pose"], p["obs_point"], p["obs_uv"], p["K"], num_iterations=10)
+    assert r["trials"] == int(g["trials"])
+    assert np.abs(r["poses"] - g["poses"]).max() / np.abs(g["poses"]).max() < REL_TOL
+    assert (np.abs(r["points"] - g["points"]).max(axis=1) / np.linalg.norm(g["points"], axis=1)).max() < REL_TOL
+    assert np.array_equal(r["point_inlier"], g["point_inlier"])

@@ -147,3 +147,14 @@ def test_relabel_semantics(pkg):
     r2 = B.optimize(p["poses"], p["points"], p["obs_pose"], p["obs_point"], p["obs_uv"], p["K"], num_iterations=10,
                     pose_only=True)
     assert np.array_equal(r2["points"], p["points"]) and r2["chi2_final"] < r2["chi2_initial"]
+
+
+def test_golden_ba(pkg):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ba_seed11_K5_L120_it10.npz"))
+    p = pkg.synth.synth_ba_problem(11, 5, 120, outlier_frac=0.05)
+    r = B.optimize(p["poses"], p["points"], p["obs_pose"], p["obs_point"], p["obs_uv"], p["K"], num_iterations=10)
+    assert r["trials"] == int(g["trials"])
+    assert np.allclose(r["poses"], g["poses"], rtol=1e-9, atol=1e-12) and np.allclose(r["points"], g["points"], rtol=1e-9)
+    assert np.allclose([r["chi2_initial"], r["chi2_final"]], g["chi2"], rtol=1e-10)
+    assert np.array_equal(r["point_inlier"], g["point_inlier"])

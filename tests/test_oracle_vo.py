@@ -83,3 +83,16 @@ def test_anms_reference_loop():
     assert np.array_equal(keep, ref)
     assert len(keep) >= num
     assert np.array_equal(V.anms(pt[:10], resp[:10], 500), np.arange(10))
+
+
+def test_golden_match_and_triangulate(pkg):
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gold, "match_ties_400x500.npz"))
+    q = pkg.synth.synth_descriptors(10, 400, dup_frac=0.3)
+    t = np.concatenate([q[::2], pkg.synth.synth_descriptors(11, 300, dup_frac=0.3)])
+    qi, ti, d = V.bf_match_crosscheck(q, t)
+    assert np.array_equal(qi, g["queryIdx"]) and np.array_equal(ti, g["trainIdx"]) and np.array_equal(d, g["distance"])
+    g = np.load(os.path.join(gold, "triangulate_64.npz"))
+    P1, P2 = V.stereo_projection_matrices(pkg.synth.FX, pkg.synth.FY, pkg.synth.CX, pkg.synth.CY, pkg.synth.BASELINE_M)
+    assert np.allclose(V.triangulate_dlt(g["xl"].astype(np.float64), g["xr"].astype(np.float64), P1, P2), g["xyz"], rtol=1e-8)

@@ -105,3 +105,13 @@ def test_null_image_and_capacity(pkg, gpu_ctx):
     # featureless image: zero keypoints, no error
     kp, desc = gpu_ctx.orb_detect_compute(np.full((376, 1241), 128, np.uint8), 2000, 0)
     assert len(kp) == 0 and desc.shape == (0, 32)
+
+
+@pytest.mark.parametrize("name,img_fn,n", [("orb_seed0_n500.npz", lambda s: s.synth_pair(0)[0], 500),
+                                           ("orb_canvas5_400x240_n300.npz", lambda s: s.synth_canvas(5, 400, 240), 300)])
+def test_golden_vectors(pkg, gpu_ctx, name, img_fn, n):
+    """CUDA path vs the committed cv2-generated fixtures (tests/golden/make_golden.py)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+    kp, desc = gpu_ctx.orb_detect_compute(img_fn(pkg.synth), n, 0)
+    _assert_kp_equal(kp, desc, g, g["desc"])
