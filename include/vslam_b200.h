@@ -253,6 +253,29 @@ int vslam_pnp_ransac(vslam_ctx* ctx, const float* xyz, const float* uv, int n, c
 int vslam_anms(vslam_ctx* ctx, const vslam_keypoint* keypoints, int n, int num, float c_robust,
                int32_t* keep_idx, int32_t* n_keep);
 
+/* ------------------------------------------------------------------------------------------------
+ * K17  landmark-sharded BA session for one-process-per-GPU runs (no reference equivalent: the reference
+ * is single-process).  Rank r owns the landmarks [shard_begin, shard_end) with all their observations,
+ * poses are replicated.  The CALLER owns the LM control flow (same schedule as vslam_ba_optimize) and
+ * performs the collectives on three DEVICE reduce buffers between the phases:
+ *   r1 = [Hpp 36K | bp 6K | chi2 | max diag Hll]   all-reduce(sum) after BUILD (max for the last entry)
+ *   r2 = [S 6Kx6K | bs 6K]                          all-reduce(sum) after SCHUR  -- one per LM trial
+ *   r3 = [chi2_trial, scale, ok, -, cnt_le[0..5]]   all-reduce(sum) after SOLVE_UPDATE / RELABEL_COUNT
+ * Phases (vslam_ba_session_phase): 1 BUILD, 2 IMPORT_BUILD (after reducing r1), 3 SCHUR(value = lambda),
+ * 4 SOLVE_UPDATE(value = lambda; after reducing r2), 5 RELABEL_COUNT, 6 RELABEL_APPLY(value = threshold).
+ * vslam_ba_session_trial_done(accept) records the LM verdict.  vslam_ba_session_end downloads the poses and
+ * this rank's shard of points / per-edge chi2 / inlier flags (zeros elsewhere: sum over ranks assembles).
+ * stereo-visual-slam_b200/sharding.py is the reference driver (torch.distributed, NCCL or gloo).
+ * ---------------------------------------------------------------------------------------------- */
+int vslam_ba_reduce_sizes(int n_poses, int* r1_doubles, int* r2_doubles, int* r3_doubles);
+int vslam_ba_session_begin(vslam_ctx* ctx, int n_poses, const double* poses, int n_points, const double* points,
+                           int n_obs, const int32_t* obs_pose, const int32_t* obs_point, const double* obs_uv,
+                           const double* Kmat, const vslam_ba_options* opt, int shard_begin, int shard_end,
+                           double* d_r1, double* d_r2, double* d_r3);
+int vslam_ba_session_phase(vslam_ctx* ctx, int phase, double value);
+int vslam_ba_session_trial_done(vslam_ctx* ctx, int accept);
+int vslam_ba_session_end(vslam_ctx* ctx, double* poses, double* points, double* chi2_per_obs, uint8_t* point_inlier);
+
 #ifdef __cplusplus
 }
 #endif

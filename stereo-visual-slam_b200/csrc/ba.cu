@@ -696,7 +696,14 @@ struct BaState {
     uint8_t* d_inlier;
     BaScalars* d_sc;
     BaScalars* h_sc;  // pinned
+    // landmark-sharded session (multi-GPU): parameters of the open session, current buffer, trial counter
+    BaParams* sess;
+    int sess_open, sess_cur, sess_trials;
+    double *sess_r1, *sess_r2, *sess_r3;
 };
+
+__global__ void ba_phase_kernel(const __grid_constant__ BaParams P, int phase, double lambda, int cur, int slot, double* r1,
+                                double* r3);
 
 // shared memory of one CTA: max(pose partials K*42, per-CTA S n*n+n, in-shared-memory Cholesky n*n+n) doubles
 static int ba_smem_bytes(int K) {
@@ -748,6 +755,7 @@ int vslam_ba_init(vslam_ctx* ctx) {
     }
     if (b->smem_bytes > 227 * 1024) return VSLAM_E_CAPACITY;
     VSLAM_CUDA(ctx, cudaFuncSetAttribute(ba_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
+    VSLAM_CUDA(ctx, cudaFuncSetAttribute(ba_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
     return VSLAM_OK;
 }
 
@@ -759,6 +767,7 @@ void vslam_ba_free(vslam_ctx* ctx) {
     cudaFree(b->d_bs); cudaFree(b->d_x); cudaFree(b->d_Spart); cudaFree(b->d_chi2); cudaFree(b->d_obs_pose);
     cudaFree(b->d_obs_point); cudaFree(b->d_obs_orig); cudaFree(b->d_lm_start); cudaFree(b->d_inlier); cudaFree(b->d_sc);
     cudaFreeHost(b->h_sc);
+    free(b->sess);
     free(b);
     ctx->ba = nullptr;
 }
@@ -853,5 +862,197 @@ extern "C" int vslam_ba_optimize(vslam_ctx* ctx, int n_poses, double* poses, int
         res->n_inlier_obs = b->h_sc->n_inlier_obs;
         res->n_outlier_obs = b->h_sc->n_outlier_obs;
     }
+    return VSLAM_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Landmark-sharded session: one process per GPU owns the landmarks [shard_begin, shard_end) with all
+// their observations; poses are replicated.  The caller runs the LM control flow and performs the collectives on the
+// three device reduce buffers between the phases (stereo-visual-slam_b200/sharding.py does it with torch.distributed):
+//   r1 = [Hpp (36K) | bp (6K) | chi2 | max|diag Hll|]     all-reduce(sum) once per outer iteration (+ max for r1[42K+1])
+//   r2 = [S (6K x 6K) | bs (6K)]                           all-reduce(sum) once per LM trial: the reduced camera system
+//   r3 = [chi2_trial | scale | ok | - | cnt_le[0..5]]      all-reduce(sum) once per LM trial (2 doubles) / once at the end
+// Every rank then solves the identical 6K x 6K system redundantly and back-substitutes its own landmarks.
+// ---------------------------------------------------------------------------------------------------------------
+enum { BA_PH_BUILD = 1, BA_PH_IMPORT_BUILD, BA_PH_SCHUR, BA_PH_SOLVE_UPDATE, BA_PH_RELABEL_COUNT, BA_PH_RELABEL_APPLY };
+
+__global__ void __launch_bounds__(BA_THREADS)
+ba_phase_kernel(const __grid_constant__ BaParams P, int phase, double lambda, int cur, int slot, double* r1, double* r3) {
+    extern __shared__ double smem[];
+    cg::grid_group grid = cg::this_grid();
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    const int n = P.n;
+    if (phase == BA_PH_BUILD) {
+        ba_phase_zero(P, gtid, gsize);
+        grid.sync();
+        ba_phase_build(P, cur, smem, gtid, gsize);
+        grid.sync();
+        if (gtid == 0) {
+            r1[42 * P.K] = P.sc->chi_cur;
+            r1[42 * P.K + 1] = __longlong_as_double((long long)P.sc->maxdiag_bits);
+            for (int r = 0; r < 6; ++r) P.sc->cnt_le[r] = 0;
+        }
+    } else if (phase == BA_PH_IMPORT_BUILD) {
+        if (gtid == 0) P.sc->chi_cur = r1[42 * P.K];
+    } else if (phase == BA_PH_SCHUR) {
+        ba_phase_schur_init(P, 0.0, slot, 0, gtid, gsize);  // partial system only: Hpp + lambda I is added after the reduce
+        grid.sync();
+        ba_phase_schur(P, lambda, smem, gtid, gsize);
+        grid.sync();
+        ba_phase_schur_reduce(P, gtid, gsize);
+    } else if (phase == BA_PH_SOLVE_UPDATE) {
+        for (int i = gtid; i < n * n; i += gsize) {  // S (reduced over ranks) += Hpp (reduced) + lambda I
+            const int r = i / n, c = i - r * n;
+            double v = 0.0;
+            if (r / 6 == c / 6) v = P.Hpp[(r / 6) * 36 + (r % 6) * 6 + (c % 6)];
+            if (r == c) v += lambda;
+            P.S[i] += v;
+        }
+        for (int i = gtid; i < n; i += gsize) P.bs[i] += P.bp[i];
+        grid.sync();
+        if (n <= BA_SMEM_CHOL_MAX) ba_phase_solve_cta(P, slot, smem);
+        else ba_phase_solve_grid(P, slot, grid, gtid, gsize);
+        grid.sync();
+        ba_phase_update(P, cur, lambda, slot, gtid, gsize);
+        grid.sync();
+        ba_phase_trial_err(P, cur, slot, gtid, gsize);
+        grid.sync();
+        if (gtid == 0) {
+            r3[0] = P.sc->chi_trial[slot];
+            r3[1] = P.sc->scale[slot];
+            r3[2] = (double)P.sc->solve_ok[slot];
+        }
+    } else if (phase == BA_PH_RELABEL_COUNT) {
+        ba_phase_relabel_count(P, gtid, gsize);
+        grid.sync();
+        if (gtid == 0)
+            for (int r = 0; r < 6; ++r) r3[4 + r] = (double)P.sc->cnt_le[r];
+    } else if (phase == BA_PH_RELABEL_APPLY) {
+        ba_phase_relabel_apply(P, lambda /* carries the threshold */, gtid, gsize);
+    }
+}
+
+extern "C" int vslam_ba_reduce_sizes(int n_poses, int* r1_doubles, int* r2_doubles, int* r3_doubles) {
+    if (n_poses <= 0) return VSLAM_E_INVALID;
+    const int n = 6 * n_poses;
+    if (r1_doubles) *r1_doubles = 42 * n_poses + 2;
+    if (r2_doubles) *r2_doubles = n * n + n;
+    if (r3_doubles) *r3_doubles = 10;
+    return VSLAM_OK;
+}
+
+extern "C" int vslam_ba_session_begin(vslam_ctx* ctx, int n_poses, const double* poses, int n_points,
+                                      const double* points, int n_obs, const int32_t* obs_pose,
+                                      const int32_t* obs_point, const double* obs_uv, const double* Kmat,
+                                      const vslam_ba_options* opt, int shard_begin, int shard_end, double* d_r1,
+                                      double* d_r2, double* d_r3) {
+    if (!ctx || !poses || !points || !Kmat || !opt || !d_r1 || !d_r2 || !d_r3) return VSLAM_E_INVALID;
+    if (n_poses <= 0 || n_points <= 0 || n_obs <= 0 || !obs_pose || !obs_point || !obs_uv) return VSLAM_E_INVALID;
+    if (shard_begin < 0 || shard_end > n_points || shard_begin > shard_end) return VSLAM_E_INVALID;
+    BaState* b = ctx->ba;
+    if (!b || !b->d_poses) return VSLAM_E_CAPACITY;
+    if (n_poses > b->maxK || n_points > b->maxL || n_obs > b->maxObs) return VSLAM_E_CAPACITY;
+    const int K = n_poses, L = n_points;
+    std::vector<int> lm_start(L + 1, 0), op(n_obs), ol(n_obs), oo(n_obs);
+    std::vector<double> uv(2 * (size_t)n_obs);
+    for (int i = 0; i < n_obs; ++i) {
+        if (obs_point[i] < 0 || obs_point[i] >= L || obs_pose[i] < 0 || obs_pose[i] >= K) return VSLAM_E_INVALID;
+        lm_start[obs_point[i] + 1]++;
+    }
+    for (int l = 0; l < L; ++l) lm_start[l + 1] += lm_start[l];
+    {
+        std::vector<int> fill(lm_start.begin(), lm_start.end() - 1);
+        for (int i = 0; i < n_obs; ++i) {
+            const int d = fill[obs_point[i]]++;
+            op[d] = obs_pose[i]; ol[d] = obs_point[i]; oo[d] = i;
+            uv[2 * d] = obs_uv[2 * i]; uv[2 * d + 1] = obs_uv[2 * i + 1];
+        }
+    }
+    cudaStream_t s = ctx->stream;
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_poses, poses, (size_t)K * 96, cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_points, points, (size_t)L * 24, cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_points + (size_t)L * 3, points, (size_t)L * 24, cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_pose, op.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_point, ol.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_orig, oo.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_uv, uv.data(), (size_t)n_obs * 16, cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_lm_start, lm_start.data(), (size_t)(L + 1) * 4, cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemsetAsync(b->d_chi2, 0, (size_t)n_obs * 8, s));
+    VSLAM_CUDA(ctx, cudaMemsetAsync(b->d_inlier, 0, (size_t)L, s));
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(s));  // the host staging vectors go out of scope
+    if (!b->sess) b->sess = (BaParams*)calloc(1, sizeof(BaParams));
+    BaParams& P = *b->sess;
+    memset(&P, 0, sizeof(P));
+    P.K = K; P.L = L; P.n_obs = n_obs; P.pose_only = opt->pose_only ? 1 : 0;
+    P.num_iterations = opt->num_iterations; P.max_trials = opt->max_trials > 0 ? opt->max_trials : 10;
+    P.delta = opt->huber_delta; P.tau = opt->tau > 0 ? opt->tau : 1e-5; P.chi2_th = opt->chi2_threshold;
+    memcpy(P.Kc, Kmat, 72);
+    P.n = 6 * K;
+    P.use_smem_S = (!P.pose_only && P.n <= BA_SMEM_S_MAX) ? 1 : 0;
+    P.n_cta = b->n_cta;
+    P.shard_L0 = shard_begin; P.shard_L1 = shard_end;
+    P.poses = b->d_poses; P.points = b->d_points; P.obs_pose = b->d_obs_pose; P.obs_point = b->d_obs_point;
+    P.obs_uv = b->d_uv; P.obs_orig = b->d_obs_orig; P.lm_start = b->d_lm_start; P.err = b->d_err; P.Hpl = b->d_Hpl;
+    P.Hll = b->d_Hll; P.bl = b->d_bl; P.Dinv = b->d_Dinv;
+    P.Hpp = d_r1; P.bp = d_r1 + 36 * K;          // pose blocks live in the caller's reduce buffer r1
+    P.S = d_r2; P.bs = d_r2 + (size_t)P.n * P.n;  // reduced camera system lives in r2
+    P.x = b->d_x; P.S_part = b->d_Spart; P.sc = b->d_sc; P.chi2_out = b->d_chi2; P.inlier_out = b->d_inlier;
+    b->sess_open = 1; b->sess_cur = 0; b->sess_trials = 0;
+    b->sess_r1 = d_r1; b->sess_r2 = d_r2; b->sess_r3 = d_r3;
+    return VSLAM_OK;
+}
+
+static int ba_session_launch(vslam_ctx* ctx, int phase, double lambda) {
+    BaState* b = ctx->ba;
+    if (!b || !b->sess_open) return VSLAM_E_INVALID;
+    BaParams P = *b->sess;
+    int cur = b->sess_cur, slot = b->sess_trials & 1;
+    double* r1 = b->sess_r1;
+    double* r3 = b->sess_r3;
+    void* args[] = {(void*)&P, (void*)&phase, (void*)&lambda, (void*)&cur, (void*)&slot, (void*)&r1, (void*)&r3};
+    vslam_time_begin(ctx, VK_BA_MISC);
+    VSLAM_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)ba_phase_kernel, dim3(b->n_cta), dim3(BA_THREADS), args,
+                                                (size_t)ba_smem_bytes(P.K), ctx->stream));
+    vslam_time_end(ctx);
+    VSLAM_LAUNCH_CHECK(ctx, "ba_phase_kernel");
+    return VSLAM_OK;
+}
+
+// phase: 1 BUILD, 2 IMPORT_BUILD, 3 SCHUR(lambda), 4 SOLVE_UPDATE(lambda), 5 RELABEL_COUNT, 6 RELABEL_APPLY(threshold)
+extern "C" int vslam_ba_session_phase(vslam_ctx* ctx, int phase, double value) {
+    if (!ctx || phase < BA_PH_BUILD || phase > BA_PH_RELABEL_APPLY) return VSLAM_E_INVALID;
+    return ba_session_launch(ctx, phase, value);
+}
+
+// LM verdict for the trial just evaluated: accept != 0 makes the trial estimate current (g2o discardTop), else pop()
+extern "C" int vslam_ba_session_trial_done(vslam_ctx* ctx, int accept) {
+    if (!ctx || !ctx->ba || !ctx->ba->sess_open) return VSLAM_E_INVALID;
+    if (accept) ctx->ba->sess_cur = 1 - ctx->ba->sess_cur;
+    ctx->ba->sess_trials++;
+    return VSLAM_OK;
+}
+
+// download: poses (replicated), and this rank's shard of points / per-edge chi2 (insertion order; zeros elsewhere) /
+// inlier flags (zeros elsewhere) so that a sum over ranks assembles the full arrays
+extern "C" int vslam_ba_session_end(vslam_ctx* ctx, double* poses, double* points, double* chi2_per_obs,
+                                    uint8_t* point_inlier) {
+    if (!ctx || !ctx->ba || !ctx->ba->sess_open) return VSLAM_E_INVALID;
+    BaState* b = ctx->ba;
+    const BaParams& P = *b->sess;
+    cudaStream_t s = ctx->stream;
+    const int cur = b->sess_cur;
+    if (poses) VSLAM_CUDA(ctx, cudaMemcpyAsync(poses, P.poses + (size_t)cur * P.K * 12, (size_t)P.K * 96, cudaMemcpyDeviceToHost, s));
+    if (points) {
+        memset(points, 0, (size_t)P.L * 24);
+        const double* src = P.points + (size_t)(P.pose_only ? 0 : cur) * P.L * 3;
+        if (P.shard_L1 > P.shard_L0)
+            VSLAM_CUDA(ctx, cudaMemcpyAsync(points + 3 * (size_t)P.shard_L0, src + 3 * (size_t)P.shard_L0,
+                                            (size_t)(P.shard_L1 - P.shard_L0) * 24, cudaMemcpyDeviceToHost, s));
+    }
+    if (chi2_per_obs) VSLAM_CUDA(ctx, cudaMemcpyAsync(chi2_per_obs, b->d_chi2, (size_t)P.n_obs * 8, cudaMemcpyDeviceToHost, s));
+    if (point_inlier) VSLAM_CUDA(ctx, cudaMemcpyAsync(point_inlier, b->d_inlier, (size_t)P.L, cudaMemcpyDeviceToHost, s));
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(s));
+    b->sess_open = 0;
     return VSLAM_OK;
 }

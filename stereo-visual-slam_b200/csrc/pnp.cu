@@ -280,7 +280,6 @@ pnp_refine_kernel(const float* __restrict__ xyz, const float* __restrict__ uv, i
                   int* __restrict__ inl) {
     __shared__ double sT[12];
     __shared__ double sH[PNP_THREADS / 32][28];
-    __shared__ double sx[6];
     __shared__ int s_best, s_stop, s_base, s_warp[PNP_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {

@@ -81,6 +81,12 @@ SIGNATURES = {
                                C.POINTER(BaResult), _vp, _vp]),
     "vslam_pnp_ransac": (_i, [_vp, _vp, _vp, _i, _vp, _i, _f, _d, _vp, _vp, _vp, _vp, _pi]),
     "vslam_anms": (_i, [_vp, _vp, _i, _i, _f, _vp, _pi]),
+    "vslam_ba_reduce_sizes": (_i, [_i, _pi, _pi, _pi]),
+    "vslam_ba_session_begin": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, C.POINTER(BaOptions), _i, _i, _vp,
+                                    _vp, _vp]),
+    "vslam_ba_session_phase": (_i, [_vp, _i, _d]),
+    "vslam_ba_session_trial_done": (_i, [_vp, _i]),
+    "vslam_ba_session_end": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "vslam_match_hamming_batch_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _d, _d, _vp, _i, _vp]),
 }
 
@@ -334,3 +340,45 @@ class Context:
         st = self.lib.vslam_anms(self.h, _ptr(kp), len(kp), int(num), float(c_robust), _ptr(keep), C.byref(n))
         self.check(st, "vslam_anms")
         return keep[:n.value].copy()
+
+    # ---- K17: landmark-sharded BA session (driver: sharding.ba_optimize_sharded) ------------
+    def ba_session(self, problem, shard, r1, r2, r3, **opt):
+        return GpuBaSession(self, problem, shard, r1, r2, r3, **opt)
+
+
+def ba_reduce_sizes(n_poses: int):
+    """(r1, r2, r3) sizes in doubles of the three reduce buffers for a window of n_poses keyframes."""
+    return 42 * n_poses + 2, 36 * n_poses * n_poses + 6 * n_poses, 10
+
+
+class GpuBaSession:
+    """One rank's side of the landmark-sharded BA: thin wrapper over vslam_ba_session_* (see include/vslam_b200.h)."""
+    BUILD, IMPORT_BUILD, SCHUR, SOLVE_UPDATE, RELABEL_COUNT, RELABEL_APPLY = 1, 2, 3, 4, 5, 6
+
+    def __init__(self, ctx, problem, shard, r1, r2, r3, num_iterations=10, pose_only=False, huber_delta=5.991,
+                 chi2_th=5.991, max_trials=10, tau=1e-5):
+        self.ctx = ctx
+        self.poses = np.ascontiguousarray(problem["poses"], dtype=np.float64).reshape(-1, 12)
+        self.points = np.ascontiguousarray(problem["points"], dtype=np.float64).reshape(-1, 3)
+        self.op = np.ascontiguousarray(problem["obs_pose"], dtype=np.int32)
+        self.ol = np.ascontiguousarray(problem["obs_point"], dtype=np.int32)
+        self.uv = np.ascontiguousarray(problem["obs_uv"], dtype=np.float64).reshape(-1, 2)
+        Kc = np.ascontiguousarray(problem["K"], dtype=np.float64).reshape(9)
+        opt = BaOptions(huber_delta, chi2_th, int(num_iterations), int(pose_only), int(max_trials), 0, tau)
+        st = ctx.lib.vslam_ba_session_begin(ctx.h, len(self.poses), _ptr(self.poses), len(self.points), _ptr(self.points),
+                                            len(self.op), _ptr(self.op), _ptr(self.ol), _ptr(self.uv), _ptr(Kc),
+                                            C.byref(opt), int(shard[0]), int(shard[1]), _ptr(r1), _ptr(r2), _ptr(r3))
+        ctx.check(st, "vslam_ba_session_begin")
+
+    def phase(self, phase: int, value: float = 0.0):
+        self.ctx.check(self.ctx.lib.vslam_ba_session_phase(self.ctx.h, int(phase), float(value)), "vslam_ba_session_phase")
+
+    def trial_done(self, accept: bool):
+        self.ctx.check(self.ctx.lib.vslam_ba_session_trial_done(self.ctx.h, int(accept)), "vslam_ba_session_trial_done")
+
+    def end(self):
+        poses = np.zeros_like(self.poses); points = np.zeros_like(self.points)
+        chi2 = np.zeros(len(self.op)); inl = np.zeros(len(self.points), dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.vslam_ba_session_end(self.ctx.h, _ptr(poses), _ptr(points), _ptr(chi2), _ptr(inl)),
+                       "vslam_ba_session_end")
+        return poses, points, chi2, inl
