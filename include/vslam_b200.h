@@ -227,6 +227,10 @@ typedef struct vslam_ba_result {
     int32_t n_inlier_obs, n_outlier_obs;
 } vslam_ba_result;
 
+/* device-side phase profile of the last vslam_ba_optimize call: nanoseconds (GPU globaltimer) spent in
+ * [zero, build, schur_init, schur, schur_reduce, solve, update, trial_err] incl. their grid-wide barriers */
+int vslam_ba_last_phase_ns(vslam_ctx* ctx, uint64_t* ns8);
+
 int vslam_ba_optimize(vslam_ctx* ctx, int n_poses, double* poses, int n_points, double* points, int n_obs,
                       const int32_t* obs_pose, const int32_t* obs_point, const double* obs_uv, const double* Kmat,
                       const vslam_ba_options* opt, vslam_ba_result* res, double* chi2_per_obs,

@@ -26,7 +26,6 @@
 namespace cg = cooperative_groups;
 
 #define BA_THREADS 256
-#define BA_SMEM_S_MAX 96     // reduced system accumulated in shared memory per CTA up to this dimension
 #define BA_SMEM_CHOL_MAX 160 // Cholesky in shared memory up to this dimension
 
 struct BaScalars {
@@ -41,6 +40,7 @@ struct BaScalars {
     double chi2_initial, chi2_final, lambda_final, chi2_threshold;
     int n_inlier_obs, n_outlier_obs;
     int pad;
+    unsigned long long phase_ns[12];  // device-side profile of the persistent kernel (globaltimer, thread 0)
 };
 
 struct BaParams {
@@ -48,7 +48,6 @@ struct BaParams {
     double delta, tau, chi2_th;
     double Kc[9];
     int n;                 // 6K
-    int use_smem_S;        // per-CTA shared-memory S + deterministic reduce
     int n_cta;             // grid size (partials)
     int shard_L0, shard_L1;  // landmark range owned by this rank (multi-GPU); [0, L) on one GPU
     double* poses;         // [2][K][12]
@@ -58,6 +57,13 @@ struct BaParams {
     const double* obs_uv;  // [n_obs][2]
     const int* obs_orig;   // original (insertion-order) index of sorted observation i
     const int* lm_start;   // [L+1]
+    const int* pose_start; // [K+1]   pose-major CSR over the (landmark-sorted) observation indices
+    const int* pose_obs;   // [n_obs]
+    int* obs_of;           // [K][L]  observation index of (pose, landmark) or -1 (filled by BUILD)
+    double* dbl;           // [L][3]  Dinv * bl
+    double* Ubuf;          // [n][n] Cholesky factor rows of the grid-wide solver
+    int* block_flag;       // [K(K+1)/2] 1 if some landmark joins poses (ki, kj): set once by the first BUILD
+    int has_dup;           // some landmark is observed twice by one pose: use the atomic Schur path
     double* err;           // [n_obs][2]  the edges' _error (last computed, trial or not -- as in g2o)
     double* Hpl;           // [n_obs][18]
     double* Hll;           // [L][9]
@@ -68,7 +74,6 @@ struct BaParams {
     double* S;             // [n][n]
     double* bs;            // [n]
     double* x;             // [n + 3L]
-    double* S_part;        // [n_cta][n*n + n]
     BaScalars* sc;
     double* chi2_out;      // [n_obs] original order
     uint8_t* inlier_out;   // [L]
@@ -139,6 +144,20 @@ __device__ __forceinline__ void residual_dev(const double* T, const double* p, c
     e1 = v - q1 / q2;
 }
 
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define BA_TICK(slot)                                        \
+    do {                                                     \
+        if (gtid == 0) {                                     \
+            const unsigned long long now__ = gtimer();       \
+            sc->phase_ns[slot] += now__ - t_last;            \
+            t_last = now__;                                  \
+        }                                                    \
+    } while (0)
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
@@ -148,145 +167,184 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ---------------------------------------------------------------------------------------------------------------
 // phases (grid-wide; called either from the persistent kernel or one kernel per phase)
 // ---------------------------------------------------------------------------------------------------------------
-// ZERO: clear the accumulators BUILD adds into
+// ZERO: clear the accumulators the BUILD phases add into
 __device__ void ba_phase_zero(const BaParams& P, int gtid, int gsize) {
     for (int i = gtid; i < P.K * 36; i += gsize) P.Hpp[i] = 0.0;
     for (int i = gtid; i < P.n; i += gsize) P.bp[i] = 0.0;
+    if (!P.pose_only) {
+        for (int i = P.shard_L0 * 9 + gtid; i < P.shard_L1 * 9; i += gsize) P.Hll[i] = 0.0;
+        for (int i = P.shard_L0 * 3 + gtid; i < P.shard_L1 * 3; i += gsize) P.bl[i] = 0.0;
+    }
     if (gtid == 0) {
         P.sc->chi_cur = 0.0;
         P.sc->maxdiag_bits = 0ull;
     }
 }
 
-// BUILD: computeActiveErrors + activeRobustChi2 + buildSystem (K13), one thread per landmark
-__device__ void ba_phase_build(const BaParams& P, int cur, double* smem, int gtid, int gsize) {
-    // shared partial pose blocks: Hpp [K][36] then bp [6K]
-    double* sHpp = smem;
-    double* sbp = smem + P.K * 36;
-    for (int i = threadIdx.x; i < P.K * 42; i += blockDim.x) smem[i] = 0.0;
-    __syncthreads();
+// residual, Huber weight and pose Jacobian of one edge (optimization.cpp:41-73 / 75-101)
+__device__ __forceinline__ void ba_edge(const BaParams& P, const double* T, const double* p, double u, double v,
+                                        double& e0, double& e1, double& r0, double& w, double* A) {
+    double pc[3];
+    residual_dev(T, p, P.Kc, u, v, e0, e1, pc);
+    huber_dev(e0 * e0 + e1 * e1, P.delta, r0, w);
+    const double fx = P.Kc[0], fy = P.Kc[4];
+    const double X = pc[0], Y = pc[1], Z = pc[2];
+    if (!P.pose_only) {  // optimization.cpp:52-73
+        const double Zinv = 1.0 / (Z + 1e-18), Zinv2 = Zinv * Zinv;
+        A[0] = -fx * Zinv; A[1] = 0; A[2] = fx * X * Zinv2; A[3] = fx * X * Y * Zinv2;
+        A[4] = -fx - fx * X * X * Zinv2; A[5] = fx * Y * Zinv;
+        A[6] = 0; A[7] = -fy * Zinv; A[8] = fy * Y * Zinv2; A[9] = fy + fy * Y * Y * Zinv2;
+        A[10] = -fy * X * Y * Zinv2; A[11] = -fy * X * Zinv;
+    } else {             // optimization.cpp:84-101
+        const double Z2 = Z * Z;
+        A[0] = -fx / Z; A[1] = 0; A[2] = fx * X / Z2; A[3] = fx * X * Y / Z2; A[4] = -fx - fx * X * X / Z2;
+        A[5] = fx * Y / Z;
+        A[6] = 0; A[7] = -fy / Z; A[8] = fy * Y / (Z * Z); A[9] = fy + fy * Y * Y / Z2; A[10] = -fy * X * Y / Z2;
+        A[11] = -fy * X / Z;
+    }
+}
+
+// BUILD-A (K13, per edge): computeActiveErrors + activeRobustChi2 + the landmark side of buildSystem.
+// One thread per observation; the 3x3 landmark blocks take fp64 reductions at L2 (a landmark has a handful of edges,
+// so no contention); Hpl (6x3) is stored per edge; obs_of records which edge joins (pose, landmark).
+__device__ void ba_phase_build_edges(const BaParams& P, int cur, int gtid, int gsize) {
     const double* poses = P.poses + (size_t)cur * P.K * 12;
     const double* points = P.points + (size_t)cur * P.L * 3;
-    const double fx = P.Kc[0], fy = P.Kc[4];
-    double chi = 0.0, mdiag = 0.0;
-    for (int l = P.shard_L0 + gtid; l < P.shard_L1; l += gsize) {
-        const int o0 = P.lm_start[l], o1 = P.lm_start[l + 1];
-        double hll[6] = {0, 0, 0, 0, 0, 0};  // upper triangle 00 01 02 11 12 22
-        double b3[3] = {0, 0, 0};
+    double chi = 0.0;
+    const int i0 = P.lm_start[P.shard_L0], i1 = P.lm_start[P.shard_L1];
+    for (int i = i0 + gtid; i < i1; i += gsize) {
+        const int k = P.obs_pose[i], l = P.obs_point[i];
+        const double* T = poses + 12 * k;
         const double p[3] = {points[3 * l], points[3 * l + 1], points[3 * l + 2]};
-        for (int i = o0; i < o1; ++i) {
-            const int k = P.obs_pose[i];
-            const double* T = poses + 12 * k;
-            double pc[3], e0, e1;
-            residual_dev(T, p, P.Kc, P.obs_uv[2 * i], P.obs_uv[2 * i + 1], e0, e1, pc);
-            P.err[2 * i] = e0;
-            P.err[2 * i + 1] = e1;
-            double r0, w;
-            huber_dev(e0 * e0 + e1 * e1, P.delta, r0, w);
-            chi += r0;
-            const double X = pc[0], Y = pc[1], Z = pc[2];
-            double A[12];
-            if (!P.pose_only) {  // optimization.cpp:52-73
-                const double Zinv = 1.0 / (Z + 1e-18), Zinv2 = Zinv * Zinv;
-                A[0] = -fx * Zinv; A[1] = 0; A[2] = fx * X * Zinv2; A[3] = fx * X * Y * Zinv2;
-                A[4] = -fx - fx * X * X * Zinv2; A[5] = fx * Y * Zinv;
-                A[6] = 0; A[7] = -fy * Zinv; A[8] = fy * Y * Zinv2; A[9] = fy + fy * Y * Y * Zinv2;
-                A[10] = -fy * X * Y * Zinv2; A[11] = -fy * X * Zinv;
-            } else {             // optimization.cpp:84-101
-                const double Z2 = Z * Z;
-                A[0] = -fx / Z; A[1] = 0; A[2] = fx * X / Z2; A[3] = fx * X * Y / Z2; A[4] = -fx - fx * X * X / Z2;
-                A[5] = fx * Y / Z;
-                A[6] = 0; A[7] = -fy / Z; A[8] = fy * Y / (Z * Z); A[9] = fy + fy * Y * Y / Z2; A[10] = -fy * X * Y / Z2;
-                A[11] = -fy * X / Z;
+        double e0, e1, r0, w, A[12];
+        ba_edge(P, T, p, P.obs_uv[2 * i], P.obs_uv[2 * i + 1], e0, e1, r0, w, A);
+        P.err[2 * i] = e0;
+        P.err[2 * i + 1] = e1;
+        chi += r0;
+        P.obs_of[(size_t)k * P.L + l] = i;
+        if (!P.pose_only) {
+            // which (ki <= kj) blocks of the reduced system are non-empty: idempotent stores, structure is fixed
+            for (int j = P.lm_start[l]; j < P.lm_start[l + 1]; ++j) {
+                const int kj = P.obs_pose[j];
+                if (kj >= k) P.block_flag[k * P.K - k * (k - 1) / 2 + (kj - k)] = 1;
             }
             const double om0 = -w * e0, om1 = -w * e1;
-            double* hk = sHpp + 36 * k;
+            double B[6];
 #pragma unroll
-            for (int a = 0; a < 6; ++a) {
-                atomicAdd(&sbp[6 * k + a], A[a] * om0 + A[6 + a] * om1);
+            for (int r = 0; r < 2; ++r)
 #pragma unroll
-                for (int b = 0; b < 6; ++b) atomicAdd(&hk[a * 6 + b], w * (A[a] * A[b] + A[6 + a] * A[6 + b]));
-            }
-            if (!P.pose_only) {
-                double B[6];
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) B[r * 3 + c] = A[r * 6] * T[c] + A[r * 6 + 1] * T[4 + c] + A[r * 6 + 2] * T[8 + c];
-                b3[0] += B[0] * om0 + B[3] * om1;
-                b3[1] += B[1] * om0 + B[4] * om1;
-                b3[2] += B[2] * om0 + B[5] * om1;
-                hll[0] += w * (B[0] * B[0] + B[3] * B[3]);
-                hll[1] += w * (B[0] * B[1] + B[3] * B[4]);
-                hll[2] += w * (B[0] * B[2] + B[3] * B[5]);
-                hll[3] += w * (B[1] * B[1] + B[4] * B[4]);
-                hll[4] += w * (B[1] * B[2] + B[4] * B[5]);
-                hll[5] += w * (B[2] * B[2] + B[5] * B[5]);
-                double* hp = P.Hpl + 18 * (size_t)i;
-#pragma unroll
-                for (int a = 0; a < 6; ++a)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) hp[a * 3 + c] = w * (A[a] * B[c] + A[6 + a] * B[3 + c]);
-            }
-        }
-        if (!P.pose_only) {
+                for (int c = 0; c < 3; ++c) B[r * 3 + c] = A[r * 6] * T[c] + A[r * 6 + 1] * T[4 + c] + A[r * 6 + 2] * T[8 + c];
             double* H = P.Hll + 9 * (size_t)l;
-            H[0] = hll[0]; H[1] = hll[1]; H[2] = hll[2];
-            H[3] = hll[1]; H[4] = hll[3]; H[5] = hll[4];
-            H[6] = hll[2]; H[7] = hll[4]; H[8] = hll[5];
-            P.bl[3 * l] = b3[0]; P.bl[3 * l + 1] = b3[1]; P.bl[3 * l + 2] = b3[2];
-            if (o1 > o0) mdiag = fmax(mdiag, fmax(fabs(hll[0]), fmax(fabs(hll[3]), fabs(hll[5]))));
+            double* bb = P.bl + 3 * (size_t)l;
+            atomicAdd(&bb[0], B[0] * om0 + B[3] * om1);
+            atomicAdd(&bb[1], B[1] * om0 + B[4] * om1);
+            atomicAdd(&bb[2], B[2] * om0 + B[5] * om1);
+            atomicAdd(&H[0], w * (B[0] * B[0] + B[3] * B[3]));
+            atomicAdd(&H[1], w * (B[0] * B[1] + B[3] * B[4]));
+            atomicAdd(&H[2], w * (B[0] * B[2] + B[3] * B[5]));
+            atomicAdd(&H[4], w * (B[1] * B[1] + B[4] * B[4]));
+            atomicAdd(&H[5], w * (B[1] * B[2] + B[4] * B[5]));
+            atomicAdd(&H[8], w * (B[2] * B[2] + B[5] * B[5]));
+            double* hp = P.Hpl + 18 * (size_t)i;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) hp[a * 3 + c] = w * (A[a] * B[c] + A[6 + a] * B[3 + c]);
         }
     }
     chi = warp_sum(chi);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mdiag = fmax(mdiag, __shfl_xor_sync(0xFFFFFFFFu, mdiag, o));
-    if ((threadIdx.x & 31) == 0) {
-        if (chi != 0.0) atomicAdd(&P.sc->chi_cur, chi);
-        if (mdiag > 0.0) atomicMax(&P.sc->maxdiag_bits, (unsigned long long)__double_as_longlong(mdiag));
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < P.K * 36; i += blockDim.x)
-        if (sHpp[i] != 0.0) atomicAdd(&P.Hpp[i], sHpp[i]);
-    for (int i = threadIdx.x; i < P.n; i += blockDim.x)
-        if (sbp[i] != 0.0) atomicAdd(&P.bp[i], sbp[i]);
-    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && chi != 0.0) atomicAdd(&P.sc->chi_cur, chi);
 }
 
-// SCHUR_INIT: S = Hpp (+ lambda on the diagonal), bs = bp; clear this trial's accumulator slots
-__device__ void ba_phase_schur_init(const BaParams& P, double lambda, int slot, int add_hpp, int gtid, int gsize) {
-    const int n = P.n;
-    for (int i = gtid; i < n * n; i += gsize) {
-        const int r = i / n, c = i - r * n;
-        double v = 0.0;
-        if (add_hpp && r / 6 == c / 6) v = P.Hpp[(r / 6) * 36 + (r % 6) * 6 + (c % 6)];
-        if (add_hpp && r == c) v += lambda;
-        P.S[i] = v;
+// BUILD-B (K13, per pose): Hpp_kk = sum w A^T A, bp_k = sum A^T (-w e) over the edges of pose k.  A CTA owns one
+// (pose, slice) work item: every thread accumulates its edges in registers (27 values: upper triangle + gradient), one
+// block reduction, and at most n_cta / K partial sums per address reach L2 -- instead of one atomic per edge per value.
+__device__ void ba_phase_build_poses(const BaParams& P, int cur, double* smem) {
+    const double* poses = P.poses + (size_t)cur * P.K * 12;
+    const double* points = P.points + (size_t)cur * P.L * 3;
+    const int parts = max(1, (int)gridDim.x / P.K);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int wi = blockIdx.x; wi < P.K * parts; wi += gridDim.x) {
+        const int k = wi % P.K, part = wi / P.K;
+        const int ps = P.pose_start[k], pe = P.pose_start[k + 1];
+        const double* T = poses + 12 * k;
+        double acc[27];
+#pragma unroll
+        for (int q = 0; q < 27; ++q) acc[q] = 0.0;
+        for (int t = ps + part * BA_THREADS + tid; t < pe; t += parts * BA_THREADS) {
+            const int i = P.pose_obs[t];
+            const int l = P.obs_point[i];
+            if (l < P.shard_L0 || l >= P.shard_L1) continue;
+            const double p[3] = {points[3 * l], points[3 * l + 1], points[3 * l + 2]};
+            double e0, e1, r0, w, A[12];
+            ba_edge(P, T, p, P.obs_uv[2 * i], P.obs_uv[2 * i + 1], e0, e1, r0, w, A);
+            const double om0 = -w * e0, om1 = -w * e1;
+            int q = 0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+#pragma unroll
+                for (int b = a; b < 6; ++b) acc[q++] += w * (A[a] * A[b] + A[6 + a] * A[6 + b]);
+            }
+#pragma unroll
+            for (int a = 0; a < 6; ++a) acc[21 + a] += A[a] * om0 + A[6 + a] * om1;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 27; ++q) {
+            const double v = warp_sum(acc[q]);
+            if (lane == 0) smem[warp * 27 + q] = v;
+        }
+        __syncthreads();
+        if (tid < 27) {
+            double v = 0.0;
+            for (int w8 = 0; w8 < BA_THREADS / 32; ++w8) v += smem[w8 * 27 + tid];
+            if (v != 0.0) {
+                if (tid < 21) {
+                    int a = 0, rem = tid;  // unpack upper-triangle index -> (a, b)
+                    while (rem >= 6 - a) { rem -= 6 - a; ++a; }
+                    atomicAdd(&P.Hpp[36 * k + a * 6 + a + rem], v);
+                } else {
+                    atomicAdd(&P.bp[6 * k + tid - 21], v);
+                }
+            }
+        }
     }
-    for (int i = gtid; i < n; i += gsize) P.bs[i] = add_hpp ? P.bp[i] : 0.0;
+}
+
+// MAXDIAG: max |diagonal| over this rank's landmark blocks (feeds computeLambdaInit); after BUILD-A + grid.sync
+__device__ void ba_phase_maxdiag(const BaParams& P, int gtid, int gsize) {
+    if (P.pose_only) return;
+    double mdiag = 0.0;
+    for (int l = P.shard_L0 + gtid; l < P.shard_L1; l += gsize) {
+        if (P.lm_start[l + 1] == P.lm_start[l]) continue;
+        const double* H = P.Hll + 9 * (size_t)l;
+        mdiag = fmax(mdiag, fmax(fabs(H[0]), fmax(fabs(H[4]), fabs(H[8]))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mdiag = fmax(mdiag, __shfl_xor_sync(0xFFFFFFFFu, mdiag, o));
+    if ((threadIdx.x & 31) == 0 && mdiag > 0.0)
+        atomicMax(&P.sc->maxdiag_bits, (unsigned long long)__double_as_longlong(mdiag));
+}
+
+__device__ void ba_phase_schur_init(const BaParams& P, double lambda, int add_hpp, int gtid, int gsize);
+
+// DINV (K14a): per landmark Dinv = (Hll + lambda I)^-1 by the direct 3x3 inverse, and Dinv * bl; clears this trial's
+// accumulator slots.
+__device__ void ba_phase_dinv(const BaParams& P, double lambda, int slot, int add_hpp, int gtid, int gsize) {
     if (gtid == 0) {
         P.sc->chi_trial[slot] = 0.0;
         P.sc->scale[slot] = 0.0;
         P.sc->solve_ok[slot] = 0;
     }
-}
-
-// SCHUR (K14): per landmark Dinv = (Hll + lambda I)^-1, S -= Hpl Dinv Hpl^T (upper block triangle), bs -= Hpl Dinv bl
-__device__ void ba_phase_schur(const BaParams& P, double lambda, double* smem, int gtid, int gsize) {
+    ba_phase_schur_init(P, lambda, add_hpp, gtid, gsize);  // S = [Hpp + lambda I], bs = bp; SCHUR subtracts from it
     if (P.pose_only) return;
-    const int n = P.n;
-    double* sS = smem;           // [n*n] when use_smem_S
-    double* sb = smem + n * n;   // [n]
-    if (P.use_smem_S) {
-        for (int i = threadIdx.x; i < n * n + n; i += blockDim.x) smem[i] = 0.0;
-        __syncthreads();
-    }
     for (int l = P.shard_L0 + gtid; l < P.shard_L1; l += gsize) {
-        const int o0 = P.lm_start[l], o1 = P.lm_start[l + 1];
         double* Di = P.Dinv + 9 * (size_t)l;
-        if (o1 == o0) {
+        double* db = P.dbl + 3 * (size_t)l;
+        if (P.lm_start[l + 1] == P.lm_start[l]) {
 #pragma unroll
             for (int q = 0; q < 9; ++q) Di[q] = 0.0;
+            db[0] = db[1] = db[2] = 0.0;
             continue;
         }
         const double* H = P.Hll + 9 * (size_t)l;
@@ -300,11 +358,42 @@ __device__ void ba_phase_schur(const BaParams& P, double lambda, double* smem, i
 #pragma unroll
         for (int q = 0; q < 9; ++q) Di[q] = d[q];
         const double b0 = P.bl[3 * l], b1 = P.bl[3 * l + 1], b2 = P.bl[3 * l + 2];
-        const double db0 = d[0] * b0 + d[1] * b1 + d[2] * b2, db1 = d[3] * b0 + d[4] * b1 + d[5] * b2,
-                     db2 = d[6] * b0 + d[7] * b1 + d[8] * b2;
-        for (int i = o0; i < o1; ++i) {
-            const int ki = P.obs_pose[i];
+        db[0] = d[0] * b0 + d[1] * b1 + d[2] * b2;
+        db[1] = d[3] * b0 + d[4] * b1 + d[5] * b2;
+        db[2] = d[6] * b0 + d[7] * b1 + d[8] * b2;
+    }
+}
+
+// SCHUR (K14b): the reduced camera system, one 6x6 block (ki <= kj, upper block triangle as g2o) per CTA work item:
+//   S_ij = [i==j] (Hpp_ii + lambda I) - sum over landmarks seen by both  Hpl_i Dinv Hpl_j^T,   bs_i = bp_i - sum Hpl_i Dinv bl
+// A thread walks (a slice of) pose ki's edges, finds the partner edge of pose kj on the same landmark through obs_of
+// and accumulates the 36 (+6) products in registers; one block reduction per work item, then one fp64 reduction per
+// value into the S initialised by DINV (n_cta / n_blocks partial sums per address at most).  Blocks that no landmark
+// joins are skipped through block_flag.
+__device__ void ba_phase_schur_blocks(const BaParams& P, double* smem) {
+    if (P.pose_only) return;
+    const int n = P.n, K = P.K;
+    const int nb = K * (K + 1) / 2;
+    const int parts = max(1, (int)gridDim.x / nb);  // CTAs per block when there are fewer blocks than CTAs
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int wi = blockIdx.x; wi < nb * parts; wi += gridDim.x) {
+        const int b = wi % nb, part = wi / nb;
+        if (!P.block_flag[b]) continue;  // uniform per CTA
+        int ki = 0, rem = b;             // unpack the upper-triangle block index
+        while (rem >= K - ki) { rem -= K - ki; ++ki; }
+        const int kj = ki + rem;
+        double acc[42];
+#pragma unroll
+        for (int q = 0; q < 42; ++q) acc[q] = 0.0;
+        const int ps = P.pose_start[ki], pe = P.pose_start[ki + 1];
+        for (int t = ps + part * BA_THREADS + tid; t < pe; t += parts * BA_THREADS) {
+            const int i = P.pose_obs[t];
+            const int l = P.obs_point[i];
+            if (l < P.shard_L0 || l >= P.shard_L1) continue;
+            const int j = (ki == kj) ? i : P.obs_of[(size_t)kj * P.L + l];
+            if (j < 0) continue;
             const double* Bi = P.Hpl + 18 * (size_t)i;
+            const double* d = P.Dinv + 9 * (size_t)l;
             double BD[18];
 #pragma unroll
             for (int a = 0; a < 6; ++a) {
@@ -312,78 +401,156 @@ __device__ void ba_phase_schur(const BaParams& P, double lambda, double* smem, i
                 BD[a * 3] = x0 * d[0] + x1 * d[3] + x2 * d[6];
                 BD[a * 3 + 1] = x0 * d[1] + x1 * d[4] + x2 * d[7];
                 BD[a * 3 + 2] = x0 * d[2] + x1 * d[5] + x2 * d[8];
-                const double vb = x0 * db0 + x1 * db1 + x2 * db2;
-                if (P.use_smem_S) atomicAdd(&sb[6 * ki + a], -vb);
-                else atomicAdd(&P.bs[6 * ki + a], -vb);
             }
-            for (int j = o0; j < o1; ++j) {
-                const int kj = P.obs_pose[j];
-                if (kj < ki) continue;  // upper block triangle only (as g2o); the solver mirrors it
-                const double* Bj = P.Hpl + 18 * (size_t)j;
-                double* dst = (P.use_smem_S ? sS : P.S) + (size_t)(6 * ki) * n + 6 * kj;
+            const double* Bj = P.Hpl + 18 * (size_t)j;
 #pragma unroll
-                for (int a = 0; a < 6; ++a)
+            for (int a = 0; a < 6; ++a)
 #pragma unroll
-                    for (int b = 0; b < 6; ++b) {
-                        if (ki == kj && b < a) continue;  // diagonal blocks: upper triangle only
-                        const double v = BD[a * 3] * Bj[b * 3] + BD[a * 3 + 1] * Bj[b * 3 + 1] + BD[a * 3 + 2] * Bj[b * 3 + 2];
-                        atomicAdd(&dst[a * n + b], -v);
-                    }
+                for (int c = 0; c < 6; ++c)
+                    acc[a * 6 + c] += BD[a * 3] * Bj[c * 3] + BD[a * 3 + 1] * Bj[c * 3 + 1] + BD[a * 3 + 2] * Bj[c * 3 + 2];
+            if (ki == kj) {
+                const double* db = P.dbl + 3 * (size_t)l;
+#pragma unroll
+                for (int a = 0; a < 6; ++a) acc[36 + a] += Bi[a * 3] * db[0] + Bi[a * 3 + 1] * db[1] + Bi[a * 3 + 2] * db[2];
+            }
+        }
+        __syncthreads();
+        const int nacc = (ki == kj) ? 42 : 36;
+#pragma unroll
+        for (int q = 0; q < 42; ++q) {
+            if (q < nacc) {
+                const double v = warp_sum(acc[q]);
+                if (lane == 0) smem[warp * 42 + q] = v;
+            }
+        }
+        __syncthreads();
+        if (tid < nacc) {
+            double v = 0.0;
+            for (int w8 = 0; w8 < BA_THREADS / 32; ++w8) v += smem[w8 * 42 + tid];
+            if (v != 0.0) {
+                if (tid < 36) atomicAdd(&P.S[(size_t)(6 * ki + tid / 6) * n + 6 * kj + tid % 6], -v);
+                else atomicAdd(&P.bs[6 * ki + tid - 36], -v);
             }
         }
     }
-    if (P.use_smem_S) {
-        __syncthreads();
-        double* part = P.S_part + (size_t)blockIdx.x * (n * n + n);
-        for (int i = threadIdx.x; i < n * n + n; i += blockDim.x) part[i] = smem[i];
-        __syncthreads();
+}
+
+// SCHUR fallback when a landmark has two edges to the same pose (obs_of cannot hold both): initialise S, then one
+// thread per edge adds its products with fp64 reductions at L2.
+__device__ void ba_phase_schur_init(const BaParams& P, double lambda, int add_hpp, int gtid, int gsize) {
+    const int n = P.n;
+    for (int i = gtid; i < n * n; i += gsize) {
+        const int r = i / n, c = i - r * n;
+        double v = 0.0;
+        if (add_hpp && r / 6 == c / 6 && c >= r) v = P.Hpp[(r / 6) * 36 + (r % 6) * 6 + (c % 6)];
+        if (add_hpp && r == c) v += lambda;
+        P.S[i] = v;
+    }
+    for (int i = gtid; i < n; i += gsize) P.bs[i] = add_hpp ? P.bp[i] : 0.0;
+}
+
+__device__ void ba_phase_schur_atomic(const BaParams& P, int gtid, int gsize) {
+    if (P.pose_only) return;
+    const int n = P.n;
+    const int i0 = P.lm_start[P.shard_L0], i1 = P.lm_start[P.shard_L1];
+    for (int i = i0 + gtid; i < i1; i += gsize) {
+        const int l = P.obs_point[i];
+        const int o0 = P.lm_start[l], o1 = P.lm_start[l + 1];
+        const double* d = P.Dinv + 9 * (size_t)l;
+        const double* db = P.dbl + 3 * (size_t)l;
+        const int ki = P.obs_pose[i];
+        const double* Bi = P.Hpl + 18 * (size_t)i;
+        double BD[18];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const double x0 = Bi[a * 3], x1 = Bi[a * 3 + 1], x2 = Bi[a * 3 + 2];
+            BD[a * 3] = x0 * d[0] + x1 * d[3] + x2 * d[6];
+            BD[a * 3 + 1] = x0 * d[1] + x1 * d[4] + x2 * d[7];
+            BD[a * 3 + 2] = x0 * d[2] + x1 * d[5] + x2 * d[8];
+            atomicAdd(&P.bs[6 * ki + a], -(x0 * db[0] + x1 * db[1] + x2 * db[2]));
+        }
+        for (int j = o0; j < o1; ++j) {
+            const int kj = P.obs_pose[j];
+            if (kj < ki) continue;
+            const double* Bj = P.Hpl + 18 * (size_t)j;
+            double* dst = P.S + (size_t)(6 * ki) * n + 6 * kj;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    if (ki == kj && c < a) continue;
+                    atomicAdd(&dst[a * n + c], -(BD[a * 3] * Bj[c * 3] + BD[a * 3 + 1] * Bj[c * 3 + 1] + BD[a * 3 + 2] * Bj[c * 3 + 2]));
+                }
+        }
     }
 }
 
-// SCHUR_REDUCE: deterministic sum of the per-CTA partials into S / bs (shared-memory path only)
-__device__ void ba_phase_schur_reduce(const BaParams& P, int gtid, int gsize) {
-    if (P.pose_only || !P.use_smem_S) return;
-    const int n = P.n, tot = n * n + n;
-    for (int i = gtid; i < tot; i += gsize) {
-        double s = 0.0;
-        for (int c = 0; c < P.n_cta; ++c) s += P.S_part[(size_t)c * tot + i];
-        if (i < n * n) P.S[i] += s;
-        else P.bs[i - n * n] += s;
+// ---- K15: dense SPD solve of the reduced camera system, 6x6-blocked (the natural block size of the pose system) ----
+// Upper Cholesky S = U^T U.  Right-looking over block rows: (1) one thread factors the 6x6 diagonal block, (2) one
+// thread per trailing column forward-substitutes its 6 panel entries, (3) all threads apply the rank-6 update.
+
+// factor the 6x6 diagonal block at (j0, j0) of the row-major matrix M (leading dimension ld) in place; false if not PD
+__device__ __forceinline__ bool chol6_diag(double* M, int ld, int j0) {
+    bool ok = true;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        double d = M[(j0 + r) * ld + j0 + r];
+#pragma unroll
+        for (int p = 0; p < 6; ++p)
+            if (p < r) d -= M[(j0 + p) * ld + j0 + r] * M[(j0 + p) * ld + j0 + r];
+        if (!(d > 0.0) || !isfinite(d)) ok = false;
+        d = sqrt(d);
+        M[(j0 + r) * ld + j0 + r] = d;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            if (c > r) {
+                double v = M[(j0 + r) * ld + j0 + c];
+#pragma unroll
+                for (int p = 0; p < 6; ++p)
+                    if (p < r) v -= M[(j0 + p) * ld + j0 + r] * M[(j0 + p) * ld + j0 + c];
+                M[(j0 + r) * ld + j0 + c] = v / d;
+            }
+        }
     }
+    return ok;
 }
 
-// triangular solves U^T y = b, U x = y by one CTA (column-oriented, parallel over the trailing entries).
-// M holds the factor: either U itself (scaled = 1) or the un-normalised rows of the grid-wide LDL^T variant
-// (scaled = 0: U[j][c] = M[j][c] / sqrt(M[j][j]), U[j][j] = sqrt(M[j][j])).
-__device__ void ba_tri_solve_cta(const BaParams& P, const double* M, int scaled, double* work) {
+// blocked triangular solves U^T y = bs, U x = y by one CTA; U row-major with leading dimension n; y: n doubles of scratch
+__device__ void ba_tri_solve_cta(const BaParams& P, const double* U, double* y) {
     const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
-    double* y = work;  // n doubles (shared or global)
     for (int i = tid; i < n; i += nt) y[i] = P.bs[i];
     __syncthreads();
-    for (int i = 0; i < n; ++i) {  // forward: y_i /= U_ii; y_k -= U_ik y_i (k > i)
-        const double dii = M[i * n + i];
-        const double uii = scaled ? dii : sqrt(dii);
-        const double yi = y[i] / uii;
+    for (int j0 = 0; j0 < n; j0 += 6) {  // forward
+        if (tid == 0) {
+            for (int r = 0; r < 6; ++r) {
+                double v = y[j0 + r];
+                for (int p = 0; p < r; ++p) v -= U[(j0 + p) * n + j0 + r] * y[j0 + p];
+                y[j0 + r] = v / U[(j0 + r) * n + j0 + r];
+            }
+        }
         __syncthreads();
-        if (tid == 0) y[i] = yi;
-        const double f = scaled ? yi : yi / uii;
-        for (int k = i + 1 + tid; k < n; k += nt) y[k] -= M[i * n + k] * f;
+        for (int c = j0 + 6 + tid; c < n; c += nt) {
+            double v = y[c];
+#pragma unroll
+            for (int p = 0; p < 6; ++p) v -= U[(j0 + p) * n + c] * y[j0 + p];
+            y[c] = v;
+        }
         __syncthreads();
     }
-    for (int i = n - 1; i >= 0; --i) {  // backward: x_i = (y_i - sum_{k>i} U_ik x_k) / U_ii
-        const double dii = M[i * n + i];
-        const double uii = scaled ? dii : sqrt(dii);
-        double part = 0.0;
-        for (int k = i + 1 + tid; k < n; k += nt) part += M[i * n + k] * y[k];
-        part = warp_sum(part);
-        __shared__ double s_part[BA_THREADS / 32];
-        if ((tid & 31) == 0) s_part[tid >> 5] = part;
-        __syncthreads();
+    for (int j0 = n - 6; j0 >= 0; j0 -= 6) {  // backward
         if (tid == 0) {
-            double t = 0.0;
-            for (int w = 0; w < nt / 32; ++w) t += s_part[w];
-            if (!scaled) t /= uii;
-            y[i] = (y[i] - t) / uii;
+            for (int r = 5; r >= 0; --r) {
+                double v = y[j0 + r];
+                for (int p = r + 1; p < 6; ++p) v -= U[(j0 + r) * n + j0 + p] * y[j0 + p];
+                y[j0 + r] = v / U[(j0 + r) * n + j0 + r];
+            }
+        }
+        __syncthreads();
+        for (int r = tid; r < j0; r += nt) {
+            double v = y[r];
+#pragma unroll
+            for (int p = 0; p < 6; ++p) v -= U[r * n + j0 + p] * y[j0 + p];
+            y[r] = v;
         }
         __syncthreads();
     }
@@ -391,63 +558,121 @@ __device__ void ba_tri_solve_cta(const BaParams& P, const double* M, int scaled,
     __syncthreads();
 }
 
-// SOLVE (K15), small systems: dense Cholesky S = U^T U of the upper-stored SPD system in shared memory, one CTA
+// small systems (6K <= 160): everything in the shared memory of CTA 0
 __device__ void ba_phase_solve_cta(const BaParams& P, int slot, double* smem) {
     if (blockIdx.x != 0) return;
     const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
     __shared__ int s_fail;
-    __shared__ double s_d;
-    double* M = smem;  // n*n doubles, then n doubles of work space
+    double* M = smem;  // n*n doubles, then n doubles of scratch
     if (tid == 0) s_fail = 0;
     for (int i = tid; i < n * n; i += nt) M[i] = P.S[i];
     __syncthreads();
-    for (int j = 0; j < n; ++j) {
-        if (tid == 0) {
-            const double d = M[j * n + j];
-            if (!(d > 0.0) || !isfinite(d)) s_fail = 1;
-            s_d = sqrt(d);
+    for (int j0 = 0; j0 < n; j0 += 6) {
+        if (tid == 0) {  // diagonal block through registers (independent loads, then a dependent arithmetic chain)
+            double D[36];
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) D[r * 6 + c] = (c >= r) ? M[(j0 + r) * n + j0 + c] : 0.0;
+            if (!chol6_diag(D, 6, 0)) s_fail = 1;
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c < 6; ++c)
+                    if (c >= r) M[(j0 + r) * n + j0 + c] = D[r * 6 + c];
         }
         __syncthreads();
         if (s_fail) break;
-        const double dj = s_d;
-        for (int c = j + tid; c < n; c += nt) M[j * n + c] = (c == j) ? dj : M[j * n + c] / dj;  // row j of U
+        {
+            double D[36];
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) D[r * 6 + c] = (c >= r) ? M[(j0 + r) * n + j0 + c] : 0.0;
+            for (int c = j0 + 6 + tid; c < n; c += nt) {  // panel: 6 forward-substitution steps per column
+                double v[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) v[r] = M[(j0 + r) * n + c];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                    for (int p = 0; p < 6; ++p)
+                        if (p < r) v[r] -= D[p * 6 + r] * v[p];
+                    v[r] /= D[r * 6 + r];
+                }
+#pragma unroll
+                for (int r = 0; r < 6; ++r) M[(j0 + r) * n + c] = v[r];
+            }
+        }
         __syncthreads();
-        const int m = n - j - 1;  // trailing update: M[r][c] -= U[j][r] * U[j][c] for j < r <= c
+        const int m = n - j0 - 6;  // trailing update, upper triangle
         for (int e = tid; e < m * m; e += nt) {
-            const int r = j + 1 + e / m, c = j + 1 + e % m;
-            if (c >= r) M[r * n + c] -= M[j * n + r] * M[j * n + c];
+            const int r = j0 + 6 + e / m, c = j0 + 6 + e % m;
+            if (c < r) continue;
+            double v = M[r * n + c];
+#pragma unroll
+            for (int p = 0; p < 6; ++p) v -= M[(j0 + p) * n + r] * M[(j0 + p) * n + c];
+            M[r * n + c] = v;
         }
         __syncthreads();
     }
     const int fail = s_fail;
-    if (!fail) ba_tri_solve_cta(P, M, 1, M + n * n);
+    if (!fail) ba_tri_solve_cta(P, M, M + n * n);
     if (tid == 0) P.sc->solve_ok[slot] = fail ? 0 : 1;
 }
 
-// SOLVE (K15), large systems (6K > 160): grid-wide right-looking LDL^T on S in L2, one grid.sync per column,
-// followed by the triangular solves in CTA 0.  Row j is final after step j-1, so no in-place scaling is needed.
-__device__ void ba_phase_solve_grid(const BaParams& P, int slot, cg::grid_group& grid, int gtid, int gsize) {
-    const int n = P.n;
+// large systems (6K > 160): S stays in L2.  Per block row every CTA redundantly factors the diagonal block and the
+// 6 x m panel into its own shared memory (cheap), then all threads of the grid share the rank-6 trailing update:
+// ONE grid-wide barrier per block row (K of them) instead of one per column.  CTA 0 keeps the factor rows in Ubuf.
+__device__ void ba_phase_solve_grid(const BaParams& P, int slot, cg::grid_group& grid, double* smem, double* Ubuf,
+                                    int gtid, int gsize) {
+    const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
+    __shared__ int s_fail;
+    double* D = smem;            // 6 x 6 diagonal block (ld 6)
+    double* Up = smem + 36;      // 6 x n panel (ld n), columns >= j0 + 6 valid
     int fail = 0;
-    for (int j = 0; j < n - 1; ++j) {
-        const double d = P.S[j * n + j];
-        if (!(d > 0.0) || !isfinite(d)) {
-            fail = 1;  // uniform: every thread reads the same value after the previous grid.sync
+    for (int j0 = 0; j0 < n; j0 += 6) {
+        if (tid < 36) D[tid] = P.S[(size_t)(j0 + tid / 6) * n + j0 + tid % 6];
+        if (tid == 0) s_fail = 0;
+        __syncthreads();
+        if (tid == 0 && !chol6_diag(D, 6, 0)) s_fail = 1;
+        __syncthreads();
+        if (s_fail) {  // uniform over the grid: every CTA factors the same block
+            fail = 1;
             break;
         }
-        const double inv = 1.0 / d;
-        const int m = n - j - 1;
+        for (int c = j0 + 6 + tid; c < n; c += nt) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                double v = P.S[(size_t)(j0 + r) * n + c];
+                for (int p = 0; p < r; ++p) v -= D[p * 6 + r] * Up[p * n + c];
+                Up[r * n + c] = v / D[r * 6 + r];
+            }
+        }
+        __syncthreads();
+        if (blockIdx.x == 0) {
+            if (tid < 36) Ubuf[(size_t)(j0 + tid / 6) * n + j0 + tid % 6] = D[tid];
+            for (int e = tid; e < 6 * (n - j0 - 6); e += nt) {
+                const int r = e / (n - j0 - 6), c = j0 + 6 + e % (n - j0 - 6);
+                Ubuf[(size_t)(j0 + r) * n + c] = Up[r * n + c];
+            }
+        }
+        const int m = n - j0 - 6;
         for (int e = gtid; e < m * m; e += gsize) {
-            const int r = j + 1 + e / m, c = j + 1 + e % m;
-            if (c >= r) P.S[r * n + c] -= P.S[j * n + r] * P.S[j * n + c] * inv;
+            const int r = j0 + 6 + e / m, c = j0 + 6 + e % m;
+            if (c < r) continue;
+            double v = P.S[(size_t)r * n + c];
+#pragma unroll
+            for (int p = 0; p < 6; ++p) v -= Up[p * n + r] * Up[p * n + c];
+            P.S[(size_t)r * n + c] = v;
         }
         grid.sync();
     }
-    if (!fail) {
-        const double d = P.S[(n - 1) * n + n - 1];
-        if (!(d > 0.0) || !isfinite(d)) fail = 1;
+    if (!fail && blockIdx.x == 0) {
+        __threadfence();
+        __syncthreads();
+        ba_tri_solve_cta(P, Ubuf, smem);
     }
-    if (!fail && blockIdx.x == 0) ba_tri_solve_cta(P, P.S, 0, P.x + P.n + 3 * (size_t)P.L);  // work space behind x
     if (gtid == 0) P.sc->solve_ok[slot] = fail ? 0 : 1;
 }
 
@@ -585,15 +810,25 @@ ba_lm_kernel(const __grid_constant__ BaParams P) {
     int cur = 0, trials = 0, accepted = 0, it = 0;
     double lambda = 0.0, ni = 2.0, chi_first = 0.0, chi_last = 0.0;
 
+    unsigned long long t_last = 0;
     if (gtid == 0) {
 #pragma unroll
         for (int r = 0; r < 6; ++r) sc->cnt_le[r] = 0;
+        for (int r = 0; r < 12; ++r) sc->phase_ns[r] = 0;
+        t_last = gtimer();
     }
     for (it = 0; it < P.num_iterations; ++it) {
         ba_phase_zero(P, gtid, gsize);
         grid.sync();
-        ba_phase_build(P, cur, smem, gtid, gsize);
+        BA_TICK(0);
+        ba_phase_build_edges(P, cur, gtid, gsize);
+        ba_phase_build_poses(P, cur, smem);
+        if (it == 0) {
+            grid.sync();  // Hll complete
+            ba_phase_maxdiag(P, gtid, gsize);
+        }
         grid.sync();
+        BA_TICK(1);
         double currentChi = sc->chi_cur;
         if (it == 0) {
             chi_first = currentChi;
@@ -611,19 +846,24 @@ ba_lm_kernel(const __grid_constant__ BaParams P) {
         int qmax = 0;
         do {
             const int slot = trials & 1;
-            ba_phase_schur_init(P, lambda, slot, 1, gtid, gsize);
+            ba_phase_dinv(P, lambda, slot, 1, gtid, gsize);
             grid.sync();
-            ba_phase_schur(P, lambda, smem, gtid, gsize);
+            BA_TICK(2);
+            if (P.has_dup) ba_phase_schur_atomic(P, gtid, gsize);
+            else ba_phase_schur_blocks(P, smem);
             grid.sync();
-            ba_phase_schur_reduce(P, gtid, gsize);
-            grid.sync();
+            BA_TICK(3);
+            BA_TICK(4);
             if (P.n <= BA_SMEM_CHOL_MAX) ba_phase_solve_cta(P, slot, smem);
-            else ba_phase_solve_grid(P, slot, grid, gtid, gsize);
+            else ba_phase_solve_grid(P, slot, grid, smem, P.Ubuf, gtid, gsize);
             grid.sync();
+            BA_TICK(5);
             ba_phase_update(P, cur, lambda, slot, gtid, gsize);
             grid.sync();
+            BA_TICK(6);
             ba_phase_trial_err(P, cur, slot, gtid, gsize);
             grid.sync();
+            BA_TICK(7);
             const int ok2 = sc->solve_ok[slot];
             const double tempChi = ok2 ? sc->chi_trial[slot] : DBL_MAX;
             const double scale = (ok2 ? sc->scale[slot] : 0.0) + 1e-3;
@@ -655,7 +895,7 @@ ba_lm_kernel(const __grid_constant__ BaParams P) {
     if (P.num_iterations <= 0) {
         ba_phase_zero(P, gtid, gsize);
         grid.sync();
-        ba_phase_build(P, cur, smem, gtid, gsize);
+        ba_phase_build_edges(P, cur, gtid, gsize);
         grid.sync();
         chi_first = chi_last = sc->chi_cur;
     }
@@ -690,7 +930,9 @@ ba_lm_kernel(const __grid_constant__ BaParams P) {
 // ---------------------------------------------------------------------------------------------------------------
 struct BaState {
     int maxK, maxL, maxObs, n_cta, smem_bytes;
-    double *d_poses, *d_points, *d_uv, *d_err, *d_Hpl, *d_Hll, *d_bl, *d_Dinv, *d_Hpp, *d_bp, *d_S, *d_bs, *d_x, *d_Spart;
+    double *d_poses, *d_points, *d_uv, *d_err, *d_Hpl, *d_Hll, *d_bl, *d_Dinv, *d_Hpp, *d_bp, *d_S, *d_bs, *d_x, *d_dbl;
+    int *d_pose_start, *d_pose_obs, *d_obs_of, *d_block_flag;
+    double* d_U;
     double* d_chi2;
     int *d_obs_pose, *d_obs_point, *d_obs_orig, *d_lm_start;
     uint8_t* d_inlier;
@@ -708,8 +950,9 @@ __global__ void ba_phase_kernel(const __grid_constant__ BaParams P, int phase, d
 // shared memory of one CTA: max(pose partials K*42, per-CTA S n*n+n, in-shared-memory Cholesky n*n+n) doubles
 static int ba_smem_bytes(int K) {
     const size_t n = 6 * (size_t)K;
-    size_t need = (size_t)K * 42;
-    if (n <= BA_SMEM_CHOL_MAX && n * n + n > need) need = n * n + n;
+    size_t need = (BA_THREADS / 32) * 42;  // block-reduction scratch of the BUILD-B / SCHUR phases
+    if (n <= BA_SMEM_CHOL_MAX && n * n + n > need) need = n * n + n;     // in-shared-memory Cholesky + scratch
+    if (n > BA_SMEM_CHOL_MAX && 36 + 6 * n > need) need = 36 + 6 * n;    // grid-wide solver: diagonal block + panel
     return (int)(need * sizeof(double));
 }
 
@@ -737,8 +980,12 @@ int vslam_ba_init(vslam_ctx* ctx) {
     VSLAM_CUDA(ctx, cudaMalloc(&b->d_S, n * n * sizeof(double)));
     VSLAM_CUDA(ctx, cudaMalloc(&b->d_bs, n * sizeof(double)));
     VSLAM_CUDA(ctx, cudaMalloc(&b->d_x, (2 * n + 3 * L) * sizeof(double)));
-    const size_t ns = n < BA_SMEM_S_MAX ? n : BA_SMEM_S_MAX;
-    VSLAM_CUDA(ctx, cudaMalloc(&b->d_Spart, (size_t)b->n_cta * (ns * ns + ns) * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_dbl, L * 3 * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_U, n * n * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_pose_start, (K + 1) * sizeof(int)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_pose_obs, O * sizeof(int)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_obs_of, K * L * sizeof(int)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_block_flag, (K * (K + 1) / 2) * sizeof(int)));
     VSLAM_CUDA(ctx, cudaMalloc(&b->d_chi2, O * sizeof(double)));
     VSLAM_CUDA(ctx, cudaMalloc(&b->d_obs_pose, O * sizeof(int)));
     VSLAM_CUDA(ctx, cudaMalloc(&b->d_obs_point, O * sizeof(int)));
@@ -764,12 +1011,86 @@ void vslam_ba_free(vslam_ctx* ctx) {
     if (!b) return;
     cudaFree(b->d_poses); cudaFree(b->d_points); cudaFree(b->d_uv); cudaFree(b->d_err); cudaFree(b->d_Hpl);
     cudaFree(b->d_Hll); cudaFree(b->d_bl); cudaFree(b->d_Dinv); cudaFree(b->d_Hpp); cudaFree(b->d_bp); cudaFree(b->d_S);
-    cudaFree(b->d_bs); cudaFree(b->d_x); cudaFree(b->d_Spart); cudaFree(b->d_chi2); cudaFree(b->d_obs_pose);
+    cudaFree(b->d_bs); cudaFree(b->d_x); cudaFree(b->d_dbl); cudaFree(b->d_U); cudaFree(b->d_block_flag); cudaFree(b->d_pose_start); cudaFree(b->d_pose_obs); cudaFree(b->d_obs_of); cudaFree(b->d_chi2); cudaFree(b->d_obs_pose);
     cudaFree(b->d_obs_point); cudaFree(b->d_obs_orig); cudaFree(b->d_lm_start); cudaFree(b->d_inlier); cudaFree(b->d_sc);
     cudaFreeHost(b->h_sc);
     free(b->sess);
     free(b);
     ctx->ba = nullptr;
+}
+
+// Host marshalling shared by vslam_ba_optimize and vslam_ba_session_begin: stable counting sorts of the edge list by
+// landmark (the device order) and by pose (CSR over device indices), duplicate (pose, landmark) detection, uploads.
+// Index bookkeeping only -- no arithmetic on the measurements.
+static int ba_marshal(vslam_ctx* ctx, BaState* b, int K, int n_points, int n_obs, const double* poses,
+                      const double* points, const int32_t* obs_pose, const int32_t* obs_point, const double* obs_uv,
+                      int* has_dup) {
+    const int L = n_points > 0 ? n_points : 1;
+    const int no = n_obs > 0 ? n_obs : 1;
+    std::vector<int> lm_start(L + 1, 0), op(no), ol(no), oo(no), pose_start(K + 1, 0), pose_obs(no);
+    std::vector<double> uv(2 * (size_t)no);
+    for (int i = 0; i < n_obs; ++i) {
+        if (obs_point[i] < 0 || obs_point[i] >= n_points || obs_pose[i] < 0 || obs_pose[i] >= K) return VSLAM_E_INVALID;
+        lm_start[obs_point[i] + 1]++;
+        pose_start[obs_pose[i] + 1]++;
+    }
+    for (int l = 0; l < L; ++l) lm_start[l + 1] += lm_start[l];
+    for (int k = 0; k < K; ++k) pose_start[k + 1] += pose_start[k];
+    {
+        std::vector<int> fill(lm_start.begin(), lm_start.end() - 1);
+        for (int i = 0; i < n_obs; ++i) {
+            const int d = fill[obs_point[i]]++;
+            op[d] = obs_pose[i]; ol[d] = obs_point[i]; oo[d] = i;
+            uv[2 * d] = obs_uv[2 * i]; uv[2 * d + 1] = obs_uv[2 * i + 1];
+        }
+    }
+    {
+        std::vector<int> fill(pose_start.begin(), pose_start.end() - 1);
+        for (int d = 0; d < n_obs; ++d) pose_obs[fill[op[d]]++] = d;  // ascending device index within each pose
+    }
+    *has_dup = 0;
+    for (int l = 0; l < n_points && !*has_dup; ++l)
+        for (int i = lm_start[l]; i < lm_start[l + 1] && !*has_dup; ++i)
+            for (int j = i + 1; j < lm_start[l + 1]; ++j)
+                if (op[i] == op[j]) { *has_dup = 1; break; }
+    cudaStream_t s = ctx->stream;
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_poses, poses, (size_t)K * 96, cudaMemcpyHostToDevice, s));
+    if (n_points > 0) {
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_points, points, (size_t)n_points * 24, cudaMemcpyHostToDevice, s));
+        // pose-only mode never writes the trial points: keep both buffers equal
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_points + (size_t)L * 3, points, (size_t)n_points * 24, cudaMemcpyHostToDevice, s));
+    }
+    if (n_obs > 0) {
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_pose, op.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_point, ol.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_orig, oo.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_pose_obs, pose_obs.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_uv, uv.data(), (size_t)n_obs * 16, cudaMemcpyHostToDevice, s));
+    }
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_lm_start, lm_start.data(), (size_t)(L + 1) * 4, cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_pose_start, pose_start.data(), (size_t)(K + 1) * 4, cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemsetAsync(b->d_obs_of, 0xFF, (size_t)K * L * sizeof(int), s));
+    VSLAM_CUDA(ctx, cudaMemsetAsync(b->d_block_flag, 0, (size_t)(K * (K + 1) / 2) * sizeof(int), s));
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(s));  // the staging vectors go out of scope
+    return VSLAM_OK;
+}
+
+static void ba_fill_params(BaParams& P, BaState* b, int K, int n_points, int n_obs, const vslam_ba_options* opt,
+                           const double* Kmat, int has_dup) {
+    memset(&P, 0, sizeof(P));
+    P.K = K; P.L = n_points; P.n_obs = n_obs; P.pose_only = opt->pose_only ? 1 : 0;
+    P.num_iterations = opt->num_iterations; P.max_trials = opt->max_trials > 0 ? opt->max_trials : 10;
+    P.delta = opt->huber_delta; P.tau = opt->tau > 0 ? opt->tau : 1e-5; P.chi2_th = opt->chi2_threshold;
+    memcpy(P.Kc, Kmat, 72);
+    P.n = 6 * K;
+    P.n_cta = b->n_cta;
+    P.shard_L0 = 0; P.shard_L1 = n_points;
+    P.has_dup = has_dup;
+    P.poses = b->d_poses; P.points = b->d_points; P.obs_pose = b->d_obs_pose; P.obs_point = b->d_obs_point;
+    P.obs_uv = b->d_uv; P.obs_orig = b->d_obs_orig; P.lm_start = b->d_lm_start; P.pose_start = b->d_pose_start;
+    P.pose_obs = b->d_pose_obs; P.obs_of = b->d_obs_of; P.dbl = b->d_dbl; P.Ubuf = b->d_U; P.block_flag = b->d_block_flag; P.err = b->d_err; P.Hpl = b->d_Hpl;
+    P.Hll = b->d_Hll; P.bl = b->d_bl; P.Dinv = b->d_Dinv; P.Hpp = b->d_Hpp; P.bp = b->d_bp; P.S = b->d_S; P.bs = b->d_bs;
+    P.x = b->d_x; P.sc = b->d_sc; P.chi2_out = b->d_chi2; P.inlier_out = b->d_inlier;
 }
 
 extern "C" int vslam_ba_optimize(vslam_ctx* ctx, int n_poses, double* poses, int n_points, double* points, int n_obs,
@@ -782,59 +1103,15 @@ extern "C" int vslam_ba_optimize(vslam_ctx* ctx, int n_poses, double* poses, int
     BaState* b = ctx->ba;
     if (!b || !b->d_poses) return VSLAM_E_CAPACITY;
     if (n_poses > b->maxK || n_points > b->maxL || n_obs > b->maxObs) return VSLAM_E_CAPACITY;
-    const int K = n_poses, L = n_points > 0 ? n_points : 1;
-    // marshal: stable counting sort of the observations by landmark (index bookkeeping only)
-    std::vector<int> lm_start(L + 1, 0), op(n_obs > 0 ? n_obs : 1), ol(n_obs > 0 ? n_obs : 1), oo(n_obs > 0 ? n_obs : 1);
-    std::vector<double> uv(2 * (size_t)(n_obs > 0 ? n_obs : 1));
-    for (int i = 0; i < n_obs; ++i) {
-        if (obs_point[i] < 0 || obs_point[i] >= n_points || obs_pose[i] < 0 || obs_pose[i] >= K) return VSLAM_E_INVALID;
-        lm_start[obs_point[i] + 1]++;
-    }
-    for (int l = 0; l < L; ++l) lm_start[l + 1] += lm_start[l];
-    {
-        std::vector<int> fill(lm_start.begin(), lm_start.end() - 1);
-        for (int i = 0; i < n_obs; ++i) {
-            const int d = fill[obs_point[i]]++;
-            op[d] = obs_pose[i];
-            ol[d] = obs_point[i];
-            oo[d] = i;
-            uv[2 * d] = obs_uv[2 * i];
-            uv[2 * d + 1] = obs_uv[2 * i + 1];
-        }
-    }
+    const int K = n_poses;
+    int has_dup = 0;
+    int mst = ba_marshal(ctx, b, K, n_points, n_obs, poses, points, obs_pose, obs_point, obs_uv, &has_dup);
+    if (mst != VSLAM_OK) return mst;
     cudaStream_t s = ctx->stream;
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_poses, poses, (size_t)K * 96, cudaMemcpyHostToDevice, s));
-    if (n_points > 0) {
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_points, points, (size_t)n_points * 24, cudaMemcpyHostToDevice, s));
-        // pose-only mode never writes the trial points: keep both buffers equal
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_points + (size_t)L * 3, points, (size_t)n_points * 24, cudaMemcpyHostToDevice, s));
-    }
-    if (n_obs > 0) {
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_pose, op.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_point, ol.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_orig, oo.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_uv, uv.data(), (size_t)n_obs * 16, cudaMemcpyHostToDevice, s));
-    }
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_lm_start, lm_start.data(), (size_t)(L + 1) * 4, cudaMemcpyHostToDevice, s));
     if (point_inlier && n_points > 0)
         VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_inlier, point_inlier, (size_t)n_points, cudaMemcpyHostToDevice, s));
-
     BaParams P;
-    memset(&P, 0, sizeof(P));
-    P.K = K; P.L = n_points; P.n_obs = n_obs; P.pose_only = opt->pose_only ? 1 : 0;
-    P.num_iterations = opt->num_iterations; P.max_trials = opt->max_trials > 0 ? opt->max_trials : 10;
-    P.delta = opt->huber_delta; P.tau = opt->tau > 0 ? opt->tau : 1e-5; P.chi2_th = opt->chi2_threshold;
-    memcpy(P.Kc, Kmat, 72);
-    P.n = 6 * K;
-    P.use_smem_S = (!P.pose_only && P.n <= BA_SMEM_S_MAX) ? 1 : 0;
-    P.n_cta = b->n_cta;
-    P.shard_L0 = 0; P.shard_L1 = n_points;
-    P.poses = b->d_poses; P.points = b->d_points; P.obs_pose = b->d_obs_pose; P.obs_point = b->d_obs_point;
-    P.obs_uv = b->d_uv; P.obs_orig = b->d_obs_orig; P.lm_start = b->d_lm_start; P.err = b->d_err; P.Hpl = b->d_Hpl;
-    P.Hll = b->d_Hll; P.bl = b->d_bl; P.Dinv = b->d_Dinv; P.Hpp = b->d_Hpp; P.bp = b->d_bp; P.S = b->d_S; P.bs = b->d_bs;
-    P.x = b->d_x; P.S_part = b->d_Spart; P.sc = b->d_sc; P.chi2_out = b->d_chi2; P.inlier_out = b->d_inlier;
-    // points buffer 1 lives at offset L*3 (L = max(n_points,1)); the kernel indexes with P.L
-    if (n_points > 0 && L != n_points) return VSLAM_E_INVALID;
+    ba_fill_params(P, b, K, n_points, n_obs, opt, Kmat, has_dup);
 
     void* args[] = {(void*)&P};
     vslam_time_begin(ctx, VK_BA_BUILD);
@@ -886,7 +1163,10 @@ ba_phase_kernel(const __grid_constant__ BaParams P, int phase, double lambda, in
     if (phase == BA_PH_BUILD) {
         ba_phase_zero(P, gtid, gsize);
         grid.sync();
-        ba_phase_build(P, cur, smem, gtid, gsize);
+        ba_phase_build_edges(P, cur, gtid, gsize);
+        ba_phase_build_poses(P, cur, smem);
+        grid.sync();
+        ba_phase_maxdiag(P, gtid, gsize);
         grid.sync();
         if (gtid == 0) {
             r1[42 * P.K] = P.sc->chi_cur;
@@ -896,23 +1176,23 @@ ba_phase_kernel(const __grid_constant__ BaParams P, int phase, double lambda, in
     } else if (phase == BA_PH_IMPORT_BUILD) {
         if (gtid == 0) P.sc->chi_cur = r1[42 * P.K];
     } else if (phase == BA_PH_SCHUR) {
-        ba_phase_schur_init(P, 0.0, slot, 0, gtid, gsize);  // partial system only: Hpp + lambda I is added after the reduce
+        // partial system only: Hpp + lambda I and bp are added after the all-reduce (SOLVE_UPDATE)
+        ba_phase_dinv(P, lambda, slot, 0, gtid, gsize);
         grid.sync();
-        ba_phase_schur(P, lambda, smem, gtid, gsize);
-        grid.sync();
-        ba_phase_schur_reduce(P, gtid, gsize);
+        if (P.has_dup) ba_phase_schur_atomic(P, gtid, gsize);
+        else ba_phase_schur_blocks(P, smem);
     } else if (phase == BA_PH_SOLVE_UPDATE) {
         for (int i = gtid; i < n * n; i += gsize) {  // S (reduced over ranks) += Hpp (reduced) + lambda I
             const int r = i / n, c = i - r * n;
             double v = 0.0;
-            if (r / 6 == c / 6) v = P.Hpp[(r / 6) * 36 + (r % 6) * 6 + (c % 6)];
+            if (r / 6 == c / 6 && c >= r) v = P.Hpp[(r / 6) * 36 + (r % 6) * 6 + (c % 6)];
             if (r == c) v += lambda;
             P.S[i] += v;
         }
         for (int i = gtid; i < n; i += gsize) P.bs[i] += P.bp[i];
         grid.sync();
         if (n <= BA_SMEM_CHOL_MAX) ba_phase_solve_cta(P, slot, smem);
-        else ba_phase_solve_grid(P, slot, grid, gtid, gsize);
+        else ba_phase_solve_grid(P, slot, grid, smem, P.Ubuf, gtid, gsize);
         grid.sync();
         ba_phase_update(P, cur, lambda, slot, gtid, gsize);
         grid.sync();
@@ -954,50 +1234,18 @@ extern "C" int vslam_ba_session_begin(vslam_ctx* ctx, int n_poses, const double*
     if (!b || !b->d_poses) return VSLAM_E_CAPACITY;
     if (n_poses > b->maxK || n_points > b->maxL || n_obs > b->maxObs) return VSLAM_E_CAPACITY;
     const int K = n_poses, L = n_points;
-    std::vector<int> lm_start(L + 1, 0), op(n_obs), ol(n_obs), oo(n_obs);
-    std::vector<double> uv(2 * (size_t)n_obs);
-    for (int i = 0; i < n_obs; ++i) {
-        if (obs_point[i] < 0 || obs_point[i] >= L || obs_pose[i] < 0 || obs_pose[i] >= K) return VSLAM_E_INVALID;
-        lm_start[obs_point[i] + 1]++;
-    }
-    for (int l = 0; l < L; ++l) lm_start[l + 1] += lm_start[l];
-    {
-        std::vector<int> fill(lm_start.begin(), lm_start.end() - 1);
-        for (int i = 0; i < n_obs; ++i) {
-            const int d = fill[obs_point[i]]++;
-            op[d] = obs_pose[i]; ol[d] = obs_point[i]; oo[d] = i;
-            uv[2 * d] = obs_uv[2 * i]; uv[2 * d + 1] = obs_uv[2 * i + 1];
-        }
-    }
+    int has_dup = 0;
+    int mst = ba_marshal(ctx, b, K, n_points, n_obs, poses, points, obs_pose, obs_point, obs_uv, &has_dup);
+    if (mst != VSLAM_OK) return mst;
     cudaStream_t s = ctx->stream;
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_poses, poses, (size_t)K * 96, cudaMemcpyHostToDevice, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_points, points, (size_t)L * 24, cudaMemcpyHostToDevice, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_points + (size_t)L * 3, points, (size_t)L * 24, cudaMemcpyHostToDevice, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_pose, op.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_point, ol.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_orig, oo.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_uv, uv.data(), (size_t)n_obs * 16, cudaMemcpyHostToDevice, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_lm_start, lm_start.data(), (size_t)(L + 1) * 4, cudaMemcpyHostToDevice, s));
     VSLAM_CUDA(ctx, cudaMemsetAsync(b->d_chi2, 0, (size_t)n_obs * 8, s));
     VSLAM_CUDA(ctx, cudaMemsetAsync(b->d_inlier, 0, (size_t)L, s));
-    VSLAM_CUDA(ctx, cudaStreamSynchronize(s));  // the host staging vectors go out of scope
     if (!b->sess) b->sess = (BaParams*)calloc(1, sizeof(BaParams));
     BaParams& P = *b->sess;
-    memset(&P, 0, sizeof(P));
-    P.K = K; P.L = L; P.n_obs = n_obs; P.pose_only = opt->pose_only ? 1 : 0;
-    P.num_iterations = opt->num_iterations; P.max_trials = opt->max_trials > 0 ? opt->max_trials : 10;
-    P.delta = opt->huber_delta; P.tau = opt->tau > 0 ? opt->tau : 1e-5; P.chi2_th = opt->chi2_threshold;
-    memcpy(P.Kc, Kmat, 72);
-    P.n = 6 * K;
-    P.use_smem_S = (!P.pose_only && P.n <= BA_SMEM_S_MAX) ? 1 : 0;
-    P.n_cta = b->n_cta;
+    ba_fill_params(P, b, K, n_points, n_obs, opt, Kmat, has_dup);
     P.shard_L0 = shard_begin; P.shard_L1 = shard_end;
-    P.poses = b->d_poses; P.points = b->d_points; P.obs_pose = b->d_obs_pose; P.obs_point = b->d_obs_point;
-    P.obs_uv = b->d_uv; P.obs_orig = b->d_obs_orig; P.lm_start = b->d_lm_start; P.err = b->d_err; P.Hpl = b->d_Hpl;
-    P.Hll = b->d_Hll; P.bl = b->d_bl; P.Dinv = b->d_Dinv;
     P.Hpp = d_r1; P.bp = d_r1 + 36 * K;          // pose blocks live in the caller's reduce buffer r1
     P.S = d_r2; P.bs = d_r2 + (size_t)P.n * P.n;  // reduced camera system lives in r2
-    P.x = b->d_x; P.S_part = b->d_Spart; P.sc = b->d_sc; P.chi2_out = b->d_chi2; P.inlier_out = b->d_inlier;
     b->sess_open = 1; b->sess_cur = 0; b->sess_trials = 0;
     b->sess_r1 = d_r1; b->sess_r2 = d_r2; b->sess_r3 = d_r3;
     return VSLAM_OK;
@@ -1054,5 +1302,11 @@ extern "C" int vslam_ba_session_end(vslam_ctx* ctx, double* poses, double* point
     if (point_inlier) VSLAM_CUDA(ctx, cudaMemcpyAsync(point_inlier, b->d_inlier, (size_t)P.L, cudaMemcpyDeviceToHost, s));
     VSLAM_CUDA(ctx, cudaStreamSynchronize(s));
     b->sess_open = 0;
+    return VSLAM_OK;
+}
+
+extern "C" int vslam_ba_last_phase_ns(vslam_ctx* ctx, uint64_t* ns8) {
+    if (!ctx || !ctx->ba || !ctx->ba->h_sc || !ns8) return VSLAM_E_INVALID;
+    for (int i = 0; i < 8; ++i) ns8[i] = ctx->ba->h_sc->phase_ns[i];
     return VSLAM_OK;
 }

@@ -288,24 +288,26 @@ extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, 
     if (width <= 0 || height <= 0 || row_pitch < width) return VSLAM_E_INVALID;
     if (width > ctx->cfg.max_width || height > ctx->cfg.max_height) return VSLAM_E_CAPACITY;
     cudaStream_t s = ctx->stream;
-    const size_t dstride = (size_t)f->pitch * height;
+    // staging keeps the caller's row pitch when the batch is one contiguous block: a single 1-D DMA per side instead
+    // of a 2-D copy of 1241-byte rows (the kernels read bytes, so the pitch need not be aligned)
+    const bool contiguous = image_stride == (long long)row_pitch * height && row_pitch <= f->pitch;
+    const int dpitch = contiguous ? row_pitch : f->pitch;
+    const size_t dstride = (size_t)dpitch * height;
     uint8_t* dl = f->d_img;
     uint8_t* dr = f->d_img + (size_t)n_pairs * dstride;
-    if (image_stride == (long long)row_pitch * height) {
-        VSLAM_CUDA(ctx, cudaMemcpy2DAsync(dl, f->pitch, left, row_pitch, width, (size_t)height * n_pairs,
-                                          cudaMemcpyHostToDevice, s));
-        VSLAM_CUDA(ctx, cudaMemcpy2DAsync(dr, f->pitch, right, row_pitch, width, (size_t)height * n_pairs,
-                                          cudaMemcpyHostToDevice, s));
+    if (contiguous) {
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(dl, left, dstride * n_pairs, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(dr, right, dstride * n_pairs, cudaMemcpyHostToDevice, s));
     } else {
         for (int i = 0; i < n_pairs; ++i) {
-            VSLAM_CUDA(ctx, cudaMemcpy2DAsync(dl + i * dstride, f->pitch, left + (size_t)i * image_stride, row_pitch,
+            VSLAM_CUDA(ctx, cudaMemcpy2DAsync(dl + i * dstride, dpitch, left + (size_t)i * image_stride, row_pitch,
                                               width, height, cudaMemcpyHostToDevice, s));
-            VSLAM_CUDA(ctx, cudaMemcpy2DAsync(dr + i * dstride, f->pitch, right + (size_t)i * image_stride, row_pitch,
+            VSLAM_CUDA(ctx, cudaMemcpy2DAsync(dr + i * dstride, dpitch, right + (size_t)i * image_stride, row_pitch,
                                               width, height, cudaMemcpyHostToDevice, s));
         }
     }
     if (T_c_w) VSLAM_CUDA(ctx, cudaMemcpyAsync(f->d_pose, T_c_w, (size_t)n_pairs * 96, cudaMemcpyHostToDevice, s));
-    int st = vslam_stereo_frontend_batch_dev(ctx, dl, dr, n_pairs, width, height, f->pitch, (long long)dstride,
+    int st = vslam_stereo_frontend_batch_dev(ctx, dl, dr, n_pairs, width, height, dpitch, (long long)dstride,
                                              nfeatures, anms_keep, anms_c, gate_rel, gate_abs, P1, P2,
                                              T_c_w ? f->d_pose : nullptr, f->d_kp, f->d_desc, f->d_nkp, f->d_match,
                                              f->d_nmatch, f->d_xyz, f->d_flags);

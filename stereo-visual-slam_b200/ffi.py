@@ -81,6 +81,7 @@ SIGNATURES = {
                                C.POINTER(BaResult), _vp, _vp]),
     "vslam_pnp_ransac": (_i, [_vp, _vp, _vp, _i, _vp, _i, _f, _d, _vp, _vp, _vp, _vp, _pi]),
     "vslam_anms": (_i, [_vp, _vp, _i, _i, _f, _vp, _pi]),
+    "vslam_ba_last_phase_ns": (_i, [_vp, _vp]),
     "vslam_ba_reduce_sizes": (_i, [_i, _pi, _pi, _pi]),
     "vslam_ba_session_begin": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, C.POINTER(BaOptions), _i, _i, _vp,
                                     _vp, _vp]),
@@ -340,6 +341,12 @@ class Context:
         st = self.lib.vslam_anms(self.h, _ptr(kp), len(kp), int(num), float(c_robust), _ptr(keep), C.byref(n))
         self.check(st, "vslam_anms")
         return keep[:n.value].copy()
+
+    def ba_last_phase_us(self) -> dict:
+        ns = np.zeros(8, dtype=np.uint64)
+        self.check(self.lib.vslam_ba_last_phase_ns(self.h, _ptr(ns)), "vslam_ba_last_phase_ns")
+        names = ["zero", "build", "schur_init", "schur", "schur_reduce", "solve", "update", "trial_err"]
+        return {k: float(v) / 1e3 for k, v in zip(names, ns)}
 
     # ---- K17: landmark-sharded BA session (driver: sharding.ba_optimize_sharded) ------------
     def ba_session(self, problem, shard, r1, r2, r3, **opt):
