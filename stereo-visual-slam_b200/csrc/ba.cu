@@ -490,7 +490,9 @@ __device__ void ba_phase_schur_atomic(const BaParams& P, int gtid, int gsize) {
 // thread per trailing column forward-substitutes its 6 panel entries, (3) all threads apply the rank-6 update.
 
 // factor the 6x6 diagonal block at (j0, j0) of the row-major matrix M (leading dimension ld) in place; false if not PD
-__device__ __forceinline__ bool chol6_diag(double* M, int ld, int j0) {
+// rinv receives the reciprocals of the diagonal of U: every later division by U_rr becomes a multiplication
+// (fp64 division and sqrt are long multi-instruction sequences; one rsqrt per pivot replaces a sqrt and a division).
+__device__ __forceinline__ bool chol6_diag(double* M, int ld, int j0, double* rinv) {
     bool ok = true;
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
@@ -499,8 +501,10 @@ __device__ __forceinline__ bool chol6_diag(double* M, int ld, int j0) {
         for (int p = 0; p < 6; ++p)
             if (p < r) d -= M[(j0 + p) * ld + j0 + r] * M[(j0 + p) * ld + j0 + r];
         if (!(d > 0.0) || !isfinite(d)) ok = false;
-        d = sqrt(d);
-        M[(j0 + r) * ld + j0 + r] = d;
+        double ri = rsqrt(d);
+        ri = ri * (1.5 - 0.5 * d * ri * ri);  // one Newton step: full double accuracy
+        rinv[r] = ri;
+        M[(j0 + r) * ld + j0 + r] = d * ri;
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
             if (c > r) {
@@ -508,7 +512,7 @@ __device__ __forceinline__ bool chol6_diag(double* M, int ld, int j0) {
 #pragma unroll
                 for (int p = 0; p < 6; ++p)
                     if (p < r) v -= M[(j0 + p) * ld + j0 + r] * M[(j0 + p) * ld + j0 + c];
-                M[(j0 + r) * ld + j0 + c] = v / d;
+                M[(j0 + r) * ld + j0 + c] = v * ri;
             }
         }
     }
@@ -525,7 +529,7 @@ __device__ void ba_tri_solve_cta(const BaParams& P, const double* U, double* y) 
             for (int r = 0; r < 6; ++r) {
                 double v = y[j0 + r];
                 for (int p = 0; p < r; ++p) v -= U[(j0 + p) * n + j0 + r] * y[j0 + p];
-                y[j0 + r] = v / U[(j0 + r) * n + j0 + r];
+                y[j0 + r] = v / U[(j0 + r) * n + j0 + r];  // thread-0 stage of the large-system path
             }
         }
         __syncthreads();
@@ -558,66 +562,99 @@ __device__ void ba_tri_solve_cta(const BaParams& P, const double* U, double* y) 
     __syncthreads();
 }
 
-// small systems (6K <= 160): everything in the shared memory of CTA 0
+// small systems (6K <= 160): everything in the shared memory of CTA 0.  The right-hand side rides along as column n of
+// the augmented matrix [S | bs] (so the forward substitution happens inside the factorisation), every thread factors
+// the 6x6 diagonal block redundantly in registers (no serial single-thread stage), and the backward substitution is
+// blocked the same way: 3 barriers per block row in total.
 __device__ void ba_phase_solve_cta(const BaParams& P, int slot, double* smem) {
     if (blockIdx.x != 0) return;
-    const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
+    const int n = P.n, ld = P.n + 1, tid = threadIdx.x, nt = blockDim.x;
     __shared__ int s_fail;
-    double* M = smem;  // n*n doubles, then n doubles of scratch
+    double* M = smem;  // n x (n + 1)
     if (tid == 0) s_fail = 0;
-    for (int i = tid; i < n * n; i += nt) M[i] = P.S[i];
+    for (int i = tid; i < n * n; i += nt) M[(i / n) * ld + i % n] = P.S[i];
+    for (int i = tid; i < n; i += nt) M[i * ld + n] = P.bs[i];
     __syncthreads();
     for (int j0 = 0; j0 < n; j0 += 6) {
-        if (tid == 0) {  // diagonal block through registers (independent loads, then a dependent arithmetic chain)
-            double D[36];
-#pragma unroll
-            for (int r = 0; r < 6; ++r)
-#pragma unroll
-                for (int c = 0; c < 6; ++c) D[r * 6 + c] = (c >= r) ? M[(j0 + r) * n + j0 + c] : 0.0;
-            if (!chol6_diag(D, 6, 0)) s_fail = 1;
-#pragma unroll
-            for (int r = 0; r < 6; ++r)
-#pragma unroll
-                for (int c = 0; c < 6; ++c)
-                    if (c >= r) M[(j0 + r) * n + j0 + c] = D[r * 6 + c];
-        }
-        __syncthreads();
-        if (s_fail) break;
         {
             double D[36];
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
-                for (int c = 0; c < 6; ++c) D[r * 6 + c] = (c >= r) ? M[(j0 + r) * n + j0 + c] : 0.0;
-            for (int c = j0 + 6 + tid; c < n; c += nt) {  // panel: 6 forward-substitution steps per column
+                for (int c = 0; c < 6; ++c) D[r * 6 + c] = (c >= r) ? M[(j0 + r) * ld + j0 + c] : 0.0;
+            double rinv[6];
+            const bool ok = chol6_diag(D, 6, 0, rinv);
+            for (int c = j0 + 6 + tid; c <= n; c += nt) {  // panel (and the rhs column c == n)
                 double v[6];
 #pragma unroll
-                for (int r = 0; r < 6; ++r) v[r] = M[(j0 + r) * n + c];
+                for (int r = 0; r < 6; ++r) v[r] = M[(j0 + r) * ld + c];
 #pragma unroll
                 for (int r = 0; r < 6; ++r) {
 #pragma unroll
                     for (int p = 0; p < 6; ++p)
                         if (p < r) v[r] -= D[p * 6 + r] * v[p];
-                    v[r] /= D[r * 6 + r];
+                    v[r] *= rinv[r];
                 }
 #pragma unroll
-                for (int r = 0; r < 6; ++r) M[(j0 + r) * n + c] = v[r];
+                for (int r = 0; r < 6; ++r) M[(j0 + r) * ld + c] = v[r];
+            }
+            __syncthreads();  // everyone has read the un-factored diagonal block
+            if (tid == 0) {
+                if (!ok) s_fail = 1;
+#pragma unroll
+                for (int r = 0; r < 6; ++r)
+#pragma unroll
+                    for (int c = 0; c < 6; ++c)
+                        if (c >= r) M[(j0 + r) * ld + j0 + c] = D[r * 6 + c];
             }
         }
         __syncthreads();
-        const int m = n - j0 - 6;  // trailing update, upper triangle
-        for (int e = tid; e < m * m; e += nt) {
-            const int r = j0 + 6 + e / m, c = j0 + 6 + e % m;
+        if (s_fail) break;
+        const int m = n - j0 - 6;  // trailing update of the upper triangle and of the rhs column
+        for (int e = tid; e < m * (m + 1); e += nt) {
+            const int r = j0 + 6 + e / (m + 1), c = j0 + 6 + e % (m + 1);
             if (c < r) continue;
-            double v = M[r * n + c];
+            double v = M[r * ld + c];
 #pragma unroll
-            for (int p = 0; p < 6; ++p) v -= M[(j0 + p) * n + r] * M[(j0 + p) * n + c];
-            M[r * n + c] = v;
+            for (int p = 0; p < 6; ++p) v -= M[(j0 + p) * ld + r] * M[(j0 + p) * ld + c];
+            M[r * ld + c] = v;
         }
         __syncthreads();
     }
     const int fail = s_fail;
-    if (!fail) ba_tri_solve_cta(P, M, M + n * n);
+    if (!fail) {
+        for (int j0 = n - 6; j0 >= 0; j0 -= 6) {  // backward substitution U x = y, y = column n
+            double D[36], x[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) D[r * 6 + c] = (c >= r) ? M[(j0 + r) * ld + j0 + c] : 0.0;
+            double rinv[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                x[r] = M[(j0 + r) * ld + n];
+                rinv[r] = 1.0 / D[r * 6 + r];  // six independent divisions, pipelined
+            }
+#pragma unroll
+            for (int r = 5; r >= 0; --r) {
+#pragma unroll
+                for (int p = 0; p < 6; ++p)
+                    if (p > r) x[r] -= D[r * 6 + p] * x[p];
+                x[r] *= rinv[r];
+            }
+            __syncthreads();  // everyone has read y_j
+            for (int r = tid; r < j0; r += nt) {
+                double v = M[r * ld + n];
+#pragma unroll
+                for (int p = 0; p < 6; ++p) v -= M[r * ld + j0 + p] * x[p];
+                M[r * ld + n] = v;
+            }
+            if (tid < 6) M[(j0 + tid) * ld + n] = x[tid];
+            __syncthreads();
+        }
+        for (int i = tid; i < n; i += nt) P.x[i] = M[i * ld + n];
+    }
+    __syncthreads();
     if (tid == 0) P.sc->solve_ok[slot] = fail ? 0 : 1;
 }
 
@@ -635,18 +672,29 @@ __device__ void ba_phase_solve_grid(const BaParams& P, int slot, cg::grid_group&
         if (tid < 36) D[tid] = P.S[(size_t)(j0 + tid / 6) * n + j0 + tid % 6];
         if (tid == 0) s_fail = 0;
         __syncthreads();
-        if (tid == 0 && !chol6_diag(D, 6, 0)) s_fail = 1;
+        double Dr[36], rinv[6];
+#pragma unroll
+        for (int q = 0; q < 36; ++q) Dr[q] = ((q % 6) >= (q / 6)) ? D[q] : 0.0;
+        const bool ok = chol6_diag(Dr, 6, 0, rinv);  // every thread, in registers
+        __syncthreads();
+        if (tid == 0 && !ok) s_fail = 1;
+        if (tid < 36) D[tid] = Dr[tid];
         __syncthreads();
         if (s_fail) {  // uniform over the grid: every CTA factors the same block
             fail = 1;
             break;
         }
         for (int c = j0 + 6 + tid; c < n; c += nt) {
+            double v[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) v[r] = P.S[(size_t)(j0 + r) * n + c];
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
-                double v = P.S[(size_t)(j0 + r) * n + c];
-                for (int p = 0; p < r; ++p) v -= D[p * 6 + r] * Up[p * n + c];
-                Up[r * n + c] = v / D[r * 6 + r];
+#pragma unroll
+                for (int p = 0; p < 6; ++p)
+                    if (p < r) v[r] -= Dr[p * 6 + r] * v[p];
+                v[r] *= rinv[r];
+                Up[r * n + c] = v[r];
             }
         }
         __syncthreads();
@@ -951,7 +999,7 @@ __global__ void ba_phase_kernel(const __grid_constant__ BaParams P, int phase, d
 static int ba_smem_bytes(int K) {
     const size_t n = 6 * (size_t)K;
     size_t need = (BA_THREADS / 32) * 42;  // block-reduction scratch of the BUILD-B / SCHUR phases
-    if (n <= BA_SMEM_CHOL_MAX && n * n + n > need) need = n * n + n;     // in-shared-memory Cholesky + scratch
+    if (n <= BA_SMEM_CHOL_MAX && n * n + n > need) need = n * n + n;     // in-shared-memory augmented system [S | bs]
     if (n > BA_SMEM_CHOL_MAX && 36 + 6 * n > need) need = 36 + 6 * n;    // grid-wide solver: diagonal block + panel
     return (int)(need * sizeof(double));
 }
