@@ -797,7 +797,9 @@ static int orb_set_geometry(vslam_ctx* ctx, int w, int h) {
         L.inv_scale = 1.f / L.scale;
         L.w = cv_round_f((float)w / L.scale);
         L.h = cv_round_f((float)h / L.scale);
-        if (L.w < 2 * ORB_EDGE + 8 || L.h < 2 * ORB_EDGE + 8) return VSLAM_E_INVALID;  // image too small for 8 levels
+        // a level narrower than 2 * 31 px simply yields no keypoints (border filter), as in cv::ORB; only degenerate
+        // sizes are refused
+        if (L.w < 16 || L.h < 16) return VSLAM_E_INVALID;
         L.pitch = (L.w + 15) & ~15;
         L.off = off;
         off += L.pitch * L.h;
