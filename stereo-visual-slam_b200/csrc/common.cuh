@@ -91,12 +91,13 @@ struct ImgSrc {
     long long img_stride;  // bytes between consecutive images of one base
     int pitch;             // bytes between rows
     int per_base;          // images per base pointer
+    int out_slot[2];       // output image slot of the first image of each base (kp / desc / count arrays)
 };
 
 // internal cross-module entry points
 int vslam_orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h, int nfeatures, int anms_keep,
                       float anms_c, vslam_keypoint* d_kp, uint8_t* d_desc, int32_t* d_n);
-int vslam_orb_check_flags(vslam_ctx* ctx, int n_img);  // synchronises the stream
+int vslam_orb_check_flags(vslam_ctx* ctx, int n_img);  // synchronises the stream; reads and clears the sticky flags
 
 // sub-module lifetime hooks (each .cu owns its state)
 int vslam_match_init(vslam_ctx* ctx);

@@ -12,6 +12,9 @@
 
 #include <stdlib.h>
 
+#define FRONT_CHUNK_PAIRS 16   // pairs per pipeline chunk (32 images keep every kernel's grid >= 2 waves)
+#define FRONT_MAX_CHUNKS 64
+
 struct FrontState {
     // host-buffer staging for vslam_stereo_frontend_batch / vslam_triangulate
     uint8_t* d_img;  // [2 * pairs][h][pitch] left images first, then right
@@ -28,6 +31,9 @@ struct FrontState {
     float* d_xl;     // vslam_triangulate staging
     float* d_xr;
     int max_pairs, kp_cap;
+    // chunked host-buffer pipeline: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of chunk c
+    cudaStream_t s_in, s_out;
+    cudaEvent_t ev_in[FRONT_MAX_CHUNKS], ev_done[FRONT_MAX_CHUNKS], ev_start;
 };
 
 struct Cam24 {
@@ -173,6 +179,13 @@ int vslam_front_init(vslam_ctx* ctx) {
     VSLAM_CUDA(ctx, cudaMalloc(&f->d_pose, np * 12 * sizeof(double)));
     VSLAM_CUDA(ctx, cudaMalloc(&f->d_xl, cap * 2 * sizeof(float)));
     VSLAM_CUDA(ctx, cudaMalloc(&f->d_xr, cap * 2 * sizeof(float)));
+    VSLAM_CUDA(ctx, cudaStreamCreateWithFlags(&f->s_in, cudaStreamNonBlocking));
+    VSLAM_CUDA(ctx, cudaStreamCreateWithFlags(&f->s_out, cudaStreamNonBlocking));
+    VSLAM_CUDA(ctx, cudaEventCreateWithFlags(&f->ev_start, cudaEventDisableTiming));
+    for (int i = 0; i < FRONT_MAX_CHUNKS; ++i) {
+        VSLAM_CUDA(ctx, cudaEventCreateWithFlags(&f->ev_in[i], cudaEventDisableTiming));
+        VSLAM_CUDA(ctx, cudaEventCreateWithFlags(&f->ev_done[i], cudaEventDisableTiming));
+    }
     return VSLAM_OK;
 }
 
@@ -190,6 +203,13 @@ void vslam_front_free(vslam_ctx* ctx) {
     cudaFree(f->d_pose);
     cudaFree(f->d_xl);
     cudaFree(f->d_xr);
+    if (f->s_in) cudaStreamDestroy(f->s_in);
+    if (f->s_out) cudaStreamDestroy(f->s_out);
+    if (f->ev_start) cudaEventDestroy(f->ev_start);
+    for (int i = 0; i < FRONT_MAX_CHUNKS; ++i) {
+        if (f->ev_in[i]) cudaEventDestroy(f->ev_in[i]);
+        if (f->ev_done[i]) cudaEventDestroy(f->ev_done[i]);
+    }
     free(f);
     ctx->front = nullptr;
 }
@@ -239,7 +259,38 @@ extern "C" int vslam_triangulate_matches_batch_dev(vslam_ctx* ctx, const vslam_k
     return VSLAM_OK;
 }
 
-// ORB(left) + ORB(right) + feature_matching(left -> right) + triangulation, everything enqueued on the stream.
+// ORB(left) + ORB(right) + feature_matching(left -> right) + triangulation for pairs [p0, p0 + n_chunk) of a batch of
+// n_pairs, everything enqueued on the context stream.  d_left / d_right point at the chunk's first image; the output
+// arrays are the whole batch's (left images occupy slots [0, n_pairs), right images [n_pairs, 2 n_pairs)).
+static int front_enqueue_chunk(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_right, int n_pairs, int p0,
+                               int n_chunk, int width, int height, int row_pitch, long long image_stride,
+                               int nfeatures, int anms_keep, float anms_c, double gate_rel, double gate_abs,
+                               const double* P1, const double* P2, const double* d_T_c_w, vslam_keypoint* d_kp,
+                               uint8_t* d_desc, int32_t* d_n_kp, vslam_dmatch* d_matches, int32_t* d_n_matches,
+                               float* d_xyz, uint8_t* d_flags) {
+    const size_t cap = (size_t)ctx->cfg.max_keypoints;
+    ImgSrc src;
+    src.base[0] = d_left;
+    src.base[1] = d_right;
+    src.img_stride = image_stride;
+    src.pitch = row_pitch;
+    src.per_base = n_chunk;
+    src.out_slot[0] = p0;
+    src.out_slot[1] = n_pairs + p0;
+    int st = vslam_orb_enqueue(ctx, src, 2 * n_chunk, width, height, nfeatures, anms_keep, anms_c, d_kp, d_desc, d_n_kp);
+    if (st != VSLAM_OK) return st;
+    // query = left descriptors (slots p0..), train = right descriptors (slots n_pairs + p0..)
+    const size_t lq = (size_t)p0, rq = (size_t)n_pairs + p0;
+    st = vslam_match_hamming_batch_dev(ctx, d_desc + lq * cap * 32, d_n_kp + lq, (int)cap, d_desc + rq * cap * 32,
+                                       d_n_kp + rq, (int)cap, n_chunk, (int)cap, 1, gate_rel, gate_abs,
+                                       d_matches + lq * cap, (int)cap, d_n_matches + lq);
+    if (st != VSLAM_OK) return st;
+    return vslam_triangulate_matches_batch_dev(ctx, d_kp + lq * cap, d_kp + rq * cap, (int)cap, d_matches + lq * cap,
+                                               d_n_matches + lq, (int)cap, n_chunk, P1, P2,
+                                               d_T_c_w ? d_T_c_w + 12 * lq : nullptr, d_xyz + lq * cap * 3,
+                                               d_flags + lq * cap);
+}
+
 extern "C" int vslam_stereo_frontend_batch_dev(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_right,
                                                int n_pairs, int width, int height, int row_pitch,
                                                long long image_stride, int nfeatures, int anms_keep, float anms_c,
@@ -252,21 +303,9 @@ extern "C" int vslam_stereo_frontend_batch_dev(vslam_ctx* ctx, const uint8_t* d_
         return VSLAM_E_INVALID;
     if (n_pairs <= 0 || width <= 0 || height <= 0 || row_pitch < width) return VSLAM_E_INVALID;
     if (2 * n_pairs > ctx->cfg.max_images) return VSLAM_E_CAPACITY;
-    const int cap = ctx->cfg.max_keypoints;
-    ImgSrc src;
-    src.base[0] = d_left;
-    src.base[1] = d_right;
-    src.img_stride = image_stride;
-    src.pitch = row_pitch;
-    src.per_base = n_pairs;
-    int st = vslam_orb_enqueue(ctx, src, 2 * n_pairs, width, height, nfeatures, anms_keep, anms_c, d_kp, d_desc, d_n_kp);
-    if (st != VSLAM_OK) return st;
-    // query = left descriptors (images 0..n_pairs-1), train = right descriptors (images n_pairs..2*n_pairs-1)
-    st = vslam_match_hamming_batch_dev(ctx, d_desc, d_n_kp, cap, d_desc + (size_t)n_pairs * cap * 32, d_n_kp + n_pairs,
-                                       cap, n_pairs, cap, 1, gate_rel, gate_abs, d_matches, cap, d_n_matches);
-    if (st != VSLAM_OK) return st;
-    return vslam_triangulate_matches_batch_dev(ctx, d_kp, d_kp + (size_t)n_pairs * cap, cap, d_matches, d_n_matches, cap,
-                                               n_pairs, P1, P2, d_T_c_w, d_xyz, d_flags);
+    return front_enqueue_chunk(ctx, d_left, d_right, n_pairs, 0, n_pairs, width, height, row_pitch, image_stride,
+                               nfeatures, anms_keep, anms_c, gate_rel, gate_abs, P1, P2, d_T_c_w, d_kp, d_desc, d_n_kp,
+                               d_matches, d_n_matches, d_xyz, d_flags);
 }
 
 // Host-buffer form (the call a user of the library makes): images come from host memory (pinned memory makes the
@@ -288,37 +327,67 @@ extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, 
     if (width <= 0 || height <= 0 || row_pitch < width) return VSLAM_E_INVALID;
     if (width > ctx->cfg.max_width || height > ctx->cfg.max_height) return VSLAM_E_CAPACITY;
     cudaStream_t s = ctx->stream;
-    // staging keeps the caller's row pitch when the batch is one contiguous block: a single 1-D DMA per side instead
-    // of a 2-D copy of 1241-byte rows (the kernels read bytes, so the pitch need not be aligned)
+    // staging keeps the caller's row pitch when the batch is one contiguous block: 1-D DMAs instead of 2-D copies of
+    // 1241-byte rows (the kernels read bytes, so the pitch need not be aligned)
     const bool contiguous = image_stride == (long long)row_pitch * height && row_pitch <= f->pitch;
     const int dpitch = contiguous ? row_pitch : f->pitch;
     const size_t dstride = (size_t)dpitch * height;
     uint8_t* dl = f->d_img;
     uint8_t* dr = f->d_img + (size_t)n_pairs * dstride;
-    if (contiguous) {
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(dl, left, dstride * n_pairs, cudaMemcpyHostToDevice, s));
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(dr, right, dstride * n_pairs, cudaMemcpyHostToDevice, s));
-    } else {
-        for (int i = 0; i < n_pairs; ++i) {
-            VSLAM_CUDA(ctx, cudaMemcpy2DAsync(dl + i * dstride, dpitch, left + (size_t)i * image_stride, row_pitch,
-                                              width, height, cudaMemcpyHostToDevice, s));
-            VSLAM_CUDA(ctx, cudaMemcpy2DAsync(dr + i * dstride, dpitch, right + (size_t)i * image_stride, row_pitch,
-                                              width, height, cudaMemcpyHostToDevice, s));
+    const size_t cap = (size_t)f->kp_cap, np = (size_t)n_pairs;
+    int chunk = FRONT_CHUNK_PAIRS;
+    if (ceil_div(n_pairs, chunk) > FRONT_MAX_CHUNKS) chunk = ceil_div(n_pairs, FRONT_MAX_CHUNKS);
+    const int n_chunks = ceil_div(n_pairs, chunk);
+    // the copy streams start after whatever the caller already queued on the context stream
+    VSLAM_CUDA(ctx, cudaEventRecord(f->ev_start, s));
+    VSLAM_CUDA(ctx, cudaStreamWaitEvent(f->s_in, f->ev_start, 0));
+    VSLAM_CUDA(ctx, cudaStreamWaitEvent(f->s_out, f->ev_start, 0));
+    if (T_c_w) VSLAM_CUDA(ctx, cudaMemcpyAsync(f->d_pose, T_c_w, np * 96, cudaMemcpyHostToDevice, f->s_in));
+    for (int c = 0; c < n_chunks; ++c) {  // all uploads are queued up front; they run back to back on the H2D engine
+        const int p0 = c * chunk, nc = n_pairs - p0 < chunk ? n_pairs - p0 : chunk;
+        if (contiguous) {
+            VSLAM_CUDA(ctx, cudaMemcpyAsync(dl + p0 * dstride, left + (size_t)p0 * image_stride, dstride * nc,
+                                            cudaMemcpyHostToDevice, f->s_in));
+            VSLAM_CUDA(ctx, cudaMemcpyAsync(dr + p0 * dstride, right + (size_t)p0 * image_stride, dstride * nc,
+                                            cudaMemcpyHostToDevice, f->s_in));
+        } else {
+            for (int i = p0; i < p0 + nc; ++i) {
+                VSLAM_CUDA(ctx, cudaMemcpy2DAsync(dl + i * dstride, dpitch, left + (size_t)i * image_stride, row_pitch,
+                                                  width, height, cudaMemcpyHostToDevice, f->s_in));
+                VSLAM_CUDA(ctx, cudaMemcpy2DAsync(dr + i * dstride, dpitch, right + (size_t)i * image_stride, row_pitch,
+                                                  width, height, cudaMemcpyHostToDevice, f->s_in));
+            }
         }
+        VSLAM_CUDA(ctx, cudaEventRecord(f->ev_in[c], f->s_in));
     }
-    if (T_c_w) VSLAM_CUDA(ctx, cudaMemcpyAsync(f->d_pose, T_c_w, (size_t)n_pairs * 96, cudaMemcpyHostToDevice, s));
-    int st = vslam_stereo_frontend_batch_dev(ctx, dl, dr, n_pairs, width, height, dpitch, (long long)dstride,
-                                             nfeatures, anms_keep, anms_c, gate_rel, gate_abs, P1, P2,
-                                             T_c_w ? f->d_pose : nullptr, f->d_kp, f->d_desc, f->d_nkp, f->d_match,
-                                             f->d_nmatch, f->d_xyz, f->d_flags);
-    if (st != VSLAM_OK) return st;
-    const size_t cap = (size_t)f->kp_cap, ni = 2 * (size_t)n_pairs, np = (size_t)n_pairs;
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(kp, f->d_kp, ni * cap * sizeof(vslam_keypoint), cudaMemcpyDeviceToHost, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(desc, f->d_desc, ni * cap * 32, cudaMemcpyDeviceToHost, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(n_kp, f->d_nkp, ni * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(matches, f->d_match, np * cap * sizeof(vslam_dmatch), cudaMemcpyDeviceToHost, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(n_matches, f->d_nmatch, np * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(xyz, f->d_xyz, np * cap * 12, cudaMemcpyDeviceToHost, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(flags, f->d_flags, np * cap, cudaMemcpyDeviceToHost, s));
-    return vslam_orb_check_flags(ctx, (int)ni);  // synchronises; VSLAM_E_OVERFLOW if a work list overflowed
+    for (int c = 0; c < n_chunks; ++c) {
+        const int p0 = c * chunk, nc = n_pairs - p0 < chunk ? n_pairs - p0 : chunk;
+        VSLAM_CUDA(ctx, cudaStreamWaitEvent(s, f->ev_in[c], 0));
+        int st = front_enqueue_chunk(ctx, dl + p0 * dstride, dr + p0 * dstride, n_pairs, p0, nc, width, height, dpitch,
+                                     (long long)dstride, nfeatures, anms_keep, anms_c, gate_rel, gate_abs, P1, P2,
+                                     T_c_w ? f->d_pose : nullptr, f->d_kp, f->d_desc, f->d_nkp, f->d_match,
+                                     f->d_nmatch, f->d_xyz, f->d_flags);
+        if (st != VSLAM_OK) {
+            cudaStreamSynchronize(f->s_in);
+            cudaStreamSynchronize(f->s_out);
+            cudaStreamSynchronize(s);
+            return st;
+        }
+        VSLAM_CUDA(ctx, cudaEventRecord(f->ev_done[c], s));
+        VSLAM_CUDA(ctx, cudaStreamWaitEvent(f->s_out, f->ev_done[c], 0));
+        const size_t l0 = (size_t)p0, r0 = np + p0, n = (size_t)nc;
+        cudaStream_t so = f->s_out;
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(kp + l0 * cap, f->d_kp + l0 * cap, n * cap * sizeof(vslam_keypoint), cudaMemcpyDeviceToHost, so));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(kp + r0 * cap, f->d_kp + r0 * cap, n * cap * sizeof(vslam_keypoint), cudaMemcpyDeviceToHost, so));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(desc + l0 * cap * 32, f->d_desc + l0 * cap * 32, n * cap * 32, cudaMemcpyDeviceToHost, so));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(desc + r0 * cap * 32, f->d_desc + r0 * cap * 32, n * cap * 32, cudaMemcpyDeviceToHost, so));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(matches + l0 * cap, f->d_match + l0 * cap, n * cap * sizeof(vslam_dmatch), cudaMemcpyDeviceToHost, so));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(xyz + l0 * cap * 3, f->d_xyz + l0 * cap * 3, n * cap * 12, cudaMemcpyDeviceToHost, so));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(flags + l0 * cap, f->d_flags + l0 * cap, n * cap, cudaMemcpyDeviceToHost, so));
+    }
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(n_kp, f->d_nkp, 2 * np * sizeof(int32_t), cudaMemcpyDeviceToHost, f->s_out));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(n_matches, f->d_nmatch, np * sizeof(int32_t), cudaMemcpyDeviceToHost, f->s_out));
+    const int st = vslam_orb_check_flags(ctx, 2 * n_pairs);  // synchronises the context stream
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(f->s_out));
+    return st;  // VSLAM_E_OVERFLOW if a work list overflowed
 }

@@ -72,6 +72,7 @@ struct OrbState {
     uint2* d_cand;        // {x | y << 16, score}
     uint2* d_sel;         // [img][level][SORT_CAP] {x | y << 16, response bits}
     ImgCounters* d_cnt;
+    uint32_t* d_sticky;   // OR of every overflow flag raised since the last check (survives chunked batches)
     uint32_t* d_keep;     // ANMS keep list [img][kp_cap]
     double* d_rad;        // ANMS radii [img][kp_cap]
     int8_t* d_pattern;    // 256 x 4
@@ -155,7 +156,7 @@ __device__ __forceinline__ bool has_arc9(uint32_t m16) {
 
 __global__ void __launch_bounds__(FAST_THREADS)
 fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g, uint2* __restrict__ cand,
-            ImgCounters* __restrict__ cnt) {
+            ImgCounters* __restrict__ cnt, uint32_t* __restrict__ sticky) {
     __shared__ uint8_t s_img[SI_H * SI_W];
     __shared__ uint8_t s_score[SS_H * SS_W];
     __shared__ uint16_t s_list[SS_H * SS_W];
@@ -295,7 +296,10 @@ fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__
     for (int i = tid; i < nout; i += FAST_THREADS) {
         if (base + i < L.cand_cap) dst[base + i] = s_out[i];
     }
-    if (tid == 0 && base + nout > L.cand_cap) atomicOr(&C->flags, 1u);
+    if (tid == 0 && base + nout > L.cand_cap) {
+        atomicOr(&C->flags, 1u);
+        atomicOr(sticky, 1u);
+    }
     if (s_hist[tid]) atomicAdd(&C->hist[l][tid], s_hist[tid]);
 }
 
@@ -310,7 +314,8 @@ __device__ __forceinline__ uint32_t float_desc_key(float f) {
 
 __global__ void __launch_bounds__(HS_THREADS)
 harris_select_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g, const __grid_constant__ OrbQuota quota,
-                     const uint2* __restrict__ cand, ImgCounters* __restrict__ cnt, uint2* __restrict__ sel) {
+                     const uint2* __restrict__ cand, ImgCounters* __restrict__ cnt, uint2* __restrict__ sel,
+                     uint32_t* __restrict__ sticky) {
     extern __shared__ unsigned long long s_key[];  // SORT_CAP
     __shared__ uint32_t s_h[256];
     __shared__ uint8_t s_patch[HS_THREADS / 32][96];
@@ -352,7 +357,10 @@ harris_select_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_c
     __syncthreads();
     int n = s_n;
     if (n > SORT_CAP) {
-        if (tid == 0) atomicOr(&C->flags, 2u);
+        if (tid == 0) {
+            atomicOr(&C->flags, 2u);
+            atomicOr(sticky, 2u);
+        }
         n = SORT_CAP;
     }
     int n2 = 1;
@@ -664,7 +672,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32)
 describe_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, const __grid_constant__ OrbGeom g,
                 const uint2* __restrict__ sel, ImgCounters* __restrict__ cnt, const uint32_t* __restrict__ keep,
                 int use_keep, const int8_t* __restrict__ pattern, int kp_cap, vslam_keypoint* __restrict__ kp_out,
-                uint8_t* __restrict__ desc_out, int32_t* __restrict__ n_out) {
+                uint8_t* __restrict__ desc_out, int32_t* __restrict__ n_out, uint32_t* __restrict__ sticky) {
     const int img = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
@@ -673,11 +681,15 @@ describe_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const uint8_t* __re
 #pragma unroll
     for (int i = 0; i < ORB_NL; ++i) total += (int)C->sel_cnt[i];
     if (total > kp_cap) {
-        if (k == 0 && lane == 0) atomicOr(&C->flags, 4u);
+        if (k == 0 && lane == 0) {
+            atomicOr(&C->flags, 4u);
+            atomicOr(sticky, 4u);
+        }
         total = kp_cap;
     }
+    const int oslot = img < src.per_base ? src.out_slot[0] + img : src.out_slot[1] + (img - src.per_base);
     const int n = use_keep ? (int)C->n_keep : total;
-    if (k == 0 && lane == 0) n_out[img] = n;
+    if (k == 0 && lane == 0) n_out[oslot] = n;
     if (k >= n) return;
     const int gi = use_keep ? (int)keep[(size_t)img * kp_cap + k] : k;
     int j;
@@ -708,7 +720,7 @@ describe_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const uint8_t* __re
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
     const float ptx = __fmul_rn((float)x, L.scale), pty = __fmul_rn((float)y, L.scale);
-    vslam_keypoint* ko = kp_out + (size_t)img * kp_cap + k;
+    vslam_keypoint* ko = kp_out + (size_t)oslot * kp_cap + k;
     if (lane < 7) {
         uint32_t w;
         switch (lane) {
@@ -744,7 +756,7 @@ describe_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const uint8_t* __re
         const int t1 = center[(long long)iy1 * L.pitch + ix1];
         byte |= (uint32_t)(t0 < t1) << t;
     }
-    desc_out[((size_t)img * kp_cap + k) * 32 + lane] = (uint8_t)byte;
+    desc_out[((size_t)oslot * kp_cap + k) * 32 + lane] = (uint8_t)byte;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -853,6 +865,8 @@ int vslam_orb_init(vslam_ctx* ctx) {
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_cand, ni * o->cand_cap_total * sizeof(uint2)));
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_sel, ni * ORB_NL * SORT_CAP * sizeof(uint2)));
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_cnt, ni * sizeof(ImgCounters)));
+    VSLAM_CUDA(ctx, cudaMalloc(&o->d_sticky, sizeof(uint32_t)));
+    VSLAM_CUDA(ctx, cudaMemset(o->d_sticky, 0, sizeof(uint32_t)));
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_keep, ni * o->kp_cap * sizeof(uint32_t)));
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_rad, ni * o->kp_cap * sizeof(double)));
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_pattern, 1024));
@@ -880,6 +894,7 @@ void vslam_orb_free(vslam_ctx* ctx) {
     cudaFree(o->d_cand);
     cudaFree(o->d_sel);
     cudaFree(o->d_cnt);
+    cudaFree(o->d_sticky);
     cudaFree(o->d_keep);
     cudaFree(o->d_rad);
     cudaFree(o->d_pattern);
@@ -919,12 +934,12 @@ int vslam_orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h
         VSLAM_LAUNCH_CHECK(ctx, "resize_level_kernel");
     }
     vslam_time_begin(ctx, VK_FAST);
-    fast_kernel<<<dim3(g.total_tiles, n_img), FAST_THREADS, 0, s>>>(src, o->d_pyr, g, o->d_cand, o->d_cnt);
+    fast_kernel<<<dim3(g.total_tiles, n_img), FAST_THREADS, 0, s>>>(src, o->d_pyr, g, o->d_cand, o->d_cnt, o->d_sticky);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "fast_kernel");
     vslam_time_begin(ctx, VK_HARRIS_SELECT);
     harris_select_kernel<<<dim3(ORB_NL, n_img), HS_THREADS, SORT_CAP * sizeof(unsigned long long), s>>>(
-        src, o->d_pyr, g, q, o->d_cand, o->d_cnt, o->d_sel);
+        src, o->d_pyr, g, q, o->d_cand, o->d_cnt, o->d_sel, o->d_sticky);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "harris_select_kernel");
     vslam_time_begin(ctx, VK_BLUR);
@@ -945,7 +960,7 @@ int vslam_orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h
     vslam_time_begin(ctx, VK_DESCRIBE);
     describe_kernel<<<dim3(ceil_div(o->kp_cap, DESC_WARPS), n_img), DESC_WARPS * 32, 0, s>>>(
         src, o->d_pyr, o->d_blur, g, o->d_sel, o->d_cnt, o->d_keep, use_keep, o->d_pattern, o->kp_cap, d_kp, d_desc,
-        d_n);
+        d_n, o->d_sticky);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "describe_kernel");
     return VSLAM_OK;
@@ -965,20 +980,20 @@ extern "C" int vslam_orb_detect_compute_batch_dev(vslam_ctx* ctx, const uint8_t*
     src.img_stride = image_stride;
     src.pitch = row_pitch;
     src.per_base = n_images > 0 ? n_images : 1;
+    src.out_slot[0] = 0;
+    src.out_slot[1] = src.per_base;
     return vslam_orb_enqueue(ctx, src, n_images, width, height, nfeatures, anms_keep, anms_c, d_kp, d_desc, d_n);
 }
 
 // flags raised by the kernels (bit0 candidate overflow, bit1 sort overflow, bit2 keypoint capacity)
 int vslam_orb_check_flags(vslam_ctx* ctx, int n_img) {
+    (void)n_img;
     OrbState* o = ctx->orb;
-    for (int i = 0; i < n_img; ++i) {
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(&o->h_cnt[i].flags, &o->d_cnt[i].flags, sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                        ctx->stream));
-    }
+    uint32_t* h = &o->h_cnt[0].flags;  // pinned scratch word
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(h, o->d_sticky, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    VSLAM_CUDA(ctx, cudaMemsetAsync(o->d_sticky, 0, sizeof(uint32_t), ctx->stream));
     VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < n_img; ++i)
-        if (o->h_cnt[i].flags) return VSLAM_E_OVERFLOW;
-    return VSLAM_OK;
+    return *h ? VSLAM_E_OVERFLOW : VSLAM_OK;
 }
 
 extern "C" int vslam_orb_last_flags(vslam_ctx* ctx, int n_images) {
@@ -1009,6 +1024,8 @@ extern "C" int vslam_orb_detect_compute_batch(vslam_ctx* ctx, const uint8_t* ima
     src.img_stride = (long long)dstride;
     src.pitch = o->in_pitch;
     src.per_base = n_images;
+    src.out_slot[0] = 0;
+    src.out_slot[1] = n_images;
     int st = vslam_orb_enqueue(ctx, src, n_images, width, height, nfeatures, anms_keep, anms_c, o->d_kp, o->d_desc, o->d_n);
     if (st != VSLAM_OK) return st;
     VSLAM_CUDA(ctx, cudaMemcpyAsync(o->h_n, o->d_n, n_images * sizeof(int32_t), cudaMemcpyDeviceToHost, s));

@@ -30,3 +30,11 @@ def gpu_ctx(pkg):
     ctx = pkg.Context(device=0, max_images=16, max_width=1241, max_height=376, max_keypoints=8192)
     yield ctx
     ctx.close()
+
+
+@pytest.fixture(scope="module")
+def gpu_ctx_big(pkg):
+    """A context sized for multi-chunk batches of the host-buffer frontend (80 images, 1280 keypoints each)."""
+    ctx = pkg.Context(device=0, max_images=80, max_width=1241, max_height=376, max_keypoints=1280)
+    yield ctx
+    ctx.close()

@@ -98,3 +98,28 @@ def test_stereo_frontend_batch(pkg, gpu_ctx, pattern, seeds):
         ref_usable = (pc[:, 2] > 10) & (pc[:, 2] < 400)
         safe = (np.abs(pc[:, 2] - 10) > 1e-6) & (np.abs(pc[:, 2] - 40) > 1e-6) & (np.abs(pc[:, 2] - 400) > 1e-6)
         assert np.array_equal((flags & 1).astype(bool)[safe], ref_usable[safe])
+
+
+def test_stereo_frontend_chunked_pipeline_equals_per_pair(pkg, gpu_ctx_big):
+    """The host-buffer call splits a batch into 16-pair chunks whose H2D / kernels / D2H overlap on three streams;
+    the results must be those of the same pairs submitted one at a time (37 pairs: two full chunks + a ragged one)."""
+    P1, P2 = _cams(pkg)
+    base = [pkg.synth.synth_pair(s)[:2] for s in range(3)]
+    b = 37
+    left = np.stack([np.roll(base[i % 3][0], 5 * (i // 3), axis=0) for i in range(b)])
+    right = np.stack([np.roll(base[i % 3][1], 5 * (i // 3), axis=0) for i in range(b)])
+    T = np.tile(np.eye(4)[:3].reshape(1, 12), (b, 1))
+    T[:, 3] = np.arange(b) * 0.25       # distinct poses: the pose of pair i must be applied to pair i
+    out = gpu_ctx_big.stereo_frontend(left, right, P1, P2, T_c_w=T, nfeatures=1000)
+    for i in (0, 1, 15, 16, 17, 31, 32, 36):
+        one = gpu_ctx_big.stereo_frontend(left[i:i + 1], right[i:i + 1], P1, P2, T_c_w=T[i:i + 1], nfeatures=1000)
+        nl, nr, nm = one["n_kp"][0], one["n_kp"][1], one["n_matches"][0]
+        assert (out["n_kp"][i], out["n_kp"][b + i], out["n_matches"][i]) == (nl, nr, nm)
+        assert nl > 900 and nm > 50
+        assert np.array_equal(out["kp"][i, :nl], one["kp"][0, :nl])
+        assert np.array_equal(out["kp"][b + i, :nr], one["kp"][1, :nr])
+        assert np.array_equal(out["desc"][i, :nl], one["desc"][0, :nl])
+        assert np.array_equal(out["desc"][b + i, :nr], one["desc"][1, :nr])
+        assert np.array_equal(out["matches"][i, :nm], one["matches"][0, :nm])
+        assert np.array_equal(out["xyz"][i, :nm], one["xyz"][0, :nm])
+        assert np.array_equal(out["flags"][i, :nm], one["flags"][0, :nm])
