@@ -139,27 +139,32 @@ resize_level_kernel(ImgSrc src, uint8_t* __restrict__ pyr, const uint32_t* __res
 // ------------------------------------------------------------------------------------------------------------
 // K2  FAST-9/16 + NMS + border filter
 // ------------------------------------------------------------------------------------------------------------
-#define SI_W (TILE_W + 8)
-#define SI_H (TILE_H + 8)
-#define SS_W (TILE_W + 2)
-#define SS_H (TILE_H + 2)
+// The tile's pixels are widened to 16 bits in shared memory so that one 32-bit word holds TWO horizontally adjacent
+// pixels; every step of the segment test / corner score then runs on a pixel pair with the native packed-16-bit
+// instructions of sm_100a (VIADD.16x2, VIMNMX.S16x2, VIMNMX3.S16x2).
+//   image tile : rows gy = ty0-4 .. ty0+35, columns gx = tx0-8 .. tx0+71 (gx < tx0-4 and gx > tx0+67 are zero padding)
+//   score tile : rows gy = ty0-1 .. ty0+32, columns gx = tx0-2 .. tx0+65, value h = max(corner score + 1, FAST_T)
+#define FI_ROWS (TILE_H + 8)
+#define FI_WORDS 40                 // words per image-tile row (80 pixels)
+#define FI_LOAD_WORDS 18            // 32-bit global words per row that carry pixels (72 pixels)
+#define FS_ROWS (TILE_H + 2)
+#define FS_WORDS 34                 // words (= pixel pairs) per score-tile row
 #define FAST_OUT_CAP 640
+#define FAST_TT ((uint32_t)FAST_T | ((uint32_t)FAST_T << 16))
 
-__device__ __forceinline__ bool has_arc9(uint32_t m16) {
-    uint32_t x = m16 | (m16 << 16);
-    uint32_t a = x & (x >> 1);
-    a &= a >> 2;
-    a &= a >> 4;
-    a &= x >> 8;
-    return (a & 0xFFFFu) != 0;
+__device__ __forceinline__ uint32_t neg16x2(uint32_t a) { return __vadd2(~a, 0x00010001u); }
+// two adjacent pixels starting at the odd pixel of word `lo` (upper half of lo, lower half of hi)
+__device__ __forceinline__ uint32_t mid16x2(uint32_t lo, uint32_t hi) { return __byte_perm(lo, hi, 0x5432); }
+__device__ __forceinline__ bool any_lane_gt_t(uint32_t e) {
+    return (int)(e << 16) > (FAST_T << 16) || (int)e > ((FAST_T << 16) | 0xFFFF);
 }
 
 __global__ void __launch_bounds__(FAST_THREADS)
 fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g, uint2* __restrict__ cand,
             ImgCounters* __restrict__ cnt, uint32_t* __restrict__ sticky) {
-    __shared__ uint8_t s_img[SI_H * SI_W];
-    __shared__ uint8_t s_score[SS_H * SS_W];
-    __shared__ uint16_t s_list[SS_H * SS_W];
+    __shared__ __align__(16) uint32_t s_img[FI_ROWS * FI_WORDS];
+    __shared__ uint32_t s_sc[FS_ROWS * FS_WORDS];
+    __shared__ uint16_t s_list[FS_ROWS * FS_WORDS];
     __shared__ uint2 s_out[FAST_OUT_CAP];
     __shared__ uint32_t s_hist[256];
     __shared__ int s_n1, s_nout, s_base;
@@ -174,16 +179,36 @@ fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__
     const int tx0 = (t % L.tiles_x) * TILE_W, ty0 = (t / L.tiles_x) * TILE_H;
     int pitch;
     const uint8_t* im = level_ptr(src, pyr, g, img, l, pitch);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int W = L.w, H = L.h;
 
-    for (int i = tid; i < SI_H * SI_W; i += FAST_THREADS) {
-        const int r = i / SI_W, c = i - r * SI_W;
-        const int gy = ty0 - 4 + r, gx = tx0 - 4 + c;
-        uint8_t v = 0;
-        if (gx >= 0 && gx < L.w && gy >= 0 && gy < L.h) v = im[(size_t)gy * pitch + gx];
-        s_img[i] = v;
+    // ---- load: 4 pixels per work item through aligned 32-bit global loads, widened to 2 x (2 pixels) ------------
+    for (int i = tid; i < FI_ROWS * FI_LOAD_WORDS; i += FAST_THREADS) {
+        const int r = i / FI_LOAD_WORDS, wj = i - r * FI_LOAD_WORDS;
+        const int gy = ty0 - 4 + r, gx = tx0 - 4 + 4 * wj;
+        uint32_t px = 0;
+        if (gy >= 0 && gy < H) {
+            const uint8_t* p = im + (size_t)gy * pitch + gx;
+            if (gx >= 0 && gx + 3 < W) {
+                const uint32_t a = (uint32_t)(uintptr_t)p & 3u;
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(p - a);
+                px = __ldg(q);
+                if (a) px = __funnelshift_r(px, __ldg(q + 1), 8 * a);
+            } else {
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (gx + b >= 0 && gx + b < W) px |= (uint32_t)p[b] << (8 * b);
+            }
+        }
+        uint2 v;
+        v.x = __byte_perm(px, 0, 0x4140);
+        v.y = __byte_perm(px, 0, 0x4342);
+        *reinterpret_cast<uint2*>(&s_img[r * FI_WORDS + 2 + 2 * wj]) = v;
     }
-    for (int i = tid; i < SS_H * SS_W; i += FAST_THREADS) s_score[i] = 0;
+    if (tid < FI_ROWS * 4) {  // zero padding: words 0,1 and 38,39 of every row
+        const int r = tid >> 2, k = tid & 3;
+        s_img[r * FI_WORDS + (k < 2 ? k : 36 + k)] = 0;
+    }
     s_hist[tid] = 0;  // FAST_THREADS == 256
     if (tid == 0) {
         s_n1 = 0;
@@ -191,99 +216,136 @@ fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__
     }
     __syncthreads();
 
-    // phase 1: compass pre-test (any 9-arc contains two adjacent compass pixels)
-    for (int i = tid; i < SS_H * SS_W; i += FAST_THREADS) {
-        const int sy = i / SS_W, sx = i - sy * SS_W;
-        const int gy = ty0 - 1 + sy, gx = tx0 - 1 + sx;
-        if (gx < 3 || gx >= L.w - 3 || gy < 3 || gy >= L.h - 3) continue;
-        const uint8_t* c = &s_img[(sy + 3) * SI_W + sx + 3];
-        const int v = c[0];
-        const int hi = v + FAST_T, lo = v - FAST_T;
-        const int p0 = c[3 * SI_W], p4 = c[3], p8 = c[-3 * SI_W], p12 = c[-3];
-        const uint32_t d = (p0 > hi) | ((p4 > hi) << 1) | ((p8 > hi) << 2) | ((p12 > hi) << 3);
-        const uint32_t b = (p0 < lo) | ((p4 < lo) << 1) | ((p8 < lo) << 2) | ((p12 < lo) << 3);
-        const uint32_t dd = d & ((d >> 1) | (d << 3));
-        const uint32_t bb = b & ((b >> 1) | (b << 3));
-        if ((dd | bb) & 0xF) s_list[atomicAdd(&s_n1, 1)] = (uint16_t)i;
+    // ---- phase 1: compass pre-test on pixel pairs (any 9-arc contains two adjacent compass pixels) ---------------
+    for (int p0 = 0; p0 < FS_ROWS * FS_WORDS; p0 += FAST_THREADS) {
+        const int p = p0 + tid;
+        bool pass = false;
+        if (p < FS_ROWS * FS_WORDS) {
+            const int r = p / FS_WORDS, j = p - r * FS_WORDS;
+            const uint32_t* c = &s_img[(r + 3) * FI_WORDS + j + 3];
+            const uint32_t nv = neg16x2(c[0]);
+            const uint32_t d0 = __vadd2(c[3 * FI_WORDS], nv), d8 = __vadd2(c[-3 * FI_WORDS], nv);
+            const uint32_t d4 = __vadd2(mid16x2(c[1], c[2]), nv), d12 = __vadd2(mid16x2(c[-2], c[-1]), nv);
+            const uint32_t mb = __vmaxs2(__vimax3_s16x2(__vmins2(d0, d4), __vmins2(d4, d8), __vmins2(d8, d12)),
+                                         __vmins2(d12, d0));
+            const uint32_t md = __vmins2(__vimin3_s16x2(__vmaxs2(d0, d4), __vmaxs2(d4, d8), __vmaxs2(d8, d12)),
+                                         __vmaxs2(d12, d0));
+            pass = any_lane_gt_t(__vmaxs2(mb, neg16x2(md)));
+            if (!pass) s_sc[p] = FAST_TT;
+        }
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pass);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_n1, __popc(bal));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (pass) s_list[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)p;
+        }
     }
     __syncthreads();
 
-    // phase 2: full segment test and corner score on the survivors
+    // ---- phase 2: full segment test + corner score on the surviving pairs ----------------------------------------
+    // score = max over the 16 arcs of max(min(d), -max(d)), d = centre - ring (sign-symmetric, so ring - centre is
+    // used); a pixel is a corner iff that exceeds FAST_T.  Sliding min / max over 9 = (pairs, quads, 4+4+1).
     const int n1 = s_n1;
     for (int e = tid; e < n1; e += FAST_THREADS) {
-        const int i = s_list[e];
-        const int sy = i / SS_W, sx = i - sy * SS_W;
-        const uint8_t* c = &s_img[(sy + 3) * SI_W + sx + 3];
-        const int v = c[0];
-        int d[16];
-        d[0] = v - c[3 * SI_W];
-        d[1] = v - c[3 * SI_W + 1];
-        d[2] = v - c[2 * SI_W + 2];
-        d[3] = v - c[1 * SI_W + 3];
-        d[4] = v - c[3];
-        d[5] = v - c[-1 * SI_W + 3];
-        d[6] = v - c[-2 * SI_W + 2];
-        d[7] = v - c[-3 * SI_W + 1];
-        d[8] = v - c[-3 * SI_W];
-        d[9] = v - c[-3 * SI_W - 1];
-        d[10] = v - c[-2 * SI_W - 2];
-        d[11] = v - c[-1 * SI_W - 3];
-        d[12] = v - c[-3];
-        d[13] = v - c[1 * SI_W - 3];
-        d[14] = v - c[2 * SI_W - 2];
-        d[15] = v - c[3 * SI_W - 1];
-        uint32_t mb = 0, md = 0;
+        const int p = s_list[e];
+        const int r = p / FS_WORDS, j = p - r * FS_WORDS;
+        const uint32_t* c = &s_img[(r + 3) * FI_WORDS + j + 3];
+        const uint32_t nv = neg16x2(c[0]);
+        uint32_t d[16];
+        {
+            const uint32_t* q = c + 3 * FI_WORDS;
+            const uint32_t a = q[-1], b = q[0], cc = q[1];
+            d[15] = mid16x2(a, b); d[0] = b; d[1] = mid16x2(b, cc);
+        }
+        {
+            const uint32_t* q = c - 3 * FI_WORDS;
+            const uint32_t a = q[-1], b = q[0], cc = q[1];
+            d[9] = mid16x2(a, b); d[8] = b; d[7] = mid16x2(b, cc);
+        }
+        d[14] = c[2 * FI_WORDS - 1]; d[2] = c[2 * FI_WORDS + 1];
+        d[10] = c[-2 * FI_WORDS - 1]; d[6] = c[-2 * FI_WORDS + 1];
+        {
+            const uint32_t* q = c + FI_WORDS;
+            d[13] = mid16x2(q[-2], q[-1]); d[3] = mid16x2(q[1], q[2]);
+        }
+        {
+            const uint32_t* q = c - FI_WORDS;
+            d[11] = mid16x2(q[-2], q[-1]); d[5] = mid16x2(q[1], q[2]);
+        }
+        d[12] = mid16x2(c[-2], c[-1]); d[4] = mid16x2(c[1], c[2]);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d[k] = __vadd2(d[k], nv);
+        uint32_t mn[16], mx[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            mb |= (uint32_t)(d[k] > FAST_T) << k;
-            md |= (uint32_t)(d[k] < -FAST_T) << k;
+            mn[k] = __vmins2(d[k], d[(k + 1) & 15]);
+            mx[k] = __vmaxs2(d[k], d[(k + 1) & 15]);
         }
-        if (!(has_arc9(mb) || has_arc9(md))) continue;
-        // best = max over the 16 arcs of max(min(d), -max(d)); sliding min/max by doubling
-        int mn[16], mx[16];
+        uint32_t mn2[16], mx2[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            mn[k] = min(d[k], d[(k + 1) & 15]);
-            mx[k] = max(d[k], d[(k + 1) & 15]);
+            mn2[k] = __vmins2(mn[k], mn[(k + 2) & 15]);
+            mx2[k] = __vmaxs2(mx[k], mx[(k + 2) & 15]);
         }
-        int mn2[16], mx2[16];
+        uint32_t a[16], b[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            mn2[k] = min(mn[k], mn[(k + 2) & 15]);
-            mx2[k] = max(mx[k], mx[(k + 2) & 15]);
+            a[k] = __vimin3_s16x2(mn2[k], mn2[(k + 4) & 15], d[(k + 8) & 15]);
+            b[k] = __vimax3_s16x2(mx2[k], mx2[(k + 4) & 15], d[(k + 8) & 15]);
         }
-        // max_k max(a_k, -b_k) == max(max_k a_k, -min_k b_k).  The negation is kept OUT of the min/max chain on
-        // purpose: ptxas 12.9 -O3 for sm_100a miscompiles max(x, -y) when it folds the negation into
-        // VIMNMX3/VIADDMNMX (reproduced standalone: tools/scratch/t_fast2.cu gives 51 instead of 22).
-        int besta = -1000, bmin = 1000;
+        uint32_t besta = __vimax3_s16x2(a[0], a[1], a[2]), bmin = __vimin3_s16x2(b[0], b[1], b[2]);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int a = min(min(mn2[k], mn2[(k + 4) & 15]), d[(k + 8) & 15]);
-            const int b = max(max(mx2[k], mx2[(k + 4) & 15]), d[(k + 8) & 15]);
-            besta = max(besta, a);
-            bmin = min(bmin, b);
+        for (int k = 3; k < 15; k += 2) {
+            besta = __vimax3_s16x2(besta, a[k], a[k + 1]);
+            bmin = __vimin3_s16x2(bmin, b[k], b[k + 1]);
         }
-        int nb = 0 - bmin;
-        asm volatile("" : "+r"(nb));
-        const int best = max(besta, nb);
-        s_score[i] = (uint8_t)(best - 1);  // best > 20 here, <= 255
+        besta = __vmaxs2(besta, a[15]);
+        bmin = __vmins2(bmin, b[15]);
+        const uint32_t best = __vmaxs2(besta, neg16x2(bmin));
+        // pixels closer than 3 to the image border have no full ring: not corners (h = FAST_T)
+        const int gy = ty0 - 1 + r, gx = tx0 - 2 + 2 * j;
+        const bool vy = gy >= 3 && gy < H - 3;
+        const uint32_t mask = ((vy && gx >= 3 && gx < W - 3) ? 0x00007FFFu : 0u) |
+                              ((vy && gx + 1 >= 3 && gx + 1 < W - 3) ? 0x7FFF0000u : 0u);
+        s_sc[p] = __vmaxs2(__vmins2(best, mask), FAST_TT);
     }
     __syncthreads();
 
-    // phase 3: 3x3 NMS (strictly greater), border filter, emit
-    for (int i = tid; i < TILE_W * TILE_H; i += FAST_THREADS) {
-        const int sy = i / TILE_W + 1, sx = i % TILE_W + 1;
-        const uint8_t* sc = &s_score[sy * SS_W + sx];
-        const int s = sc[0];
-        if (s == 0) continue;
-        if (sc[-1] >= s || sc[1] >= s || sc[-SS_W - 1] >= s || sc[-SS_W] >= s || sc[-SS_W + 1] >= s ||
-            sc[SS_W - 1] >= s || sc[SS_W] >= s || sc[SS_W + 1] >= s)
-            continue;
-        const int gy = ty0 - 1 + sy, gx = tx0 - 1 + sx;
-        if (gx < ORB_EDGE || gx >= L.w - ORB_EDGE || gy < ORB_EDGE || gy >= L.h - ORB_EDGE) continue;
-        const int pos = atomicAdd(&s_nout, 1);
-        if (pos < FAST_OUT_CAP) s_out[pos] = make_uint2((uint32_t)gx | ((uint32_t)gy << 16), (uint32_t)s);
-        atomicAdd(&s_hist[s], 1u);
+    // ---- phase 3: 3x3 NMS (strictly greater) on pixel pairs, border filter, emit ------------------------------------
+    for (int q0 = 0; q0 < TILE_W * TILE_H / 2; q0 += FAST_THREADS) {
+        const int q = q0 + tid;
+        const int r = q >> 5, j = q & 31;  // TILE_W / 2 == 32 pairs per row
+        const uint32_t* sc = &s_sc[(r + 1) * FS_WORDS + j + 1];
+        const uint32_t c0 = sc[0];
+        uint32_t m = __vimax3_s16x2(mid16x2(sc[-1], c0), mid16x2(c0, sc[1]), sc[-FS_WORDS]);
+        m = __vimax3_s16x2(m, mid16x2(sc[-FS_WORDS - 1], sc[-FS_WORDS]), mid16x2(sc[-FS_WORDS], sc[-FS_WORDS + 1]));
+        m = __vimax3_s16x2(m, mid16x2(sc[FS_WORDS - 1], sc[FS_WORDS]), mid16x2(sc[FS_WORDS], sc[FS_WORDS + 1]));
+        m = __vmaxs2(m, sc[FS_WORDS]);
+        const uint32_t x = __vmaxs2(c0, m) ^ m;  // lane != 0  <=>  centre strictly greater than its 8 neighbours
+        const int gy = ty0 + r, gx = tx0 + 2 * j;
+        const bool iny = gy >= ORB_EDGE && gy < H - ORB_EDGE;
+        const bool k0 = (x & 0xFFFFu) && iny && gx >= ORB_EDGE && gx < W - ORB_EDGE;
+        const bool k1 = (x >> 16) && iny && gx + 1 >= ORB_EDGE && gx + 1 < W - ORB_EDGE;
+        const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, k0), b1 = __ballot_sync(0xFFFFFFFFu, k1);
+        if (b0 | b1) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_nout, __popc(b0) + __popc(b1));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            const uint32_t lt = (1u << lane) - 1;
+            int pos = base + __popc(b0 & lt) + __popc(b1 & lt);
+            if (k0) {
+                const uint32_t s = (c0 & 0xFFFFu) - 1;
+                if (pos < FAST_OUT_CAP) s_out[pos] = make_uint2((uint32_t)gx | ((uint32_t)gy << 16), s);
+                atomicAdd(&s_hist[s], 1u);
+                ++pos;
+            }
+            if (k1) {
+                const uint32_t s = (c0 >> 16) - 1;
+                if (pos < FAST_OUT_CAP) s_out[pos] = make_uint2((uint32_t)(gx + 1) | ((uint32_t)gy << 16), s);
+                atomicAdd(&s_hist[s], 1u);
+            }
+        }
     }
     __syncthreads();
     const int nout = min(s_nout, FAST_OUT_CAP);  // a 64x32 tile holds at most 512 strict 3x3 maxima
