@@ -113,27 +113,61 @@ __device__ __forceinline__ const uint8_t* level_ptr(const ImgSrc& src, const uin
 // ------------------------------------------------------------------------------------------------------------
 // K1  resize INTER_LINEAR_EXACT: out = (c0y*(c0x*s00 + c1x*s01) + c1y*(c0x*s10 + c1x*s11) + 32768) >> 16
 // ------------------------------------------------------------------------------------------------------------
+// One thread produces 4 horizontally adjacent output pixels and stores them as one word.  Their source bytes span at
+// most 6 columns (scale 1.2), fetched per source row as up to three aligned words and shifted into place; the
+// horizontal pass of each pixel is one byte permute + one 16x8-bit dot product (IDP.2A).
+__device__ __forceinline__ void load_window(const uint8_t* p, int last_byte, uint32_t& v0, uint32_t& v1) {
+    const uint32_t a = (uint32_t)(uintptr_t)p & 3u;
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p - a);
+    const int need = (int)a + last_byte;  // index of the last needed byte inside the aligned window
+    const uint32_t w0 = __ldg(q);
+    const uint32_t w1 = need >= 4 ? __ldg(q + 1) : 0u;
+    const uint32_t w2 = need >= 8 ? __ldg(q + 2) : 0u;
+    v0 = __funnelshift_r(w0, w1, 8 * a);
+    v1 = __funnelshift_r(w1, w2, 8 * a);
+}
+
 __global__ void __launch_bounds__(256)
 resize_level_kernel(ImgSrc src, uint8_t* __restrict__ pyr, const uint32_t* __restrict__ tab, const __grid_constant__ OrbGeom g, int l) {
     const int img = blockIdx.z;
     const OrbLevel& L = g.lv[l];
-    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int x = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int y = blockIdx.y * 8 + threadIdx.y;
     if (x >= L.w || y >= L.h) return;
     int sp;
     const uint8_t* s = level_ptr(src, pyr, g, img, l - 1, sp);
     const int sw = g.lv[l - 1].w, sh = g.lv[l - 1].h;
-    const uint32_t tx = __ldg(&tab[L.xtab_off + x]);
+    const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(&tab[L.xtab_off + x]));  // table regions are 16-byte aligned
+    uint32_t tx[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+        if (x + k >= L.w) tx[k] = tx[0];  // columns in the row padding: any in-range value
     const uint32_t ty = __ldg(&tab[L.ytab_off + y]);
-    const int ox = tx >> 16, c1x = tx & 0xFFFF, c0x = 256 - c1x;
     const int oy = ty >> 16, c1y = ty & 0xFFFF, c0y = 256 - c1y;
-    const int ox1 = min(ox + 1, sw - 1), oy1 = min(oy + 1, sh - 1);
-    const uint8_t* r0 = s + (size_t)oy * sp;
-    const uint8_t* r1 = s + (size_t)oy1 * sp;
-    const int h0 = c0x * (int)r0[ox] + c1x * (int)r0[ox1];
-    const int h1 = c0x * (int)r1[ox] + c1x * (int)r1[ox1];
-    const int v = (c0y * h0 + c1y * h1 + 32768) >> 16;
-    pyr[(size_t)img * g.img_slab + L.off + (size_t)y * L.pitch + x] = (uint8_t)v;
+    const int oy1 = min(oy + 1, sh - 1);
+    const int ox0 = tx[0] >> 16;
+    uint32_t sel[4], coef[4];
+    int last = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int ox = tx[k] >> 16, c1x = tx[k] & 0xFFFF;
+        const int d0 = ox - ox0, d1 = min(ox + 1, sw - 1) - ox0;
+        sel[k] = (uint32_t)d0 | ((uint32_t)d1 << 4);
+        coef[k] = (uint32_t)(256 - c1x) | ((uint32_t)c1x << 16);
+        last = max(last, d1);
+    }
+    uint32_t a0, a1, b0, b1;
+    load_window(s + (size_t)oy * sp + ox0, last, a0, a1);
+    load_window(s + (size_t)oy1 * sp + ox0, last, b0, b1);
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t h0 = __dp2a_lo(coef[k], __byte_perm(a0, a1, sel[k]), 0u);
+        const uint32_t h1 = __dp2a_lo(coef[k], __byte_perm(b0, b1, sel[k]), 0u);
+        const uint32_t v = ((uint32_t)c0y * h0 + (uint32_t)c1y * h1 + 32768u) >> 16;
+        packed |= v << (8 * k);
+    }
+    *reinterpret_cast<uint32_t*>(&pyr[(size_t)img * g.img_slab + L.off + (size_t)y * L.pitch + x]) = packed;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -512,8 +546,8 @@ harris_select_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_c
 // ------------------------------------------------------------------------------------------------------------
 // K8  descriptor blur (see oracle/orb_restate.blur7 for how the op order was pinned against cv2)
 // ------------------------------------------------------------------------------------------------------------
-#define BI_W (TILE_W + 6)
-#define BI_H (TILE_H + 6)
+#define BL_ROWS (TILE_H + 6)  // input rows gy = ty0-3 .. ty0+34
+#define BL_WORDS 18           // input bytes gx = tx0-4 .. tx0+67 as 18 words per row
 
 __device__ __forceinline__ int reflect101(int p, int n) {
     if (p < 0) p = -p;
@@ -521,10 +555,16 @@ __device__ __forceinline__ int reflect101(int p, int n) {
     return p;
 }
 
+// byte k (0..3) of w as float, exactly: 0x4B0000bb is 8388608 + b
+template <int K>
+__device__ __forceinline__ float byte_to_float(uint32_t w) {
+    return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 | K)), 8388608.f);
+}
+
 __global__ void __launch_bounds__(256)
 blur_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, const __grid_constant__ OrbGeom g) {
-    __shared__ uint8_t s_in[BI_H * BI_W];
-    __shared__ float s_row[BI_H * TILE_W];
+    __shared__ uint32_t s_in[BL_ROWS * BL_WORDS];
+    __shared__ __align__(16) float s_row[BL_ROWS * TILE_W];
     const float k0 = 0x1.1f5f62p-4f, k1 = 0x1.0c70fcp-3f, k2 = 0x1.869472p-3f, k3 = 0x1.ba95c0p-3f;
 
     const int img = blockIdx.y;
@@ -538,51 +578,95 @@ blur_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ b
     int pitch;
     const uint8_t* im = level_ptr(src, pyr, g, img, l, pitch);
     const int tid = threadIdx.x;
-    for (int i = tid; i < BI_H * BI_W; i += 256) {
-        const int r = i / BI_W, c = i - r * BI_W;
-        const int gy = reflect101(min(ty0 - 3 + r, L.h + 2), L.h);
-        const int gx = reflect101(min(tx0 - 3 + c, L.w + 2), L.w);
-        s_in[i] = im[(size_t)gy * pitch + gx];
-    }
-    __syncthreads();
-    const int tail = (L.w / 32) * 32;  // cv2's AVX2 row filter: 32-wide fused body, unfused scalar tail
-    for (int i = tid; i < BI_H * TILE_W; i += 256) {
-        const int r = i / TILE_W, c = i - r * TILE_W;
-        const uint8_t* p = &s_in[r * BI_W + c];
-        const float v0 = (float)p[0], v1 = (float)p[1], v2 = (float)p[2], v3 = (float)p[3], v4 = (float)p[4],
-                    v5 = (float)p[5], v6 = (float)p[6];
-        float acc = __fmul_rn(k0, v0);
-        if (tx0 + c < tail) {
-            acc = fmaf(k1, v1, acc);
-            acc = fmaf(k2, v2, acc);
-            acc = fmaf(k3, v3, acc);
-            acc = fmaf(k2, v4, acc);
-            acc = fmaf(k1, v5, acc);
-            acc = fmaf(k0, v6, acc);
+    const int W = L.w, H = L.h;
+
+    // load: 4 pixels per work item (aligned 32-bit global loads inside the image, BORDER_REFLECT_101 bytes outside)
+    for (int i = tid; i < BL_ROWS * BL_WORDS; i += 256) {
+        const int r = i / BL_WORDS, wj = i - r * BL_WORDS;
+        const int gy = ty0 - 3 + r, gx = tx0 - 4 + 4 * wj;
+        uint32_t px = 0;
+        if (gy >= 0 && gy < H && gx >= 0 && gx + 3 < W) {
+            const uint8_t* p = im + (size_t)gy * pitch + gx;
+            const uint32_t a = (uint32_t)(uintptr_t)p & 3u;
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(p - a);
+            px = __ldg(q);
+            if (a) px = __funnelshift_r(px, __ldg(q + 1), 8 * a);
         } else {
-            acc = __fadd_rn(acc, __fmul_rn(k1, v1));
-            acc = __fadd_rn(acc, __fmul_rn(k2, v2));
-            acc = __fadd_rn(acc, __fmul_rn(k3, v3));
-            acc = __fadd_rn(acc, __fmul_rn(k2, v4));
-            acc = __fadd_rn(acc, __fmul_rn(k1, v5));
-            acc = __fadd_rn(acc, __fmul_rn(k0, v6));
+            const uint8_t* row = im + (size_t)reflect101(min(gy, H + 2), H) * pitch;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) px |= (uint32_t)row[reflect101(min(gx + b, W + 2), W)] << (8 * b);
         }
-        s_row[i] = acc;
+        s_in[i] = px;
     }
     __syncthreads();
-    uint8_t* out = blur + (size_t)img * g.img_slab + L.off;
-    for (int i = tid; i < TILE_H * TILE_W; i += 256) {
-        const int r = i / TILE_W, c = i - r * TILE_W;
-        const int gy = ty0 + r, gx = tx0 + c;
-        if (gy >= L.h || gx >= L.w) continue;
-        const float* p = &s_row[(r + 3) * TILE_W + c];
-        float acc = __fmul_rn(k3, p[0]);
-        acc = fmaf(__fadd_rn(p[TILE_W], p[-TILE_W]), k2, acc);
-        acc = fmaf(__fadd_rn(p[2 * TILE_W], p[-2 * TILE_W]), k1, acc);
-        acc = fmaf(__fadd_rn(p[3 * TILE_W], p[-3 * TILE_W]), k0, acc);
-        int v = __float2int_rn(acc);
-        v = max(0, min(255, v));
-        out[(size_t)gy * L.pitch + gx] = (uint8_t)v;
+
+    // row pass: 4 outputs per work item from 10 input bytes.  cv2's AVX2 row filter: fused 32-wide body, unfused
+    // scalar tail (x >= 32 * (W / 32)); a quad never straddles the boundary.
+    const int tail = (W / 32) * 32;
+    for (int i = tid; i < BL_ROWS * (TILE_W / 4); i += 256) {
+        const int r = i >> 4, qi = i & 15;
+        const uint32_t* w = &s_in[r * BL_WORDS + qi];
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+        float f[10];
+        f[0] = byte_to_float<1>(w0); f[1] = byte_to_float<2>(w0); f[2] = byte_to_float<3>(w0);
+        f[3] = byte_to_float<0>(w1); f[4] = byte_to_float<1>(w1); f[5] = byte_to_float<2>(w1); f[6] = byte_to_float<3>(w1);
+        f[7] = byte_to_float<0>(w2); f[8] = byte_to_float<1>(w2); f[9] = byte_to_float<2>(w2);
+        float o[4];
+        if (tx0 + 4 * qi < tail) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float acc = __fmul_rn(k0, f[k]);
+                acc = fmaf(k1, f[k + 1], acc);
+                acc = fmaf(k2, f[k + 2], acc);
+                acc = fmaf(k3, f[k + 3], acc);
+                acc = fmaf(k2, f[k + 4], acc);
+                acc = fmaf(k1, f[k + 5], acc);
+                o[k] = fmaf(k0, f[k + 6], acc);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float acc = __fmul_rn(k0, f[k]);
+                acc = __fadd_rn(acc, __fmul_rn(k1, f[k + 1]));
+                acc = __fadd_rn(acc, __fmul_rn(k2, f[k + 2]));
+                acc = __fadd_rn(acc, __fmul_rn(k3, f[k + 3]));
+                acc = __fadd_rn(acc, __fmul_rn(k2, f[k + 4]));
+                acc = __fadd_rn(acc, __fmul_rn(k1, f[k + 5]));
+                o[k] = __fadd_rn(acc, __fmul_rn(k0, f[k + 6]));
+            }
+        }
+        *reinterpret_cast<float4*>(&s_row[r * TILE_W + 4 * qi]) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();
+
+    // column pass: 4 x 2 outputs per thread (symmetric pairing, fused), rounded once, packed 32-bit stores
+    {
+        const int qi = tid & 15, r0 = (tid >> 4) * 2;
+        const int gx = tx0 + 4 * qi;
+        if (gx >= W) return;
+        float4 p[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) p[k] = *reinterpret_cast<const float4*>(&s_row[(r0 + k) * TILE_W + 4 * qi]);
+        uint8_t* out = blur + (size_t)img * g.img_slab + L.off;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int gy = ty0 + r0 + a;
+            if (gy >= H) break;
+            uint32_t packed = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float* pc = reinterpret_cast<const float*>(&p[0]) + c;  // element c of each float4 (stride 4)
+                float acc = __fmul_rn(k3, pc[4 * (a + 3)]);
+                acc = fmaf(__fadd_rn(pc[4 * (a + 4)], pc[4 * (a + 2)]), k2, acc);
+                acc = fmaf(__fadd_rn(pc[4 * (a + 5)], pc[4 * (a + 1)]), k1, acc);
+                acc = fmaf(__fadd_rn(pc[4 * (a + 6)], pc[4 * a]), k0, acc);
+                int v = __float2int_rn(acc);
+                v = max(0, min(255, v));
+                packed |= (uint32_t)v << (8 * c);
+            }
+            // gx is a multiple of 4 below W and the plane pitch is a multiple of 16: the word stays inside the row
+            *reinterpret_cast<uint32_t*>(&out[(size_t)gy * L.pitch + gx]) = packed;
+        }
     }
 }
 
@@ -885,10 +969,10 @@ static int orb_set_geometry(vslam_ctx* ctx, int w, int h) {
         L.cand_off = cand;
         L.cand_cap = (L.w * L.h) / 12 + 64;
         cand += L.cand_cap;
-        L.xtab_off = tab;
-        tab += L.w;
+        L.xtab_off = tab;  // 16-byte aligned regions, zero-padded to a multiple of 4 entries (uint4 loads)
+        tab += (L.w + 3) & ~3;
         L.ytab_off = tab;
-        tab += L.h;
+        tab += (L.h + 3) & ~3;
     }
     g.total_tiles = tiles;
     g.img_slab = off;
@@ -989,7 +1073,7 @@ int vslam_orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h
     cudaStream_t s = ctx->stream;
     VSLAM_CUDA(ctx, cudaMemsetAsync(o->d_cnt, 0, (size_t)n_img * sizeof(ImgCounters), s));
     for (int l = 1; l < ORB_NL; ++l) {
-        dim3 grid(ceil_div(g.lv[l].w, 32), ceil_div(g.lv[l].h, 8), n_img);
+        dim3 grid(ceil_div(ceil_div(g.lv[l].w, 4), 32), ceil_div(g.lv[l].h, 8), n_img);
         vslam_time_begin(ctx, VK_RESIZE);
         resize_level_kernel<<<grid, dim3(32, 8), 0, s>>>(src, o->d_pyr, o->d_tab, g, l);
         vslam_time_end(ctx);
