@@ -32,12 +32,21 @@ struct MatchState {
     int32_t* h_cnt;       // pinned
 };
 
+// 256-bit Hamming distance.  POPC issues on the quarter-rate XU pipe, which bounds this kernel; three carry-save
+// adders (2 LOP3 each, full-rate ALU pipe) compress 7 of the 8 XOR words into one "ones" and three "twos" words, so a
+// distance costs 5 POPC instead of 8 and the two pipes are balanced:
+//   d = popc(s3) + popc(x7) + 2 * (popc(c1) + popc(c2) + popc(c3))
+__device__ __forceinline__ uint32_t csa_sum(uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; }
+__device__ __forceinline__ uint32_t csa_carry(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
+
 __device__ __forceinline__ uint32_t hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
-    uint32_t d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z);
-    d += __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x);
-    d += __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z);
-    d += __popc(a1.w ^ b1.w);
-    return d;
+    const uint32_t x0 = a0.x ^ b0.x, x1 = a0.y ^ b0.y, x2 = a0.z ^ b0.z, x3 = a0.w ^ b0.w;
+    const uint32_t x4 = a1.x ^ b1.x, x5 = a1.y ^ b1.y, x6 = a1.z ^ b1.z, x7 = a1.w ^ b1.w;
+    const uint32_t s1 = csa_sum(x0, x1, x2), c1 = csa_carry(x0, x1, x2);
+    const uint32_t s2 = csa_sum(x3, x4, x5), c2 = csa_carry(x3, x4, x5);
+    const uint32_t s3 = csa_sum(s1, s2, x6), c3 = csa_carry(s1, s2, x6);
+    const uint32_t twos = __popc(c1) + __popc(c2) + __popc(c3);
+    return __popc(s3) + __popc(x7) + 2 * twos;
 }
 
 __global__ void __launch_bounds__(MT_THREADS)

@@ -31,7 +31,8 @@
 #define FAST_THREADS 256
 #define SORT_CAP 8192
 #define HS_THREADS 1024
-#define DESC_WARPS 8
+#define DESC_WARPS 4
+#define DESC_KPW 8  // keypoints per warp (power of two <= 32)
 
 struct OrbLevel {
     int w, h, pitch;
@@ -75,7 +76,7 @@ struct OrbState {
     uint32_t* d_sticky;   // OR of every overflow flag raised since the last check (survives chunked batches)
     uint32_t* d_keep;     // ANMS keep list [img][kp_cap]
     double* d_rad;        // ANMS radii [img][kp_cap]
-    int8_t* d_pattern;    // 256 x 4
+    float* d_pattern;     // 256 x 4 (x0, y0, x1, y1) as float
     // staging for the host-buffer entry point
     uint8_t* d_in;
     int in_pitch;
@@ -814,20 +815,23 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
+// One warp describes DESC_KPW keypoints: the intensity-centroid sums and the 256 tests of each keypoint are spread
+// over the 32 lanes, while the per-keypoint scalar work (fastAtan2, the double-precision cos/sin OpenCV uses, the
+// keypoint record) is done once with lane i owning keypoint i instead of 32 times redundantly.
 __global__ void __launch_bounds__(DESC_WARPS * 32)
 describe_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, const __grid_constant__ OrbGeom g,
                 const uint2* __restrict__ sel, ImgCounters* __restrict__ cnt, const uint32_t* __restrict__ keep,
-                int use_keep, const int8_t* __restrict__ pattern, int kp_cap, vslam_keypoint* __restrict__ kp_out,
+                int use_keep, const float* __restrict__ pattern, int kp_cap, vslam_keypoint* __restrict__ kp_out,
                 uint8_t* __restrict__ desc_out, int32_t* __restrict__ n_out, uint32_t* __restrict__ sticky) {
     const int img = blockIdx.y;
     const int lane = threadIdx.x & 31;
-    const int k = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
+    const int k0 = (blockIdx.x * DESC_WARPS + (threadIdx.x >> 5)) * DESC_KPW;
     ImgCounters* C = &cnt[img];
     int total = 0;
 #pragma unroll
     for (int i = 0; i < ORB_NL; ++i) total += (int)C->sel_cnt[i];
     if (total > kp_cap) {
-        if (k == 0 && lane == 0) {
+        if (k0 == 0 && lane == 0) {
             atomicOr(&C->flags, 4u);
             atomicOr(sticky, 4u);
         }
@@ -835,74 +839,94 @@ describe_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const uint8_t* __re
     }
     const int oslot = img < src.per_base ? src.out_slot[0] + img : src.out_slot[1] + (img - src.per_base);
     const int n = use_keep ? (int)C->n_keep : total;
-    if (k == 0 && lane == 0) n_out[oslot] = n;
-    if (k >= n) return;
-    const int gi = use_keep ? (int)keep[(size_t)img * kp_cap + k] : k;
+    if (k0 == 0 && lane == 0) n_out[oslot] = n;
+    if (k0 >= n) return;
+    const int nk = min(DESC_KPW, n - k0);  // keypoints of this warp
+
+    // lane i (mod DESC_KPW) owns keypoint k0 + i
+    const int slot = lane & (DESC_KPW - 1);
+    const int my_k = min(k0 + slot, n - 1);
+    const int gi = use_keep ? (int)keep[(size_t)img * kp_cap + my_k] : my_k;
     int j;
-    const int l = locate_level(C->sel_cnt, gi, j);
-    const uint2 e = sel[((size_t)img * ORB_NL + l) * SORT_CAP + j];
-    const int x = e.x & 0xFFFF, y = e.x >> 16;
-    const OrbLevel& L = g.lv[l];
+    const int my_l = locate_level(C->sel_cnt, gi, j);
+    const uint2 my_e = sel[((size_t)img * ORB_NL + my_l) * SORT_CAP + j];
+    const int my_x = my_e.x & 0xFFFF, my_y = my_e.x >> 16;
 
     // intensity centroid over the radius-15 disc (orb.cpp ICAngles); lanes run along u, rows along v
-    int pitch;
-    const uint8_t* im = level_ptr(src, pyr, g, img, l, pitch);
     const int u = lane - 15;
-    int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int au = abs(u);
-        const uint8_t* c = im + (size_t)y * pitch + x + u;
+    const int au = abs(u);
+    int my_m10 = 0, my_m01 = 0;
+    for (int i = 0; i < nk; ++i) {
+        const int x = __shfl_sync(0xFFFFFFFFu, my_x, i), y = __shfl_sync(0xFFFFFFFFu, my_y, i);
+        const int l = __shfl_sync(0xFFFFFFFFu, my_l, i);
+        int pitch;
+        const uint8_t* im = level_ptr(src, pyr, g, img, l, pitch);
+        int m10 = 0, m01 = 0;
+        if (lane < 31) {
+            const uint8_t* c = im + (size_t)y * pitch + x + u;
 #pragma unroll
-        for (int v = -15; v <= 15; ++v) {
-            if (au <= c_umax[v < 0 ? -v : v]) {
-                const int val = c[(long long)v * pitch];
-                m10 += u * val;
-                m01 += v * val;
+            for (int v = -15; v <= 15; ++v) {
+                if (au <= c_umax[v < 0 ? -v : v]) {
+                    const int val = c[v * pitch];
+                    m10 += u * val;
+                    m01 += v * val;
+                }
             }
         }
-    }
-    m10 = __reduce_add_sync(0xFFFFFFFFu, m10);
-    m01 = __reduce_add_sync(0xFFFFFFFFu, m01);
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-
-    const float ptx = __fmul_rn((float)x, L.scale), pty = __fmul_rn((float)y, L.scale);
-    vslam_keypoint* ko = kp_out + (size_t)oslot * kp_cap + k;
-    if (lane < 7) {
-        uint32_t w;
-        switch (lane) {
-            case 0: w = __float_as_uint(ptx); break;
-            case 1: w = __float_as_uint(pty); break;
-            case 2: w = __float_as_uint(__fmul_rn(31.f, L.scale)); break;
-            case 3: w = __float_as_uint(angle); break;
-            case 4: w = e.y; break;
-            case 5: w = (uint32_t)l; break;
-            default: w = 0xFFFFFFFFu; break;  // class_id = -1
+        m10 = __reduce_add_sync(0xFFFFFFFFu, m10);
+        m01 = __reduce_add_sync(0xFFFFFFFFu, m01);
+        if (slot == i) {
+            my_m10 = m10;
+            my_m01 = m01;
         }
-        reinterpret_cast<uint32_t*>(ko)[lane] = w;
     }
+    const OrbLevel& ML = g.lv[my_l];
+    const float angle = fast_atan2_deg((float)my_m01, (float)my_m10);
+    const float ptx = __fmul_rn((float)my_x, ML.scale), pty = __fmul_rn((float)my_y, ML.scale);
+    if (lane < nk) {
+        vslam_keypoint kp;
+        kp.x = ptx;
+        kp.y = pty;
+        kp.size = __fmul_rn(31.f, ML.scale);
+        kp.angle = angle;
+        kp.response = __uint_as_float(my_e.y);
+        kp.octave = my_l;
+        kp.class_id = -1;
+        kp_out[(size_t)oslot * kp_cap + k0 + lane] = kp;
+    }
+    const int my_cx = __float2int_rn(__fmul_rn(ptx, ML.inv_scale));
+    const int my_cy = __float2int_rn(__fmul_rn(pty, ML.inv_scale));
+    const float th = __fmul_rn(angle, 0x1.1df46ap-6f);  // (float)(CV_PI/180)
+    const float my_a = (float)cos((double)th), my_b = (float)sin((double)th);
 
     // rotated BRIEF on the blurred level (orb.cpp computeOrbDescriptors, WTA_K = 2); lane = output byte
-    const uint8_t* bl = blur + (size_t)img * g.img_slab + L.off;
-    const int cx = __float2int_rn(__fmul_rn(ptx, L.inv_scale));
-    const int cy = __float2int_rn(__fmul_rn(pty, L.inv_scale));
-    const float th = __fmul_rn(angle, 0x1.1df46ap-6f);  // (float)(CV_PI/180)
-    const float a = (float)cos((double)th), b = (float)sin((double)th);
-    const uint8_t* center = bl + (size_t)cy * L.pitch + cx;
-    const char4* pat = reinterpret_cast<const char4*>(pattern) + lane * 8;
-    uint32_t byte = 0;
+    const float4* pat = reinterpret_cast<const float4*>(pattern) + lane * 8;
+    float4 pt[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const char4 p0 = __ldg(&pat[t]);  // (x0, y0, x1, y1) of test 8*lane + t
-        const float x0 = (float)p0.x, y0 = (float)p0.y, x1 = (float)p0.z, y1 = (float)p0.w;
-        const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int t0 = center[(long long)iy0 * L.pitch + ix0];
-        const int t1 = center[(long long)iy1 * L.pitch + ix1];
-        byte |= (uint32_t)(t0 < t1) << t;
+    for (int t = 0; t < 8; ++t) pt[t] = __ldg(&pat[t]);  // (x0, y0, x1, y1) of test 8*lane + t
+    for (int i = 0; i < nk; ++i) {
+        const float a = __shfl_sync(0xFFFFFFFFu, my_a, i), b = __shfl_sync(0xFFFFFFFFu, my_b, i);
+        const int cx = __shfl_sync(0xFFFFFFFFu, my_cx, i), cy = __shfl_sync(0xFFFFFFFFu, my_cy, i);
+        const int l = __shfl_sync(0xFFFFFFFFu, my_l, i);
+        const int bp = g.lv[l].pitch;
+        const uint8_t* center = blur + (size_t)img * g.img_slab + g.lv[l].off + (size_t)cy * bp + cx;
+        uint32_t byte = 0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const float4 p0 = pt[t];
+            // cvRound: adding 1.5 * 2^23 rounds to the nearest integer, ties to even, exactly like F2I.RN (|v| < 2^22)
+            const float rx0 = __fadd_rn(__fsub_rn(__fmul_rn(p0.x, a), __fmul_rn(p0.y, b)), 12582912.f);
+            const float ry0 = __fadd_rn(__fadd_rn(__fmul_rn(p0.x, b), __fmul_rn(p0.y, a)), 12582912.f);
+            const float rx1 = __fadd_rn(__fsub_rn(__fmul_rn(p0.z, a), __fmul_rn(p0.w, b)), 12582912.f);
+            const float ry1 = __fadd_rn(__fadd_rn(__fmul_rn(p0.z, b), __fmul_rn(p0.w, a)), 12582912.f);
+            const int ix0 = __float_as_int(rx0) - 0x4B400000, iy0 = __float_as_int(ry0) - 0x4B400000;
+            const int ix1 = __float_as_int(rx1) - 0x4B400000, iy1 = __float_as_int(ry1) - 0x4B400000;
+            const int t0 = center[iy0 * bp + ix0];
+            const int t1 = center[iy1 * bp + ix1];
+            byte |= (uint32_t)(t0 < t1) << t;
+        }
+        desc_out[((size_t)oslot * kp_cap + k0 + i) * 32 + lane] = (uint8_t)byte;
     }
-    desc_out[((size_t)oslot * kp_cap + k) * 32 + lane] = (uint8_t)byte;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1015,8 +1039,12 @@ int vslam_orb_init(vslam_ctx* ctx) {
     VSLAM_CUDA(ctx, cudaMemset(o->d_sticky, 0, sizeof(uint32_t)));
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_keep, ni * o->kp_cap * sizeof(uint32_t)));
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_rad, ni * o->kp_cap * sizeof(double)));
-    VSLAM_CUDA(ctx, cudaMalloc(&o->d_pattern, 1024));
-    VSLAM_CUDA(ctx, cudaMemcpy(o->d_pattern, h_orb_pattern, 1024, cudaMemcpyHostToDevice));
+    VSLAM_CUDA(ctx, cudaMalloc(&o->d_pattern, 1024 * sizeof(float)));
+    {
+        float hp[1024];
+        for (int i = 0; i < 1024; ++i) hp[i] = (float)h_orb_pattern[i];
+        VSLAM_CUDA(ctx, cudaMemcpy(o->d_pattern, hp, sizeof(hp), cudaMemcpyHostToDevice));
+    }
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_in, ni * (size_t)o->in_pitch * c.max_height));
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_kp, ni * o->kp_cap * sizeof(vslam_keypoint)));
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_desc, ni * o->kp_cap * 32));
@@ -1104,7 +1132,7 @@ int vslam_orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h
         VSLAM_LAUNCH_CHECK(ctx, "anms_kernel");
     }
     vslam_time_begin(ctx, VK_DESCRIBE);
-    describe_kernel<<<dim3(ceil_div(o->kp_cap, DESC_WARPS), n_img), DESC_WARPS * 32, 0, s>>>(
+    describe_kernel<<<dim3(ceil_div(o->kp_cap, DESC_WARPS * DESC_KPW), n_img), DESC_WARPS * 32, 0, s>>>(
         src, o->d_pyr, o->d_blur, g, o->d_sel, o->d_cnt, o->d_keep, use_keep, o->d_pattern, o->kp_cap, d_kp, d_desc,
         d_n, o->d_sticky);
     vslam_time_end(ctx);
