@@ -11,4 +11,8 @@ if [ "$1" == "ncu" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --pairs 32 --cpu-seconds 1 > gpurun_out/ncu_bench.log 2>&1
   echo "ncu rc=$?"; tail -3 gpurun_out/launches.csv
 fi
+if [ "$2" == "full" ]; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:fast_kernel|blur_kernel|describe_kernel|hamming_argmin|harris_select|resize_level|triangulate|crosscheck" -s 15 -c 15 -f -o gpurun_out/full python tools/profile_frontend.py 32 2 > gpurun_out/ncu_full.log 2>&1
+  echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log; ls -la gpurun_out/*.ncu-rep
+fi
 exit 0
