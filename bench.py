@@ -173,6 +173,17 @@ def algorithmic_bytes(n_images: int, n_pairs: int, n_kp: float, n_match: float):
     }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the ncu --set full capture under profiles/
+# (r01_v6_ncu_full_frontend_summary.json: 64 images / 32 pairs per launch), divided by the units of that launch.
+NCU_TRAFFIC_PER_UNIT = {
+    "fast_kernel": (93.321472e6 + 9.894656e6) / 64, "blur_kernel": (94.415360e6 + 57.704192e6) / 64,
+    "describe_kernel": (151.679744e6 + 8.143104e6) / 64, "harris_select_kernel": (85.250816e6 + 2.286080e6) / 64,
+    "hamming_argmin_kernel": 4.623616e6 / 32, "crosscheck_gate_compact_kernel": 0.529152e6 / 32,
+    "triangulate_kernel": 2.209536e6 / 32,
+}
+NCU_TRAFFIC_SOURCE = "profiles/r01_v6_ncu_full_frontend_summary.json"
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import vslam_b200_loader
@@ -291,7 +302,11 @@ def run_ours(args, rank, world, local_rank):
     avg_ms = ktimes[top][0] / ktimes[top][1]
     achieved = alg.get(top, 0.0) / (avg_ms * 1e-3) / 1e9
     roof = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg_ms,
+            "traffic": (NCU_TRAFFIC_PER_UNIT[top] * (B if top in ("hamming_argmin_kernel", "triangulate_kernel",
+                                                                  "crosscheck_gate_compact_kernel") else 2 * B)
+                        if top in NCU_TRAFFIC_PER_UNIT else None),
+            "traffic_source": NCU_TRAFFIC_SOURCE + " (per-unit DRAM bytes of the capture x units per launch here)",
+            "peak_source": peak_src, "avg_launch_ms": avg_ms,
             "algorithmic_bytes_per_launch": alg.get(top, 0.0),
             "kernel_time_share": {k: round(v / tot_k, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
             "note": "per-kernel CUDA-event times measured live over the timed region; see DESIGN.md §4 for the bytes"}

@@ -34,6 +34,11 @@ def cv_orb(img, n):
                 desc=desc[order])
 
 
+def sgbm_crop(s, seed, h, w, y0=100, x0=300):
+    left, right, _ = s.synth_pair(seed)
+    return np.ascontiguousarray(left[y0:y0 + h, x0:x0 + w]), np.ascontiguousarray(right[y0:y0 + h, x0:x0 + w])
+
+
 def main():
     s = pkg.synth
     left, right, _ = s.synth_pair(0)
@@ -63,6 +68,10 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ba_seed11_K5_L120_it10.npz"), poses=r["poses"], points=r["points"],
                         chi2=np.array([r["chi2_initial"], r["chi2_final"]]), trials=r["trials"],
                         lambda_final=r["lambda_final"], point_inlier=r["point_inlier"], trace=r["trace"])
+    # dense stereo: cv2.StereoSGBM with the reference's constants (visual_odometry.cpp:163-164) on crops of pair 0
+    sg = cv2.StereoSGBM_create(0, 96, 9, 8 * 81, 32 * 81, 1, 63, 10, 100, 32)
+    crop = sgbm_crop(s, 0, 64, 360)
+    np.savez_compressed(os.path.join(HERE, "sgbm_pair0_crop64x360.npz"), disp16=sg.compute(*crop))
     print("golden vectors written to", HERE)
 
 
