@@ -258,6 +258,37 @@ int vslam_anms(vslam_ctx* ctx, const vslam_keypoint* keypoints, int n, int num, 
                int32_t* keep_idx, int32_t* n_keep);
 
 /* ------------------------------------------------------------------------------------------------
+ * K18-K23  dense semi-global stereo matching: the reference's own depth source.
+ * Replaces cv::StereoSGBM::create(0, 96, 9, 8*9*9, 32*9*9, 1, 63, 10, 100, 32)->compute(left, right, disp)
+ * and the convertTo(CV_32F, 1/16) that follows it in VO::disparity_map (visual_odometry.cpp:159-174).
+ * Bit-exact against cv2 4.13.0 StereoSGBM (MODE_SGBM): Birchfield-Tomasi cost on the x-Sobel and raw planes,
+ * 9x9 block sum, five aggregation paths, uniqueness / LR check / sub-pixel fit, medianBlur(3), filterSpeckles.
+ *   params   NULL = the reference's constants (vslam_sgbm_default_params).  The kernels are specialised for
+ *            min_disparity 0, num_disparities 96, block_size 9 (anything else: VSLAM_E_INVALID); P1, P2,
+ *            disp12_max_diff, pre_filter_cap, uniqueness_ratio, speckle_* are free.
+ *   disp16   n_pairs x height x width int16, disparity * 16, -16 = invalid (CV_16S as cv::StereoSGBM writes it)
+ *   disp_f32 n_pairs x height x width float, disparity in pixels, -1 = invalid (the reference's Frame::disparity_)
+ *            either output may be NULL.
+ * width - 96 must exceed 4 (OpenCV raises for narrower images); returns VSLAM_E_INVALID otherwise.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vslam_sgbm_params {
+    int32_t min_disparity, num_disparities, block_size, P1, P2, disp12_max_diff, pre_filter_cap, uniqueness_ratio,
+        speckle_window_size, speckle_range;
+} vslam_sgbm_params;
+void vslam_sgbm_default_params(vslam_sgbm_params* p);
+int vslam_sgbm_compute(vslam_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_pairs, int width, int height,
+                       int row_pitch, long long image_stride, const vslam_sgbm_params* params, int16_t* disp16,
+                       float* disp_f32);
+/* device-resident form: asynchronous on the context stream */
+int vslam_sgbm_compute_dev(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_right, int n_pairs, int width,
+                           int height, int row_pitch, long long image_stride, const vslam_sgbm_params* params,
+                           int16_t* d_disp16, float* d_disp_f32);
+/* test taps: stage 0 = cost volume C [h][w-96][96] u16, 1..3 = path volumes (1 holds S4 after a full run),
+ * 4 = disparity before the median, 5 = after the median; stop_after 1 = stop after the vertical sweep */
+int vslam_sgbm_debug_read(vslam_ctx* ctx, int pair, int stage, void* host_out, size_t bytes);
+int vslam_sgbm_debug_stop_after(vslam_ctx* ctx, int stage);
+
+/* ------------------------------------------------------------------------------------------------
  * K17  landmark-sharded BA session for one-process-per-GPU runs (no reference equivalent: the reference
  * is single-process).  Rank r owns the landmarks [shard_begin, shard_end) with all their observations,
  * poses are replicated.  The CALLER owns the LM control flow (same schedule as vslam_ba_optimize) and

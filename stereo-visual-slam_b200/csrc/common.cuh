@@ -16,11 +16,13 @@ struct MatchState; // match.cu
 struct BaState;    // ba.cu
 struct FrontState; // frontend.cu
 struct PnpState;   // pnp.cu
+struct SgbmState;  // sgbm.cu
 
 // kernel ids for the optional per-launch CUDA-event timing (vslam_ctx_timing_*)
 enum {
     VK_RESIZE = 0, VK_FAST, VK_HARRIS_SELECT, VK_BLUR, VK_ANMS, VK_DESCRIBE, VK_HAMMING_ARGMIN, VK_CROSSCHECK,
-    VK_TRIANGULATE, VK_BA_BUILD, VK_BA_SOLVE, VK_BA_UPDATE, VK_BA_MISC, VK_PNP, VK_COUNT
+    VK_TRIANGULATE, VK_BA_BUILD, VK_BA_SOLVE, VK_BA_UPDATE, VK_BA_MISC, VK_PNP, VK_SGBM_PREFILTER, VK_SGBM_COST,
+    VK_SGBM_VERTICAL, VK_SGBM_HORIZONTAL, VK_SGBM_POST, VK_COUNT
 };
 #define VSLAM_TIMING_CAP 16384
 struct TimingRec {
@@ -45,6 +47,7 @@ struct vslam_ctx {
     BaState* ba;
     FrontState* front;
     PnpState* pnp;
+    SgbmState* sgbm;
 };
 
 static inline int vslam_set_cuda_error(vslam_ctx* ctx, cudaError_t e, const char* where) {
@@ -110,3 +113,5 @@ int vslam_front_init(vslam_ctx* ctx);
 void vslam_front_free(vslam_ctx* ctx);
 int vslam_pnp_init(vslam_ctx* ctx);
 void vslam_pnp_free(vslam_ctx* ctx);
+int vslam_sgbm_init(vslam_ctx* ctx);
+void vslam_sgbm_free(vslam_ctx* ctx);

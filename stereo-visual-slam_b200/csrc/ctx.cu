@@ -52,6 +52,7 @@ extern "C" int vslam_ctx_create(const vslam_config* cfg, vslam_ctx** out) {
     if (st == VSLAM_OK) st = vslam_ba_init(ctx);
     if (st == VSLAM_OK) st = vslam_front_init(ctx);
     if (st == VSLAM_OK) st = vslam_pnp_init(ctx);
+    if (st == VSLAM_OK) st = vslam_sgbm_init(ctx);
     if (st != VSLAM_OK) {
         vslam_ctx_destroy(ctx);
         return st;
@@ -64,6 +65,7 @@ extern "C" void vslam_ctx_destroy(vslam_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
+    vslam_sgbm_free(ctx);
     vslam_pnp_free(ctx);
     vslam_front_free(ctx);
     vslam_ba_free(ctx);
@@ -98,7 +100,8 @@ extern "C" int64_t vslam_ctx_launch_count(const vslam_ctx* ctx) { return ctx ? c
 static const char* const k_kernel_names[VK_COUNT] = {
     "resize_level_kernel", "fast_kernel", "harris_select_kernel", "blur_kernel", "anms_kernel", "describe_kernel",
     "hamming_argmin_kernel", "crosscheck_gate_compact_kernel", "triangulate_kernel", "ba_lm_kernel",
-    "ba_solve_kernel", "ba_update_kernel", "ba_misc_kernel", "pnp_kernel"};
+    "ba_solve_kernel", "ba_update_kernel", "ba_misc_kernel", "pnp_kernel", "sgbm_prefilter_kernel", "sgbm_cost_kernel",
+    "sgbm_vertical_kernel", "sgbm_horizontal_kernel", "sgbm_post_kernels"};
 
 extern "C" int vslam_kernel_count(void) { return VK_COUNT; }
 extern "C" const char* vslam_kernel_name(int id) { return id >= 0 && id < VK_COUNT ? k_kernel_names[id] : ""; }

@@ -1,0 +1,757 @@
+// K18-K23  dense semi-global stereo matching, the reference's actual depth source.
+//
+// Replaces cv::StereoSGBM::create(0, 96, 9, 8*9*9, 32*9*9, 1, 63, 10, 100, 32)->compute(left, right, disparity_sgbm)
+// in VO::disparity_map (/root/reference/src/stereo_visual_slam_main/visual_odometry.cpp:159-174).  The arithmetic
+// lives in OpenCV (calib3d/src/stereosgbm.cpp, un-vendored); oracle/sgbm_restate.py restates it and is pinned
+// bit-exact against live cv2 4.13.0.  Output is bit-exact CV_16S disparity*16 with (minD-1)*16 = -16 as "invalid".
+//
+// OpenCV walks the image row by row on one core, carrying five path costs per pixel.  The five paths are independent
+// of each other, so here every path direction is its own sweep over a materialised cost volume:
+//   K18 sgbm_prefilter_kernel   x-Sobel + clip table, raw row, half-pixel min/max (Birchfield-Tomasi operands)
+//   K19 sgbm_cost_kernel        BT pixel cost on both planes + 9x9 box sum (replicated borders) -> C[y][x][d] u16
+//   K20 sgbm_vertical_kernel    paths from the row above (up-left, up, up-right): one warp per path, diagonal paths
+//                               wrap around the image so every warp walks all H rows with no inter-warp traffic
+//   K21 sgbm_horizontal_kernel  one warp per row: left->right path, then right->left path fused with the winner-
+//                               take-all, uniqueness test, sub-pixel fit, right-image map and LR consistency check
+//   K22 sgbm_median_kernel      cv::medianBlur(3)
+//   K23 speckle_*_kernel        cv::filterSpeckles as union-find connected components
+// 96 disparities are held as 48 packed s16x2 words; a path step is VIADD.16x2 / VIMNMX.S16x2 on 2 words per lane
+// (24 lanes) plus one CREDUX.MIN for min_k L_r(p-r, k).  All volumes are HBM-resident u16: these kernels are
+// bandwidth-bound.
+#include "common.cuh"
+
+#include <stdlib.h>
+
+#define SG_D 96
+#define SG_NDP 48                    // packed disparity pairs
+#define SG_R 4                       // block radius (blockSize 9)
+#define SG_TX 16                     // columns per cost-kernel strip
+#define SG_NC (SG_TX + 2 * SG_R)     // pixel-cost columns a strip needs
+#define SG_NRH 61                    // packed right-row words per parity
+#define SG_BANDS 8                   // row bands of the cost kernel (each re-computes 2*SG_R halo rows)
+#define SG_BIG2 0x75307530u          // 30000 | 30000 << 16: "no predecessor" cost, > any reachable min + P2
+#define SG_MAXCOST 32767
+#define SG_INVALID (-16)
+#define SG_HW 4                      // rows (warps) per CTA of the horizontal kernel
+#define SG_PF 8                      // rows the vertical sweep loads ahead
+#define SG_CHUNK_PAIRS 8             // pairs per scratch chunk (8 x 331 MB)
+
+struct SgParams {
+    int P1, P2, disp12, uniq, ftzero, speckle_window, speckle_diff;
+};
+
+struct SgbmState {
+    uint2* d_pre;       // [2*chunk][H][W] {sobel pack, raw pack}: v | min << 8 | max << 16
+    uint32_t* d_C;      // [chunk][H][W1][48] packed u16 pairs
+    uint32_t* d_L[3];   // path costs from the row above; d_L[0] is overwritten with S4 = sat(L0+L1+L2+L3)
+    int16_t* d_raw;     // [chunk][H][W]
+    int16_t* d_med;
+    int32_t* d_label;
+    int32_t* d_size;
+    uint8_t* d_img;     // host-entry staging: [2*chunk][H][pitch]
+    int16_t* d_out;
+    float* d_outf;
+    int cap_pairs, cap_w, cap_h, pitch;
+    int stop_after;     // test tap: 1 = stop after the vertical sweep (keeps L1 intact)
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// K18: per pixel the Birchfield-Tomasi operands of both planes
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sgbm_prefilter_kernel(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right,
+                                                             long long img_stride, int pitch, int n_pairs, int W, int H,
+                                                             int ftzero, uint2* __restrict__ pre) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
+    if (x >= W) return;
+    const uint8_t* base = img < n_pairs ? left + (long long)img * img_stride : right + (long long)(img - n_pairs) * img_stride;
+    const uint8_t* r = base + (long long)y * pitch;
+    const uint8_t* up = base + (long long)max(y - 1, 0) * pitch;
+    const uint8_t* dn = base + (long long)min(y + 1, H - 1) * pitch;
+    int s[3], v[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int xx = min(max(x - 1 + k, 0), W - 1);
+        if (xx <= 0 || xx >= W - 1) {
+            s[k] = ftzero;  // tab[0]: zero gradient, on both planes (stereosgbm.cpp calcPixelCostBT border init)
+            v[k] = ftzero;
+        } else {
+            const int g = ((int)r[xx + 1] - (int)r[xx - 1]) * 2 + (int)up[xx + 1] - (int)up[xx - 1] + (int)dn[xx + 1] - (int)dn[xx - 1];
+            s[k] = min(max(g, -ftzero), ftzero) + ftzero;
+            v[k] = r[xx];
+        }
+    }
+    const int sl = (s[1] + s[0]) >> 1, sr = (s[1] + s[2]) >> 1, vl = (v[1] + v[0]) >> 1, vr = (v[1] + v[2]) >> 1;
+    uint2 o;
+    o.x = (uint32_t)s[1] | (uint32_t)min(min(sl, sr), s[1]) << 8 | (uint32_t)max(max(sl, sr), s[1]) << 16;
+    o.y = (uint32_t)v[1] | (uint32_t)min(min(vl, vr), v[1]) << 8 | (uint32_t)max(max(vl, vr), v[1]) << 16;
+    pre[((size_t)img * H + y) * W + x] = o;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K19: pixel cost + box sum.  CTA = SG_TX columns x one row band, thread = (column, disparity pair), marching down.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bcast16(int v) { return (uint32_t)(v & 0xffff) * 0x00010001u; }
+__device__ __forceinline__ uint32_t neg2(uint32_t a) { return __vadd2(~a, 0x00010001u); }
+
+// min(c0, c1) of Birchfield-Tomasi on packed pairs; nX = -X
+__device__ __forceinline__ uint32_t bt_cost2(uint32_t u, uint32_t u0, uint32_t nu, uint32_t nu1, uint32_t v, uint32_t v0,
+                                             uint32_t nv, uint32_t nv1) {
+    const uint32_t c0 = __vimax3_s16x2(__vadd2(u, nv1), __vadd2(v0, nu), 0u);
+    const uint32_t c1 = __vimax3_s16x2(__vadd2(v, nu1), __vadd2(u0, nv), 0u);
+    return __vmins2(c0, c1);
+}
+
+__global__ void __launch_bounds__(SG_TX* SG_NDP) sgbm_cost_kernel(const uint2* __restrict__ pre, int n_pairs, int W, int H, int W1,
+                                                                 int band_rows, uint32_t* __restrict__ Cvol) {
+    __shared__ uint32_t sL[SG_NC][8];          // u, u0, -u, -u1 (sobel) ; u, u0, -u, -u1 (raw), broadcast pairs
+    __shared__ uint32_t sR[2][8][SG_NRH];      // [parity][v, v0, -v, -v1 (sobel), same (raw)][k]: (val[j], val[j-1])
+    __shared__ uint32_t sPd[SG_NC][SG_NDP];    // pixel cost of the current row
+    __shared__ uint32_t sRing[2 * SG_R + 1][SG_TX * SG_NDP];
+    const int t = threadIdx.x, dp = t % SG_NDP, xl = t / SG_NDP;
+    const int x1s = blockIdx.x * SG_TX, pair = blockIdx.z;
+    const int y0 = blockIdx.y * band_rows, y1 = min(y0 + band_rows, H);
+    if (y0 >= H) return;
+    const uint2* preL = pre + (size_t)pair * H * W;
+    const uint2* preR = pre + (size_t)(n_pairs + pair) * H * W;
+    const int jb = x1s - SG_R;  // image column of right-row slot 0
+#pragma unroll
+    for (int s = 0; s < 2 * SG_R + 1; ++s) sRing[s][t] = 0;
+    uint32_t run = 0;
+    int slot = 0;
+    const int x1 = x1s + xl;
+    uint32_t* Cout = Cvol + (size_t)pair * H * W1 * SG_NDP;
+
+    auto load_row = [&](int row) {  // phase A
+        const int rr = min(max(row, 0), H - 1);
+        if (t < 2 * SG_NRH) {
+            const int j = min(max(jb + t, 0), W - 1), jm = min(max(jb + t - 1, 0), W - 1);
+            const uint2 a = preR[(size_t)rr * W + j], b = preR[(size_t)rr * W + jm];
+            uint32_t* d = &sR[t & 1][0][t >> 1];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const uint32_t pa = c ? a.y : a.x, pb = c ? b.y : b.x;
+                const uint32_t v = (pa & 0xff) | (pb & 0xff) << 16;
+                const uint32_t v0 = (pa >> 8 & 0xff) | (pb >> 8 & 0xff) << 16;
+                const uint32_t v1 = (pa >> 16 & 0xff) | (pb >> 16 & 0xff) << 16;
+                d[(4 * c + 0) * SG_NRH] = v;
+                d[(4 * c + 1) * SG_NRH] = v0;
+                d[(4 * c + 2) * SG_NRH] = neg2(v);
+                d[(4 * c + 3) * SG_NRH] = neg2(v1);
+            }
+        } else if (t >= 128 && t < 128 + SG_NC) {
+            const int c_rel = t - 128;
+            const int xc = min(max(x1s - SG_R + c_rel, 0), W1 - 1) + SG_D;
+            const uint2 a = preL[(size_t)rr * W + xc];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const uint32_t pa = c ? a.y : a.x;
+                const uint32_t u = bcast16(pa & 0xff), u0 = bcast16(pa >> 8 & 0xff), u1 = bcast16(pa >> 16 & 0xff);
+                sL[c_rel][4 * c + 0] = u;
+                sL[c_rel][4 * c + 1] = u0;
+                sL[c_rel][4 * c + 2] = neg2(u);
+                sL[c_rel][4 * c + 3] = neg2(u1);
+            }
+        }
+    };
+
+    const int r_first = y0 - SG_R, r_last = y1 - 1 + SG_R;
+    load_row(r_first);
+    for (int row = r_first; row <= r_last; ++row) {
+        __syncthreads();
+        // phase B: pixel cost of every (column, pair) of the strip + halo
+        for (int i = t; i < SG_NC * SG_NDP; i += SG_TX * SG_NDP) {
+            const int c_rel = i / SG_NDP, dq = i - c_rel * SG_NDP;
+            const int xc = min(max(x1s - SG_R + c_rel, 0), W1 - 1) + SG_D;
+            const int r = xc - 2 * dq - jb;
+            const uint32_t* pr = &sR[r & 1][0][r >> 1];
+            const uint32_t* pl = sL[c_rel];
+            const uint32_t cs = bt_cost2(pl[0], pl[1], pl[2], pl[3], pr[0], pr[SG_NRH], pr[2 * SG_NRH], pr[3 * SG_NRH]);
+            const uint32_t cr = bt_cost2(pl[4], pl[5], pl[6], pl[7], pr[4 * SG_NRH], pr[5 * SG_NRH], pr[6 * SG_NRH], pr[7 * SG_NRH]);
+            sPd[c_rel][dq] = cs + ((cr >> 2) & 0x3fff3fffu);
+        }
+        __syncthreads();
+        // phase C: horizontal window, vertical running sum; phase A of the next row rides along
+        uint32_t hs = 0;
+#pragma unroll
+        for (int k = 0; k < 2 * SG_R + 1; ++k) hs += sPd[xl + k][dp];
+        run = run + hs - sRing[slot][t];
+        sRing[slot][t] = hs;
+        slot = slot == 2 * SG_R ? 0 : slot + 1;
+        const int yo = row - SG_R;
+        if (yo >= y0 && x1 < W1) Cout[((size_t)yo * W1 + x1) * SG_NDP + dp] = run;
+        if (row < r_last) load_row(row + 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One SGM step on a warp: lanes 0..23 hold disparities 4l..4l+3 as two s16x2 words (a0 = d, d+1; a1 = d+2, d+3),
+// lanes 24..31 hold SG_BIG2.  L(d) = C(d) + min(Lp(d), Lp(d-1) + P1, Lp(d+1) + P1, m + P2) - m,  m = min_k Lp(k).
+// Returns the new minimum over the warp.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sgm_step(uint32_t& a0, uint32_t& a1, int m, uint32_t c0, uint32_t c1, uint32_t P1b, int P2,
+                                        int lane) {
+    uint32_t up = __shfl_up_sync(0xffffffffu, a1, 1);
+    const uint32_t dn = __shfl_down_sync(0xffffffffu, a0, 1);
+    if (lane == 0) up = SG_BIG2;
+    const uint32_t lm0 = __byte_perm(up, a0, 0x5432);  // (L[4l-1], L[4l])
+    const uint32_t mid = __byte_perm(a0, a1, 0x5432);  // (L[4l+1], L[4l+2])
+    const uint32_t lp1 = __byte_perm(a1, dn, 0x5432);  // (L[4l+3], L[4l+4])
+    const uint32_t mp2 = bcast16(m + P2), mm = bcast16(m);
+    const uint32_t t0 = __vmins2(__vmins2(__vadd2(__vmins2(lm0, mid), P1b), mp2), a0);
+    const uint32_t t1 = __vmins2(__vmins2(__vadd2(__vmins2(mid, lp1), P1b), mp2), a1);
+    uint32_t r0 = c0 + t0 - mm, r1 = c1 + t1 - mm;  // halves stay in [0, 32767]: plain 32-bit arithmetic is exact
+    if (lane >= 24) r0 = r1 = SG_BIG2;
+    a0 = r0;
+    a1 = r1;
+    const uint32_t w = __vmins2(r0, r1);
+    return __reduce_min_sync(0xffffffffu, (int)min(w & 0xffffu, w >> 16));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K20: the three paths that come from the row above.  blockIdx.y: 0 = from (x-1, y-1), 1 = from (x, y-1),
+// 2 = from (x+1, y-1).  Warp k starts at column k of row 0; a diagonal path that leaves the image re-enters on the
+// other side with a fresh (zero) predecessor, which is what OpenCV's zero-initialised border columns give.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sgbm_vertical_kernel(const uint32_t* __restrict__ Cvol, uint32_t* __restrict__ L0v,
+                                                            uint32_t* __restrict__ L1v, uint32_t* __restrict__ L2v, int W1,
+                                                            int H, int P1, int P2) {
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (k >= W1) return;
+    const int dir = blockIdx.y, pair = blockIdx.z;
+    const int dx = 1 - dir;  // +1, 0, -1
+    const size_t vol = (size_t)pair * H * W1 * SG_NDP;
+    const uint2* C = reinterpret_cast<const uint2*>(Cvol + vol);
+    uint2* Lo = reinterpret_cast<uint2*>((dir == 0 ? L0v : dir == 1 ? L1v : L2v) + vol);
+    const bool active = lane < 24;
+    const uint32_t P1b = bcast16(P1);
+    const int reset_x = dir == 0 ? 0 : dir == 2 ? W1 - 1 : -1;
+
+    uint2 cb[SG_PF];
+    int xp = k;  // column of the row being prefetched
+#pragma unroll
+    for (int i = 0; i < SG_PF; ++i) {
+        cb[i] = make_uint2(0, 0);
+        if (active && i < H) cb[i] = __ldcs(&C[((size_t)i * W1 + xp) * 24 + lane]);
+        xp += dx;
+        if (xp == W1) xp = 0;
+        if (xp < 0) xp = W1 - 1;
+    }
+    uint32_t a0 = active ? 0u : SG_BIG2, a1 = a0;
+    int m = 0, x = k;
+    for (int y = 0; y < H; y += SG_PF) {
+#pragma unroll
+        for (int i = 0; i < SG_PF; ++i) {
+            const int yy = y + i;
+            if (yy < H) {
+                const uint2 c = cb[i];
+                if (active && yy + SG_PF < H) cb[i] = __ldcs(&C[((size_t)(yy + SG_PF) * W1 + xp) * 24 + lane]);
+                xp += dx;
+                if (xp == W1) xp = 0;
+                if (xp < 0) xp = W1 - 1;
+                if (x == reset_x) {
+                    a0 = a1 = active ? 0u : SG_BIG2;
+                    m = 0;
+                }
+                m = sgm_step(a0, a1, m, c.x, c.y, P1b, P2, lane);
+                if (active) Lo[((size_t)yy * W1 + x) * 24 + lane] = make_uint2(a0, a1);
+                x += dx;
+                if (x == W1) x = 0;
+                if (x < 0) x = W1 - 1;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K21: one warp per image row.  Pass 1 walks left->right (path 0) and folds the four finished paths into
+// S4 = sat16(L0+L1+L2+L3) (written over L1's volume); pass 2 walks right->left (the fifth path of MODE_SGBM's single
+// pass), adds it, and does disparity selection exactly in OpenCV's order (descending x, so the right-image map sees
+// the same first writer on cost ties).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SG_HW * 32) sgbm_horizontal_kernel(const uint32_t* __restrict__ Cvol, uint32_t* __restrict__ L0v,
+                                                                    const uint32_t* __restrict__ L1v,
+                                                                    const uint32_t* __restrict__ L2v, int W, int W1, int H,
+                                                                    SgParams p, int16_t* __restrict__ disp_raw) {
+    extern __shared__ int16_t sg_sm[];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int y = blockIdx.x * SG_HW + wp, pair = blockIdx.y;
+    if (y >= H) return;
+    const int Wp = (W + 1) & ~1;  // keeps s_S 4-byte aligned
+    int16_t* s_d1 = sg_sm + (size_t)wp * (3 * Wp + 2 * SG_D);
+    int16_t* s_d2 = s_d1 + Wp;
+    int16_t* s_c2 = s_d2 + Wp;
+    int16_t* s_S = s_c2 + Wp;  // [2][96]
+    const size_t rowoff = ((size_t)pair * H + y) * W1 * 24;
+    const uint2* C = reinterpret_cast<const uint2*>(Cvol) + rowoff;
+    uint2* T = reinterpret_cast<uint2*>(L0v) + rowoff;
+    const uint2* LB = reinterpret_cast<const uint2*>(L1v) + rowoff;
+    const uint2* LC = reinterpret_cast<const uint2*>(L2v) + rowoff;
+    const bool active = lane < 24;
+    const uint32_t P1b = bcast16(p.P1);
+    const uint32_t SAT = 0x7fff7fffu;
+
+    // ---- pass 1: left -> right ----
+    {
+        uint32_t a0 = active ? 0u : SG_BIG2, a1 = a0;
+        int m = 0;
+        constexpr int PF = 4;
+        uint2 cb[PF], l0b[PF], l1b[PF], l2b[PF];
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+            cb[i] = l0b[i] = l1b[i] = l2b[i] = make_uint2(0, 0);
+            if (active && i < W1) {
+                cb[i] = C[(size_t)i * 24 + lane];
+                l0b[i] = T[(size_t)i * 24 + lane];
+                l1b[i] = __ldcs(&LB[(size_t)i * 24 + lane]);
+                l2b[i] = __ldcs(&LC[(size_t)i * 24 + lane]);
+            }
+        }
+        for (int x = 0; x < W1; x += PF) {
+#pragma unroll
+            for (int i = 0; i < PF; ++i) {
+                const int xx = x + i;
+                if (xx < W1) {
+                    const uint2 c = cb[i], l0 = l0b[i], l1 = l1b[i], l2 = l2b[i];
+                    if (active && xx + PF < W1) {
+                        cb[i] = C[(size_t)(xx + PF) * 24 + lane];
+                        l0b[i] = T[(size_t)(xx + PF) * 24 + lane];
+                        l1b[i] = __ldcs(&LB[(size_t)(xx + PF) * 24 + lane]);
+                        l2b[i] = __ldcs(&LC[(size_t)(xx + PF) * 24 + lane]);
+                    }
+                    m = sgm_step(a0, a1, m, c.x, c.y, P1b, p.P2, lane);
+                    // three paths <= 3 * (15309 + P2) < 65536: exact in u16; then saturate like CostType
+                    uint2 s;
+                    s.x = __vminu2(__vminu2(l0.x + l1.x + l2.x, SAT) + a0, SAT);
+                    s.y = __vminu2(__vminu2(l0.y + l1.y + l2.y, SAT) + a1, SAT);
+                    if (active) T[(size_t)xx * 24 + lane] = s;
+                }
+            }
+        }
+    }
+    for (int i = lane; i < W; i += 32) {
+        s_d1[i] = SG_INVALID;
+        s_d2[i] = SG_INVALID;
+        s_c2[i] = SG_MAXCOST;
+    }
+    __syncwarp();
+    // ---- pass 2: right -> left + disparity selection ----
+    {
+        uint32_t a0 = active ? 0u : SG_BIG2, a1 = a0;
+        int m = 0;
+        constexpr int PF = 4;
+        uint2 cb[PF], tb[PF];
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+            cb[i] = tb[i] = make_uint2(0, 0);
+            const int xx = W1 - 1 - i;
+            if (active && xx >= 0) {
+                cb[i] = __ldcs(&C[(size_t)xx * 24 + lane]);
+                tb[i] = __ldcs(&T[(size_t)xx * 24 + lane]);
+            }
+        }
+        const int uq = 100 - p.uniq;
+        for (int x = W1 - 1; x >= 0; x -= PF) {
+#pragma unroll
+            for (int i = 0; i < PF; ++i) {
+                const int xx = x - i;
+                if (xx >= 0) {
+                    const uint2 c = cb[i], tt = tb[i];
+                    if (active && xx - PF >= 0) {
+                        cb[i] = __ldcs(&C[(size_t)(xx - PF) * 24 + lane]);
+                        tb[i] = __ldcs(&T[(size_t)(xx - PF) * 24 + lane]);
+                    }
+                    m = sgm_step(a0, a1, m, c.x, c.y, P1b, p.P2, lane);
+                    const uint32_t S0 = __vminu2(tt.x + a0, SAT), S1 = __vminu2(tt.y + a1, SAT);
+                    const int d0 = 4 * lane;
+                    const int s0 = S0 & 0xffff, s1 = S0 >> 16, s2 = S1 & 0xffff, s3 = S1 >> 16;
+                    uint32_t key = min(min((uint32_t)s0 << 8 | d0, (uint32_t)s1 << 8 | (d0 + 1)),
+                                       min((uint32_t)s2 << 8 | (d0 + 2), (uint32_t)s3 << 8 | (d0 + 3)));
+                    if (!active) key = 0xffffffffu;
+                    key = __reduce_min_sync(0xffffffffu, key);
+                    const int minS = key >> 8, bestd = key & 0xff;
+                    const int thr = minS * 100;
+                    bool nu = (s0 * uq < thr && abs(bestd - d0) > 1) || (s1 * uq < thr && abs(bestd - d0 - 1) > 1) ||
+                              (s2 * uq < thr && abs(bestd - d0 - 2) > 1) || (s3 * uq < thr && abs(bestd - d0 - 3) > 1);
+                    nu = __any_sync(0xffffffffu, nu && active);
+                    uint32_t* sS = reinterpret_cast<uint32_t*>(s_S + (xx & 1) * SG_D);
+                    if (active) {
+                        sS[2 * lane] = S0;
+                        sS[2 * lane + 1] = S1;
+                    }
+                    __syncwarp();
+                    if (!nu && lane == 0) {
+                        const int16_t* Sp = s_S + (xx & 1) * SG_D;
+                        const int x2 = xx + SG_D - bestd;
+                        if (s_c2[x2] > minS) {
+                            s_c2[x2] = (int16_t)minS;
+                            s_d2[x2] = (int16_t)bestd;
+                        }
+                        int dd = bestd * 16;
+                        if (0 < bestd && bestd < SG_D - 1) {
+                            const int denom2 = max((int)Sp[bestd - 1] + Sp[bestd + 1] - 2 * minS, 1);
+                            dd += (((int)Sp[bestd - 1] - Sp[bestd + 1]) * 16 + denom2) / (denom2 * 2);
+                        }
+                        s_d1[xx + SG_D] = (int16_t)dd;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // ---- left-right consistency + write-out ----
+    int16_t* out = disp_raw + ((size_t)pair * H + y) * W;
+    for (int xx = lane; xx < W; xx += 32) {
+        int d1 = s_d1[xx];
+        if (d1 != SG_INVALID) {
+            const int dl = d1 >> 4, dh = (d1 + 15) >> 4;
+            const int xa = xx - dl, xb = xx - dh;
+            if (xa >= 0 && xa < W && xb >= 0 && xb < W) {
+                const int ea = s_d2[xa], eb = s_d2[xb];
+                if (ea >= 0 && abs(ea - dl) > p.disp12 && eb >= 0 && abs(eb - dh) > p.disp12) d1 = SG_INVALID;
+            }
+        }
+        out[xx] = (int16_t)d1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K22: cv::medianBlur(ksize 3) on CV_16S (replicated border)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cswap(int& a, int& b) {
+    const int lo = min(a, b), hi = max(a, b);
+    a = lo;
+    b = hi;
+}
+
+__global__ void __launch_bounds__(256) sgbm_median_kernel(const int16_t* __restrict__ in, int16_t* __restrict__ out, int W, int H) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const int16_t* base = in + (size_t)blockIdx.z * H * W;
+    int v[9];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+        const int16_t* r = base + (size_t)min(max(y - 1 + dy, 0), H - 1) * W;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[dy * 3 + k] = r[min(max(x - 1 + k, 0), W - 1)];
+    }
+    // median-of-9 exchange network
+    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
+    cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
+    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
+    cswap(v[0], v[3]); cswap(v[5], v[8]); cswap(v[4], v[7]);
+    cswap(v[3], v[6]); cswap(v[1], v[4]); cswap(v[2], v[5]);
+    cswap(v[4], v[7]); cswap(v[4], v[2]); cswap(v[6], v[4]);
+    cswap(v[4], v[2]);
+    out[((size_t)blockIdx.z * H + y) * W + x] = (int16_t)v[4];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K23: cv::filterSpeckles(disp, newVal = -16, maxSpeckleSize, maxDiff) as union-find connected components.
+// Two valid 4-neighbours are connected when |a - b| <= maxDiff; components are equivalence classes, so the result
+// does not depend on OpenCV's scan order.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(int* L, int a) {
+    int r = a;
+    while (true) {
+        const int pr = L[r];
+        if (pr == r) break;
+        r = pr;
+    }
+    return r;
+}
+
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+    while (true) {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a == b) return;
+        if (a < b) {
+            const int t = a;
+            a = b;
+            b = t;
+        }
+        const int old = atomicMin(&L[a], b);  // a > b: hang root a under b
+        if (old == a) return;
+        a = old;
+    }
+}
+
+__global__ void __launch_bounds__(256) speckle_init_kernel(const int16_t* __restrict__ d, int* __restrict__ label,
+                                                           int* __restrict__ size, int n, int hw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    label[i] = d[i] != SG_INVALID ? i % hw : -1;  // labels are pixel indices inside their own image
+    size[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) speckle_merge_kernel(const int16_t* __restrict__ d, int* __restrict__ label, int W, int H,
+                                                            int max_diff) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const size_t img = (size_t)blockIdx.z * H * W;
+    const int16_t* p = d + img;
+    int* L = label + img;
+    const int i = y * W + x;
+    const int v = p[i];
+    if (v == SG_INVALID) return;
+    if (x + 1 < W) {
+        const int r = p[i + 1];
+        if (r != SG_INVALID && abs(v - r) <= max_diff) uf_union(L, i, i + 1);
+    }
+    if (y + 1 < H) {
+        const int b = p[i + W];
+        if (b != SG_INVALID && abs(v - b) <= max_diff) uf_union(L, i, i + W);
+    }
+}
+
+__global__ void __launch_bounds__(256) speckle_count_kernel(int* __restrict__ label, int* __restrict__ size, int hw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hw) return;
+    const size_t img = (size_t)blockIdx.y * hw;
+    int* L = label + img;
+    if (L[i] < 0) return;
+    const int r = uf_find(L, i);
+    atomicAdd(&size[img + r], 1);
+}
+
+__global__ void __launch_bounds__(256) speckle_apply_kernel(const int16_t* __restrict__ d, const int* __restrict__ label,
+                                                            const int* __restrict__ size, int hw, int max_size,
+                                                            int16_t* __restrict__ out, float* __restrict__ outf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hw) return;
+    const size_t img = (size_t)blockIdx.y * hw;
+    int v = d[img + i];
+    if (max_size > 0 && v != SG_INVALID) {
+        int r = i;
+        while (true) {
+            const int pr = label[img + r];
+            if (pr == r) break;
+            r = pr;
+        }
+        if (size[img + r] <= max_size) v = SG_INVALID;
+    }
+    if (out) out[img + i] = (int16_t)v;
+    if (outf) outf[img + i] = (float)v * 0.0625f;  // convertTo(CV_32F, 1/16): exact
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+int vslam_sgbm_init(vslam_ctx* ctx) {
+    ctx->sgbm = (SgbmState*)calloc(1, sizeof(SgbmState));
+    return ctx->sgbm ? VSLAM_OK : VSLAM_E_INVALID;
+}
+
+static void sgbm_release(SgbmState* s) {
+    cudaFree(s->d_pre);
+    cudaFree(s->d_C);
+    for (int i = 0; i < 3; ++i) cudaFree(s->d_L[i]);
+    cudaFree(s->d_raw);
+    cudaFree(s->d_med);
+    cudaFree(s->d_label);
+    cudaFree(s->d_size);
+    cudaFree(s->d_img);
+    cudaFree(s->d_out);
+    cudaFree(s->d_outf);
+    const int stop = s->stop_after;
+    memset(s, 0, sizeof(*s));
+    s->stop_after = stop;
+}
+
+void vslam_sgbm_free(vslam_ctx* ctx) {
+    if (!ctx->sgbm) return;
+    sgbm_release(ctx->sgbm);
+    free(ctx->sgbm);
+    ctx->sgbm = nullptr;
+}
+
+// scratch for `pairs` pairs of w x h images (grown on demand; the volumes dominate: 4 x H x W1 x 192 B per pair)
+static int sgbm_reserve(vslam_ctx* ctx, int pairs, int w, int h) {
+    SgbmState* s = ctx->sgbm;
+    if (pairs <= s->cap_pairs && w == s->cap_w && h == s->cap_h) return VSLAM_OK;
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int keep = s->cap_w == w && s->cap_h == h ? s->cap_pairs : 0;
+    sgbm_release(s);
+    pairs = pairs > keep ? pairs : keep;
+    const size_t px = (size_t)w * h, vol = (size_t)h * (w - SG_D) * SG_NDP * sizeof(uint32_t);
+    s->pitch = (w + 15) & ~15;
+    VSLAM_CUDA(ctx, cudaMalloc(&s->d_pre, 2 * pairs * px * sizeof(uint2)));
+    VSLAM_CUDA(ctx, cudaMalloc(&s->d_C, pairs * vol));
+    for (int i = 0; i < 3; ++i) VSLAM_CUDA(ctx, cudaMalloc(&s->d_L[i], pairs * vol));
+    VSLAM_CUDA(ctx, cudaMalloc(&s->d_raw, pairs * px * sizeof(int16_t)));
+    VSLAM_CUDA(ctx, cudaMalloc(&s->d_med, pairs * px * sizeof(int16_t)));
+    VSLAM_CUDA(ctx, cudaMalloc(&s->d_label, pairs * px * sizeof(int32_t)));
+    VSLAM_CUDA(ctx, cudaMalloc(&s->d_size, pairs * px * sizeof(int32_t)));
+    VSLAM_CUDA(ctx, cudaMalloc(&s->d_img, 2 * (size_t)pairs * h * s->pitch));
+    VSLAM_CUDA(ctx, cudaMalloc(&s->d_out, pairs * px * sizeof(int16_t)));
+    VSLAM_CUDA(ctx, cudaMalloc(&s->d_outf, pairs * px * sizeof(float)));
+    s->cap_pairs = pairs;
+    s->cap_w = w;
+    s->cap_h = h;
+    return VSLAM_OK;
+}
+
+extern "C" void vslam_sgbm_default_params(vslam_sgbm_params* p) {
+    if (!p) return;
+    // visual_odometry.cpp:163-164
+    p->min_disparity = 0;
+    p->num_disparities = 96;
+    p->block_size = 9;
+    p->P1 = 8 * 9 * 9;
+    p->P2 = 32 * 9 * 9;
+    p->disp12_max_diff = 1;
+    p->pre_filter_cap = 63;
+    p->uniqueness_ratio = 10;
+    p->speckle_window_size = 100;
+    p->speckle_range = 32;
+}
+
+static int sgbm_check(const vslam_sgbm_params* in, int w, int h, SgParams* out) {
+    vslam_sgbm_params p;
+    if (in) p = *in; else vslam_sgbm_default_params(&p);
+    // the kernels are specialised for the reference's geometry: 96 disparities from 0, 9x9 block
+    if (p.min_disparity != 0 || p.num_disparities != SG_D || p.block_size != 2 * SG_R + 1) return VSLAM_E_INVALID;
+    if (h < 1 || w - SG_D <= SG_R) return VSLAM_E_INVALID;  // OpenCV raises for such images (stereosgbm.cpp:511)
+    out->P1 = p.P1 > 0 ? p.P1 : 2;
+    const int p2 = p.P2 > 0 ? p.P2 : 5;
+    out->P2 = p2 > out->P1 + 1 ? p2 : out->P1 + 1;
+    out->disp12 = p.disp12_max_diff > 0 ? p.disp12_max_diff : 1;
+    out->uniq = p.uniqueness_ratio >= 0 ? p.uniqueness_ratio : 10;
+    out->ftzero = (p.pre_filter_cap > 15 ? p.pre_filter_cap : 15) | 1;
+    out->speckle_window = p.speckle_window_size;
+    out->speckle_diff = 16 * p.speckle_range;
+    // packed s16 arithmetic needs 81*189 + P2 + P1 < 30000 and ftzero <= 127 (u8 operands)
+    if (out->P2 + out->P1 + 81 * 189 >= 30000 || out->ftzero > 127 || out->uniq > 100) return VSLAM_E_INVALID;
+    return VSLAM_OK;
+}
+
+// enqueue the whole pipeline for n (<= cap_pairs) pairs; images and outputs are device pointers
+static int sgbm_enqueue(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_right, int n, int w, int h, int pitch,
+                        long long img_stride, const SgParams& p, int16_t* d_disp16, float* d_dispf) {
+    SgbmState* s = ctx->sgbm;
+    cudaStream_t st = ctx->stream;
+    const int W1 = w - SG_D;
+    vslam_time_begin(ctx, VK_SGBM_PREFILTER);
+    sgbm_prefilter_kernel<<<dim3(ceil_div(w, 256), h, 2 * n), 256, 0, st>>>(d_left, d_right, img_stride, pitch, n, w, h, p.ftzero,
+                                                                            s->d_pre);
+    vslam_time_end(ctx);
+    VSLAM_LAUNCH_CHECK(ctx, "sgbm_prefilter_kernel");
+    const int band_rows = ceil_div(h, SG_BANDS);
+    vslam_time_begin(ctx, VK_SGBM_COST);
+    sgbm_cost_kernel<<<dim3(ceil_div(W1, SG_TX), ceil_div(h, band_rows), n), SG_TX * SG_NDP, 0, st>>>(s->d_pre, n, w, h, W1,
+                                                                                                      band_rows, s->d_C);
+    vslam_time_end(ctx);
+    VSLAM_LAUNCH_CHECK(ctx, "sgbm_cost_kernel");
+    vslam_time_begin(ctx, VK_SGBM_VERTICAL);
+    sgbm_vertical_kernel<<<dim3(ceil_div(W1, 8), 3, n), 256, 0, st>>>(s->d_C, s->d_L[0], s->d_L[1], s->d_L[2], W1, h, p.P1, p.P2);
+    vslam_time_end(ctx);
+    VSLAM_LAUNCH_CHECK(ctx, "sgbm_vertical_kernel");
+    if (s->stop_after == 1) return VSLAM_OK;
+    const size_t smem = (size_t)SG_HW * (3 * ((w + 1) & ~1) + 2 * SG_D) * sizeof(int16_t);
+    VSLAM_CUDA(ctx, cudaFuncSetAttribute(sgbm_horizontal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vslam_time_begin(ctx, VK_SGBM_HORIZONTAL);
+    sgbm_horizontal_kernel<<<dim3(ceil_div(h, SG_HW), n), SG_HW * 32, smem, st>>>(s->d_C, s->d_L[0], s->d_L[1], s->d_L[2], w, W1, h, p,
+                                                                                  s->d_raw);
+    vslam_time_end(ctx);
+    VSLAM_LAUNCH_CHECK(ctx, "sgbm_horizontal_kernel");
+    const int hw = w * h;
+    vslam_time_begin(ctx, VK_SGBM_POST);
+    sgbm_median_kernel<<<dim3(ceil_div(w, 256), h, n), 256, 0, st>>>(s->d_raw, s->d_med, w, h);
+    ctx->launches++;
+    if (p.speckle_window > 0) {
+        speckle_init_kernel<<<ceil_div(n * hw, 256), 256, 0, st>>>(s->d_med, s->d_label, s->d_size, n * hw, hw);
+        speckle_merge_kernel<<<dim3(ceil_div(w, 256), h, n), 256, 0, st>>>(s->d_med, s->d_label, w, h, p.speckle_diff);
+        speckle_count_kernel<<<dim3(ceil_div(hw, 256), n), 256, 0, st>>>(s->d_label, s->d_size, hw);
+        ctx->launches += 3;
+    }
+    speckle_apply_kernel<<<dim3(ceil_div(hw, 256), n), 256, 0, st>>>(s->d_med, s->d_label, s->d_size, hw, p.speckle_window, d_disp16,
+                                                                    d_dispf);
+    vslam_time_end(ctx);
+    VSLAM_LAUNCH_CHECK(ctx, "sgbm post kernels");
+    return VSLAM_OK;
+}
+
+extern "C" int vslam_sgbm_compute_dev(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_right, int n_pairs, int width,
+                                      int height, int row_pitch, long long image_stride, const vslam_sgbm_params* params,
+                                      int16_t* d_disp16, float* d_disp_f32) {
+    if (!ctx || !d_left || !d_right || n_pairs < 0 || row_pitch < width || (!d_disp16 && !d_disp_f32)) return VSLAM_E_INVALID;
+    SgParams p;
+    int st = sgbm_check(params, width, height, &p);
+    if (st != VSLAM_OK) return st;
+    if (n_pairs == 0) return VSLAM_OK;
+    VSLAM_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const int chunk = n_pairs < SG_CHUNK_PAIRS ? n_pairs : SG_CHUNK_PAIRS;
+    st = sgbm_reserve(ctx, chunk, width, height);
+    if (st != VSLAM_OK) return st;
+    const size_t px = (size_t)width * height;
+    for (int b = 0; b < n_pairs; b += chunk) {
+        const int n = n_pairs - b < chunk ? n_pairs - b : chunk;
+        st = sgbm_enqueue(ctx, d_left + (long long)b * image_stride, d_right + (long long)b * image_stride, n, width, height,
+                          row_pitch, image_stride, p, d_disp16 ? d_disp16 + b * px : nullptr,
+                          d_disp_f32 ? d_disp_f32 + b * px : nullptr);
+        if (st != VSLAM_OK) return st;
+    }
+    return VSLAM_OK;
+}
+
+extern "C" int vslam_sgbm_compute(vslam_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_pairs, int width, int height,
+                                  int row_pitch, long long image_stride, const vslam_sgbm_params* params, int16_t* disp16,
+                                  float* disp_f32) {
+    if (!ctx || !left || !right || n_pairs < 0 || row_pitch < width || (!disp16 && !disp_f32)) return VSLAM_E_INVALID;
+    SgParams p;
+    int st = sgbm_check(params, width, height, &p);
+    if (st != VSLAM_OK) return st;
+    if (n_pairs == 0) return VSLAM_OK;
+    VSLAM_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const int chunk = n_pairs < SG_CHUNK_PAIRS ? n_pairs : SG_CHUNK_PAIRS;
+    st = sgbm_reserve(ctx, chunk, width, height);
+    if (st != VSLAM_OK) return st;
+    SgbmState* s = ctx->sgbm;
+    const size_t px = (size_t)width * height;
+    const long long dstride = (long long)s->pitch * height;
+    for (int b = 0; b < n_pairs; b += chunk) {
+        const int n = n_pairs - b < chunk ? n_pairs - b : chunk;
+        for (int side = 0; side < 2; ++side)
+            for (int i = 0; i < n; ++i)
+                VSLAM_CUDA(ctx, cudaMemcpy2DAsync(s->d_img + (size_t)(side * n + i) * dstride, s->pitch,
+                                                  (side ? right : left) + (long long)(b + i) * image_stride, row_pitch, width,
+                                                  height, cudaMemcpyHostToDevice, ctx->stream));
+        st = sgbm_enqueue(ctx, s->d_img, s->d_img + (size_t)n * dstride, n, width, height, s->pitch, dstride, p,
+                          disp16 ? s->d_out : nullptr, disp_f32 ? s->d_outf : nullptr);
+        if (st != VSLAM_OK) return st;
+        if (s->stop_after == 0) {
+            if (disp16)
+                VSLAM_CUDA(ctx, cudaMemcpyAsync(disp16 + b * px, s->d_out, n * px * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+            if (disp_f32)
+                VSLAM_CUDA(ctx, cudaMemcpyAsync(disp_f32 + b * px, s->d_outf, n * px * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return VSLAM_OK;
+}
+
+// test tap: stage 0 = C, 1..3 = path volumes (1 holds S4 after the horizontal sweep), 4 = raw disparity, 5 = median
+extern "C" int vslam_sgbm_debug_read(vslam_ctx* ctx, int pair, int stage, void* host_out, size_t bytes) {
+    if (!ctx || !ctx->sgbm || !host_out || pair < 0 || pair >= ctx->sgbm->cap_pairs) return VSLAM_E_INVALID;
+    SgbmState* s = ctx->sgbm;
+    const size_t vol = (size_t)s->cap_h * (s->cap_w - SG_D) * SG_NDP * sizeof(uint32_t);
+    const size_t img = (size_t)s->cap_w * s->cap_h * sizeof(int16_t);
+    const void* src;
+    size_t n;
+    if (stage == 0) { src = (const char*)s->d_C + pair * vol; n = vol; }
+    else if (stage >= 1 && stage <= 3) { src = (const char*)s->d_L[stage - 1] + pair * vol; n = vol; }
+    else if (stage == 4) { src = (const char*)s->d_raw + pair * img; n = img; }
+    else if (stage == 5) { src = (const char*)s->d_med + pair * img; n = img; }
+    else return VSLAM_E_INVALID;
+    if (bytes < n) return VSLAM_E_CAPACITY;
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VSLAM_CUDA(ctx, cudaMemcpy(host_out, src, n, cudaMemcpyDeviceToHost));
+    return VSLAM_OK;
+}
+
+extern "C" int vslam_sgbm_debug_stop_after(vslam_ctx* ctx, int stage) {
+    if (!ctx || !ctx->sgbm) return VSLAM_E_INVALID;
+    ctx->sgbm->stop_after = stage;
+    return VSLAM_OK;
+}

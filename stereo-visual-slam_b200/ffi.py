@@ -40,6 +40,14 @@ class BaResult(C.Structure):
                 ("chi2_threshold", C.c_double), ("n_inlier_obs", C.c_int32), ("n_outlier_obs", C.c_int32)]
 
 
+class SgbmParams(C.Structure):
+    """vslam_sgbm_params; defaults = cv::StereoSGBM::create(0, 96, 9, 8*9*9, 32*9*9, 1, 63, 10, 100, 32)
+    (visual_odometry.cpp:163-164)."""
+    _fields_ = [(n, C.c_int32) for n in ("min_disparity", "num_disparities", "block_size", "P1", "P2",
+                                         "disp12_max_diff", "pre_filter_cap", "uniqueness_ratio",
+                                         "speckle_window_size", "speckle_range")]
+
+
 KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
                            ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
@@ -88,6 +96,11 @@ SIGNATURES = {
     "vslam_ba_session_phase": (_i, [_vp, _i, _d]),
     "vslam_ba_session_trial_done": (_i, [_vp, _i]),
     "vslam_ba_session_end": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "vslam_sgbm_default_params": (None, [C.POINTER(SgbmParams)]),
+    "vslam_sgbm_compute": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_longlong, C.POINTER(SgbmParams), _vp, _vp]),
+    "vslam_sgbm_compute_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_longlong, C.POINTER(SgbmParams), _vp, _vp]),
+    "vslam_sgbm_debug_read": (_i, [_vp, _i, _i, _vp, C.c_size_t]),
+    "vslam_sgbm_debug_stop_after": (_i, [_vp, _i]),
     "vslam_match_hamming_batch_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _d, _d, _vp, _i, _vp]),
 }
 
@@ -341,6 +354,46 @@ class Context:
         st = self.lib.vslam_anms(self.h, _ptr(kp), len(kp), int(num), float(c_robust), _ptr(keep), C.byref(n))
         self.check(st, "vslam_anms")
         return keep[:n.value].copy()
+
+    # ---- dense stereo (VO::disparity_map, visual_odometry.cpp:159-174) -----------------------------------
+    def sgbm_params(self, **kw) -> SgbmParams:
+        p = SgbmParams()
+        self.lib.vslam_sgbm_default_params(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, int(v))
+        return p
+
+    def sgbm_compute(self, left, right, params: SgbmParams | None = None, want_float: bool = False):
+        """left/right: (H, W) or (n, H, W) uint8 host arrays -> int16 disparity*16 (and float32 disparity)."""
+        left = np.ascontiguousarray(left, dtype=np.uint8)
+        right = np.ascontiguousarray(right, dtype=np.uint8)
+        single = left.ndim == 2
+        if single:
+            left, right = left[None], right[None]
+        n, h, w = left.shape
+        d16 = np.empty((n, h, w), np.int16)
+        df = np.empty((n, h, w), np.float32) if want_float else None
+        st = self.lib.vslam_sgbm_compute(self.h, _ptr(left), _ptr(right), n, w, h, w, w * h,
+                                         C.byref(params) if params is not None else None, _ptr(d16), _ptr(df))
+        self.check(st, "vslam_sgbm_compute")
+        if single:
+            d16, df = d16[0], (df[0] if df is not None else None)
+        return (d16, df) if want_float else d16
+
+    def sgbm_compute_dev(self, d_left, d_right, n_pairs, w, h, pitch, img_stride, d_disp16, d_disp_f32=None, params=None):
+        st = self.lib.vslam_sgbm_compute_dev(self.h, _ptr(d_left), _ptr(d_right), n_pairs, w, h, pitch, img_stride,
+                                             C.byref(params) if params is not None else None, _ptr(d_disp16),
+                                             _ptr(d_disp_f32))
+        self.check(st, "vslam_sgbm_compute_dev")
+
+    def sgbm_debug_volume(self, pair: int, stage: int, h: int, w: int):
+        """stage 0 = C, 1..3 = path volumes -> (h, w-96, 96) uint16; 4 / 5 = raw / median disparity (h, w) int16."""
+        out = np.empty((h, w - 96, 96), np.uint16) if stage <= 3 else np.empty((h, w), np.int16)
+        self.check(self.lib.vslam_sgbm_debug_read(self.h, pair, stage, _ptr(out), out.nbytes), "vslam_sgbm_debug_read")
+        return out
+
+    def sgbm_debug_stop_after(self, stage: int):
+        self.check(self.lib.vslam_sgbm_debug_stop_after(self.h, stage), "vslam_sgbm_debug_stop_after")
 
     def ba_last_phase_us(self) -> dict:
         ns = np.zeros(8, dtype=np.uint64)
