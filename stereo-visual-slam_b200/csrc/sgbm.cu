@@ -45,9 +45,11 @@ struct SgbmState {
     uint32_t* d_C;      // [chunk][H][W1][48] packed u16 pairs
     uint32_t* d_L[3];   // path costs from the row above; d_L[0] is overwritten with S4 = sat(L0+L1+L2+L3)
     int16_t* d_raw;     // [chunk][H][W]
+    uint2* d_rec;       // [chunk][H][W1] per-column records of the row sweep
     int16_t* d_med;
     int32_t* d_label;
     int32_t* d_size;
+    int32_t* d_runlen;
     uint8_t* d_img;     // host-entry staging: [2*chunk][H][pitch]
     int16_t* d_out;
     float* d_outf;
@@ -184,34 +186,88 @@ __global__ void __launch_bounds__(SG_TX* SG_NDP) sgbm_cost_kernel(const uint2* _
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One SGM step on a warp: lanes 0..23 hold disparities 4l..4l+3 as two s16x2 words (a0 = d, d+1; a1 = d+2, d+3),
-// lanes 24..31 hold SG_BIG2.  L(d) = C(d) + min(Lp(d), Lp(d-1) + P1, Lp(d+1) + P1, m + P2) - m,  m = min_k Lp(k).
-// Returns the new minimum over the warp.
+// One SGM step on a warp: lanes 0..23 hold disparities 4l..4l+3 as two s16x2 words (a0 = d, d+1; a1 = d+2, d+3).
+//   L(d) = C(d) + min(Lp(d), Lp(d-1) + P1, Lp(d+1) + P1, m + P2) - m,   m = min_k Lp(k)
+// `mm` carries m in both halves of a word (the CREDUX of a word whose halves are equal is monotone in that value,
+// so the reduction returns the next broadcast word directly).  Lanes 24..31 are padding: they are fed the cost
+// SG_CPAD so their values stay in [28000, 28000 + P2] -- above every reachable m + P2, below s16 overflow -- which
+// gives lane 23 its "no d+1 neighbour" and, through the rotating shuffle, lane 0 its "no d-1 neighbour" for free.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int sgm_step(uint32_t& a0, uint32_t& a1, int m, uint32_t c0, uint32_t c1, uint32_t P1b, int P2,
-                                        int lane) {
-    uint32_t up = __shfl_up_sync(0xffffffffu, a1, 1);
+#define SG_CPAD 0x6d606d60u  // 28000 | 28000 << 16
+
+__device__ __forceinline__ void sgm_step(uint32_t& a0, uint32_t& a1, uint32_t& mm, uint32_t c0, uint32_t c1, uint32_t P1b,
+                                         uint32_t P2b, int src_up) {
+    const uint32_t up = __shfl_sync(0xffffffffu, a1, src_up);  // lane - 1 (lane 0 reads padding lane 31)
     const uint32_t dn = __shfl_down_sync(0xffffffffu, a0, 1);
-    if (lane == 0) up = SG_BIG2;
     const uint32_t lm0 = __byte_perm(up, a0, 0x5432);  // (L[4l-1], L[4l])
     const uint32_t mid = __byte_perm(a0, a1, 0x5432);  // (L[4l+1], L[4l+2])
     const uint32_t lp1 = __byte_perm(a1, dn, 0x5432);  // (L[4l+3], L[4l+4])
-    const uint32_t mp2 = bcast16(m + P2), mm = bcast16(m);
+    const uint32_t mp2 = mm + P2b;
     const uint32_t t0 = __vmins2(__vmins2(__vadd2(__vmins2(lm0, mid), P1b), mp2), a0);
     const uint32_t t1 = __vmins2(__vmins2(__vadd2(__vmins2(mid, lp1), P1b), mp2), a1);
-    uint32_t r0 = c0 + t0 - mm, r1 = c1 + t1 - mm;  // halves stay in [0, 32767]: plain 32-bit arithmetic is exact
-    if (lane >= 24) r0 = r1 = SG_BIG2;
-    a0 = r0;
-    a1 = r1;
-    const uint32_t w = __vmins2(r0, r1);
-    return __reduce_min_sync(0xffffffffu, (int)min(w & 0xffffu, w >> 16));
+    a0 = c0 + t0 - mm;  // halves stay in [0, 32767]: plain 32-bit arithmetic is exact on the packed pairs
+    a1 = c1 + t1 - mm;
+    const uint32_t w = __vmins2(a0, a1);
+    mm = (uint32_t)__reduce_min_sync(0xffffffffu, (int)__vmins2(w, __byte_perm(w, w, 0x1032)));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // K20: the three paths that come from the row above.  blockIdx.y: 0 = from (x-1, y-1), 1 = from (x, y-1),
 // 2 = from (x+1, y-1).  Warp k starts at column k of row 0; a diagonal path that leaves the image re-enters on the
 // other side with a fresh (zero) predecessor, which is what OpenCV's zero-initialised border columns give.
+// The three sweeps of one pair run concurrently and touch row y at about the same time, so C is read with the
+// default policy (two of the three reads hit L2) while the path volumes are streamed out.
 // ---------------------------------------------------------------------------------------------------------------
+template <int DX>
+__device__ __forceinline__ void vertical_path(const uint2* __restrict__ C, uint2* __restrict__ Lo, int k, int W1, int H,
+                                              uint32_t P1b, uint32_t P2b, int lane) {
+    const bool active = lane < 24;
+    const int src_up = (lane + 31) & 31;
+    const uint32_t rowstep = (uint32_t)(W1 + DX) * 24u, wrapfix = (uint32_t)W1 * 24u;
+    auto advance = [&](uint32_t& off, int& x) {
+        x += DX;
+        off += rowstep;
+        if (DX > 0 && x == W1) {
+            x = 0;
+            off -= wrapfix;
+        }
+        if (DX < 0 && x < 0) {
+            x = W1 - 1;
+            off += wrapfix;
+        }
+    };
+    uint2 cb[SG_PF];
+    uint32_t offp = (uint32_t)k * 24u + lane;
+    int xp = k;
+#pragma unroll
+    for (int i = 0; i < SG_PF; ++i) {
+        cb[i] = make_uint2(SG_CPAD, SG_CPAD);
+        if (active && i < H) cb[i] = C[offp];
+        advance(offp, xp);
+    }
+    uint32_t a0 = active ? 0u : SG_BIG2, a1 = a0, mm = 0;
+    uint32_t off = (uint32_t)k * 24u + lane;
+    int x = k;
+    for (int y = 0; y < H; y += SG_PF) {
+#pragma unroll
+        for (int i = 0; i < SG_PF; ++i) {
+            const int yy = y + i;
+            if (yy < H) {
+                const uint2 c = cb[i];
+                if (active && yy + SG_PF < H) cb[i] = C[offp];
+                advance(offp, xp);
+                if (DX != 0 && x == (DX > 0 ? 0 : W1 - 1)) {
+                    a0 = a1 = active ? 0u : SG_BIG2;
+                    mm = 0;
+                }
+                sgm_step(a0, a1, mm, c.x, c.y, P1b, P2b, src_up);
+                if (active) __stcs(&Lo[off], make_uint2(a0, a1));
+                advance(off, x);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) sgbm_vertical_kernel(const uint32_t* __restrict__ Cvol, uint32_t* __restrict__ L0v,
                                                             uint32_t* __restrict__ L1v, uint32_t* __restrict__ L2v, int W1,
                                                             int H, int P1, int P2) {
@@ -219,92 +275,65 @@ __global__ void __launch_bounds__(256) sgbm_vertical_kernel(const uint32_t* __re
     const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (k >= W1) return;
     const int dir = blockIdx.y, pair = blockIdx.z;
-    const int dx = 1 - dir;  // +1, 0, -1
     const size_t vol = (size_t)pair * H * W1 * SG_NDP;
     const uint2* C = reinterpret_cast<const uint2*>(Cvol + vol);
-    uint2* Lo = reinterpret_cast<uint2*>((dir == 0 ? L0v : dir == 1 ? L1v : L2v) + vol);
-    const bool active = lane < 24;
-    const uint32_t P1b = bcast16(P1);
-    const int reset_x = dir == 0 ? 0 : dir == 2 ? W1 - 1 : -1;
-
-    uint2 cb[SG_PF];
-    int xp = k;  // column of the row being prefetched
-#pragma unroll
-    for (int i = 0; i < SG_PF; ++i) {
-        cb[i] = make_uint2(0, 0);
-        if (active && i < H) cb[i] = __ldcs(&C[((size_t)i * W1 + xp) * 24 + lane]);
-        xp += dx;
-        if (xp == W1) xp = 0;
-        if (xp < 0) xp = W1 - 1;
-    }
-    uint32_t a0 = active ? 0u : SG_BIG2, a1 = a0;
-    int m = 0, x = k;
-    for (int y = 0; y < H; y += SG_PF) {
-#pragma unroll
-        for (int i = 0; i < SG_PF; ++i) {
-            const int yy = y + i;
-            if (yy < H) {
-                const uint2 c = cb[i];
-                if (active && yy + SG_PF < H) cb[i] = __ldcs(&C[((size_t)(yy + SG_PF) * W1 + xp) * 24 + lane]);
-                xp += dx;
-                if (xp == W1) xp = 0;
-                if (xp < 0) xp = W1 - 1;
-                if (x == reset_x) {
-                    a0 = a1 = active ? 0u : SG_BIG2;
-                    m = 0;
-                }
-                m = sgm_step(a0, a1, m, c.x, c.y, P1b, P2, lane);
-                if (active) Lo[((size_t)yy * W1 + x) * 24 + lane] = make_uint2(a0, a1);
-                x += dx;
-                if (x == W1) x = 0;
-                if (x < 0) x = W1 - 1;
-            }
-        }
-    }
+    const uint32_t P1b = bcast16(P1), P2b = bcast16(P2);
+    if (dir == 0) vertical_path<1>(C, reinterpret_cast<uint2*>(L0v + vol), k, W1, H, P1b, P2b, lane);
+    else if (dir == 1) vertical_path<0>(C, reinterpret_cast<uint2*>(L1v + vol), k, W1, H, P1b, P2b, lane);
+    else vertical_path<-1>(C, reinterpret_cast<uint2*>(L2v + vol), k, W1, H, P1b, P2b, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // K21: one warp per image row.  Pass 1 walks left->right (path 0) and folds the four finished paths into
-// S4 = sat16(L0+L1+L2+L3) (written over L1's volume); pass 2 walks right->left (the fifth path of MODE_SGBM's single
-// pass), adds it, and does disparity selection exactly in OpenCV's order (descending x, so the right-image map sees
-// the same first writer on cost ties).
+// S4 = sat16(L0+L1+L2+L3) (written over the first path volume); pass 2 walks right->left (the fifth path of MODE_SGBM's
+// single pass), adds it and reduces every column to a record {min S, argmin, not-unique, S[best-1], S[best+1]}.
+// The per-column epilogue (right-image map, sub-pixel fit, LR check) then runs lane-parallel over x: OpenCV's
+// "first writer in descending x wins a cost tie" becomes an atomicMin on the key (minS << 12 | 4095 - x).
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SG_HW * 32) sgbm_horizontal_kernel(const uint32_t* __restrict__ Cvol, uint32_t* __restrict__ L0v,
                                                                     const uint32_t* __restrict__ L1v,
                                                                     const uint32_t* __restrict__ L2v, int W, int W1, int H,
-                                                                    SgParams p, int16_t* __restrict__ disp_raw) {
-    extern __shared__ int16_t sg_sm[];
+                                                                    SgParams p, uint2* __restrict__ rec_all,
+                                                                    int16_t* __restrict__ disp_raw) {
+    extern __shared__ uint32_t sg_sm[];
+    __shared__ uint2 s_excl[8];
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const int y = blockIdx.x * SG_HW + wp, pair = blockIdx.y;
+    if (threadIdx.x < 8) {
+        // 16-bit lanes of (d, d+1 | d+2, d+3) to ignore when the winner sits at local index e = t - 1
+        const uint2 tab[8] = {{0x0000ffffu, 0u}, {0xffffffffu, 0u}, {0xffffffffu, 0x0000ffffu}, {0xffff0000u, 0xffffffffu},
+                              {0u, 0xffffffffu}, {0u, 0xffff0000u}, {0u, 0u}, {0u, 0u}};
+        s_excl[threadIdx.x] = tab[threadIdx.x];
+    }
+    __syncthreads();
     if (y >= H) return;
-    const int Wp = (W + 1) & ~1;  // keeps s_S 4-byte aligned
-    int16_t* s_d1 = sg_sm + (size_t)wp * (3 * Wp + 2 * SG_D);
-    int16_t* s_d2 = s_d1 + Wp;
-    int16_t* s_c2 = s_d2 + Wp;
-    int16_t* s_S = s_c2 + Wp;  // [2][96]
+    uint32_t* s_key = sg_sm + (size_t)wp * W;  // right-image map: (cost << 12 | 4095 - x) of the best left pixel
     const size_t rowoff = ((size_t)pair * H + y) * W1 * 24;
-    const uint2* C = reinterpret_cast<const uint2*>(Cvol) + rowoff;
-    uint2* T = reinterpret_cast<uint2*>(L0v) + rowoff;
-    const uint2* LB = reinterpret_cast<const uint2*>(L1v) + rowoff;
-    const uint2* LC = reinterpret_cast<const uint2*>(L2v) + rowoff;
+    const uint2* C = reinterpret_cast<const uint2*>(Cvol) + rowoff + lane;
+    uint2* T = reinterpret_cast<uint2*>(L0v) + rowoff + lane;
+    const uint2* LB = reinterpret_cast<const uint2*>(L1v) + rowoff + lane;
+    const uint2* LC = reinterpret_cast<const uint2*>(L2v) + rowoff + lane;
+    uint2* rec = rec_all + ((size_t)pair * H + y) * W1;
     const bool active = lane < 24;
-    const uint32_t P1b = bcast16(p.P1);
+    const int src_up = (lane + 31) & 31;
+    const uint32_t P1b = bcast16(p.P1), P2b = bcast16(p.P2);
     const uint32_t SAT = 0x7fff7fffu;
+    const uint2 pad = make_uint2(SG_CPAD, SG_CPAD);
 
     // ---- pass 1: left -> right ----
     {
-        uint32_t a0 = active ? 0u : SG_BIG2, a1 = a0;
-        int m = 0;
+        uint32_t a0 = active ? 0u : SG_BIG2, a1 = a0, mm = 0;
         constexpr int PF = 4;
         uint2 cb[PF], l0b[PF], l1b[PF], l2b[PF];
 #pragma unroll
         for (int i = 0; i < PF; ++i) {
-            cb[i] = l0b[i] = l1b[i] = l2b[i] = make_uint2(0, 0);
+            cb[i] = pad;
+            l0b[i] = l1b[i] = l2b[i] = make_uint2(0, 0);
             if (active && i < W1) {
-                cb[i] = C[(size_t)i * 24 + lane];
-                l0b[i] = T[(size_t)i * 24 + lane];
-                l1b[i] = __ldcs(&LB[(size_t)i * 24 + lane]);
-                l2b[i] = __ldcs(&LC[(size_t)i * 24 + lane]);
+                cb[i] = C[i * 24];
+                l0b[i] = __ldcs(&T[i * 24]);
+                l1b[i] = __ldcs(&LB[i * 24]);
+                l2b[i] = __ldcs(&LC[i * 24]);
             }
         }
         for (int x = 0; x < W1; x += PF) {
@@ -314,43 +343,40 @@ __global__ void __launch_bounds__(SG_HW * 32) sgbm_horizontal_kernel(const uint3
                 if (xx < W1) {
                     const uint2 c = cb[i], l0 = l0b[i], l1 = l1b[i], l2 = l2b[i];
                     if (active && xx + PF < W1) {
-                        cb[i] = C[(size_t)(xx + PF) * 24 + lane];
-                        l0b[i] = T[(size_t)(xx + PF) * 24 + lane];
-                        l1b[i] = __ldcs(&LB[(size_t)(xx + PF) * 24 + lane]);
-                        l2b[i] = __ldcs(&LC[(size_t)(xx + PF) * 24 + lane]);
+                        cb[i] = C[(xx + PF) * 24];
+                        l0b[i] = __ldcs(&T[(xx + PF) * 24]);
+                        l1b[i] = __ldcs(&LB[(xx + PF) * 24]);
+                        l2b[i] = __ldcs(&LC[(xx + PF) * 24]);
                     }
-                    m = sgm_step(a0, a1, m, c.x, c.y, P1b, p.P2, lane);
+                    sgm_step(a0, a1, mm, c.x, c.y, P1b, P2b, src_up);
                     // three paths <= 3 * (15309 + P2) < 65536: exact in u16; then saturate like CostType
                     uint2 s;
                     s.x = __vminu2(__vminu2(l0.x + l1.x + l2.x, SAT) + a0, SAT);
                     s.y = __vminu2(__vminu2(l0.y + l1.y + l2.y, SAT) + a1, SAT);
-                    if (active) T[(size_t)xx * 24 + lane] = s;
+                    if (active) T[xx * 24] = s;
                 }
             }
         }
     }
-    for (int i = lane; i < W; i += 32) {
-        s_d1[i] = SG_INVALID;
-        s_d2[i] = SG_INVALID;
-        s_c2[i] = SG_MAXCOST;
-    }
-    __syncwarp();
-    // ---- pass 2: right -> left + disparity selection ----
+    for (int i = lane; i < W; i += 32) s_key[i] = 0xffffffffu;
+    // ---- pass 2: right -> left, per-column record ----
     {
-        uint32_t a0 = active ? 0u : SG_BIG2, a1 = a0;
-        int m = 0;
-        constexpr int PF = 4;
+        uint32_t a0 = active ? 0u : SG_BIG2, a1 = a0, mm = 0;
+        constexpr int PF = 8;
         uint2 cb[PF], tb[PF];
 #pragma unroll
         for (int i = 0; i < PF; ++i) {
-            cb[i] = tb[i] = make_uint2(0, 0);
+            cb[i] = pad;
+            tb[i] = make_uint2(0, 0);
             const int xx = W1 - 1 - i;
             if (active && xx >= 0) {
-                cb[i] = __ldcs(&C[(size_t)xx * 24 + lane]);
-                tb[i] = __ldcs(&T[(size_t)xx * 24 + lane]);
+                cb[i] = __ldcs(&C[xx * 24]);
+                tb[i] = __ldcs(&T[xx * 24]);
             }
         }
-        const int uq = 100 - p.uniq;
+        const uint32_t uq = 100 - p.uniq;
+        const uint64_t uq_magic = ((1ull << 40) / uq) + 1;  // floor(n / uq) = n * magic >> 40 for n < 2^33
+        const uint32_t d0 = 4 * lane;
         for (int x = W1 - 1; x >= 0; x -= PF) {
 #pragma unroll
             for (int i = 0; i < PF; ++i) {
@@ -358,60 +384,67 @@ __global__ void __launch_bounds__(SG_HW * 32) sgbm_horizontal_kernel(const uint3
                 if (xx >= 0) {
                     const uint2 c = cb[i], tt = tb[i];
                     if (active && xx - PF >= 0) {
-                        cb[i] = __ldcs(&C[(size_t)(xx - PF) * 24 + lane]);
-                        tb[i] = __ldcs(&T[(size_t)(xx - PF) * 24 + lane]);
+                        cb[i] = __ldcs(&C[(xx - PF) * 24]);
+                        tb[i] = __ldcs(&T[(xx - PF) * 24]);
                     }
-                    m = sgm_step(a0, a1, m, c.x, c.y, P1b, p.P2, lane);
+                    sgm_step(a0, a1, mm, c.x, c.y, P1b, P2b, src_up);
                     const uint32_t S0 = __vminu2(tt.x + a0, SAT), S1 = __vminu2(tt.y + a1, SAT);
-                    const int d0 = 4 * lane;
-                    const int s0 = S0 & 0xffff, s1 = S0 >> 16, s2 = S1 & 0xffff, s3 = S1 >> 16;
-                    uint32_t key = min(min((uint32_t)s0 << 8 | d0, (uint32_t)s1 << 8 | (d0 + 1)),
-                                       min((uint32_t)s2 << 8 | (d0 + 2), (uint32_t)s3 << 8 | (d0 + 3)));
+                    uint32_t key = min(min((S0 & 0xffffu) << 8 | d0, (S0 >> 16) << 8 | (d0 + 1)),
+                                       min((S1 & 0xffffu) << 8 | (d0 + 2), (S1 >> 16) << 8 | (d0 + 3)));
                     if (!active) key = 0xffffffffu;
                     key = __reduce_min_sync(0xffffffffu, key);
-                    const int minS = key >> 8, bestd = key & 0xff;
-                    const int thr = minS * 100;
-                    bool nu = (s0 * uq < thr && abs(bestd - d0) > 1) || (s1 * uq < thr && abs(bestd - d0 - 1) > 1) ||
-                              (s2 * uq < thr && abs(bestd - d0 - 2) > 1) || (s3 * uq < thr && abs(bestd - d0 - 3) > 1);
-                    nu = __any_sync(0xffffffffu, nu && active);
-                    uint32_t* sS = reinterpret_cast<uint32_t*>(s_S + (xx & 1) * SG_D);
-                    if (active) {
-                        sS[2 * lane] = S0;
-                        sS[2 * lane + 1] = S1;
-                    }
-                    __syncwarp();
-                    if (!nu && lane == 0) {
-                        const int16_t* Sp = s_S + (xx & 1) * SG_D;
-                        const int x2 = xx + SG_D - bestd;
-                        if (s_c2[x2] > minS) {
-                            s_c2[x2] = (int16_t)minS;
-                            s_d2[x2] = (int16_t)bestd;
-                        }
-                        int dd = bestd * 16;
-                        if (0 < bestd && bestd < SG_D - 1) {
-                            const int denom2 = max((int)Sp[bestd - 1] + Sp[bestd + 1] - 2 * minS, 1);
-                            dd += (((int)Sp[bestd - 1] - Sp[bestd + 1]) * 16 + denom2) / (denom2 * 2);
-                        }
-                        s_d1[xx + SG_D] = (int16_t)dd;
-                    }
+                    const uint32_t minS = key >> 8, bestd = key & 0xff;
+                    // uniqueness: some S(d) * (100 - u) < minS * 100 with |d - best| > 1  <=>  S(d) < ceil(minS * 100 / (100 - u))
+                    const uint32_t q = (uint32_t)(((uint64_t)(minS * 100u + uq - 1) * uq_magic) >> 40);
+                    const uint2 ex = s_excl[min(bestd - d0 + 1u, 6u)];
+                    const uint32_t z = __vminu2(S0 | ex.x, S1 | ex.y);
+                    const bool nu = __any_sync(0xffffffffu, active && min(z & 0xffffu, z >> 16) < q);
+                    // S(best - 1), S(best + 1) from their owner lanes
+                    const uint32_t im = bestd - 1, ip = bestd + 1;
+                    const uint32_t wm = (im & 2) ? S1 : S0, wq = (ip & 2) ? S1 : S0;
+                    const uint32_t Sm = __shfl_sync(0xffffffffu, wm >> ((im & 1) * 16), (im >> 2) & 31) & 0xffffu;
+                    const uint32_t Sp = __shfl_sync(0xffffffffu, wq >> ((ip & 1) * 16), (ip >> 2) & 31) & 0xffffu;
+                    if (lane == 0) rec[xx] = make_uint2(minS | bestd << 16 | (nu ? 0x80000000u : 0u), Sm | Sp << 16);
                 }
             }
         }
     }
     __syncwarp();
-    // ---- left-right consistency + write-out ----
+    // ---- lane-parallel epilogue: right-image map ----
+    for (int xx = lane; xx < W1; xx += 32) {
+        const uint32_t r0 = rec[xx].x;
+        const uint32_t minS = r0 & 0xffffu, bestd = (r0 >> 16) & 0xffu;
+        // OpenCV: if (disp2cost[x2] > minS) with disp2cost initialised to MAX_COST
+        if (!(r0 >> 31) && minS < SG_MAXCOST) atomicMin(&s_key[xx + SG_D - bestd], minS << 12 | (4095u - xx));
+    }
+    __syncwarp();
+    // ---- sub-pixel fit, left-right consistency, write-out ----
     int16_t* out = disp_raw + ((size_t)pair * H + y) * W;
-    for (int xx = lane; xx < W; xx += 32) {
-        int d1 = s_d1[xx];
-        if (d1 != SG_INVALID) {
-            const int dl = d1 >> 4, dh = (d1 + 15) >> 4;
-            const int xa = xx - dl, xb = xx - dh;
-            if (xa >= 0 && xa < W && xb >= 0 && xb < W) {
-                const int ea = s_d2[xa], eb = s_d2[xb];
-                if (ea >= 0 && abs(ea - dl) > p.disp12 && eb >= 0 && abs(eb - dh) > p.disp12) d1 = SG_INVALID;
+    for (int xi = lane; xi < W; xi += 32) {
+        int d1 = SG_INVALID;
+        if (xi >= SG_D) {
+            const uint2 r = rec[xi - SG_D];
+            if (!(r.x >> 31)) {
+                const int minS = r.x & 0xffffu, bestd = (r.x >> 16) & 0xffu;
+                d1 = bestd * 16;
+                if (0 < bestd && bestd < SG_D - 1) {
+                    const int Sm = r.y & 0xffffu, Sp = r.y >> 16;
+                    const int denom2 = max(Sm + Sp - 2 * minS, 1);
+                    d1 += ((Sm - Sp) * 16 + denom2) / (denom2 * 2);
+                }
+                const int dl = d1 >> 4, dh = (d1 + 15) >> 4;
+                const int xa = xi - dl, xb = xi - dh;
+                if (xa >= 0 && xb >= 0) {  // xa, xb <= xi < W
+                    const uint32_t ka = s_key[xa], kb = s_key[xb];
+                    if (ka != 0xffffffffu && kb != 0xffffffffu) {
+                        // disparity stored in the right-image map = x_left - x_right
+                        const int ea = (int)(4095u - (ka & 0xfffu)) + SG_D - xa, eb = (int)(4095u - (kb & 0xfffu)) + SG_D - xb;
+                        if (abs(ea - dl) > p.disp12 && abs(eb - dh) > p.disp12) d1 = SG_INVALID;
+                    }
+                }
             }
         }
-        out[xx] = (int16_t)d1;
+        out[xi] = (int16_t)d1;
     }
 }
 
@@ -477,42 +510,83 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
     }
 }
 
-__global__ void __launch_bounds__(256) speckle_init_kernel(const int16_t* __restrict__ d, int* __restrict__ label,
-                                                           int* __restrict__ size, int n, int hw) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    label[i] = d[i] != SG_INVALID ? i % hw : -1;  // labels are pixel indices inside their own image
-    size[i] = 0;
+// One warp per row: every pixel is labelled with the first pixel of its horizontal run (ballot + clz, carried across
+// 32-pixel chunks), so the union-find forest starts with one node per run instead of one per pixel.
+__global__ void __launch_bounds__(256) speckle_runs_kernel(const int16_t* __restrict__ d, int* __restrict__ label,
+                                                           int* __restrict__ size, int* __restrict__ runlen, int W, int H,
+                                                           int n_rows, int max_diff) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);  // row over all images
+    if (row >= n_rows) return;
+    const int16_t* p = d + (size_t)row * W;
+    const int base = (row % H) * W;  // labels are pixel indices inside their own image
+    int* L = label + (size_t)row * W;
+    int* S = size + (size_t)row * W;
+    int* R = runlen + (size_t)row * W;
+    int carry_start = -1;       // start of the run that reaches into this chunk from the left
+    int prev_last = SG_INVALID; // value of the last pixel of the previous chunk
+    for (int x0 = 0; x0 < W; x0 += 32) {
+        const int x = x0 + lane;
+        const int v = x < W ? p[x] : SG_INVALID;
+        int left = __shfl_up_sync(0xffffffffu, v, 1);
+        if (lane == 0) left = prev_last;
+        const bool valid = v != SG_INVALID;
+        const bool conn = valid && left != SG_INVALID && abs(v - left) <= max_diff && x > 0;
+        const unsigned starts = __ballot_sync(0xffffffffu, valid && !conn);
+        const unsigned below = starts & (0xffffffffu >> (31 - lane));
+        const int start = below ? x0 + 31 - __clz(below) : carry_start;
+        // is this pixel the last of its run?  (next pixel not connected to it)
+        int nv = __shfl_down_sync(0xffffffffu, v, 1);
+        int nx_valid_conn;
+        if (lane == 31 || x + 1 >= W) {
+            const int nxt = x + 1 < W ? p[x + 1] : SG_INVALID;
+            nv = nxt;
+        }
+        nx_valid_conn = valid && nv != SG_INVALID && abs(nv - v) <= max_diff && x + 1 < W;
+        if (x < W) {
+            L[x] = valid ? base + start : -1;
+            S[x] = 0;
+            R[x] = 0;
+        }
+        __syncwarp();
+        if (valid && !nx_valid_conn) R[start] = x - start + 1;
+        carry_start = __shfl_sync(0xffffffffu, start, 31);
+        if (!__shfl_sync(0xffffffffu, (int)valid, 31)) carry_start = -1;
+        prev_last = __shfl_sync(0xffffffffu, v, 31);
+    }
 }
 
+// vertical links between runs; a link is skipped when the pixel to the left already made it
 __global__ void __launch_bounds__(256) speckle_merge_kernel(const int16_t* __restrict__ d, int* __restrict__ label, int W, int H,
                                                             int max_diff) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= W) return;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y + 1;
+    if (x >= W || y >= H) return;
     const size_t img = (size_t)blockIdx.z * H * W;
     const int16_t* p = d + img;
     int* L = label + img;
     const int i = y * W + x;
-    const int v = p[i];
-    if (v == SG_INVALID) return;
-    if (x + 1 < W) {
-        const int r = p[i + 1];
-        if (r != SG_INVALID && abs(v - r) <= max_diff) uf_union(L, i, i + 1);
+    const int v = p[i], u = p[i - W];
+    if (v == SG_INVALID || u == SG_INVALID || abs(v - u) > max_diff) return;
+    if (x > 0) {
+        const int vl = p[i - 1], ul = p[i - W - 1];
+        if (vl != SG_INVALID && ul != SG_INVALID && abs(v - vl) <= max_diff && abs(u - ul) <= max_diff &&
+            abs(vl - ul) <= max_diff)
+            return;
     }
-    if (y + 1 < H) {
-        const int b = p[i + W];
-        if (b != SG_INVALID && abs(v - b) <= max_diff) uf_union(L, i, i + W);
-    }
+    uf_union(L, L[i], L[i - W]);
 }
 
-__global__ void __launch_bounds__(256) speckle_count_kernel(int* __restrict__ label, int* __restrict__ size, int hw) {
+// every run adds its length to its component's root
+__global__ void __launch_bounds__(256) speckle_count_kernel(int* __restrict__ label, int* __restrict__ size,
+                                                            const int* __restrict__ runlen, int hw) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= hw) return;
     const size_t img = (size_t)blockIdx.y * hw;
+    const int n = runlen[img + i];
+    if (n == 0) return;
     int* L = label + img;
-    if (L[i] < 0) return;
     const int r = uf_find(L, i);
-    atomicAdd(&size[img + r], 1);
+    atomicAdd(&size[img + r], n);
 }
 
 __global__ void __launch_bounds__(256) speckle_apply_kernel(const int16_t* __restrict__ d, const int* __restrict__ label,
@@ -523,7 +597,7 @@ __global__ void __launch_bounds__(256) speckle_apply_kernel(const int16_t* __res
     const size_t img = (size_t)blockIdx.y * hw;
     int v = d[img + i];
     if (max_size > 0 && v != SG_INVALID) {
-        int r = i;
+        int r = label[img + i];
         while (true) {
             const int pr = label[img + r];
             if (pr == r) break;
@@ -548,9 +622,11 @@ static void sgbm_release(SgbmState* s) {
     cudaFree(s->d_C);
     for (int i = 0; i < 3; ++i) cudaFree(s->d_L[i]);
     cudaFree(s->d_raw);
+    cudaFree(s->d_rec);
     cudaFree(s->d_med);
     cudaFree(s->d_label);
     cudaFree(s->d_size);
+    cudaFree(s->d_runlen);
     cudaFree(s->d_img);
     cudaFree(s->d_out);
     cudaFree(s->d_outf);
@@ -580,9 +656,11 @@ static int sgbm_reserve(vslam_ctx* ctx, int pairs, int w, int h) {
     VSLAM_CUDA(ctx, cudaMalloc(&s->d_C, pairs * vol));
     for (int i = 0; i < 3; ++i) VSLAM_CUDA(ctx, cudaMalloc(&s->d_L[i], pairs * vol));
     VSLAM_CUDA(ctx, cudaMalloc(&s->d_raw, pairs * px * sizeof(int16_t)));
+    VSLAM_CUDA(ctx, cudaMalloc(&s->d_rec, pairs * px * sizeof(uint2)));
     VSLAM_CUDA(ctx, cudaMalloc(&s->d_med, pairs * px * sizeof(int16_t)));
     VSLAM_CUDA(ctx, cudaMalloc(&s->d_label, pairs * px * sizeof(int32_t)));
     VSLAM_CUDA(ctx, cudaMalloc(&s->d_size, pairs * px * sizeof(int32_t)));
+    VSLAM_CUDA(ctx, cudaMalloc(&s->d_runlen, pairs * px * sizeof(int32_t)));
     VSLAM_CUDA(ctx, cudaMalloc(&s->d_img, 2 * (size_t)pairs * h * s->pitch));
     VSLAM_CUDA(ctx, cudaMalloc(&s->d_out, pairs * px * sizeof(int16_t)));
     VSLAM_CUDA(ctx, cudaMalloc(&s->d_outf, pairs * px * sizeof(float)));
@@ -621,8 +699,11 @@ static int sgbm_check(const vslam_sgbm_params* in, int w, int h, SgParams* out) 
     out->ftzero = (p.pre_filter_cap > 15 ? p.pre_filter_cap : 15) | 1;
     out->speckle_window = p.speckle_window_size;
     out->speckle_diff = 16 * p.speckle_range;
-    // packed s16 arithmetic needs 81*189 + P2 + P1 < 30000 and ftzero <= 127 (u8 operands)
-    if (out->P2 + out->P1 + 81 * 189 >= 30000 || out->ftzero > 127 || out->uniq > 100) return VSLAM_E_INVALID;
+    // packed s16 arithmetic: real costs stay below 81*189 + P2 + P1 < 28000, padding lanes sit at 28000 .. 28000 + P2
+    // and must survive + P1 without s16 overflow; ftzero <= 127 (u8 operands); the row sweep packs x into 12 bits
+    if (out->P2 + out->P1 + 81 * 189 >= 28000 || 28000 + out->P2 + out->P1 > 32767 || out->ftzero > 127 ||
+        out->uniq >= 100 || w - SG_D > 4096)
+        return VSLAM_E_INVALID;
     return VSLAM_OK;
 }
 
@@ -648,11 +729,11 @@ static int sgbm_enqueue(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "sgbm_vertical_kernel");
     if (s->stop_after == 1) return VSLAM_OK;
-    const size_t smem = (size_t)SG_HW * (3 * ((w + 1) & ~1) + 2 * SG_D) * sizeof(int16_t);
+    const size_t smem = (size_t)SG_HW * w * sizeof(uint32_t);
     VSLAM_CUDA(ctx, cudaFuncSetAttribute(sgbm_horizontal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     vslam_time_begin(ctx, VK_SGBM_HORIZONTAL);
     sgbm_horizontal_kernel<<<dim3(ceil_div(h, SG_HW), n), SG_HW * 32, smem, st>>>(s->d_C, s->d_L[0], s->d_L[1], s->d_L[2], w, W1, h, p,
-                                                                                  s->d_raw);
+                                                                                  s->d_rec, s->d_raw);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "sgbm_horizontal_kernel");
     const int hw = w * h;
@@ -660,10 +741,12 @@ static int sgbm_enqueue(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_
     sgbm_median_kernel<<<dim3(ceil_div(w, 256), h, n), 256, 0, st>>>(s->d_raw, s->d_med, w, h);
     ctx->launches++;
     if (p.speckle_window > 0) {
-        speckle_init_kernel<<<ceil_div(n * hw, 256), 256, 0, st>>>(s->d_med, s->d_label, s->d_size, n * hw, hw);
-        speckle_merge_kernel<<<dim3(ceil_div(w, 256), h, n), 256, 0, st>>>(s->d_med, s->d_label, w, h, p.speckle_diff);
-        speckle_count_kernel<<<dim3(ceil_div(hw, 256), n), 256, 0, st>>>(s->d_label, s->d_size, hw);
-        ctx->launches += 3;
+        speckle_runs_kernel<<<ceil_div(n * h, 8), 256, 0, st>>>(s->d_med, s->d_label, s->d_size, s->d_runlen, w, h, n * h,
+                                                               p.speckle_diff);
+        if (h > 1)
+            speckle_merge_kernel<<<dim3(ceil_div(w, 256), h - 1, n), 256, 0, st>>>(s->d_med, s->d_label, w, h, p.speckle_diff);
+        speckle_count_kernel<<<dim3(ceil_div(hw, 256), n), 256, 0, st>>>(s->d_label, s->d_size, s->d_runlen, hw);
+        ctx->launches += h > 1 ? 3 : 2;
     }
     speckle_apply_kernel<<<dim3(ceil_div(hw, 256), n), 256, 0, st>>>(s->d_med, s->d_label, s->d_size, hw, p.speckle_window, d_disp16,
                                                                     d_dispf);

@@ -14,7 +14,9 @@ ctx = pkg.Context(max_images=2, max_keypoints=2048)
 dev = torch.device("cuda:0")
 dl, dr = torch.from_numpy(L).to(dev), torch.from_numpy(R).to(dev)
 d16 = torch.empty((B, H, W), dtype=torch.int16, device=dev)
-ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+stream = torch.cuda.Stream()
+ctx.set_stream(stream.cuda_stream)
+torch.cuda.set_stream(stream)
 for _ in range(2):
     ctx.sgbm_compute_dev(dl, dr, B, W, H, W, W * H, d16)
 torch.cuda.synchronize()
