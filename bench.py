@@ -353,9 +353,67 @@ def run_ours(args, rank, world, local_rank):
             line["ba"] = bench_ba(ctx, pkg, args)
         except Exception as ex:  # the BA numbers are secondary; never lose the headline line
             line["ba"] = {"error": repr(ex)}
+    if args.sgbm:
+        try:
+            line["sgbm"] = bench_sgbm(ctx, pkg, torch, dev, stream, sets[0][2][:8], sets[0][3][:8], peak)
+        except Exception as ex:
+            line["sgbm"] = {"error": repr(ex)}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def bench_sgbm(ctx, pkg, torch, dev, stream, dl, dr, hbm_peak):
+    """Dense stereo (VO::disparity_map, the reference's StereoSGBM call, visual_odometry.cpp:163-168): device-resident
+    throughput on a batch of 8 pairs, single-pair latency through the host-buffer C-ABI call, per-kernel algorithmic
+    HBM rates (one u16 volume = H x (W-96) x 96 x 2 B per pair) and live cv2.StereoSGBM beside it."""
+    import cv2
+    B = int(dl.shape[0])
+    d16 = torch.empty((B, H, W), dtype=torch.int16, device=dev)
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            ctx.sgbm_compute_dev(dl, dr, B, W, H, W, W * H, d16)
+    torch.cuda.synchronize(dev)
+    ctx.timing_enable(True)
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(reps):
+            ctx.sgbm_compute_dev(dl, dr, B, W, H, W, W * H, d16)
+        e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    kt = {k: v for k, v in ctx.timing_read().items() if k.startswith("sgbm")}
+    ctx.timing_enable(False)
+    vol = H * (W - 96) * 96 * 2
+    # algorithmic volume transfers per pair: cost writes C; vertical reads C once and writes 3 path volumes;
+    # horizontal reads C + 3 paths, writes S4, then reads C + S4
+    alg = {"sgbm_cost_kernel": 1 * vol, "sgbm_vertical_kernel": 4 * vol, "sgbm_horizontal_kernel": 7 * vol}
+    kern = {}
+    for k, (tot, n) in kt.items():
+        per = tot / max(n, 1)
+        kern[k] = {"ms_per_launch": per}
+        if k in alg:
+            gbs = alg[k] * B / (per * 1e-3) / 1e9
+            kern[k].update({"algorithmic_GBps": gbs, "hbm_frac": gbs / hbm_peak})
+    hl, hr = dl[0].cpu().numpy(), dr[0].cpu().numpy()
+    ctx.sgbm_compute(hl, hr)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        one = ctx.sgbm_compute(hl, hr)
+    lat_ms = (time.perf_counter() - t0) / 5 * 1e3
+    sg = cv2.StereoSGBM_create(0, 96, 9, 8 * 81, 32 * 81, 1, 63, 10, 100, 32)
+    ref = sg.compute(hl, hr)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        sg.compute(hl, hr)
+    cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+    return {"workload": f"cv::StereoSGBM(0,96,9,648,2592,1,63,10,100,32) on {B} synthetic 1241x376 pairs per launch",
+            "pairs_per_s_device": B / (ms * 1e-3), "ms_per_pair_device": ms / B,
+            "single_pair_e2e_ms": lat_ms, "cv2_ms_per_pair": cpu_ms, "cv2_threads": cv2.getNumThreads(),
+            "bit_exact_vs_cv2": bool(np.array_equal(one, ref) and np.array_equal(d16[0].cpu().numpy(), ref)),
+            "kernels": kern}
 
 
 def bench_ba(ctx, pkg, args):
@@ -400,6 +458,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-ba", dest="ba", action="store_false")
+    ap.add_argument("--no-sgbm", dest="sgbm", action="store_false")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -2,7 +2,7 @@
 // (/root/reference/src/run_vslam.cpp:17-92): per frame VO::pipeline(), and after every keyframe insertion with a full
 // window optimize_map(5) x2 (outlier relabel only), optimize_map(10) with pose write-back and optimize_pose_only(10).
 //
-//   run_vslam <dataset_dir/> <n_frames> [--no-ba] [--nfeatures N] [--anms K]
+//   run_vslam <dataset_dir/> <n_frames> [--no-ba] [--nfeatures N] [--anms K] [--dense]
 // reads <dataset_dir>/image_{0,1}/%06d.pgm, appends evicted / remaining keyframe poses to ./estimated_traj.txt
 // (the reference's format) and prints one "frame <id> <12 numbers of T_w_c> <inliers> <is_keyframe>" line per frame.
 #include <cstdio>
@@ -17,15 +17,16 @@
 
 int main(int argc, char** argv) {
     if (argc < 3) {
-        std::fprintf(stderr, "usage: run_vslam <dataset_dir/> <n_frames> [--no-ba] [--nfeatures N] [--anms K]\n");
+        std::fprintf(stderr, "usage: run_vslam <dataset_dir/> <n_frames> [--no-ba] [--nfeatures N] [--anms K] [--dense]\n");
         return 2;
     }
     const std::string dataset = argv[1];
     const int n_frames = std::atoi(argv[2]);
-    bool do_ba = true;
+    bool do_ba = true, dense = false;
     int nfeatures = 3000, anms = 500;
     for (int i = 3; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--no-ba")) do_ba = false;
+        else if (!std::strcmp(argv[i], "--dense")) dense = true;  // the reference's StereoSGBM depth source
         else if (!std::strcmp(argv[i], "--nfeatures") && i + 1 < argc) nfeatures = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--anms") && i + 1 < argc) anms = std::atoi(argv[++i]);
     }
@@ -38,6 +39,7 @@ int main(int argc, char** argv) {
     vslam::VO my_VO(dataset, nh, my_map);
     my_VO.detector_nfeatures_ = nfeatures;
     my_VO.anms_keep_ = anms;
+    my_VO.dense_stereo_ = dense;
 
     const double fx = 718.856, fy = 718.856, cx = 607.1928, cy = 185.2157;
     cv::Mat K = (cv::Mat_<double>(3, 3) << fx, 0, cx, 0, fy, cy, 0, 0, 1);

@@ -33,6 +33,9 @@ public:
     int detector_nfeatures_ = 3000;  // cv::ORB::create(3000), visual_odometry.cpp:22,31
     int anms_keep_ = 500;            // adaptive_non_maximal_suppresion(keypoints, 500), visual_odometry.cpp:82
     vslam_ctx* ctx_ = nullptr;       // owned
+    // depth source of disparity_map: false = sparse stereo (ORB on both images + L<->R matching + DLT, the north
+    // star's triangulation), true = the reference's dense StereoSGBM (visual_odometry.cpp:163-168) on the GPU
+    bool dense_stereo_ = false;
 
     int num_inliers_ = 0;
     SE3 T_c_l_ = SE3();
@@ -59,9 +62,10 @@ public:
     VO& operator=(const VO&) = delete;
 
     int read_img(int id, cv::Mat& left_img, cv::Mat& right_img);
-    // reference: dense SGBM.  Here: SPARSE disparity -- ORB on both images, L<->R feature_matching, per-match DLT;
-    // `disparity` is CV_32F, -1 everywhere except at the (truncated) pixel of every matched left keypoint, where it
-    // holds fx*b/Z, so Frame::find_3d and set_ref_3d_position work unchanged.
+    // reference: dense SGBM (dense_stereo_ = true reproduces it bit-exactly).  Default: SPARSE disparity -- ORB on
+    // both images, L<->R feature_matching, per-match DLT; `disparity` is CV_32F, -1 everywhere except at the
+    // (truncated) pixel of every matched left keypoint, where it holds fx*b/Z, so Frame::find_3d and
+    // set_ref_3d_position work unchanged in both modes.
     int disparity_map(const Frame& frame, cv::Mat& disparity);
     bool initialization();
     bool tracking(bool& if_insert_keyframe);

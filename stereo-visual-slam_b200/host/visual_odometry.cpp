@@ -137,6 +137,15 @@ int VO::disparity_map(const Frame& frame, cv::Mat& disparity) {
     const cv::Mat& L = frame.left_img_;
     const cv::Mat& R = frame.right_img_;
     if (!L.data || !R.data) return -1;
+    if (dense_stereo_) {
+        // the reference's own path (visual_odometry.cpp:163-168): StereoSGBM(0, 96, 9, 8*81, 32*81, 1, 63, 10, 100, 32)
+        // followed by convertTo(CV_32F, 1/16); both happen on the device, bit-exact against cv2 4.13
+        disparity.create(L.rows, L.cols, cv::CV_32F);
+        check(vslam_sgbm_compute(ctx_, L.data, R.data, 1, L.cols, L.rows, (int)L.step, (long long)L.step * L.rows, nullptr,
+                                 nullptr, reinterpret_cast<float*>(disparity.data)),
+              "vslam_sgbm_compute");
+        return 0;
+    }
     const int cap = vslam_orb_keypoint_capacity(ctx_);
     std::vector<vslam_keypoint> kp(2 * (size_t)cap);
     std::vector<uint8_t> desc(2 * (size_t)cap * 32), flags(cap);

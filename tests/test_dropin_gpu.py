@@ -65,3 +65,15 @@ def test_full_pipeline_with_ba(sequence, tmp_path):
     ids2, T2, meta2, _ = _run(seq_dir, n, tmp_path, "--nfeatures", "1000", "--anms", "110", "--no-ba")
     err2 = np.abs(T2[:, :, 3] - t[:n]).max(axis=1)
     assert err.max() < err2.max() + 0.05
+
+
+def test_vo_with_dense_stereo_like_the_reference(sequence, tmp_path):
+    """--dense: VO::disparity_map = StereoSGBM on the GPU (the reference's depth source, visual_odometry.cpp:163-168)"""
+    seq_dir, n, t = sequence
+    ids, T, meta, out = _run(seq_dir, n, tmp_path, "--dense")
+    assert len(ids) == n and (ids == np.arange(n)).all(), out
+    assert "VO IS LOST" not in out and "Rejected" not in out
+    assert (meta[1:, 0] >= 10).all()
+    err = np.abs(T[:, :, 3] - t[:n]).max(axis=1)
+    assert err.max() < 0.05, err
+    assert np.abs(T[:, :, :3] - np.eye(3)).max() < 5e-3

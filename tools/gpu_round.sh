@@ -13,6 +13,8 @@ if [ "$1" == "ncu" ]; then
 fi
 if [ "$2" == "full" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k "regex:fast_kernel|blur_kernel|describe_kernel|hamming_argmin|harris_select|resize_level|triangulate|crosscheck" -s 15 -c 15 -f -o gpurun_out/full python tools/profile_frontend.py 32 2 > gpurun_out/ncu_full.log 2>&1
-  echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log; ls -la gpurun_out/*.ncu-rep
+  echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:sgbm|speckle" -s 9 -c 9 -f -o gpurun_out/sgbm_full python tools/profile_sgbm.py 8 2 > gpurun_out/ncu_sgbm.log 2>&1
+  echo "ncu sgbm rc=$?"; tail -2 gpurun_out/ncu_sgbm.log; ls -la gpurun_out/*.ncu-rep
 fi
 exit 0
