@@ -388,8 +388,8 @@ def bench_sgbm(ctx, pkg, torch, dev, stream, dl, dr, hbm_peak):
     ctx.timing_enable(False)
     vol = H * (W - 96) * 96 * 2
     # algorithmic volume transfers per pair: cost writes C; vertical reads C once and writes 3 path volumes;
-    # horizontal reads C + 3 paths, writes S4, then reads C + S4
-    alg = {"sgbm_cost_kernel": 1 * vol, "sgbm_vertical_kernel": 4 * vol, "sgbm_horizontal_kernel": 7 * vol}
+    # row-forward reads C + 3 paths and writes S4; row-backward reads C + S4
+    alg = {"sgbm_cost_kernel": 1 * vol, "sgbm_vertical_kernel": 4 * vol, "sgbm_row_forward_kernel": 5 * vol, "sgbm_row_backward_kernel": 2 * vol}
     kern = {}
     for k, (tot, n) in kt.items():
         per = tot / max(n, 1)

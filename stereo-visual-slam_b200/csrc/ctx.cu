@@ -101,7 +101,7 @@ static const char* const k_kernel_names[VK_COUNT] = {
     "resize_level_kernel", "fast_kernel", "harris_select_kernel", "blur_kernel", "anms_kernel", "describe_kernel",
     "hamming_argmin_kernel", "crosscheck_gate_compact_kernel", "triangulate_kernel", "ba_lm_kernel",
     "ba_solve_kernel", "ba_update_kernel", "ba_misc_kernel", "pnp_kernel", "sgbm_prefilter_kernel", "sgbm_cost_kernel",
-    "sgbm_vertical_kernel", "sgbm_horizontal_kernel", "sgbm_post_kernels"};
+    "sgbm_vertical_kernel", "sgbm_row_forward_kernel", "sgbm_row_backward_kernel", "sgbm_post_kernels"};
 
 extern "C" int vslam_kernel_count(void) { return VK_COUNT; }
 extern "C" const char* vslam_kernel_name(int id) { return id >= 0 && id < VK_COUNT ? k_kernel_names[id] : ""; }

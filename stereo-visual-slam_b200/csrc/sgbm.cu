@@ -11,8 +11,9 @@
 //   K19 sgbm_cost_kernel        BT pixel cost on both planes + 9x9 box sum (replicated borders) -> C[y][x][d] u16
 //   K20 sgbm_vertical_kernel    paths from the row above (up-left, up, up-right): one warp per path, diagonal paths
 //                               wrap around the image so every warp walks all H rows with no inter-warp traffic
-//   K21 sgbm_horizontal_kernel  one warp per row: left->right path, then right->left path fused with the winner-
-//                               take-all, uniqueness test, sub-pixel fit, right-image map and LR consistency check
+//   K21 sgbm_row_forward_kernel / sgbm_row_backward_kernel  one warp per row: left->right path, then right->left
+//                               path fused with the winner-take-all, uniqueness test, sub-pixel fit, right-image map
+//                               and LR consistency check
 //   K22 sgbm_median_kernel      cv::medianBlur(3)
 //   K23 speckle_*_kernel        cv::filterSpeckles as union-find connected components
 // 96 disparities are held as 48 packed s16x2 words; a path step is VIADD.16x2 / VIMNMX.S16x2 on 2 words per lane
@@ -32,8 +33,10 @@
 #define SG_BIG2 0x75307530u          // 30000 | 30000 << 16: "no predecessor" cost, > any reachable min + P2
 #define SG_MAXCOST 32767
 #define SG_INVALID (-16)
-#define SG_HW 4                      // rows (warps) per CTA of the horizontal kernel
+#define SG_HW 2                      // rows (warps) per CTA of the row sweeps
 #define SG_PF 8                      // rows the vertical sweep loads ahead
+#define SG_PF1 8                     // columns the row sweep loads ahead, pass 1 (4 volumes)
+#define SG_PF2 16                    // pass 2 (2 volumes)
 #define SG_CHUNK_PAIRS 8             // pairs per scratch chunk (8 x 331 MB)
 
 struct SgParams {
@@ -284,18 +287,144 @@ __global__ void __launch_bounds__(256) sgbm_vertical_kernel(const uint32_t* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K21: one warp per image row.  Pass 1 walks left->right (path 0) and folds the four finished paths into
+// K21: one warp per image row, two launches (each fits one resident wave).  Pass 1 walks left->right (path 0) and folds the four finished paths into
 // S4 = sat16(L0+L1+L2+L3) (written over the first path volume); pass 2 walks right->left (the fifth path of MODE_SGBM's
 // single pass), adds it and reduces every column to a record {min S, argmin, not-unique, S[best-1], S[best+1]}.
 // The per-column epilogue (right-image map, sub-pixel fit, LR check) then runs lane-parallel over x: OpenCV's
 // "first writer in descending x wins a cost tie" becomes an atomicMin on the key (minS << 12 | 4095 - x).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SG_HW * 32) sgbm_horizontal_kernel(const uint32_t* __restrict__ Cvol, uint32_t* __restrict__ L0v,
-                                                                    const uint32_t* __restrict__ L1v,
-                                                                    const uint32_t* __restrict__ L2v, int W, int W1, int H,
-                                                                    SgParams p, uint2* __restrict__ rec_all,
-                                                                    int16_t* __restrict__ disp_raw) {
-    extern __shared__ uint32_t sg_sm[];
+// ---- TMA bulk-copy plumbing (per-warp rings: every warp owns its stages and mbarriers) ---------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SG_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni SG_DONE;\n"
+        "bra.uni SG_WAIT;\n"
+        "SG_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+#define RS_CH 8                         // columns per bulk copy: 8 x 192 B = 1536 contiguous bytes per volume
+#define RS_NST 4                        // ring stages per warp
+#define RS_ARR (RS_CH * SG_D * 2)       // bytes of one volume's chunk
+#define RS_FWD_WARP (RS_NST * 4 * RS_ARR)
+#define RS_BWD_STAGES (RS_NST * 2 * RS_ARR)
+
+// The row sweeps stream each image row exactly once, 192 B per column per volume.  Issued as per-lane loads that is a
+// trickle of small requests from thousands of concurrent rows (poor DRAM page locality: measured 3.4 TB/s at best);
+// here one lane moves 1.5 KB chunks per volume with cp.async.bulk into a per-warp ring, completion on an mbarrier.
+__global__ void __launch_bounds__(SG_HW * 32) sgbm_row_forward_kernel(const uint32_t* __restrict__ Cvol, uint32_t* __restrict__ L0v,
+                                                                     const uint32_t* __restrict__ L1v,
+                                                                     const uint32_t* __restrict__ L2v, int W1, int H,
+                                                                     SgParams p) {
+    extern __shared__ __align__(128) unsigned char rs_smem[];
+    __shared__ uint64_t bars[SG_HW][RS_NST];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int y = blockIdx.x * SG_HW + wp, pair = blockIdx.y;
+    if (y >= H) return;
+    const size_t rowoff = ((size_t)pair * H + y) * W1 * (SG_D * 2);
+    const unsigned char* gC = reinterpret_cast<const unsigned char*>(Cvol) + rowoff;
+    unsigned char* gT = reinterpret_cast<unsigned char*>(L0v) + rowoff;
+    const unsigned char* gB = reinterpret_cast<const unsigned char*>(L1v) + rowoff;
+    const unsigned char* gD = reinterpret_cast<const unsigned char*>(L2v) + rowoff;
+    unsigned char* wbase = rs_smem + (size_t)wp * RS_FWD_WARP;
+    uint64_t* bar = bars[wp];
+    const bool active = lane < 24;
+    const int src_up = (lane + 31) & 31;
+    const uint32_t P1b = bcast16(p.P1), P2b = bcast16(p.P2);
+    const uint32_t SAT = 0x7fff7fffu;
+    const int n_chunks = (W1 + RS_CH - 1) / RS_CH;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < RS_NST; ++s) mbar_init(&bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int j) {  // lane 0
+        const int s = j % RS_NST, x0 = j * RS_CH;
+        const uint32_t bytes = (uint32_t)min(RS_CH, W1 - x0) * (SG_D * 2);
+        unsigned char* st = wbase + s * 4 * RS_ARR;
+        const size_t go = (size_t)x0 * (SG_D * 2);
+        mbar_expect_tx(&bar[s], 4 * bytes);
+        bulk_g2s(st, gC + go, bytes, &bar[s]);
+        bulk_g2s(st + RS_ARR, gT + go, bytes, &bar[s]);
+        bulk_g2s(st + 2 * RS_ARR, gB + go, bytes, &bar[s]);
+        bulk_g2s(st + 3 * RS_ARR, gD + go, bytes, &bar[s]);
+    };
+    if (lane == 0)
+        for (int j = 0; j < RS_NST - 1 && j < n_chunks; ++j) issue(j);
+    uint32_t a0 = active ? 0u : SG_BIG2, a1 = a0, mm = 0;
+    for (int j = 0; j < n_chunks; ++j) {
+        const int s = j % RS_NST, x0 = j * RS_CH, n = min(RS_CH, W1 - x0);
+        mbar_wait(&bar[s], (j / RS_NST) & 1);
+        uint2* sC = reinterpret_cast<uint2*>(wbase + s * 4 * RS_ARR) + lane;
+        uint2* sT = sC + RS_ARR / 8;
+        const uint2* sB = sT + RS_ARR / 8;
+        const uint2* sD = sB + RS_ARR / 8;
+#pragma unroll
+        for (int i = 0; i < RS_CH; ++i) {
+            if (i < n) {
+                uint2 c = make_uint2(SG_CPAD, SG_CPAD), l0 = make_uint2(0, 0), l1 = l0, l2 = l0;
+                if (active) {
+                    c = sC[i * 24];
+                    l0 = sT[i * 24];
+                    l1 = sB[i * 24];
+                    l2 = sD[i * 24];
+                }
+                sgm_step(a0, a1, mm, c.x, c.y, P1b, P2b, src_up);
+                // three paths <= 3 * (15309 + P2) < 65536: exact in u16; then saturate like CostType
+                uint2 o;
+                o.x = __vminu2(__vminu2(l0.x + l1.x + l2.x, SAT) + a0, SAT);
+                o.y = __vminu2(__vminu2(l0.y + l1.y + l2.y, SAT) + a1, SAT);
+                if (active) sT[i * 24] = o;
+            }
+        }
+        fence_async_smem();  // the S4 chunk was written through the generic proxy; the bulk store reads it through the async one
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g(gT + (size_t)x0 * (SG_D * 2), wbase + s * 4 * RS_ARR + RS_ARR, (uint32_t)n * (SG_D * 2));
+            bulk_commit();
+            if (j + RS_NST - 1 < n_chunks) {
+                bulk_wait_read<1>();  // the store of chunk j-1 has drained its stage: refill it
+                issue(j + RS_NST - 1);
+            }
+        }
+    }
+    if (lane == 0) bulk_wait_read<0>();
+}
+
+__global__ void __launch_bounds__(SG_HW * 32) sgbm_row_backward_kernel(const uint32_t* __restrict__ Cvol,
+                                                                      const uint32_t* __restrict__ L0v, int W, int W1, int H,
+                                                                      SgParams p, uint2* __restrict__ rec_all,
+                                                                      int16_t* __restrict__ disp_raw) {
+    extern __shared__ __align__(128) unsigned char rs_smem[];
+    __shared__ uint64_t bars[SG_HW][RS_NST];
     __shared__ uint2 s_excl[8];
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const int y = blockIdx.x * SG_HW + wp, pair = blockIdx.y;
@@ -307,85 +436,58 @@ __global__ void __launch_bounds__(SG_HW * 32) sgbm_horizontal_kernel(const uint3
     }
     __syncthreads();
     if (y >= H) return;
-    uint32_t* s_key = sg_sm + (size_t)wp * W;  // right-image map: (cost << 12 | 4095 - x) of the best left pixel
-    const size_t rowoff = ((size_t)pair * H + y) * W1 * 24;
-    const uint2* C = reinterpret_cast<const uint2*>(Cvol) + rowoff + lane;
-    uint2* T = reinterpret_cast<uint2*>(L0v) + rowoff + lane;
-    const uint2* LB = reinterpret_cast<const uint2*>(L1v) + rowoff + lane;
-    const uint2* LC = reinterpret_cast<const uint2*>(L2v) + rowoff + lane;
+    unsigned char* wbase = rs_smem + (size_t)wp * RS_BWD_STAGES;
+    uint32_t* s_key = reinterpret_cast<uint32_t*>(rs_smem + (size_t)SG_HW * RS_BWD_STAGES) + (size_t)wp * W;
+    uint64_t* bar = bars[wp];
+    const size_t rowoff = ((size_t)pair * H + y) * W1 * (SG_D * 2);
+    const unsigned char* gC = reinterpret_cast<const unsigned char*>(Cvol) + rowoff;
+    const unsigned char* gT = reinterpret_cast<const unsigned char*>(L0v) + rowoff;
     uint2* rec = rec_all + ((size_t)pair * H + y) * W1;
     const bool active = lane < 24;
     const int src_up = (lane + 31) & 31;
     const uint32_t P1b = bcast16(p.P1), P2b = bcast16(p.P2);
     const uint32_t SAT = 0x7fff7fffu;
-    const uint2 pad = make_uint2(SG_CPAD, SG_CPAD);
-
-    // ---- pass 1: left -> right ----
-    {
-        uint32_t a0 = active ? 0u : SG_BIG2, a1 = a0, mm = 0;
-        constexpr int PF = 4;
-        uint2 cb[PF], l0b[PF], l1b[PF], l2b[PF];
+    const int n_chunks = (W1 + RS_CH - 1) / RS_CH;
+    if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < PF; ++i) {
-            cb[i] = pad;
-            l0b[i] = l1b[i] = l2b[i] = make_uint2(0, 0);
-            if (active && i < W1) {
-                cb[i] = C[i * 24];
-                l0b[i] = __ldcs(&T[i * 24]);
-                l1b[i] = __ldcs(&LB[i * 24]);
-                l2b[i] = __ldcs(&LC[i * 24]);
-            }
-        }
-        for (int x = 0; x < W1; x += PF) {
-#pragma unroll
-            for (int i = 0; i < PF; ++i) {
-                const int xx = x + i;
-                if (xx < W1) {
-                    const uint2 c = cb[i], l0 = l0b[i], l1 = l1b[i], l2 = l2b[i];
-                    if (active && xx + PF < W1) {
-                        cb[i] = C[(xx + PF) * 24];
-                        l0b[i] = __ldcs(&T[(xx + PF) * 24]);
-                        l1b[i] = __ldcs(&LB[(xx + PF) * 24]);
-                        l2b[i] = __ldcs(&LC[(xx + PF) * 24]);
-                    }
-                    sgm_step(a0, a1, mm, c.x, c.y, P1b, P2b, src_up);
-                    // three paths <= 3 * (15309 + P2) < 65536: exact in u16; then saturate like CostType
-                    uint2 s;
-                    s.x = __vminu2(__vminu2(l0.x + l1.x + l2.x, SAT) + a0, SAT);
-                    s.y = __vminu2(__vminu2(l0.y + l1.y + l2.y, SAT) + a1, SAT);
-                    if (active) T[xx * 24] = s;
-                }
-            }
-        }
+        for (int s = 0; s < RS_NST; ++s) mbar_init(&bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = lane; i < W; i += 32) s_key[i] = 0xffffffffu;
-    // ---- pass 2: right -> left, per-column record ----
+    __syncwarp();
+    auto issue = [&](int j) {  // lane 0; chunk j counts from the right end of the row
+        const int s = j % RS_NST, x0 = (n_chunks - 1 - j) * RS_CH;
+        const uint32_t bytes = (uint32_t)min(RS_CH, W1 - x0) * (SG_D * 2);
+        unsigned char* st = wbase + s * 2 * RS_ARR;
+        const size_t go = (size_t)x0 * (SG_D * 2);
+        mbar_expect_tx(&bar[s], 2 * bytes);
+        bulk_g2s(st, gC + go, bytes, &bar[s]);
+        bulk_g2s(st + RS_ARR, gT + go, bytes, &bar[s]);
+    };
+    if (lane == 0)
+        for (int j = 0; j < RS_NST - 1 && j < n_chunks; ++j) issue(j);  // chunk j >= 1 tops the ring up with chunk j + NST - 2
+    // ---- right -> left, per-column record ----
     {
         uint32_t a0 = active ? 0u : SG_BIG2, a1 = a0, mm = 0;
-        constexpr int PF = 8;
-        uint2 cb[PF], tb[PF];
-#pragma unroll
-        for (int i = 0; i < PF; ++i) {
-            cb[i] = pad;
-            tb[i] = make_uint2(0, 0);
-            const int xx = W1 - 1 - i;
-            if (active && xx >= 0) {
-                cb[i] = __ldcs(&C[xx * 24]);
-                tb[i] = __ldcs(&T[xx * 24]);
-            }
-        }
         const uint32_t uq = 100 - p.uniq;
         const uint64_t uq_magic = ((1ull << 40) / uq) + 1;  // floor(n / uq) = n * magic >> 40 for n < 2^33
         const uint32_t d0 = 4 * lane;
-        for (int x = W1 - 1; x >= 0; x -= PF) {
+        for (int j = 0; j < n_chunks; ++j) {
+            const int s = j % RS_NST, x0 = (n_chunks - 1 - j) * RS_CH, n = min(RS_CH, W1 - x0);
+            // the stage of chunk j-1 was released by the __syncwarp that closed the previous iteration: refill it
+            if (lane == 0 && j >= 1 && j + RS_NST - 2 < n_chunks) issue(j + RS_NST - 2);
+            mbar_wait(&bar[s], (j / RS_NST) & 1);
+            const uint2* sC = reinterpret_cast<const uint2*>(wbase + s * 2 * RS_ARR) + lane;
+            const uint2* sT = sC + RS_ARR / 8;
 #pragma unroll
-            for (int i = 0; i < PF; ++i) {
-                const int xx = x - i;
-                if (xx >= 0) {
-                    const uint2 c = cb[i], tt = tb[i];
-                    if (active && xx - PF >= 0) {
-                        cb[i] = __ldcs(&C[(xx - PF) * 24]);
-                        tb[i] = __ldcs(&T[(xx - PF) * 24]);
+            for (int ii = 0; ii < RS_CH; ++ii) {
+                const int i = RS_CH - 1 - ii;
+                if (i < n) {
+                    const int xx = x0 + i;
+                    uint2 c = make_uint2(SG_CPAD, SG_CPAD), tt = make_uint2(0, 0);
+                    if (active) {
+                        c = sC[i * 24];
+                        tt = sT[i * 24];
                     }
                     sgm_step(a0, a1, mm, c.x, c.y, P1b, P2b, src_up);
                     const uint32_t S0 = __vminu2(tt.x + a0, SAT), S1 = __vminu2(tt.y + a1, SAT);
@@ -407,6 +509,7 @@ __global__ void __launch_bounds__(SG_HW * 32) sgbm_horizontal_kernel(const uint3
                     if (lane == 0) rec[xx] = make_uint2(minS | bestd << 16 | (nu ? 0x80000000u : 0u), Sm | Sp << 16);
                 }
             }
+            __syncwarp();  // every lane is done reading this stage
         }
     }
     __syncwarp();
@@ -729,13 +832,20 @@ static int sgbm_enqueue(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "sgbm_vertical_kernel");
     if (s->stop_after == 1) return VSLAM_OK;
-    const size_t smem = (size_t)SG_HW * w * sizeof(uint32_t);
-    VSLAM_CUDA(ctx, cudaFuncSetAttribute(sgbm_horizontal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vslam_time_begin(ctx, VK_SGBM_HORIZONTAL);
-    sgbm_horizontal_kernel<<<dim3(ceil_div(h, SG_HW), n), SG_HW * 32, smem, st>>>(s->d_C, s->d_L[0], s->d_L[1], s->d_L[2], w, W1, h, p,
-                                                                                  s->d_rec, s->d_raw);
+    const size_t smem_f = (size_t)SG_HW * RS_FWD_WARP;
+    const size_t smem = (size_t)SG_HW * RS_BWD_STAGES + (size_t)SG_HW * w * sizeof(uint32_t);
+    VSLAM_CUDA(ctx, cudaFuncSetAttribute(sgbm_row_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+    VSLAM_CUDA(ctx, cudaFuncSetAttribute(sgbm_row_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vslam_time_begin(ctx, VK_SGBM_ROW_FWD);
+    sgbm_row_forward_kernel<<<dim3(ceil_div(h, SG_HW), n), SG_HW * 32, smem_f, st>>>(s->d_C, s->d_L[0], s->d_L[1], s->d_L[2], W1, h,
+                                                                                    p);
     vslam_time_end(ctx);
-    VSLAM_LAUNCH_CHECK(ctx, "sgbm_horizontal_kernel");
+    VSLAM_LAUNCH_CHECK(ctx, "sgbm_row_forward_kernel");
+    vslam_time_begin(ctx, VK_SGBM_ROW_BWD);
+    sgbm_row_backward_kernel<<<dim3(ceil_div(h, SG_HW), n), SG_HW * 32, smem, st>>>(s->d_C, s->d_L[0], w, W1, h, p, s->d_rec,
+                                                                                    s->d_raw);
+    vslam_time_end(ctx);
+    VSLAM_LAUNCH_CHECK(ctx, "sgbm_row_backward_kernel");
     const int hw = w * h;
     vslam_time_begin(ctx, VK_SGBM_POST);
     sgbm_median_kernel<<<dim3(ceil_div(w, 256), h, n), 256, 0, st>>>(s->d_raw, s->d_med, w, h);

@@ -37,7 +37,7 @@ e1.record(); torch.cuda.synchronize()
 ms2 = e0.elapsed_time(e1) / iters
 W1 = W - 96
 vol = H * W1 * 96 * 2
-alg = {"sgbm_cost_kernel": vol, "sgbm_vertical_kernel": vol * 6, "sgbm_horizontal_kernel": vol * 7}
+alg = {"sgbm_cost_kernel": vol, "sgbm_vertical_kernel": vol * 4, "sgbm_row_forward_kernel": vol * 5, "sgbm_row_backward_kernel": vol * 2}
 out = {"pairs": B, "ms_per_batch": ms2, "ms_per_pair": ms2 / B, "fps": B / ms2 * 1e3, "ms_per_batch_with_events": ms,
        "kernels": {k: {"ms_per_launch": v[0] / max(v[1], 1), "launches": v[1],
                        "alg_GBps": (alg[k] * B / (v[0] / max(v[1], 1) * 1e-3) / 1e9 if k in alg else None)} for k, v in kt.items()}}
