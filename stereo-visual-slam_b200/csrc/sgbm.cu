@@ -470,43 +470,73 @@ __global__ void __launch_bounds__(SG_HW * 32) sgbm_row_backward_kernel(const uin
     {
         uint32_t a0 = active ? 0u : SG_BIG2, a1 = a0, mm = 0;
         const uint32_t uq = 100 - p.uniq;
-        const uint64_t uq_magic = ((1ull << 40) / uq) + 1;  // floor(n / uq) = n * magic >> 40 for n < 2^33
+        const uint32_t uq_magic = (uint32_t)((1ull << 32) / uq) + 1;  // floor(n / uq) = umulhi(n, magic) while n * uq < 2^32
         const uint32_t d0 = 4 * lane;
+        const uint32_t dk0 = d0, dk1 = d0 + 1, dk2 = d0 + 2, dk3 = d0 + 3;  // PRMT source: byte 4 = d, bytes 5..7 = 0
+        const uint32_t lane_or = active ? 0u : 0xffffffffu;
         for (int j = 0; j < n_chunks; ++j) {
             const int s = j % RS_NST, x0 = (n_chunks - 1 - j) * RS_CH, n = min(RS_CH, W1 - x0);
             // the stage of chunk j-1 was released by the __syncwarp that closed the previous iteration: refill it
             if (lane == 0 && j >= 1 && j + RS_NST - 2 < n_chunks) issue(j + RS_NST - 2);
             mbar_wait(&bar[s], (j / RS_NST) & 1);
             const uint2* sC = reinterpret_cast<const uint2*>(wbase + s * 2 * RS_ARR) + lane;
-            const uint2* sT = sC + RS_ARR / 8;
+            uint2* sT = reinterpret_cast<uint2*>(wbase + s * 2 * RS_ARR + RS_ARR) + lane;
+            // phase A: the recurrence for the whole chunk (descending x); S = sat16(S4 + L_r) replaces S4 in the stage
+            uint32_t S0[RS_CH], S1[RS_CH];
 #pragma unroll
             for (int ii = 0; ii < RS_CH; ++ii) {
                 const int i = RS_CH - 1 - ii;
+                S0[i] = S1[i] = SAT;
                 if (i < n) {
-                    const int xx = x0 + i;
-                    uint2 c = make_uint2(SG_CPAD, SG_CPAD), tt = make_uint2(0, 0);
+                    uint2 c = make_uint2(SG_CPAD, SG_CPAD), tt = make_uint2(SAT, SAT);  // padding lanes: S = 32767, d >= 96
                     if (active) {
                         c = sC[i * 24];
                         tt = sT[i * 24];
                     }
                     sgm_step(a0, a1, mm, c.x, c.y, P1b, P2b, src_up);
-                    const uint32_t S0 = __vminu2(tt.x + a0, SAT), S1 = __vminu2(tt.y + a1, SAT);
-                    uint32_t key = min(min((S0 & 0xffffu) << 8 | d0, (S0 >> 16) << 8 | (d0 + 1)),
-                                       min((S1 & 0xffffu) << 8 | (d0 + 2), (S1 >> 16) << 8 | (d0 + 3)));
-                    if (!active) key = 0xffffffffu;
-                    key = __reduce_min_sync(0xffffffffu, key);
-                    const uint32_t minS = key >> 8, bestd = key & 0xff;
-                    // uniqueness: some S(d) * (100 - u) < minS * 100 with |d - best| > 1  <=>  S(d) < ceil(minS * 100 / (100 - u))
-                    const uint32_t q = (uint32_t)(((uint64_t)(minS * 100u + uq - 1) * uq_magic) >> 40);
-                    const uint2 ex = s_excl[min(bestd - d0 + 1u, 6u)];
-                    const uint32_t z = __vminu2(S0 | ex.x, S1 | ex.y);
-                    const bool nu = __any_sync(0xffffffffu, active && min(z & 0xffffu, z >> 16) < q);
-                    // S(best - 1), S(best + 1) from their owner lanes
-                    const uint32_t im = bestd - 1, ip = bestd + 1;
-                    const uint32_t wm = (im & 2) ? S1 : S0, wq = (ip & 2) ? S1 : S0;
-                    const uint32_t Sm = __shfl_sync(0xffffffffu, wm >> ((im & 1) * 16), (im >> 2) & 31) & 0xffffu;
-                    const uint32_t Sp = __shfl_sync(0xffffffffu, wq >> ((ip & 1) * 16), (ip >> 2) & 31) & 0xffffu;
-                    if (lane == 0) rec[xx] = make_uint2(minS | bestd << 16 | (nu ? 0x80000000u : 0u), Sm | Sp << 16);
+                    S0[i] = __vminu2(tt.x + a0, SAT);
+                    S1[i] = __vminu2(tt.y + a1, SAT);
+                    if (active) sT[i * 24] = make_uint2(S0[i], S1[i]);  // u16 S[d] of column i at d = 4 lane + k
+                }
+            }
+            // phase B: winner-take-all per column.  The columns are independent, so every warp-wide operation is
+            // issued for all of them back to back and their latencies overlap instead of adding up.
+            // key = S << 8 | d, one PRMT per element: bytes {d, S.lo, S.hi, 0}
+            uint32_t key[RS_CH];
+#pragma unroll
+            for (int i = 0; i < RS_CH; ++i)
+                key[i] = min(min(__byte_perm(S0[i], dk0, 0x5104), __byte_perm(S0[i], dk1, 0x5324)),
+                             min(__byte_perm(S1[i], dk2, 0x5104), __byte_perm(S1[i], dk3, 0x5324)));
+#pragma unroll
+            for (int i = 0; i < RS_CH; ++i) key[i] = __reduce_min_sync(0xffffffffu, key[i]);
+            bool nuq[RS_CH];
+#pragma unroll
+            for (int i = 0; i < RS_CH; ++i) {
+                const uint32_t minS = key[i] >> 8, bestd = key[i] & 0xff;
+                // uniqueness: some S(d) * (100 - u) < minS * 100 with |d - best| > 1  <=>  S(d) < ceil(minS * 100 / (100 - u))
+                const uint32_t q = __umulhi(minS * 100u + uq - 1, uq_magic);
+                const uint2 ex = s_excl[min(bestd - d0 + 1u, 6u)];
+                const uint32_t z = __vminu2(S0[i] | ex.x | lane_or, S1[i] | ex.y | lane_or);
+                nuq[i] = min(z & 0xffffu, z >> 16) < q;
+            }
+#pragma unroll
+            for (int i = 0; i < RS_CH; ++i) nuq[i] = __any_sync(0xffffffffu, nuq[i]);
+            __syncwarp();  // the S chunk is complete in shared memory
+            {
+                // lane i finishes column i: S(best - 1), S(best + 1) come from the chunk in shared memory
+                uint32_t k = key[0];
+                bool nq = nuq[0];
+#pragma unroll
+                for (int i = 1; i < RS_CH; ++i)
+                    if (lane == i) {
+                        k = key[i];
+                        nq = nuq[i];
+                    }
+                if (lane < n) {
+                    const uint32_t bestd = k & 0xff;
+                    const uint16_t* Sc = reinterpret_cast<const uint16_t*>(wbase + s * 2 * RS_ARR + RS_ARR) + lane * SG_D;
+                    const uint32_t Sm = Sc[max((int)bestd - 1, 0)], Sp = Sc[min(bestd + 1, (uint32_t)SG_D - 1)];
+                    rec[x0 + lane] = make_uint2((k >> 8) | bestd << 16 | (nq ? 0x80000000u : 0u), Sm | Sp << 16);
                 }
             }
             __syncwarp();  // every lane is done reading this stage
