@@ -188,112 +188,7 @@ __global__ void __launch_bounds__(SG_TX* SG_NDP) sgbm_cost_kernel(const uint2* _
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// One SGM step on a warp: lanes 0..23 hold disparities 4l..4l+3 as two s16x2 words (a0 = d, d+1; a1 = d+2, d+3).
-//   L(d) = C(d) + min(Lp(d), Lp(d-1) + P1, Lp(d+1) + P1, m + P2) - m,   m = min_k Lp(k)
-// `mm` carries m in both halves of a word (the CREDUX of a word whose halves are equal is monotone in that value,
-// so the reduction returns the next broadcast word directly).  Lanes 24..31 are padding: they are fed the cost
-// SG_CPAD so their values stay in [28000, 28000 + P2] -- above every reachable m + P2, below s16 overflow -- which
-// gives lane 23 its "no d+1 neighbour" and, through the rotating shuffle, lane 0 its "no d-1 neighbour" for free.
-// ---------------------------------------------------------------------------------------------------------------
-#define SG_CPAD 0x6d606d60u  // 28000 | 28000 << 16
-
-__device__ __forceinline__ void sgm_step(uint32_t& a0, uint32_t& a1, uint32_t& mm, uint32_t c0, uint32_t c1, uint32_t P1b,
-                                         uint32_t P2b, int src_up) {
-    const uint32_t up = __shfl_sync(0xffffffffu, a1, src_up);  // lane - 1 (lane 0 reads padding lane 31)
-    const uint32_t dn = __shfl_down_sync(0xffffffffu, a0, 1);
-    const uint32_t lm0 = __byte_perm(up, a0, 0x5432);  // (L[4l-1], L[4l])
-    const uint32_t mid = __byte_perm(a0, a1, 0x5432);  // (L[4l+1], L[4l+2])
-    const uint32_t lp1 = __byte_perm(a1, dn, 0x5432);  // (L[4l+3], L[4l+4])
-    const uint32_t mp2 = mm + P2b;
-    const uint32_t t0 = __vmins2(__vmins2(__vadd2(__vmins2(lm0, mid), P1b), mp2), a0);
-    const uint32_t t1 = __vmins2(__vmins2(__vadd2(__vmins2(mid, lp1), P1b), mp2), a1);
-    a0 = c0 + t0 - mm;  // halves stay in [0, 32767]: plain 32-bit arithmetic is exact on the packed pairs
-    a1 = c1 + t1 - mm;
-    const uint32_t w = __vmins2(a0, a1);
-    mm = (uint32_t)__reduce_min_sync(0xffffffffu, (int)__vmins2(w, __byte_perm(w, w, 0x1032)));
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// K20: the three paths that come from the row above.  blockIdx.y: 0 = from (x-1, y-1), 1 = from (x, y-1),
-// 2 = from (x+1, y-1).  Warp k starts at column k of row 0; a diagonal path that leaves the image re-enters on the
-// other side with a fresh (zero) predecessor, which is what OpenCV's zero-initialised border columns give.
-// The three sweeps of one pair run concurrently and touch row y at about the same time, so C is read with the
-// default policy (two of the three reads hit L2) while the path volumes are streamed out.
-// ---------------------------------------------------------------------------------------------------------------
-template <int DX>
-__device__ __forceinline__ void vertical_path(const uint2* __restrict__ C, uint2* __restrict__ Lo, int k, int W1, int H,
-                                              uint32_t P1b, uint32_t P2b, int lane) {
-    const bool active = lane < 24;
-    const int src_up = (lane + 31) & 31;
-    const uint32_t rowstep = (uint32_t)(W1 + DX) * 24u, wrapfix = (uint32_t)W1 * 24u;
-    auto advance = [&](uint32_t& off, int& x) {
-        x += DX;
-        off += rowstep;
-        if (DX > 0 && x == W1) {
-            x = 0;
-            off -= wrapfix;
-        }
-        if (DX < 0 && x < 0) {
-            x = W1 - 1;
-            off += wrapfix;
-        }
-    };
-    uint2 cb[SG_PF];
-    uint32_t offp = (uint32_t)k * 24u + lane;
-    int xp = k;
-#pragma unroll
-    for (int i = 0; i < SG_PF; ++i) {
-        cb[i] = make_uint2(SG_CPAD, SG_CPAD);
-        if (active && i < H) cb[i] = C[offp];
-        advance(offp, xp);
-    }
-    uint32_t a0 = active ? 0u : SG_BIG2, a1 = a0, mm = 0;
-    uint32_t off = (uint32_t)k * 24u + lane;
-    int x = k;
-    for (int y = 0; y < H; y += SG_PF) {
-#pragma unroll
-        for (int i = 0; i < SG_PF; ++i) {
-            const int yy = y + i;
-            if (yy < H) {
-                const uint2 c = cb[i];
-                if (active && yy + SG_PF < H) cb[i] = C[offp];
-                advance(offp, xp);
-                if (DX != 0 && x == (DX > 0 ? 0 : W1 - 1)) {
-                    a0 = a1 = active ? 0u : SG_BIG2;
-                    mm = 0;
-                }
-                sgm_step(a0, a1, mm, c.x, c.y, P1b, P2b, src_up);
-                if (active) __stcs(&Lo[off], make_uint2(a0, a1));
-                advance(off, x);
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256) sgbm_vertical_kernel(const uint32_t* __restrict__ Cvol, uint32_t* __restrict__ L0v,
-                                                            uint32_t* __restrict__ L1v, uint32_t* __restrict__ L2v, int W1,
-                                                            int H, int P1, int P2) {
-    const int lane = threadIdx.x & 31;
-    const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (k >= W1) return;
-    const int dir = blockIdx.y, pair = blockIdx.z;
-    const size_t vol = (size_t)pair * H * W1 * SG_NDP;
-    const uint2* C = reinterpret_cast<const uint2*>(Cvol + vol);
-    const uint32_t P1b = bcast16(P1), P2b = bcast16(P2);
-    if (dir == 0) vertical_path<1>(C, reinterpret_cast<uint2*>(L0v + vol), k, W1, H, P1b, P2b, lane);
-    else if (dir == 1) vertical_path<0>(C, reinterpret_cast<uint2*>(L1v + vol), k, W1, H, P1b, P2b, lane);
-    else vertical_path<-1>(C, reinterpret_cast<uint2*>(L2v + vol), k, W1, H, P1b, P2b, lane);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// K21: one warp per image row, two launches (each fits one resident wave).  Pass 1 walks left->right (path 0) and folds the four finished paths into
-// S4 = sat16(L0+L1+L2+L3) (written over the first path volume); pass 2 walks right->left (the fifth path of MODE_SGBM's
-// single pass), adds it and reduces every column to a record {min S, argmin, not-unique, S[best-1], S[best+1]}.
-// The per-column epilogue (right-image map, sub-pixel fit, LR check) then runs lane-parallel over x: OpenCV's
-// "first writer in descending x wins a cost tie" becomes an atomicMin on the key (minS << 12 | 4095 - x).
-// ---------------------------------------------------------------------------------------------------------------
-// ---- TMA bulk-copy plumbing (per-warp rings: every warp owns its stages and mbarriers) ---------------------------
+// ---- TMA bulk-copy plumbing  ---------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -330,6 +225,127 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One SGM step on a warp: lanes 0..23 hold disparities 4l..4l+3 as two s16x2 words (a0 = d, d+1; a1 = d+2, d+3).
+//   L(d) = C(d) + min(Lp(d), Lp(d-1) + P1, Lp(d+1) + P1, m + P2) - m,   m = min_k Lp(k)
+// `mm` carries m in both halves of a word (the CREDUX of a word whose halves are equal is monotone in that value,
+// so the reduction returns the next broadcast word directly).  Lanes 24..31 are padding: they are fed the cost
+// SG_CPAD so their values stay in [28000, 28000 + P2] -- above every reachable m + P2, below s16 overflow -- which
+// gives lane 23 its "no d+1 neighbour" and, through the rotating shuffle, lane 0 its "no d-1 neighbour" for free.
+// ---------------------------------------------------------------------------------------------------------------
+#define SG_CPAD 0x6d606d60u  // 28000 | 28000 << 16
+
+__device__ __forceinline__ void sgm_step(uint32_t& a0, uint32_t& a1, uint32_t& mm, uint32_t c0, uint32_t c1, uint32_t P1b,
+                                         uint32_t P2b, int src_up) {
+    const uint32_t up = __shfl_sync(0xffffffffu, a1, src_up);  // lane - 1 (lane 0 reads padding lane 31)
+    const uint32_t dn = __shfl_down_sync(0xffffffffu, a0, 1);
+    const uint32_t lm0 = __byte_perm(up, a0, 0x5432);  // (L[4l-1], L[4l])
+    const uint32_t mid = __byte_perm(a0, a1, 0x5432);  // (L[4l+1], L[4l+2])
+    const uint32_t lp1 = __byte_perm(a1, dn, 0x5432);  // (L[4l+3], L[4l+4])
+    const uint32_t mp2 = mm + P2b;
+    const uint32_t t0 = __vmins2(__vmins2(__vadd2(__vmins2(lm0, mid), P1b), mp2), a0);
+    const uint32_t t1 = __vmins2(__vmins2(__vadd2(__vmins2(mid, lp1), P1b), mp2), a1);
+    a0 = c0 + t0 - mm;  // halves stay in [0, 32767]: plain 32-bit arithmetic is exact on the packed pairs
+    a1 = c1 + t1 - mm;
+    const uint32_t w = __vmins2(a0, a1);
+    mm = (uint32_t)__reduce_min_sync(0xffffffffu, (int)__vmins2(w, __byte_perm(w, w, 0x1032)));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K20: the three paths that come from the row above.  blockIdx.y: 0 = from (x-1, y-1), 1 = from (x, y-1),
+// 2 = from (x+1, y-1).  Warp k starts at column k of row 0; a diagonal path that leaves the image re-enters on the
+// other side with a fresh (zero) predecessor, which is what OpenCV's zero-initialised border columns give.
+// The three sweeps of one pair run concurrently and touch row y at about the same time, so C is read with the
+// default policy (two of the three reads hit L2) while the path volumes are streamed out.
+// ---------------------------------------------------------------------------------------------------------------
+#define VT_NST 16   // rows in flight per CTA: 16 x 1536 B
+#define VT_WARPS 8  // paths per CTA (+ 1 producer warp)
+
+template <int DX>
+__device__ __forceinline__ void vertical_cta(const unsigned char* __restrict__ gC, unsigned char* __restrict__ gL, int k0, int W1,
+                                             int H, uint32_t P1b, uint32_t P2b, unsigned char* ring, unsigned char* outb,
+                                             uint64_t* full, uint64_t* empty) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nact = min(VT_WARPS, W1 - k0);  // paths of this CTA
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < VT_NST; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], nact);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (w == VT_WARPS) {
+        // producer warp: one lane streams row y of the CTA's nact adjacent columns (1 or 2 pieces when the range wraps)
+        if (lane == 0) {
+            int xb = k0;
+            for (int y = 0; y < H; ++y) {
+                const int s = y % VT_NST;
+                if (y >= VT_NST) mbar_wait(&empty[s], ((y / VT_NST) - 1) & 1);
+                const int n1 = min(nact, W1 - xb);
+                mbar_expect_tx(&full[s], (uint32_t)nact * (SG_D * 2));
+                bulk_g2s(ring + s * (VT_WARPS * SG_D * 2), gC + ((size_t)y * W1 + xb) * (SG_D * 2), (uint32_t)n1 * (SG_D * 2), &full[s]);
+                if (n1 < nact)
+                    bulk_g2s(ring + s * (VT_WARPS * SG_D * 2) + n1 * (SG_D * 2), gC + (size_t)y * W1 * (SG_D * 2),
+                             (uint32_t)(nact - n1) * (SG_D * 2), &full[s]);
+                xb += DX;
+                if (DX > 0 && xb == W1) xb = 0;
+                if (DX < 0 && xb < 0) xb = W1 - 1;
+            }
+        }
+        return;
+    }
+    if (w >= nact) return;
+    const bool active = lane < 24;
+    const int src_up = (lane + 31) & 31;
+    uint32_t a0 = active ? 0u : SG_BIG2, a1 = a0, mm = 0;
+    int x = k0 + w;
+    for (int y = 0; y < H; ++y) {
+        const int s = y % VT_NST;
+        mbar_wait(&full[s], (y / VT_NST) & 1);
+        uint2 c = make_uint2(SG_CPAD, SG_CPAD);
+        if (active) c = reinterpret_cast<const uint2*>(ring + s * (VT_WARPS * SG_D * 2) + w * (SG_D * 2))[lane];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (DX != 0 && x == (DX > 0 ? 0 : W1 - 1)) {
+            a0 = a1 = active ? 0u : SG_BIG2;
+            mm = 0;
+        }
+        sgm_step(a0, a1, mm, c.x, c.y, P1b, P2b, src_up);
+        if (active) __stcs(reinterpret_cast<uint2*>(gL + ((size_t)y * W1 + x) * (SG_D * 2)) + lane, make_uint2(a0, a1));
+        x += DX;
+        if (DX > 0 && x == W1) x = 0;
+        if (DX < 0 && x < 0) x = W1 - 1;
+    }
+}
+
+__global__ void __launch_bounds__((VT_WARPS + 1) * 32) sgbm_vertical_kernel(const uint32_t* __restrict__ Cvol, uint32_t* __restrict__ L0v,
+                                                                           uint32_t* __restrict__ L1v, uint32_t* __restrict__ L2v,
+                                                                           int W1, int H, int P1, int P2) {
+    __shared__ __align__(128) unsigned char ring[VT_NST * VT_WARPS * SG_D * 2];
+    __shared__ __align__(128) unsigned char outb[VT_WARPS * 2 * SG_D * 2];
+    __shared__ uint64_t full[VT_NST], empty[VT_NST];
+    const int k0 = blockIdx.x * VT_WARPS;
+    const int dir = blockIdx.y, pair = blockIdx.z;
+    const size_t vol = (size_t)pair * H * W1 * (SG_D * 2);
+    const unsigned char* gC = reinterpret_cast<const unsigned char*>(Cvol) + vol;
+    const uint32_t P1b = bcast16(P1), P2b = bcast16(P2);
+    if (dir == 0) vertical_cta<1>(gC, reinterpret_cast<unsigned char*>(L0v) + vol, k0, W1, H, P1b, P2b, ring, outb, full, empty);
+    else if (dir == 1) vertical_cta<0>(gC, reinterpret_cast<unsigned char*>(L1v) + vol, k0, W1, H, P1b, P2b, ring, outb, full, empty);
+    else vertical_cta<-1>(gC, reinterpret_cast<unsigned char*>(L2v) + vol, k0, W1, H, P1b, P2b, ring, outb, full, empty);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K21: one warp per image row, two launches (each fits one resident wave).  Pass 1 walks left->right (path 0) and folds the four finished paths into
+// S4 = sat16(L0+L1+L2+L3) (written over the first path volume); pass 2 walks right->left (the fifth path of MODE_SGBM's
+// single pass), adds it and reduces every column to a record {min S, argmin, not-unique, S[best-1], S[best+1]}.
+// The per-column epilogue (right-image map, sub-pixel fit, LR check) then runs lane-parallel over x: OpenCV's
+// "first writer in descending x wins a cost tie" becomes an atomicMin on the key (minS << 12 | 4095 - x).
+// ---------------------------------------------------------------------------------------------------------------
 #define RS_CH 8                         // columns per bulk copy: 8 x 192 B = 1536 contiguous bytes per volume
 #define RS_NST 4                        // ring stages per warp
 #define RS_ARR (RS_CH * SG_D * 2)       // bytes of one volume's chunk
@@ -858,7 +874,7 @@ static int sgbm_enqueue(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "sgbm_cost_kernel");
     vslam_time_begin(ctx, VK_SGBM_VERTICAL);
-    sgbm_vertical_kernel<<<dim3(ceil_div(W1, 8), 3, n), 256, 0, st>>>(s->d_C, s->d_L[0], s->d_L[1], s->d_L[2], W1, h, p.P1, p.P2);
+    sgbm_vertical_kernel<<<dim3(ceil_div(W1, VT_WARPS), 3, n), (VT_WARPS + 1) * 32, 0, st>>>(s->d_C, s->d_L[0], s->d_L[1], s->d_L[2], W1, h, p.P1, p.P2);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "sgbm_vertical_kernel");
     if (s->stop_after == 1) return VSLAM_OK;
