@@ -93,98 +93,160 @@ __global__ void __launch_bounds__(256) sgbm_prefilter_kernel(const uint8_t* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K19: pixel cost + box sum.  CTA = SG_TX columns x one row band, thread = (column, disparity pair), marching down.
+// K19: pixel cost + 9x9 box sum.  CTA = CK_CW output columns x one row band, marching down the rows.
+// Thread (g, q) owns 8 consecutive columns and the 4 disparities 4q..4q+3 (two s16x2 words).  Walking its columns
+// left to right, the right-image operand of disparity d at column x is position x - d: one new position per column
+// feeds all four disparities (register window), and the operands of the second word are the first word's operands
+// of two columns ago.  Operands stay byte-packed (v | min << 8 | max << 16, as the prefilter wrote them) in shared
+// memory and are widened with PRMT; u - v is computed as u + (255 - v) with the +255 bias folded into the max.
+// Pixel costs go through a shared exchange buffer once (no halo recomputation inside the CTA), the horizontal
+// window slides in registers, the vertical window is a 9-slot ring in shared memory.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t bcast16(int v) { return (uint32_t)(v & 0xffff) * 0x00010001u; }
-__device__ __forceinline__ uint32_t neg2(uint32_t a) { return __vadd2(~a, 0x00010001u); }
 
-// min(c0, c1) of Birchfield-Tomasi on packed pairs; nX = -X
-__device__ __forceinline__ uint32_t bt_cost2(uint32_t u, uint32_t u0, uint32_t nu, uint32_t nu1, uint32_t v, uint32_t v0,
-                                             uint32_t nv, uint32_t nv1) {
-    const uint32_t c0 = __vimax3_s16x2(__vadd2(u, nv1), __vadd2(v0, nu), 0u);
-    const uint32_t c1 = __vimax3_s16x2(__vadd2(v, nu1), __vadd2(u0, nv), 0u);
+#define CK_Q 24                        // threads per column group
+#define CK_GC 8                        // columns per group
+#define CK_CW 112                      // output columns per CTA
+#define CK_NG (CK_CW / CK_GC + 2)      // 14 output groups + one halo group on each side
+#define CK_COLS (CK_NG * CK_GC)        // 128 columns whose pixel cost the CTA computes
+#define CK_PSTR 50                     // words per column in the exchange buffer (48 + 2: groups land in different banks)
+#define CK_NPOS 232                    // right-image positions staged per row (CK_COLS + 95 + 3, rounded up)
+#define CK_THREADS (CK_NG * CK_Q)      // 384
+#define CK_SMEM (2 * (CK_COLS + CK_NPOS) * 8 + CK_COLS * CK_PSTR * 4 + 9 * CK_CW * SG_NDP * 4)
+#define CK_FF 0x00ff00ffu
+
+struct BtOps {  // widened operands of one (position pair, channel): v, min, 255 - v, 255 - max
+    uint32_t v, v0, vc, v1c;
+};
+
+__device__ __forceinline__ BtOps bt_expand(uint32_t p_lo, uint32_t p_hi) {  // low half: p_lo's pixel, high half: p_hi's
+    BtOps o;
+    o.v = __byte_perm(p_lo, p_hi, 0x7430);
+    o.v0 = __byte_perm(p_lo, p_hi, 0x7531);
+    o.vc = o.v ^ CK_FF;
+    o.v1c = __byte_perm(p_lo, p_hi, 0x7632) ^ CK_FF;
+    return o;
+}
+
+// min(c0, c1) + 255 with c0 = max(0, u - v1, v0 - u), c1 = max(0, v - u1, u0 - v)
+__device__ __forceinline__ uint32_t bt_cost255(const BtOps& u, const BtOps& v) {
+    const uint32_t c0 = __vimax3_s16x2(u.v + v.v1c, v.v0 + u.vc, CK_FF);
+    const uint32_t c1 = __vimax3_s16x2(v.v + u.v1c, u.v0 + v.vc, CK_FF);
     return __vmins2(c0, c1);
 }
 
-__global__ void __launch_bounds__(SG_TX* SG_NDP) sgbm_cost_kernel(const uint2* __restrict__ pre, int n_pairs, int W, int H, int W1,
+// sobel-plane cost + (raw-plane cost >> 2)
+__device__ __forceinline__ uint32_t bt_pixel_cost(const BtOps& us, const BtOps& ur, const BtOps& vs, const BtOps& vr) {
+    const uint32_t cr = ((bt_cost255(ur, vr) - CK_FF) >> 2) & 0x3fff3fffu;
+    return bt_cost255(us, vs) + cr - CK_FF;
+}
+
+__global__ void __launch_bounds__(CK_THREADS, 1) sgbm_cost_kernel(const uint2* __restrict__ pre, int n_pairs, int W, int H, int W1,
                                                                  int band_rows, uint32_t* __restrict__ Cvol) {
-    __shared__ uint32_t sL[SG_NC][8];          // u, u0, -u, -u1 (sobel) ; u, u0, -u, -u1 (raw), broadcast pairs
-    __shared__ uint32_t sR[2][8][SG_NRH];      // [parity][v, v0, -v, -v1 (sobel), same (raw)][k]: (val[j], val[j-1])
-    __shared__ uint32_t sPd[SG_NC][SG_NDP];    // pixel cost of the current row
-    __shared__ uint32_t sRing[2 * SG_R + 1][SG_TX * SG_NDP];
-    const int t = threadIdx.x, dp = t % SG_NDP, xl = t / SG_NDP;
-    const int x1s = blockIdx.x * SG_TX, pair = blockIdx.z;
+    extern __shared__ __align__(16) unsigned char ck_smem[];
+    uint2* sOp = reinterpret_cast<uint2*>(ck_smem);                              // [2][CK_COLS left | CK_NPOS right]
+    uint32_t* sPd = reinterpret_cast<uint32_t*>(sOp + 2 * (CK_COLS + CK_NPOS));  // [CK_COLS][CK_PSTR]
+    uint32_t* sRing = sPd + CK_COLS * CK_PSTR;                                   // [9][CK_CW][48]
+    const int t = threadIdx.x, g = t / CK_Q, q = t - g * CK_Q;
+    const int x1s = blockIdx.x * CK_CW, pair = blockIdx.z;
     const int y0 = blockIdx.y * band_rows, y1 = min(y0 + band_rows, H);
     if (y0 >= H) return;
     const uint2* preL = pre + (size_t)pair * H * W;
     const uint2* preR = pre + (size_t)(n_pairs + pair) * H * W;
-    const int jb = x1s - SG_R;  // image column of right-row slot 0
-#pragma unroll
-    for (int s = 0; s < 2 * SG_R + 1; ++s) sRing[s][t] = 0;
-    uint32_t run = 0;
-    int slot = 0;
-    const int x1 = x1s + xl;
+    const int xfirst = x1s - CK_GC;         // W1-coordinate of exchange-buffer column 0
+    const int pb = xfirst + SG_D - 95 - 3;  // image position of right-row slot 0
+    const int xg = xfirst + g * CK_GC;      // first column of this thread
+    const int nvalid = xg < 0 ? 0 : min(CK_GC, W1 - xg);  // columns of this group inside the image (groups are 8-aligned)
+    const bool out_group = g >= 1 && g <= CK_NG - 2 && nvalid > 0;
     uint32_t* Cout = Cvol + (size_t)pair * H * W1 * SG_NDP;
 
-    auto load_row = [&](int row) {  // phase A
+    auto load_ops = [&](int buf, int row) {
         const int rr = min(max(row, 0), H - 1);
-        if (t < 2 * SG_NRH) {
-            const int j = min(max(jb + t, 0), W - 1), jm = min(max(jb + t - 1, 0), W - 1);
-            const uint2 a = preR[(size_t)rr * W + j], b = preR[(size_t)rr * W + jm];
-            uint32_t* d = &sR[t & 1][0][t >> 1];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const uint32_t pa = c ? a.y : a.x, pb = c ? b.y : b.x;
-                const uint32_t v = (pa & 0xff) | (pb & 0xff) << 16;
-                const uint32_t v0 = (pa >> 8 & 0xff) | (pb >> 8 & 0xff) << 16;
-                const uint32_t v1 = (pa >> 16 & 0xff) | (pb >> 16 & 0xff) << 16;
-                d[(4 * c + 0) * SG_NRH] = v;
-                d[(4 * c + 1) * SG_NRH] = v0;
-                d[(4 * c + 2) * SG_NRH] = neg2(v);
-                d[(4 * c + 3) * SG_NRH] = neg2(v1);
-            }
-        } else if (t >= 128 && t < 128 + SG_NC) {
-            const int c_rel = t - 128;
-            const int xc = min(max(x1s - SG_R + c_rel, 0), W1 - 1) + SG_D;
-            const uint2 a = preL[(size_t)rr * W + xc];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const uint32_t pa = c ? a.y : a.x;
-                const uint32_t u = bcast16(pa & 0xff), u0 = bcast16(pa >> 8 & 0xff), u1 = bcast16(pa >> 16 & 0xff);
-                sL[c_rel][4 * c + 0] = u;
-                sL[c_rel][4 * c + 1] = u0;
-                sL[c_rel][4 * c + 2] = neg2(u);
-                sL[c_rel][4 * c + 3] = neg2(u1);
-            }
+        uint2* dst = sOp + buf * (CK_COLS + CK_NPOS);
+        for (int i = t; i < CK_COLS + CK_NPOS; i += CK_THREADS) {
+            if (i < CK_COLS)
+                dst[i] = preL[(size_t)rr * W + min(max(xfirst + i, 0), W1 - 1) + SG_D];
+            else
+                dst[i] = preR[(size_t)rr * W + min(max(pb + i - CK_COLS, 0), W - 1)];
         }
     };
 
+    // exchange-buffer word offsets of the 16 columns under this thread's horizontal windows (borders replicated)
+    int woff[2 * CK_GC];
+#pragma unroll
+    for (int k = 0; k < 2 * CK_GC; ++k) woff[k] = (min(max(xg - SG_R + k, 0), W1 - 1) - xfirst) * CK_PSTR + 2 * q;
+    uint32_t* ring = sRing + ((g - 1) * CK_GC) * SG_NDP + 2 * q;
+    if (out_group)
+        for (int s = 0; s < 2 * SG_R + 1; ++s)
+#pragma unroll
+            for (int i = 0; i < CK_GC; ++i) *reinterpret_cast<uint2*>(ring + (s * CK_CW + i) * SG_NDP) = make_uint2(0, 0);
+    uint32_t run0[CK_GC], run1[CK_GC];
+#pragma unroll
+    for (int i = 0; i < CK_GC; ++i) run0[i] = run1[i] = 0;
+    int slot = 0;
     const int r_first = y0 - SG_R, r_last = y1 - 1 + SG_R;
-    load_row(r_first);
+    load_ops(0, r_first);
     for (int row = r_first; row <= r_last; ++row) {
+        const int buf = (row - r_first) & 1;
         __syncthreads();
-        // phase B: pixel cost of every (column, pair) of the strip + halo
-        for (int i = t; i < SG_NC * SG_NDP; i += SG_TX * SG_NDP) {
-            const int c_rel = i / SG_NDP, dq = i - c_rel * SG_NDP;
-            const int xc = min(max(x1s - SG_R + c_rel, 0), W1 - 1) + SG_D;
-            const int r = xc - 2 * dq - jb;
-            const uint32_t* pr = &sR[r & 1][0][r >> 1];
-            const uint32_t* pl = sL[c_rel];
-            const uint32_t cs = bt_cost2(pl[0], pl[1], pl[2], pl[3], pr[0], pr[SG_NRH], pr[2 * SG_NRH], pr[3 * SG_NRH]);
-            const uint32_t cr = bt_cost2(pl[4], pl[5], pl[6], pl[7], pr[4 * SG_NRH], pr[5 * SG_NRH], pr[6 * SG_NRH], pr[7 * SG_NRH]);
-            sPd[c_rel][dq] = cs + ((cr >> 2) & 0x3fff3fffu);
+        // ---- phase B: pixel cost of this thread's columns -> exchange buffer ----
+        if (nvalid > 0) {
+            const uint2* Lp = sOp + buf * (CK_COLS + CK_NPOS) + g * CK_GC;
+            const uint2* Rp = sOp + buf * (CK_COLS + CK_NPOS) + CK_COLS + (xg - xfirst) + (SG_D - pb + xfirst) - 4 * q;
+            // Rp[i] = position of disparity 4q at column i; Rp[i - e] = disparity 4q + e
+            uint2 w1 = Rp[-1], w2 = Rp[-2], w3 = Rp[-3];
+            BtOps hs2 = bt_expand(w2.x, w3.x), hr2 = bt_expand(w2.y, w3.y);  // word-0 operands of column -2 = word 1 of column 0
+            BtOps hs1 = bt_expand(w1.x, w2.x), hr1 = bt_expand(w1.y, w2.y);  // ... of column -1
+            uint32_t* pdst = sPd + (g * CK_GC) * CK_PSTR + 2 * q;
+#pragma unroll
+            for (int i = 0; i < CK_GC; ++i) {
+                if (i < nvalid) {
+                    const uint2 w0 = Rp[i], lp = Lp[i];
+                    const BtOps vs = bt_expand(w0.x, w1.x), vr = bt_expand(w0.y, w1.y);
+                    const BtOps us = bt_expand(lp.x, lp.x), ur = bt_expand(lp.y, lp.y);
+                    uint2 pd;
+                    pd.x = bt_pixel_cost(us, ur, vs, vr);
+                    pd.y = bt_pixel_cost(us, ur, hs2, hr2);
+                    *reinterpret_cast<uint2*>(pdst + i * CK_PSTR) = pd;
+                    hs2 = hs1;
+                    hr2 = hr1;
+                    hs1 = vs;
+                    hr1 = vr;
+                    w1 = w0;
+                }
+            }
         }
         __syncthreads();
-        // phase C: horizontal window, vertical running sum; phase A of the next row rides along
-        uint32_t hs = 0;
+        // ---- phase C: horizontal window in registers, vertical window through the ring, running sum, store ----
+        if (row < r_last) load_ops(buf ^ 1, row + 1);
+        if (out_group) {
+            const int yo = row - SG_R;
+            uint2 win[2 * CK_GC];
 #pragma unroll
-        for (int k = 0; k < 2 * SG_R + 1; ++k) hs += sPd[xl + k][dp];
-        run = run + hs - sRing[slot][t];
-        sRing[slot][t] = hs;
+            for (int k = 0; k < 2 * CK_GC; ++k) win[k] = *reinterpret_cast<const uint2*>(sPd + woff[k]);
+            uint2 hsum = make_uint2(0, 0);
+#pragma unroll
+            for (int k = 0; k < 2 * SG_R + 1; ++k) {
+                hsum.x += win[k].x;
+                hsum.y += win[k].y;
+            }
+#pragma unroll
+            for (int i = 0; i < CK_GC; ++i) {
+                if (i < nvalid) {
+                    uint2* rp = reinterpret_cast<uint2*>(ring + (slot * CK_CW + i) * SG_NDP);
+                    const uint2 old = *rp;
+                    *rp = hsum;
+                    run0[i] += hsum.x - old.x;
+                    run1[i] += hsum.y - old.y;
+                    if (yo >= y0) *reinterpret_cast<uint2*>(Cout + ((size_t)yo * W1 + xg + i) * SG_NDP + 2 * q) = make_uint2(run0[i], run1[i]);
+                    if (i + 1 < CK_GC) {
+                        hsum.x += win[i + 2 * SG_R + 1].x - win[i].x;
+                        hsum.y += win[i + 2 * SG_R + 1].y - win[i].y;
+                    }
+                }
+            }
+        }
         slot = slot == 2 * SG_R ? 0 : slot + 1;
-        const int yo = row - SG_R;
-        if (yo >= y0 && x1 < W1) Cout[((size_t)yo * W1 + x1) * SG_NDP + dp] = run;
-        if (row < r_last) load_row(row + 1);
     }
 }
 
@@ -867,10 +929,22 @@ static int sgbm_enqueue(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_
                                                                             s->d_pre);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "sgbm_prefilter_kernel");
-    const int band_rows = ceil_div(h, SG_BANDS);
+    // row bands: every band re-computes 2*SG_R halo rows; pick the band count whose waves x rows is smallest
+    const int strips = ceil_div(W1, CK_CW);
+    int bands = 1;
+    long long best_cost = -1;
+    for (int b = 1; b <= 32 && b <= h; ++b) {
+        const long long waves = ((long long)strips * b * n + ctx->num_sms - 1) / ctx->num_sms;
+        const long long cost = waves * (ceil_div(h, b) + 2 * SG_R);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            bands = b;
+        }
+    }
+    const int band_rows = ceil_div(h, bands);
+    VSLAM_CUDA(ctx, cudaFuncSetAttribute(sgbm_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CK_SMEM));
     vslam_time_begin(ctx, VK_SGBM_COST);
-    sgbm_cost_kernel<<<dim3(ceil_div(W1, SG_TX), ceil_div(h, band_rows), n), SG_TX * SG_NDP, 0, st>>>(s->d_pre, n, w, h, W1,
-                                                                                                      band_rows, s->d_C);
+    sgbm_cost_kernel<<<dim3(strips, ceil_div(h, band_rows), n), CK_THREADS, CK_SMEM, st>>>(s->d_pre, n, w, h, W1, band_rows, s->d_C);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "sgbm_cost_kernel");
     vslam_time_begin(ctx, VK_SGBM_VERTICAL);
