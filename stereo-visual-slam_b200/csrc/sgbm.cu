@@ -109,10 +109,11 @@ __device__ __forceinline__ uint32_t bcast16(int v) { return (uint32_t)(v & 0xfff
 #define CK_CW 112                      // output columns per CTA
 #define CK_NG (CK_CW / CK_GC + 2)      // 14 output groups + one halo group on each side
 #define CK_COLS (CK_NG * CK_GC)        // 128 columns whose pixel cost the CTA computes
-#define CK_PSTR 50                     // words per column in the exchange buffer (48 + 2: groups land in different banks)
+#define CK_GSTR (CK_GC * SG_NDP + 16)   // words per column group (8 x 48 + 16: neighbouring groups start 16 banks apart)
 #define CK_NPOS 232                    // right-image positions staged per row (CK_COLS + 95 + 3, rounded up)
 #define CK_THREADS (CK_NG * CK_Q)      // 384
-#define CK_SMEM (2 * (CK_COLS + CK_NPOS) * 8 + CK_COLS * CK_PSTR * 4 + 9 * CK_CW * SG_NDP * 4)
+#define CK_RSLOT ((CK_NG - 2) * CK_GSTR)  // words per ring slot
+#define CK_SMEM ((CK_COLS + CK_NPOS) * 8 + CK_NG * CK_GSTR * 4 + 9 * CK_RSLOT * 4)
 #define CK_FF 0x00ff00ffu
 
 struct BtOps {  // widened operands of one (position pair, channel): v, min, 255 - v, 255 - max
@@ -144,9 +145,9 @@ __device__ __forceinline__ uint32_t bt_pixel_cost(const BtOps& us, const BtOps& 
 __global__ void __launch_bounds__(CK_THREADS, 1) sgbm_cost_kernel(const uint2* __restrict__ pre, int n_pairs, int W, int H, int W1,
                                                                  int band_rows, uint32_t* __restrict__ Cvol) {
     extern __shared__ __align__(16) unsigned char ck_smem[];
-    uint2* sOp = reinterpret_cast<uint2*>(ck_smem);                              // [2][CK_COLS left | CK_NPOS right]
-    uint32_t* sPd = reinterpret_cast<uint32_t*>(sOp + 2 * (CK_COLS + CK_NPOS));  // [CK_COLS][CK_PSTR]
-    uint32_t* sRing = sPd + CK_COLS * CK_PSTR;                                   // [9][CK_CW][48]
+    uint2* sOp = reinterpret_cast<uint2*>(ck_smem);                          // [CK_COLS left | CK_NPOS right]
+    uint32_t* sPd = reinterpret_cast<uint32_t*>(sOp + CK_COLS + CK_NPOS);    // [CK_NG groups][8 columns][48] (+16 pad)
+    uint32_t* sRing = sPd + CK_NG * CK_GSTR;                                 // [9][14 groups][8 columns][48] (+16 pad)
     const int t = threadIdx.x, g = t / CK_Q, q = t - g * CK_Q;
     const int x1s = blockIdx.x * CK_CW, pair = blockIdx.z;
     const int y0 = blockIdx.y * band_rows, y1 = min(y0 + band_rows, H);
@@ -160,44 +161,43 @@ __global__ void __launch_bounds__(CK_THREADS, 1) sgbm_cost_kernel(const uint2* _
     const bool out_group = g >= 1 && g <= CK_NG - 2 && nvalid > 0;
     uint32_t* Cout = Cvol + (size_t)pair * H * W1 * SG_NDP;
 
-    auto load_ops = [&](int buf, int row) {
-        const int rr = min(max(row, 0), H - 1);
-        uint2* dst = sOp + buf * (CK_COLS + CK_NPOS);
-        for (int i = t; i < CK_COLS + CK_NPOS; i += CK_THREADS) {
-            if (i < CK_COLS)
-                dst[i] = preL[(size_t)rr * W + min(max(xfirst + i, 0), W1 - 1) + SG_D];
-            else
-                dst[i] = preR[(size_t)rr * W + min(max(pb + i - CK_COLS, 0), W - 1)];
-        }
+    // one operand per thread per row (CK_COLS + CK_NPOS = 360 <= CK_THREADS): fetched early, parked in shared memory late
+    const uint2* op_src = nullptr;
+    if (t < CK_COLS) op_src = preL + min(max(xfirst + t, 0), W1 - 1) + SG_D;
+    else if (t < CK_COLS + CK_NPOS) op_src = preR + min(max(pb + t - CK_COLS, 0), W - 1);
+    auto fetch_op = [&](int row) {
+        return op_src ? op_src[(size_t)min(max(row, 0), H - 1) * W] : make_uint2(0, 0);
     };
 
     // exchange-buffer word offsets of the 16 columns under this thread's horizontal windows (borders replicated)
     int woff[2 * CK_GC];
 #pragma unroll
-    for (int k = 0; k < 2 * CK_GC; ++k) woff[k] = (min(max(xg - SG_R + k, 0), W1 - 1) - xfirst) * CK_PSTR + 2 * q;
-    uint32_t* ring = sRing + ((g - 1) * CK_GC) * SG_NDP + 2 * q;
+    for (int k = 0; k < 2 * CK_GC; ++k) {
+        const int col = min(max(xg - SG_R + k, 0), W1 - 1) - xfirst;
+        woff[k] = (col >> 3) * CK_GSTR + (col & 7) * SG_NDP + 2 * q;
+    }
+    uint32_t* ring = sRing + (g - 1) * CK_GSTR + 2 * q;
     if (out_group)
         for (int s = 0; s < 2 * SG_R + 1; ++s)
 #pragma unroll
-            for (int i = 0; i < CK_GC; ++i) *reinterpret_cast<uint2*>(ring + (s * CK_CW + i) * SG_NDP) = make_uint2(0, 0);
+            for (int i = 0; i < CK_GC; ++i) *reinterpret_cast<uint2*>(ring + s * CK_RSLOT + i * SG_NDP) = make_uint2(0, 0);
     uint32_t run0[CK_GC], run1[CK_GC];
 #pragma unroll
     for (int i = 0; i < CK_GC; ++i) run0[i] = run1[i] = 0;
     int slot = 0;
     const int r_first = y0 - SG_R, r_last = y1 - 1 + SG_R;
-    load_ops(0, r_first);
+    if (t < CK_COLS + CK_NPOS) sOp[t] = fetch_op(r_first);
     for (int row = r_first; row <= r_last; ++row) {
-        const int buf = (row - r_first) & 1;
         __syncthreads();
         // ---- phase B: pixel cost of this thread's columns -> exchange buffer ----
         if (nvalid > 0) {
-            const uint2* Lp = sOp + buf * (CK_COLS + CK_NPOS) + g * CK_GC;
-            const uint2* Rp = sOp + buf * (CK_COLS + CK_NPOS) + CK_COLS + (xg - xfirst) + (SG_D - pb + xfirst) - 4 * q;
+            const uint2* Lp = sOp + g * CK_GC;
+            const uint2* Rp = sOp + CK_COLS + (xg - xfirst) + (SG_D - pb + xfirst) - 4 * q;
             // Rp[i] = position of disparity 4q at column i; Rp[i - e] = disparity 4q + e
             uint2 w1 = Rp[-1], w2 = Rp[-2], w3 = Rp[-3];
             BtOps hs2 = bt_expand(w2.x, w3.x), hr2 = bt_expand(w2.y, w3.y);  // word-0 operands of column -2 = word 1 of column 0
             BtOps hs1 = bt_expand(w1.x, w2.x), hr1 = bt_expand(w1.y, w2.y);  // ... of column -1
-            uint32_t* pdst = sPd + (g * CK_GC) * CK_PSTR + 2 * q;
+            uint32_t* pdst = sPd + g * CK_GSTR + 2 * q;
 #pragma unroll
             for (int i = 0; i < CK_GC; ++i) {
                 if (i < nvalid) {
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(CK_THREADS, 1) sgbm_cost_kernel(const uint2* _
                     uint2 pd;
                     pd.x = bt_pixel_cost(us, ur, vs, vr);
                     pd.y = bt_pixel_cost(us, ur, hs2, hr2);
-                    *reinterpret_cast<uint2*>(pdst + i * CK_PSTR) = pd;
+                    *reinterpret_cast<uint2*>(pdst + i * SG_NDP) = pd;
                     hs2 = hs1;
                     hr2 = hr1;
                     hs1 = vs;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(CK_THREADS, 1) sgbm_cost_kernel(const uint2* _
         }
         __syncthreads();
         // ---- phase C: horizontal window in registers, vertical window through the ring, running sum, store ----
-        if (row < r_last) load_ops(buf ^ 1, row + 1);
+        const uint2 next_op = row < r_last ? fetch_op(row + 1) : make_uint2(0, 0);  // in flight during phase C
         if (out_group) {
             const int yo = row - SG_R;
             uint2 win[2 * CK_GC];
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(CK_THREADS, 1) sgbm_cost_kernel(const uint2* _
 #pragma unroll
             for (int i = 0; i < CK_GC; ++i) {
                 if (i < nvalid) {
-                    uint2* rp = reinterpret_cast<uint2*>(ring + (slot * CK_CW + i) * SG_NDP);
+                    uint2* rp = reinterpret_cast<uint2*>(ring + slot * CK_RSLOT + i * SG_NDP);
                     const uint2 old = *rp;
                     *rp = hsum;
                     run0[i] += hsum.x - old.x;
@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(CK_THREADS, 1) sgbm_cost_kernel(const uint2* _
             }
         }
         slot = slot == 2 * SG_R ? 0 : slot + 1;
+        if (t < CK_COLS + CK_NPOS) sOp[t] = next_op;  // phase B of this row finished reading before the barrier above
     }
 }
 
