@@ -174,14 +174,14 @@ def algorithmic_bytes(n_images: int, n_pairs: int, n_kp: float, n_match: float):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the ncu --set full capture under profiles/
-# (r01_v6_ncu_full_frontend_summary.json: 64 images / 32 pairs per launch), divided by the units of that launch.
+# (r01_v9_ncu_full_frontend_summary.json: 64 images / 32 pairs per launch), divided by the units of that launch.
 NCU_TRAFFIC_PER_UNIT = {
-    "fast_kernel": (93.321472e6 + 9.894656e6) / 64, "blur_kernel": (94.415360e6 + 57.704192e6) / 64,
-    "describe_kernel": (151.679744e6 + 8.143104e6) / 64, "harris_select_kernel": (85.250816e6 + 2.286080e6) / 64,
-    "hamming_argmin_kernel": 4.623616e6 / 32, "crosscheck_gate_compact_kernel": 0.529152e6 / 32,
+    "fast_kernel": (93.319168e6 + 9.874688e6) / 64, "blur_kernel": (94.490368e6 + 61.008896e6) / 64,
+    "describe_kernel": (151.682048e6 + 8.757504e6) / 64, "harris_select_kernel": (85.254400e6 + 4.321536e6) / 64,
+    "hamming_argmin_kernel": 4.623104e6 / 32, "crosscheck_gate_compact_kernel": 0.529152e6 / 32,
     "triangulate_kernel": 2.209536e6 / 32,
 }
-NCU_TRAFFIC_SOURCE = "profiles/r01_v6_ncu_full_frontend_summary.json"
+NCU_TRAFFIC_SOURCE = "profiles/r01_v9_ncu_full_frontend_summary.json"
 
 
 def run_ours(args, rank, world, local_rank):
