@@ -288,8 +288,18 @@ def run_ours(args, rank, world, local_rank):
     matches_e2e = int(out["n_matches"].sum())
     usable = int(sum(int((out["flags"][i, :out["n_matches"][i]] & 1).sum()) for i in range(B)))
 
+    # ---- secondary metric on every rank: one BA window per GPU (replicas, weak scaling) and, for N > 1, the
+    # landmark-sharded window with its per-trial all-reduce (strong scaling) ---------------------------------
+    ba_block = None
+    if args.ba:
+        try:
+            ba_block = bench_ba(ctx, pkg, args, torch, dev, dist, rank, world, stream)
+        except Exception as ex:  # the BA numbers are secondary; never lose the headline line
+            ba_block = {"error": repr(ex)}
+
     if rank != 0:
         if dist is not None:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
@@ -348,11 +358,8 @@ def run_ours(args, rank, world, local_rank):
                              "sample": f"{n_cpu} stereo pairs of the same batch through the oracle's cv2 "
                                        f"{cv2.__version__} path (ORB(2000) x2, BFMatcher crossCheck + gate, "
                                        f"triangulatePoints), cv2.setNumThreads({ncores})"}}
-    if args.ba:
-        try:
-            line["ba"] = bench_ba(ctx, pkg, args)
-        except Exception as ex:  # the BA numbers are secondary; never lose the headline line
-            line["ba"] = {"error": repr(ex)}
+    if ba_block is not None:
+        line["ba"] = ba_block
     if args.sgbm:
         try:
             line["sgbm"] = bench_sgbm(ctx, pkg, torch, dev, stream, sets[0][2][:8], sets[0][3][:8], peak)
@@ -360,6 +367,7 @@ def run_ours(args, rank, world, local_rank):
             line["sgbm"] = {"error": repr(ex)}
     print(json.dumps(line))
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -416,11 +424,15 @@ def bench_sgbm(ctx, pkg, torch, dev, stream, dl, dr, hbm_peak):
             "kernels": kern}
 
 
-def bench_ba(ctx, pkg, args):
+def bench_ba(ctx, pkg, args, torch, dev, dist, rank, world, stream):
     """Secondary metric of BASELINE.json: BA LM-iterations/s on configs[2] (K=10, L=5000) and configs[4]
     (K=50, L=20000, 100k observations), through the host-buffer C-ABI call (e2e) and kernel-only (CUDA events),
-    next to the single-thread C oracle (g2o's default build has no OpenMP)."""
-    from oracle import ba_oracle
+    next to the single-thread C oracle (g2o's default build has no OpenMP).
+
+    N GPUs: every rank optimises its own window at the same time (independent windows = replicas, no collective;
+    whole-job rate = N x iterations / max-over-ranks time), and the landmark-sharded session solves ONE window on
+    all ranks with one all-reduce of the reduced camera system per LM trial (strong scaling; at these window sizes a
+    trial is shorter than its collectives)."""
     out = {}
     for name, (seed, nk, nl, nobs, nit) in {"cfg3_K10_L5000": (42, 10, 5000, None, 10),
                                             "cfg5_K50_L20000_obs100k": (43, 50, 20000, 100000, 10)}.items():
@@ -428,6 +440,8 @@ def bench_ba(ctx, pkg, args):
         a = (p["poses"], p["points"], p["obs_pose"], p["obs_point"], p["obs_uv"], p["K"])
         for _ in range(2):
             r = ctx.ba_optimize(*a, num_iterations=nit)
+        if dist is not None:
+            dist.barrier()
         ctx.timing_enable(True)
         reps = 5
         t0 = time.perf_counter()
@@ -437,15 +451,46 @@ def bench_ba(ctx, pkg, args):
         kt = ctx.timing_read().get("ba_lm_kernel", (0.0, 1))
         ctx.timing_enable(False)
         kms = kt[0] / max(kt[1], 1)
-        t0 = time.perf_counter()
-        o = ba_oracle.optimize(*a, num_iterations=nit)
-        dt_cpu = time.perf_counter() - t0
-        rel = float(np.abs(r["poses"] - o["poses"]).max() / np.abs(o["poses"]).max())
-        out[name] = {"observations": int(len(p["obs_pose"])), "lm_iterations": r["iterations"], "lm_trials": r["trials"],
-                     "e2e_iters_per_s": r["iterations"] / dt, "kernel_iters_per_s": r["iterations"] / (kms * 1e-3),
-                     "kernel_ms": kms, "e2e_ms": dt * 1e3,
-                     "cpu_oracle_iters_per_s": o["iterations"] / dt_cpu, "cpu_cores": 1,
-                     "pose_rel_err_vs_oracle": rel, "chi2": [r["chi2_initial"], r["chi2_final"]]}
+        tt = torch.tensor([dt * 1e3, kms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms, kms = float(tt[0]), float(tt[1])
+        rec = {"observations": int(len(p["obs_pose"])), "lm_iterations": r["iterations"], "lm_trials": r["trials"],
+               "windows_in_parallel": world, "scaling": "weak (one window per GPU, no collective)",
+               "e2e_iters_per_s": world * r["iterations"] / (e2e_ms * 1e-3),
+               "kernel_iters_per_s": world * r["iterations"] / (kms * 1e-3),
+               "kernel_ms": kms, "e2e_ms": e2e_ms, "chi2": [r["chi2_initial"], r["chi2_final"]]}
+        if world > 1:
+            # strong scaling: one window, landmarks sharded over the ranks
+            shards = pkg.sharding.landmark_shards(p["obs_point"], nl, world)
+            n1, n2, n3 = pkg.ffi.ba_reduce_sizes(nk)
+            with torch.cuda.stream(stream):
+                r1, r2, r3 = (torch.zeros(n, dtype=torch.float64, device=dev) for n in (n1, n2, n3))
+                times = []
+                for _ in range(3):
+                    sess = ctx.ba_session(p, shards[rank], r1, r2, r3, num_iterations=nit)
+                    torch.cuda.synchronize(dev)
+                    dist.barrier()
+                    t0 = time.perf_counter()
+                    res = pkg.sharding.ba_optimize_sharded(sess, r1, r2, r3, nk, len(p["obs_pose"]), num_iterations=nit,
+                                                           group=dist.group.WORLD)
+                    torch.cuda.synchronize(dev)
+                    times.append(time.perf_counter() - t0)
+                    sp, _, _, _ = sess.end()
+            ts = torch.tensor([min(times[1:])], dtype=torch.float64, device=dev)
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            rec["sharded"] = {"scaling": "strong (one window, landmarks sharded, 1 all-reduce of [S|b] per LM trial)",
+                              "iters_per_s": res["iterations"] / float(ts[0]), "ms_per_iter": float(ts[0]) * 1e3 / res["iterations"],
+                              "allreduce_bytes_per_trial": 8 * (n2 + n3),
+                              "pose_rel_diff_vs_single_gpu": float(np.abs(sp - r["poses"]).max() / np.abs(r["poses"]).max())}
+        if rank == 0:
+            from oracle import ba_oracle
+            t0 = time.perf_counter()
+            o = ba_oracle.optimize(*a, num_iterations=nit)
+            dt_cpu = time.perf_counter() - t0
+            rec.update({"cpu_oracle_iters_per_s": o["iterations"] / dt_cpu, "cpu_cores": 1,
+                        "pose_rel_err_vs_oracle": float(np.abs(r["poses"] - o["poses"]).max() / np.abs(o["poses"]).max())})
+        out[name] = rec
     return out
 
 

@@ -102,3 +102,24 @@ def test_sgbm_device_entry_matches_host_entry(pkg, gpu_ctx):
     host = gpu_ctx.sgbm_compute(left, right)
     assert np.array_equal(d16.cpu().numpy(), host)
     assert np.array_equal(df.cpu().numpy(), host.astype(np.float32) / 16)
+
+
+def test_sgbm_batch_larger_than_one_chunk_and_row_pitch(pkg, gpu_ctx):
+    """11 pairs cross the 8-pair scratch chunk; the device entry reads rows at a pitch wider than the image"""
+    import torch
+    cv2 = pytest.importorskip("cv2")
+    sg = cv2.StereoSGBM_create(0, 96, 9, 8 * 81, 32 * 81, 1, 63, 10, 100, 32)
+    n, h, w, pitch = 11, 30, 150, 160
+    L = np.stack([_crop(pkg, s, h, w, y0=20 * (s % 5), x0=100 + 40 * s)[0] for s in range(n)])
+    R = np.stack([_crop(pkg, s, h, w, y0=20 * (s % 5), x0=100 + 40 * s)[1] for s in range(n)])
+    ref = np.stack([sg.compute(L[i], R[i]) for i in range(n)])
+    assert np.array_equal(gpu_ctx.sgbm_compute(L, R), ref)
+    padl = np.full((n, h, pitch), 255, np.uint8)
+    padr = np.full((n, h, pitch), 255, np.uint8)
+    padl[:, :, :w], padr[:, :, :w] = L, R
+    dl, dr = torch.from_numpy(padl).cuda(), torch.from_numpy(padr).cuda()
+    d16 = torch.empty((n, h, w), dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
+    gpu_ctx.sgbm_compute_dev(dl, dr, n, w, h, pitch, pitch * h, d16)
+    gpu_ctx.synchronize()
+    assert np.array_equal(d16.cpu().numpy(), ref)
