@@ -519,49 +519,6 @@ __device__ __forceinline__ bool chol6_diag(double* M, int ld, int j0, double* ri
     return ok;
 }
 
-// blocked triangular solves U^T y = bs, U x = y by one CTA; U row-major with leading dimension n; y: n doubles of scratch
-__device__ void ba_tri_solve_cta(const BaParams& P, const double* U, double* y) {
-    const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < n; i += nt) y[i] = P.bs[i];
-    __syncthreads();
-    for (int j0 = 0; j0 < n; j0 += 6) {  // forward
-        if (tid == 0) {
-            for (int r = 0; r < 6; ++r) {
-                double v = y[j0 + r];
-                for (int p = 0; p < r; ++p) v -= U[(j0 + p) * n + j0 + r] * y[j0 + p];
-                y[j0 + r] = v / U[(j0 + r) * n + j0 + r];  // thread-0 stage of the large-system path
-            }
-        }
-        __syncthreads();
-        for (int c = j0 + 6 + tid; c < n; c += nt) {
-            double v = y[c];
-#pragma unroll
-            for (int p = 0; p < 6; ++p) v -= U[(j0 + p) * n + c] * y[j0 + p];
-            y[c] = v;
-        }
-        __syncthreads();
-    }
-    for (int j0 = n - 6; j0 >= 0; j0 -= 6) {  // backward
-        if (tid == 0) {
-            for (int r = 5; r >= 0; --r) {
-                double v = y[j0 + r];
-                for (int p = r + 1; p < 6; ++p) v -= U[(j0 + r) * n + j0 + p] * y[j0 + p];
-                y[j0 + r] = v / U[(j0 + r) * n + j0 + r];
-            }
-        }
-        __syncthreads();
-        for (int r = tid; r < j0; r += nt) {
-            double v = y[r];
-#pragma unroll
-            for (int p = 0; p < 6; ++p) v -= U[r * n + j0 + p] * y[j0 + p];
-            y[r] = v;
-        }
-        __syncthreads();
-    }
-    for (int i = tid; i < n; i += nt) P.x[i] = y[i];
-    __syncthreads();
-}
-
 // small systems (6K <= 160): everything in the shared memory of CTA 0.  The right-hand side rides along as column n of
 // the augmented matrix [S | bs] (so the forward substitution happens inside the factorisation), every thread factors
 // the 6x6 diagonal block redundantly in registers (no serial single-thread stage), and the backward substitution is
@@ -658,68 +615,152 @@ __device__ void ba_phase_solve_cta(const BaParams& P, int slot, double* smem) {
     if (tid == 0) P.sc->solve_ok[slot] = fail ? 0 : 1;
 }
 
-// large systems (6K > 160): S stays in L2.  Per block row every CTA redundantly factors the diagonal block and the
-// 6 x m panel into its own shared memory (cheap), then all threads of the grid share the rank-6 trailing update:
-// ONE grid-wide barrier per block row (K of them) instead of one per column.  CTA 0 keeps the factor rows in Ubuf.
+// large systems (6K > 160): S stays in L2 and is factored in panels of BA_NB = 30 rows (5 pose blocks).  Every CTA loads
+// the panel [S | bs](J0 .. J0+30, J0 .. n] into its own shared memory and factors it redundantly (6x6 diagonal blocks
+// in registers by every thread, forward substitution of the panel columns and of the right-hand side spread over the
+// threads, 3 block barriers per 6 rows); then the whole grid shares the rank-30 trailing update of S and bs.  ONE
+// grid-wide barrier per panel: 10 for K = 50 instead of one per block row.  CTA 0 keeps the factor rows in Ubuf and the
+// forward-substituted right-hand side in x, and finishes with the blocked backward substitution (diagonal blocks
+// staged in shared memory once).
+#define BA_NB 30
 __device__ void ba_phase_solve_grid(const BaParams& P, int slot, cg::grid_group& grid, double* smem, double* Ubuf,
                                     int gtid, int gsize) {
-    const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
+    const int n = P.n, ld = P.n + 1, tid = threadIdx.x, nt = blockDim.x;
     __shared__ int s_fail;
-    double* D = smem;            // 6 x 6 diagonal block (ld 6)
-    double* Up = smem + 36;      // 6 x n panel (ld n), columns >= j0 + 6 valid
+    double* Pn = smem;  // BA_NB x ld, columns J0 .. n valid (column n = right-hand side)
     int fail = 0;
-    for (int j0 = 0; j0 < n; j0 += 6) {
-        if (tid < 36) D[tid] = P.S[(size_t)(j0 + tid / 6) * n + j0 + tid % 6];
+    for (int J0 = 0; J0 < n; J0 += BA_NB) {
+        const int nb = min(BA_NB, n - J0), wcols = n - J0;
         if (tid == 0) s_fail = 0;
+        for (int e = tid; e < nb * (wcols + 1); e += nt) {
+            const int r = e / (wcols + 1), cc = e - r * (wcols + 1);
+            Pn[r * ld + J0 + cc] = cc < wcols ? P.S[(size_t)(J0 + r) * n + J0 + cc] : P.bs[J0 + r];
+        }
         __syncthreads();
-        double Dr[36], rinv[6];
+        for (int j = 0; j < nb; j += 6) {
+            const int c0 = J0 + j;  // column of this diagonal block
+            double Dr[36], rinv[6];
 #pragma unroll
-        for (int q = 0; q < 36; ++q) Dr[q] = ((q % 6) >= (q / 6)) ? D[q] : 0.0;
-        const bool ok = chol6_diag(Dr, 6, 0, rinv);  // every thread, in registers
-        __syncthreads();
-        if (tid == 0 && !ok) s_fail = 1;
-        if (tid < 36) D[tid] = Dr[tid];
-        __syncthreads();
-        if (s_fail) {  // uniform over the grid: every CTA factors the same block
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) Dr[r * 6 + c] = (c >= r) ? Pn[(j + r) * ld + c0 + c] : 0.0;
+            const bool ok = chol6_diag(Dr, 6, 0, rinv);  // every thread, in registers
+            for (int c = c0 + 6 + tid; c <= n; c += nt) {  // block row of the panel and the rhs column c == n
+                double v[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) v[r] = Pn[(j + r) * ld + c];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q)
+                        if (q < r) v[r] -= Dr[q * 6 + r] * v[q];
+                    v[r] *= rinv[r];
+                }
+#pragma unroll
+                for (int r = 0; r < 6; ++r) Pn[(j + r) * ld + c] = v[r];
+            }
+            __syncthreads();  // block row done; everyone has read the un-factored diagonal block
+            if (tid == 0) {   // nobody reads this diagonal block again inside the panel
+                if (!ok) s_fail = 1;
+#pragma unroll
+                for (int r = 0; r < 6; ++r)
+#pragma unroll
+                    for (int c = 0; c < 6; ++c)
+                        if (c >= r) Pn[(j + r) * ld + c0 + c] = Dr[r * 6 + c];
+            }
+            const int mr = nb - j - 6, mc = n + 1 - (c0 + 6);  // rows of the panel still to factor x columns c0+6 .. n
+            for (int e = tid; e < mr * mc; e += nt) {
+                const int r2 = j + 6 + e / mc, c = c0 + 6 + e % mc;
+                if (c < J0 + r2) continue;
+                double v = Pn[r2 * ld + c];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) v -= Pn[(j + q) * ld + J0 + r2] * Pn[(j + q) * ld + c];
+                Pn[r2 * ld + c] = v;
+            }
+            __syncthreads();
+            if (s_fail) break;
+        }
+        if (s_fail) {  // uniform over the grid: every CTA factors the same panel
             fail = 1;
             break;
         }
-        for (int c = j0 + 6 + tid; c < n; c += nt) {
-            double v[6];
-#pragma unroll
-            for (int r = 0; r < 6; ++r) v[r] = P.S[(size_t)(j0 + r) * n + c];
-#pragma unroll
-            for (int r = 0; r < 6; ++r) {
-#pragma unroll
-                for (int p = 0; p < 6; ++p)
-                    if (p < r) v[r] -= Dr[p * 6 + r] * v[p];
-                v[r] *= rinv[r];
-                Up[r * n + c] = v[r];
-            }
-        }
-        __syncthreads();
         if (blockIdx.x == 0) {
-            if (tid < 36) Ubuf[(size_t)(j0 + tid / 6) * n + j0 + tid % 6] = D[tid];
-            for (int e = tid; e < 6 * (n - j0 - 6); e += nt) {
-                const int r = e / (n - j0 - 6), c = j0 + 6 + e % (n - j0 - 6);
-                Ubuf[(size_t)(j0 + r) * n + c] = Up[r * n + c];
+            for (int e = tid; e < nb * wcols; e += nt) {
+                const int r = e / wcols, cc = e - r * wcols;
+                if (cc >= r) Ubuf[(size_t)(J0 + r) * n + J0 + cc] = Pn[r * ld + J0 + cc];
             }
+            for (int r = tid; r < nb; r += nt) P.x[J0 + r] = Pn[r * ld + n];  // y = U^-T bs
         }
-        const int m = n - j0 - 6;
-        for (int e = gtid; e < m * m; e += gsize) {
-            const int r = j0 + 6 + e / m, c = j0 + 6 + e % m;
+        const int m = n - J0 - nb;
+        for (int e = gtid; e < m * (m + 1); e += gsize) {
+            const int r = J0 + nb + e / (m + 1), cc = e % (m + 1);
+            const int c = cc < m ? J0 + nb + cc : n;
             if (c < r) continue;
-            double v = P.S[(size_t)r * n + c];
-#pragma unroll
-            for (int p = 0; p < 6; ++p) v -= Up[p * n + r] * Up[p * n + c];
-            P.S[(size_t)r * n + c] = v;
+            double v = c < n ? P.S[(size_t)r * n + c] : P.bs[r];
+#pragma unroll 6
+            for (int q = 0; q < nb; ++q) v -= Pn[q * ld + r] * Pn[q * ld + c];
+            if (c < n) P.S[(size_t)r * n + c] = v;
+            else P.bs[r] = v;
         }
         grid.sync();
     }
     if (!fail && blockIdx.x == 0) {
-        __threadfence();
+        // backward substitution U x = y by CTA 0: y and the 6x6 diagonal blocks live in shared memory
+        double* y = smem;
+        double* Dg = smem + n;  // [n / 6][36]
+        for (int i = tid; i < n; i += nt) y[i] = P.x[i];
+        for (int e = tid; e < n * 6; e += nt) {
+            const int blk = e / 36, q = e - blk * 36;
+            Dg[e] = Ubuf[(size_t)(blk * 6 + q / 6) * n + blk * 6 + q % 6];
+        }
         __syncthreads();
-        ba_tri_solve_cta(P, Ubuf, smem);
+        // each thread owns rows tid and tid + nt (n <= 2 nt) and fetches their 6 factor entries one block step ahead
+        double un[2][6];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int r = tid + k * nt;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) un[k][q] = r < n - 6 ? Ubuf[(size_t)r * n + n - 6 + q] : 0.0;
+        }
+        for (int j0 = n - 6; j0 >= 0; j0 -= 6) {
+            const double* D = Dg + (j0 / 6) * 36;
+            double x[6], rinv[6], uc[2][6];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int r = tid + k * nt;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    uc[k][q] = un[k][q];
+                    un[k][q] = (j0 >= 6 && r < j0 - 6) ? Ubuf[(size_t)r * n + j0 - 6 + q] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                x[r] = y[j0 + r];
+                rinv[r] = 1.0 / D[r * 6 + r];  // six independent divisions, pipelined
+            }
+#pragma unroll
+            for (int r = 5; r >= 0; --r) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q)
+                    if (q > r) x[r] -= D[r * 6 + q] * x[q];
+                x[r] *= rinv[r];
+            }
+            __syncthreads();  // everyone has read y_j
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int r = tid + k * nt;
+                if (r < j0) {
+                    double v = y[r];
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) v -= uc[k][q] * x[q];
+                    y[r] = v;
+                }
+            }
+            if (tid < 6) y[j0 + tid] = x[tid];
+            __syncthreads();
+        }
+        for (int i = tid; i < n; i += nt) P.x[i] = y[i];
     }
     if (gtid == 0) P.sc->solve_ok[slot] = fail ? 0 : 1;
 }
@@ -1000,7 +1041,7 @@ static int ba_smem_bytes(int K) {
     const size_t n = 6 * (size_t)K;
     size_t need = (BA_THREADS / 32) * 42;  // block-reduction scratch of the BUILD-B / SCHUR phases
     if (n <= BA_SMEM_CHOL_MAX && n * n + n > need) need = n * n + n;     // in-shared-memory augmented system [S | bs]
-    if (n > BA_SMEM_CHOL_MAX && 36 + 6 * n > need) need = 36 + 6 * n;    // grid-wide solver: diagonal block + panel
+    if (n > BA_SMEM_CHOL_MAX && 30 * (n + 1) > need) need = 30 * (n + 1);  // grid-wide solver: BA_NB x (n + 1) panel (>= 7n)
     return (int)(need * sizeof(double));
 }
 
