@@ -259,19 +259,27 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// try_wait suspends for a hardware-defined time slice per call; a copy that never lands (a bad address) traps after
+// 2^24 slices instead of hanging the device.  Takes a shared-window address.
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {
     asm volatile(
         "{\n"
-        ".reg .pred p;\n"
+        ".reg .pred p, q;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, 0;\n"
         "SG_WAIT:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra.uni SG_DONE;\n"
-        "bra.uni SG_WAIT;\n"
+        "add.u32 n, n, 1;\n"
+        "setp.lt.u32 q, n, 16777216;\n"
+        "@q bra.uni SG_WAIT;\n"
+        "trap;\n"
         "SG_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
+        "}\n" ::"r"(bar_addr),
         "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_a(smem_u32(bar), parity); }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -330,8 +338,8 @@ __device__ __forceinline__ void sgm_step(uint32_t& a0, uint32_t& a1, uint32_t& m
 
 template <int DX>
 __device__ __forceinline__ void vertical_cta(const unsigned char* __restrict__ gC, unsigned char* __restrict__ gL, int k0, int W1,
-                                             int H, uint32_t P1b, uint32_t P2b, unsigned char* ring, unsigned char* outb,
-                                             uint64_t* full, uint64_t* empty) {
+                                             int H, uint32_t P1b, uint32_t P2b, unsigned char* ring, uint64_t* full,
+                                             uint64_t* empty) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nact = min(VT_WARPS, W1 - k0);  // paths of this CTA
     if (threadIdx.x == 0) {
@@ -367,22 +375,34 @@ __device__ __forceinline__ void vertical_cta(const unsigned char* __restrict__ g
     const int src_up = (lane + 31) & 31;
     uint32_t a0 = active ? 0u : SG_BIG2, a1 = a0, mm = 0;
     int x = k0 + w;
+    // everything the row loop touches is a 32-bit shared address plus an immediate, or a pointer advanced by a constant
+    const uint32_t ring_a = smem_u32(ring) + w * (SG_D * 2) + lane * 8, full_a = smem_u32(full), empty_a = smem_u32(empty);
+    unsigned char* gp = gL + (size_t)x * (SG_D * 2) + lane * 8;
+    const long long rowstep = (long long)(W1 + DX) * (SG_D * 2), wrapfix = (long long)W1 * (SG_D * 2);
+#pragma unroll 2
     for (int y = 0; y < H; ++y) {
-        const int s = y % VT_NST;
-        mbar_wait(&full[s], (y / VT_NST) & 1);
+        const uint32_t s = y & (VT_NST - 1), par = (y / VT_NST) & 1;
+        mbar_wait_a(full_a + s * 8, par);
         uint2 c = make_uint2(SG_CPAD, SG_CPAD);
-        if (active) c = reinterpret_cast<const uint2*>(ring + s * (VT_WARPS * SG_D * 2) + w * (SG_D * 2))[lane];
+        if (active) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(c.x), "=r"(c.y) : "r"(ring_a + s * (VT_WARPS * SG_D * 2)));
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_a + s * 8) : "memory");
         if (DX != 0 && x == (DX > 0 ? 0 : W1 - 1)) {
             a0 = a1 = active ? 0u : SG_BIG2;
             mm = 0;
         }
         sgm_step(a0, a1, mm, c.x, c.y, P1b, P2b, src_up);
-        if (active) __stcs(reinterpret_cast<uint2*>(gL + ((size_t)y * W1 + x) * (SG_D * 2)) + lane, make_uint2(a0, a1));
+        if (active) __stcs(reinterpret_cast<uint2*>(gp), make_uint2(a0, a1));
         x += DX;
-        if (DX > 0 && x == W1) x = 0;
-        if (DX < 0 && x < 0) x = W1 - 1;
+        gp += rowstep;
+        if (DX > 0 && x == W1) {
+            x = 0;
+            gp -= wrapfix;
+        }
+        if (DX < 0 && x < 0) {
+            x = W1 - 1;
+            gp += wrapfix;
+        }
     }
 }
 
@@ -390,16 +410,15 @@ __global__ void __launch_bounds__((VT_WARPS + 1) * 32) sgbm_vertical_kernel(cons
                                                                            uint32_t* __restrict__ L1v, uint32_t* __restrict__ L2v,
                                                                            int W1, int H, int P1, int P2) {
     __shared__ __align__(128) unsigned char ring[VT_NST * VT_WARPS * SG_D * 2];
-    __shared__ __align__(128) unsigned char outb[VT_WARPS * 2 * SG_D * 2];
     __shared__ uint64_t full[VT_NST], empty[VT_NST];
     const int k0 = blockIdx.x * VT_WARPS;
     const int dir = blockIdx.y, pair = blockIdx.z;
     const size_t vol = (size_t)pair * H * W1 * (SG_D * 2);
     const unsigned char* gC = reinterpret_cast<const unsigned char*>(Cvol) + vol;
     const uint32_t P1b = bcast16(P1), P2b = bcast16(P2);
-    if (dir == 0) vertical_cta<1>(gC, reinterpret_cast<unsigned char*>(L0v) + vol, k0, W1, H, P1b, P2b, ring, outb, full, empty);
-    else if (dir == 1) vertical_cta<0>(gC, reinterpret_cast<unsigned char*>(L1v) + vol, k0, W1, H, P1b, P2b, ring, outb, full, empty);
-    else vertical_cta<-1>(gC, reinterpret_cast<unsigned char*>(L2v) + vol, k0, W1, H, P1b, P2b, ring, outb, full, empty);
+    if (dir == 0) vertical_cta<1>(gC, reinterpret_cast<unsigned char*>(L0v) + vol, k0, W1, H, P1b, P2b, ring, full, empty);
+    else if (dir == 1) vertical_cta<0>(gC, reinterpret_cast<unsigned char*>(L1v) + vol, k0, W1, H, P1b, P2b, ring, full, empty);
+    else vertical_cta<-1>(gC, reinterpret_cast<unsigned char*>(L2v) + vol, k0, W1, H, P1b, P2b, ring, full, empty);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
