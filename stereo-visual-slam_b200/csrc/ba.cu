@@ -627,25 +627,31 @@ __device__ void ba_phase_solve_grid(const BaParams& P, int slot, cg::grid_group&
                                     int gtid, int gsize) {
     const int n = P.n, ld = P.n + 1, tid = threadIdx.x, nt = blockDim.x;
     __shared__ int s_fail;
+    __shared__ double s_rinv[BA_NB];  // reciprocal diagonal of the factored nb x nb block
     double* Pn = smem;  // BA_NB x ld, columns J0 .. n valid (column n = right-hand side)
     int fail = 0;
     for (int J0 = 0; J0 < n; J0 += BA_NB) {
         const int nb = min(BA_NB, n - J0), wcols = n - J0;
         if (tid == 0) s_fail = 0;
-        for (int e = tid; e < nb * (wcols + 1); e += nt) {
-            const int r = e / (wcols + 1), cc = e - r * (wcols + 1);
-            Pn[r * ld + J0 + cc] = cc < wcols ? P.S[(size_t)(J0 + r) * n + J0 + cc] : P.bs[J0 + r];
+        // panel load: row by row, unrolled so that a thread has a dozen independent L2 reads in flight
+        for (int cc = tid; cc < wcols; cc += nt) {
+#pragma unroll 6
+            for (int r = 0; r < BA_NB; ++r)
+                if (r < nb) Pn[r * ld + J0 + cc] = P.S[(size_t)(J0 + r) * n + J0 + cc];
         }
+        if (tid < nb) Pn[tid * ld + n] = P.bs[J0 + tid];
         __syncthreads();
+        // (1) the nb x nb diagonal block, 6x6-blocked, inside shared memory (tiny: every step is a few dozen entries)
+        const int cend = J0 + nb;  // first column right of the diagonal block
         for (int j = 0; j < nb; j += 6) {
-            const int c0 = J0 + j;  // column of this diagonal block
+            const int c0 = J0 + j;  // column of this 6x6 block
             double Dr[36], rinv[6];
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
                 for (int c = 0; c < 6; ++c) Dr[r * 6 + c] = (c >= r) ? Pn[(j + r) * ld + c0 + c] : 0.0;
             const bool ok = chol6_diag(Dr, 6, 0, rinv);  // every thread, in registers
-            for (int c = c0 + 6 + tid; c <= n; c += nt) {  // block row of the panel and the rhs column c == n
+            for (int c = c0 + 6 + tid; c < cend; c += nt) {
                 double v[6];
 #pragma unroll
                 for (int r = 0; r < 6; ++r) v[r] = Pn[(j + r) * ld + c];
@@ -659,18 +665,20 @@ __device__ void ba_phase_solve_grid(const BaParams& P, int slot, cg::grid_group&
 #pragma unroll
                 for (int r = 0; r < 6; ++r) Pn[(j + r) * ld + c] = v[r];
             }
-            __syncthreads();  // block row done; everyone has read the un-factored diagonal block
-            if (tid == 0) {   // nobody reads this diagonal block again inside the panel
+            __syncthreads();  // block row done; everyone has read the un-factored 6x6 block
+            if (tid == 0) {
                 if (!ok) s_fail = 1;
 #pragma unroll
-                for (int r = 0; r < 6; ++r)
+                for (int r = 0; r < 6; ++r) {
 #pragma unroll
                     for (int c = 0; c < 6; ++c)
                         if (c >= r) Pn[(j + r) * ld + c0 + c] = Dr[r * 6 + c];
+                    s_rinv[j + r] = rinv[r];
+                }
             }
-            const int mr = nb - j - 6, mc = n + 1 - (c0 + 6);  // rows of the panel still to factor x columns c0+6 .. n
-            for (int e = tid; e < mr * mc; e += nt) {
-                const int r2 = j + 6 + e / mc, c = c0 + 6 + e % mc;
+            const int mr = nb - j - 6;  // rows of the diagonal block still to factor
+            for (int e = tid; e < mr * mr; e += nt) {
+                const int r2 = j + 6 + e / mr, c = c0 + 6 + e % mr;
                 if (c < J0 + r2) continue;
                 double v = Pn[r2 * ld + c];
 #pragma unroll
@@ -680,6 +688,40 @@ __device__ void ba_phase_solve_grid(const BaParams& P, int slot, cg::grid_group&
             __syncthreads();
             if (s_fail) break;
         }
+        // (2) the panel right of it and the right-hand side: one thread per column runs the whole nb-step forward
+        // substitution in registers against the factored block (broadcast reads), no barrier inside.  Each entry first
+        // collects the contributions of the finished 6-row groups in four independent accumulators (short dependency
+        // chains), then the 6x6 triangle of its own group.
+        if (!s_fail) {
+            for (int c = cend + tid; c <= n; c += nt) {
+                double v[BA_NB];
+#pragma unroll
+                for (int r = 0; r < BA_NB; ++r) v[r] = r < nb ? Pn[r * ld + c] : 0.0;
+#pragma unroll
+                for (int g0 = 0; g0 < BA_NB; g0 += 6) {
+                    if (g0 < nb) {
+#pragma unroll
+                        for (int r = g0; r < g0 + 6; ++r) {
+                            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                            for (int q = 0; q < g0; ++q) acc[q & 3] += Pn[q * ld + J0 + r] * v[q];
+                            v[r] -= (acc[0] + acc[1]) + (acc[2] + acc[3]);
+                        }
+#pragma unroll
+                        for (int r = g0; r < g0 + 6; ++r) {
+#pragma unroll
+                            for (int q = g0; q < g0 + 6; ++q)
+                                if (q < r) v[r] -= Pn[q * ld + J0 + r] * v[q];
+                            v[r] *= s_rinv[r];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < BA_NB; ++r)
+                    if (r < nb) Pn[r * ld + c] = v[r];
+            }
+        }
+        __syncthreads();
         if (s_fail) {  // uniform over the grid: every CTA factors the same panel
             fail = 1;
             break;
