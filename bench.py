@@ -146,7 +146,7 @@ def run_reference(args, rank, world):
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "configs[1]: 1241x376 synthetic stereo pairs, 2000 ORB kp, detect+match+triangulate",
                        "pairs_per_step": sample},
-            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": ncores, "kind": "reference",
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": ncores, "kind": "port",
                              "sample": f"{sample} stereo pairs/step x {args.steps} steps; live cv2 {cv2.__version__} "
                                        "(cv::ORB(2000) detectAndCompute x2, BFMatcher crossCheck + gate, "
                                        "triangulatePoints) = the OpenCV calls of the reference's VO path, "
