@@ -340,6 +340,26 @@ def run_ours(args, rank, world, local_rank):
         cv2_frontend(cv2, V, Ls[n_cpu], Rs[n_cpu], P1, P2)
         n_cpu += 1
     cpu_fps = n_cpu / (time.perf_counter() - t0)
+    # the same path on one thread and stage by stage: median of 5 on pair 0
+    def _med(fn, reps=5):
+        ts = []
+        for _ in range(reps):
+            t1 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t1)
+        return float(np.median(ts) * 1e3)
+    orb = cv2.ORB_create(NFEAT)
+    kl0, dl0 = orb.detectAndCompute(Ls[0], None)
+    kr0, dr0 = orb.detectAndCompute(Rs[0], None)
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True)
+    stages = {"threads": ncores,
+              "orb_detect_ms": _med(lambda: orb.detect(Ls[0], None)),
+              "orb_compute_ms": _med(lambda: orb.compute(Ls[0], kl0)),
+              "bf_match_ms": _med(lambda: bf.match(dl0, dr0))}
+    cv2.setNumThreads(1)
+    stages_1t = {"threads": 1, "frontend_pair_ms": _med(lambda: cv2_frontend(cv2, V, Ls[0], Rs[0], P1, P2), 3),
+                 "bf_match_ms": _med(lambda: bf.match(dl0, dr0), 3)}
+    cv2.setNumThreads(ncores)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -357,7 +377,8 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": {"value": cpu_fps, "unit": UNIT, "cores": ncores, "kind": "port",
                              "sample": f"{n_cpu} stereo pairs of the same batch through the oracle's cv2 "
                                        f"{cv2.__version__} path (ORB(2000) x2, BFMatcher crossCheck + gate, "
-                                       f"triangulatePoints), cv2.setNumThreads({ncores})"}}
+                                       f"triangulatePoints), cv2.setNumThreads({ncores})",
+                             "stages_ms": stages, "single_thread": stages_1t}}
     if ba_block is not None:
         line["ba"] = ba_block
     if args.sgbm:

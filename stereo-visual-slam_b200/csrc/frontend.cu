@@ -12,7 +12,7 @@
 
 #include <stdlib.h>
 
-#define FRONT_CHUNK_PAIRS 16   // pairs per pipeline chunk (32 images keep every kernel's grid >= 2 waves)
+#define FRONT_CHUNK_PAIRS 32   // pairs per pipeline chunk
 #define FRONT_MAX_CHUNKS 64
 
 struct FrontState {
@@ -181,10 +181,10 @@ int vslam_front_init(vslam_ctx* ctx) {
     VSLAM_CUDA(ctx, cudaMalloc(&f->d_xr, cap * 2 * sizeof(float)));
     VSLAM_CUDA(ctx, cudaStreamCreateWithFlags(&f->s_in, cudaStreamNonBlocking));
     VSLAM_CUDA(ctx, cudaStreamCreateWithFlags(&f->s_out, cudaStreamNonBlocking));
-    VSLAM_CUDA(ctx, cudaEventCreateWithFlags(&f->ev_start, cudaEventDisableTiming));
+    VSLAM_CUDA(ctx, cudaEventCreate(&f->ev_start));
     for (int i = 0; i < FRONT_MAX_CHUNKS; ++i) {
-        VSLAM_CUDA(ctx, cudaEventCreateWithFlags(&f->ev_in[i], cudaEventDisableTiming));
-        VSLAM_CUDA(ctx, cudaEventCreateWithFlags(&f->ev_done[i], cudaEventDisableTiming));
+        VSLAM_CUDA(ctx, cudaEventCreate(&f->ev_in[i]));
+        VSLAM_CUDA(ctx, cudaEventCreate(&f->ev_done[i]));
     }
     return VSLAM_OK;
 }
@@ -335,16 +335,25 @@ extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, 
     uint8_t* dl = f->d_img;
     uint8_t* dr = f->d_img + (size_t)n_pairs * dstride;
     const size_t cap = (size_t)f->kp_cap, np = (size_t)n_pairs;
-    int chunk = FRONT_CHUNK_PAIRS;
-    if (ceil_div(n_pairs, chunk) > FRONT_MAX_CHUNKS) chunk = ceil_div(n_pairs, FRONT_MAX_CHUNKS);
-    const int n_chunks = ceil_div(n_pairs, chunk);
+    // chunk schedule: equal chunks.  Every chunk costs ~0.35 ms of launch tails on top of ~48 us per pair (measured with
+    // VSLAM_FRONT_TRACE=1), so ramping the pipeline up with small chunks loses more than the exposed first upload costs.
+    int c_start[FRONT_MAX_CHUNKS + 1], n_chunks = 0;
+    {
+        int chunk = FRONT_CHUNK_PAIRS;
+        if (ceil_div(n_pairs, chunk) > FRONT_MAX_CHUNKS) chunk = ceil_div(n_pairs, FRONT_MAX_CHUNKS);
+        c_start[0] = 0;
+        for (int done = 0; done < n_pairs;) {
+            done += n_pairs - done < chunk ? n_pairs - done : chunk;
+            c_start[++n_chunks] = done;
+        }
+    }
     // the copy streams start after whatever the caller already queued on the context stream
     VSLAM_CUDA(ctx, cudaEventRecord(f->ev_start, s));
     VSLAM_CUDA(ctx, cudaStreamWaitEvent(f->s_in, f->ev_start, 0));
     VSLAM_CUDA(ctx, cudaStreamWaitEvent(f->s_out, f->ev_start, 0));
     if (T_c_w) VSLAM_CUDA(ctx, cudaMemcpyAsync(f->d_pose, T_c_w, np * 96, cudaMemcpyHostToDevice, f->s_in));
     for (int c = 0; c < n_chunks; ++c) {  // all uploads are queued up front; they run back to back on the H2D engine
-        const int p0 = c * chunk, nc = n_pairs - p0 < chunk ? n_pairs - p0 : chunk;
+        const int p0 = c_start[c], nc = c_start[c + 1] - p0;
         if (contiguous) {
             VSLAM_CUDA(ctx, cudaMemcpyAsync(dl + p0 * dstride, left + (size_t)p0 * image_stride, dstride * nc,
                                             cudaMemcpyHostToDevice, f->s_in));
@@ -361,7 +370,7 @@ extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, 
         VSLAM_CUDA(ctx, cudaEventRecord(f->ev_in[c], f->s_in));
     }
     for (int c = 0; c < n_chunks; ++c) {
-        const int p0 = c * chunk, nc = n_pairs - p0 < chunk ? n_pairs - p0 : chunk;
+        const int p0 = c_start[c], nc = c_start[c + 1] - p0;
         VSLAM_CUDA(ctx, cudaStreamWaitEvent(s, f->ev_in[c], 0));
         int st = front_enqueue_chunk(ctx, dl + p0 * dstride, dr + p0 * dstride, n_pairs, p0, nc, width, height, dpitch,
                                      (long long)dstride, nfeatures, anms_keep, anms_c, gate_rel, gate_abs, P1, P2,
@@ -389,5 +398,13 @@ extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, 
     VSLAM_CUDA(ctx, cudaMemcpyAsync(n_matches, f->d_nmatch, np * sizeof(int32_t), cudaMemcpyDeviceToHost, f->s_out));
     const int st = vslam_orb_check_flags(ctx, 2 * n_pairs);  // synchronises the context stream
     VSLAM_CUDA(ctx, cudaStreamSynchronize(f->s_out));
+    if (getenv("VSLAM_FRONT_TRACE")) {  // pipeline trace: when each chunk's upload and kernels finished, ms after the call began
+        for (int c = 0; c < n_chunks; ++c) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, f->ev_start, f->ev_in[c]);
+            cudaEventElapsedTime(&b, f->ev_start, f->ev_done[c]);
+            fprintf(stderr, "[front] chunk %d pairs %d..%d  h2d done %.3f ms  kernels done %.3f ms\n", c, c_start[c], c_start[c + 1], a, b);
+        }
+    }
     return st;  // VSLAM_E_OVERFLOW if a work list overflowed
 }
