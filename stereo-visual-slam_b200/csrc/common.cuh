@@ -98,8 +98,16 @@ struct ImgSrc {
 };
 
 // internal cross-module entry points
+// scratch0: first image slot of the context's scratch (pyramids, candidate lists ...) this call may use; calls on
+// different streams must use disjoint slot ranges
 int vslam_orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h, int nfeatures, int anms_keep,
-                      float anms_c, vslam_keypoint* d_kp, uint8_t* d_desc, int32_t* d_n);
+                      float anms_c, vslam_keypoint* d_kp, uint8_t* d_desc, int32_t* d_n, int scratch0);
+int vslam_orb_prepare(vslam_ctx* ctx, int w, int h);  // upload the per-geometry tables on the context stream
+// vslam_match_hamming_batch_dev on the key scratch of pairs [scratch_pair0, scratch_pair0 + batch)
+int vslam_match_enqueue(vslam_ctx* ctx, const uint8_t* d_query, const int32_t* d_nq, int q_stride_rows,
+                        const uint8_t* d_train, const int32_t* d_nt, int t_stride_rows, int batch, int max_rows,
+                        int cross_check, double gate_rel, double gate_abs, vslam_dmatch* d_out, int out_stride,
+                        int32_t* d_n_out, int scratch_pair0);
 int vslam_orb_check_flags(vslam_ctx* ctx, int n_img);  // synchronises the stream; reads and clears the sticky flags
 
 // sub-module lifetime hooks (each .cu owns its state)

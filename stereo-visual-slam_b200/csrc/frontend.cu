@@ -33,6 +33,8 @@ struct FrontState {
     int max_pairs, kp_cap;
     // chunked host-buffer pipeline: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of chunk c
     cudaStream_t s_in, s_out;
+    cudaStream_t s_alt;  // second compute stream: odd chunks run here so that one chunk's launch tails overlap the next
+    cudaEvent_t ev_join;
     cudaEvent_t ev_in[FRONT_MAX_CHUNKS], ev_done[FRONT_MAX_CHUNKS], ev_start;
 };
 
@@ -181,6 +183,8 @@ int vslam_front_init(vslam_ctx* ctx) {
     VSLAM_CUDA(ctx, cudaMalloc(&f->d_xr, cap * 2 * sizeof(float)));
     VSLAM_CUDA(ctx, cudaStreamCreateWithFlags(&f->s_in, cudaStreamNonBlocking));
     VSLAM_CUDA(ctx, cudaStreamCreateWithFlags(&f->s_out, cudaStreamNonBlocking));
+    VSLAM_CUDA(ctx, cudaStreamCreateWithFlags(&f->s_alt, cudaStreamNonBlocking));
+    VSLAM_CUDA(ctx, cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming));
     VSLAM_CUDA(ctx, cudaEventCreate(&f->ev_start));
     for (int i = 0; i < FRONT_MAX_CHUNKS; ++i) {
         VSLAM_CUDA(ctx, cudaEventCreate(&f->ev_in[i]));
@@ -205,6 +209,8 @@ void vslam_front_free(vslam_ctx* ctx) {
     cudaFree(f->d_xr);
     if (f->s_in) cudaStreamDestroy(f->s_in);
     if (f->s_out) cudaStreamDestroy(f->s_out);
+    if (f->s_alt) cudaStreamDestroy(f->s_alt);
+    if (f->ev_join) cudaEventDestroy(f->ev_join);
     if (f->ev_start) cudaEventDestroy(f->ev_start);
     for (int i = 0; i < FRONT_MAX_CHUNKS; ++i) {
         if (f->ev_in[i]) cudaEventDestroy(f->ev_in[i]);
@@ -267,7 +273,7 @@ static int front_enqueue_chunk(vslam_ctx* ctx, const uint8_t* d_left, const uint
                                int nfeatures, int anms_keep, float anms_c, double gate_rel, double gate_abs,
                                const double* P1, const double* P2, const double* d_T_c_w, vslam_keypoint* d_kp,
                                uint8_t* d_desc, int32_t* d_n_kp, vslam_dmatch* d_matches, int32_t* d_n_matches,
-                               float* d_xyz, uint8_t* d_flags) {
+                               float* d_xyz, uint8_t* d_flags, int scratch_pair0 = 0) {
     const size_t cap = (size_t)ctx->cfg.max_keypoints;
     ImgSrc src;
     src.base[0] = d_left;
@@ -277,13 +283,14 @@ static int front_enqueue_chunk(vslam_ctx* ctx, const uint8_t* d_left, const uint
     src.per_base = n_chunk;
     src.out_slot[0] = p0;
     src.out_slot[1] = n_pairs + p0;
-    int st = vslam_orb_enqueue(ctx, src, 2 * n_chunk, width, height, nfeatures, anms_keep, anms_c, d_kp, d_desc, d_n_kp);
+    int st = vslam_orb_enqueue(ctx, src, 2 * n_chunk, width, height, nfeatures, anms_keep, anms_c, d_kp, d_desc, d_n_kp,
+                               2 * scratch_pair0);
     if (st != VSLAM_OK) return st;
     // query = left descriptors (slots p0..), train = right descriptors (slots n_pairs + p0..)
     const size_t lq = (size_t)p0, rq = (size_t)n_pairs + p0;
-    st = vslam_match_hamming_batch_dev(ctx, d_desc + lq * cap * 32, d_n_kp + lq, (int)cap, d_desc + rq * cap * 32,
-                                       d_n_kp + rq, (int)cap, n_chunk, (int)cap, 1, gate_rel, gate_abs,
-                                       d_matches + lq * cap, (int)cap, d_n_matches + lq);
+    st = vslam_match_enqueue(ctx, d_desc + lq * cap * 32, d_n_kp + lq, (int)cap, d_desc + rq * cap * 32, d_n_kp + rq,
+                             (int)cap, n_chunk, (int)cap, 1, gate_rel, gate_abs, d_matches + lq * cap, (int)cap,
+                             d_n_matches + lq, scratch_pair0);
     if (st != VSLAM_OK) return st;
     return vslam_triangulate_matches_batch_dev(ctx, d_kp + lq * cap, d_kp + rq * cap, (int)cap, d_matches + lq * cap,
                                                d_n_matches + lq, (int)cap, n_chunk, P1, P2,
@@ -303,9 +310,36 @@ extern "C" int vslam_stereo_frontend_batch_dev(vslam_ctx* ctx, const uint8_t* d_
         return VSLAM_E_INVALID;
     if (n_pairs <= 0 || width <= 0 || height <= 0 || row_pitch < width) return VSLAM_E_INVALID;
     if (2 * n_pairs > ctx->cfg.max_images) return VSLAM_E_CAPACITY;
-    return front_enqueue_chunk(ctx, d_left, d_right, n_pairs, 0, n_pairs, width, height, row_pitch, image_stride,
-                               nfeatures, anms_keep, anms_c, gate_rel, gate_abs, P1, P2, d_T_c_w, d_kp, d_desc, d_n_kp,
-                               d_matches, d_n_matches, d_xyz, d_flags);
+    FrontState* f = ctx->front;
+    // large batches are cut into chunks that alternate between the context stream and a second stream (disjoint scratch
+    // slots): every kernel of the pipeline ends in a tail of a few long CTAs, and the other stream's kernels fill it
+    static const int split_env = getenv("VSLAM_FRONT_SPLIT") ? atoi(getenv("VSLAM_FRONT_SPLIT")) : 0;
+    int n_chunks = split_env > 0 ? split_env : (n_pairs >= 64 ? 2 : 1);  // measured at 128 pairs: 1 -> 20.99k, 2 -> 21.5k, 4 -> 20.8k fps
+    if (!f || !f->s_alt || n_chunks > n_pairs) n_chunks = 1;
+    if (n_chunks == 1)
+        return front_enqueue_chunk(ctx, d_left, d_right, n_pairs, 0, n_pairs, width, height, row_pitch, image_stride,
+                                   nfeatures, anms_keep, anms_c, gate_rel, gate_abs, P1, P2, d_T_c_w, d_kp, d_desc,
+                                   d_n_kp, d_matches, d_n_matches, d_xyz, d_flags);
+    const int chunk = ceil_div(n_pairs, n_chunks);
+    int st = vslam_orb_prepare(ctx, width, height);
+    if (st != VSLAM_OK) return st;
+    cudaStream_t s = ctx->stream;
+    VSLAM_CUDA(ctx, cudaEventRecord(f->ev_start, s));
+    VSLAM_CUDA(ctx, cudaStreamWaitEvent(f->s_alt, f->ev_start, 0));
+    for (int c = 0, p0 = 0; p0 < n_pairs; ++c, p0 += chunk) {
+        const int nc = n_pairs - p0 < chunk ? n_pairs - p0 : chunk;
+        const bool alt = c & 1;
+        ctx->stream = alt ? f->s_alt : s;
+        st = front_enqueue_chunk(ctx, d_left + (long long)p0 * image_stride, d_right + (long long)p0 * image_stride, n_pairs, p0,
+                                 nc, width, height, row_pitch, image_stride, nfeatures, anms_keep, anms_c, gate_rel,
+                                 gate_abs, P1, P2, d_T_c_w, d_kp, d_desc, d_n_kp, d_matches, d_n_matches, d_xyz, d_flags,
+                                 alt ? chunk : 0);
+        ctx->stream = s;
+        if (st != VSLAM_OK) break;
+    }
+    cudaEventRecord(f->ev_join, f->s_alt);  // join even on error: the context stream must cover everything enqueued
+    cudaStreamWaitEvent(s, f->ev_join, 0);
+    return st;
 }
 
 // Host-buffer form (the call a user of the library makes): images come from host memory (pinned memory makes the
@@ -347,6 +381,10 @@ extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, 
             c_start[++n_chunks] = done;
         }
     }
+    {
+        const int stg = vslam_orb_prepare(ctx, width, height);  // tables go up on s, before the streams fork
+        if (stg != VSLAM_OK) return stg;
+    }
     // the copy streams start after whatever the caller already queued on the context stream
     VSLAM_CUDA(ctx, cudaEventRecord(f->ev_start, s));
     VSLAM_CUDA(ctx, cudaStreamWaitEvent(f->s_in, f->ev_start, 0));
@@ -369,20 +407,30 @@ extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, 
         }
         VSLAM_CUDA(ctx, cudaEventRecord(f->ev_in[c], f->s_in));
     }
+    // odd chunks run on a second compute stream with their own scratch slots (when the context has room for two chunks):
+    // the launch tails of one chunk (a few long CTAs per kernel) are filled by the other chunk's kernels
+    const int chunk_max = c_start[1] - c_start[0];
+    const bool two_streams = n_chunks > 1 && 4 * chunk_max <= ctx->cfg.max_images;
+    if (two_streams) VSLAM_CUDA(ctx, cudaStreamWaitEvent(f->s_alt, f->ev_start, 0));
     for (int c = 0; c < n_chunks; ++c) {
         const int p0 = c_start[c], nc = c_start[c + 1] - p0;
-        VSLAM_CUDA(ctx, cudaStreamWaitEvent(s, f->ev_in[c], 0));
+        const bool alt = two_streams && (c & 1);
+        cudaStream_t sc = alt ? f->s_alt : s;
+        VSLAM_CUDA(ctx, cudaStreamWaitEvent(sc, f->ev_in[c], 0));
+        ctx->stream = sc;  // every enqueue below launches on the context's current stream
         int st = front_enqueue_chunk(ctx, dl + p0 * dstride, dr + p0 * dstride, n_pairs, p0, nc, width, height, dpitch,
                                      (long long)dstride, nfeatures, anms_keep, anms_c, gate_rel, gate_abs, P1, P2,
                                      T_c_w ? f->d_pose : nullptr, f->d_kp, f->d_desc, f->d_nkp, f->d_match,
-                                     f->d_nmatch, f->d_xyz, f->d_flags);
+                                     f->d_nmatch, f->d_xyz, f->d_flags, alt ? chunk_max : 0);
+        ctx->stream = s;
         if (st != VSLAM_OK) {
             cudaStreamSynchronize(f->s_in);
             cudaStreamSynchronize(f->s_out);
+            cudaStreamSynchronize(f->s_alt);
             cudaStreamSynchronize(s);
             return st;
         }
-        VSLAM_CUDA(ctx, cudaEventRecord(f->ev_done[c], s));
+        VSLAM_CUDA(ctx, cudaEventRecord(f->ev_done[c], sc));
         VSLAM_CUDA(ctx, cudaStreamWaitEvent(f->s_out, f->ev_done[c], 0));
         const size_t l0 = (size_t)p0, r0 = np + p0, n = (size_t)nc;
         cudaStream_t so = f->s_out;
@@ -396,6 +444,10 @@ extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, 
     }
     VSLAM_CUDA(ctx, cudaMemcpyAsync(n_kp, f->d_nkp, 2 * np * sizeof(int32_t), cudaMemcpyDeviceToHost, f->s_out));
     VSLAM_CUDA(ctx, cudaMemcpyAsync(n_matches, f->d_nmatch, np * sizeof(int32_t), cudaMemcpyDeviceToHost, f->s_out));
+    if (two_streams) {  // join: the context stream (and the flag read below) waits for the second compute stream
+        VSLAM_CUDA(ctx, cudaEventRecord(f->ev_join, f->s_alt));
+        VSLAM_CUDA(ctx, cudaStreamWaitEvent(s, f->ev_join, 0));
+    }
     const int st = vslam_orb_check_flags(ctx, 2 * n_pairs);  // synchronises the context stream
     VSLAM_CUDA(ctx, cudaStreamSynchronize(f->s_out));
     if (getenv("VSLAM_FRONT_TRACE")) {  // pipeline trace: when each chunk's upload and kernels finished, ms after the call began

@@ -237,21 +237,30 @@ extern "C" int vslam_match_hamming_batch_dev(vslam_ctx* ctx, const uint8_t* d_qu
                                              int t_stride_rows, int batch, int max_rows, int cross_check,
                                              double gate_rel, double gate_abs, vslam_dmatch* d_out, int out_stride,
                                              int32_t* d_n_out) {
+    return vslam_match_enqueue(ctx, d_query, d_nq, q_stride_rows, d_train, d_nt, t_stride_rows, batch, max_rows,
+                               cross_check, gate_rel, gate_abs, d_out, out_stride, d_n_out, 0);
+}
+
+int vslam_match_enqueue(vslam_ctx* ctx, const uint8_t* d_query, const int32_t* d_nq, int q_stride_rows,
+                        const uint8_t* d_train, const int32_t* d_nt, int t_stride_rows, int batch, int max_rows,
+                        int cross_check, double gate_rel, double gate_abs, vslam_dmatch* d_out, int out_stride,
+                        int32_t* d_n_out, int scratch_pair0) {
     if (!ctx || !d_query || !d_train || !d_nq || !d_nt || !d_out || !d_n_out) return VSLAM_E_INVALID;
-    if (batch <= 0 || max_rows <= 0) return VSLAM_E_INVALID;
+    if (batch <= 0 || max_rows <= 0 || scratch_pair0 < 0) return VSLAM_E_INVALID;
     MatchState* m = ctx->match;
-    if (batch > m->max_pairs || max_rows > m->max_rows || max_rows > 65535) return VSLAM_E_CAPACITY;
+    if (scratch_pair0 + batch > m->max_pairs || max_rows > m->max_rows || max_rows > 65535) return VSLAM_E_CAPACITY;
     if (((uintptr_t)d_query | (uintptr_t)d_train) & 15) return VSLAM_E_INVALID;
-    VSLAM_CUDA(ctx, cudaMemsetAsync(m->d_keys, 0xFF, (size_t)batch * 2 * m->max_rows * sizeof(uint32_t), ctx->stream));
+    uint32_t* keys = m->d_keys + (size_t)scratch_pair0 * 2 * m->max_rows;
+    VSLAM_CUDA(ctx, cudaMemsetAsync(keys, 0xFF, (size_t)batch * 2 * m->max_rows * sizeof(uint32_t), ctx->stream));
     dim3 grid(ceil_div(max_rows, MT_TILE_Q), ceil_div(max_rows, MT_TILE_T), batch);
     vslam_time_begin(ctx, VK_HAMMING_ARGMIN);
     hamming_argmin_kernel<<<grid, MT_THREADS, 0, ctx->stream>>>(d_query, d_nq, q_stride_rows, d_train, d_nt,
-                                                                t_stride_rows, m->d_keys, m->max_rows);
+                                                                t_stride_rows, keys, m->max_rows);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "hamming_argmin_kernel");
     vslam_time_begin(ctx, VK_CROSSCHECK);
     crosscheck_gate_compact_kernel<<<batch, CC_THREADS, 0, ctx->stream>>>(
-        d_nq, d_nt, m->d_keys, m->max_rows, cross_check, gate_rel, gate_abs, d_out, out_stride, d_n_out);
+        d_nq, d_nt, keys, m->max_rows, cross_check, gate_rel, gate_abs, d_out, out_stride, d_n_out);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "crosscheck_gate_compact_kernel");
     return VSLAM_OK;

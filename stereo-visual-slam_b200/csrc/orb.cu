@@ -1084,12 +1084,20 @@ void vslam_orb_free(vslam_ctx* ctx) {
     ctx->orb = nullptr;
 }
 
+// geometry-dependent tables are uploaded on the context stream; callers that fan out over several streams call this
+// first and order their streams after it
+int vslam_orb_prepare(vslam_ctx* ctx, int w, int h) {
+    if (!ctx->orb) return VSLAM_E_CAPACITY;
+    if (w > ctx->cfg.max_width || h > ctx->cfg.max_height || w >= 65536 || h >= 65536) return VSLAM_E_CAPACITY;
+    return orb_set_geometry(ctx, w, h);
+}
+
 // Enqueue the whole ORB pipeline for n_img images on the context stream (no host synchronisation).
 int vslam_orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h, int nfeatures, int anms_keep,
-                       float anms_c, vslam_keypoint* d_kp, uint8_t* d_desc, int32_t* d_n) {
+                      float anms_c, vslam_keypoint* d_kp, uint8_t* d_desc, int32_t* d_n, int scratch0) {
     OrbState* o = ctx->orb;
     if (!o || !o->d_pyr) return VSLAM_E_CAPACITY;
-    if (n_img <= 0 || n_img > o->max_images) return VSLAM_E_CAPACITY;
+    if (n_img <= 0 || scratch0 < 0 || scratch0 + n_img > o->max_images) return VSLAM_E_CAPACITY;
     if (w > ctx->cfg.max_width || h > ctx->cfg.max_height) return VSLAM_E_CAPACITY;
     if (w >= 65536 || h >= 65536) return VSLAM_E_CAPACITY;
     if (nfeatures <= 0 || nfeatures > o->kp_cap) return VSLAM_E_CAPACITY;
@@ -1099,25 +1107,33 @@ int vslam_orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h
     OrbQuota q;
     orb_quotas(nfeatures, &q);
     cudaStream_t s = ctx->stream;
-    VSLAM_CUDA(ctx, cudaMemsetAsync(o->d_cnt, 0, (size_t)n_img * sizeof(ImgCounters), s));
+    // scratch of this call: image slots [scratch0, scratch0 + n_img) -- two chunks on two streams use disjoint slots
+    uint8_t* pyr = o->d_pyr + (size_t)scratch0 * g.img_slab;
+    uint8_t* blur = o->d_blur + (size_t)scratch0 * g.img_slab;
+    uint2* cand = o->d_cand + (size_t)scratch0 * g.cand_slab;
+    uint2* sel = o->d_sel + (size_t)scratch0 * ORB_NL * SORT_CAP;
+    ImgCounters* cnt = o->d_cnt + scratch0;
+    uint32_t* keep = o->d_keep + (size_t)scratch0 * o->kp_cap;
+    double* rad = o->d_rad + (size_t)scratch0 * o->kp_cap;
+    VSLAM_CUDA(ctx, cudaMemsetAsync(cnt, 0, (size_t)n_img * sizeof(ImgCounters), s));
     for (int l = 1; l < ORB_NL; ++l) {
         dim3 grid(ceil_div(ceil_div(g.lv[l].w, 4), 32), ceil_div(g.lv[l].h, 8), n_img);
         vslam_time_begin(ctx, VK_RESIZE);
-        resize_level_kernel<<<grid, dim3(32, 8), 0, s>>>(src, o->d_pyr, o->d_tab, g, l);
+        resize_level_kernel<<<grid, dim3(32, 8), 0, s>>>(src, pyr, o->d_tab, g, l);
         vslam_time_end(ctx);
         VSLAM_LAUNCH_CHECK(ctx, "resize_level_kernel");
     }
     vslam_time_begin(ctx, VK_FAST);
-    fast_kernel<<<dim3(g.total_tiles, n_img), FAST_THREADS, 0, s>>>(src, o->d_pyr, g, o->d_cand, o->d_cnt, o->d_sticky);
+    fast_kernel<<<dim3(g.total_tiles, n_img), FAST_THREADS, 0, s>>>(src, pyr, g, cand, cnt, o->d_sticky);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "fast_kernel");
     vslam_time_begin(ctx, VK_HARRIS_SELECT);
     harris_select_kernel<<<dim3(ORB_NL, n_img), HS_THREADS, SORT_CAP * sizeof(unsigned long long), s>>>(
-        src, o->d_pyr, g, q, o->d_cand, o->d_cnt, o->d_sel, o->d_sticky);
+        src, pyr, g, q, cand, cnt, sel, o->d_sticky);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "harris_select_kernel");
     vslam_time_begin(ctx, VK_BLUR);
-    blur_kernel<<<dim3(g.total_tiles, n_img), 256, 0, s>>>(src, o->d_pyr, o->d_blur, g);
+    blur_kernel<<<dim3(g.total_tiles, n_img), 256, 0, s>>>(src, pyr, blur, g);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "blur_kernel");
     const int use_keep = anms_keep > 0 ? 1 : 0;
@@ -1126,14 +1142,13 @@ int vslam_orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h
         while (n2 < o->kp_cap) n2 <<= 1;
         if ((size_t)n2 * 8 > 65536) return VSLAM_E_CAPACITY;
         vslam_time_begin(ctx, VK_ANMS);
-        anms_kernel<<<n_img, ANMS_THREADS, (size_t)n2 * 8, s>>>(g, o->d_sel, o->d_cnt, o->kp_cap, anms_keep, anms_c,
-                                                               o->d_rad, o->d_keep);
+        anms_kernel<<<n_img, ANMS_THREADS, (size_t)n2 * 8, s>>>(g, sel, cnt, o->kp_cap, anms_keep, anms_c, rad, keep);
         vslam_time_end(ctx);
         VSLAM_LAUNCH_CHECK(ctx, "anms_kernel");
     }
     vslam_time_begin(ctx, VK_DESCRIBE);
     describe_kernel<<<dim3(ceil_div(o->kp_cap, DESC_WARPS * DESC_KPW), n_img), DESC_WARPS * 32, 0, s>>>(
-        src, o->d_pyr, o->d_blur, g, o->d_sel, o->d_cnt, o->d_keep, use_keep, o->d_pattern, o->kp_cap, d_kp, d_desc,
+        src, pyr, blur, g, sel, cnt, keep, use_keep, o->d_pattern, o->kp_cap, d_kp, d_desc,
         d_n, o->d_sticky);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "describe_kernel");
@@ -1156,7 +1171,7 @@ extern "C" int vslam_orb_detect_compute_batch_dev(vslam_ctx* ctx, const uint8_t*
     src.per_base = n_images > 0 ? n_images : 1;
     src.out_slot[0] = 0;
     src.out_slot[1] = src.per_base;
-    return vslam_orb_enqueue(ctx, src, n_images, width, height, nfeatures, anms_keep, anms_c, d_kp, d_desc, d_n);
+    return vslam_orb_enqueue(ctx, src, n_images, width, height, nfeatures, anms_keep, anms_c, d_kp, d_desc, d_n, 0);
 }
 
 // flags raised by the kernels (bit0 candidate overflow, bit1 sort overflow, bit2 keypoint capacity)
@@ -1200,7 +1215,7 @@ extern "C" int vslam_orb_detect_compute_batch(vslam_ctx* ctx, const uint8_t* ima
     src.per_base = n_images;
     src.out_slot[0] = 0;
     src.out_slot[1] = n_images;
-    int st = vslam_orb_enqueue(ctx, src, n_images, width, height, nfeatures, anms_keep, anms_c, o->d_kp, o->d_desc, o->d_n);
+    int st = vslam_orb_enqueue(ctx, src, n_images, width, height, nfeatures, anms_keep, anms_c, o->d_kp, o->d_desc, o->d_n, 0);
     if (st != VSLAM_OK) return st;
     VSLAM_CUDA(ctx, cudaMemcpyAsync(o->h_n, o->d_n, n_images * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     st = vslam_orb_check_flags(ctx, n_images);  // synchronises
