@@ -58,6 +58,8 @@ struct SgbmState {
     float* d_outf;
     int cap_pairs, cap_w, cap_h, pitch;
     int stop_after;     // test tap: 1 = stop after the vertical sweep (keeps L1 intact)
+    cudaStream_t s_alt; // second stream: odd chunks of a device-resident batch run here on their own scratch slots
+    cudaEvent_t ev_fork, ev_join;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -845,7 +847,11 @@ __global__ void __launch_bounds__(256) speckle_apply_kernel(const int16_t* __res
 // ---------------------------------------------------------------------------------------------------------------
 int vslam_sgbm_init(vslam_ctx* ctx) {
     ctx->sgbm = (SgbmState*)calloc(1, sizeof(SgbmState));
-    return ctx->sgbm ? VSLAM_OK : VSLAM_E_INVALID;
+    if (!ctx->sgbm) return VSLAM_E_INVALID;
+    VSLAM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->sgbm->s_alt, cudaStreamNonBlocking));
+    VSLAM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->sgbm->ev_fork, cudaEventDisableTiming));
+    VSLAM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->sgbm->ev_join, cudaEventDisableTiming));
+    return VSLAM_OK;
 }
 
 static void sgbm_release(SgbmState* s) {
@@ -861,14 +867,20 @@ static void sgbm_release(SgbmState* s) {
     cudaFree(s->d_img);
     cudaFree(s->d_out);
     cudaFree(s->d_outf);
-    const int stop = s->stop_after;
+    SgbmState keep = *s;
     memset(s, 0, sizeof(*s));
-    s->stop_after = stop;
+    s->stop_after = keep.stop_after;
+    s->s_alt = keep.s_alt;
+    s->ev_fork = keep.ev_fork;
+    s->ev_join = keep.ev_join;
 }
 
 void vslam_sgbm_free(vslam_ctx* ctx) {
     if (!ctx->sgbm) return;
     sgbm_release(ctx->sgbm);
+    if (ctx->sgbm->s_alt) cudaStreamDestroy(ctx->sgbm->s_alt);
+    if (ctx->sgbm->ev_fork) cudaEventDestroy(ctx->sgbm->ev_fork);
+    if (ctx->sgbm->ev_join) cudaEventDestroy(ctx->sgbm->ev_join);
     free(ctx->sgbm);
     ctx->sgbm = nullptr;
 }
@@ -939,11 +951,25 @@ static int sgbm_check(const vslam_sgbm_params* in, int w, int h, SgParams* out) 
 }
 
 // enqueue the whole pipeline for n (<= cap_pairs) pairs; images and outputs are device pointers
+// scratch of this call: pair slots [slot0, slot0 + n) of the context's volumes
 static int sgbm_enqueue(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_right, int n, int w, int h, int pitch,
-                        long long img_stride, const SgParams& p, int16_t* d_disp16, float* d_dispf) {
-    SgbmState* s = ctx->sgbm;
+                        long long img_stride, const SgParams& p, int16_t* d_disp16, float* d_dispf, int slot0 = 0) {
+    SgbmState* s0 = ctx->sgbm;
     cudaStream_t st = ctx->stream;
     const int W1 = w - SG_D;
+    if (slot0 < 0 || slot0 + n > s0->cap_pairs) return VSLAM_E_CAPACITY;
+    const size_t px0 = (size_t)slot0 * w * h, vol0 = (size_t)slot0 * h * W1 * SG_NDP;
+    SgbmState view = *s0;  // the same buffers, shifted to this call's slots
+    view.d_pre += 2 * px0;
+    view.d_C += vol0;
+    for (int i = 0; i < 3; ++i) view.d_L[i] += vol0;
+    view.d_rec += px0;
+    view.d_raw += px0;
+    view.d_med += px0;
+    view.d_label += px0;
+    view.d_size += px0;
+    view.d_runlen += px0;
+    const SgbmState* s = &view;
     vslam_time_begin(ctx, VK_SGBM_PREFILTER);
     sgbm_prefilter_kernel<<<dim3(ceil_div(w, 256), h, 2 * n), 256, 0, st>>>(d_left, d_right, img_stride, pitch, n, w, h, p.ftzero,
                                                                             s->d_pre);
@@ -1014,18 +1040,36 @@ extern "C" int vslam_sgbm_compute_dev(vslam_ctx* ctx, const uint8_t* d_left, con
     if (st != VSLAM_OK) return st;
     if (n_pairs == 0) return VSLAM_OK;
     VSLAM_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
-    const int chunk = n_pairs < SG_CHUNK_PAIRS ? n_pairs : SG_CHUNK_PAIRS;
-    st = sgbm_reserve(ctx, chunk, width, height);
+    // chunks alternate between the context stream and a second stream on disjoint scratch slots: the issue-bound
+    // sweeps of one chunk overlap the bandwidth-bound sweeps of the other, and launch tails are filled
+    static const int split_env = getenv("VSLAM_SGBM_SPLIT") ? atoi(getenv("VSLAM_SGBM_SPLIT")) : -1;
+    const bool two = split_env != 0 && n_pairs >= 2;
+    int chunk = two ? (n_pairs + 1) / 2 : n_pairs;
+    if (chunk > SG_CHUNK_PAIRS / (two ? 2 : 1)) chunk = SG_CHUNK_PAIRS / (two ? 2 : 1);
+    st = sgbm_reserve(ctx, two ? 2 * chunk : chunk, width, height);
     if (st != VSLAM_OK) return st;
+    SgbmState* sg = ctx->sgbm;
     const size_t px = (size_t)width * height;
-    for (int b = 0; b < n_pairs; b += chunk) {
+    cudaStream_t s = ctx->stream;
+    if (two) {
+        VSLAM_CUDA(ctx, cudaEventRecord(sg->ev_fork, s));
+        VSLAM_CUDA(ctx, cudaStreamWaitEvent(sg->s_alt, sg->ev_fork, 0));
+    }
+    for (int b = 0, c = 0; b < n_pairs; b += chunk, ++c) {
         const int n = n_pairs - b < chunk ? n_pairs - b : chunk;
+        const bool alt = two && (c & 1);
+        ctx->stream = alt ? sg->s_alt : s;
         st = sgbm_enqueue(ctx, d_left + (long long)b * image_stride, d_right + (long long)b * image_stride, n, width, height,
                           row_pitch, image_stride, p, d_disp16 ? d_disp16 + b * px : nullptr,
-                          d_disp_f32 ? d_disp_f32 + b * px : nullptr);
-        if (st != VSLAM_OK) return st;
+                          d_disp_f32 ? d_disp_f32 + b * px : nullptr, alt ? chunk : 0);
+        ctx->stream = s;
+        if (st != VSLAM_OK) break;
     }
-    return VSLAM_OK;
+    if (two) {
+        cudaEventRecord(sg->ev_join, sg->s_alt);
+        cudaStreamWaitEvent(s, sg->ev_join, 0);
+    }
+    return st;
 }
 
 extern "C" int vslam_sgbm_compute(vslam_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_pairs, int width, int height,
