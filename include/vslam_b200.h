@@ -79,6 +79,11 @@ void vslam_ctx_destroy(vslam_ctx* ctx);
 /* run on a caller-owned stream (a cudaStream_t, e.g. torch's current stream); NULL = context's own */
 int vslam_ctx_set_stream(vslam_ctx* ctx, void* cuda_stream);
 int vslam_ctx_synchronize(vslam_ctx* ctx);
+/* Batched entry points cut large batches into chunks that alternate between the context stream and an internal second
+ * stream (disjoint scratch, joined back into the context stream before the call returns / the stream continues), so
+ * that one chunk's launch tails overlap the other chunk's kernels.  on = 0 keeps every launch on the context stream,
+ * e.g. to time kernels in isolation.  Default: on. */
+int vslam_ctx_set_concurrency(vslam_ctx* ctx, int on);
 /* number of kernels this context has launched since creation (for bench.py's gpu_launches) */
 int64_t vslam_ctx_launch_count(const vslam_ctx* ctx);
 

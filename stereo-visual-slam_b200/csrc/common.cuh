@@ -38,6 +38,7 @@ struct vslam_ctx {
     char err[256];
     int num_sms;
     int timing_on;
+    int serial;  // 1 = no internal second stream (vslam_ctx_set_concurrency(ctx, 0))
     int n_trec, n_trec_alloc;
     TimingRec* trec;
     double t_ms[VK_COUNT];

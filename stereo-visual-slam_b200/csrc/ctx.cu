@@ -88,6 +88,12 @@ extern "C" int vslam_ctx_set_stream(vslam_ctx* ctx, void* cuda_stream) {
     return VSLAM_OK;
 }
 
+extern "C" int vslam_ctx_set_concurrency(vslam_ctx* ctx, int on) {
+    if (!ctx) return VSLAM_E_INVALID;
+    ctx->serial = on ? 0 : 1;
+    return VSLAM_OK;
+}
+
 extern "C" int vslam_ctx_synchronize(vslam_ctx* ctx) {
     if (!ctx) return VSLAM_E_INVALID;
     VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

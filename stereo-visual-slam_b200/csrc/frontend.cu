@@ -315,7 +315,7 @@ extern "C" int vslam_stereo_frontend_batch_dev(vslam_ctx* ctx, const uint8_t* d_
     // slots): every kernel of the pipeline ends in a tail of a few long CTAs, and the other stream's kernels fill it
     static const int split_env = getenv("VSLAM_FRONT_SPLIT") ? atoi(getenv("VSLAM_FRONT_SPLIT")) : 0;
     int n_chunks = split_env > 0 ? split_env : (n_pairs >= 64 ? 2 : 1);  // measured at 128 pairs: 1 -> 20.99k, 2 -> 21.5k, 4 -> 20.8k fps
-    if (!f || !f->s_alt || n_chunks > n_pairs) n_chunks = 1;
+    if (!f || !f->s_alt || n_chunks > n_pairs || (ctx->serial && split_env <= 0)) n_chunks = 1;
     if (n_chunks == 1)
         return front_enqueue_chunk(ctx, d_left, d_right, n_pairs, 0, n_pairs, width, height, row_pitch, image_stride,
                                    nfeatures, anms_keep, anms_c, gate_rel, gate_abs, P1, P2, d_T_c_w, d_kp, d_desc,
@@ -410,7 +410,7 @@ extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, 
     // odd chunks run on a second compute stream with their own scratch slots (when the context has room for two chunks):
     // the launch tails of one chunk (a few long CTAs per kernel) are filled by the other chunk's kernels
     const int chunk_max = c_start[1] - c_start[0];
-    const bool two_streams = n_chunks > 1 && 4 * chunk_max <= ctx->cfg.max_images;
+    const bool two_streams = n_chunks > 1 && !ctx->serial && 4 * chunk_max <= ctx->cfg.max_images;
     if (two_streams) VSLAM_CUDA(ctx, cudaStreamWaitEvent(f->s_alt, f->ev_start, 0));
     for (int c = 0; c < n_chunks; ++c) {
         const int p0 = c_start[c], nc = c_start[c + 1] - p0;

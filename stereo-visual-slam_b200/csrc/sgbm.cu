@@ -1043,7 +1043,7 @@ extern "C" int vslam_sgbm_compute_dev(vslam_ctx* ctx, const uint8_t* d_left, con
     // chunks alternate between the context stream and a second stream on disjoint scratch slots: the issue-bound
     // sweeps of one chunk overlap the bandwidth-bound sweeps of the other, and launch tails are filled
     static const int split_env = getenv("VSLAM_SGBM_SPLIT") ? atoi(getenv("VSLAM_SGBM_SPLIT")) : -1;
-    const bool two = split_env != 0 && n_pairs >= 2;
+    const bool two = split_env != 0 && !ctx->serial && n_pairs >= 2;
     int chunk = two ? (n_pairs + 1) / 2 : n_pairs;
     if (chunk > SG_CHUNK_PAIRS / (two ? 2 : 1)) chunk = SG_CHUNK_PAIRS / (two ? 2 : 1);
     st = sgbm_reserve(ctx, two ? 2 * chunk : chunk, width, height);

@@ -67,6 +67,7 @@ SIGNATURES = {
     "vslam_ctx_destroy": (None, [_vp]),
     "vslam_ctx_set_stream": (_i, [_vp, _vp]),
     "vslam_ctx_synchronize": (_i, [_vp]),
+    "vslam_ctx_set_concurrency": (_i, [_vp, _i]),
     "vslam_ctx_launch_count": (_i64, [_vp]),
     "vslam_kernel_count": (_i, []),
     "vslam_kernel_name": (C.c_char_p, [_i]),
@@ -162,6 +163,10 @@ class Context:
 
     def set_stream(self, cuda_stream_handle: int | None):
         self.check(self.lib.vslam_ctx_set_stream(self.h, C.c_void_p(cuda_stream_handle or 0)), "set_stream")
+
+    def set_concurrency(self, on: bool):
+        """on=False keeps every launch on the context stream (kernels timed in isolation)"""
+        self.check(self.lib.vslam_ctx_set_concurrency(self.h, int(on)), "vslam_ctx_set_concurrency")
 
     def synchronize(self):
         self.check(self.lib.vslam_ctx_synchronize(self.h), "synchronize")
