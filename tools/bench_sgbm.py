@@ -20,6 +20,7 @@ torch.cuda.set_stream(stream)
 for _ in range(2):
     ctx.sgbm_compute_dev(dl, dr, B, W, H, W, W * H, d16)
 torch.cuda.synchronize()
+ctx.set_concurrency(False)  # kernels alone on the stream for the per-kernel numbers
 ctx.timing_enable(True)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
@@ -29,6 +30,7 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
 kt = {k: v for k, v in ctx.timing_read().items() if k.startswith("sgbm")}
 ctx.timing_enable(False)
+ctx.set_concurrency(True)
 # same without the per-launch events
 e0.record()
 for _ in range(iters):
