@@ -123,3 +123,55 @@ def test_stereo_frontend_chunked_pipeline_equals_per_pair(pkg, gpu_ctx_big):
         assert np.array_equal(out["matches"][i, :nm], one["matches"][0, :nm])
         assert np.array_equal(out["xyz"][i, :nm], one["xyz"][0, :nm])
         assert np.array_equal(out["flags"][i, :nm], one["flags"][0, :nm])
+
+
+def test_two_stream_chunking_equals_single_stream(pkg):
+    """Host-buffer path (3 chunks: 32 + 32 + 8 pairs alternating between two compute streams on disjoint scratch) and
+    device-resident path (2 half-batches) give bit-identical results with vslam_ctx_set_concurrency on and off."""
+    import torch
+    n, nfeat, h, w = 72, 400, 200, 640
+    ctx = pkg.Context(device=0, max_images=2 * n, max_width=w, max_height=h, max_keypoints=512)
+    try:
+        P1, P2 = _cams(pkg)
+        L = np.stack([np.ascontiguousarray(pkg.synth.synth_pair(100 + i)[0][60:60 + h, 40 + i:40 + i + w]) for i in range(n)])
+        Rr = np.stack([np.ascontiguousarray(pkg.synth.synth_pair(100 + i)[1][60:60 + h, 40 + i:40 + i + w]) for i in range(n)])
+        res = {}
+        for on in (True, False):
+            ctx.set_concurrency(on)
+            o = ctx.stereo_frontend(L, Rr, P1, P2, nfeatures=nfeat)
+            res[on] = {k: np.array(v, copy=True) for k, v in o.items() if isinstance(v, np.ndarray)}
+        a, b = res[True], res[False]
+        assert np.array_equal(a["n_kp"], b["n_kp"]) and np.array_equal(a["n_matches"], b["n_matches"])
+        assert a["n_kp"].min() > 100 and a["n_matches"].min() > 10
+        for i in range(2 * n):
+            k = a["n_kp"][i]
+            assert a["kp"][i, :k].tobytes() == b["kp"][i, :k].tobytes() and np.array_equal(a["desc"][i, :k], b["desc"][i, :k])
+        for i in range(n):
+            m = a["n_matches"][i]
+            assert a["matches"][i, :m].tobytes() == b["matches"][i, :m].tobytes()
+            assert np.array_equal(a["xyz"][i, :m], b["xyz"][i, :m]) and np.array_equal(a["flags"][i, :m], b["flags"][i, :m])
+        # device-resident entry: 72 pairs >= 64 -> two half-batches on two streams
+        dev = torch.device("cuda:0")
+        dl, dr = torch.from_numpy(L).to(dev), torch.from_numpy(Rr).to(dev)
+        cap = ctx.kp_cap
+        outs = {}
+        for on in (True, False):
+            ctx.set_concurrency(on)
+            d_kp = torch.zeros((2 * n, cap, 7), dtype=torch.int32, device=dev)
+            d_desc = torch.zeros((2 * n, cap, 32), dtype=torch.uint8, device=dev)
+            d_nkp = torch.zeros(2 * n, dtype=torch.int32, device=dev)
+            d_m = torch.zeros((n, cap, 4), dtype=torch.int32, device=dev)
+            d_nm = torch.zeros(n, dtype=torch.int32, device=dev)
+            d_xyz = torch.zeros((n, cap, 3), dtype=torch.float32, device=dev)
+            d_fl = torch.zeros((n, cap), dtype=torch.uint8, device=dev)
+            torch.cuda.synchronize()
+            ctx.stereo_frontend_dev(dl, dr, n, w, h, w, w * h, P1, P2, None, d_kp, d_desc, d_nkp, d_m, d_nm, d_xyz, d_fl,
+                                    nfeatures=nfeat)
+            ctx.synchronize()
+            outs[on] = [t.cpu().numpy() for t in (d_nkp, d_nm, d_kp, d_desc, d_m, d_xyz)]
+        assert np.array_equal(outs[True][0], a["n_kp"]) and np.array_equal(outs[True][1], a["n_matches"])
+        for x, y in zip(outs[True], outs[False]):
+            assert np.array_equal(x, y)
+    finally:
+        ctx.set_concurrency(True)
+        ctx.close()

@@ -123,3 +123,25 @@ def test_sgbm_batch_larger_than_one_chunk_and_row_pitch(pkg, gpu_ctx):
     gpu_ctx.sgbm_compute_dev(dl, dr, n, w, h, pitch, pitch * h, d16)
     gpu_ctx.synchronize()
     assert np.array_equal(d16.cpu().numpy(), ref)
+
+
+def test_sgbm_two_stream_chunks_equal_single_stream(pkg, gpu_ctx):
+    """device batches alternate chunks between two streams on disjoint scratch slots; results do not change"""
+    import torch
+    n, h, w = 6, 40, 260
+    L = np.stack([_crop(pkg, s, h, w, y0=30 * s, x0=200 + 50 * s)[0] for s in range(n)])
+    R = np.stack([_crop(pkg, s, h, w, y0=30 * s, x0=200 + 50 * s)[1] for s in range(n)])
+    dl, dr = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+    got = {}
+    try:
+        for on in (True, False):
+            gpu_ctx.set_concurrency(on)
+            d16 = torch.empty((n, h, w), dtype=torch.int16, device="cuda")
+            torch.cuda.synchronize()
+            gpu_ctx.sgbm_compute_dev(dl, dr, n, w, h, w, w * h, d16)
+            gpu_ctx.synchronize()
+            got[on] = d16.cpu().numpy()
+    finally:
+        gpu_ctx.set_concurrency(True)
+    assert np.array_equal(got[True], got[False])
+    assert np.array_equal(got[True], np.stack([G.sgbm_compute(L[i], R[i]) for i in range(n)]))
