@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) sgbm_prefilter_kernel(const uint8_t* __re
 
 // ---------------------------------------------------------------------------------------------------------------
 // K19: pixel cost + 9x9 box sum.  CTA = CK_CW output columns x one row band, marching down the rows.
-// Thread (g, q) owns 8 consecutive columns and the 4 disparities 4q..4q+3 (two s16x2 words).  Walking its columns
+// Thread (g, q) owns 4 consecutive columns and the 4 disparities 4q..4q+3 (two s16x2 words).  Walking its columns
 // left to right, the right-image operand of disparity d at column x is position x - d: one new position per column
 // feeds all four disparities (register window), and the operands of the second word are the first word's operands
 // of two columns ago.  Operands stay byte-packed (v | min << 8 | max << 16, as the prefilter wrote them) in shared
@@ -107,13 +107,14 @@ __global__ void __launch_bounds__(256) sgbm_prefilter_kernel(const uint8_t* __re
 __device__ __forceinline__ uint32_t bcast16(int v) { return (uint32_t)(v & 0xffff) * 0x00010001u; }
 
 #define CK_Q 24                        // threads per column group
-#define CK_GC 8                        // columns per group
-#define CK_CW 112                      // output columns per CTA
-#define CK_NG (CK_CW / CK_GC + 2)      // 14 output groups + one halo group on each side
-#define CK_COLS (CK_NG * CK_GC)        // 128 columns whose pixel cost the CTA computes
-#define CK_GSTR (CK_GC * SG_NDP + 16)   // words per column group (8 x 48 + 16: neighbouring groups start 16 banks apart)
+#define CK_GC 4                        // columns per group
+#define CK_CW 108                      // output columns per CTA
+#define CK_NG (CK_CW / CK_GC + 2)      // 27 output groups + one halo group (= the 4 halo columns) on each side
+#define CK_COLS (CK_NG * CK_GC)        // 116 columns whose pixel cost the CTA computes
+#define CK_GSTR (CK_GC * SG_NDP + 16)   // words per column group (4 x 48 + 16: neighbouring groups start 16 banks apart)
 #define CK_NPOS 232                    // right-image positions staged per row (CK_COLS + 95 + 3, rounded up)
-#define CK_THREADS (CK_NG * CK_Q)      // 384
+#define CK_THREADS (CK_NG * CK_Q)      // 696
+#define CK_WIN (CK_GC + 2 * SG_R)       // exchange-buffer columns under one thread's horizontal windows
 #define CK_RSLOT ((CK_NG - 2) * CK_GSTR)  // words per ring slot
 #define CK_SMEM ((CK_COLS + CK_NPOS) * 8 + CK_NG * CK_GSTR * 4 + 9 * CK_RSLOT * 4)
 #define CK_FF 0x00ff00ffu
@@ -148,8 +149,8 @@ __global__ void __launch_bounds__(CK_THREADS, 1) sgbm_cost_kernel(const uint2* _
                                                                  int band_rows, uint32_t* __restrict__ Cvol) {
     extern __shared__ __align__(16) unsigned char ck_smem[];
     uint2* sOp = reinterpret_cast<uint2*>(ck_smem);                          // [CK_COLS left | CK_NPOS right]
-    uint32_t* sPd = reinterpret_cast<uint32_t*>(sOp + CK_COLS + CK_NPOS);    // [CK_NG groups][8 columns][48] (+16 pad)
-    uint32_t* sRing = sPd + CK_NG * CK_GSTR;                                 // [9][14 groups][8 columns][48] (+16 pad)
+    uint32_t* sPd = reinterpret_cast<uint32_t*>(sOp + CK_COLS + CK_NPOS);    // [CK_NG groups][CK_GC columns][48] (+16 pad)
+    uint32_t* sRing = sPd + CK_NG * CK_GSTR;                                 // [9][CK_NG - 2 groups][CK_GC columns][48] (+16 pad)
     const int t = threadIdx.x, g = t / CK_Q, q = t - g * CK_Q;
     const int x1s = blockIdx.x * CK_CW, pair = blockIdx.z;
     const int y0 = blockIdx.y * band_rows, y1 = min(y0 + band_rows, H);
@@ -159,11 +160,11 @@ __global__ void __launch_bounds__(CK_THREADS, 1) sgbm_cost_kernel(const uint2* _
     const int xfirst = x1s - CK_GC;         // W1-coordinate of exchange-buffer column 0
     const int pb = xfirst + SG_D - 95 - 3;  // image position of right-row slot 0
     const int xg = xfirst + g * CK_GC;      // first column of this thread
-    const int nvalid = xg < 0 ? 0 : min(CK_GC, W1 - xg);  // columns of this group inside the image (groups are 8-aligned)
+    const int nvalid = xg < 0 ? 0 : min(CK_GC, W1 - xg);  // columns of this group inside the image (groups are CK_GC-aligned)
     const bool out_group = g >= 1 && g <= CK_NG - 2 && nvalid > 0;
     uint32_t* Cout = Cvol + (size_t)pair * H * W1 * SG_NDP;
 
-    // one operand per thread per row (CK_COLS + CK_NPOS = 360 <= CK_THREADS): fetched early, parked in shared memory late
+    // one operand per thread per row (CK_COLS + CK_NPOS = 348 <= CK_THREADS): fetched early, parked in shared memory late
     const uint2* op_src = nullptr;
     if (t < CK_COLS) op_src = preL + min(max(xfirst + t, 0), W1 - 1) + SG_D;
     else if (t < CK_COLS + CK_NPOS) op_src = preR + min(max(pb + t - CK_COLS, 0), W - 1);
@@ -172,11 +173,11 @@ __global__ void __launch_bounds__(CK_THREADS, 1) sgbm_cost_kernel(const uint2* _
     };
 
     // exchange-buffer word offsets of the 16 columns under this thread's horizontal windows (borders replicated)
-    int woff[2 * CK_GC];
+    int woff[CK_WIN];
 #pragma unroll
-    for (int k = 0; k < 2 * CK_GC; ++k) {
+    for (int k = 0; k < CK_WIN; ++k) {
         const int col = min(max(xg - SG_R + k, 0), W1 - 1) - xfirst;
-        woff[k] = (col >> 3) * CK_GSTR + (col & 7) * SG_NDP + 2 * q;
+        woff[k] = (col / CK_GC) * CK_GSTR + (col % CK_GC) * SG_NDP + 2 * q;
     }
     uint32_t* ring = sRing + (g - 1) * CK_GSTR + 2 * q;
     if (out_group)
@@ -223,9 +224,9 @@ __global__ void __launch_bounds__(CK_THREADS, 1) sgbm_cost_kernel(const uint2* _
         const uint2 next_op = row < r_last ? fetch_op(row + 1) : make_uint2(0, 0);  // in flight during phase C
         if (out_group) {
             const int yo = row - SG_R;
-            uint2 win[2 * CK_GC];
+            uint2 win[CK_WIN];
 #pragma unroll
-            for (int k = 0; k < 2 * CK_GC; ++k) win[k] = *reinterpret_cast<const uint2*>(sPd + woff[k]);
+            for (int k = 0; k < CK_WIN; ++k) win[k] = *reinterpret_cast<const uint2*>(sPd + woff[k]);
             uint2 hsum = make_uint2(0, 0);
 #pragma unroll
             for (int k = 0; k < 2 * SG_R + 1; ++k) {
@@ -820,6 +821,7 @@ __global__ void __launch_bounds__(256) speckle_count_kernel(int* __restrict__ la
     int* L = label + img;
     const int r = uf_find(L, i);
     atomicAdd(&size[img + r], n);
+    if (r != i) L[i] = r;  // path compression: the apply pass reaches the root in two hops (roots stay roots here)
 }
 
 __global__ void __launch_bounds__(256) speckle_apply_kernel(const int16_t* __restrict__ d, const int* __restrict__ label,
