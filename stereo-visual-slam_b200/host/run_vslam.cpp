@@ -2,7 +2,7 @@
 // (/root/reference/src/run_vslam.cpp:17-92): per frame VO::pipeline(), and after every keyframe insertion with a full
 // window optimize_map(5) x2 (outlier relabel only), optimize_map(10) with pose write-back and optimize_pose_only(10).
 //
-//   run_vslam <dataset_dir/> <n_frames> [--no-ba] [--nfeatures N] [--anms K] [--dense]
+//   run_vslam <dataset_dir/> <n_frames> [--no-ba] [--nfeatures N] [--anms K] [--dense] [--window W] [--update-landmarks]
 // reads <dataset_dir>/image_{0,1}/%06d.pgm, appends evicted / remaining keyframe poses to ./estimated_traj.txt
 // (the reference's format) and prints one "frame <id> <12 numbers of T_w_c> <inliers> <is_keyframe>" line per frame.
 #include <cstdio>
@@ -17,16 +17,19 @@
 
 int main(int argc, char** argv) {
     if (argc < 3) {
-        std::fprintf(stderr, "usage: run_vslam <dataset_dir/> <n_frames> [--no-ba] [--nfeatures N] [--anms K] [--dense]\n");
+        std::fprintf(stderr, "usage: run_vslam <dataset_dir/> <n_frames> [--no-ba] [--nfeatures N] [--anms K] [--dense] [--window W] [--update-landmarks]\n");
         return 2;
     }
     const std::string dataset = argv[1];
     const int n_frames = std::atoi(argv[2]);
     bool do_ba = true, dense = false;
-    int nfeatures = 3000, anms = 500;
+    int nfeatures = 3000, anms = 500, window = 10;
+    bool update_landmarks = false;  // the reference never writes landmarks back (run_vslam.cpp:61-64)
     for (int i = 3; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--no-ba")) do_ba = false;
         else if (!std::strcmp(argv[i], "--dense")) dense = true;  // the reference's StereoSGBM depth source
+        else if (!std::strcmp(argv[i], "--window") && i + 1 < argc) window = std::atoi(argv[++i]);
+        else if (!std::strcmp(argv[i], "--update-landmarks")) update_landmarks = true;
         else if (!std::strcmp(argv[i], "--nfeatures") && i + 1 < argc) nfeatures = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--anms") && i + 1 < argc) anms = std::atoi(argv[++i]);
     }
@@ -36,6 +39,11 @@ int main(int argc, char** argv) {
     nh.setParam("/if_rviz", false);
 
     vslam::Map my_map(nh);
+    if (window < 2 || window > 64) {
+        std::fprintf(stderr, "--window must be in [2, 64]\n");
+        return 2;
+    }
+    my_map.num_keyframes_ = window;
     vslam::VO my_VO(dataset, nh, my_map);
     my_VO.detector_nfeatures_ = nfeatures;
     my_VO.anms_keep_ = anms;
@@ -47,10 +55,10 @@ int main(int argc, char** argv) {
     for (int ite = 0; ite < n_frames; ++ite) {
         bool if_insert_keyframe = false;
         const bool not_lost = my_VO.pipeline(if_insert_keyframe);
-        if (if_insert_keyframe && do_ba && (int)my_map.keyframes_.size() >= 10) {
+        if (if_insert_keyframe && do_ba && (int)my_map.keyframes_.size() >= my_map.num_keyframes_) {
             vslam::optimize_map(my_map.keyframes_, my_map.landmarks_, K, false, false, 5);
             vslam::optimize_map(my_map.keyframes_, my_map.landmarks_, K, false, false, 5);
-            vslam::optimize_map(my_map.keyframes_, my_map.landmarks_, K, true, false, 10);
+            vslam::optimize_map(my_map.keyframes_, my_map.landmarks_, K, true, update_landmarks, 10);
             vslam::optimize_pose_only(my_map.keyframes_, my_map.landmarks_, K, true, 10);
         }
         const vslam::Frame& f = ite == 0 ? my_VO.frame_last_ : my_VO.frame_current_;

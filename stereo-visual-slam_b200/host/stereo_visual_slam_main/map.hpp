@@ -15,7 +15,9 @@ struct Map {
     std::unordered_map<unsigned long, Frame> keyframes_;
     std::unordered_map<unsigned long, Landmark> landmarks_;
 
-    const int num_keyframes_ = 10;  // window size (reference: map.hpp:22)
+    // window size.  The reference fixes it at 10 (`const int`, map.hpp:22); here it can be raised up to the BA kernels'
+    // limit of 64 keyframes before the first frame.
+    int num_keyframes_ = 10;
     int current_keyframe_id_ = 0;
 
     VslamVisual my_visual_;

@@ -31,7 +31,7 @@ void VO::create_context() {
     cfg.max_width = kMaxW;
     cfg.max_height = kMaxH;
     cfg.max_keypoints = kMaxKp;
-    cfg.max_ba_poses = 16;
+    cfg.max_ba_poses = 64;
     cfg.max_ba_points = 65536;
     cfg.max_ba_obs = 262144;
     check(vslam_ctx_create(&cfg, &ctx_), "vslam_ctx_create");  // throws without a B200: there is no CPU path

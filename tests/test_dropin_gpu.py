@@ -77,3 +77,21 @@ def test_vo_with_dense_stereo_like_the_reference(sequence, tmp_path):
     err = np.abs(T[:, :, 3] - t[:n]).max(axis=1)
     assert err.max() < 0.05, err
     assert np.abs(T[:, :, :3] - np.eye(3)).max() < 5e-3
+
+
+def test_wider_window_and_landmark_write_back(sequence, tmp_path):
+    """a 12-keyframe window (the reference fixes 10), and if_update_landmark = true.
+    The reference's graph fixes no vertex (optimization.cpp has no setFixed), so writing the landmarks back moves the
+    whole window in its gauge freedom: the run must stay tracked and bounded, not match the ground-truth frame."""
+    seq_dir, n, t = sequence
+    ids, T, meta, out = _run(seq_dir, n, tmp_path, "--nfeatures", "1000", "--anms", "110", "--window", "12")
+    assert len(ids) == n and "VO IS LOST" not in out
+    assert meta[:, 2].max() == 12
+    err = np.abs(T[:, :, 3] - t[:n]).max(axis=1)
+    assert err.max() < 0.05, err
+    ids, T, meta, out = _run(seq_dir, n, tmp_path, "--nfeatures", "1000", "--anms", "110", "--window", "12",
+                             "--update-landmarks")
+    assert len(ids) == n and "VO IS LOST" not in out and meta[:, 2].max() == 12
+    err = np.abs(T[:, :, 3] - t[:n]).max(axis=1)
+    assert err[:12].max() < 0.05 and err.max() < 0.5, err   # before the first BA: identical; after: gauge drift only
+    assert (meta[1:, 0] >= 10).all()
