@@ -405,6 +405,10 @@ def run_ours(args, rank, world, local_rank):
                              "stages_ms": stages, "single_thread": stages_1t}}
     if ba_block is not None:
         line["ba"] = ba_block
+    try:
+        line["pnp"] = bench_pnp(ctx, pkg)
+    except Exception as ex:
+        line["pnp"] = {"error": repr(ex)}
     if args.sgbm:
         try:
             line["sgbm"] = bench_sgbm(ctx, pkg, torch, dev, stream, sets[0][2][:8], sets[0][3][:8], peak)
@@ -414,6 +418,35 @@ def run_ours(args, rank, world, local_rank):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_pnp(ctx, pkg):
+    """VO::motion_estimation's solvePnPRansac call (visual_odometry.cpp:277: 100 iterations, 4 px, 0.99) on 400
+    landmark-keypoint pairs with 20 % gross outliers: host-buffer C-ABI call vs live cv2 on the host."""
+    import cv2
+    rng = np.random.default_rng(0)
+    n = 400
+    K = pkg.synth.kitti_K()
+    R, t = pkg.synth.se3_exp(np.array([0.4, -0.05, 0.9, 0.01, 0.03, -0.005]))
+    pw = np.stack([rng.uniform(-15, 15, n), rng.uniform(-3, 3, n), rng.uniform(6, 45, n)], 1).astype(np.float32)
+    pc = pw.astype(np.float64) @ R.T + t
+    uv = (pc[:, :2] / pc[:, 2:3]) * [K[0, 0], K[1, 1]] + [K[0, 2], K[1, 2]] + rng.normal(0, 0.3, (n, 2))
+    bad = rng.permutation(n)[:n // 5]
+    uv[bad] += rng.uniform(30, 200, (len(bad), 2)) * rng.choice([-1, 1], (len(bad), 2))
+    uv = uv.astype(np.float32)
+    g = ctx.pnp_ransac(pw, uv, K, 100, 4.0, 0.99)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        g = ctx.pnp_ransac(pw, uv, K, 100, 4.0, 0.99)
+    gpu_ms = (time.perf_counter() - t0) / 20 * 1e3
+    ok, rvec, tvec, inl = cv2.solvePnPRansac(pw, uv, K, None, iterationsCount=100, reprojectionError=4.0, confidence=0.99)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        cv2.solvePnPRansac(pw, uv, K, None, iterationsCount=100, reprojectionError=4.0, confidence=0.99)
+    cpu_ms = (time.perf_counter() - t0) / 20 * 1e3
+    return {"points": n, "e2e_ms_per_call": gpu_ms, "cv2_ms_per_call": cpu_ms,
+            "inlier_sets_differ_by": int(len(np.setxor1d(g["inliers"], inl.ravel()))),
+            "t_rel_diff_vs_cv2": float(np.abs(g["tvec"] - tvec.ravel()).max() / np.linalg.norm(tvec))}
 
 
 def bench_sgbm(ctx, pkg, torch, dev, stream, dl, dr, hbm_peak):
