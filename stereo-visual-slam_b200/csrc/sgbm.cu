@@ -329,6 +329,34 @@ __device__ __forceinline__ void sgm_step(uint32_t& a0, uint32_t& a1, uint32_t& m
     mm = (uint32_t)__reduce_min_sync(0xffffffffu, (int)__vmins2(w, __byte_perm(w, w, 0x1032)));
 }
 
+// Two paths per warp: each half-warp owns one path, lane sl = lane & 15 holds disparities 6 sl .. 6 sl + 5 as three
+// s16x2 words -- all 32 lanes carry data (the one-path layout above idles 8), and the per-step bookkeeping of a warp
+// (barrier wait, loads, stores, pointer updates) is shared by two paths.  The minimum of each half comes from two
+// full-warp CREDUX with the other half neutralised.
+__device__ __forceinline__ void sgm_step2(uint32_t (&a)[3], uint32_t& mm, const uint32_t (&c)[3], uint32_t P1b, uint32_t P2b,
+                                          int sl, bool upper_half) {
+    uint32_t up = __shfl_up_sync(0xffffffffu, a[2], 1, 16);
+    uint32_t dn = __shfl_down_sync(0xffffffffu, a[0], 1, 16);
+    if (sl == 0) up = SG_BIG2;
+    if (sl == 15) dn = SG_BIG2;
+    const uint32_t lm0 = __byte_perm(up, a[0], 0x5432);    // (L[6s-1], L[6s])
+    const uint32_t m01 = __byte_perm(a[0], a[1], 0x5432);  // (L[6s+1], L[6s+2])
+    const uint32_t m12 = __byte_perm(a[1], a[2], 0x5432);  // (L[6s+3], L[6s+4])
+    const uint32_t lp2 = __byte_perm(a[2], dn, 0x5432);    // (L[6s+5], L[6s+6])
+    const uint32_t mp2 = mm + P2b;
+    const uint32_t t0 = __vmins2(__vmins2(__vadd2(__vmins2(lm0, m01), P1b), mp2), a[0]);
+    const uint32_t t1 = __vmins2(__vmins2(__vadd2(__vmins2(m01, m12), P1b), mp2), a[1]);
+    const uint32_t t2 = __vmins2(__vmins2(__vadd2(__vmins2(m12, lp2), P1b), mp2), a[2]);
+    a[0] = c[0] + t0 - mm;
+    a[1] = c[1] + t1 - mm;
+    a[2] = c[2] + t2 - mm;
+    const uint32_t w = __vimin3_s16x2(a[0], a[1], a[2]);
+    const uint32_t v = __vmins2(w, __byte_perm(w, w, 0x1032));
+    const uint32_t mlo = (uint32_t)__reduce_min_sync(0xffffffffu, (int)(upper_half ? SG_BIG2 : v));
+    const uint32_t mhi = (uint32_t)__reduce_min_sync(0xffffffffu, (int)(upper_half ? v : SG_BIG2));
+    mm = upper_half ? mhi : mlo;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // K20: the three paths that come from the row above.  blockIdx.y: 0 = from (x-1, y-1), 1 = from (x, y-1),
 // 2 = from (x+1, y-1).  Warp k starts at column k of row 0; a diagonal path that leaves the image re-enters on the
@@ -337,18 +365,19 @@ __device__ __forceinline__ void sgm_step(uint32_t& a0, uint32_t& a1, uint32_t& m
 // default policy (two of the three reads hit L2) while the path volumes are streamed out.
 // ---------------------------------------------------------------------------------------------------------------
 #define VT_NST 16   // rows in flight per CTA: 16 x 1536 B
-#define VT_WARPS 8  // paths per CTA (+ 1 producer warp)
+#define VT_PATHS 8  // paths per CTA
+#define VT_WARPS 4  // consumer warps per CTA: two paths each (+ 1 producer warp)
 
 template <int DX>
 __device__ __forceinline__ void vertical_cta(const unsigned char* __restrict__ gC, unsigned char* __restrict__ gL, int k0, int W1,
                                              int H, uint32_t P1b, uint32_t P2b, unsigned char* ring, uint64_t* full,
                                              uint64_t* empty) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int nact = min(VT_WARPS, W1 - k0);  // paths of this CTA
+    const int nact = min(VT_PATHS, W1 - k0);  // paths of this CTA
     if (threadIdx.x == 0) {
         for (int s = 0; s < VT_NST; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], nact);
+            mbar_init(&empty[s], (nact + 1) / 2);  // one arrival per consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -362,9 +391,9 @@ __device__ __forceinline__ void vertical_cta(const unsigned char* __restrict__ g
                 if (y >= VT_NST) mbar_wait(&empty[s], ((y / VT_NST) - 1) & 1);
                 const int n1 = min(nact, W1 - xb);
                 mbar_expect_tx(&full[s], (uint32_t)nact * (SG_D * 2));
-                bulk_g2s(ring + s * (VT_WARPS * SG_D * 2), gC + ((size_t)y * W1 + xb) * (SG_D * 2), (uint32_t)n1 * (SG_D * 2), &full[s]);
+                bulk_g2s(ring + s * (VT_PATHS * SG_D * 2), gC + ((size_t)y * W1 + xb) * (SG_D * 2), (uint32_t)n1 * (SG_D * 2), &full[s]);
                 if (n1 < nact)
-                    bulk_g2s(ring + s * (VT_WARPS * SG_D * 2) + n1 * (SG_D * 2), gC + (size_t)y * W1 * (SG_D * 2),
+                    bulk_g2s(ring + s * (VT_PATHS * SG_D * 2) + n1 * (SG_D * 2), gC + (size_t)y * W1 * (SG_D * 2),
                              (uint32_t)(nact - n1) * (SG_D * 2), &full[s]);
                 xb += DX;
                 if (DX > 0 && xb == W1) xb = 0;
@@ -373,29 +402,41 @@ __device__ __forceinline__ void vertical_cta(const unsigned char* __restrict__ g
         }
         return;
     }
-    if (w >= nact) return;
-    const bool active = lane < 24;
-    const int src_up = (lane + 31) & 31;
-    uint32_t a0 = active ? 0u : SG_BIG2, a1 = a0, mm = 0;
-    int x = k0 + w;
+    // consumer warp w walks paths k0 + 2w (lower half-warp) and k0 + 2w + 1 (upper half-warp)
+    if (2 * w >= nact) return;
+    const bool upper = lane >= 16;
+    const int sl = lane & 15, pidx = 2 * w + (upper ? 1 : 0);
+    const bool pvalid = pidx < nact;  // the last CTA may hold an odd number of paths
+    uint32_t a[3] = {0u, 0u, 0u}, mm = 0;
+    int x = k0 + pidx;
     // everything the row loop touches is a 32-bit shared address plus an immediate, or a pointer advanced by a constant
-    const uint32_t ring_a = smem_u32(ring) + w * (SG_D * 2) + lane * 8, full_a = smem_u32(full), empty_a = smem_u32(empty);
-    unsigned char* gp = gL + (size_t)x * (SG_D * 2) + lane * 8;
+    const uint32_t ring_a = smem_u32(ring) + pidx * (SG_D * 2) + sl * 12, full_a = smem_u32(full), empty_a = smem_u32(empty);
+    unsigned char* gp = gL + (size_t)x * (SG_D * 2) + sl * 12;
     const long long rowstep = (long long)(W1 + DX) * (SG_D * 2), wrapfix = (long long)W1 * (SG_D * 2);
 #pragma unroll 2
     for (int y = 0; y < H; ++y) {
         const uint32_t s = y & (VT_NST - 1), par = (y / VT_NST) & 1;
         mbar_wait_a(full_a + s * 8, par);
-        uint2 c = make_uint2(SG_CPAD, SG_CPAD);
-        if (active) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(c.x), "=r"(c.y) : "r"(ring_a + s * (VT_WARPS * SG_D * 2)));
+        uint32_t c[3] = {0u, 0u, 0u};
+        if (pvalid) {
+            const uint32_t ra = ring_a + s * (VT_PATHS * SG_D * 2);
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c[0]) : "r"(ra));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c[1]) : "r"(ra + 4));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c[2]) : "r"(ra + 8));
+        }
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_a + s * 8) : "memory");
         if (DX != 0 && x == (DX > 0 ? 0 : W1 - 1)) {
-            a0 = a1 = active ? 0u : SG_BIG2;
+            a[0] = a[1] = a[2] = 0u;
             mm = 0;
         }
-        sgm_step(a0, a1, mm, c.x, c.y, P1b, P2b, src_up);
-        if (active) __stcs(reinterpret_cast<uint2*>(gp), make_uint2(a0, a1));
+        sgm_step2(a, mm, c, P1b, P2b, sl, upper);
+        if (pvalid) {
+            uint32_t* o = reinterpret_cast<uint32_t*>(gp);
+            __stcs(o, a[0]);
+            __stcs(o + 1, a[1]);
+            __stcs(o + 2, a[2]);
+        }
         x += DX;
         gp += rowstep;
         if (DX > 0 && x == W1) {
@@ -412,9 +453,9 @@ __device__ __forceinline__ void vertical_cta(const unsigned char* __restrict__ g
 __global__ void __launch_bounds__((VT_WARPS + 1) * 32) sgbm_vertical_kernel(const uint32_t* __restrict__ Cvol, uint32_t* __restrict__ L0v,
                                                                            uint32_t* __restrict__ L1v, uint32_t* __restrict__ L2v,
                                                                            int W1, int H, int P1, int P2) {
-    __shared__ __align__(128) unsigned char ring[VT_NST * VT_WARPS * SG_D * 2];
+    __shared__ __align__(128) unsigned char ring[VT_NST * VT_PATHS * SG_D * 2];
     __shared__ uint64_t full[VT_NST], empty[VT_NST];
-    const int k0 = blockIdx.x * VT_WARPS;
+    const int k0 = blockIdx.x * VT_PATHS;
     const int dir = blockIdx.y, pair = blockIdx.z;
     const size_t vol = (size_t)pair * H * W1 * (SG_D * 2);
     const unsigned char* gC = reinterpret_cast<const unsigned char*>(Cvol) + vol;
@@ -996,7 +1037,7 @@ static int sgbm_enqueue(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "sgbm_cost_kernel");
     vslam_time_begin(ctx, VK_SGBM_VERTICAL);
-    sgbm_vertical_kernel<<<dim3(ceil_div(W1, VT_WARPS), 3, n), (VT_WARPS + 1) * 32, 0, st>>>(s->d_C, s->d_L[0], s->d_L[1], s->d_L[2], W1, h, p.P1, p.P2);
+    sgbm_vertical_kernel<<<dim3(ceil_div(W1, VT_PATHS), 3, n), (VT_WARPS + 1) * 32, 0, st>>>(s->d_C, s->d_L[0], s->d_L[1], s->d_L[2], W1, h, p.P1, p.P2);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "sgbm_vertical_kernel");
     if (s->stop_after == 1) return VSLAM_OK;
