@@ -272,10 +272,10 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) 
         "mov.u32 n, 0;\n"
         "SG_WAIT:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra.uni SG_DONE;\n"
+        "@p bra SG_DONE;\n"
         "add.u32 n, n, 1;\n"
         "setp.lt.u32 q, n, 16777216;\n"
-        "@q bra.uni SG_WAIT;\n"
+        "@q bra SG_WAIT;\n"
         "trap;\n"
         "SG_DONE:\n"
         "}\n" ::"r"(bar_addr),
@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(SG_HW * 32) sgbm_row_backward_kernel(const uin
     __syncthreads();
     if (y >= H) return;
     unsigned char* wbase = rs_smem + (size_t)wp * RS_BWD_STAGES;
-    uint32_t* s_key = reinterpret_cast<uint32_t*>(rs_smem + (size_t)SG_HW * RS_BWD_STAGES) + (size_t)wp * W;
+    uint32_t* s_key = reinterpret_cast<uint32_t*>(wbase);  // the right-image map reuses the ring once the sweep is over
     uint64_t* bar = bars[wp];
     const size_t rowoff = ((size_t)pair * H + y) * W1 * (SG_D * 2);
     const unsigned char* gC = reinterpret_cast<const unsigned char*>(Cvol) + rowoff;
@@ -595,7 +595,6 @@ __global__ void __launch_bounds__(SG_HW * 32) sgbm_row_backward_kernel(const uin
         for (int s = 0; s < RS_NST; ++s) mbar_init(&bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = lane; i < W; i += 32) s_key[i] = 0xffffffffu;
     __syncwarp();
     auto issue = [&](int j) {  // lane 0; chunk j counts from the right end of the row
         const int s = j % RS_NST, x0 = (n_chunks - 1 - j) * RS_CH;
@@ -685,7 +684,9 @@ __global__ void __launch_bounds__(SG_HW * 32) sgbm_row_backward_kernel(const uin
         }
     }
     __syncwarp();
-    // ---- lane-parallel epilogue: right-image map ----
+    // ---- lane-parallel epilogue: right-image map (every bulk copy has landed and been consumed: the ring is free) ----
+    for (int i = lane; i < W; i += 32) s_key[i] = 0xffffffffu;
+    __syncwarp();
     for (int xx = lane; xx < W1; xx += 32) {
         const uint32_t r0 = rec[xx].x;
         const uint32_t minS = r0 & 0xffffu, bestd = (r0 >> 16) & 0xffu;
@@ -988,7 +989,7 @@ static int sgbm_check(const vslam_sgbm_params* in, int w, int h, SgParams* out) 
     // packed s16 arithmetic: real costs stay below 81*189 + P2 + P1 < 28000, padding lanes sit at 28000 .. 28000 + P2
     // and must survive + P1 without s16 overflow; ftzero <= 127 (u8 operands); the row sweep packs x into 12 bits
     if (out->P2 + out->P1 + 81 * 189 >= 28000 || 28000 + out->P2 + out->P1 > 32767 || out->ftzero > 127 ||
-        out->uniq >= 100 || w - SG_D > 4096)
+        out->uniq >= 100 || w - SG_D > 4096 || (size_t)w * 4 > RS_BWD_STAGES)
         return VSLAM_E_INVALID;
     return VSLAM_OK;
 }
@@ -1042,7 +1043,7 @@ static int sgbm_enqueue(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_
     VSLAM_LAUNCH_CHECK(ctx, "sgbm_vertical_kernel");
     if (s->stop_after == 1) return VSLAM_OK;
     const size_t smem_f = (size_t)SG_HW * RS_FWD_WARP;
-    const size_t smem = (size_t)SG_HW * RS_BWD_STAGES + (size_t)SG_HW * w * sizeof(uint32_t);
+    const size_t smem = (size_t)SG_HW * RS_BWD_STAGES;  // the right-image map (w x 4 B) aliases the ring afterwards
     VSLAM_CUDA(ctx, cudaFuncSetAttribute(sgbm_row_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
     VSLAM_CUDA(ctx, cudaFuncSetAttribute(sgbm_row_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     vslam_time_begin(ctx, VK_SGBM_ROW_FWD);
