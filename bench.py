@@ -409,6 +409,10 @@ def run_ours(args, rank, world, local_rank):
         line["pnp"] = bench_pnp(ctx, pkg)
     except Exception as ex:
         line["pnp"] = {"error": repr(ex)}
+    try:
+        line["vo_loop"] = bench_vo_loop(pkg)
+    except Exception as ex:
+        line["vo_loop"] = {"error": repr(ex)}
     if args.sgbm:
         try:
             line["sgbm"] = bench_sgbm(ctx, pkg, torch, dev, stream, sets[0][2][:8], sets[0][3][:8], peak)
@@ -418,6 +422,49 @@ def run_ours(args, rank, world, local_rank):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_vo_loop(pkg):
+    """The reference's own published number: wall-clock per keyframe / per non-keyframe of the sequential VO loop
+    (README.md:90: ~0.18 s and ~0.04 s on an unstated CPU, KITTI 00).  Here: the C++ drop-in layer's run_vslam on a
+    24-frame synthetic 1241x376 stereo sequence at the reference's operating point -- ORB(3000) + ANMS(500), dense
+    StereoSGBM depth (--dense), and per keyframe with a full window optimize_map x3 (5+5+10 LM iterations) +
+    optimize_pose_only (10).  A second run with fewer features makes every frame a keyframe so that the BA part is timed."""
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.abspath(__file__))
+    exe = os.path.join(root, "stereo-visual-slam_b200", "run_vslam")
+    if not os.path.exists(exe):
+        return {"error": "run_vslam not built"}
+    n = 24
+    lefts, rights, t, _ = pkg.synth.synth_sequence(3, n)
+    out = {"published_reference": {"keyframe_s": 0.18, "non_keyframe_s": 0.04, "hardware": "not stated (README.md:90)"}}
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(d + "/image_0")
+        os.makedirs(d + "/image_1")
+        for i in range(n):
+            pkg.synth.write_pgm(f"{d}/image_0/{i:06d}.pgm", lefts[i])
+            pkg.synth.write_pgm(f"{d}/image_1/{i:06d}.pgm", rights[i])
+        for name, extra in (("reference_defaults_dense", ["--dense"]),
+                            ("keyframe_every_frame_dense", ["--dense", "--nfeatures", "1000", "--anms", "110"])):
+            with tempfile.TemporaryDirectory() as w:
+                r = subprocess.run([exe, d + "/", str(n), *extra], cwd=w, capture_output=True, text=True, timeout=300)
+            rows = [l.split() for l in r.stdout.splitlines() if l.startswith("frame ")]
+            if r.returncode != 0 or len(rows) < 3:
+                out[name] = {"error": (r.stderr or r.stdout)[-200:]}
+                continue
+            ms = np.array([float(x[18]) for x in rows])
+            kf = np.array([int(x[15]) for x in rows]).astype(bool)
+            nkf_window = np.array([int(x[16]) for x in rows])
+            err = np.abs(np.array([[float(x[5]), float(x[9]), float(x[13])] for x in rows]) - t[:len(rows)]).max()
+            steady = np.arange(len(rows)) >= 2  # frame 0 = initialisation, frame 1 pays one-off allocations
+            full = nkf_window >= 10
+            rec = {"frames": len(rows), "keyframes": int(kf.sum()), "max_abs_position_error_m": float(err),
+                   "non_keyframe_ms": float(np.median(ms[steady & ~kf])) if (steady & ~kf).any() else None,
+                   "keyframe_ms": float(np.median(ms[steady & kf])) if (steady & kf).any() else None,
+                   "keyframe_with_full_window_ba_ms": float(np.median(ms[steady & kf & full])) if (steady & kf & full).any() else None}
+            out[name] = rec
+    return out
 
 
 def bench_pnp(ctx, pkg):

@@ -701,6 +701,45 @@ __device__ __forceinline__ int locate_level(const uint32_t* sel_cnt, int gidx, i
 // ------------------------------------------------------------------------------------------------------------
 #define ANMS_THREADS 1024
 
+// radii: grid (slices, images); every thread owns one keypoint i and scans the stronger ones.  min_j sqrt(d2_j) equals
+// sqrt(min_j d2_j) bit for bit (sqrt is monotone and correctly rounded), so the scan keeps the squared distance --
+// computed exactly as the reference's operands, float differences widened to double -- and takes one sqrt at the end.
+__global__ void __launch_bounds__(256)
+anms_radius_kernel(const __grid_constant__ OrbGeom g, const uint2* __restrict__ sel, const ImgCounters* __restrict__ cnt,
+                   int kp_cap, int num, float c_robust, double* __restrict__ rad) {
+    const int img = blockIdx.y;
+    const ImgCounters* C = &cnt[img];
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < ORB_NL; ++i) n += (int)C->sel_cnt[i];
+    if (n > kp_cap) n = kp_cap;
+    if (n < num) return;  // ANMS is a no-op for this image (visual_odometry.cpp:100)
+    double* R = rad + (size_t)img * kp_cap;
+    const uint2* S = sel + (size_t)img * ORB_NL * SORT_CAP;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int j;
+        const int l = locate_level(C->sel_cnt, i, j);
+        const uint2 e = S[(size_t)l * SORT_CAP + j];
+        const float sc = g.lv[l].scale;
+        const float xi = __fmul_rn((float)(e.x & 0xFFFF), sc), yi = __fmul_rn((float)(e.x >> 16), sc);
+        const float thr = __fmul_rn(__uint_as_float(e.y), c_robust);
+        double best2 = 1.7976931348623157e308;
+        for (int l2 = 0; l2 < ORB_NL; ++l2) {
+            const int c2 = (int)C->sel_cnt[l2];
+            const float sc2 = g.lv[l2].scale;
+            const uint2* S2 = S + (size_t)l2 * SORT_CAP;
+            for (int q = 0; q < c2; ++q) {
+                const uint2 f = S2[q];
+                if (!(__uint_as_float(f.y) > thr)) break;  // per-level lists are response-descending
+                const float dx = __fsub_rn(xi, __fmul_rn((float)(f.x & 0xFFFF), sc2));
+                const float dy = __fsub_rn(yi, __fmul_rn((float)(f.x >> 16), sc2));
+                best2 = fmin(best2, __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)));
+            }
+        }
+        R[i] = best2 < 1.7976931348623157e308 ? sqrt(best2) : best2;
+    }
+}
+
 __global__ void __launch_bounds__(ANMS_THREADS)
 anms_kernel(const __grid_constant__ OrbGeom g, const uint2* __restrict__ sel, ImgCounters* __restrict__ cnt, int kp_cap, int num,
             float c_robust, double* __restrict__ rad, uint32_t* __restrict__ keep) {
@@ -720,31 +759,7 @@ anms_kernel(const __grid_constant__ OrbGeom g, const uint2* __restrict__ sel, Im
         if (tid == 0) C->n_keep = n;
         return;
     }
-    double* R = rad + (size_t)img * kp_cap;
-    const uint2* S = sel + (size_t)img * ORB_NL * SORT_CAP;
-    for (int i = tid; i < n; i += ANMS_THREADS) {
-        int j;
-        const int l = locate_level(C->sel_cnt, i, j);
-        const uint2 e = S[(size_t)l * SORT_CAP + j];
-        const float sc = g.lv[l].scale;
-        const float xi = __fmul_rn((float)(e.x & 0xFFFF), sc), yi = __fmul_rn((float)(e.x >> 16), sc);
-        const float thr = __fmul_rn(__uint_as_float(e.y), c_robust);
-        double best = 1.7976931348623157e308;
-        for (int l2 = 0; l2 < ORB_NL; ++l2) {
-            const int c2 = (int)C->sel_cnt[l2];
-            const float sc2 = g.lv[l2].scale;
-            const uint2* S2 = S + (size_t)l2 * SORT_CAP;
-            for (int q = 0; q < c2; ++q) {
-                const uint2 f = S2[q];
-                if (!(__uint_as_float(f.y) > thr)) break;  // per-level lists are response-descending
-                const float dx = __fsub_rn(xi, __fmul_rn((float)(f.x & 0xFFFF), sc2));
-                const float dy = __fsub_rn(yi, __fmul_rn((float)(f.x >> 16), sc2));
-                const double d = sqrt(__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)));
-                best = fmin(best, d);
-            }
-        }
-        R[i] = best;
-    }
+    const double* R = rad + (size_t)img * kp_cap;  // written by anms_radius_kernel
     __syncthreads();
     // num-th largest radius by bitonic sort (descending) of the (positive) doubles
     int n2 = 1;
@@ -1142,6 +1157,12 @@ int vslam_orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h
         while (n2 < o->kp_cap) n2 <<= 1;
         if ((size_t)n2 * 8 > 65536) return VSLAM_E_CAPACITY;
         vslam_time_begin(ctx, VK_ANMS);
+        // a single image spreads its radius scan over ~2 CTAs per SM; big batches use one slice per image
+        int slices = (2 * ctx->num_sms + n_img - 1) / n_img;
+        if (slices > ceil_div(o->kp_cap, 256)) slices = ceil_div(o->kp_cap, 256);
+        if (slices < 1) slices = 1;
+        anms_radius_kernel<<<dim3(slices, n_img), 256, 0, s>>>(g, sel, cnt, o->kp_cap, anms_keep, anms_c, rad);
+        ctx->launches++;
         anms_kernel<<<n_img, ANMS_THREADS, (size_t)n2 * 8, s>>>(g, sel, cnt, o->kp_cap, anms_keep, anms_c, rad, keep);
         vslam_time_end(ctx);
         VSLAM_LAUNCH_CHECK(ctx, "anms_kernel");

@@ -4,9 +4,11 @@
 //
 //   run_vslam <dataset_dir/> <n_frames> [--no-ba] [--nfeatures N] [--anms K] [--dense] [--window W] [--update-landmarks]
 // reads <dataset_dir>/image_{0,1}/%06d.pgm, appends evicted / remaining keyframe poses to ./estimated_traj.txt
-// (the reference's format) and prints one "frame <id> <12 numbers of T_w_c> <inliers> <is_keyframe>" line per frame.
+// (the reference's format) and prints one "frame <id> <12 numbers of T_w_c> <inliers> <is_keyframe> <#keyframes>
+// <#landmarks> <frame wall-clock ms>" line per frame.
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <iostream>
 #include <string>
@@ -53,6 +55,7 @@ int main(int argc, char** argv) {
     cv::Mat K = (cv::Mat_<double>(3, 3) << fx, 0, cx, 0, fy, cy, 0, 0, 1);
 
     for (int ite = 0; ite < n_frames; ++ite) {
+        const auto t_frame = std::chrono::steady_clock::now();
         bool if_insert_keyframe = false;
         const bool not_lost = my_VO.pipeline(if_insert_keyframe);
         if (if_insert_keyframe && do_ba && (int)my_map.keyframes_.size() >= my_map.num_keyframes_) {
@@ -67,7 +70,10 @@ int main(int argc, char** argv) {
         for (int r = 0; r < 3; ++r)
             std::printf(" %.9g %.9g %.9g %.9g", T_w_c.rotationMatrix()(r, 0), T_w_c.rotationMatrix()(r, 1),
                         T_w_c.rotationMatrix()(r, 2), T_w_c.translation()(r));
-        std::printf(" %d %d %zu %zu\n", my_VO.num_inliers_, (int)if_insert_keyframe, my_map.keyframes_.size(), my_map.landmarks_.size());
+        // wall-clock of this frame: pipeline (+ BA when it ran); the reference's README quotes these per (non-)keyframe
+        const double frame_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_frame).count();
+        std::printf(" %d %d %zu %zu %.3f\n", my_VO.num_inliers_, (int)if_insert_keyframe, my_map.keyframes_.size(),
+                    my_map.landmarks_.size(), frame_ms);
         if (!not_lost) break;
     }
     my_map.write_remaining_pose();

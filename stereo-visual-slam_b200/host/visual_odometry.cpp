@@ -6,6 +6,8 @@
 #include <stereo_visual_slam_main/visual_odometry.hpp>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -327,6 +329,15 @@ bool VO::initialization() {
 }
 
 bool VO::tracking(bool& if_insert_keyframe) {
+    // VSLAM_VO_TRACE=1: per-stage wall clock of this frame on stderr
+    static const bool trace = std::getenv("VSLAM_VO_TRACE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    double t_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    auto lap = [&](int k) {
+        const auto t1 = std::chrono::steady_clock::now();
+        t_ms[k] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        t0 = t1;
+    };
     frame_current_ = Frame();
     // pick up the BA-optimised pose of the last keyframe
     if (frame_last_.is_keyframe_) {
@@ -338,10 +349,12 @@ bool VO::tracking(bool& if_insert_keyframe) {
         return false;
     }
     frame_current_.frame_id_ = seq_;
+    lap(0);
 
     std::vector<cv::KeyPoint> keypoints;
     cv::Mat descriptors;
     feature_detection(frame_current_.left_img_, keypoints, descriptors);
+    lap(1);
 
     // descriptors of the last frame's features, gathered into one matrix
     cv::Mat descriptors_last((int)frame_last_.features_.size(), 32, cv::CV_8U);
@@ -349,6 +362,7 @@ bool VO::tracking(bool& if_insert_keyframe) {
         std::memcpy(descriptors_last.ptr<uint8_t>((int)i), frame_last_.features_[i].descriptor_.data, 32);
     std::vector<cv::DMatch> matches;
     feature_matching(descriptors_last, descriptors, matches);  // query = last frame, train = current frame
+    lap(2);
 
     for (size_t i = 0; i < matches.size(); ++i) {
         Feature f((int)i, seq_, keypoints[matches[i].trainIdx], descriptors.row(matches[i].trainIdx));
@@ -356,14 +370,22 @@ bool VO::tracking(bool& if_insert_keyframe) {
         frame_current_.features_.push_back(f);
     }
 
+    lap(5);
     motion_estimation(frame_current_);
+    lap(3);
     frame_current_.T_c_w_ = T_c_w_;
     T_c_l_ = frame_current_.T_c_w_ * frame_last_.T_c_w_.inverse();
 
     const bool ok = check_motion_estimation();
+    lap(6);
     std::vector<cv::Point3f> pts_3d;
     if_insert_keyframe = insert_key_frame(ok, pts_3d, keypoints, descriptors);
+    lap(4);
     if (ok) move_frame();
+    lap(7);
+    if (trace)
+        std::fprintf(stderr, "[vo] frame %d: read %.3f detect %.3f match %.3f pnp %.3f check %.3f keyframe %.3f move %.3f bookkeeping %.3f ms\n",
+                     seq_, t_ms[0], t_ms[1], t_ms[2], t_ms[3], t_ms[6], t_ms[4], t_ms[7], t_ms[5]);
     seq_++;
     return ok;
 }
