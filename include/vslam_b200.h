@@ -250,7 +250,8 @@ int vslam_ba_optimize(vslam_ctx* ctx, int n_poses, double* poses, int n_points, 
  * (T_c_w, may be NULL), and the ascending inlier index list.  The pose is the Gauss-Newton optimum of
  * the reprojection error over the inliers of the best hypothesis (what OpenCV returns);
  * all `iters` hypotheses are scored (no confidence-based early exit), so on inputs with a clear
- * consensus the inlier set and pose equal cv2's.  n < 6 yields *n_inliers = 0.
+ * consensus the inlier set and pose equal cv2's.  n < 6 yields *n_inliers = 0.  `inliers` must hold n entries; the first
+ * *n_inliers are the ascending inlier indices, the rest is unspecified.
  * ---------------------------------------------------------------------------------------------- */
 int vslam_pnp_ransac(vslam_ctx* ctx, const float* xyz, const float* uv, int n, const double* Kmat, int iters,
                      float reproj_err, double confidence, double* rvec, double* tvec, double* T_c_w,

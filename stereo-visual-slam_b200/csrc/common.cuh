@@ -22,7 +22,7 @@ struct SgbmState;  // sgbm.cu
 enum {
     VK_RESIZE = 0, VK_FAST, VK_HARRIS_SELECT, VK_BLUR, VK_ANMS, VK_DESCRIBE, VK_HAMMING_ARGMIN, VK_CROSSCHECK,
     VK_TRIANGULATE, VK_BA_BUILD, VK_BA_SOLVE, VK_BA_UPDATE, VK_BA_MISC, VK_PNP, VK_SGBM_PREFILTER, VK_SGBM_COST,
-    VK_SGBM_VERTICAL, VK_SGBM_ROW_FWD, VK_SGBM_ROW_BWD, VK_SGBM_POST, VK_COUNT
+    VK_SGBM_VERTICAL, VK_SGBM_ROW_FWD, VK_SGBM_ROW_BWD, VK_SGBM_POST, VK_PNP_REFINE, VK_COUNT
 };
 #define VSLAM_TIMING_CAP 16384
 struct TimingRec {

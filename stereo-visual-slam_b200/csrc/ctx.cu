@@ -106,8 +106,8 @@ extern "C" int64_t vslam_ctx_launch_count(const vslam_ctx* ctx) { return ctx ? c
 static const char* const k_kernel_names[VK_COUNT] = {
     "resize_level_kernel", "fast_kernel", "harris_select_kernel", "blur_kernel", "anms_kernel", "describe_kernel",
     "hamming_argmin_kernel", "crosscheck_gate_compact_kernel", "triangulate_kernel", "ba_lm_kernel",
-    "ba_solve_kernel", "ba_update_kernel", "ba_misc_kernel", "pnp_kernel", "sgbm_prefilter_kernel", "sgbm_cost_kernel",
-    "sgbm_vertical_kernel", "sgbm_row_forward_kernel", "sgbm_row_backward_kernel", "sgbm_post_kernels"};
+    "ba_solve_kernel", "ba_update_kernel", "ba_misc_kernel", "pnp_hypothesis_kernel", "sgbm_prefilter_kernel", "sgbm_cost_kernel",
+    "sgbm_vertical_kernel", "sgbm_row_forward_kernel", "sgbm_row_backward_kernel", "sgbm_post_kernels", "pnp_refine_kernel"};
 
 extern "C" int vslam_kernel_count(void) { return VK_COUNT; }
 extern "C" const char* vslam_kernel_name(int id) { return id >= 0 && id < VK_COUNT ? k_kernel_names[id] : ""; }

@@ -143,63 +143,67 @@ __device__ __forceinline__ void gn_accumulate(const double* T, const PnpCam& cam
     }
 }
 
-// 6-point DLT: null vector of the 12x12 system by one-sided Jacobi on A^T (12 columns), then pose extraction
-__device__ bool dlt6(const float* xyz, const float* uv, const int* idx, const PnpCam& cam, double* T) {
-    double A[12][12], V[12][12];
-    for (int i = 0; i < 12; ++i)
-        for (int j = 0; j < 12; ++j) {
-            A[i][j] = 0;
-            V[i][j] = i == j ? 1.0 : 0.0;
-        }
+// 6-point DLT.  The 12x12 system's null vector is the eigenvector of the smallest eigenvalue of M = A^T A; it is found
+// by inverse iteration on a Cholesky factor of M + mu I (the gap between the noise-level smallest eigenvalue and the
+// next one makes a handful of iterations converge to machine precision), a few hundred flops instead of the thousands
+// of dependent rotations of a one-sided Jacobi SVD that used to make this kernel the longest stage of a VO frame.
+// The pose is then polished by Gauss-Newton on the sample itself, which removes what the normal equations lose.
+__device__ void dlt6_rows(const float* xyz, const float* uv, const int* idx, const PnpCam& cam, double* A /*[12][12]*/) {
+    for (int i = 0; i < 144; ++i) A[i] = 0;
     for (int s = 0; s < 6; ++s) {
         const int i = idx[s];
         const double X = xyz[3 * i], Y = xyz[3 * i + 1], Z = xyz[3 * i + 2];
         const double x = ((double)uv[2 * i] - cam.cx) / cam.fx, y = ((double)uv[2 * i + 1] - cam.cy) / cam.fy;  // normalised
-        double* r0 = A[2 * s];
-        double* r1 = A[2 * s + 1];
+        double* r0 = A + 12 * (2 * s);
+        double* r1 = A + 12 * (2 * s + 1);
         r0[0] = X; r0[1] = Y; r0[2] = Z; r0[3] = 1; r0[8] = -x * X; r0[9] = -x * Y; r0[10] = -x * Z; r0[11] = -x;
         r1[4] = X; r1[5] = Y; r1[6] = Z; r1[7] = 1; r1[8] = -y * X; r1[9] = -y * Y; r1[10] = -y * Z; r1[11] = -y;
     }
-    for (int sweep = 0; sweep < 40; ++sweep) {
-        bool changed = false;
-        for (int i = 0; i < 11; ++i)
-            for (int j = i + 1; j < 12; ++j) {
-                double a = 0, b = 0, p = 0;
-                for (int k = 0; k < 12; ++k) {
-                    a += A[k][i] * A[k][i];
-                    b += A[k][j] * A[k][j];
-                    p += A[k][i] * A[k][j];
-                }
-                if (fabs(p) <= 1e-15 * sqrt(a * b)) continue;
-                changed = true;
-                p *= 2;
-                const double beta = a - b, gamma = hypot(p, beta);
-                double c, s;
-                if (beta < 0) {
-                    s = sqrt((gamma - beta) * 0.5 / gamma);
-                    c = p / (gamma * s * 2);
-                } else {
-                    c = sqrt((gamma + beta) / (gamma * 2));
-                    s = p / (gamma * c * 2);
-                }
-                for (int k = 0; k < 12; ++k) {
-                    const double t0 = c * A[k][i] + s * A[k][j], t1 = -s * A[k][i] + c * A[k][j];
-                    A[k][i] = t0; A[k][j] = t1;
-                    const double v0 = c * V[k][i] + s * V[k][j], v1 = -s * V[k][i] + c * V[k][j];
-                    V[k][i] = v0; V[k][j] = v1;
-                }
-            }
-        if (!changed) break;
+}
+
+// M (12x12 symmetric, row-major, overwritten by its Cholesky factor) -> unit eigenvector of the smallest eigenvalue
+__device__ bool smallest_eigvec12(double* M, double* x) {
+    double tr = 0;
+    for (int i = 0; i < 12; ++i) tr += M[i * 13];
+    if (!(tr > 0) || !isfinite(tr)) return false;
+    const double mu = 1e-13 * tr;
+    for (int j = 0; j < 12; ++j) {  // lower Cholesky, in place
+        double d = M[j * 13] + mu;
+        for (int k = 0; k < j; ++k) d -= M[j * 12 + k] * M[j * 12 + k];
+        if (!(d > 0)) d = mu;  // rank-deficient sample: keep going, the hypothesis will score badly
+        const double l = sqrt(d), il = 1.0 / l;
+        M[j * 13] = l;
+        for (int i = j + 1; i < 12; ++i) {
+            double v = M[i * 12 + j];
+            for (int k = 0; k < j; ++k) v -= M[i * 12 + k] * M[j * 12 + k];
+            M[i * 12 + j] = v * il;
+        }
     }
-    int bi = 0;
-    double best = 1e300;
-    for (int j = 0; j < 12; ++j) {
-        double n = 0;
-        for (int k = 0; k < 12; ++k) n += A[k][j] * A[k][j];
-        if (n < best) { best = n; bi = j; }
+    for (int i = 0; i < 12; ++i) x[i] = 0.28867513459481287 * ((i & 1) ? 1.0 : 0.9) * ((i % 3) ? 1.0 : 1.1);  // generic start
+    for (int it = 0; it < 6; ++it) {
+        for (int i = 0; i < 12; ++i) {  // L y = x
+            double v = x[i];
+            for (int k = 0; k < i; ++k) v -= M[i * 12 + k] * x[k];
+            x[i] = v / M[i * 13];
+        }
+        for (int i = 11; i >= 0; --i) {  // L^T z = y
+            double v = x[i];
+            for (int k = i + 1; k < 12; ++k) v -= M[k * 12 + i] * x[k];
+            x[i] = v / M[i * 13];
+        }
+        double nn = 0;
+        for (int i = 0; i < 12; ++i) nn += x[i] * x[i];
+        if (!(nn > 0) || !isfinite(nn)) return false;
+        const double inv = 1.0 / sqrt(nn);
+        for (int i = 0; i < 12; ++i) x[i] *= inv;
     }
+    return true;
+}
+
+// pose from the DLT null vector P = s [R | t], then Gauss-Newton on the six correspondences
+__device__ bool dlt6_pose(const float* xyz, const float* uv, const int* idx, const PnpCam& cam, const double* Pv, double* T) {
     double P[12];
-    for (int k = 0; k < 12; ++k) P[k] = V[k][bi];
+    for (int k = 0; k < 12; ++k) P[k] = Pv[k];
     // P = s [R | t]: fix the sign with det(R) > 0, the scale with the mean row norm
     double R[9] = {P[0], P[1], P[2], P[4], P[5], P[6], P[8], P[9], P[10]};
     const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
@@ -234,8 +238,8 @@ __device__ bool dlt6(const float* xyz, const float* uv, const int* idx, const Pn
 __global__ void __launch_bounds__(PNP_THREADS)
 pnp_hypothesis_kernel(const float* __restrict__ xyz, const float* __restrict__ uv, int n, PnpCam cam, float thr2,
                       uint32_t seed, double* __restrict__ hyp, int* __restrict__ cnt) {
-    __shared__ double sT[12];
-    __shared__ int s_ok, s_cnt;
+    __shared__ double sT[12], sA[144], sM[144];
+    __shared__ int s_ok, s_cnt, s_idx[6];
     const int h = blockIdx.x;
     if (threadIdx.x == 0) {
         uint32_t s = seed * 2654435761u + (uint32_t)h * 40503u + 12345u;
@@ -249,10 +253,27 @@ pnp_hypothesis_kernel(const float* __restrict__ xyz, const float* __restrict__ u
                 if (!dup) { idx[k] = c; break; }
             }
         }
-        double T[12];
-        s_ok = dlt6(xyz, uv, idx, cam, T) ? 1 : 0;
-        for (int i = 0; i < 12; ++i) sT[i] = T[i];
+        for (int k = 0; k < 6; ++k) s_idx[k] = idx[k];
+        dlt6_rows(xyz, uv, idx, cam, sA);
         s_cnt = 0;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 144; e += PNP_THREADS) {  // M = A^T A, one entry per thread
+        const int r = e / 12, c = e - r * 12;
+        double v = 0;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) v += sA[k * 12 + r] * sA[k * 12 + c];
+        sM[e] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int idx[6];
+        for (int k = 0; k < 6; ++k) idx[k] = s_idx[k];
+        double x[12], T[12];
+        bool ok = smallest_eigvec12(sM, x);
+        if (ok) ok = dlt6_pose(xyz, uv, idx, cam, x, T);
+        s_ok = ok ? 1 : 0;
+        for (int i = 0; i < 12; ++i) sT[i] = ok ? T[i] : 0.0;
     }
     __syncthreads();
     int c = 0;
@@ -510,20 +531,20 @@ extern "C" int vslam_pnp_ransac(vslam_ctx* ctx, const float* xyz, const float* u
     pnp_hypothesis_kernel<<<iters, PNP_THREADS, 0, s>>>(p->d_xyz, p->d_uv, n, cam, thr2, 0x9E3779B9u, p->d_hyp, p->d_cnt);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "pnp_hypothesis_kernel");
-    vslam_time_begin(ctx, VK_PNP);
+    vslam_time_begin(ctx, VK_PNP_REFINE);
     pnp_refine_kernel<<<1, PNP_THREADS, 0, s>>>(p->d_xyz, p->d_uv, n, cam, thr2, iters, p->d_hyp, p->d_cnt, 30, p->d_out,
                                                 p->d_inl);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "pnp_refine_kernel");
     double out[18];
     int cnt = 0;
+    // one round trip: count, pose and the whole index buffer (entries past the count are unspecified, as documented)
     VSLAM_CUDA(ctx, cudaMemcpyAsync(&cnt, p->d_inl, sizeof(int), cudaMemcpyDeviceToHost, s));
     VSLAM_CUDA(ctx, cudaMemcpyAsync(out, p->d_out, sizeof(out), cudaMemcpyDeviceToHost, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(inliers, p->d_inl + 1, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
     VSLAM_CUDA(ctx, cudaStreamSynchronize(s));
     *n_inliers = cnt;
     if (cnt <= 0) return VSLAM_OK;
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(inliers, p->d_inl + 1, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, s));
-    VSLAM_CUDA(ctx, cudaStreamSynchronize(s));
     for (int i = 0; i < 3; ++i) {
         rvec[i] = out[i];
         tvec[i] = out[3 + i];
