@@ -701,7 +701,7 @@ __device__ __forceinline__ int locate_level(const uint32_t* sel_cnt, int gidx, i
 // ------------------------------------------------------------------------------------------------------------
 #define ANMS_THREADS 1024
 
-// radii: grid (slices, images); every thread owns one keypoint i and scans the stronger ones.  min_j sqrt(d2_j) equals
+// radii: grid (slices, images); every warp owns one keypoint i at a time and scans the stronger ones.  min_j sqrt(d2_j) equals
 // sqrt(min_j d2_j) bit for bit (sqrt is monotone and correctly rounded), so the scan keeps the squared distance --
 // computed exactly as the reference's operands, float differences widened to double -- and takes one sqrt at the end.
 __global__ void __launch_bounds__(256)
@@ -716,7 +716,9 @@ anms_radius_kernel(const __grid_constant__ OrbGeom g, const uint2* __restrict__ 
     if (n < num) return;  // ANMS is a no-op for this image (visual_odometry.cpp:100)
     double* R = rad + (size_t)img * kp_cap;
     const uint2* S = sel + (size_t)img * ORB_NL * SORT_CAP;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    // one warp per keypoint i, lanes stride over the stronger keypoints of every level, warp-min at the end
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
         int j;
         const int l = locate_level(C->sel_cnt, i, j);
         const uint2 e = S[(size_t)l * SORT_CAP + j];
@@ -728,7 +730,7 @@ anms_radius_kernel(const __grid_constant__ OrbGeom g, const uint2* __restrict__ 
             const int c2 = (int)C->sel_cnt[l2];
             const float sc2 = g.lv[l2].scale;
             const uint2* S2 = S + (size_t)l2 * SORT_CAP;
-            for (int q = 0; q < c2; ++q) {
+            for (int q = lane; q < c2; q += 32) {
                 const uint2 f = S2[q];
                 if (!(__uint_as_float(f.y) > thr)) break;  // per-level lists are response-descending
                 const float dx = __fsub_rn(xi, __fmul_rn((float)(f.x & 0xFFFF), sc2));
@@ -736,7 +738,9 @@ anms_radius_kernel(const __grid_constant__ OrbGeom g, const uint2* __restrict__ 
                 best2 = fmin(best2, __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)));
             }
         }
-        R[i] = best2 < 1.7976931348623157e308 ? sqrt(best2) : best2;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best2 = fmin(best2, __shfl_xor_sync(0xFFFFFFFFu, best2, o));
+        if (lane == 0) R[i] = best2 < 1.7976931348623157e308 ? sqrt(best2) : best2;
     }
 }
 
@@ -1158,8 +1162,8 @@ int vslam_orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h
         if ((size_t)n2 * 8 > 65536) return VSLAM_E_CAPACITY;
         vslam_time_begin(ctx, VK_ANMS);
         // a single image spreads its radius scan over ~2 CTAs per SM; big batches use one slice per image
-        int slices = (2 * ctx->num_sms + n_img - 1) / n_img;
-        if (slices > ceil_div(o->kp_cap, 256)) slices = ceil_div(o->kp_cap, 256);
+        int slices = (4 * ctx->num_sms + n_img - 1) / n_img;
+        if (slices > ceil_div(o->kp_cap, 8)) slices = ceil_div(o->kp_cap, 8);  // 8 warps = 8 keypoints per CTA pass
         if (slices < 1) slices = 1;
         anms_radius_kernel<<<dim3(slices, n_img), 256, 0, s>>>(g, sel, cnt, o->kp_cap, anms_keep, anms_c, rad);
         ctx->launches++;
