@@ -446,7 +446,9 @@ def bench_vo_loop(pkg):
             pkg.synth.write_pgm(f"{d}/image_0/{i:06d}.pgm", lefts[i])
             pkg.synth.write_pgm(f"{d}/image_1/{i:06d}.pgm", rights[i])
         for name, extra in (("reference_defaults_dense", ["--dense"]),
-                            ("keyframe_every_frame_dense", ["--dense", "--nfeatures", "1000", "--anms", "110"])):
+                            ("keyframe_every_frame_dense", ["--dense", "--nfeatures", "1000", "--anms", "110"]),
+                            # the north star's sparse-stereo depth (ORB on both images + L<->R matching + DLT) instead of SGBM
+                            ("keyframe_every_frame_sparse", ["--nfeatures", "1000", "--anms", "110"])):
             with tempfile.TemporaryDirectory() as w:
                 r = subprocess.run([exe, d + "/", str(n), *extra], cwd=w, capture_output=True, text=True, timeout=300)
             rows = [l.split() for l in r.stdout.splitlines() if l.startswith("frame ")]
