@@ -12,7 +12,7 @@
 
 #include <stdlib.h>
 
-#define FRONT_CHUNK_PAIRS 32   // pairs per pipeline chunk
+#define FRONT_CHUNK_PAIRS 16   // pairs per pipeline chunk (two compute streams: 12 -> 17.7k, 16 -> 18.4k, 24 -> 18.2k, 32 -> 18.0k e2e fps)
 #define FRONT_MAX_CHUNKS 64
 
 struct FrontState {
@@ -373,7 +373,8 @@ extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, 
     // VSLAM_FRONT_TRACE=1), so ramping the pipeline up with small chunks loses more than the exposed first upload costs.
     int c_start[FRONT_MAX_CHUNKS + 1], n_chunks = 0;
     {
-        int chunk = FRONT_CHUNK_PAIRS;
+        static const int chunk_env = getenv("VSLAM_FRONT_CHUNK") ? atoi(getenv("VSLAM_FRONT_CHUNK")) : 0;
+        int chunk = chunk_env > 0 ? chunk_env : FRONT_CHUNK_PAIRS;
         if (ceil_div(n_pairs, chunk) > FRONT_MAX_CHUNKS) chunk = ceil_div(n_pairs, FRONT_MAX_CHUNKS);
         c_start[0] = 0;
         for (int done = 0; done < n_pairs;) {
