@@ -9,16 +9,17 @@
 // of each other, so here every path direction is its own sweep over a materialised cost volume:
 //   K18 sgbm_prefilter_kernel   x-Sobel + clip table, raw row, half-pixel min/max (Birchfield-Tomasi operands)
 //   K19 sgbm_cost_kernel        BT pixel cost on both planes + 9x9 box sum (replicated borders) -> C[y][x][d] u16
-//   K20 sgbm_vertical_kernel    paths from the row above (up-left, up, up-right): one warp per path, diagonal paths
-//                               wrap around the image so every warp walks all H rows with no inter-warp traffic
+//   K20 sgbm_vertical_kernel    paths from the row above (up-left, up, up-right): two paths per warp (one per
+//                               half-warp), diagonal paths wrap around the image so every path walks all H rows with
+//                               no inter-warp traffic; rows of C arrive through a cp.async.bulk ring
 //   K21 sgbm_row_forward_kernel / sgbm_row_backward_kernel  one warp per row: left->right path, then right->left
 //                               path fused with the winner-take-all, uniqueness test, sub-pixel fit, right-image map
 //                               and LR consistency check
 //   K22 sgbm_median_kernel      cv::medianBlur(3)
 //   K23 speckle_*_kernel        cv::filterSpeckles as union-find connected components
-// 96 disparities are held as 48 packed s16x2 words; a path step is VIADD.16x2 / VIMNMX.S16x2 on 2 words per lane
-// (24 lanes) plus one CREDUX.MIN for min_k L_r(p-r, k).  All volumes are HBM-resident u16: these kernels are
-// bandwidth-bound.
+// 96 disparities are held as 48 packed s16x2 words; a path step is VIADD.16x2 / VIMNMX.S16x2 on 2 words per lane over 24
+// lanes (row sweeps) or 3 words per lane over a half-warp (vertical sweep) plus CREDUX.MIN for min_k L_r(p-r, k).  All
+// volumes are HBM-resident u16 and stream through cp.async.bulk (TMA) rings; DESIGN.md §4 has the bounds.
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -26,17 +27,10 @@
 #define SG_D 96
 #define SG_NDP 48                    // packed disparity pairs
 #define SG_R 4                       // block radius (blockSize 9)
-#define SG_TX 16                     // columns per cost-kernel strip
-#define SG_NC (SG_TX + 2 * SG_R)     // pixel-cost columns a strip needs
-#define SG_NRH 61                    // packed right-row words per parity
-#define SG_BANDS 8                   // row bands of the cost kernel (each re-computes 2*SG_R halo rows)
 #define SG_BIG2 0x75307530u          // 30000 | 30000 << 16: "no predecessor" cost, > any reachable min + P2
 #define SG_MAXCOST 32767
 #define SG_INVALID (-16)
 #define SG_HW 2                      // rows (warps) per CTA of the row sweeps
-#define SG_PF 8                      // rows the vertical sweep loads ahead
-#define SG_PF1 8                     // columns the row sweep loads ahead, pass 1 (4 volumes)
-#define SG_PF2 16                    // pass 2 (2 volumes)
 #define SG_CHUNK_PAIRS 8             // pairs per scratch chunk (8 x 331 MB)
 
 struct SgParams {
