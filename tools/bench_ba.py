@@ -5,7 +5,7 @@ import numpy as np
 import vslam_b200_loader as L
 pkg = L.pkg
 ctx = pkg.Context(max_images=0, max_width=0, max_height=0, max_keypoints=1)
-for name, (seed, nk, nl, nobs) in {"cfg3": (42, 10, 5000, None), "cfg5": (43, 50, 20000, 100000)}.items():
+for name, (seed, nk, nl, nobs) in {"vo_window": (7, 10, 600, None), "cfg3": (42, 10, 5000, None), "cfg5": (43, 50, 20000, 100000)}.items():
     p = pkg.synth.synth_ba_problem(seed, nk, nl, n_obs_exact=nobs)
     a = (p["poses"], p["points"], p["obs_pose"], p["obs_point"], p["obs_uv"], p["K"])
     for _ in range(2):
