@@ -527,9 +527,22 @@ __device__ void ba_phase_solve_cta(const BaParams& P, int slot, double* smem) {
     if (blockIdx.x != 0) return;
     const int n = P.n, ld = P.n + 1, tid = threadIdx.x, nt = blockDim.x;
     __shared__ int s_fail;
+    __shared__ double s_rd[BA_SMEM_CHOL_MAX];  // reciprocal diagonal of U, for the backward substitution
     double* M = smem;  // n x (n + 1)
     if (tid == 0) s_fail = 0;
-    for (int i = tid; i < n * n; i += nt) M[(i / n) * ld + i % n] = P.S[i];
+    for (int base = 0; base < n * n; base += 8 * nt) {  // eight independent L2 reads in flight per thread
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = base + k * nt + tid;
+            v[k] = i < n * n ? P.S[i] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = base + k * nt + tid;
+            if (i < n * n) M[(i / n) * ld + i % n] = v[k];
+        }
+    }
     for (int i = tid; i < n; i += nt) M[i * ld + n] = P.bs[i];
     __syncthreads();
     for (int j0 = 0; j0 < n; j0 += 6) {
@@ -555,18 +568,18 @@ __device__ void ba_phase_solve_cta(const BaParams& P, int slot, double* smem) {
 #pragma unroll
                 for (int r = 0; r < 6; ++r) M[(j0 + r) * ld + c] = v[r];
             }
-            __syncthreads();  // everyone has read the un-factored diagonal block
-            if (tid == 0) {
+            __syncthreads();  // block row done; everyone has read the un-factored diagonal block
+            if (tid == 0) {   // nobody reads this diagonal block again before the backward substitution
                 if (!ok) s_fail = 1;
 #pragma unroll
-                for (int r = 0; r < 6; ++r)
+                for (int r = 0; r < 6; ++r) {
 #pragma unroll
                     for (int c = 0; c < 6; ++c)
                         if (c >= r) M[(j0 + r) * ld + j0 + c] = D[r * 6 + c];
+                    s_rd[j0 + r] = rinv[r];
+                }
             }
         }
-        __syncthreads();
-        if (s_fail) break;
         const int m = n - j0 - 6;  // trailing update of the upper triangle and of the rhs column
         for (int e = tid; e < m * (m + 1); e += nt) {
             const int r = j0 + 6 + e / (m + 1), c = j0 + 6 + e % (m + 1);
@@ -577,6 +590,7 @@ __device__ void ba_phase_solve_cta(const BaParams& P, int slot, double* smem) {
             M[r * ld + c] = v;
         }
         __syncthreads();
+        if (s_fail) break;
     }
     const int fail = s_fail;
     if (!fail) {
@@ -590,7 +604,7 @@ __device__ void ba_phase_solve_cta(const BaParams& P, int slot, double* smem) {
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 x[r] = M[(j0 + r) * ld + n];
-                rinv[r] = 1.0 / D[r * 6 + r];  // six independent divisions, pipelined
+                rinv[r] = s_rd[j0 + r];
             }
 #pragma unroll
             for (int r = 5; r >= 0; --r) {
