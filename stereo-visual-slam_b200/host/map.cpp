@@ -7,6 +7,11 @@
 
 namespace vslam {
 
+Map::Map(ros::NodeHandle& nh) : my_visual_(nh) {
+    nh.getParam("/if_write_pose", if_write_pose_);
+    nh.getParam("/if_rviz", if_rviz_);
+}
+
 int Map::insert_keyframe(Frame frame_to_add) {
     current_keyframe_id_ = frame_to_add.keyframe_id_;
     keyframes_[frame_to_add.keyframe_id_] = frame_to_add;

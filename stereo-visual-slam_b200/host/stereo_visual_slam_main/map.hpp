@@ -21,19 +21,17 @@ struct Map {
     int current_keyframe_id_ = 0;
 
     VslamVisual my_visual_;
-    bool if_write_pose_ = false;
-    bool if_rviz_ = false;
+    bool if_write_pose_ = false, if_rviz_ = false;  // parameter server: /if_write_pose, /if_rviz
 
-    explicit Map(ros::NodeHandle& nh) : my_visual_(nh) {
-        nh.getParam("/if_write_pose", if_write_pose_);
-        nh.getParam("/if_rviz", if_rviz_);
-    }
+    explicit Map(ros::NodeHandle& nh);
 
+    // window maintenance (all return 0, like the reference)
     int insert_keyframe(Frame frame_to_add);
     int insert_landmark(Landmark landmark_to_add);
     int remove_keyframe();
     int clean_map();
-    void publish_keyframes() {}
+    // output
+    void publish_keyframes() {}  // rviz only in the reference
     void write_pose(const Frame& frame);
     void write_remaining_pose();
 };
