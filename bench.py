@@ -458,10 +458,13 @@ def bench_vo_loop(pkg):
             ms = np.array([float(x[18]) for x in rows])
             kf = np.array([int(x[15]) for x in rows]).astype(bool)
             nkf_window = np.array([int(x[16]) for x in rows])
-            err = np.abs(np.array([[float(x[5]), float(x[9]), float(x[13])] for x in rows]) - t[:len(rows)]).max()
+            pos = np.array([[float(x[5]), float(x[9]), float(x[13])] for x in rows])
+            err = np.abs(pos - t[:len(rows)]).max()
+            ate = float(np.sqrt(((pos - t[:len(rows)]) ** 2).sum(axis=1).mean()))  # no alignment: frame 0 is the origin
             steady = np.arange(len(rows)) >= 2  # frame 0 = initialisation, frame 1 pays one-off allocations
             full = nkf_window >= 10
-            rec = {"frames": len(rows), "keyframes": int(kf.sum()), "max_abs_position_error_m": float(err),
+            rec = {"frames": len(rows), "keyframes": int(kf.sum()), "max_abs_position_error_m": float(err), "ate_rmse_m": ate,
+                   "path_length_m": float(np.linalg.norm(np.diff(t[:len(rows)], axis=0), axis=1).sum()),
                    "non_keyframe_ms": float(np.median(ms[steady & ~kf])) if (steady & ~kf).any() else None,
                    "keyframe_ms": float(np.median(ms[steady & kf])) if (steady & kf).any() else None,
                    "keyframe_with_full_window_ba_ms": float(np.median(ms[steady & kf & full])) if (steady & kf & full).any() else None}
