@@ -78,3 +78,23 @@ def test_find_3d_truncates_like_mat_at():
     kp = np.array([[7.9, 3.9], [8.0, 3.0]], np.float32)
     X = G.find_3d(kp, disp, 718.856, 718.856, 607.1928, 185.2157, 0.573)
     assert np.isclose(X[0, 2], 718.856 * 0.573 / 8.0) and X[1, 2] < 0  # invalid (-1) gives a negative depth
+
+
+def test_sgbm_random_parameters_and_sizes(pkg):
+    """seeded sweep over image sizes and the free parameters (penalties, uniqueness, LR tolerance, prefilter cap,
+    speckle filter): the restatement must equal live cv2 everywhere, not only at the reference's constants"""
+    rng = np.random.default_rng(2024)
+    for trial in range(14):
+        h = int(rng.integers(3, 48))
+        w = int(rng.integers(104, 260))
+        left, right = _crop(pkg, int(rng.integers(0, 10)), h, w, y0=int(rng.integers(0, 300)), x0=int(rng.integers(0, 900)))
+        if trial % 4 == 3:  # decorrelate the pair now and then: many invalid / speckle pixels
+            right = np.ascontiguousarray(np.roll(right, int(rng.integers(1, 7)), axis=0))
+        P1 = int(rng.integers(1, 900))
+        kw = dict(P1=P1, P2=P1 + int(rng.integers(1, 2500)), disp12MaxDiff=int(rng.integers(1, 5)),
+                  preFilterCap=int(rng.integers(1, 64)), uniquenessRatio=int(rng.integers(0, 40)),
+                  speckleWindowSize=int(rng.choice([0, 10, 50, 100, 200])), speckleRange=int(rng.integers(1, 40)))
+        p = G.Params(P1=kw["P1"], P2=kw["P2"], disp12_max_diff=kw["disp12MaxDiff"], pre_filter_cap=kw["preFilterCap"],
+                     uniqueness_ratio=kw["uniquenessRatio"], speckle_window_size=kw["speckleWindowSize"],
+                     speckle_range=kw["speckleRange"])
+        assert np.array_equal(G.sgbm_compute(left, right, p), _cv(left, right, **kw)), (trial, h, w, kw)

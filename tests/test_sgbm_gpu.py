@@ -145,3 +145,24 @@ def test_sgbm_two_stream_chunks_equal_single_stream(pkg, gpu_ctx):
         gpu_ctx.set_concurrency(True)
     assert np.array_equal(got[True], got[False])
     assert np.array_equal(got[True], np.stack([G.sgbm_compute(L[i], R[i]) for i in range(n)]))
+
+
+def test_sgbm_random_parameters_and_sizes(pkg, gpu_ctx):
+    """the seeded parameter / size sweep of tests/test_oracle_sgbm.py through the C-ABI, against live cv2"""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(2024)
+    for trial in range(14):
+        h = int(rng.integers(3, 48))
+        w = int(rng.integers(104, 260))
+        left, right = _crop(pkg, int(rng.integers(0, 10)), h, w, y0=int(rng.integers(0, 300)), x0=int(rng.integers(0, 900)))
+        if trial % 4 == 3:
+            right = np.ascontiguousarray(np.roll(right, int(rng.integers(1, 7)), axis=0))
+        P1 = int(rng.integers(1, 900))
+        kw = dict(P1=P1, P2=P1 + int(rng.integers(1, 2500)), disp12MaxDiff=int(rng.integers(1, 5)),
+                  preFilterCap=int(rng.integers(1, 64)), uniquenessRatio=int(rng.integers(0, 40)),
+                  speckleWindowSize=int(rng.choice([0, 10, 50, 100, 200])), speckleRange=int(rng.integers(1, 40)))
+        ref = cv2.StereoSGBM_create(minDisparity=0, numDisparities=96, blockSize=9, **kw).compute(left, right)
+        p = gpu_ctx.sgbm_params(P1=kw["P1"], P2=kw["P2"], disp12_max_diff=kw["disp12MaxDiff"], pre_filter_cap=kw["preFilterCap"],
+                                uniqueness_ratio=kw["uniquenessRatio"], speckle_window_size=kw["speckleWindowSize"],
+                                speckle_range=kw["speckleRange"])
+        assert np.array_equal(gpu_ctx.sgbm_compute(left, right, p), ref), (trial, h, w, kw)
