@@ -46,3 +46,22 @@ def test_no_cpu_fallback(pkg):
     with pytest.raises(pkg.VslamError) as e:
         pkg.Context()
     assert e.value.status == -4
+
+
+def test_product_path_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package (Python, CUDA, C++ host layer) may import, include or
+    execute it; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm may."""
+    pk = os.path.join(ROOT, "stereo-visual-slam_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pk):
+        if os.sep + "build" in dirpath or "__pycache__" in dirpath:
+            continue
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".inc")):
+                continue
+            txt = open(os.path.join(dirpath, f), errors="ignore").read()
+            for m in re.finditer(r"^\s*(from\s+oracle|import\s+oracle|#include\s+[\"<][^\">]*oracle)", txt, flags=re.M):
+                offenders.append((os.path.relpath(os.path.join(dirpath, f), ROOT), m.group(0).strip()))
+            if re.search(r"oracle/_build|oracle/_ref|libba_oracle", txt):
+                offenders.append((os.path.relpath(os.path.join(dirpath, f), ROOT), "links the oracle library"))
+    assert not offenders, offenders
