@@ -32,6 +32,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W, H, NFEAT = 1241, 376, 2000
+WORKLOAD = ("configs[1] batched: 1241x376 synthetic stereo pairs, 2000 ORB kp, "
+            "detect(L,R)+BF-Hamming cross-check match+DLT triangulate")
 METRIC = "stereo_frames_per_sec"
 UNIT = "stereo frames/s"
 
@@ -144,7 +146,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1]: 1241x376 synthetic stereo pairs, 2000 ORB kp, detect+match+triangulate",
+            "config": {"workload": WORKLOAD,
                        "pairs_per_step": sample},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": ncores, "kind": "port",
                              "sample": f"{sample} stereo pairs/step x {args.steps} steps; live cv2 {cv2.__version__} "
@@ -387,8 +389,7 @@ def run_ours(args, rank, world, local_rank):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1] batched: 1241x376 synthetic stereo pairs, 2000 ORB kp, "
-                                   "detect(L,R)+BF-Hamming cross-check match+DLT triangulate",
+            "config": {"workload": WORKLOAD,
                        "pairs_per_step_per_gpu": B, "nfeatures": NFEAT, "anms": "off (configs[1])",
                        "l2": "two alternating input sets + 256 MiB flush before the timed region; per-step working "
                              "set (inputs+pyramids+blurred) ~%.0f MB > 126 MB L2" % (2 * B * 3.7),
