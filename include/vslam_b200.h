@@ -247,15 +247,25 @@ int vslam_ba_optimize(vslam_ctx* ctx, int n_poses, double* poses, int n_points, 
  * VO::motion_estimation (visual_odometry.cpp:253-314, call at :277).  xyz: n x 3 float32 world points
  * (Landmark::pt_3d_), uv: n x 2 float32 pixels, Kmat row-major 3x3 (no distortion).  Outputs: rvec
  * (Rodrigues) and tvec as cv::solvePnPRansac returns them, optionally the same pose as a 3x4 [R|t]
- * (T_c_w, may be NULL), and the ascending inlier index list.  The pose is the Gauss-Newton optimum of
- * the reprojection error over the inliers of the best hypothesis (what OpenCV returns);
- * all `iters` hypotheses are scored (no confidence-based early exit), so on inputs with a clear
- * consensus the inlier set and pose equal cv2's.  n < 6 yields *n_inliers = 0.  `inliers` must hold n entries; the first
- * *n_inliers are the ascending inlier indices, the rest is unspecified.
+ * (T_c_w, may be NULL), and the ascending inlier index list.
+ * The RANSAC is OpenCV 4.13's, sample for sample: cv::RNG((uint64)-1) sample stream with duplicate rejection,
+ * 5-point EPnP minimal solver in OpenCV's exact fp64 arithmetic, float32 reprojection errors against
+ * (float)(reproj_err^2) without a cheirality test, "goodCount > max(best, 4)" update rule and the
+ * confidence-driven shrinking of the iteration budget (RANSACUpdateNumIters) -- so the inlier list equals
+ * cv2's index for index on any input.  The returned pose is the least-squares optimum of the reprojection
+ * error over those inliers (OpenCV: solvePnP(SOLVEPNP_ITERATIVE) on them; here Gauss-Newton to convergence).
+ *   n == 5      OpenCV skips RANSAC: EPnP pose of the five points, all five reported as inliers
+ *   n  < 5      *n_inliers = 0 (OpenCV asserts n >= 4 and uses P3P for n == 4; the reference rejects
+ *               every frame with fewer than 10 inliers, visual_odometry.cpp:316-346)
+ *   iters       <= 512 (VSLAM_E_CAPACITY above); 0 < confidence < 1 (VSLAM_E_INVALID otherwise)
+ * `inliers` must hold n entries; the first *n_inliers are the ascending inlier indices, the rest is unspecified.
  * ---------------------------------------------------------------------------------------------- */
 int vslam_pnp_ransac(vslam_ctx* ctx, const float* xyz, const float* uv, int n, const double* Kmat, int iters,
                      float reproj_err, double confidence, double* rvec, double* tvec, double* T_c_w,
                      int32_t* inliers, int32_t* n_inliers);
+/* test tap: the model (row-major R then t, 12 doubles) and the inlier count of RANSAC sample `it` of the last
+ * vslam_pnp_ransac call, and the number of iterations OpenCV's loop executes before its budget runs out */
+int vslam_pnp_debug_read(vslam_ctx* ctx, int it, double* R_t12, int32_t* count, int32_t* executed);
 
 /* K7 stand-alone: VO::adaptive_non_maximal_suppresion (visual_odometry.cpp:96-157) on caller keypoints.
  * keep_idx receives the indices (ascending, into `keypoints`) of the survivors: radius >= num-th largest

@@ -22,7 +22,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # -fmad=false: the bit-exact float stages (Harris, fastAtan2, rBRIEF rotation, blur tail) must not be
 # contracted; fused operations are written explicitly with fmaf()/fma() where the CPU path fuses.
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
-NO_FMAD = {"orb.cu"}  # everything else (fp64 BA, triangulation) may contract
+NO_FMAD = {"orb.cu", "pnp.cu"}  # (pnp.cu: OpenCV's EPnP in its exact fp64 arithmetic) everything else may contract
 
 
 def _newer(src: str, dst: str, extra=()) -> bool:

@@ -1,70 +1,53 @@
-// K12: PnP-RANSAC hypothesis scoring + inlier refit, and K7 as a stand-alone call (ANMS on caller keypoints).
+// K12: PnP-RANSAC (cv::solvePnPRansac, sample for sample) + inlier refit, and K7 as a stand-alone call (ANMS on caller
+// keypoints).
 //
 // Replaces cv::solvePnPRansac(pts3d, pts2d, K, noDist, rvec, tvec, false, 100, 4.0, 0.99, inliers) inside
 // VO::motion_estimation (/root/reference/src/stereo_visual_slam_main/visual_odometry.cpp:253-314, call at :277) and the
 // reference's own VO::adaptive_non_maximal_suppresion (visual_odometry.cpp:96-157).
 //
-// Parity definition (SURVEY.md §7 hard part 3, §A.4): OpenCV's result is the Gauss-Newton optimum of the reprojection
-// error over the inlier set selected by the best minimal hypothesis.  On inputs with a clear consensus every good
-// hypothesis selects the same set, so this implementation matches cv2 on (inlier indices, pose) without reproducing
-// OpenCV's RNG stream or its EPnP minimal solver:
-//   pnp_hypothesis_kernel  one CTA per hypothesis: thread 0 solves a 6-point DLT (12x12 one-sided Jacobi SVD, polar
-//                          orthogonalisation, 5 Gauss-Newton steps on the sample), all threads score the M points
-//   pnp_refine_kernel      one CTA: first best hypothesis (strictly-greater rule like RANSACPointSetRegistrator),
-//                          inlier mask at reprojection error <= 4 px, Gauss-Newton refit on the inliers (fp64, 6x6
-//                          normal equations by block reduction), Rodrigues vector, ascending inlier index list
+// Parity definition: the inlier list equals cv2 4.13.0's index for index on any input, because the whole RANSAC is
+// reproduced (restated and pinned against live cv2 in oracle/pnp_oracle.c):
+//   host                   the sample stream: cv::RNG((uint64)-1) multiply-with-carry, getSubset's duplicate rejection
+//                          (it depends only on n, so all `iters` samples are drawn up front)
+//   pnp_hypothesis_kernel  one CTA per sample: thread 0 runs OpenCV's 5-point EPnP in its exact arithmetic (epnp.cuh),
+//                          turns R into the (rvec, tvec) model and back as the RANSAC callback and projectPoints do;
+//                          all threads then count the inliers with projectPoints' float32 arithmetic
+//                          (err = |uv - (float)proj|^2 <= (float)(thr^2), no cheirality test)
+//   pnp_refine_kernel      one CTA: RANSACPointSetRegistrator::run's sequential logic over the counts (a model is
+//                          kept iff goodCount > max(best, 4); RANSACUpdateNumIters shrinks the iteration budget, later
+//                          samples are ignored exactly as if they had never been drawn), inlier mask of the winner,
+//                          then OpenCV's final solvePnP(ITERATIVE) on the inliers = the least-squares optimum of the
+//                          reprojection error, reached here by Gauss-Newton in fp64 from the RANSAC model
 #include "common.cuh"
+#include "epnp.cuh"
 
 #include <math.h>
 #include <stdlib.h>
 
 #define PNP_THREADS 256
+#define PNP_HYP_THREADS 128
 #define PNP_MAX_HYP 512
+#define PNP_HYP_STRIDE 16  // doubles per hypothesis record: R (9), t (3), pad
 
 struct PnpState {
-    float* d_xyz;
-    float* d_uv;
-    double* d_hyp;    // [H][12] pose [R|t]
+    float* d_in;      // [cap*3 xyz | cap*2 uv | PNP_MAX_HYP*5 sample indices]
+    double* d_hyp;    // [H][PNP_HYP_STRIDE]
     int* d_cnt;       // [H]
-    double* d_out;    // rvec(3) tvec(3) R|t (12)
-    int* d_inl;       // [cap + 1]: count, then indices
+    uint8_t* d_mask;  // [cap]
+    int* d_res;       // [PNP_RES_HEAD ints: count, best, executed iterations, pad | 18 doubles | cap inlier indices]
+    void* h_in;       // pinned mirrors
+    void* h_res;
     int cap;
     // ANMS staging
     vslam_keypoint* d_kp;
     double* d_rad;
     int* d_keep;
 };
+#define PNP_RES_HEAD 4
 
 struct PnpCam {
     double fx, fy, cx, cy;
 };
-
-__device__ __forceinline__ uint32_t pnp_rng(uint32_t& s) {
-    s ^= s << 13;
-    s ^= s >> 17;
-    s ^= s << 5;
-    return s;
-}
-
-// R <- nearest rotation (polar decomposition by Newton iteration R <- (R + R^-T)/2), det forced positive by the caller
-__device__ void orthonormalize3(double* R) {
-    for (int it = 0; it < 30; ++it) {
-        const double c0 = R[4] * R[8] - R[5] * R[7], c1 = R[5] * R[6] - R[3] * R[8], c2 = R[3] * R[7] - R[4] * R[6];
-        const double det = R[0] * c0 + R[1] * c1 + R[2] * c2;
-        const double id = 1.0 / det;
-        double T[9];  // inverse transpose = cofactor / det
-        T[0] = c0 * id; T[1] = c1 * id; T[2] = c2 * id;
-        T[3] = (R[2] * R[7] - R[1] * R[8]) * id; T[4] = (R[0] * R[8] - R[2] * R[6]) * id; T[5] = (R[1] * R[6] - R[0] * R[7]) * id;
-        T[6] = (R[1] * R[5] - R[2] * R[4]) * id; T[7] = (R[2] * R[3] - R[0] * R[5]) * id; T[8] = (R[0] * R[4] - R[1] * R[3]) * id;
-        double diff = 0;
-        for (int i = 0; i < 9; ++i) {
-            const double n = 0.5 * (R[i] + T[i]);
-            diff += fabs(n - R[i]);
-            R[i] = n;
-        }
-        if (diff < 1e-15) break;
-    }
-}
 
 // solve the 6x6 SPD system H x = g in place (Cholesky), returns false if not positive definite
 __device__ bool solve6(double* H, double* g) {
@@ -123,12 +106,11 @@ __device__ void pose_oplus(double* T, const double* xi) {
 
 // accumulate the Gauss-Newton normal equations of one correspondence into H (21 upper entries) and g (6)
 __device__ __forceinline__ void gn_accumulate(const double* T, const PnpCam& cam, float X, float Y, float Z, float u,
-                                              float v, double* H21, double* g, double& err2) {
+                                              float v, double* H21, double* g) {
     const double px = T[0] * X + T[1] * Y + T[2] * Z + T[3], py = T[4] * X + T[5] * Y + T[6] * Z + T[7],
                  pz = T[8] * X + T[9] * Y + T[10] * Z + T[11];
     const double iz = 1.0 / pz, iz2 = iz * iz;
     const double e0 = (double)u - (cam.fx * px * iz + cam.cx), e1 = (double)v - (cam.fy * py * iz + cam.cy);
-    err2 = e0 * e0 + e1 * e1;
     double J0[6], J1[6];  // d e / d xi for T <- exp(xi) T  (optimization.cpp:68-71)
     J0[0] = -cam.fx * iz; J0[1] = 0; J0[2] = cam.fx * px * iz2; J0[3] = cam.fx * px * py * iz2;
     J0[4] = -cam.fx - cam.fx * px * px * iz2; J0[5] = cam.fx * py * iz;
@@ -143,194 +125,116 @@ __device__ __forceinline__ void gn_accumulate(const double* T, const PnpCam& cam
     }
 }
 
-// 6-point DLT.  The 12x12 system's null vector is the eigenvector of the smallest eigenvalue of M = A^T A; it is found
-// by inverse iteration on a Cholesky factor of M + mu I (the gap between the noise-level smallest eigenvalue and the
-// next one makes a handful of iterations converge to machine precision), a few hundred flops instead of the thousands
-// of dependent rotations of a one-sided Jacobi SVD that used to make this kernel the longest stage of a VO frame.
-// The pose is then polished by Gauss-Newton on the sample itself, which removes what the normal equations lose.
-__device__ void dlt6_rows(const float* xyz, const float* uv, const int* idx, const PnpCam& cam, double* A /*[12][12]*/) {
-    for (int i = 0; i < 144; ++i) A[i] = 0;
-    for (int s = 0; s < 6; ++s) {
-        const int i = idx[s];
-        const double X = xyz[3 * i], Y = xyz[3 * i + 1], Z = xyz[3 * i + 2];
-        const double x = ((double)uv[2 * i] - cam.cx) / cam.fx, y = ((double)uv[2 * i + 1] - cam.cy) / cam.fy;  // normalised
-        double* r0 = A + 12 * (2 * s);
-        double* r1 = A + 12 * (2 * s + 1);
-        r0[0] = X; r0[1] = Y; r0[2] = Z; r0[3] = 1; r0[8] = -x * X; r0[9] = -x * Y; r0[10] = -x * Z; r0[11] = -x;
-        r1[4] = X; r1[5] = Y; r1[6] = Z; r1[7] = 1; r1[8] = -y * X; r1[9] = -y * Y; r1[10] = -y * Z; r1[11] = -y;
-    }
+// PnPRansacCallback::computeError for one correspondence: cv::projectPoints in double, stored as float32, squared
+// float32 distance to the measured pixel.  R row-major, no distortion.
+__device__ __forceinline__ float pnp_reproj_err(const double* R, const double* t, const PnpCam& cam, const float* xyz,
+                                                const float* uv, int i) {
+    const double X = xyz[3 * i], Y = xyz[3 * i + 1], Z = xyz[3 * i + 2];
+    double x = R[0] * X + R[1] * Y + R[2] * Z + t[0];
+    double y = R[3] * X + R[4] * Y + R[5] * Z + t[1];
+    double z = R[6] * X + R[7] * Y + R[8] * Z + t[2];
+    z = z ? 1. / z : 1;
+    x *= z;
+    y *= z;
+    const float pu = (float)(x * cam.fx + cam.cx), pv = (float)(y * cam.fy + cam.cy);
+    const float dx = uv[2 * i] - pu, dy = uv[2 * i + 1] - pv;
+    return dx * dx + dy * dy;
 }
 
-// M (12x12 symmetric, row-major, overwritten by its Cholesky factor) -> unit eigenvector of the smallest eigenvalue
-__device__ bool smallest_eigvec12(double* M, double* x) {
-    double tr = 0;
-    for (int i = 0; i < 12; ++i) tr += M[i * 13];
-    if (!(tr > 0) || !isfinite(tr)) return false;
-    const double mu = 1e-13 * tr;
-    for (int j = 0; j < 12; ++j) {  // lower Cholesky, in place
-        double d = M[j * 13] + mu;
-        for (int k = 0; k < j; ++k) d -= M[j * 12 + k] * M[j * 12 + k];
-        if (!(d > 0)) d = mu;  // rank-deficient sample: keep going, the hypothesis will score badly
-        const double l = sqrt(d), il = 1.0 / l;
-        M[j * 13] = l;
-        for (int i = j + 1; i < 12; ++i) {
-            double v = M[i * 12 + j];
-            for (int k = 0; k < j; ++k) v -= M[i * 12 + k] * M[j * 12 + k];
-            M[i * 12 + j] = v * il;
-        }
-    }
-    for (int i = 0; i < 12; ++i) x[i] = 0.28867513459481287 * ((i & 1) ? 1.0 : 0.9) * ((i % 3) ? 1.0 : 1.1);  // generic start
-    for (int it = 0; it < 6; ++it) {
-        for (int i = 0; i < 12; ++i) {  // L y = x
-            double v = x[i];
-            for (int k = 0; k < i; ++k) v -= M[i * 12 + k] * x[k];
-            x[i] = v / M[i * 13];
-        }
-        for (int i = 11; i >= 0; --i) {  // L^T z = y
-            double v = x[i];
-            for (int k = i + 1; k < 12; ++k) v -= M[k * 12 + i] * x[k];
-            x[i] = v / M[i * 13];
-        }
-        double nn = 0;
-        for (int i = 0; i < 12; ++i) nn += x[i] * x[i];
-        if (!(nn > 0) || !isfinite(nn)) return false;
-        const double inv = 1.0 / sqrt(nn);
-        for (int i = 0; i < 12; ++i) x[i] *= inv;
-    }
-    return true;
-}
-
-// pose from the DLT null vector P = s [R | t], then Gauss-Newton on the six correspondences
-__device__ bool dlt6_pose(const float* xyz, const float* uv, const int* idx, const PnpCam& cam, const double* Pv, double* T) {
-    double P[12];
-    for (int k = 0; k < 12; ++k) P[k] = Pv[k];
-    // P = s [R | t]: fix the sign with det(R) > 0, the scale with the mean row norm
-    double R[9] = {P[0], P[1], P[2], P[4], P[5], P[6], P[8], P[9], P[10]};
-    const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
-    if (!(fabs(det) > 1e-300)) return false;
-    const double sc = cbrt(det);
-    for (int i = 0; i < 9; ++i) R[i] /= sc;
-    orthonormalize3(R);
-    T[0] = R[0]; T[1] = R[1]; T[2] = R[2]; T[3] = P[3] / sc;
-    T[4] = R[3]; T[5] = R[4]; T[6] = R[5]; T[7] = P[7] / sc;
-    T[8] = R[6]; T[9] = R[7]; T[10] = R[8]; T[11] = P[11] / sc;
-    for (int i = 0; i < 12; ++i)
-        if (!isfinite(T[i])) return false;
-    // a few Gauss-Newton steps on the sample itself
-    for (int it = 0; it < 5; ++it) {
-        double H21[21], g[6], H[36], e2;
-        for (int i = 0; i < 21; ++i) H21[i] = 0;
-        for (int i = 0; i < 6; ++i) g[i] = 0;
-        for (int s = 0; s < 6; ++s) {
-            const int i = idx[s];
-            gn_accumulate(T, cam, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], uv[2 * i], uv[2 * i + 1], H21, g, e2);
-        }
-        int q = 0;
-        for (int a = 0; a < 6; ++a)
-            for (int b = a; b < 6; ++b) { H[a * 6 + b] = H21[q]; H[b * 6 + a] = H21[q]; ++q; }
-        for (int a = 0; a < 6; ++a) H[a * 6 + a] += 1e-9;
-        if (!solve6(H, g)) return false;
-        pose_oplus(T, g);
-    }
-    return true;
-}
-
-__global__ void __launch_bounds__(PNP_THREADS)
+__global__ void __launch_bounds__(PNP_HYP_THREADS)
 pnp_hypothesis_kernel(const float* __restrict__ xyz, const float* __restrict__ uv, int n, PnpCam cam, float thr2,
-                      uint32_t seed, double* __restrict__ hyp, int* __restrict__ cnt) {
-    __shared__ double sT[12], sA[144], sM[144];
-    __shared__ int s_ok, s_cnt, s_idx[6];
+                      const int* __restrict__ samples, double* __restrict__ hyp, int* __restrict__ cnt) {
+    __shared__ EpnpWork work;
+    __shared__ double sR[9], st[3];
+    __shared__ int s_cnt;
     const int h = blockIdx.x;
     if (threadIdx.x == 0) {
-        uint32_t s = seed * 2654435761u + (uint32_t)h * 40503u + 12345u;
-        pnp_rng(s);
-        int idx[6];
-        for (int k = 0; k < 6; ++k) {  // 6 distinct indices
-            for (;;) {
-                const int c = (int)(pnp_rng(s) % (uint32_t)n);
-                bool dup = false;
-                for (int q = 0; q < k; ++q) dup |= idx[q] == c;
-                if (!dup) { idx[k] = c; break; }
-            }
-        }
-        for (int k = 0; k < 6; ++k) s_idx[k] = idx[k];
-        dlt6_rows(xyz, uv, idx, cam, sA);
+        int idx[5];
+        for (int k = 0; k < 5; ++k) idx[k] = samples[5 * h + k];
+        double R[9], t[3], rv[3];
+        epnp5_dev(work, xyz, uv, idx, cam.fx, cam.fy, cam.cx, cam.cy, R, t);
+        rodrigues_to_vec_dev(R, rv);  // the model RANSAC carries is (rvec, tvec) ...
+        rodrigues_to_mat_dev(rv, R);  // ... and projectPoints turns it back into a matrix
+        for (int k = 0; k < 9; ++k) sR[k] = R[k];
+        for (int k = 0; k < 3; ++k) st[k] = t[k];
         s_cnt = 0;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < 144; e += PNP_THREADS) {  // M = A^T A, one entry per thread
-        const int r = e / 12, c = e - r * 12;
-        double v = 0;
-#pragma unroll
-        for (int k = 0; k < 12; ++k) v += sA[k * 12 + r] * sA[k * 12 + c];
-        sM[e] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int idx[6];
-        for (int k = 0; k < 6; ++k) idx[k] = s_idx[k];
-        double x[12], T[12];
-        bool ok = smallest_eigvec12(sM, x);
-        if (ok) ok = dlt6_pose(xyz, uv, idx, cam, x, T);
-        s_ok = ok ? 1 : 0;
-        for (int i = 0; i < 12; ++i) sT[i] = ok ? T[i] : 0.0;
-    }
-    __syncthreads();
     int c = 0;
-    if (s_ok) {
-        for (int i = threadIdx.x; i < n; i += PNP_THREADS) {
-            const double X = xyz[3 * i], Y = xyz[3 * i + 1], Z = xyz[3 * i + 2];
-            const double pz = sT[8] * X + sT[9] * Y + sT[10] * Z + sT[11];
-            const double px = sT[0] * X + sT[1] * Y + sT[2] * Z + sT[3], py = sT[4] * X + sT[5] * Y + sT[6] * Z + sT[7];
-            const double e0 = (double)uv[2 * i] - (cam.fx * px / pz + cam.cx), e1 = (double)uv[2 * i + 1] - (cam.fy * py / pz + cam.cy);
-            c += (pz > 0 && e0 * e0 + e1 * e1 <= (double)thr2) ? 1 : 0;
-        }
-    }
+    for (int i = threadIdx.x; i < n; i += PNP_HYP_THREADS) c += pnp_reproj_err(sR, st, cam, xyz, uv, i) <= thr2 ? 1 : 0;
     c = __reduce_add_sync(0xFFFFFFFFu, c);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
     __syncthreads();
     if (threadIdx.x == 0) {
-        cnt[h] = s_ok ? s_cnt : -1;
-        for (int i = 0; i < 12; ++i) hyp[12 * h + i] = sT[i];
+        cnt[h] = s_cnt;
+        for (int k = 0; k < 9; ++k) hyp[PNP_HYP_STRIDE * h + k] = sR[k];
+        for (int k = 0; k < 3; ++k) hyp[PNP_HYP_STRIDE * h + 9 + k] = st[k];
     }
 }
 
+// cv::RANSACUpdateNumIters
+__device__ int ransac_update_num_iters(double p, double ep, int model_points, int max_iters) {
+    p = fmin(fmax(p, 0.), 1.);
+    ep = fmin(fmax(ep, 0.), 1.);
+    double num = fmax(1. - p, DBL_MIN);
+    double denom = 1. - pow(1. - ep, (double)model_points);
+    if (denom < DBL_MIN) return 0;
+    num = log(num);
+    denom = log(denom);
+    return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : __double2int_rn(num / denom);
+}
+
+// direct != 0: n == 5, OpenCV skips RANSAC and returns the EPnP pose of the five points with all of them as inliers
 __global__ void __launch_bounds__(PNP_THREADS)
 pnp_refine_kernel(const float* __restrict__ xyz, const float* __restrict__ uv, int n, PnpCam cam, float thr2, int n_hyp,
-                  const double* __restrict__ hyp, const int* __restrict__ cnt, int max_iter, double* __restrict__ out,
-                  int* __restrict__ inl) {
-    __shared__ double sT[12];
+                  double confidence, int direct, const double* __restrict__ hyp, const int* __restrict__ cnt, int max_iter,
+                  uint8_t* __restrict__ mask, int* __restrict__ res) {
+    __shared__ double sT[12], sR[9], st[3];
     __shared__ double sH[PNP_THREADS / 32][28];
     __shared__ int s_best, s_stop, s_base, s_warp[PNP_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* out = reinterpret_cast<double*>(res + PNP_RES_HEAD);
+    int* inl = res + PNP_RES_HEAD + 36;
     if (tid == 0) {
-        int best = -1, bc = 4;  // RANSACPointSetRegistrator: goodCount > max(maxGoodCount, modelPoints - 1)
-        for (int h = 0; h < n_hyp; ++h)
-            if (cnt[h] > bc) { bc = cnt[h]; best = h; }
+        int best = -1, executed = 0;
+        if (direct) {
+            best = 0;
+            executed = 1;
+        } else {  // RANSACPointSetRegistrator::run over the precomputed samples
+            int niters = n_hyp > 1 ? n_hyp : 1, max_good = 0;
+            for (int it = 0; it < niters && it < n_hyp; ++it) {
+                const int good = cnt[it];
+                if (good > (max_good > 4 ? max_good : 4)) {
+                    best = it;
+                    max_good = good;
+                    niters = ransac_update_num_iters(confidence, (double)(n - good) / n, 5, niters);
+                }
+                executed = it + 1;
+            }
+        }
         s_best = best;
-        if (best >= 0)
-            for (int i = 0; i < 12; ++i) sT[i] = hyp[12 * best + i];
+        if (best >= 0) {
+            for (int i = 0; i < 9; ++i) sR[i] = hyp[PNP_HYP_STRIDE * best + i];
+            for (int i = 0; i < 3; ++i) st[i] = hyp[PNP_HYP_STRIDE * best + 9 + i];
+            for (int r = 0; r < 3; ++r) {
+                sT[r * 4] = sR[r * 3]; sT[r * 4 + 1] = sR[r * 3 + 1]; sT[r * 4 + 2] = sR[r * 3 + 2]; sT[r * 4 + 3] = st[r];
+            }
+        }
+        res[1] = best;
+        res[2] = executed;
         s_stop = 0;
         s_base = 0;
     }
     __syncthreads();
     if (s_best < 0) {
-        if (tid == 0) inl[0] = 0;
+        if (tid == 0) res[0] = 0;
         return;
     }
-    // inlier mask of the winning hypothesis (kept as flags in registers, recomputed per pass: n is small)
-    const double T0[12] = {sT[0], sT[1], sT[2], sT[3], sT[4], sT[5], sT[6], sT[7], sT[8], sT[9], sT[10], sT[11]};
-    auto is_inlier = [&](int i) {
-        const double X = xyz[3 * i], Y = xyz[3 * i + 1], Z = xyz[3 * i + 2];
-        const double pz = T0[8] * X + T0[9] * Y + T0[10] * Z + T0[11];
-        const double px = T0[0] * X + T0[1] * Y + T0[2] * Z + T0[3], py = T0[4] * X + T0[5] * Y + T0[6] * Z + T0[7];
-        const double e0 = (double)uv[2 * i] - (cam.fx * px / pz + cam.cx), e1 = (double)uv[2 * i + 1] - (cam.fy * py / pz + cam.cy);
-        return pz > 0 && e0 * e0 + e1 * e1 <= (double)thr2;
-    };
-    // ascending inlier index list
+    // inlier mask of the winning model + ascending index list
     for (int i0 = 0; i0 < n; i0 += PNP_THREADS) {
         const int i = i0 + tid;
-        const bool k = i < n && is_inlier(i);
+        const bool k = i < n && (direct || pnp_reproj_err(sR, st, cam, xyz, uv, i) <= thr2);
+        if (i < n) mask[i] = k ? 1 : 0;
         const uint32_t bal = __ballot_sync(0xFFFFFFFFu, k);
         if (lane == 0) s_warp[warp] = __popc(bal);
         __syncthreads();
@@ -339,13 +243,13 @@ pnp_refine_kernel(const float* __restrict__ xyz, const float* __restrict__ uv, i
             before += w < warp ? s_warp[w] : 0;
             total += s_warp[w];
         }
-        if (k) inl[1 + s_base + before + __popc(bal & ((1u << lane) - 1))] = i;
+        if (k) inl[s_base + before + __popc(bal & ((1u << lane) - 1))] = i;
         __syncthreads();
         if (tid == 0) s_base += total;
         __syncthreads();
     }
-    // Gauss-Newton refit on the inliers
-    for (int it = 0; it < max_iter; ++it) {
+    // refit on the inliers (skipped when OpenCV returns the EPnP pose itself)
+    for (int it = 0; it < max_iter && !direct; ++it) {
         double H21[21], g[6];
 #pragma unroll
         for (int i = 0; i < 21; ++i) H21[i] = 0;
@@ -355,9 +259,8 @@ pnp_refine_kernel(const float* __restrict__ xyz, const float* __restrict__ uv, i
 #pragma unroll
         for (int i = 0; i < 12; ++i) T[i] = sT[i];
         for (int i = tid; i < n; i += PNP_THREADS) {
-            if (!is_inlier(i)) continue;
-            double e2;
-            gn_accumulate(T, cam, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], uv[2 * i], uv[2 * i + 1], H21, g, e2);
+            if (!mask[i]) continue;
+            gn_accumulate(T, cam, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], uv[2 * i], uv[2 * i + 1], H21, g);
         }
 #pragma unroll
         for (int i = 0; i < 21; ++i) {
@@ -400,20 +303,10 @@ pnp_refine_kernel(const float* __restrict__ xyz, const float* __restrict__ uv, i
         if (s_stop) break;
     }
     if (tid == 0) {
-        inl[0] = s_base;
-        // Rodrigues vector of R (cv::Rodrigues inverse)
-        const double* R = sT;
-        const double tr = R[0] + R[5] + R[10];
-        const double c = fmin(1.0, fmax(-1.0, 0.5 * (tr - 1.0)));
-        const double th = acos(c);
-        double w[3] = {R[9] - R[6], R[2] - R[8], R[4] - R[1]};
-        double f = th < 1e-10 ? 0.5 : th / (2.0 * sin(th));
-        if (M_PI - th < 1e-6) {
-            double ax[3] = {sqrt(fmax(0.0, (R[0] - c) / (1 - c))), sqrt(fmax(0.0, (R[5] - c) / (1 - c))), sqrt(fmax(0.0, (R[10] - c) / (1 - c)))};
-            for (int i = 0; i < 3; ++i) w[i] = (w[i] < 0 ? -ax[i] : ax[i]) * th;
-            f = 1.0;
-        }
-        out[0] = w[0] * f; out[1] = w[1] * f; out[2] = w[2] * f;
+        res[0] = s_base;
+        double R[9] = {sT[0], sT[1], sT[2], sT[4], sT[5], sT[6], sT[8], sT[9], sT[10]}, rv[3];
+        rodrigues_to_vec_dev(R, rv);
+        out[0] = rv[0]; out[1] = rv[1]; out[2] = rv[2];
         out[3] = sT[3]; out[4] = sT[7]; out[5] = sT[11];
         for (int i = 0; i < 12; ++i) out[6 + i] = sT[i];
     }
@@ -481,18 +374,22 @@ anms_points_kernel(const vslam_keypoint* __restrict__ kp, int n, int num, float 
 // ----------------------------------------------------------------------------------------------------------------
 static PnpState* pnp_state(vslam_ctx* ctx) { return ctx->pnp; }
 
+static size_t pnp_in_bytes(int cap) { return (size_t)cap * 20 + PNP_MAX_HYP * 5 * sizeof(int); }
+static size_t pnp_res_bytes(int cap) { return (PNP_RES_HEAD + 36 + (size_t)cap) * sizeof(int); }
+
 int vslam_pnp_init(vslam_ctx* ctx) {
     PnpState* p = (PnpState*)calloc(1, sizeof(PnpState));
     if (!p) return VSLAM_E_INVALID;
     ctx->pnp = p;
     p->cap = ctx->cfg.max_keypoints > 0 ? ctx->cfg.max_keypoints : 1;
     const size_t cap = (size_t)p->cap;
-    VSLAM_CUDA(ctx, cudaMalloc(&p->d_xyz, cap * 12));
-    VSLAM_CUDA(ctx, cudaMalloc(&p->d_uv, cap * 8));
-    VSLAM_CUDA(ctx, cudaMalloc(&p->d_hyp, PNP_MAX_HYP * 12 * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&p->d_in, pnp_in_bytes(p->cap)));
+    VSLAM_CUDA(ctx, cudaMalloc(&p->d_hyp, PNP_MAX_HYP * PNP_HYP_STRIDE * sizeof(double)));
     VSLAM_CUDA(ctx, cudaMalloc(&p->d_cnt, PNP_MAX_HYP * sizeof(int)));
-    VSLAM_CUDA(ctx, cudaMalloc(&p->d_out, 18 * sizeof(double)));
-    VSLAM_CUDA(ctx, cudaMalloc(&p->d_inl, (cap + 1) * sizeof(int)));
+    VSLAM_CUDA(ctx, cudaMalloc(&p->d_mask, cap));
+    VSLAM_CUDA(ctx, cudaMalloc(&p->d_res, pnp_res_bytes(p->cap)));
+    VSLAM_CUDA(ctx, cudaMallocHost(&p->h_in, pnp_in_bytes(p->cap)));
+    VSLAM_CUDA(ctx, cudaMallocHost(&p->h_res, pnp_res_bytes(p->cap)));
     VSLAM_CUDA(ctx, cudaMalloc(&p->d_kp, cap * sizeof(vslam_keypoint)));
     VSLAM_CUDA(ctx, cudaMalloc(&p->d_rad, cap * sizeof(double)));
     VSLAM_CUDA(ctx, cudaMalloc(&p->d_keep, (cap + 1) * sizeof(int)));
@@ -503,54 +400,101 @@ int vslam_pnp_init(vslam_ctx* ctx) {
 void vslam_pnp_free(vslam_ctx* ctx) {
     PnpState* p = ctx->pnp;
     if (!p) return;
-    cudaFree(p->d_xyz); cudaFree(p->d_uv); cudaFree(p->d_hyp); cudaFree(p->d_cnt); cudaFree(p->d_out);
-    cudaFree(p->d_inl); cudaFree(p->d_kp); cudaFree(p->d_rad); cudaFree(p->d_keep);
+    cudaFree(p->d_in); cudaFree(p->d_hyp); cudaFree(p->d_cnt); cudaFree(p->d_mask); cudaFree(p->d_res);
+    cudaFreeHost(p->h_in); cudaFreeHost(p->h_res);
+    cudaFree(p->d_kp); cudaFree(p->d_rad); cudaFree(p->d_keep);
     free(p);
     ctx->pnp = nullptr;
+}
+
+// cv::RNG as RANSACPointSetRegistrator::run seeds it, and getSubset's draw of 5 distinct indices per iteration.  The
+// stream does not depend on the data, so every sample the loop could reach is drawn before the kernels start.
+static void pnp_draw_samples(int n, int iters, int* out) {
+    uint64_t state = (uint64_t)-1;
+    for (int it = 0; it < iters; ++it) {
+        int* idx = out + 5 * it;
+        for (int i = 0; i < 5; ++i) {
+            for (;;) {
+                state = (uint64_t)(uint32_t)state * 4164903690ull + (uint32_t)(state >> 32);
+                const int c = (int)((uint32_t)state % (uint32_t)n);
+                bool dup = false;
+                for (int q = 0; q < i; ++q) dup |= idx[q] == c;
+                if (!dup) { idx[i] = c; break; }
+            }
+        }
+    }
 }
 
 extern "C" int vslam_pnp_ransac(vslam_ctx* ctx, const float* xyz, const float* uv, int n, const double* Kmat, int iters,
                                 float reproj_err, double confidence, double* rvec, double* tvec, double* T_c_w,
                                 int32_t* inliers, int32_t* n_inliers) {
-    (void)confidence;  // all `iters` hypotheses are evaluated (no early exit): see the header comment
     if (!ctx || !n_inliers || !Kmat || n < 0) return VSLAM_E_INVALID;
     *n_inliers = 0;
-    if (n < 6) return VSLAM_OK;  // not enough correspondences for a hypothesis: no inliers, pose untouched
+    // OpenCV asserts n >= 4 and switches to a P3P kernel for exactly 4 points; the reference rejects any frame with
+    // fewer than 10 inliers (visual_odometry.cpp:316-346), so both cases end as "no inliers" here
+    if (n < 5) return VSLAM_OK;
     if (!xyz || !uv || !rvec || !tvec || !inliers) return VSLAM_E_INVALID;
+    if (!(confidence > 0 && confidence < 1)) return VSLAM_E_INVALID;  // CV_Assert in RANSACPointSetRegistrator::run
     PnpState* p = pnp_state(ctx);
     if (!p) return VSLAM_E_CAPACITY;
     if (n > p->cap) return VSLAM_E_CAPACITY;
-    if (iters <= 0) iters = 100;
-    if (iters > PNP_MAX_HYP) iters = PNP_MAX_HYP;
+    if (iters <= 0) iters = 1;  // niters = MAX(maxIters, 1)
+    if (iters > PNP_MAX_HYP) return VSLAM_E_CAPACITY;
+    const int direct = n == 5;
+    const int n_hyp = direct ? 1 : iters;
     PnpCam cam = {Kmat[0], Kmat[4], Kmat[2], Kmat[5]};
-    const float thr2 = reproj_err * reproj_err;
+    const float thr2 = (float)((double)reproj_err * (double)reproj_err);
     cudaStream_t s = ctx->stream;
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(p->d_xyz, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(p->d_uv, uv, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    // one upload: [xyz | uv | samples]
+    float* h_in = (float*)p->h_in;
+    memcpy(h_in, xyz, (size_t)n * 12);
+    memcpy(h_in + (size_t)n * 3, uv, (size_t)n * 8);
+    int* h_samples = (int*)(h_in + (size_t)n * 5);
+    if (direct)
+        for (int i = 0; i < 5; ++i) h_samples[i] = i;
+    else
+        pnp_draw_samples(n, n_hyp, h_samples);
+    const size_t in_bytes = (size_t)n * 20 + (size_t)n_hyp * 5 * sizeof(int);
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(p->d_in, h_in, in_bytes, cudaMemcpyHostToDevice, s));
+    const float* d_xyz = p->d_in;
+    const float* d_uv = p->d_in + (size_t)n * 3;
+    const int* d_samples = (const int*)(p->d_in + (size_t)n * 5);
     vslam_time_begin(ctx, VK_PNP);
-    pnp_hypothesis_kernel<<<iters, PNP_THREADS, 0, s>>>(p->d_xyz, p->d_uv, n, cam, thr2, 0x9E3779B9u, p->d_hyp, p->d_cnt);
+    pnp_hypothesis_kernel<<<n_hyp, PNP_HYP_THREADS, 0, s>>>(d_xyz, d_uv, n, cam, thr2, d_samples, p->d_hyp, p->d_cnt);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "pnp_hypothesis_kernel");
     vslam_time_begin(ctx, VK_PNP_REFINE);
-    pnp_refine_kernel<<<1, PNP_THREADS, 0, s>>>(p->d_xyz, p->d_uv, n, cam, thr2, iters, p->d_hyp, p->d_cnt, 30, p->d_out,
-                                                p->d_inl);
+    pnp_refine_kernel<<<1, PNP_THREADS, 0, s>>>(d_xyz, d_uv, n, cam, thr2, n_hyp, confidence, direct, p->d_hyp, p->d_cnt, 30,
+                                                p->d_mask, p->d_res);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "pnp_refine_kernel");
-    double out[18];
-    int cnt = 0;
-    // one round trip: count, pose and the whole index buffer (entries past the count are unspecified, as documented)
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(&cnt, p->d_inl, sizeof(int), cudaMemcpyDeviceToHost, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(out, p->d_out, sizeof(out), cudaMemcpyDeviceToHost, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(inliers, p->d_inl + 1, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    // one download: count, pose and the index list (entries past the count are unspecified, as documented)
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(p->h_res, p->d_res, pnp_res_bytes(n), cudaMemcpyDeviceToHost, s));
     VSLAM_CUDA(ctx, cudaStreamSynchronize(s));
+    const int* h_res = (const int*)p->h_res;
+    const int cnt = h_res[0];
     *n_inliers = cnt;
     if (cnt <= 0) return VSLAM_OK;
+    const double* out = (const double*)(h_res + PNP_RES_HEAD);
+    memcpy(inliers, h_res + PNP_RES_HEAD + 36, (size_t)cnt * sizeof(int));
     for (int i = 0; i < 3; ++i) {
         rvec[i] = out[i];
         tvec[i] = out[3 + i];
     }
     if (T_c_w)
         for (int i = 0; i < 12; ++i) T_c_w[i] = out[6 + i];
+    return VSLAM_OK;
+}
+
+/* test tap: model (R row-major 9, t 3) and inlier count of RANSAC sample `it` of the last vslam_pnp_ransac call, and
+ * the number of iterations OpenCV's loop would have executed */
+extern "C" int vslam_pnp_debug_read(vslam_ctx* ctx, int it, double* R_t12, int32_t* count, int32_t* executed) {
+    if (!ctx || !ctx->pnp || it < 0 || it >= PNP_MAX_HYP) return VSLAM_E_INVALID;
+    PnpState* p = ctx->pnp;
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (R_t12) VSLAM_CUDA(ctx, cudaMemcpy(R_t12, p->d_hyp + (size_t)PNP_HYP_STRIDE * it, 12 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (count) VSLAM_CUDA(ctx, cudaMemcpy(count, p->d_cnt + it, sizeof(int), cudaMemcpyDeviceToHost));
+    if (executed) *executed = ((const int*)p->h_res)[2];
     return VSLAM_OK;
 }
 

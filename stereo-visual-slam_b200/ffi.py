@@ -89,6 +89,7 @@ SIGNATURES = {
     "vslam_ba_optimize": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, C.POINTER(BaOptions),
                                C.POINTER(BaResult), _vp, _vp]),
     "vslam_pnp_ransac": (_i, [_vp, _vp, _vp, _i, _vp, _i, _f, _d, _vp, _vp, _vp, _vp, _pi]),
+    "vslam_pnp_debug_read": (_i, [_vp, _i, _vp, _pi, _pi]),
     "vslam_anms": (_i, [_vp, _vp, _i, _i, _f, _vp, _pi]),
     "vslam_ba_last_phase_ns": (_i, [_vp, _vp]),
     "vslam_ba_reduce_sizes": (_i, [_i, _pi, _pi, _pi]),
@@ -351,6 +352,18 @@ class Context:
                                        float(confidence), _ptr(rvec), _ptr(tvec), _ptr(T), _ptr(inl), C.byref(n))
         self.check(st, "vslam_pnp_ransac")
         return dict(rvec=rvec, tvec=tvec, T_c_w=T.reshape(3, 4), inliers=inl[:n.value].copy())
+
+    def pnp_debug(self, n_samples):
+        """Test tap: per-sample models [n_samples, 12] (R row-major, t), inlier counts and the executed iterations of
+        the last pnp_ransac call."""
+        models = np.zeros((n_samples, 12))
+        counts = np.zeros(n_samples, dtype=np.int32)
+        ex = C.c_int(0)
+        for i in range(n_samples):
+            c = C.c_int(0)
+            self.check(self.lib.vslam_pnp_debug_read(self.h, i, _ptr(models[i]), C.byref(c), C.byref(ex)), "vslam_pnp_debug_read")
+            counts[i] = c.value
+        return models, counts, ex.value
 
     def anms(self, keypoints, num=500, c_robust=1.11):
         kp = np.ascontiguousarray(keypoints, dtype=KEYPOINT_DTYPE)
