@@ -105,8 +105,8 @@ def make_batch(pkg, n_pairs: int, seed0: int):
     return L, R
 
 
-def cv2_frontend(cv2, V, left, right, P1, P2, nfeat=NFEAT):
-    """The reference CPU path for one stereo pair (oracle wrappers over the OpenCV calls the reference makes)."""
+def cv2_frontend(cv2, left, right, P1, P2, nfeat=NFEAT):
+    """The reference CPU path for one stereo pair: the OpenCV calls the reference's VO path makes, live cv2."""
     orb = cv2.ORB_create(nfeat)
     kl, dl = orb.detectAndCompute(left, None)
     kr, dr = orb.detectAndCompute(right, None)
@@ -128,19 +128,18 @@ def run_reference(args, rank, world):
     import cv2
     import vslam_b200_loader
     pkg = vslam_b200_loader.pkg
-    from oracle import vo_restate as V
     ncores = os.cpu_count() or 1
     cv2.setNumThreads(ncores)
     s = pkg.synth
-    P1, P2 = V.stereo_projection_matrices(s.FX, s.FY, s.CX, s.CY, s.BASELINE_M)
+    P1, P2 = s.stereo_projection_matrices()
     sample = 4  # stereo pairs per step: a bounded sample of the batch workload
     L, R = make_batch(pkg, sample, 0)
     for _ in range(max(args.warmup, 1)):
-        cv2_frontend(cv2, V, L[0], R[0], P1, P2)
+        cv2_frontend(cv2, L[0], R[0], P1, P2)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for i in range(sample):
-            cv2_frontend(cv2, V, L[i], R[i], P1, P2)
+            cv2_frontend(cv2, L[i], R[i], P1, P2)
     dt = time.perf_counter() - t0
     fps = args.steps * sample / dt
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -190,7 +189,6 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import vslam_b200_loader
     pkg = vslam_b200_loader.pkg
-    from oracle import vo_restate as V  # only for P1/P2 construction helpers and the cpu_baseline leg
 
     dist = None
     if world > 1:
@@ -205,7 +203,7 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.Stream(device=dev)
     ctx.set_stream(stream.cuda_stream)
     s = pkg.synth
-    P1, P2 = V.stereo_projection_matrices(s.FX, s.FY, s.CX, s.CY, s.BASELINE_M)
+    P1, P2 = s.stereo_projection_matrices()
 
     # two alternating input sets (2 x 2B x 466 KB > L2 for B >= 64), pinned on the host for the e2e leg
     sets = []
@@ -359,10 +357,10 @@ def run_ours(args, rank, world, local_rank):
     ncores = os.cpu_count() or 1
     cv2.setNumThreads(ncores)
     Ls, Rs = sets[0][0].numpy(), sets[0][1].numpy()
-    cv2_frontend(cv2, V, Ls[0], Rs[0], P1, P2)
+    cv2_frontend(cv2, Ls[0], Rs[0], P1, P2)
     n_cpu, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < args.cpu_seconds and n_cpu < B:
-        cv2_frontend(cv2, V, Ls[n_cpu], Rs[n_cpu], P1, P2)
+        cv2_frontend(cv2, Ls[n_cpu], Rs[n_cpu], P1, P2)
         n_cpu += 1
     cpu_fps = n_cpu / (time.perf_counter() - t0)
     # the same path on one thread and stage by stage: median of 5 on pair 0
@@ -382,7 +380,7 @@ def run_ours(args, rank, world, local_rank):
               "orb_compute_ms": _med(lambda: orb.compute(Ls[0], kl0)),
               "bf_match_ms": _med(lambda: bf.match(dl0, dr0))}
     cv2.setNumThreads(1)
-    stages_1t = {"threads": 1, "frontend_pair_ms": _med(lambda: cv2_frontend(cv2, V, Ls[0], Rs[0], P1, P2), 3),
+    stages_1t = {"threads": 1, "frontend_pair_ms": _med(lambda: cv2_frontend(cv2, Ls[0], Rs[0], P1, P2), 3),
                  "bf_match_ms": _med(lambda: bf.match(dl0, dr0), 3)}
     cv2.setNumThreads(ncores)
 
@@ -429,7 +427,7 @@ def bench_vo_loop(pkg):
     """The reference's own published number: wall-clock per keyframe / per non-keyframe of the sequential VO loop
     (README.md:90: ~0.18 s and ~0.04 s on an unstated CPU, KITTI 00).  Here: the C++ drop-in layer's run_vslam on a
     24-frame synthetic 1241x376 stereo sequence at the reference's operating point -- ORB(3000) + ANMS(500), dense
-    StereoSGBM depth (--dense), and per keyframe with a full window optimize_map x3 (5+5+10 LM iterations) +
+    StereoSGBM depth (the default), and per keyframe with a full window optimize_map x3 (5+5+10 LM iterations) +
     optimize_pose_only (10).  A second run with fewer features makes every frame a keyframe so that the BA part is timed."""
     import subprocess
     import tempfile
@@ -446,10 +444,10 @@ def bench_vo_loop(pkg):
         for i in range(n):
             pkg.synth.write_pgm(f"{d}/image_0/{i:06d}.pgm", lefts[i])
             pkg.synth.write_pgm(f"{d}/image_1/{i:06d}.pgm", rights[i])
-        for name, extra in (("reference_defaults_dense", ["--dense"]),
-                            ("keyframe_every_frame_dense", ["--dense", "--nfeatures", "1000", "--anms", "110"]),
+        for name, extra in (("reference_defaults_dense", []),   # dense StereoSGBM depth is the drop-in layer's default
+                            ("keyframe_every_frame_dense", ["--nfeatures", "1000", "--anms", "110"]),
                             # the north star's sparse-stereo depth (ORB on both images + L<->R matching + DLT) instead of SGBM
-                            ("keyframe_every_frame_sparse", ["--nfeatures", "1000", "--anms", "110"])):
+                            ("keyframe_every_frame_sparse", ["--sparse", "--nfeatures", "1000", "--anms", "110"])):
             with tempfile.TemporaryDirectory() as w:
                 r = subprocess.run([exe, d + "/", str(n), *extra], cwd=w, capture_output=True, text=True, timeout=300)
             rows = [l.split() for l in r.stdout.splitlines() if l.startswith("frame ")]

@@ -317,6 +317,11 @@ int vslam_sgbm_debug_stop_after(vslam_ctx* ctx, int stage);
  * vslam_ba_session_trial_done(accept) records the LM verdict.  vslam_ba_session_end downloads the poses and
  * this rank's shard of points / per-edge chi2 / inlier flags (zeros elsewhere: sum over ranks assembles).
  * stereo-visual-slam_b200/sharding.py is the reference driver (torch.distributed, NCCL or gloo).
+ * STREAM CONTRACT: every phase is enqueued on the context stream (vslam_ctx_set_stream) without synchronising; the
+ * caller's collectives on r1/r2/r3 and its host reads of them must be ordered on that SAME stream (with
+ * torch.distributed: make the context stream torch's current stream before vslam_ba_session_begin, as
+ * ffi.GpuBaSession does) -- otherwise the phases race with the all-reduces.
+ * For a single-process, multi-device caller use vslam_ba_optimize_multi below: it needs no collective library.
  * ---------------------------------------------------------------------------------------------- */
 int vslam_ba_reduce_sizes(int n_poses, int* r1_doubles, int* r2_doubles, int* r3_doubles);
 int vslam_ba_session_begin(vslam_ctx* ctx, int n_poses, const double* poses, int n_points, const double* points,

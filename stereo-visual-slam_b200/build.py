@@ -100,9 +100,32 @@ def build_host(force: bool = False) -> str:
     return HOST_LIB
 
 
+REF_MAIN_SRC = "/root/reference/src/run_vslam.cpp"
+RUN_VSLAM_REF = os.path.join(HERE, "run_vslam_ref")
+
+
+def build_reference_main(force: bool = False):
+    """The reference's own main loop, /root/reference/src/run_vslam.cpp, compiled UNMODIFIED from where it lies against
+    the drop-in headers and linked with the drop-in host library ("run_vslam.cpp links unchanged apart from ROS
+    plumbing").  Only possible where /root/reference exists (this container); the binary is git-ignored and travels to
+    the GPU box with the snapshot.  Returns the path or None."""
+    if not os.path.exists(REF_MAIN_SRC):
+        return RUN_VSLAM_REF if os.path.exists(RUN_VSLAM_REF) else None
+    cxx = os.environ.get("CXX", "g++")
+    if force or not os.path.exists(RUN_VSLAM_REF) or os.path.getmtime(RUN_VSLAM_REF) < os.path.getmtime(HOST_LIB):
+        cmd = [cxx, "-std=c++17", "-O2", "-I", HOST, "-o", RUN_VSLAM_REF, REF_MAIN_SRC,
+               "-L", HERE, "-lvslam_b200_host", "-lvslam_b200", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout)
+            raise RuntimeError("reference run_vslam.cpp did not compile against the drop-in layer")
+    return RUN_VSLAM_REF
+
+
 if __name__ == "__main__":
     if "--host" in sys.argv:
         build_native()
         print(build_host(force="--force" in sys.argv))
+        print(build_reference_main(force="--force" in sys.argv))
         sys.exit(0)
     print(build_native(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -8,7 +8,7 @@
 // accept/reject rule as the oracle -- only summation order differs (documented tolerance 1e-4 relative on poses).
 //
 // Data layout: observations are sorted by landmark on the host (stable counting sort, O(n_obs) index marshalling), so
-// one thread owns one landmark: its 3x3 Hll block, bl and its Schur products never need atomics.  Pose blocks
+// a group of eight lanes owns one landmark: its 3x3 Hll block, bl and its Schur products never need atomics.  Pose blocks
 // (Hpp, bp) are accumulated in shared memory per CTA and flushed with fp64 atomics; the reduced camera system S
 // (6K x 6K) is accumulated per CTA in shared memory and reduced deterministically through a partial buffer when it
 // fits (6K <= 96), with global fp64 atomics otherwise.  The dense SPD solve (K15) runs in one CTA, in shared memory
@@ -204,52 +204,75 @@ __device__ __forceinline__ void ba_edge(const BaParams& P, const double* T, cons
     }
 }
 
-// BUILD-A (K13, per edge): computeActiveErrors + activeRobustChi2 + the landmark side of buildSystem.
-// One thread per observation; the 3x3 landmark blocks take fp64 reductions at L2 (a landmark has a handful of edges,
-// so no contention); Hpl (6x3) is stored per edge; obs_of records which edge joins (pose, landmark).
+// BUILD-A (K13, per landmark): computeActiveErrors + activeRobustChi2 + the landmark side of buildSystem.
+// Eight lanes own one landmark (observations are sorted by landmark): lane q takes the landmark's edges q, q + 8, ...,
+// the 3x3 block and gradient are summed over the group with a fixed xor butterfly and written once -- no atomics, the
+// same summation order on every run.  Hpl (6x3) is stored per edge; obs_of records which edge joins (pose, landmark).
+#define BA_LM_GROUP 8
 __device__ void ba_phase_build_edges(const BaParams& P, int cur, int gtid, int gsize) {
     const double* poses = P.poses + (size_t)cur * P.K * 12;
     const double* points = P.points + (size_t)cur * P.L * 3;
     double chi = 0.0;
-    const int i0 = P.lm_start[P.shard_L0], i1 = P.lm_start[P.shard_L1];
-    for (int i = i0 + gtid; i < i1; i += gsize) {
-        const int k = P.obs_pose[i], l = P.obs_point[i];
-        const double* T = poses + 12 * k;
-        const double p[3] = {points[3 * l], points[3 * l + 1], points[3 * l + 2]};
-        double e0, e1, r0, w, A[12];
-        ba_edge(P, T, p, P.obs_uv[2 * i], P.obs_uv[2 * i + 1], e0, e1, r0, w, A);
-        P.err[2 * i] = e0;
-        P.err[2 * i + 1] = e1;
-        chi += r0;
-        P.obs_of[(size_t)k * P.L + l] = i;
-        if (!P.pose_only) {
-            // which (ki <= kj) blocks of the reduced system are non-empty: idempotent stores, structure is fixed
-            for (int j = P.lm_start[l]; j < P.lm_start[l + 1]; ++j) {
-                const int kj = P.obs_pose[j];
-                if (kj >= k) P.block_flag[k * P.K - k * (k - 1) / 2 + (kj - k)] = 1;
+    const int sub = gtid & (BA_LM_GROUP - 1);
+    const int ngroups = gsize / BA_LM_GROUP;
+    const int nl = P.shard_L1 - P.shard_L0;
+    // every lane of a warp runs the same number of iterations (the butterflies below are warp-wide)
+    const int iters = (nl + ngroups - 1) / ngroups;
+    for (int itl = 0; itl < iters; ++itl) {
+        const int l = P.shard_L0 + itl * ngroups + gtid / BA_LM_GROUP;
+        const bool live = l < P.shard_L1;
+        const int o0 = live ? P.lm_start[l] : 0, o1 = live ? P.lm_start[l + 1] : 0;
+        double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // Hll upper triangle (6) + bl (3)
+        const double p[3] = {live ? points[3 * l] : 0.0, live ? points[3 * l + 1] : 0.0, live ? points[3 * l + 2] : 0.0};
+        for (int i = o0 + sub; i < o1; i += BA_LM_GROUP) {
+            const int k = P.obs_pose[i];
+            const double* T = poses + 12 * k;
+            double e0, e1, r0, w, A[12];
+            ba_edge(P, T, p, P.obs_uv[2 * i], P.obs_uv[2 * i + 1], e0, e1, r0, w, A);
+            P.err[2 * i] = e0;
+            P.err[2 * i + 1] = e1;
+            chi += r0;
+            P.obs_of[(size_t)k * P.L + l] = i;
+            if (!P.pose_only) {
+                // which (ki <= kj) blocks of the reduced system are non-empty: idempotent stores, structure is fixed
+                for (int j = o0; j < o1; ++j) {
+                    const int kj = P.obs_pose[j];
+                    if (kj >= k) P.block_flag[k * P.K - k * (k - 1) / 2 + (kj - k)] = 1;
+                }
+                const double om0 = -w * e0, om1 = -w * e1;
+                double B[6];
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) B[r * 3 + c] = A[r * 6] * T[c] + A[r * 6 + 1] * T[4 + c] + A[r * 6 + 2] * T[8 + c];
+                h[0] += w * (B[0] * B[0] + B[3] * B[3]);
+                h[1] += w * (B[0] * B[1] + B[3] * B[4]);
+                h[2] += w * (B[0] * B[2] + B[3] * B[5]);
+                h[3] += w * (B[1] * B[1] + B[4] * B[4]);
+                h[4] += w * (B[1] * B[2] + B[4] * B[5]);
+                h[5] += w * (B[2] * B[2] + B[5] * B[5]);
+                h[6] += B[0] * om0 + B[3] * om1;
+                h[7] += B[1] * om0 + B[4] * om1;
+                h[8] += B[2] * om0 + B[5] * om1;
+                double* hp = P.Hpl + 18 * (size_t)i;
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) hp[a * 3 + c] = w * (A[a] * B[c] + A[6 + a] * B[3 + c]);
             }
-            const double om0 = -w * e0, om1 = -w * e1;
-            double B[6];
+        }
+        if (!P.pose_only) {
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
+            for (int q = 0; q < 9; ++q) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) B[r * 3 + c] = A[r * 6] * T[c] + A[r * 6 + 1] * T[4 + c] + A[r * 6 + 2] * T[8 + c];
-            double* H = P.Hll + 9 * (size_t)l;
-            double* bb = P.bl + 3 * (size_t)l;
-            atomicAdd(&bb[0], B[0] * om0 + B[3] * om1);
-            atomicAdd(&bb[1], B[1] * om0 + B[4] * om1);
-            atomicAdd(&bb[2], B[2] * om0 + B[5] * om1);
-            atomicAdd(&H[0], w * (B[0] * B[0] + B[3] * B[3]));
-            atomicAdd(&H[1], w * (B[0] * B[1] + B[3] * B[4]));
-            atomicAdd(&H[2], w * (B[0] * B[2] + B[3] * B[5]));
-            atomicAdd(&H[4], w * (B[1] * B[1] + B[4] * B[4]));
-            atomicAdd(&H[5], w * (B[1] * B[2] + B[4] * B[5]));
-            atomicAdd(&H[8], w * (B[2] * B[2] + B[5] * B[5]));
-            double* hp = P.Hpl + 18 * (size_t)i;
-#pragma unroll
-            for (int a = 0; a < 6; ++a)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) hp[a * 3 + c] = w * (A[a] * B[c] + A[6 + a] * B[3 + c]);
+                for (int o = BA_LM_GROUP / 2; o > 0; o >>= 1) h[q] += __shfl_xor_sync(0xFFFFFFFFu, h[q], o);
+            }
+            if (live && sub == 0 && o1 > o0) {  // ZERO cleared the blocks of landmarks without edges
+                double* H = P.Hll + 9 * (size_t)l;
+                H[0] = h[0]; H[1] = h[1]; H[2] = h[2]; H[4] = h[3]; H[5] = h[4]; H[8] = h[5];
+                double* bb = P.bl + 3 * (size_t)l;
+                bb[0] = h[6]; bb[1] = h[7]; bb[2] = h[8];
+            }
         }
     }
     chi = warp_sum(chi);

@@ -436,6 +436,12 @@ class GpuBaSession:
     def __init__(self, ctx, problem, shard, r1, r2, r3, num_iterations=10, pose_only=False, huber_delta=5.991,
                  chi2_th=5.991, max_trials=10, tau=1e-5):
         self.ctx = ctx
+        # Stream contract (vslam_b200.h K17): the phases run on the context stream, the caller's collectives and
+        # host reads on the stream that owns r1/r2/r3 -- they must be the SAME stream.  With torch reduce buffers the
+        # session therefore moves the context onto torch's current stream of that device.
+        if hasattr(r1, "is_cuda") and r1.is_cuda:
+            import torch
+            ctx.set_stream(torch.cuda.current_stream(r1.device).cuda_stream)
         self.poses = np.ascontiguousarray(problem["poses"], dtype=np.float64).reshape(-1, 12)
         self.points = np.ascontiguousarray(problem["points"], dtype=np.float64).reshape(-1, 3)
         self.op = np.ascontiguousarray(problem["obs_pose"], dtype=np.int32)

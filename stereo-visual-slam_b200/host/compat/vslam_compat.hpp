@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -276,17 +277,61 @@ public:
 // ----------------------------------------------------------------------------------------------------------------
 namespace ros {
 
-// parameter-server stub: values are set programmatically (the reference reads /dataset, /if_write_pose, /if_rviz)
+// parameter-server stub (the reference reads /dataset, /if_write_pose, /if_rviz from the ROS parameter server,
+// run_vslam.cpp:20-28).  Values come from setParam() on the handle, or from the process-wide store that ros::init()
+// fills from "<name>:=<value>" arguments (e.g. /dataset:=/data/kitti/00/ /if_write_pose:=true) and from the
+// environment (VSLAM_PARAM_dataset, VSLAM_PARAM_if_write_pose, VSLAM_PARAM_if_rviz).
+struct ParamStore {
+    std::map<std::string, bool> b;
+    std::map<std::string, std::string> s;
+    static ParamStore& global() { static ParamStore g; return g; }
+    static bool parse_bool(const std::string& v) { return v == "true" || v == "1" || v == "True"; }
+    void set(const std::string& key, const std::string& value) {
+        s[key] = value;
+        b[key] = parse_bool(value);
+    }
+};
 class NodeHandle {
 public:
-    void setParam(const std::string& k, bool v) { b_[k] = v; }
-    void setParam(const std::string& k, const std::string& v) { s_[k] = v; }
-    bool getParam(const std::string& k, bool& v) const { auto i = b_.find(k); if (i == b_.end()) { v = false; return false; } v = i->second; return true; }
-    bool getParam(const std::string& k, std::string& v) const { auto i = s_.find(k); if (i == s_.end()) return false; v = i->second; return true; }
+    void setParam(const std::string& k, bool v) { own_.b[k] = v; }
+    void setParam(const std::string& k, const std::string& v) { own_.s[k] = v; }
+    bool getParam(const std::string& k, bool& v) const {
+        for (const ParamStore* p : {&own_, (const ParamStore*)&ParamStore::global()}) {
+            auto i = p->b.find(k);
+            if (i != p->b.end()) { v = i->second; return true; }
+        }
+        v = false;
+        return false;
+    }
+    bool getParam(const std::string& k, std::string& v) const {
+        for (const ParamStore* p : {&own_, (const ParamStore*)&ParamStore::global()}) {
+            auto i = p->s.find(k);
+            if (i != p->s.end()) { v = i->second; return true; }
+        }
+        return false;
+    }
 private:
-    std::map<std::string, bool> b_;
-    std::map<std::string, std::string> s_;
+    ParamStore own_;
 };
+// ros::init / ros::spin / ros::spinOnce (run_vslam.cpp:19,89; visual_odometry.cpp:458,703): ROS plumbing, no-ops here
+// apart from the parameter arguments described above
+inline void init(int& argc, char** argv, const std::string& /*node_name*/) {
+    ParamStore& g = ParamStore::global();
+    for (const char* key : {"dataset", "if_write_pose", "if_rviz"}) {
+        const char* e = std::getenv((std::string("VSLAM_PARAM_") + key).c_str());
+        if (e) g.set(std::string("/") + key, e);
+    }
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        const size_t p = a.find(":=");
+        if (p == std::string::npos) continue;
+        std::string key = a.substr(0, p);
+        if (!key.empty() && key[0] == '_') key = key.substr(1);
+        if (key.empty() || key[0] != '/') key = "/" + key;
+        g.set(key, a.substr(p + 2));
+    }
+}
+inline void spin() {}
 inline void spinOnce() {}
 
 }  // namespace ros

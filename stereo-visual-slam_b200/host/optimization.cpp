@@ -3,16 +3,27 @@
 // insertion order) and marshals them into flat arrays; the optimisation itself is one call into the CUDA library.
 #include <stereo_visual_slam_main/optimization.hpp>
 
+#include <algorithm>
 #include <map>
+#include <vector>
 #include <stdexcept>
 
 #include "../../include/vslam_b200.h"
 
 namespace vslam {
 
-static vslam_ctx* g_opt_ctx = nullptr;
-void set_optimization_context(vslam_ctx* ctx) { g_opt_ctx = ctx; }
-vslam_ctx* optimization_context() { return g_opt_ctx; }
+static std::vector<vslam_ctx*>& opt_ctx_stack() {
+    static std::vector<vslam_ctx*> s;
+    return s;
+}
+void set_optimization_context(vslam_ctx* ctx) {
+    if (ctx) opt_ctx_stack().push_back(ctx);
+}
+void release_optimization_context(vslam_ctx* ctx) {
+    auto& s = opt_ctx_stack();
+    s.erase(std::remove(s.begin(), s.end(), ctx), s.end());
+}
+vslam_ctx* optimization_context() { return opt_ctx_stack().empty() ? nullptr : opt_ctx_stack().back(); }
 
 namespace {
 
@@ -60,6 +71,7 @@ Graph build_graph(std::unordered_map<unsigned long, Frame>& keyframes,
 
 void run(std::unordered_map<unsigned long, Frame>& keyframes, std::unordered_map<unsigned long, Landmark>& landmarks,
          const cv::Mat& K, bool pose_only, bool if_update_map, bool if_update_landmark, int num_ite) {
+    vslam_ctx* g_opt_ctx = optimization_context();
     if (!g_opt_ctx) throw std::runtime_error("vslam::optimize_*: no library context (set_optimization_context)");
     Graph g = build_graph(keyframes, landmarks, !pose_only);
     if (g.kf_ids.empty()) return;

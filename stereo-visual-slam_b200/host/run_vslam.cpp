@@ -2,7 +2,8 @@
 // (/root/reference/src/run_vslam.cpp:17-92): per frame VO::pipeline(), and after every keyframe insertion with a full
 // window optimize_map(5) x2 (outlier relabel only), optimize_map(10) with pose write-back and optimize_pose_only(10).
 //
-//   run_vslam <dataset_dir/> <n_frames> [--no-ba] [--nfeatures N] [--anms K] [--dense] [--window W] [--update-landmarks]
+//   run_vslam <dataset_dir/> <n_frames> [--no-ba] [--nfeatures N] [--anms K] [--sparse] [--window W] [--update-landmarks]
+// (depth source: the reference's dense StereoSGBM unless --sparse; --dense is accepted and redundant)
 // reads <dataset_dir>/image_{0,1}/%06d.pgm, appends evicted / remaining keyframe poses to ./estimated_traj.txt
 // (the reference's format) and prints one "frame <id> <12 numbers of T_w_c> <inliers> <is_keyframe> <#keyframes>
 // <#landmarks> <frame wall-clock ms>" line per frame.
@@ -19,17 +20,18 @@
 
 int main(int argc, char** argv) {
     if (argc < 3) {
-        std::fprintf(stderr, "usage: run_vslam <dataset_dir/> <n_frames> [--no-ba] [--nfeatures N] [--anms K] [--dense] [--window W] [--update-landmarks]\n");
+        std::fprintf(stderr, "usage: run_vslam <dataset_dir/> <n_frames> [--no-ba] [--nfeatures N] [--anms K] [--sparse] [--window W] [--update-landmarks]\n");
         return 2;
     }
     const std::string dataset = argv[1];
     const int n_frames = std::atoi(argv[2]);
-    bool do_ba = true, dense = false;
+    bool do_ba = true, dense = true;
     int nfeatures = 3000, anms = 500, window = 10;
     bool update_landmarks = false;  // the reference never writes landmarks back (run_vslam.cpp:61-64)
     for (int i = 3; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--no-ba")) do_ba = false;
-        else if (!std::strcmp(argv[i], "--dense")) dense = true;  // the reference's StereoSGBM depth source
+        else if (!std::strcmp(argv[i], "--dense")) dense = true;  // the reference's StereoSGBM depth source (default)
+        else if (!std::strcmp(argv[i], "--sparse")) dense = false;  // opt-in fast mode: sparse L<->R matching + DLT
         else if (!std::strcmp(argv[i], "--window") && i + 1 < argc) window = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--update-landmarks")) update_landmarks = true;
         else if (!std::strcmp(argv[i], "--nfeatures") && i + 1 < argc) nfeatures = std::atoi(argv[++i]);

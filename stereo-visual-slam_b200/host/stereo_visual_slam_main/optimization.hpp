@@ -16,9 +16,12 @@ struct vslam_ctx;
 namespace vslam {
 
 // The library context used by optimize_map / optimize_pose_only (the reference's free functions take no handle).
-// VO's constructor sets it; stand-alone callers can set their own.  Not owned.
-void set_optimization_context(vslam_ctx* ctx);
-vslam_ctx* optimization_context();
+// Contexts are kept on a small stack: every VO registers its context on construction and withdraws it on destruction,
+// the most recently registered one still alive is used -- destroying one VO never leaves another VO's optimize_* calls
+// without a context.  Stand-alone callers can register their own.  Not owned.
+void set_optimization_context(vslam_ctx* ctx);       // register (push); nullptr is ignored
+void release_optimization_context(vslam_ctx* ctx);   // withdraw every registration of ctx
+vslam_ctx* optimization_context();                   // the context optimize_* will use, or nullptr
 
 // optimize_map: LM(Schur) over every keyframe pose and every landmark with is_inlier && reliable_depth_, `num_ite`
 // iterations, then the adaptive chi2 relabel of Landmark::is_inlier; poses written back if if_update_map, landmarks

@@ -33,9 +33,10 @@ public:
     int detector_nfeatures_ = 3000;  // cv::ORB::create(3000), visual_odometry.cpp:22,31
     int anms_keep_ = 500;            // adaptive_non_maximal_suppresion(keypoints, 500), visual_odometry.cpp:82
     vslam_ctx* ctx_ = nullptr;       // owned
-    // depth source of disparity_map: false = sparse stereo (ORB on both images + L<->R matching + DLT, the north
-    // star's triangulation), true = the reference's dense StereoSGBM (visual_odometry.cpp:163-168) on the GPU
-    bool dense_stereo_ = false;
+    // depth source of disparity_map: true (default) = the reference's dense StereoSGBM (visual_odometry.cpp:163-168)
+    // on the GPU, bit-exact; false = opt-in fast mode, sparse stereo (ORB on both images + L<->R matching on the same
+    // row band with positive disparity + DLT, the north star's triangulation) -- NOT what the reference computes
+    bool dense_stereo_ = true;
 
     int num_inliers_ = 0;
     SE3 T_c_l_ = SE3();
@@ -62,10 +63,10 @@ public:
     VO& operator=(const VO&) = delete;
 
     int read_img(int id, cv::Mat& left_img, cv::Mat& right_img);
-    // reference: dense SGBM (dense_stereo_ = true reproduces it bit-exactly).  Default: SPARSE disparity -- ORB on
-    // both images, L<->R feature_matching, per-match DLT; `disparity` is CV_32F, -1 everywhere except at the
-    // (truncated) pixel of every matched left keypoint, where it holds fx*b/Z, so Frame::find_3d and
-    // set_ref_3d_position work unchanged in both modes.
+    // reference: dense SGBM (the default, dense_stereo_ = true, reproduces it bit-exactly).  With dense_stereo_ = false:
+    // SPARSE disparity -- ORB on both images, L<->R feature_matching, matches gated to |dy| <= 2 px and positive
+    // disparity, per-match DLT; `disparity` is CV_32F, -1 everywhere except at the (truncated) pixel of every matched
+    // left keypoint, where it holds fx*b/Z, so Frame::find_3d and set_ref_3d_position work unchanged in both modes.
     int disparity_map(const Frame& frame, cv::Mat& disparity);
     bool initialization();
     bool tracking(bool& if_insert_keyframe);

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <cstdio>
 #include <fstream>
@@ -38,6 +39,10 @@ void VO::create_context() {
     cfg.max_ba_obs = 262144;
     check(vslam_ctx_create(&cfg, &ctx_), "vslam_ctx_create");  // throws without a B200: there is no CPU path
     set_optimization_context(ctx_);
+    // runtime knobs for callers that cannot reach the members (the reference's unmodified main, run_vslam.cpp:17-92)
+    if (const char* e = std::getenv("VSLAM_NFEATURES")) detector_nfeatures_ = std::atoi(e);
+    if (const char* e = std::getenv("VSLAM_ANMS_KEEP")) anms_keep_ = std::atoi(e);
+    if (const char* e = std::getenv("VSLAM_SPARSE_STEREO")) dense_stereo_ = std::atoi(e) == 0;
 }
 
 VO::VO(ros::NodeHandle& nh, Map& map) : my_map_(map), my_visual_(nh) {
@@ -52,7 +57,7 @@ VO::VO(std::string dataset, ros::NodeHandle& nh, Map& map) : my_map_(map), my_vi
 }
 
 VO::~VO() {
-    if (optimization_context() == ctx_) set_optimization_context(nullptr);
+    release_optimization_context(ctx_);
     vslam_ctx_destroy(ctx_);
 }
 
@@ -96,6 +101,14 @@ int VO::feature_detection(const cv::Mat& img, std::vector<cv::KeyPoint>& keypoin
     const int st = vslam_orb_detect_compute(ctx_, img.data, img.cols, img.rows, (int)img.step, detector_nfeatures_,
                                             anms_keep_, 1.11f, reinterpret_cast<vslam_keypoint*>(kp.data()), desc.data, &n);
     if (st == VSLAM_E_INVALID) return -1;
+    if (st == VSLAM_E_OVERFLOW || st == VSLAM_E_CAPACITY) {
+        // a device work list overflowed / the image exceeds the context: degrade like the reference does on a bad frame
+        // (no keypoints -> no matches -> "Rejected - inliers not enough") instead of throwing out of VO::pipeline
+        std::cout << "feature_detection: " << vslam_status_string(st) << " -- frame dropped" << std::endl;
+        keypoints.clear();
+        descriptors = cv::Mat(0, 32, cv::CV_8U);
+        return -1;
+    }
     check(st, "vslam_orb_detect_compute");
     kp.resize(n);
     keypoints.swap(kp);
@@ -165,8 +178,11 @@ int VO::disparity_map(const Frame& frame, cv::Mat& disparity) {
     disparity.setTo(-1.0);  // "no depth", as SGBM's invalid value after the /16 conversion
     for (int i = 0; i < n_m; ++i) {
         const vslam_keypoint& k = kp[matches[i].queryIdx];
+        const vslam_keypoint& kr = kp[(size_t)cap + matches[i].trainIdx];
         const float Z = xyz[3 * i + 2];
-        if (!(Z > 0)) continue;
+        // rectified pair: a true correspondence lies on the same row (within the ORB localisation error of the coarser
+        // octaves) and to the left in the right image
+        if (!(Z > 0) || !(k.x - kr.x > 0.f) || std::fabs(k.y - kr.y) > 2.f) continue;
         disparity.at<float>((int)k.y, (int)k.x) = (float)(frame.fx_ * frame.b_ / Z);
     }
     return 0;
@@ -390,11 +406,28 @@ bool VO::tracking(bool& if_insert_keyframe) {
     return ok;
 }
 
+// VSLAM_FRAME_LOG=<path>: one "frame <id> <12 numbers of T_w_c> <inliers> <is_keyframe> <#keyframes> <#landmarks>"
+// line per processed frame (the same record run_vslam prints), so that any main loop over VO::pipeline can be compared
+static void log_frame(const Frame& f, int inliers, bool kf, const Map& map) {
+    static const char* path = std::getenv("VSLAM_FRAME_LOG");
+    if (!path) return;
+    FILE* fp = std::fopen(path, "a");
+    if (!fp) return;
+    const SE3 T_w_c = f.T_c_w_.inverse();
+    std::fprintf(fp, "frame %d", f.frame_id_);
+    for (int r = 0; r < 3; ++r)
+        std::fprintf(fp, " %.9g %.9g %.9g %.9g", T_w_c.rotationMatrix()(r, 0), T_w_c.rotationMatrix()(r, 1),
+                     T_w_c.rotationMatrix()(r, 2), T_w_c.translation()(r));
+    std::fprintf(fp, " %d %d %zu %zu\n", inliers, (int)kf, map.keyframes_.size(), map.landmarks_.size());
+    std::fclose(fp);
+}
+
 bool VO::pipeline(bool& if_insert_keyframe) {
     switch (state_) {
         case Init:
             if (initialization()) {
                 state_ = Track;
+                log_frame(frame_last_, num_inliers_, false, my_map_);
             } else if (++num_lost_ > 10) {
                 state_ = Lost;
             }
@@ -405,6 +438,7 @@ bool VO::pipeline(bool& if_insert_keyframe) {
             } else if (++num_lost_ > 10) {
                 state_ = Lost;
             }
+            if (frame_current_.left_img_.data) log_frame(frame_current_, num_inliers_, if_insert_keyframe, my_map_);
             break;
         case Lost:
             std::cout << "VO IS LOST" << std::endl;

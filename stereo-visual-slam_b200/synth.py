@@ -22,6 +22,14 @@ def kitti_K() -> np.ndarray:
     return np.array([[FX, 0.0, CX], [0.0, FY, CY], [0.0, 0.0, 1.0]], dtype=np.float64)
 
 
+def stereo_projection_matrices(fx: float = FX, fy: float = FY, cx: float = CX, cy: float = CY, b: float = BASELINE_M):
+    """Rectified KITTI-style pair: P1 = K [I | 0], P2 = K [I | (-b, 0, 0)] (types_def.hpp:53-54 constants)."""
+    K = np.array([[fx, 0.0, cx], [0.0, fy, cy], [0.0, 0.0, 1.0]])
+    P1 = K @ np.hstack([np.eye(3), np.zeros((3, 1))])
+    P2 = K @ np.hstack([np.eye(3), np.array([[-b], [0.0], [0.0]])])
+    return P1, P2
+
+
 def _gauss_blur_sep(img: np.ndarray, sigma: float) -> np.ndarray:
     r = int(np.ceil(3 * sigma))
     x = np.arange(-r, r + 1, dtype=np.float64)

@@ -94,6 +94,23 @@ def test_large_window_cfg5_shape(pkg, ba_ctx):
     _compare(g, o)
 
 
+def test_full_size_configs_vs_oracle(pkg, ba_ctx):
+    """BASELINE.json configs[2] (K=10, L=5000, ~20k observations, seed 42) and configs[4] (K=50, L=20000, exactly 100k
+    observations, seed 43) at FULL size against the C oracle: same trial sequence, poses / landmarks within 1e-4"""
+    for seed, nk, nl, kw, nit in ((42, 10, 5000, {}, 10), (43, 50, 20000, dict(n_obs_exact=100000), 10)):
+        p = pkg.synth.synth_ba_problem(seed, nk, nl, **kw)
+        if kw:
+            assert len(p["obs_pose"]) == 100000
+        args = (p["poses"], p["points"], p["obs_pose"], p["obs_point"], p["obs_uv"], p["K"])
+        g = ba_ctx.ba_optimize(*args, num_iterations=nit)
+        o = B.optimize(*args, num_iterations=nit)
+        _compare(g, o)
+        assert g["chi2_final"] < 0.01 * g["chi2_initial"]
+        # determinism of the landmark-owned build: two runs give bit-identical landmark blocks -> identical results
+        g2 = ba_ctx.ba_optimize(*args, num_iterations=nit)
+        assert g2["trials"] == g["trials"] and np.abs(g2["poses"] - g["poses"]).max() < 1e-12
+
+
 def test_edge_cases(pkg, ba_ctx):
     p = pkg.synth.synth_ba_problem(9, 4, 60)
     args = (p["poses"], p["points"], p["obs_pose"], p["obs_point"], p["obs_uv"], p["K"])

@@ -35,7 +35,8 @@ def _run(seq_dir, n, cwd, *extra):
 
 
 def test_vo_only_reference_defaults(sequence, tmp_path):
-    """ORB(3000) -> ANMS(500) -> match -> PnP, the reference operating point; window never fills, so no BA"""
+    """ORB(3000) -> ANMS(500) -> match -> PnP with StereoSGBM depth (the default, as in the reference,
+    visual_odometry.cpp:163-168): the reference operating point; window never fills, so no BA"""
     seq_dir, n, t = sequence
     ids, T, meta, out = _run(seq_dir, n, tmp_path)
     assert len(ids) == n and (ids == np.arange(n)).all(), out
@@ -61,16 +62,19 @@ def test_full_pipeline_with_ba(sequence, tmp_path):
     for row in traj:
         i = int(row[0])
         assert np.abs(row[[4, 8, 12]] - t[i]).max() < 0.10
-    # the same run without BA must also track; BA must not make the trajectory worse than VO-only by much
+    # the same run on the sparse depth source, and without BA, must also track; BA must not make it worse by much
+    ids3, T3, meta3, out3 = _run(seq_dir, n, tmp_path, "--sparse", "--nfeatures", "1000", "--anms", "110")
+    assert len(ids3) == n and "VO IS LOST" not in out3 and np.abs(T3[:, :, 3] - t[:n]).max() < 0.10
     ids2, T2, meta2, _ = _run(seq_dir, n, tmp_path, "--nfeatures", "1000", "--anms", "110", "--no-ba")
     err2 = np.abs(T2[:, :, 3] - t[:n]).max(axis=1)
     assert err.max() < err2.max() + 0.05
 
 
-def test_vo_with_dense_stereo_like_the_reference(sequence, tmp_path):
-    """--dense: VO::disparity_map = StereoSGBM on the GPU (the reference's depth source, visual_odometry.cpp:163-168)"""
+def test_vo_with_sparse_stereo_opt_in(sequence, tmp_path):
+    """--sparse: VO::disparity_map from ORB on both images + L<->R matching (row / positive-disparity gate) + DLT --
+    the north star's triangulation, an opt-in fast mode that is NOT what the reference computes"""
     seq_dir, n, t = sequence
-    ids, T, meta, out = _run(seq_dir, n, tmp_path, "--dense")
+    ids, T, meta, out = _run(seq_dir, n, tmp_path, "--sparse")
     assert len(ids) == n and (ids == np.arange(n)).all(), out
     assert "VO IS LOST" not in out and "Rejected" not in out
     assert (meta[1:, 0] >= 10).all()
