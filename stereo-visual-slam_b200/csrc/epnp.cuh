@@ -17,11 +17,28 @@
 #include <math.h>
 #include <stdint.h>
 
+// The same source is compiled for the device (one warp per sample) and, by tests/native/epnp_host.cpp, for the CPU,
+// where the lanes of a wavefront become a loop.
+#ifdef EPNP_HOST_BUILD
+#define EPNP_SYNCWARP()
+#define EPNP_FOR_LANES(p, cnt, lane) for (int p = 0; p < (cnt); ++p)
+#define EPNP_ANY(x) (x)
+#else
+#define EPNP_SYNCWARP() __syncwarp()
+#define EPNP_FOR_LANES(p, cnt, lane) \
+    const int p = (lane);            \
+    if (p < (cnt))
+#define EPNP_ANY(x) __any_sync(0xFFFFFFFFu, (x))
+#endif
+
+#define EPNP_AS 13  // row stride of the 12x12 matrix in shared memory: rows of different lanes fall into different banks
+
 struct EpnpWork {  // per-sample scratch (shared memory)
-    double At[144];  // M^T M transposed -> rows of U^T
+    double At[12 * EPNP_AS];  // M^T M (symmetric) -> rows of U^T
+    double W12[12], d12[12];
     double M[10 * 12];
-    double pws[15], us[10], alphas[20], pcs[15];
-    double cws[4][3], ccs[4][3];
+    double pws[15], us[10], alphas[20];
+    double cws[4][3];
     double L[60], rho[6];
     double uc, vc, fu, fv;
 };
@@ -45,143 +62,211 @@ __device__ __forceinline__ double cv_hypot(double a, double b) {
     return 0;
 }
 
-// One-sided Jacobi SVD of the n rows (length m) of At; rows become U^T, W the singular values (descending), Vt (n x n,
-// optional) the right singular vectors.  n <= 12.
-__device__ __noinline__ void jacobi_svd_dev(double* At, int astep, double* Wout, double* Vt, int vstep, int m, int n) {
+// One rotation step of JacobiSVDImpl_ on rows i, j (length M, compile-time so that the loads and products of a row are
+// independent instructions; the three sums stay sequential in k, as in OpenCV).  Returns whether the pair was rotated.
+template <int M, int NV>
+__device__ __forceinline__ bool jacobi_pair(double* __restrict__ Ai, double* __restrict__ Aj, double* __restrict__ Vi,
+                                            double* __restrict__ Vj, double& Wi, double& Wj) {
+    const double eps = DBL_EPSILON * 10;
+    double ai[M], aj[M];
+#pragma unroll
+    for (int k = 0; k < M; k++) {
+        ai[k] = Ai[k];
+        aj[k] = Aj[k];
+    }
+    double a = Wi, p = 0, b = Wj;
+#pragma unroll
+    for (int k = 0; k < M; k++) p += ai[k] * aj[k];
+    if (fabs(p) <= eps * sqrt(a * b)) return false;
+    p *= 2;
+    const double beta = a - b, gamma = cv_hypot(p, beta);
+    double c, s;
+    if (beta < 0) {
+        const double delta = (gamma - beta) * 0.5;
+        s = sqrt(delta / gamma);
+        c = p / (gamma * s * 2);
+    } else {
+        c = sqrt((gamma + beta) / (gamma * 2));
+        s = p / (gamma * c * 2);
+    }
+    a = b = 0;
+#pragma unroll
+    for (int k = 0; k < M; k++) {
+        const double t0 = c * ai[k] + s * aj[k];
+        const double t1 = -s * ai[k] + c * aj[k];
+        Ai[k] = t0;
+        Aj[k] = t1;
+        a += t0 * t0;
+        b += t1 * t1;
+    }
+    Wi = a;
+    Wj = b;
+    if (NV > 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            const double t0 = c * Vi[k] + s * Vj[k];
+            const double t1 = -s * Vi[k] + c * Vj[k];
+            Vi[k] = t0;
+            Vj[k] = t1;
+        }
+    }
+    return true;
+}
+
+// Tail of JacobiSVDImpl_: singular values = row norms, selection sort (descending, first maximum wins), rows scaled to
+// unit length -- a row whose norm is <= DBL_MIN is replaced by OpenCV's random +-1/m vector orthogonalised against the
+// rows before it.  AS = row stride of At.
+template <int M, int N, int AS, bool WITH_V>
+__device__ void jacobi_finish(double* At, double* W, double* Wout, double* Vt) {
     const double eps = DBL_EPSILON * 10, minval = DBL_MIN;
-    double W[12];
-    const int max_iter = m > 30 ? m : 30;
-    for (int i = 0; i < n; i++) {
+    for (int i = 0; i < N; i++) {
         double sd = 0;
-        for (int k = 0; k < m; k++) {
-            const double t = At[i * astep + k];
-            sd += t * t;
-        }
-        W[i] = sd;
-        if (Vt) {
-            for (int k = 0; k < n; k++) Vt[i * vstep + k] = 0;
-            Vt[i * vstep + i] = 1;
-        }
-    }
-#pragma unroll 1
-    for (int iter = 0; iter < max_iter; iter++) {
-        bool changed = false;
-#pragma unroll 1
-        for (int i = 0; i < n - 1; i++)
-#pragma unroll 1
-            for (int j = i + 1; j < n; j++) {
-                double *Ai = At + i * astep, *Aj = At + j * astep;
-                double a = W[i], p = 0, b = W[j];
-                for (int k = 0; k < m; k++) p += Ai[k] * Aj[k];
-                if (fabs(p) <= eps * sqrt(a * b)) continue;
-                p *= 2;
-                const double beta = a - b, gamma = cv_hypot(p, beta);
-                double c, s;
-                if (beta < 0) {
-                    const double delta = (gamma - beta) * 0.5;
-                    s = sqrt(delta / gamma);
-                    c = p / (gamma * s * 2);
-                } else {
-                    c = sqrt((gamma + beta) / (gamma * 2));
-                    s = p / (gamma * c * 2);
-                }
-                a = b = 0;
-                for (int k = 0; k < m; k++) {
-                    const double t0 = c * Ai[k] + s * Aj[k];
-                    const double t1 = -s * Ai[k] + c * Aj[k];
-                    Ai[k] = t0;
-                    Aj[k] = t1;
-                    a += t0 * t0;
-                    b += t1 * t1;
-                }
-                W[i] = a;
-                W[j] = b;
-                changed = true;
-                if (Vt) {
-                    double *Vi = Vt + i * vstep, *Vj = Vt + j * vstep;
-                    for (int k = 0; k < n; k++) {
-                        const double t0 = c * Vi[k] + s * Vj[k];
-                        const double t1 = -s * Vi[k] + c * Vj[k];
-                        Vi[k] = t0;
-                        Vj[k] = t1;
-                    }
-                }
-            }
-        if (!changed) break;
-    }
-    for (int i = 0; i < n; i++) {
-        double sd = 0;
-        for (int k = 0; k < m; k++) {
-            const double t = At[i * astep + k];
+#pragma unroll
+        for (int k = 0; k < M; k++) {
+            const double t = At[i * AS + k];
             sd += t * t;
         }
         W[i] = sqrt(sd);
     }
-    for (int i = 0; i < n - 1; i++) {
+    for (int i = 0; i < N - 1; i++) {
         int j = i;
-        for (int k = i + 1; k < n; k++)
+        for (int k = i + 1; k < N; k++)
             if (W[j] < W[k]) j = k;
         if (i != j) {
             double t = W[i];
             W[i] = W[j];
             W[j] = t;
-            for (int k = 0; k < m; k++) {
-                t = At[i * astep + k];
-                At[i * astep + k] = At[j * astep + k];
-                At[j * astep + k] = t;
+#pragma unroll
+            for (int k = 0; k < M; k++) {
+                t = At[i * AS + k];
+                At[i * AS + k] = At[j * AS + k];
+                At[j * AS + k] = t;
             }
-            if (Vt)
-                for (int k = 0; k < n; k++) {
-                    t = Vt[i * vstep + k];
-                    Vt[i * vstep + k] = Vt[j * vstep + k];
-                    Vt[j * vstep + k] = t;
+            if (WITH_V)
+#pragma unroll
+                for (int k = 0; k < N; k++) {
+                    t = Vt[i * N + k];
+                    Vt[i * N + k] = Vt[j * N + k];
+                    Vt[j * N + k] = t;
                 }
         }
     }
-    for (int i = 0; i < n; i++) Wout[i] = W[i];
+    for (int i = 0; i < N; i++) Wout[i] = W[i];
     uint64_t rng = 0x12345678;
-    for (int i = 0; i < n; i++) {
+    for (int i = 0; i < N; i++) {
         double sd = W[i];
         for (int ii = 0; ii < 100 && sd <= minval; ii++) {
-            // zero singular value: OpenCV draws a +-1/m vector and orthogonalises it against the previous rows
-            const double val0 = 1. / m;
-            for (int k = 0; k < m; k++) At[i * astep + k] = (cvrng_next(rng) & 256) != 0 ? val0 : -val0;
+            const double val0 = 1. / M;
+            for (int k = 0; k < M; k++) At[i * AS + k] = (cvrng_next(rng) & 256) != 0 ? val0 : -val0;
             for (int iter = 0; iter < 2; iter++)
                 for (int j = 0; j < i; j++) {
                     sd = 0;
-                    for (int k = 0; k < m; k++) sd += At[i * astep + k] * At[j * astep + k];
+                    for (int k = 0; k < M; k++) sd += At[i * AS + k] * At[j * AS + k];
                     double asum = 0;
-                    for (int k = 0; k < m; k++) {
-                        const double t = At[i * astep + k] - sd * At[j * astep + k];
-                        At[i * astep + k] = t;
+                    for (int k = 0; k < M; k++) {
+                        const double t = At[i * AS + k] - sd * At[j * AS + k];
+                        At[i * AS + k] = t;
                         asum += fabs(t);
                     }
                     asum = asum > eps * 100 ? 1 / asum : 0;
-                    for (int k = 0; k < m; k++) At[i * astep + k] *= asum;
+                    for (int k = 0; k < M; k++) At[i * AS + k] *= asum;
                 }
             sd = 0;
-            for (int k = 0; k < m; k++) {
-                const double t = At[i * astep + k];
+            for (int k = 0; k < M; k++) {
+                const double t = At[i * AS + k];
                 sd += t * t;
             }
             sd = sqrt(sd);
         }
         const double s = sd > minval ? 1 / sd : 0.;
-        for (int k = 0; k < m; k++) At[i * astep + k] *= s;
+#pragma unroll
+        for (int k = 0; k < M; k++) At[i * AS + k] *= s;
     }
 }
 
-// cv::SVD::compute of A (m x n row-major, m >= n): Ut = n rows of length m, Vt = n x n
-__device__ void svd_small_dev(const double* A, int m, int n, double* w, double* Ut, double* Vt) {
-    for (int i = 0; i < n; i++)
-        for (int k = 0; k < m; k++) Ut[i * m + k] = A[k * n + i];
-    jacobi_svd_dev(Ut, m, w, Vt, n, m, n);
+// One-sided Jacobi SVD (JacobiSVDImpl_<double>) of the N rows (length M) of At; rows become U^T, Wout the singular
+// values (descending), Vt (N x N) the right singular vectors.  One thread, cyclic pair order.
+template <int M, int N>
+__device__ __noinline__ void jacobi_svd_small(double* At, double* Wout, double* Vt) {
+    double W[N];
+    const int max_iter = M > 30 ? M : 30;
+    for (int i = 0; i < N; i++) {
+        double sd = 0;
+#pragma unroll
+        for (int k = 0; k < M; k++) {
+            const double t = At[i * M + k];
+            sd += t * t;
+        }
+        W[i] = sd;
+#pragma unroll
+        for (int k = 0; k < N; k++) Vt[i * N + k] = 0;
+        Vt[i * N + i] = 1;
+    }
+#pragma unroll 1
+    for (int iter = 0; iter < max_iter; iter++) {
+        bool changed = false;
+#pragma unroll 1
+        for (int i = 0; i < N - 1; i++)
+#pragma unroll 1
+            for (int j = i + 1; j < N; j++)
+                changed |= jacobi_pair<M, N>(At + i * M, At + j * M, Vt + i * N, Vt + j * N, W[i], W[j]);
+        if (!changed) break;
+    }
+    jacobi_finish<M, N, M, true>(At, W, Wout, Vt);
+}
+
+// The 12x12 decomposition of M^T M (only U^T is used), rows of At padded to EPNP_AS doubles.  OpenCV walks the 66 row
+// pairs (i, j) of a sweep in cyclic order; pair (i, j) only depends on the last earlier pairs that touched row i or
+// row j, which puts it on wavefront i + j - 1: the up to six pairs of one wavefront touch disjoint rows and are
+// rotated by six lanes at once, 21 wavefronts per sweep instead of 66 sequential pairs -- with every row seeing exactly
+// the sequence of rotations (and therefore the bits) of the sequential loop.  Called by a whole warp (lanes >= 6 idle);
+// on the host build the lanes of a wavefront are a loop.
+__device__ void jacobi_svd12_wave(double* At, double* W /*[12] shared*/, double* Wout, int lane) {
+    const int N = 12;
+    if (lane == 0)
+        for (int i = 0; i < N; i++) {
+            double sd = 0;
+#pragma unroll
+            for (int k = 0; k < 12; k++) {
+                const double t = At[i * EPNP_AS + k];
+                sd += t * t;
+            }
+            W[i] = sd;
+        }
+    EPNP_SYNCWARP();
+#pragma unroll 1
+    for (int iter = 0; iter < 30; iter++) {
+        bool changed = false;
+#pragma unroll 1
+        for (int t = 0; t <= 2 * N - 4; t++) {
+            const int i_lo = t + 1 - (N - 1) > 0 ? t + 1 - (N - 1) : 0, cnt = t / 2 - i_lo + 1;
+            EPNP_FOR_LANES(p, cnt, lane) {
+                const int i = i_lo + p, j = t + 1 - i;
+                changed |= jacobi_pair<12, 0>(At + i * EPNP_AS, At + j * EPNP_AS, nullptr, nullptr, W[i], W[j]);
+            }
+            EPNP_SYNCWARP();
+        }
+        if (!EPNP_ANY(changed)) break;
+    }
+    if (lane == 0) jacobi_finish<12, 12, EPNP_AS, false>(At, W, Wout, nullptr);
+    EPNP_SYNCWARP();
+}
+
+// cv::SVD::compute of A (M x N row-major, M >= N): Ut = N rows of length M, Vt = N x N
+template <int M, int N>
+__device__ void svd_small_dev(const double* A, double* w, double* Ut, double* Vt) {
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int k = 0; k < M; k++) Ut[i * M + k] = A[k * N + i];
+    jacobi_svd_small<M, N>(Ut, w, Vt);
 }
 
 // cv::solve(A (6 x n), b, x, DECOMP_SVD): x = V diag(1/w) U^T b, singular values <= 2 eps sum(w) dropped
-__device__ void solve_svd6_dev(const double* A, int n, const double* b, double* x) {
-    double Ut[30], Vt[25], w[5];
-    svd_small_dev(A, 6, n, w, Ut, Vt);
+template <int N>
+__device__ void solve_svd6_dev(const double* A, const double* b, double* x) {
+    const int n = N;
+    double Ut[6 * N], Vt[N * N], w[N];
+    svd_small_dev<6, N>(A, w, Ut, Vt);
     double threshold = 0;
     for (int i = 0; i < n; i++) x[i] = 0;
     for (int i = 0; i < n; i++) threshold += w[i];
@@ -200,7 +285,7 @@ __device__ void solve_svd6_dev(const double* A, int n, const double* b, double* 
 // cv::invert(A 3x3, DECOMP_SVD)
 __device__ void invert3_svd_dev(const double* A, double* Ainv) {
     double Ut[9], Vt[9], w[3];
-    svd_small_dev(A, 3, 3, w, Ut, Vt);
+    svd_small_dev<3, 3>(A, w, Ut, Vt);
     const double threshold = (w[0] + w[1] + w[2]) * DBL_EPSILON * 2;
     for (int i = 0; i < 9; i++) Ainv[i] = 0;
     for (int i = 0; i < 3; i++) {
@@ -213,13 +298,13 @@ __device__ void invert3_svd_dev(const double* A, double* Ainv) {
 }
 
 // dst = src^T src (rows x cols), every entry summed over the rows in order, upper triangle mirrored
-__device__ void mul_transposed_dev(const double* src, int rows, int cols, double* dst) {
+__device__ void mul_transposed_dev(const double* src, int rows, int cols, double* dst, int dst_stride) {
     for (int i = 0; i < cols; i++)
         for (int j = i; j < cols; j++) {
             double s0 = 0;
             for (int k = 0; k < rows; k++) s0 += src[k * cols + i] * src[k * cols + j];
-            dst[i * cols + j] = s0;
-            dst[j * cols + i] = s0;
+            dst[i * dst_stride + j] = s0;
+            dst[j * dst_stride + i] = s0;
         }
 }
 
@@ -231,7 +316,7 @@ __device__ __forceinline__ double dist2_dev(const double* p1, const double* p2) 
 // R -> rotation vector (the matrix is first replaced by U V^T of its SVD, as cv::Rodrigues does)
 __device__ void rodrigues_to_vec_dev(const double* Rin, double* r) {
     double w[3], Ut[9], Vt[9], R[9];
-    svd_small_dev(Rin, 3, 3, w, Ut, Vt);
+    svd_small_dev<3, 3>(Rin, w, Ut, Vt);
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) R[i * 3 + j] = Ut[i] * Vt[j] + Ut[3 + i] * Vt[3 + j] + Ut[6 + i] * Vt[6 + j];
     double rx = R[7] - R[5], ry = R[2] - R[6], rz = R[3] - R[1];
@@ -287,11 +372,11 @@ __device__ void epnp_choose_control_points(EpnpWork& e, int n) {
     double pw0[15], g[9], dc[3], At[9];
     for (int i = 0; i < n; i++)
         for (int j = 0; j < 3; j++) pw0[3 * i + j] = e.pws[3 * i + j] - e.cws[0][j];
-    mul_transposed_dev(pw0, n, 3, g);
+    mul_transposed_dev(pw0, n, 3, g, 3);
     for (int i = 0; i < 3; i++)
         for (int k = 0; k < 3; k++) At[i * 3 + k] = g[k * 3 + i];
     double Vt[9];
-    jacobi_svd_dev(At, 3, dc, Vt, 3, 3, 3);
+    jacobi_svd_small<3, 3>(At, dc, Vt);
     for (int i = 1; i < 4; i++) {
         const double k = sqrt(dc[i - 1] / n);
         for (int j = 0; j < 3; j++) e.cws[i][j] = e.cws[0][j] + k * At[3 * (i - 1) + j];
@@ -313,29 +398,30 @@ __device__ void epnp_barycentric(EpnpWork& e, int n) {
     }
 }
 
-__device__ double epnp_R_and_t(EpnpWork& e, int n, const double* betas, double* R /*[9]*/, double* t) {
+__device__ double epnp_R_and_t(const EpnpWork& e, int n, const double* betas, double* R /*[9]*/, double* t) {
     // compute_ccs / compute_pcs / solve_for_sign
-    for (int i = 0; i < 4; i++) e.ccs[i][0] = e.ccs[i][1] = e.ccs[i][2] = 0.0;
+    double ccs[4][3], pcs[15];
+    for (int i = 0; i < 4; i++) ccs[i][0] = ccs[i][1] = ccs[i][2] = 0.0;
     for (int i = 0; i < 4; i++) {
-        const double* v = e.At + 12 * (11 - i);
+        const double* v = e.At + EPNP_AS * (11 - i);
         for (int j = 0; j < 4; j++)
-            for (int k = 0; k < 3; k++) e.ccs[j][k] += betas[i] * v[3 * j + k];
+            for (int k = 0; k < 3; k++) ccs[j][k] += betas[i] * v[3 * j + k];
     }
     for (int i = 0; i < n; i++) {
         const double* a = e.alphas + 4 * i;
         for (int j = 0; j < 3; j++)
-            e.pcs[3 * i + j] = a[0] * e.ccs[0][j] + a[1] * e.ccs[1][j] + a[2] * e.ccs[2][j] + a[3] * e.ccs[3][j];
+            pcs[3 * i + j] = a[0] * ccs[0][j] + a[1] * ccs[1][j] + a[2] * ccs[2][j] + a[3] * ccs[3][j];
     }
-    if (e.pcs[2] < 0.0) {
+    if (pcs[2] < 0.0) {
         for (int i = 0; i < 4; i++)
-            for (int j = 0; j < 3; j++) e.ccs[i][j] = -e.ccs[i][j];
-        for (int i = 0; i < 3 * n; i++) e.pcs[i] = -e.pcs[i];
+            for (int j = 0; j < 3; j++) ccs[i][j] = -ccs[i][j];
+        for (int i = 0; i < 3 * n; i++) pcs[i] = -pcs[i];
     }
     // estimate_R_and_t
     double pc0[3] = {0, 0, 0}, pw0[3] = {0, 0, 0};
     for (int i = 0; i < n; i++)
         for (int j = 0; j < 3; j++) {
-            pc0[j] += e.pcs[3 * i + j];
+            pc0[j] += pcs[3 * i + j];
             pw0[j] += e.pws[3 * i + j];
         }
     for (int j = 0; j < 3; j++) {
@@ -344,7 +430,7 @@ __device__ double epnp_R_and_t(EpnpWork& e, int n, const double* betas, double* 
     }
     double abt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < n; i++) {
-        const double* pc = e.pcs + 3 * i;
+        const double* pc = pcs + 3 * i;
         const double* pw = e.pws + 3 * i;
         for (int j = 0; j < 3; j++) {
             abt[3 * j] += (pc[j] - pc0[j]) * (pw[0] - pw0[0]);
@@ -353,7 +439,7 @@ __device__ double epnp_R_and_t(EpnpWork& e, int n, const double* betas, double* 
         }
     }
     double w[3], Ut[9], Vt[9];
-    svd_small_dev(abt, 3, 3, w, Ut, Vt);
+    svd_small_dev<3, 3>(abt, w, Ut, Vt);
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) R[i * 3 + j] = Ut[i] * Vt[j] + Ut[3 + i] * Vt[3 + j] + Ut[6 + i] * Vt[6 + j];
     const double det = R[0] * R[4] * R[8] + R[1] * R[5] * R[6] + R[2] * R[3] * R[7] - R[2] * R[4] * R[6] - R[1] * R[3] * R[8] -
@@ -382,7 +468,7 @@ __device__ double epnp_R_and_t(EpnpWork& e, int n, const double* betas, double* 
 }
 
 __device__ void epnp_L_6x10(const double* ut, double* l_6x10) {
-    const double* v[4] = {ut + 12 * 11, ut + 12 * 10, ut + 12 * 9, ut + 12 * 8};
+    const double* v[4] = {ut + EPNP_AS * 11, ut + EPNP_AS * 10, ut + EPNP_AS * 9, ut + EPNP_AS * 8};
     double dv[4][6][3];
     for (int i = 0; i < 4; i++) {
         int a = 0, b = 1;
@@ -422,7 +508,7 @@ __device__ void epnp_betas_approx(int which, const double* L, const double* rho,
             l[i * 4 + 2] = L[i * 10 + 3];
             l[i * 4 + 3] = L[i * 10 + 6];
         }
-        solve_svd6_dev(l, 4, rho, b);
+        solve_svd6_dev<4>(l, rho, b);
         if (b[0] < 0) {
             betas[0] = sqrt(-b[0]);
             betas[1] = -b[1] / betas[0];
@@ -439,7 +525,8 @@ __device__ void epnp_betas_approx(int which, const double* L, const double* rho,
     const int nc = which == 2 ? 3 : 5;  // [B11 B12 B22] or [B11 B12 B22 B13 B23]
     for (int i = 0; i < 6; i++)
         for (int j = 0; j < nc; j++) l[i * nc + j] = L[i * 10 + j];
-    solve_svd6_dev(l, nc, rho, b);
+    if (which == 2) solve_svd6_dev<3>(l, rho, b);
+    else solve_svd6_dev<5>(l, rho, b);
     if (b[0] < 0) {
         betas[0] = sqrt(-b[0]);
         betas[1] = (b[2] < 0) ? sqrt(-b[2]) : 0.0;
@@ -520,62 +607,82 @@ __device__ void epnp_gauss_newton(const double* L, const double* rho, double* be
 }
 
 // solvePnP(SOLVEPNP_EPNP) on the 5 correspondences idx[0..4]: undistortPoints stores the normalised image points as
-// float32, epnp's constructor maps them back through the camera matrix in double.  One thread.
+// float32, epnp's constructor maps them back through the camera matrix in double.
+// Phase 1 (one warp): control points, barycentric coordinates, M, M^T M by lane 0; the 12x12 SVD by the warp; L, rho.
+__device__ void epnp5_prepare(EpnpWork& e, const float* xyz, const float* uv, const int* idx, double fx, double fy, double cx,
+                              double cy, int lane) {
+    const int n = 5;
+    if (lane == 0) {
+        e.fu = fx;
+        e.fv = fy;
+        e.uc = cx;
+        e.vc = cy;
+        const double ifx = 1. / fx, ify = 1. / fy;
+        for (int i = 0; i < n; i++) {
+            const int q = idx[i];
+            e.pws[3 * i] = xyz[3 * q];
+            e.pws[3 * i + 1] = xyz[3 * q + 1];
+            e.pws[3 * i + 2] = xyz[3 * q + 2];
+            const float xn = (float)(((double)uv[2 * q] - cx) * ifx), yn = (float)(((double)uv[2 * q + 1] - cy) * ify);
+            e.us[2 * i] = xn * fx + cx;
+            e.us[2 * i + 1] = yn * fy + cy;
+        }
+        epnp_choose_control_points(e, n);
+        epnp_barycentric(e, n);
+        for (int i = 0; i < n; i++) {  // fill_M
+            double* M1 = e.M + 2 * i * 12;
+            double* M2 = M1 + 12;
+            const double* as = e.alphas + 4 * i;
+            const double u = e.us[2 * i], v = e.us[2 * i + 1];
+            for (int k = 0; k < 4; k++) {
+                M1[3 * k] = as[k] * e.fu;
+                M1[3 * k + 1] = 0.0;
+                M1[3 * k + 2] = as[k] * (e.uc - u);
+                M2[3 * k] = 0.0;
+                M2[3 * k + 1] = as[k] * e.fv;
+                M2[3 * k + 2] = as[k] * (e.vc - v);
+            }
+        }
+        mul_transposed_dev(e.M, 2 * n, 12, e.At, EPNP_AS);  // symmetric: its transpose is itself
+    }
+    EPNP_SYNCWARP();
+    jacobi_svd12_wave(e.At, e.W12, e.d12, lane);
+    if (lane == 0) {
+        epnp_L_6x10(e.At, e.L);
+        e.rho[0] = dist2_dev(e.cws[0], e.cws[1]);
+        e.rho[1] = dist2_dev(e.cws[0], e.cws[2]);
+        e.rho[2] = dist2_dev(e.cws[0], e.cws[3]);
+        e.rho[3] = dist2_dev(e.cws[1], e.cws[2]);
+        e.rho[4] = dist2_dev(e.cws[1], e.cws[3]);
+        e.rho[5] = dist2_dev(e.cws[2], e.cws[3]);
+    }
+    EPNP_SYNCWARP();
+}
+
+// Phase 2 (one thread per branch N = 1, 2, 3; the branches only read the work area): starting betas, five Gauss-Newton
+// steps, pose and mean reprojection error
+__device__ double epnp5_branch(const EpnpWork& e, int N, double* R /*[9]*/, double* t /*[3]*/) {
+    double betas[4];
+    epnp_betas_approx(N, e.L, e.rho, betas);
+    epnp_gauss_newton(e.L, e.rho, betas);
+    return epnp_R_and_t(e, 5, betas, R, t);
+}
+
+// Phase 3: OpenCV's choice  N = 1; if (err[2] < err[1]) N = 2; if (err[3] < err[N]) N = 3  (a NaN never wins)
+__device__ __forceinline__ int epnp5_select(const double* err /*[3]*/) {
+    int N = 0;
+    if (err[1] < err[0]) N = 1;
+    if (err[2] < err[N]) N = 2;
+    return N;
+}
+
+// all phases in one thread (host build of the tests; lane 0 semantics)
 __device__ void epnp5_dev(EpnpWork& e, const float* xyz, const float* uv, const int* idx, double fx, double fy, double cx,
                           double cy, double* R /*[9]*/, double* t /*[3]*/) {
-    const int n = 5;
-    e.fu = fx;
-    e.fv = fy;
-    e.uc = cx;
-    e.vc = cy;
-    const double ifx = 1. / fx, ify = 1. / fy;
-    for (int i = 0; i < n; i++) {
-        const int q = idx[i];
-        e.pws[3 * i] = xyz[3 * q];
-        e.pws[3 * i + 1] = xyz[3 * q + 1];
-        e.pws[3 * i + 2] = xyz[3 * q + 2];
-        const float xn = (float)(((double)uv[2 * q] - cx) * ifx), yn = (float)(((double)uv[2 * q + 1] - cy) * ify);
-        e.us[2 * i] = xn * fx + cx;
-        e.us[2 * i + 1] = yn * fy + cy;
-    }
-    epnp_choose_control_points(e, n);
-    epnp_barycentric(e, n);
-    for (int i = 0; i < n; i++) {  // fill_M
-        double* M1 = e.M + 2 * i * 12;
-        double* M2 = M1 + 12;
-        const double* as = e.alphas + 4 * i;
-        const double u = e.us[2 * i], v = e.us[2 * i + 1];
-        for (int k = 0; k < 4; k++) {
-            M1[3 * k] = as[k] * e.fu;
-            M1[3 * k + 1] = 0.0;
-            M1[3 * k + 2] = as[k] * (e.uc - u);
-            M2[3 * k] = 0.0;
-            M2[3 * k + 1] = as[k] * e.fv;
-            M2[3 * k + 2] = as[k] * (e.vc - v);
-        }
-    }
-    mul_transposed_dev(e.M, 2 * n, 12, e.At);  // symmetric: its transpose is itself
-    double d[12];
-    jacobi_svd_dev(e.At, 12, d, nullptr, 0, 12, 12);
-    epnp_L_6x10(e.At, e.L);
-    e.rho[0] = dist2_dev(e.cws[0], e.cws[1]);
-    e.rho[1] = dist2_dev(e.cws[0], e.cws[2]);
-    e.rho[2] = dist2_dev(e.cws[0], e.cws[3]);
-    e.rho[3] = dist2_dev(e.cws[1], e.cws[2]);
-    e.rho[4] = dist2_dev(e.cws[1], e.cws[3]);
-    e.rho[5] = dist2_dev(e.cws[2], e.cws[3]);
-    double best_err = 0;
-#pragma unroll 1
-    for (int N = 1; N <= 3; ++N) {
-        double betas[4], Rn[9], tn[3];
-        epnp_betas_approx(N, e.L, e.rho, betas);
-        epnp_gauss_newton(e.L, e.rho, betas);
-        const double err = epnp_R_and_t(e, n, betas, Rn, tn);
-        // OpenCV: N = 1; if (err[2] < err[1]) N = 2; if (err[3] < err[N]) N = 3  (NaN never wins, N = 1 is the default)
-        if (N == 1 || err < best_err) {
-            best_err = err;
-            for (int k = 0; k < 9; k++) R[k] = Rn[k];
-            for (int k = 0; k < 3; k++) t[k] = tn[k];
-        }
-    }
+    epnp5_prepare(e, xyz, uv, idx, fx, fy, cx, cy, 0);
+    double err[3], Rn[3][9], tn[3][3];
+    for (int N = 1; N <= 3; ++N) err[N - 1] = epnp5_branch(e, N, Rn[N - 1], tn[N - 1]);
+    const int b = epnp5_select(err);
+    for (int k = 0; k < 9; k++) R[k] = Rn[b][k];
+    for (int k = 0; k < 3; k++) t[k] = tn[b][k];
 }

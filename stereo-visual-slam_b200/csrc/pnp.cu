@@ -9,9 +9,11 @@
 // reproduced (restated and pinned against live cv2 in oracle/pnp_oracle.c):
 //   host                   the sample stream: cv::RNG((uint64)-1) multiply-with-carry, getSubset's duplicate rejection
 //                          (it depends only on n, so all `iters` samples are drawn up front)
-//   pnp_hypothesis_kernel  one CTA per sample: thread 0 runs OpenCV's 5-point EPnP in its exact arithmetic (epnp.cuh),
-//                          turns R into the (rvec, tvec) model and back as the RANSAC callback and projectPoints do;
-//                          all threads then count the inliers with projectPoints' float32 arithmetic
+//   pnp_hypothesis_kernel  one CTA per sample: OpenCV's 5-point EPnP in its exact arithmetic (epnp.cuh) -- the 12x12
+//                          Jacobi SVD rotates the independent row pairs of a wavefront on six lanes (bit-identical to
+//                          the sequential sweep), the three beta initialisations run on three warps -- then R is
+//                          turned into the (rvec, tvec) model and back as the RANSAC callback and projectPoints do
+//                          and all threads count the inliers with projectPoints' float32 arithmetic
 //                          (err = |uv - (float)proj|^2 <= (float)(thr^2), no cheirality test)
 //   pnp_refine_kernel      one CTA: RANSACPointSetRegistrator::run's sequential logic over the counts (a model is
 //                          kept iff goodCount > max(best, 4); RANSACUpdateNumIters shrinks the iteration budget, later
@@ -145,27 +147,35 @@ __global__ void __launch_bounds__(PNP_HYP_THREADS)
 pnp_hypothesis_kernel(const float* __restrict__ xyz, const float* __restrict__ uv, int n, PnpCam cam, float thr2,
                       const int* __restrict__ samples, double* __restrict__ hyp, int* __restrict__ cnt) {
     __shared__ EpnpWork work;
+    __shared__ double sRb[3][9], stb[3][3], s_err[3];
     __shared__ double sR[9], st[3];
-    __shared__ int s_cnt;
-    const int h = blockIdx.x;
-    if (threadIdx.x == 0) {
-        int idx[5];
-        for (int k = 0; k < 5; ++k) idx[k] = samples[5 * h + k];
-        double R[9], t[3], rv[3];
-        epnp5_dev(work, xyz, uv, idx, cam.fx, cam.fy, cam.cx, cam.cy, R, t);
+    __shared__ int s_cnt, s_idx[5];
+    const int h = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < 5) s_idx[tid] = samples[5 * h + tid];
+    __syncthreads();
+    // phase 1: warp 0 (lane 0 sets the 12x12 system up, six lanes rotate the independent row pairs of a wavefront)
+    if (warp == 0) epnp5_prepare(work, xyz, uv, s_idx, cam.fx, cam.fy, cam.cx, cam.cy, lane);
+    __syncthreads();
+    // phase 2: the three beta initialisations are independent: one warp each (a single lane: sequential fp64 chains)
+    if (warp < 3 && lane == 0) s_err[warp] = epnp5_branch(work, warp + 1, sRb[warp], stb[warp]);
+    __syncthreads();
+    if (tid == 0) {
+        const int b = epnp5_select(s_err);
+        double R[9], rv[3];
+        for (int k = 0; k < 9; ++k) R[k] = sRb[b][k];
         rodrigues_to_vec_dev(R, rv);  // the model RANSAC carries is (rvec, tvec) ...
         rodrigues_to_mat_dev(rv, R);  // ... and projectPoints turns it back into a matrix
         for (int k = 0; k < 9; ++k) sR[k] = R[k];
-        for (int k = 0; k < 3; ++k) st[k] = t[k];
+        for (int k = 0; k < 3; ++k) st[k] = stb[b][k];
         s_cnt = 0;
     }
     __syncthreads();
     int c = 0;
-    for (int i = threadIdx.x; i < n; i += PNP_HYP_THREADS) c += pnp_reproj_err(sR, st, cam, xyz, uv, i) <= thr2 ? 1 : 0;
+    for (int i = tid; i < n; i += PNP_HYP_THREADS) c += pnp_reproj_err(sR, st, cam, xyz, uv, i) <= thr2 ? 1 : 0;
     c = __reduce_add_sync(0xFFFFFFFFu, c);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+    if (lane == 0 && c) atomicAdd(&s_cnt, c);
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         cnt[h] = s_cnt;
         for (int k = 0; k < 9; ++k) hyp[PNP_HYP_STRIDE * h + k] = sR[k];
         for (int k = 0; k < 3; ++k) hyp[PNP_HYP_STRIDE * h + 9 + k] = st[k];

@@ -1,7 +1,9 @@
 // Host build of the DEVICE EPnP source (csrc/epnp.cuh, CUDA qualifiers defined away) so that the port can be checked
 // bit for bit against oracle/pnp_oracle.c and live cv2 on a machine without a GPU (tests/test_oracle_pnp.py).
 // Test infrastructure only.
+#define EPNP_HOST_BUILD
 #define __device__
+#define __restrict__
 #define __forceinline__ inline
 #define __noinline__
 #include "../../stereo-visual-slam_b200/csrc/epnp.cuh"
