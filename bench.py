@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -133,23 +133,26 @@ def run_reference(args, rank, world):
     s = pkg.synth
     P1, P2 = s.stereo_projection_matrices()
     sample = 4  # stereo pairs per step: a bounded sample of the batch workload
+    nfeat = 4000 if args.config == 3 else NFEAT
     L, R = make_batch(pkg, sample, 0)
     for _ in range(max(args.warmup, 1)):
-        cv2_frontend(cv2, L[0], R[0], P1, P2)
+        cv2_frontend(cv2, L[0], R[0], P1, P2, nfeat)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for i in range(sample):
-            cv2_frontend(cv2, L[i], R[i], P1, P2)
+            cv2_frontend(cv2, L[i], R[i], P1, P2, nfeat)
     dt = time.perf_counter() - t0
     fps = args.steps * sample / dt
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "pairs_per_step": sample},
+            "config": {"workload": WORKLOAD if args.config != 3 else
+                       "configs[3]: batched 64 synthetic 1241x376 stereo pairs, 4000 ORB kp, frame-parallel over the GPUs, "
+                       "detect(L,R)+BF-Hamming cross-check match+DLT triangulate",
+                       "pairs_per_step": sample, "nfeatures": nfeat},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": ncores, "kind": "port",
                              "sample": f"{sample} stereo pairs/step x {args.steps} steps; live cv2 {cv2.__version__} "
-                                       "(cv::ORB(2000) detectAndCompute x2, BFMatcher crossCheck + gate, "
+                                       f"(cv::ORB({nfeat}) detectAndCompute x2, BFMatcher crossCheck + gate, "
                                        "triangulatePoints) = the OpenCV calls of the reference's VO path, "
                                        f"cv2.setNumThreads({ncores})"},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -174,15 +177,120 @@ def algorithmic_bytes(n_images: int, n_pairs: int, n_kp: float, n_match: float):
     }
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the ncu --set full capture under profiles/
-# (r01_v9_ncu_full_frontend_summary.json: 64 images / 32 pairs per launch), divided by the units of that launch.
-NCU_TRAFFIC_PER_UNIT = {
-    "fast_kernel": (93.319168e6 + 9.874688e6) / 64, "blur_kernel": (94.490368e6 + 61.008896e6) / 64,
-    "describe_kernel": (151.682048e6 + 8.757504e6) / 64, "harris_select_kernel": (85.254400e6 + 4.321536e6) / 64,
-    "hamming_argmin_kernel": 4.623104e6 / 32, "crosscheck_gate_compact_kernel": 0.529152e6 / 32,
-    "triangulate_kernel": 2.209536e6 / 32,
-}
-NCU_TRAFFIC_SOURCE = "profiles/r01_v9_ncu_full_frontend_summary.json"
+def _to_bytes(txt):
+    """'93.319168 Mbyte' -> bytes"""
+    v, u = txt.split()[:2]
+    return float(v) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+
+
+def load_ncu_summary(kind="frontend"):
+    """Newest profiles/rNN_vM_ncu_full_<kind>_summary.json (ncu --set full, tools/ncu_summary.py): per kernel the DRAM
+    bytes per UNIT of work (image or pair) of that capture and the pipe percentages -- roofline.traffic and the pipe
+    figures are read from here, never from literals."""
+    import glob
+    import re
+    best = None
+    for f in glob.glob(os.path.join(ROOT, "profiles", f"r*_v*_ncu_full_{kind}_summary.json")):
+        m = re.search(r"r(\d+)_v(\d+)_", os.path.basename(f))
+        key = (int(m.group(1)), int(m.group(2)))
+        if best is None or key > best[0]:
+            best = (key, f)
+    if best is None:
+        return None
+    d = json.load(open(best[1]))
+    m = re.search(r"(\d+) stereo pairs", d.get("command", ""))
+    pairs = int(m.group(1)) if m else 32
+    per_pair = ("hamming_argmin_kernel", "crosscheck_gate_compact_kernel", "triangulate_matches_kernel", "triangulate_kernel")
+    out = {"source": os.path.relpath(best[1], ROOT), "pairs_per_launch": pairs, "kernels": {}}
+    acc = {}
+    for l in d["launches"]:
+        k = l["kernel"]
+        a = acc.setdefault(k, {"n": 0, "bytes": 0.0, "pipes": {}})
+        a["n"] += 1
+        a["bytes"] += _to_bytes(l["dram__bytes_read.sum"]) + _to_bytes(l["dram__bytes_write.sum"])
+        for name, key in (("alu_pipe_pct", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                          ("lsu_pipe_pct", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+                          ("xu_pipe_pct", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+                          ("issue_active_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                          ("dram_pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")):
+            if key in l:
+                a["pipes"][name] = a["pipes"].get(name, 0.0) + float(l[key].split()[0])
+    for k, a in acc.items():
+        units = pairs if k in per_pair else 2 * pairs
+        name = "triangulate_kernel" if k == "triangulate_matches_kernel" else k
+        # resize runs once per level: bytes of all its launches belong to one pass over the image
+        tot = a["bytes"] if k == "resize_level_kernel" else a["bytes"] / a["n"]
+        out["kernels"][name] = {"dram_bytes_per_unit": tot / units,
+                                "pipes": {p: round(v / a["n"], 1) for p, v in a["pipes"].items()}}
+    return out
+
+
+def pin_to_gpu_numa(index: int):
+    """Pin this process (and its first-touch pinned host buffers) to the CPUs of the NUMA node the GPU hangs off:
+    with 8 ranks the host staging of the e2e leg otherwise crosses sockets.  Returns a short description."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = "0000:" + bus.split(":", 1)[1]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return "numa node unknown (single node)"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"numa node {node}, {len(cpus)} cpus"
+        return f"numa node {node}: no allowed cpus"
+    except Exception as ex:  # best effort
+        return f"not pinned ({type(ex).__name__})"
+
+
+def frontend_fps(pkg, torch, ctx, dev, stream, dist, world, B, nfeat, cap, steps, warmup, seed0):
+    """Device-resident stereo frames/s of one workload (CUDA events on the launching stream, max over ranks)."""
+    P1, P2 = pkg.synth.stereo_projection_matrices()
+    sets = []
+    for k in range(2):
+        L, R = make_batch(pkg, B, seed0 + 17 * k)
+        sets.append((torch.from_numpy(L).to(dev), torch.from_numpy(R).to(dev)))
+    d_kp = torch.zeros((2 * B, cap, 7), dtype=torch.int32, device=dev)
+    d_desc = torch.zeros((2 * B, cap, 32), dtype=torch.uint8, device=dev)
+    d_nkp = torch.zeros(2 * B, dtype=torch.int32, device=dev)
+    d_m = torch.zeros((B, cap, 4), dtype=torch.int32, device=dev)
+    d_nm = torch.zeros(B, dtype=torch.int32, device=dev)
+    d_xyz = torch.zeros((B, cap, 3), dtype=torch.float32, device=dev)
+    d_fl = torch.zeros((B, cap), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step(i):
+        dl, dr = sets[i & 1]
+        ctx.stereo_frontend_dev(dl, dr, B, W, H, W, W * H, P1, P2, None, d_kp, d_desc, d_nkp, d_m, d_nm, d_xyz, d_fl,
+                                nfeatures=nfeat)
+    with torch.cuda.stream(stream):
+        for i in range(warmup):
+            step(i)
+    ctx.orb_last_flags(2 * B)
+    torch.cuda.synchronize(dev)
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        flush.fill_(1)
+        e0.record(stream)
+        for i in range(steps):
+            step(i)
+        e1.record(stream)
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"stereo_frames_per_s": world * B * steps / (ms * 1e-3), "ms_per_step": ms / steps, "pairs_per_gpu": B,
+            "pairs_total": world * B, "nfeatures": nfeat, "steps": steps,
+            "mean_keypoints_per_image": float(d_nkp.float().mean()), "mean_matches_per_pair": float(d_nm.float().mean())}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -196,8 +304,15 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    B = args.pairs
-    cap = 2304
+    numa = pin_to_gpu_numa(local_rank)
+    if args.config == 3:
+        # BASELINE.json configs[3]: 64 pairs at 4000 keypoints, frame-parallel over the GPUs of the box (strong scaling)
+        B, NFEAT, cap = max(1, 64 // world), 4000, 4608
+        workload = ("configs[3]: batched 64 synthetic 1241x376 stereo pairs, 4000 ORB kp, frame-parallel over the GPUs, "
+                    "detect(L,R)+BF-Hamming cross-check match+DLT triangulate")
+    else:
+        B, NFEAT, cap = args.pairs, 2000, 2304
+        workload = WORKLOAD
     ctx = pkg.Context(device=local_rank, max_images=2 * B, max_keypoints=cap, max_ba_poses=64, max_ba_points=32768,
                       max_ba_obs=262144)
     stream = torch.cuda.Stream(device=dev)
@@ -315,6 +430,20 @@ def run_ours(args, rank, world, local_rank):
         except Exception as ex:  # the BA numbers are secondary; never lose the headline line
             ba_block = {"error": repr(ex)}
 
+    # ---- BASELINE.json configs[3] beside the headline: 64 pairs at 4000 keypoints over all ranks ------------------
+    cfg3_block = None
+    if args.config != 3 and args.cfg3:
+        try:
+            ctx3 = pkg.Context(device=local_rank, max_images=2 * max(1, 64 // world), max_keypoints=4608, max_ba_poses=0,
+                               max_ba_points=0, max_ba_obs=0)
+            ctx3.set_stream(stream.cuda_stream)
+            cfg3_block = frontend_fps(pkg, torch, ctx3, dev, stream, dist, world, max(1, 64 // world), 4000, 4608, 10, 3,
+                                      1000 + 100 * rank)
+            cfg3_block["scaling"] = "strong (64 pairs in total, frame-parallel, no data-path collective)"
+            ctx3.close()
+        except Exception as ex:
+            cfg3_block = {"error": repr(ex)}
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -329,15 +458,16 @@ def run_ours(args, rank, world, local_rank):
     top = max(share, key=share.get)
     avg_ms = ktimes[top][0] / ktimes[top][1]
     achieved = alg.get(top, 0.0) / (avg_ms * 1e-3) / 1e9
+    ncu = load_ncu_summary("frontend")
+    per_pair = ("hamming_argmin_kernel", "triangulate_kernel", "crosscheck_gate_compact_kernel")
+    nk = (ncu or {}).get("kernels", {}).get(top)
     roof = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": (NCU_TRAFFIC_PER_UNIT[top] * (B if top in ("hamming_argmin_kernel", "triangulate_kernel",
-                                                                  "crosscheck_gate_compact_kernel") else 2 * B)
-                        if top in NCU_TRAFFIC_PER_UNIT else None),
-            "traffic_source": NCU_TRAFFIC_SOURCE + " (per-unit DRAM bytes of the capture x units per launch here)",
+            "traffic": nk["dram_bytes_per_unit"] * (B if top in per_pair else 2 * B) if nk else None,
+            "traffic_source": (ncu["source"] + " (dram__bytes_read+write per unit of the newest ncu --set full capture x "
+                               "units per launch here)") if ncu else None,
             "peak_source": peak_src, "avg_launch_ms": avg_ms,
-            "ncu_pipes": {"source": NCU_TRAFFIC_SOURCE, "fast_kernel": {"alu_pipe_pct": 72.4, "issue_active_pct": 71.4,
-                                                                         "dram_pct": 1.8},
-                          "note": "the dominant kernel is integer-ALU bound (packed 16x2 segment test), not HBM bound"},
+            "ncu_pipes": {"source": ncu["source"] if ncu else None, top: nk["pipes"] if nk else None,
+                          "note": "pipe utilisation (% of peak, sustained active) of the dominant kernel in that capture"},
             "algorithmic_bytes_per_launch": alg.get(top, 0.0),
             "kernel_time_share": {k: round(v / tot_k, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
             "note": "per-kernel CUDA-event times measured live in this run, right after the timed region, with every launch "
@@ -346,10 +476,15 @@ def run_ours(args, rank, world, local_rank):
     # Hamming kernel: the north star asks for its HBM fraction; it is POPC-pipe bound by construction
     if "hamming_argmin_kernel" in ktimes:
         hm = ktimes["hamming_argmin_kernel"][0] / ktimes["hamming_argmin_kernel"][1]
+        hk = (ncu or {}).get("kernels", {}).get("hamming_argmin_kernel")
         roof["hamming"] = {"hbm_GBps": alg["hamming_argmin_kernel"] / (hm * 1e-3) / 1e9,
                            "hbm_frac": alg["hamming_argmin_kernel"] / (hm * 1e-3) / 1e9 / peak,
-                           "popc_Tops": B * n_kp_mean * n_kp_mean * 8 / (hm * 1e-3) / 1e12,
+                           # 256-bit distance = 8 XOR words, carry-save compressed to 5 POPC (match.cu)
+                           "popc_issued_Tops": B * n_kp_mean * n_kp_mean * 5 / (hm * 1e-3) / 1e12,
                            "popc_pipe_peak_Tops": 148 * 16 * (clk["sm_mhz"] or 1965.0) * 1e6 / 1e12,
+                           "ncu_pipes": hk["pipes"] if hk else None,
+                           "bound": "integer ALU (LOP3 carry-save + min/compare) with the POPC (XU) pipe second; HBM "
+                                    "fraction is tiny by construction: brute force has N/4 ops per byte (SURVEY 8d)",
                            "avg_launch_ms": hm}
 
     # ---- CPU baseline beside it (bounded sample, all host threads) ----------------------------------------
@@ -357,10 +492,10 @@ def run_ours(args, rank, world, local_rank):
     ncores = os.cpu_count() or 1
     cv2.setNumThreads(ncores)
     Ls, Rs = sets[0][0].numpy(), sets[0][1].numpy()
-    cv2_frontend(cv2, Ls[0], Rs[0], P1, P2)
+    cv2_frontend(cv2, Ls[0], Rs[0], P1, P2, NFEAT)
     n_cpu, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < args.cpu_seconds and n_cpu < B:
-        cv2_frontend(cv2, Ls[n_cpu], Rs[n_cpu], P1, P2)
+        cv2_frontend(cv2, Ls[n_cpu], Rs[n_cpu], P1, P2, NFEAT)
         n_cpu += 1
     cpu_fps = n_cpu / (time.perf_counter() - t0)
     # the same path on one thread and stage by stage: median of 5 on pair 0
@@ -380,15 +515,16 @@ def run_ours(args, rank, world, local_rank):
               "orb_compute_ms": _med(lambda: orb.compute(Ls[0], kl0)),
               "bf_match_ms": _med(lambda: bf.match(dl0, dr0))}
     cv2.setNumThreads(1)
-    stages_1t = {"threads": 1, "frontend_pair_ms": _med(lambda: cv2_frontend(cv2, Ls[0], Rs[0], P1, P2), 3),
+    stages_1t = {"threads": 1, "frontend_pair_ms": _med(lambda: cv2_frontend(cv2, Ls[0], Rs[0], P1, P2, NFEAT), 3),
                  "bf_match_ms": _med(lambda: bf.match(dl0, dr0), 3)}
     cv2.setNumThreads(ncores)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.config == 3 else "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "pairs_per_step_per_gpu": B, "nfeatures": NFEAT, "anms": "off (configs[1])",
+            "config": {"workload": workload,
+                       "pairs_per_step_per_gpu": B, "nfeatures": NFEAT, "anms": "off (configs[1])", "host_affinity": numa,
                        "l2": "two alternating input sets + 256 MiB flush before the timed region; per-step working "
                              "set (inputs+pyramids+blurred) ~%.0f MB > 126 MB L2" % (2 * B * 3.7),
                        "mean_keypoints_per_image": n_kp_mean, "mean_matches_per_pair": n_m_mean,
@@ -399,11 +535,13 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
             "cpu_baseline": {"value": cpu_fps, "unit": UNIT, "cores": ncores, "kind": "port",
                              "sample": f"{n_cpu} stereo pairs of the same batch through the oracle's cv2 "
-                                       f"{cv2.__version__} path (ORB(2000) x2, BFMatcher crossCheck + gate, "
+                                       f"{cv2.__version__} path (ORB({NFEAT}) x2, BFMatcher crossCheck + gate, "
                                        f"triangulatePoints), cv2.setNumThreads({ncores})",
                              "stages_ms": stages, "single_thread": stages_1t}}
     if ba_block is not None:
         line["ba"] = ba_block
+    if cfg3_block is not None:
+        line["configs3_64pairs_4000kp"] = cfg3_block
     try:
         line["pnp"] = bench_pnp(ctx, pkg)
     except Exception as ex:
@@ -447,7 +585,10 @@ def bench_vo_loop(pkg):
         for name, extra in (("reference_defaults_dense", []),   # dense StereoSGBM depth is the drop-in layer's default
                             ("keyframe_every_frame_dense", ["--nfeatures", "1000", "--anms", "110"]),
                             # the north star's sparse-stereo depth (ORB on both images + L<->R matching + DLT) instead of SGBM
-                            ("keyframe_every_frame_sparse", ["--sparse", "--nfeatures", "1000", "--anms", "110"])):
+                            ("keyframe_every_frame_sparse", ["--sparse", "--nfeatures", "1000", "--anms", "110"]),
+                            # BASELINE.json configs[2]: the stream at 2000 keypoints per frame (no ANMS thinning); its
+                            # K=10 / L=5000 BA window is timed in the "ba" block (cfg3_K10_L5000.reference_call_sequence_ms)
+                            ("configs2_stream_2000kp", ["--nfeatures", "2000", "--anms", "0"])):
             with tempfile.TemporaryDirectory() as w:
                 r = subprocess.run([exe, d + "/", str(n), *extra], cwd=w, capture_output=True, text=True, timeout=300)
             rows = [l.split() for l in r.stdout.splitlines() if l.startswith("frame ")]
@@ -599,6 +740,14 @@ def bench_ba(ctx, pkg, args, torch, dev, dist, rank, world, stream):
                "e2e_iters_per_s": world * r["iterations"] / (e2e_ms * 1e-3),
                "kernel_iters_per_s": world * r["iterations"] / (kms * 1e-3),
                "kernel_ms": kms, "e2e_ms": e2e_ms, "chi2": [r["chi2_initial"], r["chi2_final"]]}
+        if name.startswith("cfg3"):
+            # the reference's per-keyframe call sequence on this window (run_vslam.cpp:61-70): optimize_map(5), (5), (10)
+            # and optimize_pose_only(10), four host-buffer C-ABI calls
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                for nit2, po in ((5, False), (5, False), (10, False), (10, True)):
+                    ctx.ba_optimize(*a, num_iterations=nit2, pose_only=po)
+            rec["reference_call_sequence_ms"] = (time.perf_counter() - t0) / reps * 1e3
         if world > 1:
             # strong scaling: one window, landmarks sharded over the ranks
             shards = pkg.sharding.landmark_shards(p["obs_point"], nl, world)
@@ -638,7 +787,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=128, help="stereo pairs per step per GPU")
+    ap.add_argument("--pairs", type=int, default=256, help="stereo pairs per step per GPU (configs[1] batched)")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 3],
+                    help="headline workload: BASELINE.json configs[1] (batched, 2000 kp) or configs[3] (64 pairs, 4000 kp)")
+    ap.add_argument("--no-cfg3", dest="cfg3", action="store_false")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-ba", dest="ba", action="store_false")

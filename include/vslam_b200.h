@@ -331,6 +331,12 @@ int vslam_ba_session_begin(vslam_ctx* ctx, int n_poses, const double* poses, int
 int vslam_ba_session_phase(vslam_ctx* ctx, int phase, double value);
 int vslam_ba_session_trial_done(vslam_ctx* ctx, int accept);
 int vslam_ba_session_end(vslam_ctx* ctx, double* poses, double* points, double* chi2_per_obs, uint8_t* point_inlier);
+/* Measurement probe (the north star's "tensor cores only for the dense J^T J camera-block GEMM"): after phase SCHUR of a
+ * session that covers ALL landmarks, form the same product -(Hpl Hll^-1 Hpl^T) as ONE dense fp64 SYRK on the tensor
+ * cores (DMMA m8n8k4) into d_S_dense (n x n device doubles, n = 6 * n_poses, upper triangle written) and report the
+ * device times of the dense-operand fill and of the SYRK.  The session's sparse result is in r2 for comparison.
+ * optimize_map's BlockSolver_6_3 (optimization.cpp:111-120) is the call both variants accelerate. */
+int vslam_ba_session_schur_dense(vslam_ctx* ctx, double* d_S_dense, float* ms_fill, float* ms_syrk);
 
 #ifdef __cplusplus
 }

@@ -1110,6 +1110,8 @@ struct BaState {
     BaParams* sess;
     int sess_open, sess_cur, sess_trials;
     double *sess_r1, *sess_r2, *sess_r3;
+    double* d_dense;  // Y of the dense-SYRK probe (allocated on first use)
+    size_t dense_bytes;
 };
 
 __global__ void ba_phase_kernel(const __grid_constant__ BaParams P, int phase, double lambda, int cur, int slot, double* r1,
@@ -1182,6 +1184,7 @@ void vslam_ba_free(vslam_ctx* ctx) {
     cudaFree(b->d_bs); cudaFree(b->d_x); cudaFree(b->d_dbl); cudaFree(b->d_U); cudaFree(b->d_block_flag); cudaFree(b->d_pose_start); cudaFree(b->d_pose_obs); cudaFree(b->d_obs_of); cudaFree(b->d_chi2); cudaFree(b->d_obs_pose);
     cudaFree(b->d_obs_point); cudaFree(b->d_obs_orig); cudaFree(b->d_lm_start); cudaFree(b->d_inlier); cudaFree(b->d_sc);
     cudaFreeHost(b->h_sc);
+    if (b->d_dense) cudaFree(b->d_dense);
     free(b->sess);
     free(b);
     ctx->ba = nullptr;
@@ -1470,6 +1473,147 @@ extern "C" int vslam_ba_session_end(vslam_ctx* ctx, double* poses, double* point
     if (point_inlier) VSLAM_CUDA(ctx, cudaMemcpyAsync(point_inlier, b->d_inlier, (size_t)P.L, cudaMemcpyDeviceToHost, s));
     VSLAM_CUDA(ctx, cudaStreamSynchronize(s));
     b->sess_open = 0;
+    return VSLAM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// N1 probe: the reduced camera system as ONE dense fp64 SYRK on the tensor cores (DMMA, mma.sync.m8n8k4.f64), to be
+// timed beside the sparse per-block formation above.  With Dinv_l = C_l C_l^T (3x3 Cholesky) and Y = [Hpl_l C_l]_l
+// (6K x 3L, dense storage, zero where pose k does not see landmark l):  sum_l Hpl_l Dinv_l Hpl_l^T = Y Y^T.
+// BlockSolver_6_3 (optimization.cpp:111-120) forms the same product block-sparsely; the dense form spends
+// (6K)^2 * 3L * 2 flops (10.8 GFLOP at K=50 / L=20000 against 77 MFLOP sparse).
+// ---------------------------------------------------------------------------------------------------------------
+#define DS_TM 64   // output tile (rows = cols)
+#define DS_TK 32   // k chunk staged in shared memory
+#define DS_LD 36   // row stride in doubles: 36 mod 16 == 4 -> the 16 lanes of a half-warp (4 rows x 4 k) hit 16 banks
+
+__global__ void ba_dense_fill_kernel(const __grid_constant__ BaParams P, double* __restrict__ Y, int ldY) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_obs) return;
+    const int k = P.obs_pose[i], l = P.obs_point[i];
+    const double* d = P.Dinv + 9 * (size_t)l;
+    // lower Cholesky factor of the SPD 3x3 block
+    const double c00 = sqrt(d[0]), c10 = d[3] / c00, c20 = d[6] / c00;
+    const double c11 = sqrt(d[4] - c10 * c10), c21 = (d[7] - c20 * c10) / c11;
+    const double c22 = sqrt(d[8] - c20 * c20 - c21 * c21);
+    const double* B = P.Hpl + 18 * (size_t)i;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        double* y = Y + (size_t)(6 * k + a) * ldY + 3 * l;
+        y[0] = B[a * 3] * c00 + B[a * 3 + 1] * c10 + B[a * 3 + 2] * c20;
+        y[1] = B[a * 3 + 1] * c11 + B[a * 3 + 2] * c21;
+        y[2] = B[a * 3 + 2] * c22;
+    }
+}
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// S(upper tiles) -= Y Y^T.  grid = (tile pairs I <= J, k slices); 4 warps, warp (wm, wn) owns a 32x32 sub-tile = 4x4
+// DMMA tiles.  Fragment layout of m8n8k4: A[row = lane/4][k = lane%4], B[k = lane%4][col = lane/4],
+// C[row = lane/4][col = 2*(lane%4) + {0,1}].
+__global__ void __launch_bounds__(128)
+ba_dense_syrk_kernel(const double* __restrict__ Y, int ldY, int n, int tiles, int chunks_per_slice, double* __restrict__ S) {
+    __shared__ double As[DS_TM * DS_LD], Bs[DS_TM * DS_LD];
+    int I = 0, rem = blockIdx.x;
+    while (rem >= tiles - I) { rem -= tiles - I; ++I; }
+    const int J = I + rem;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1, g = lane >> 2, t = lane & 3;
+    const int n_chunks = ldY / DS_TK;
+    const int c_begin = blockIdx.y * chunks_per_slice, c_end = min(n_chunks, c_begin + chunks_per_slice);
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    const double* Bt = (I == J) ? As : Bs;
+    for (int ch = c_begin; ch < c_end; ++ch) {
+        const size_t k0 = (size_t)ch * DS_TK;
+        for (int e = tid; e < DS_TM * (DS_TK / 2); e += 128) {  // 16-byte loads, k contiguous
+            const int row = e / (DS_TK / 2), c2 = e % (DS_TK / 2);
+            const int rI = I * DS_TM + row, rJ = J * DS_TM + row;
+            double2 va = make_double2(0.0, 0.0), vb = make_double2(0.0, 0.0);
+            if (rI < n) va = *reinterpret_cast<const double2*>(Y + (size_t)rI * ldY + k0 + 2 * c2);
+            if (I != J && rJ < n) vb = *reinterpret_cast<const double2*>(Y + (size_t)rJ * ldY + k0 + 2 * c2);
+            As[row * DS_LD + 2 * c2] = va.x;
+            As[row * DS_LD + 2 * c2 + 1] = va.y;
+            if (I != J) {
+                Bs[row * DS_LD + 2 * c2] = vb.x;
+                Bs[row * DS_LD + 2 * c2 + 1] = vb.y;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < DS_TK; kk += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                a[q] = As[(wm * 32 + q * 8 + g) * DS_LD + kk + t];
+                b[q] = Bt[(wn * 32 + q * 8 + g) * DS_LD + kk + t];
+            }
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = I * DS_TM + wm * 32 + mi * 8 + g, c = J * DS_TM + wn * 32 + ni * 8 + 2 * t + h;
+                if (r < n && c < n && c >= r && acc[mi][ni][h] != 0.0) atomicAdd(&S[(size_t)r * n + c], -acc[mi][ni][h]);
+            }
+}
+
+// After vslam_ba_session_phase(SCHUR) of an open session covering ALL landmarks: forms -(Hpl Hll^-1 Hpl^T) densely into
+// d_S_dense (n x n device doubles, upper triangle r <= c written, the rest zero) and reports the device time of the
+// two kernels.  The session's own (sparse) result stays in its r2 buffer for comparison.
+extern "C" int vslam_ba_session_schur_dense(vslam_ctx* ctx, double* d_S_dense, float* ms_fill, float* ms_syrk) {
+    if (!ctx || !ctx->ba || !ctx->ba->sess_open || !d_S_dense) return VSLAM_E_INVALID;
+    BaState* b = ctx->ba;
+    BaParams P = *b->sess;
+    if (P.pose_only || P.has_dup || P.shard_L0 != 0 || P.shard_L1 != P.L || P.n_obs <= 0) return VSLAM_E_INVALID;
+    const int n = P.n;
+    const int ldY = ceil_div(3 * P.L, DS_TK) * DS_TK;
+    const size_t bytes = (size_t)n * ldY * sizeof(double);
+    if (b->dense_bytes < bytes) {
+        if (b->d_dense) cudaFree(b->d_dense);
+        b->d_dense = nullptr;
+        b->dense_bytes = 0;
+        VSLAM_CUDA(ctx, cudaMalloc(&b->d_dense, bytes));
+        b->dense_bytes = bytes;
+    }
+    cudaStream_t s = ctx->stream;
+    cudaEvent_t e0, e1, e2;
+    VSLAM_CUDA(ctx, cudaEventCreate(&e0));
+    VSLAM_CUDA(ctx, cudaEventCreate(&e1));
+    VSLAM_CUDA(ctx, cudaEventCreate(&e2));
+    VSLAM_CUDA(ctx, cudaMemsetAsync(d_S_dense, 0, (size_t)n * n * sizeof(double), s));
+    VSLAM_CUDA(ctx, cudaEventRecord(e0, s));
+    VSLAM_CUDA(ctx, cudaMemsetAsync(b->d_dense, 0, bytes, s));
+    ba_dense_fill_kernel<<<ceil_div(P.n_obs, 256), 256, 0, s>>>(P, b->d_dense, ldY);
+    VSLAM_LAUNCH_CHECK(ctx, "ba_dense_fill_kernel");
+    VSLAM_CUDA(ctx, cudaEventRecord(e1, s));
+    const int tiles = ceil_div(n, DS_TM), pairs = tiles * (tiles + 1) / 2, n_chunks = ldY / DS_TK;
+    int slices = max(1, (4 * ctx->num_sms) / pairs);  // ~4 CTAs per SM
+    slices = min(slices, n_chunks);
+    const int cps = ceil_div(n_chunks, slices);
+    ba_dense_syrk_kernel<<<dim3(pairs, ceil_div(n_chunks, cps)), 128, 0, s>>>(b->d_dense, ldY, n, tiles, cps, d_S_dense);
+    VSLAM_LAUNCH_CHECK(ctx, "ba_dense_syrk_kernel");
+    VSLAM_CUDA(ctx, cudaEventRecord(e2, s));
+    VSLAM_CUDA(ctx, cudaEventSynchronize(e2));
+    float a = 0, c = 0;
+    cudaEventElapsedTime(&a, e0, e1);
+    cudaEventElapsedTime(&c, e1, e2);
+    if (ms_fill) *ms_fill = a;
+    if (ms_syrk) *ms_syrk = c;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     return VSLAM_OK;
 }
 

@@ -98,6 +98,7 @@ SIGNATURES = {
     "vslam_ba_session_phase": (_i, [_vp, _i, _d]),
     "vslam_ba_session_trial_done": (_i, [_vp, _i]),
     "vslam_ba_session_end": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "vslam_ba_session_schur_dense": (_i, [_vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "vslam_sgbm_default_params": (None, [C.POINTER(SgbmParams)]),
     "vslam_sgbm_compute": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_longlong, C.POINTER(SgbmParams), _vp, _vp]),
     "vslam_sgbm_compute_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_longlong, C.POINTER(SgbmParams), _vp, _vp]),
@@ -459,6 +460,13 @@ class GpuBaSession:
 
     def trial_done(self, accept: bool):
         self.ctx.check(self.ctx.lib.vslam_ba_session_trial_done(self.ctx.h, int(accept)), "vslam_ba_session_trial_done")
+
+    def schur_dense(self, d_S):
+        """N1 probe: dense DMMA SYRK form of the Schur product into the device tensor d_S (n x n); returns (ms_fill, ms_syrk)"""
+        a, b = C.c_float(0), C.c_float(0)
+        self.ctx.check(self.ctx.lib.vslam_ba_session_schur_dense(self.ctx.h, _ptr(d_S), C.byref(a), C.byref(b)),
+                       "vslam_ba_session_schur_dense")
+        return a.value, b.value
 
     def end(self):
         poses = np.zeros_like(self.poses); points = np.zeros_like(self.points)

@@ -146,3 +146,37 @@ def test_golden_ba(pkg, ba_ctx):
     assert np.abs(r["poses"] - g["poses"]).max() / np.abs(g["poses"]).max() < REL_TOL
     assert (np.abs(r["points"] - g["points"]).max(axis=1) / np.linalg.norm(g["points"], axis=1)).max() < REL_TOL
     assert np.array_equal(r["point_inlier"], g["point_inlier"])
+
+
+def _dense_vs_sparse(pkg, seed, nk, nl, nobs):
+    """runs BUILD + SCHUR of a one-shard session, then the dense DMMA SYRK probe; returns (S_sparse, S_dense, ms)"""
+    import torch
+    p = pkg.synth.synth_ba_problem(seed, nk, nl, n_obs_exact=nobs)
+    ctx = pkg.Context(device=0, max_images=0, max_width=0, max_height=0, max_keypoints=1, max_ba_poses=64,
+                      max_ba_points=32768, max_ba_obs=262144)
+    n = 6 * nk
+    n1, n2, n3 = pkg.ffi.ba_reduce_sizes(nk)
+    r1, r2, r3 = (torch.zeros(k, dtype=torch.float64, device="cuda:0") for k in (n1, n2, n3))
+    S_dense = torch.zeros(n * n, dtype=torch.float64, device="cuda:0")
+    torch.cuda.synchronize()
+    sess = ctx.ba_session(p, (0, nl), r1, r2, r3, num_iterations=1)
+    sess.phase(sess.BUILD)
+    sess.phase(sess.SCHUR, 1e-3)
+    ms = sess.schur_dense(S_dense)
+    torch.cuda.synchronize()
+    Ss, Sd = r2[:n * n].cpu().numpy().reshape(n, n), S_dense.cpu().numpy().reshape(n, n)
+    sess.end()
+    ctx.close()
+    return Ss, Sd, ms
+
+
+@pytest.mark.parametrize("seed,nk,nl,nobs", [(51, 10, 1000, None), (52, 16, 2500, None), (43, 50, 20000, 100000)])
+def test_dense_dmma_schur_equals_sparse(pkg, seed, nk, nl, nobs):
+    """row N1: -(Hpl Hll^-1 Hpl^T) formed as one dense fp64 tensor-core SYRK equals the block-sparse formation
+    (upper triangle; the sparse path fills whole diagonal blocks)"""
+    Ss, Sd, ms = _dense_vs_sparse(pkg, seed, nk, nl, nobs)
+    iu = np.triu_indices(len(Ss))
+    scale = np.abs(Ss[iu]).max()
+    assert scale > 0
+    assert np.abs(Ss[iu] - Sd[iu]).max() / scale < 1e-11
+    assert np.all(Sd[np.tril_indices(len(Ss), -1)] == 0)
