@@ -772,6 +772,38 @@ def bench_ba(ctx, pkg, args, torch, dev, dist, rank, world, stream):
                               "allreduce_bytes_per_trial": 8 * (n2 + n3),
                               "pose_rel_diff_vs_single_gpu": float(np.abs(sp - r["poses"]).max() / np.abs(r["poses"]).max())}
         if rank == 0:
+            try:   # device-side phase profile of the last call and, for the large window, the dense DMMA Schur probe
+                ph = ctx.ba_last_phase_us()
+                tr = max(r["trials"], 1)
+                rec["phase_us_per_trial"] = {k: round(v / tr, 2) for k, v in ph.items()}
+                if name.startswith("cfg5"):
+                    n = 6 * nk
+                    n1, n2, n3 = pkg.ffi.ba_reduce_sizes(nk)
+                    with torch.cuda.stream(stream):
+                        q1, q2, q3 = (torch.zeros(k, dtype=torch.float64, device=dev) for k in (n1, n2, n3))
+                        Sd = torch.zeros(n * n, dtype=torch.float64, device=dev)
+                    torch.cuda.synchronize(dev)
+                    sess = ctx.ba_session(p, (0, nl), q1, q2, q3, num_iterations=1)
+                    sess.phase(sess.BUILD)
+                    sess.phase(sess.SCHUR, 1e-3)
+                    best = None
+                    for _ in range(3):
+                        m = sess.schur_dense(Sd)
+                        best = m if best is None or m[1] < best[1] else best
+                    torch.cuda.synchronize(dev)
+                    Ss = q2[:n * n].reshape(n, n)
+                    iu = torch.triu(torch.ones(n, n, dtype=torch.bool, device=dev))
+                    diff = float((Ss - Sd.reshape(n, n))[iu].abs().max() / Ss[iu].abs().max())
+                    sess.end()
+                    flops = 2.0 * n * n * 3 * nl
+                    rec["dense_dmma_schur"] = {
+                        "what": "the same Schur product as ONE dense fp64 SYRK on the tensor cores (mma.sync.m8n8k4.f64)",
+                        "fill_ms": best[0], "syrk_ms": best[1], "dense_flops": flops,
+                        "upper_tile_TFLOPs": 0.5 * flops * 1.2 / (best[1] * 1e-3) / 1e12,
+                        "sparse_schur_us": rec["phase_us_per_trial"].get("schur"),
+                        "sparse_flops": "77e6 (SURVEY 8d)", "max_rel_diff_vs_sparse": diff}
+            except Exception as ex:
+                rec["dense_dmma_schur"] = {"error": repr(ex)}
             from oracle import ba_oracle
             t0 = time.perf_counter()
             o = ba_oracle.optimize(*a, num_iterations=nit)
