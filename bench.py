@@ -730,6 +730,7 @@ def bench_ba(ctx, pkg, args, torch, dev, dist, rank, world, stream):
         dt = (time.perf_counter() - t0) / reps
         kt = ctx.timing_read().get("ba_lm_kernel", (0.0, 1))
         ctx.timing_enable(False)
+        phase_us = ctx.ba_last_phase_us()   # device-side profile of the last of those calls
         kms = kt[0] / max(kt[1], 1)
         tt = torch.tensor([dt * 1e3, kms], dtype=torch.float64, device=dev)
         if dist is not None:
@@ -771,11 +772,50 @@ def bench_ba(ctx, pkg, args, torch, dev, dist, rank, world, stream):
                               "iters_per_s": res["iterations"] / float(ts[0]), "ms_per_iter": float(ts[0]) * 1e3 / res["iterations"],
                               "allreduce_bytes_per_trial": 8 * (n2 + n3),
                               "pose_rel_diff_vs_single_gpu": float(np.abs(sp - r["poses"]).max() / np.abs(r["poses"]).max())}
+        if world > 1:
+            # strong scaling, device-side: ONE process (rank 0) drives all GPUs of the box through
+            # vslam_ba_optimize_multi -- persistent LM kernel per GPU, partial systems exchanged by peer stores over
+            # NVLink, no host or NCCL in the loop.  The other ranks idle at the barrier meanwhile.
+            dist.barrier()
+            if rank == 0:
+                try:
+                    ctxs = [ctx] + [pkg.Context(device=dd, max_images=0, max_width=0, max_height=0, max_keypoints=1,
+                                                max_ba_poses=64, max_ba_points=32768, max_ba_obs=262144)
+                                    for dd in range(world) if dd != local_rank]
+                    ctx.set_stream(None)
+                    rm = pkg.Context.ba_optimize_multi(ctxs, *a, num_iterations=nit)
+                    for _ in range(2):
+                        rm = pkg.Context.ba_optimize_multi(ctxs, *a, num_iterations=nit)
+                    for cc in ctxs:
+                        cc.timing_enable(True)
+                    t0 = time.perf_counter()
+                    for _ in range(5):
+                        rm = pkg.Context.ba_optimize_multi(ctxs, *a, num_iterations=nit)
+                    dtm = (time.perf_counter() - t0) / 5
+                    kmax = 0.0
+                    for cc in ctxs:
+                        ktm = cc.timing_read().get("ba_lm_kernel", (0.0, 1))
+                        kmax = max(kmax, ktm[0] / max(ktm[1], 1))
+                        cc.timing_enable(False)
+                    rec["multi_device"] = {
+                        "scaling": "strong (one window, landmarks sharded over the GPUs of one process, device-side LM, "
+                                   "P2P exchange of [S|bs|bp|chi2] per trial + scalar exchanges)",
+                        "gpus": world, "kernel_ms_max_over_gpus": kmax, "e2e_ms": dtm * 1e3,
+                        "kernel_iters_per_s": rm["iterations"] / (kmax * 1e-3), "ms_per_iter_kernel": kmax / rm["iterations"],
+                        "e2e_iters_per_s": rm["iterations"] / dtm, "exchanges": rm["exchanges"], "trials": rm["trials"],
+                        "exchange_bytes_per_trial_per_gpu": 8 * ((6 * nk) ** 2 // 2 + 3 * 6 * nk) * world,
+                        "speedup_vs_one_gpu_kernel": kms / kmax,
+                        "pose_rel_diff_vs_single_gpu": float(np.abs(rm["poses"] - r["poses"]).max() / np.abs(r["poses"]).max())}
+                    for cc in ctxs[1:]:
+                        cc.close()
+                    ctx.set_stream(stream.cuda_stream)
+                except Exception as ex:
+                    rec["multi_device"] = {"error": repr(ex)}
+            dist.barrier()
         if rank == 0:
             try:   # device-side phase profile of the last call and, for the large window, the dense DMMA Schur probe
-                ph = ctx.ba_last_phase_us()
                 tr = max(r["trials"], 1)
-                rec["phase_us_per_trial"] = {k: round(v / tr, 2) for k, v in ph.items()}
+                rec["phase_us_per_trial"] = {k: round(v / tr, 2) for k, v in phase_us.items()}
                 if name.startswith("cfg5"):
                     n = 6 * nk
                     n1, n2, n3 = pkg.ffi.ba_reduce_sizes(nk)

@@ -331,6 +331,22 @@ int vslam_ba_session_begin(vslam_ctx* ctx, int n_poses, const double* poses, int
 int vslam_ba_session_phase(vslam_ctx* ctx, int phase, double value);
 int vslam_ba_session_trial_done(vslam_ctx* ctx, int accept);
 int vslam_ba_session_end(vslam_ctx* ctx, double* poses, double* points, double* chi2_per_obs, uint8_t* point_inlier);
+/* ------------------------------------------------------------------------------------------------
+ * K17b  ONE window on n_dev GPUs of this process (strong scaling), same arguments and results as
+ * vslam_ba_optimize.  ctxs[r] must live on distinct devices with peer access (NVLink / NVSwitch); rank r owns a
+ * contiguous, observation-balanced landmark range, poses are replicated.  The whole Levenberg-Marquardt loop runs
+ * device-side in one persistent kernel per GPU; per LM trial the ranks exchange their partial reduced camera system
+ * [S | bs | bp | chi2] by direct peer stores + release/acquire flag words (no host round trip, no collective library)
+ * and sum it in rank order, so every rank solves the bit-identical 6K x 6K system; the accept/reject scalars, the
+ * lambda initialisation and the relabel counts ride on the same flag protocol.  res->reserved returns the number of
+ * exchanges executed.  Replaces the same reference code as vslam_ba_optimize (optimization.cpp:103-436); n_dev == 1
+ * forwards to it.  Host-synchronous; every context's stream is used.
+ * ---------------------------------------------------------------------------------------------- */
+int vslam_ba_optimize_multi(vslam_ctx* const* ctxs, int n_dev, int n_poses, double* poses, int n_points, double* points,
+                            int n_obs, const int32_t* obs_pose, const int32_t* obs_point, const double* obs_uv,
+                            const double* Kmat, const vslam_ba_options* opt, vslam_ba_result* res, double* chi2_per_obs,
+                            uint8_t* point_inlier);
+
 /* Measurement probe (the north star's "tensor cores only for the dense J^T J camera-block GEMM"): after phase SCHUR of a
  * session that covers ALL landmarks, form the same product -(Hpl Hll^-1 Hpl^T) as ONE dense fp64 SYRK on the tensor
  * cores (DMMA m8n8k4) into d_S_dense (n x n device doubles, n = 6 * n_poses, upper triangle written) and report the

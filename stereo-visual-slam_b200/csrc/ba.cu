@@ -71,6 +71,7 @@ struct BaParams {
     double* Dinv;          // [L][9]
     double* Hpp;           // [K][36]
     double* bp;            // [6K]
+    const double* bp_scale;  // gradient used by computeScale: bp, or the sum over ranks in the multi-device kernel
     double* S;             // [n][n]
     double* bs;            // [n]
     double* x;             // [n + 3L]
@@ -466,7 +467,7 @@ __device__ void ba_phase_schur_init(const BaParams& P, double lambda, int add_hp
         const int r = i / n, c = i - r * n;
         double v = 0.0;
         if (add_hpp && r / 6 == c / 6 && c >= r) v = P.Hpp[(r / 6) * 36 + (r % 6) * 6 + (c % 6)];
-        if (add_hpp && r == c) v += lambda;
+        if (add_hpp == 1 && r == c) v += lambda;  // add_hpp == 2: this rank's partial Hpp only, lambda after the exchange
         P.S[i] = v;
     }
     for (int i = gtid; i < n; i += gsize) P.bs[i] = add_hpp ? P.bp[i] : 0.0;
@@ -857,7 +858,7 @@ __device__ void ba_phase_update(const BaParams& P, int cur, double lambda, int s
         const int k = gtid;
         const double* xi = P.x + 6 * k;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) scale += xi[a] * (lambda * xi[a] + P.bp[6 * k + a]);
+        for (int a = 0; a < 6; ++a) scale += xi[a] * (lambda * xi[a] + P.bp_scale[6 * k + a]);
     }
     if (gtid < P.K) {
         const int k = gtid;
@@ -1112,10 +1113,15 @@ struct BaState {
     double *sess_r1, *sess_r2, *sess_r3;
     double* d_dense;  // Y of the dense-SYRK probe (allocated on first use)
     size_t dense_bytes;
+    // multi-device exchange areas (allocated on the first vslam_ba_optimize_multi call)
+    double *x_big, *x_small, *d_bp_glob;
+    unsigned* x_flags;
 };
 
 __global__ void ba_phase_kernel(const __grid_constant__ BaParams P, int phase, double lambda, int cur, int slot, double* r1,
                                 double* r3);
+struct BaMulti;
+__global__ void ba_lm_multi_kernel(const __grid_constant__ BaParams P, const __grid_constant__ BaMulti M);
 
 // shared memory of one CTA: max(pose partials K*42, per-CTA S n*n+n, in-shared-memory Cholesky n*n+n) doubles
 static int ba_smem_bytes(int K) {
@@ -1149,7 +1155,7 @@ int vslam_ba_init(vslam_ctx* ctx) {
     VSLAM_CUDA(ctx, cudaMalloc(&b->d_bp, n * sizeof(double)));
     VSLAM_CUDA(ctx, cudaMalloc(&b->d_S, n * n * sizeof(double)));
     VSLAM_CUDA(ctx, cudaMalloc(&b->d_bs, n * sizeof(double)));
-    VSLAM_CUDA(ctx, cudaMalloc(&b->d_x, (2 * n + 3 * L) * sizeof(double)));
+    VSLAM_CUDA(ctx, cudaMalloc(&b->d_x, (2 * n + 3 * L + 16) * sizeof(double)));  // + n + 16: staging of the small exchanges
     VSLAM_CUDA(ctx, cudaMalloc(&b->d_dbl, L * 3 * sizeof(double)));
     VSLAM_CUDA(ctx, cudaMalloc(&b->d_U, n * n * sizeof(double)));
     VSLAM_CUDA(ctx, cudaMalloc(&b->d_pose_start, (K + 1) * sizeof(int)));
@@ -1173,6 +1179,7 @@ int vslam_ba_init(vslam_ctx* ctx) {
     if (b->smem_bytes > 227 * 1024) return VSLAM_E_CAPACITY;
     VSLAM_CUDA(ctx, cudaFuncSetAttribute(ba_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
     VSLAM_CUDA(ctx, cudaFuncSetAttribute(ba_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
+    VSLAM_CUDA(ctx, cudaFuncSetAttribute(ba_lm_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
     return VSLAM_OK;
 }
 
@@ -1185,45 +1192,59 @@ void vslam_ba_free(vslam_ctx* ctx) {
     cudaFree(b->d_obs_point); cudaFree(b->d_obs_orig); cudaFree(b->d_lm_start); cudaFree(b->d_inlier); cudaFree(b->d_sc);
     cudaFreeHost(b->h_sc);
     if (b->d_dense) cudaFree(b->d_dense);
+    if (b->x_big) { cudaFree(b->x_big); cudaFree(b->x_small); cudaFree(b->x_flags); cudaFree(b->d_bp_glob); }
     free(b->sess);
     free(b);
     ctx->ba = nullptr;
 }
 
-// Host marshalling shared by vslam_ba_optimize and vslam_ba_session_begin: stable counting sorts of the edge list by
-// landmark (the device order) and by pose (CSR over device indices), duplicate (pose, landmark) detection, uploads.
-// Index bookkeeping only -- no arithmetic on the measurements.
-static int ba_marshal(vslam_ctx* ctx, BaState* b, int K, int n_points, int n_obs, const double* poses,
-                      const double* points, const int32_t* obs_pose, const int32_t* obs_point, const double* obs_uv,
-                      int* has_dup) {
+// Host marshalling shared by vslam_ba_optimize, vslam_ba_session_begin and vslam_ba_optimize_multi: stable counting
+// sorts of the edge list by landmark (the device order) and by pose (CSR over device indices), duplicate (pose,
+// landmark) detection -- once on the host -- then the uploads to one device.  Index bookkeeping only, no arithmetic on
+// the measurements.
+struct BaHostGraph {
+    int K, n_points, n_obs, has_dup;
+    std::vector<int> lm_start, op, ol, oo, pose_start, pose_obs;
+    std::vector<double> uv;
+};
+
+static int ba_prepare_host(BaHostGraph& g, int K, int n_points, int n_obs, const int32_t* obs_pose,
+                           const int32_t* obs_point, const double* obs_uv) {
     const int L = n_points > 0 ? n_points : 1;
     const int no = n_obs > 0 ? n_obs : 1;
-    std::vector<int> lm_start(L + 1, 0), op(no), ol(no), oo(no), pose_start(K + 1, 0), pose_obs(no);
-    std::vector<double> uv(2 * (size_t)no);
+    g.K = K; g.n_points = n_points; g.n_obs = n_obs; g.has_dup = 0;
+    g.lm_start.assign(L + 1, 0); g.pose_start.assign(K + 1, 0);
+    g.op.resize(no); g.ol.resize(no); g.oo.resize(no); g.pose_obs.resize(no); g.uv.resize(2 * (size_t)no);
     for (int i = 0; i < n_obs; ++i) {
         if (obs_point[i] < 0 || obs_point[i] >= n_points || obs_pose[i] < 0 || obs_pose[i] >= K) return VSLAM_E_INVALID;
-        lm_start[obs_point[i] + 1]++;
-        pose_start[obs_pose[i] + 1]++;
+        g.lm_start[obs_point[i] + 1]++;
+        g.pose_start[obs_pose[i] + 1]++;
     }
-    for (int l = 0; l < L; ++l) lm_start[l + 1] += lm_start[l];
-    for (int k = 0; k < K; ++k) pose_start[k + 1] += pose_start[k];
+    for (int l = 0; l < L; ++l) g.lm_start[l + 1] += g.lm_start[l];
+    for (int k = 0; k < K; ++k) g.pose_start[k + 1] += g.pose_start[k];
     {
-        std::vector<int> fill(lm_start.begin(), lm_start.end() - 1);
+        std::vector<int> fill(g.lm_start.begin(), g.lm_start.end() - 1);
         for (int i = 0; i < n_obs; ++i) {
             const int d = fill[obs_point[i]]++;
-            op[d] = obs_pose[i]; ol[d] = obs_point[i]; oo[d] = i;
-            uv[2 * d] = obs_uv[2 * i]; uv[2 * d + 1] = obs_uv[2 * i + 1];
+            g.op[d] = obs_pose[i]; g.ol[d] = obs_point[i]; g.oo[d] = i;
+            g.uv[2 * d] = obs_uv[2 * i]; g.uv[2 * d + 1] = obs_uv[2 * i + 1];
         }
     }
     {
-        std::vector<int> fill(pose_start.begin(), pose_start.end() - 1);
-        for (int d = 0; d < n_obs; ++d) pose_obs[fill[op[d]]++] = d;  // ascending device index within each pose
+        std::vector<int> fill(g.pose_start.begin(), g.pose_start.end() - 1);
+        for (int d = 0; d < n_obs; ++d) g.pose_obs[fill[g.op[d]]++] = d;  // ascending device index within each pose
     }
-    *has_dup = 0;
-    for (int l = 0; l < n_points && !*has_dup; ++l)
-        for (int i = lm_start[l]; i < lm_start[l + 1] && !*has_dup; ++i)
-            for (int j = i + 1; j < lm_start[l + 1]; ++j)
-                if (op[i] == op[j]) { *has_dup = 1; break; }
+    for (int l = 0; l < n_points && !g.has_dup; ++l)
+        for (int i = g.lm_start[l]; i < g.lm_start[l + 1] && !g.has_dup; ++i)
+            for (int j = i + 1; j < g.lm_start[l + 1]; ++j)
+                if (g.op[i] == g.op[j]) { g.has_dup = 1; break; }
+    return VSLAM_OK;
+}
+
+// uploads on the context stream of the CURRENT device; the caller synchronises before `g` goes out of scope
+static int ba_upload(vslam_ctx* ctx, BaState* b, const BaHostGraph& g, const double* poses, const double* points) {
+    const int K = g.K, n_points = g.n_points, n_obs = g.n_obs;
+    const int L = n_points > 0 ? n_points : 1;
     cudaStream_t s = ctx->stream;
     VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_poses, poses, (size_t)K * 96, cudaMemcpyHostToDevice, s));
     if (n_points > 0) {
@@ -1232,17 +1253,29 @@ static int ba_marshal(vslam_ctx* ctx, BaState* b, int K, int n_points, int n_obs
         VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_points + (size_t)L * 3, points, (size_t)n_points * 24, cudaMemcpyHostToDevice, s));
     }
     if (n_obs > 0) {
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_pose, op.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_point, ol.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_orig, oo.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_pose_obs, pose_obs.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_uv, uv.data(), (size_t)n_obs * 16, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_pose, g.op.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_point, g.ol.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_orig, g.oo.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_pose_obs, g.pose_obs.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_uv, g.uv.data(), (size_t)n_obs * 16, cudaMemcpyHostToDevice, s));
     }
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_lm_start, lm_start.data(), (size_t)(L + 1) * 4, cudaMemcpyHostToDevice, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_pose_start, pose_start.data(), (size_t)(K + 1) * 4, cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_lm_start, g.lm_start.data(), (size_t)(L + 1) * 4, cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_pose_start, g.pose_start.data(), (size_t)(K + 1) * 4, cudaMemcpyHostToDevice, s));
     VSLAM_CUDA(ctx, cudaMemsetAsync(b->d_obs_of, 0xFF, (size_t)K * L * sizeof(int), s));
     VSLAM_CUDA(ctx, cudaMemsetAsync(b->d_block_flag, 0, (size_t)(K * (K + 1) / 2) * sizeof(int), s));
-    VSLAM_CUDA(ctx, cudaStreamSynchronize(s));  // the staging vectors go out of scope
+    return VSLAM_OK;
+}
+
+static int ba_marshal(vslam_ctx* ctx, BaState* b, int K, int n_points, int n_obs, const double* poses,
+                      const double* points, const int32_t* obs_pose, const int32_t* obs_point, const double* obs_uv,
+                      int* has_dup) {
+    BaHostGraph g;
+    int st = ba_prepare_host(g, K, n_points, n_obs, obs_pose, obs_point, obs_uv);
+    if (st != VSLAM_OK) return st;
+    *has_dup = g.has_dup;
+    st = ba_upload(ctx, b, g, poses, points);
+    if (st != VSLAM_OK) return st;
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging vectors go out of scope
     return VSLAM_OK;
 }
 
@@ -1262,6 +1295,7 @@ static void ba_fill_params(BaParams& P, BaState* b, int K, int n_points, int n_o
     P.pose_obs = b->d_pose_obs; P.obs_of = b->d_obs_of; P.dbl = b->d_dbl; P.Ubuf = b->d_U; P.block_flag = b->d_block_flag; P.err = b->d_err; P.Hpl = b->d_Hpl;
     P.Hll = b->d_Hll; P.bl = b->d_bl; P.Dinv = b->d_Dinv; P.Hpp = b->d_Hpp; P.bp = b->d_bp; P.S = b->d_S; P.bs = b->d_bs;
     P.x = b->d_x; P.sc = b->d_sc; P.chi2_out = b->d_chi2; P.inlier_out = b->d_inlier;
+    P.bp_scale = P.bp;
 }
 
 extern "C" int vslam_ba_optimize(vslam_ctx* ctx, int n_poses, double* poses, int n_points, double* points, int n_obs,
@@ -1416,6 +1450,7 @@ extern "C" int vslam_ba_session_begin(vslam_ctx* ctx, int n_poses, const double*
     ba_fill_params(P, b, K, n_points, n_obs, opt, Kmat, has_dup);
     P.shard_L0 = shard_begin; P.shard_L1 = shard_end;
     P.Hpp = d_r1; P.bp = d_r1 + 36 * K;          // pose blocks live in the caller's reduce buffer r1
+    P.bp_scale = P.bp;
     P.S = d_r2; P.bs = d_r2 + (size_t)P.n * P.n;  // reduced camera system lives in r2
     b->sess_open = 1; b->sess_cur = 0; b->sess_trials = 0;
     b->sess_r1 = d_r1; b->sess_r2 = d_r2; b->sess_r3 = d_r3;
@@ -1473,6 +1508,433 @@ extern "C" int vslam_ba_session_end(vslam_ctx* ctx, double* poses, double* point
     if (point_inlier) VSLAM_CUDA(ctx, cudaMemcpyAsync(point_inlier, b->d_inlier, (size_t)P.L, cudaMemcpyDeviceToHost, s));
     VSLAM_CUDA(ctx, cudaStreamSynchronize(s));
     b->sess_open = 0;
+    return VSLAM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K17b: ONE window on several GPUs of one process, the whole Levenberg-Marquardt loop device-side.
+// Rank r (= device r of the call) owns a contiguous landmark range with all its observations, poses are replicated.
+// Every rank runs the same persistent cooperative kernel; the ranks meet through peer memory over NVLink:
+//   * big exchange, once per LM trial: each rank stores its partial [S (upper block rows) | bs | bp | chi2 at the
+//     linearisation point] straight into slot `rank` of EVERY rank's receive area (P2P stores), publishes an epoch flag
+//     with st.release.sys, waits for the other ranks' flags with ld.acquire.sys, and sums the slots in rank order --
+//     all-gather + local reduction in one hop, no host, no collective library, bit-identical sums on every rank;
+//   * small exchange (a few doubles riding on the same flag protocol): lambda initialisation (max |diag|), the trial's
+//     [chi2, scale, ok] for the accept/reject decision, the relabel counts.
+// Every rank then solves the identical reduced camera system redundantly and back-substitutes its own landmarks, so
+// the LM control flow needs no broadcast.  A peer that never shows up trips a bounded wait (trap), not a hang.
+// ---------------------------------------------------------------------------------------------------------------
+#define BA_MAX_DEV 8
+#define BA_XS 512  // doubles per small-exchange slot (>= 6 * 64 + 8)
+struct BaMulti {
+    int rank, world;
+    unsigned epoch0;              // flags only ever grow: base epoch of this launch
+    int xlen;                     // doubles per big slot: n*n + 2n + 8
+    double* xbig[BA_MAX_DEV];     // receive area of device g: [world][xlen]
+    double* xsmall[BA_MAX_DEV];   // [2][world][BA_XS]
+    unsigned* flags[BA_MAX_DEV];  // [world]: epoch of the last exchange rank s has published towards device g
+    double* bp_glob;              // local [n]: sum over ranks of bp
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Called by every thread after its peer stores of this exchange.  Returns when every rank's data of `epoch` is visible.
+__device__ void ba_multi_signal_wait(const BaMulti& M, cg::grid_group& grid, unsigned epoch) {
+    __threadfence_system();  // this thread's peer stores are ordered before whatever follows the grid barrier
+    grid.sync();
+    if (blockIdx.x == 0 && (int)threadIdx.x < M.world) st_release_sys_u32(M.flags[threadIdx.x] + M.rank, epoch);
+    if ((int)threadIdx.x < M.world) {
+        const unsigned* f = M.flags[M.rank] + threadIdx.x;
+        const unsigned long long t0 = gtimer();
+        while ((int)(ld_acquire_sys_u32(f) - epoch) < 0) {
+            if (gtimer() - t0 > 4000000000ull) __trap();  // 4 s: a peer kernel is not running
+        }
+    }
+    __syncthreads();
+}
+
+// big exchange + rank-ordered sum: S <- sum_g S_g + lambda I, bs <- sum_g bs_g, bp_glob <- sum_g bp_g; returns sum_g chi_g
+__device__ double ba_multi_exchange_system(const BaParams& P, const BaMulti& M, cg::grid_group& grid, unsigned epoch,
+                                           double lambda, double chi_local, int gtid, int gsize) {
+    const int n = P.n, lane = threadIdx.x & 31, gw = gtid >> 5, nw = gsize >> 5;
+    const size_t slot = (size_t)M.rank * M.xlen;
+    for (int r = gw; r < n; r += nw) {  // one warp per row: the row segment right of (and including) the diagonal block
+        const int c0 = 6 * (r / 6);
+        for (int c = c0 + lane; c < n; c += 32) {
+            const double v = P.S[(size_t)r * n + c];
+            for (int g = 0; g < M.world; ++g) M.xbig[g][slot + (size_t)r * n + c] = v;
+        }
+    }
+    for (int i = gtid; i < 2 * n + 1; i += gsize) {
+        const double v = i < n ? P.bs[i] : i < 2 * n ? P.bp[i - n] : chi_local;
+        for (int g = 0; g < M.world; ++g) M.xbig[g][slot + (size_t)n * n + i] = v;
+    }
+    ba_multi_signal_wait(M, grid, epoch);
+    const double* rx = M.xbig[M.rank];
+    for (int r = gw; r < n; r += nw) {
+        const int c0 = 6 * (r / 6);
+        for (int c = c0 + lane; c < n; c += 32) {
+            double v = 0.0;
+            for (int g = 0; g < M.world; ++g) v += __ldcg(rx + (size_t)g * M.xlen + (size_t)r * n + c);
+            P.S[(size_t)r * n + c] = r == c ? v + lambda : v;
+        }
+    }
+    for (int i = gtid; i < 2 * n; i += gsize) {
+        double v = 0.0;
+        for (int g = 0; g < M.world; ++g) v += __ldcg(rx + (size_t)g * M.xlen + (size_t)n * n + i);
+        if (i < n) P.bs[i] = v;
+        else M.bp_glob[i - n] = v;
+    }
+    double chi = 0.0;
+    for (int g = 0; g < M.world; ++g) chi += __ldcg(rx + (size_t)g * M.xlen + (size_t)n * n + 2 * n);
+    grid.sync();
+    return chi;
+}
+
+// small exchange: every rank publishes `len` doubles (taken from `src` in local global memory); afterwards slot g of the
+// returned area holds rank g's values.  Two parities so that two consecutive small exchanges never share a slot.
+__device__ const double* ba_multi_exchange_small(const BaMulti& M, cg::grid_group& grid, unsigned epoch, const double* src,
+                                                 int len, int gtid) {
+    const int par = epoch & 1;
+    const size_t off = ((size_t)par * M.world + M.rank) * BA_XS;
+    if (gtid < len) {
+        const double v = src[gtid];
+        for (int g = 0; g < M.world; ++g) M.xsmall[g][off + gtid] = v;
+    }
+    ba_multi_signal_wait(M, grid, epoch);
+    return M.xsmall[M.rank] + (size_t)par * M.world * BA_XS;
+}
+
+__global__ void __launch_bounds__(BA_THREADS)
+ba_lm_multi_kernel(const __grid_constant__ BaParams P, const __grid_constant__ BaMulti M) {
+    extern __shared__ double smem[];
+    cg::grid_group grid = cg::this_grid();
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    BaScalars* sc = P.sc;
+    double* stage = P.x + P.n + 3 * (size_t)P.L;  // n spare doubles behind the update vector: small-exchange staging
+    unsigned epoch = M.epoch0;
+    int cur = 0, trials = 0, accepted = 0, it = 0;
+    double lambda = 0.0, ni = 2.0, chi_first = 0.0, chi_last = 0.0;
+    if (gtid == 0)
+        for (int r = 0; r < 6; ++r) sc->cnt_le[r] = 0;
+    for (it = 0; it < P.num_iterations; ++it) {
+        ba_phase_zero(P, gtid, gsize);
+        grid.sync();
+        ba_phase_build_edges(P, cur, gtid, gsize);
+        ba_phase_build_poses(P, cur, smem);
+        if (it == 0) {
+            grid.sync();
+            ba_phase_maxdiag(P, gtid, gsize);
+        }
+        grid.sync();
+        const double chi_local = sc->chi_cur;
+        if (it == 0) {
+            // computeLambdaInit: tau * max |diagonal| over the landmark blocks of all ranks and the SUMMED pose blocks
+            if (gtid < P.n) stage[gtid] = P.Hpp[(gtid / 6) * 36 + (gtid % 6) * 7];
+            if (gtid == 0) stage[P.n] = __longlong_as_double((long long)sc->maxdiag_bits);
+            grid.sync();
+            const double* rs = ba_multi_exchange_small(M, grid, ++epoch, stage, P.n + 1, gtid);
+            __shared__ double s_md;
+            if (threadIdx.x == 0) {
+                double md = 0.0;
+                for (int g = 0; g < M.world; ++g) md = fmax(md, __ldcg(rs + (size_t)g * BA_XS + P.n));
+                for (int i = 0; i < P.n; ++i) {
+                    double d = 0.0;
+                    for (int g = 0; g < M.world; ++g) d += __ldcg(rs + (size_t)g * BA_XS + i);
+                    md = fmax(md, fabs(d));
+                }
+                s_md = md;
+            }
+            __syncthreads();
+            lambda = P.tau * s_md;
+            ni = 2.0;
+        }
+        double currentChi = 0.0, rho = 0.0;
+        int qmax = 0;
+        do {
+            const int slot = trials & 1;
+            ba_phase_dinv(P, lambda, slot, 2, gtid, gsize);  // S = this rank's Hpp (no lambda), bs = its bp
+            grid.sync();
+            if (P.has_dup) ba_phase_schur_atomic(P, gtid, gsize);
+            else ba_phase_schur_blocks(P, smem);
+            grid.sync();
+            const double chi_sum = ba_multi_exchange_system(P, M, grid, ++epoch, lambda, chi_local, gtid, gsize);
+            if (qmax == 0) {
+                currentChi = chi_sum;
+                if (it == 0) chi_first = currentChi;
+            }
+            if (P.n <= BA_SMEM_CHOL_MAX) ba_phase_solve_cta(P, slot, smem);
+            else ba_phase_solve_grid(P, slot, grid, smem, P.Ubuf, gtid, gsize);
+            grid.sync();
+            ba_phase_update(P, cur, lambda, slot, gtid, gsize);
+            grid.sync();
+            ba_phase_trial_err(P, cur, slot, gtid, gsize);
+            grid.sync();
+            const int ok_local = sc->solve_ok[slot];
+            if (gtid == 0) {
+                stage[0] = sc->chi_trial[slot];
+                stage[1] = sc->scale[slot];
+                stage[2] = (double)ok_local;
+            }
+            grid.sync();
+            const double* rs = ba_multi_exchange_small(M, grid, ++epoch, stage, 3, gtid);
+            double tchi = 0.0, tscale = 0.0, tok = 0.0;
+            for (int g = 0; g < M.world; ++g) {
+                tchi += __ldcg(rs + (size_t)g * BA_XS);
+                tscale += __ldcg(rs + (size_t)g * BA_XS + 1);
+                tok += __ldcg(rs + (size_t)g * BA_XS + 2);
+            }
+            const int ok2 = tok > M.world - 0.5;
+            const double tempChi = ok2 ? tchi : DBL_MAX;
+            const double scale = (ok2 ? tscale : 0.0) + 1e-3;
+            rho = (currentChi - tempChi) / scale;
+            if (rho > 0 && isfinite(tempChi)) {
+                double alpha = 1. - pow(2 * rho - 1, 3);
+                alpha = fmin(alpha, 2. / 3.);
+                lambda *= fmax(1. / 3., alpha);
+                ni = 2;
+                currentChi = tempChi;
+                cur = 1 - cur;
+                accepted++;
+            } else {
+                lambda *= ni;
+                ni *= 2;
+            }
+            qmax++;
+            trials++;
+        } while (rho < 0 && qmax < P.max_trials);
+        chi_last = currentChi;
+        if (qmax == P.max_trials || rho == 0) {
+            it++;
+            break;
+        }
+    }
+    if (P.num_iterations <= 0) {
+        ba_phase_zero(P, gtid, gsize);
+        grid.sync();
+        ba_phase_build_edges(P, cur, gtid, gsize);
+        grid.sync();
+        if (gtid == 0) stage[0] = sc->chi_cur;
+        grid.sync();
+        const double* rs = ba_multi_exchange_small(M, grid, ++epoch, stage, 1, gtid);
+        double c = 0.0;
+        for (int g = 0; g < M.world; ++g) c += __ldcg(rs + (size_t)g * BA_XS);
+        chi_first = chi_last = c;
+    }
+    // relabel: counts summed over the ranks, identical threshold everywhere
+    grid.sync();
+    ba_phase_relabel_count(P, gtid, gsize);
+    grid.sync();
+    if (gtid < 6) stage[gtid] = (double)sc->cnt_le[gtid];
+    grid.sync();
+    const double* rc = ba_multi_exchange_small(M, grid, ++epoch, stage, 6, gtid);
+    int cnt[6];
+    for (int r = 0; r < 6; ++r) {
+        double c = 0.0;
+        for (int g = 0; g < M.world; ++g) c += __ldcg(rc + (size_t)g * BA_XS + r);
+        cnt[r] = (int)(c + 0.5);
+    }
+    double th = P.chi2_th;
+    int rr = 0;
+    for (; rr < 5; ++rr) {
+        if (cnt[rr] / (double)P.n_obs > 0.5) break;
+        th *= 2;
+    }
+    ba_phase_relabel_apply(P, th, gtid, gsize);
+    if (cur == 1) {
+        for (int i = gtid; i < P.K * 12; i += gsize) P.poses[i] = P.poses[P.K * 12 + i];
+        if (!P.pose_only)
+            for (int i = gtid; i < P.L * 3; i += gsize) P.points[i] = P.points[(size_t)P.L * 3 + i];
+    }
+    if (gtid == 0) {
+        sc->iterations = it;
+        sc->trials = trials;
+        sc->accepted = accepted;
+        sc->chi2_initial = chi_first;
+        sc->chi2_final = chi_last;
+        sc->lambda_final = lambda;
+        sc->chi2_threshold = th;
+        sc->n_inlier_obs = cnt[rr];
+        sc->n_outlier_obs = P.n_obs - cnt[rr];
+        sc->pad = (int)(epoch - M.epoch0);  // exchanges executed
+    }
+}
+
+// contiguous landmark ranges with (nearly) equal numbers of observations
+static void ba_landmark_shards(const BaHostGraph& g, int world, int* cuts /*[world + 1]*/) {
+    const long long total = g.n_obs;
+    cuts[0] = 0;
+    int l = 0;
+    for (int r = 1; r < world; ++r) {
+        const long long target = total * r / world;
+        while (l < g.n_points && g.lm_start[l] < target) ++l;
+        cuts[r] = l < cuts[r - 1] ? cuts[r - 1] : l;
+    }
+    cuts[world] = g.n_points;
+}
+
+static unsigned g_ba_multi_epoch = 0;  // grows by 65536 per call: flag words are never reset
+
+extern "C" int vslam_ba_optimize_multi(vslam_ctx* const* ctxs, int n_dev, int n_poses, double* poses, int n_points,
+                                       double* points, int n_obs, const int32_t* obs_pose, const int32_t* obs_point,
+                                       const double* obs_uv, const double* Kmat, const vslam_ba_options* opt,
+                                       vslam_ba_result* res, double* chi2_per_obs, uint8_t* point_inlier) {
+    if (!ctxs || n_dev < 1 || n_dev > BA_MAX_DEV) return VSLAM_E_INVALID;
+    for (int d = 0; d < n_dev; ++d)
+        if (!ctxs[d] || !ctxs[d]->ba || !ctxs[d]->ba->d_poses) return VSLAM_E_INVALID;
+    if (n_dev == 1)
+        return vslam_ba_optimize(ctxs[0], n_poses, poses, n_points, points, n_obs, obs_pose, obs_point, obs_uv, Kmat, opt, res,
+                                 chi2_per_obs, point_inlier);
+    if (!poses || !points || !Kmat || !opt || n_poses <= 0 || n_points <= 0 || n_obs <= 0 || !obs_pose || !obs_point || !obs_uv)
+        return VSLAM_E_INVALID;
+    for (int d = 0; d < n_dev; ++d) {
+        BaState* b = ctxs[d]->ba;
+        if (n_poses > b->maxK || n_points > b->maxL || n_obs > b->maxObs) return VSLAM_E_CAPACITY;
+        for (int e = 0; e < d; ++e)
+            if (ctxs[e]->cfg.device == ctxs[d]->cfg.device) return VSLAM_E_INVALID;  // one context per device
+    }
+    int dev0 = 0;
+    cudaGetDevice(&dev0);
+    const int K = n_poses, n = 6 * K;
+    BaHostGraph g;
+    int st = ba_prepare_host(g, K, n_points, n_obs, obs_pose, obs_point, obs_uv);
+    if (st != VSLAM_OK) return st;
+    int cuts[BA_MAX_DEV + 1];
+    ba_landmark_shards(g, n_dev, cuts);
+    for (int d = 0; d < n_dev; ++d)
+        if (cuts[d + 1] <= cuts[d]) return VSLAM_E_INVALID;  // fewer landmarks than devices: use fewer devices
+    const int xlen = n * n + 2 * n + 8;
+    vslam_ctx* c0 = ctxs[0];
+#define MULTI_CUDA(d, call)                                                            \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess) {                                                      \
+            vslam_set_cuda_error(ctxs[d], e__, #call);                                 \
+            if ((d) != 0) vslam_set_cuda_error(c0, e__, #call);                        \
+            cudaSetDevice(dev0);                                                       \
+            return VSLAM_E_CUDA;                                                       \
+        }                                                                              \
+    } while (0)
+    // peer access + exchange areas (first call per context), uploads
+    for (int d = 0; d < n_dev; ++d) {
+        vslam_ctx* ctx = ctxs[d];
+        BaState* b = ctx->ba;
+        MULTI_CUDA(d, cudaSetDevice(ctx->cfg.device));
+        for (int e = 0; e < n_dev; ++e) {
+            if (e == d) continue;
+            int can = 0;
+            MULTI_CUDA(d, cudaDeviceCanAccessPeer(&can, ctx->cfg.device, ctxs[e]->cfg.device));
+            if (!can) {
+                cudaSetDevice(dev0);
+                snprintf(c0->err, sizeof(c0->err), "no peer access between devices %d and %d", ctx->cfg.device, ctxs[e]->cfg.device);
+                return VSLAM_E_NODEVICE;
+            }
+            const cudaError_t pe = cudaDeviceEnablePeerAccess(ctxs[e]->cfg.device, 0);
+            if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else MULTI_CUDA(d, pe);
+        }
+        if (!b->x_big) {
+            const size_t nmax = 6 * (size_t)b->maxK;
+            MULTI_CUDA(d, cudaMalloc(&b->x_big, BA_MAX_DEV * (nmax * nmax + 2 * nmax + 8) * sizeof(double)));
+            MULTI_CUDA(d, cudaMalloc(&b->x_small, 2 * BA_MAX_DEV * BA_XS * sizeof(double)));
+            MULTI_CUDA(d, cudaMalloc(&b->x_flags, BA_MAX_DEV * sizeof(unsigned)));
+            MULTI_CUDA(d, cudaMalloc(&b->d_bp_glob, nmax * sizeof(double)));
+            MULTI_CUDA(d, cudaMemset(b->x_flags, 0, BA_MAX_DEV * sizeof(unsigned)));
+            // flags written by peers before must not be lost: a fresh context starts at the running epoch
+            if (g_ba_multi_epoch) {
+                unsigned init[BA_MAX_DEV];
+                for (int q = 0; q < BA_MAX_DEV; ++q) init[q] = g_ba_multi_epoch;
+                MULTI_CUDA(d, cudaMemcpy(b->x_flags, init, sizeof(init), cudaMemcpyHostToDevice));
+            }
+            MULTI_CUDA(d, cudaDeviceSynchronize());
+        }
+        st = ba_upload(ctx, b, g, poses, points);
+        if (st != VSLAM_OK) { cudaSetDevice(dev0); return st; }
+        MULTI_CUDA(d, cudaMemsetAsync(b->d_chi2, 0, (size_t)n_obs * 8, ctx->stream));
+        if (point_inlier) MULTI_CUDA(d, cudaMemcpyAsync(b->d_inlier, point_inlier, (size_t)n_points, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const unsigned epoch0 = g_ba_multi_epoch;
+    g_ba_multi_epoch += 65536u;
+    // launch the same kernel on every device; they meet through peer memory
+    for (int d = 0; d < n_dev; ++d) {
+        vslam_ctx* ctx = ctxs[d];
+        BaState* b = ctx->ba;
+        MULTI_CUDA(d, cudaSetDevice(ctx->cfg.device));
+        BaParams P;
+        ba_fill_params(P, b, K, n_points, n_obs, opt, Kmat, g.has_dup);
+        P.shard_L0 = cuts[d]; P.shard_L1 = cuts[d + 1];
+        BaMulti M;
+        memset(&M, 0, sizeof(M));
+        M.rank = d; M.world = n_dev; M.epoch0 = epoch0; M.xlen = xlen;
+        for (int e = 0; e < n_dev; ++e) {
+            M.xbig[e] = ctxs[e]->ba->x_big;
+            M.xsmall[e] = ctxs[e]->ba->x_small;
+            M.flags[e] = ctxs[e]->ba->x_flags;
+        }
+        M.bp_glob = b->d_bp_glob;
+        P.bp_scale = b->d_bp_glob;
+        void* args[] = {(void*)&P, (void*)&M};
+        vslam_time_begin(ctx, VK_BA_BUILD);
+        MULTI_CUDA(d, cudaLaunchCooperativeKernel((const void*)ba_lm_multi_kernel, dim3(b->n_cta), dim3(BA_THREADS), args,
+                                                  (size_t)ba_smem_bytes(K), ctx->stream));
+        vslam_time_end(ctx);
+        ctx->launches++;
+    }
+    // results: poses and scalars from rank 0; points / inlier flags from the owner of each landmark range; per-edge
+    // chi2 is zero outside a rank's shard, so the per-rank arrays add up
+    std::vector<double> chi_tmp;
+    for (int d = 0; d < n_dev; ++d) {
+        vslam_ctx* ctx = ctxs[d];
+        BaState* b = ctx->ba;
+        MULTI_CUDA(d, cudaSetDevice(ctx->cfg.device));
+        cudaStream_t s = ctx->stream;
+        if (d == 0) {
+            MULTI_CUDA(d, cudaMemcpyAsync(b->h_sc, b->d_sc, sizeof(BaScalars), cudaMemcpyDeviceToHost, s));
+            MULTI_CUDA(d, cudaMemcpyAsync(poses, b->d_poses, (size_t)K * 96, cudaMemcpyDeviceToHost, s));
+        }
+        const int l0 = cuts[d], l1 = cuts[d + 1];
+        if (l1 > l0) {
+            if (!opt->pose_only)
+                MULTI_CUDA(d, cudaMemcpyAsync(points + 3 * (size_t)l0, b->d_points + 3 * (size_t)l0, (size_t)(l1 - l0) * 24,
+                                              cudaMemcpyDeviceToHost, s));
+            if (point_inlier)
+                MULTI_CUDA(d, cudaMemcpyAsync(point_inlier + l0, b->d_inlier + l0, (size_t)(l1 - l0), cudaMemcpyDeviceToHost, s));
+        }
+    }
+    if (chi2_per_obs) {
+        chi_tmp.resize((size_t)n_obs * n_dev);
+        for (int d = 0; d < n_dev; ++d) {
+            MULTI_CUDA(d, cudaSetDevice(ctxs[d]->cfg.device));
+            MULTI_CUDA(d, cudaMemcpyAsync(chi_tmp.data() + (size_t)d * n_obs, ctxs[d]->ba->d_chi2, (size_t)n_obs * 8,
+                                          cudaMemcpyDeviceToHost, ctxs[d]->stream));
+        }
+    }
+    for (int d = 0; d < n_dev; ++d) {
+        MULTI_CUDA(d, cudaSetDevice(ctxs[d]->cfg.device));
+        MULTI_CUDA(d, cudaStreamSynchronize(ctxs[d]->stream));
+    }
+    cudaSetDevice(dev0);
+#undef MULTI_CUDA
+    if (chi2_per_obs) {
+        for (int i = 0; i < n_obs; ++i) {
+            double v = 0.0;
+            for (int d = 0; d < n_dev; ++d) v += chi_tmp[(size_t)d * n_obs + i];
+            chi2_per_obs[i] = v;
+        }
+    }
+    if (res) {
+        const BaScalars* h = c0->ba->h_sc;
+        res->iterations = h->iterations; res->trials = h->trials; res->accepted = h->accepted; res->reserved = h->pad;
+        res->chi2_initial = h->chi2_initial; res->chi2_final = h->chi2_final; res->lambda_final = h->lambda_final;
+        res->chi2_threshold = h->chi2_threshold; res->n_inlier_obs = h->n_inlier_obs; res->n_outlier_obs = h->n_outlier_obs;
+    }
     return VSLAM_OK;
 }
 

@@ -88,6 +88,8 @@ SIGNATURES = {
                                              _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vslam_ba_optimize": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, C.POINTER(BaOptions),
                                C.POINTER(BaResult), _vp, _vp]),
+    "vslam_ba_optimize_multi": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, C.POINTER(BaOptions),
+                                     C.POINTER(BaResult), _vp, _vp]),
     "vslam_pnp_ransac": (_i, [_vp, _vp, _vp, _i, _vp, _i, _f, _d, _vp, _vp, _vp, _vp, _pi]),
     "vslam_pnp_debug_read": (_i, [_vp, _i, _vp, _pi, _pi]),
     "vslam_anms": (_i, [_vp, _vp, _i, _i, _f, _vp, _pi]),
@@ -337,6 +339,33 @@ class Context:
         self.check(st, "vslam_ba_optimize")
         return dict(poses=poses, points=points, chi2_per_obs=chi2[:len(op)], point_inlier=inl[:len(points)].astype(bool),
                     iterations=res.iterations, trials=res.trials, accepted=res.accepted,
+                    chi2_initial=res.chi2_initial, chi2_final=res.chi2_final, lambda_final=res.lambda_final,
+                    chi2_threshold=res.chi2_threshold, n_inlier_obs=res.n_inlier_obs, n_outlier_obs=res.n_outlier_obs)
+
+    @staticmethod
+    def ba_optimize_multi(ctxs, poses, points, obs_pose, obs_point, obs_uv, K, num_iterations=10, pose_only=False,
+                          huber_delta=5.991, chi2_th=5.991, max_trials=10, tau=1e-5, point_inlier=None):
+        """ONE window on len(ctxs) GPUs of this process (vslam_ba_optimize_multi): device-side LM loop, the ranks
+        exchange the reduced camera system through peer memory.  Same dict as ba_optimize plus `exchanges`."""
+        poses = np.array(poses, dtype=np.float64, order="C").reshape(-1, 12).copy()
+        points = np.array(points, dtype=np.float64, order="C").reshape(-1, 3).copy()
+        op = np.ascontiguousarray(obs_pose, dtype=np.int32)
+        ol = np.ascontiguousarray(obs_point, dtype=np.int32)
+        uv = np.ascontiguousarray(obs_uv, dtype=np.float64).reshape(-1, 2)
+        Kc = np.ascontiguousarray(K, dtype=np.float64).reshape(9)
+        opt = BaOptions(huber_delta, chi2_th, int(num_iterations), int(pose_only), int(max_trials), 0, tau)
+        res = BaResult()
+        chi2 = np.zeros(max(len(op), 1), dtype=np.float64)
+        inl = (np.ones(max(len(points), 1), dtype=np.uint8) if point_inlier is None
+               else np.ascontiguousarray(point_inlier, dtype=np.uint8).copy())
+        handles = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        lib = ctxs[0].lib
+        st = lib.vslam_ba_optimize_multi(handles, len(ctxs), len(poses), _ptr(poses), len(points), _ptr(points), len(op),
+                                         _ptr(op), _ptr(ol), _ptr(uv), _ptr(Kc), C.byref(opt), C.byref(res), _ptr(chi2),
+                                         _ptr(inl))
+        ctxs[0].check(st, "vslam_ba_optimize_multi")
+        return dict(poses=poses, points=points, chi2_per_obs=chi2[:len(op)], point_inlier=inl[:len(points)].astype(bool),
+                    iterations=res.iterations, trials=res.trials, accepted=res.accepted, exchanges=res.reserved,
                     chi2_initial=res.chi2_initial, chi2_final=res.chi2_final, lambda_final=res.lambda_final,
                     chi2_threshold=res.chi2_threshold, n_inlier_obs=res.n_inlier_obs, n_outlier_obs=res.n_outlier_obs)
 
