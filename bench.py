@@ -781,7 +781,7 @@ def bench_ba(ctx, pkg, args, torch, dev, dist, rank, world, stream):
                 try:
                     ctxs = [ctx] + [pkg.Context(device=dd, max_images=0, max_width=0, max_height=0, max_keypoints=1,
                                                 max_ba_poses=64, max_ba_points=32768, max_ba_obs=262144)
-                                    for dd in range(world) if dd != local_rank]
+                                    for dd in range(world) if dd != dev.index]
                     ctx.set_stream(None)
                     rm = pkg.Context.ba_optimize_multi(ctxs, *a, num_iterations=nit)
                     for _ in range(2):

@@ -1302,6 +1302,7 @@ extern "C" int vslam_ba_optimize(vslam_ctx* ctx, int n_poses, double* poses, int
                                  const int32_t* obs_pose, const int32_t* obs_point, const double* obs_uv,
                                  const double* Kmat, const vslam_ba_options* opt, vslam_ba_result* res,
                                  double* chi2_per_obs, uint8_t* point_inlier) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !poses || !Kmat || !opt || n_poses <= 0 || n_points < 0 || n_obs < 0) return VSLAM_E_INVALID;
     if (n_obs > 0 && (!obs_pose || !obs_point || !obs_uv)) return VSLAM_E_INVALID;
     if (n_points > 0 && !points) return VSLAM_E_INVALID;
@@ -1432,6 +1433,7 @@ extern "C" int vslam_ba_session_begin(vslam_ctx* ctx, int n_poses, const double*
                                       const int32_t* obs_point, const double* obs_uv, const double* Kmat,
                                       const vslam_ba_options* opt, int shard_begin, int shard_end, double* d_r1,
                                       double* d_r2, double* d_r3) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !poses || !points || !Kmat || !opt || !d_r1 || !d_r2 || !d_r3) return VSLAM_E_INVALID;
     if (n_poses <= 0 || n_points <= 0 || n_obs <= 0 || !obs_pose || !obs_point || !obs_uv) return VSLAM_E_INVALID;
     if (shard_begin < 0 || shard_end > n_points || shard_begin > shard_end) return VSLAM_E_INVALID;
@@ -1475,6 +1477,7 @@ static int ba_session_launch(vslam_ctx* ctx, int phase, double lambda) {
 
 // phase: 1 BUILD, 2 IMPORT_BUILD, 3 SCHUR(lambda), 4 SOLVE_UPDATE(lambda), 5 RELABEL_COUNT, 6 RELABEL_APPLY(threshold)
 extern "C" int vslam_ba_session_phase(vslam_ctx* ctx, int phase, double value) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || phase < BA_PH_BUILD || phase > BA_PH_RELABEL_APPLY) return VSLAM_E_INVALID;
     return ba_session_launch(ctx, phase, value);
 }
@@ -1491,6 +1494,7 @@ extern "C" int vslam_ba_session_trial_done(vslam_ctx* ctx, int accept) {
 // inlier flags (zeros elsewhere) so that a sum over ranks assembles the full arrays
 extern "C" int vslam_ba_session_end(vslam_ctx* ctx, double* poses, double* points, double* chi2_per_obs,
                                     uint8_t* point_inlier) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !ctx->ba || !ctx->ba->sess_open) return VSLAM_E_INVALID;
     BaState* b = ctx->ba;
     const BaParams& P = *b->sess;
@@ -2037,6 +2041,7 @@ ba_dense_syrk_kernel(const double* __restrict__ Y, int ldY, int n, int tiles, in
 // d_S_dense (n x n device doubles, upper triangle r <= c written, the rest zero) and reports the device time of the
 // two kernels.  The session's own (sparse) result stays in its r2 buffer for comparison.
 extern "C" int vslam_ba_session_schur_dense(vslam_ctx* ctx, double* d_S_dense, float* ms_fill, float* ms_syrk) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !ctx->ba || !ctx->ba->sess_open || !d_S_dense) return VSLAM_E_INVALID;
     BaState* b = ctx->ba;
     BaParams P = *b->sess;

@@ -87,6 +87,20 @@ static inline void vslam_time_end(vslam_ctx* ctx) {
     ctx->n_trec++;
 }
 
+// Every entry point runs on the device of its context, whatever device the calling thread had current, and leaves the
+// caller's current device as it found it (a process may hold contexts on several devices: vslam_ba_optimize_multi).
+struct VslamDeviceGuard {
+    int prev;
+    bool switched;
+    explicit VslamDeviceGuard(const vslam_ctx* ctx) : prev(-1), switched(false) {
+        if (!ctx) return;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != ctx->cfg.device) switched = cudaSetDevice(ctx->cfg.device) == cudaSuccess;
+    }
+    ~VslamDeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // Level 0 is read in place from the caller's buffers (left images first, then right images).

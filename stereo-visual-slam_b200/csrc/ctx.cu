@@ -34,6 +34,8 @@ extern "C" int vslam_ctx_create(const vslam_config* cfg, vslam_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return VSLAM_E_NODEVICE;
     if (prop.major != 10) return VSLAM_E_NODEVICE;  // the only code in this library is sm_100a SASS
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);  // the caller's current device is restored on return
     if (cudaSetDevice(cfg->device) != cudaSuccess) return VSLAM_E_NODEVICE;
 
     vslam_ctx* ctx = (vslam_ctx*)calloc(1, sizeof(vslam_ctx));
@@ -55,14 +57,18 @@ extern "C" int vslam_ctx_create(const vslam_config* cfg, vslam_ctx** out) {
     if (st == VSLAM_OK) st = vslam_sgbm_init(ctx);
     if (st != VSLAM_OK) {
         vslam_ctx_destroy(ctx);
+        if (prev_dev >= 0) cudaSetDevice(prev_dev);
         return st;
     }
     *out = ctx;
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
     return VSLAM_OK;
 }
 
 extern "C" void vslam_ctx_destroy(vslam_ctx* ctx) {
     if (!ctx) return;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
     vslam_sgbm_free(ctx);
@@ -80,6 +86,7 @@ extern "C" void vslam_ctx_destroy(vslam_ctx* ctx) {
     }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     free(ctx);
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
 }
 
 extern "C" int vslam_ctx_set_stream(vslam_ctx* ctx, void* cuda_stream) {
@@ -95,6 +102,7 @@ extern "C" int vslam_ctx_set_concurrency(vslam_ctx* ctx, int on) {
 }
 
 extern "C" int vslam_ctx_synchronize(vslam_ctx* ctx) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx) return VSLAM_E_INVALID;
     VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VSLAM_OK;
@@ -113,6 +121,7 @@ extern "C" int vslam_kernel_count(void) { return VK_COUNT; }
 extern "C" const char* vslam_kernel_name(int id) { return id >= 0 && id < VK_COUNT ? k_kernel_names[id] : ""; }
 
 extern "C" int vslam_ctx_timing_enable(vslam_ctx* ctx, int on) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx) return VSLAM_E_INVALID;
     VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->timing_on = on ? 1 : 0;
@@ -126,6 +135,7 @@ extern "C" int vslam_ctx_timing_enable(vslam_ctx* ctx, int on) {
 
 // synchronise, fold the pending event pairs into per-kernel totals and report kernel `id`
 extern "C" int vslam_ctx_timing_read(vslam_ctx* ctx, int id, double* total_ms, int64_t* launches) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || id < 0 || id >= VK_COUNT) return VSLAM_E_INVALID;
     if (ctx->n_trec > 0) {
         VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -222,6 +222,7 @@ void vslam_front_free(vslam_ctx* ctx) {
 
 extern "C" int vslam_triangulate(vslam_ctx* ctx, const float* xl, const float* xr, int n, const double* P1,
                                  const double* P2, const double* T_c_w, float* xyz_world, uint8_t* flags) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || n < 0 || !P1 || !P2) return VSLAM_E_INVALID;
     if (n == 0) return VSLAM_OK;
     if (!xl || !xr || !xyz_world || !flags) return VSLAM_E_INVALID;
@@ -250,6 +251,7 @@ extern "C" int vslam_triangulate_matches_batch_dev(vslam_ctx* ctx, const vslam_k
                                                    const vslam_dmatch* d_matches, const int32_t* d_n_matches,
                                                    int match_stride, int batch, const double* P1, const double* P2,
                                                    const double* d_T_c_w, float* d_xyz, uint8_t* d_flags) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !d_kp_left || !d_kp_right || !d_matches || !d_n_matches || !P1 || !P2 || !d_xyz || !d_flags)
         return VSLAM_E_INVALID;
     if (batch <= 0 || match_stride <= 0) return VSLAM_E_INVALID;
@@ -305,6 +307,7 @@ extern "C" int vslam_stereo_frontend_batch_dev(vslam_ctx* ctx, const uint8_t* d_
                                                const double* d_T_c_w, vslam_keypoint* d_kp, uint8_t* d_desc,
                                                int32_t* d_n_kp, vslam_dmatch* d_matches, int32_t* d_n_matches,
                                                float* d_xyz, uint8_t* d_flags) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !d_left || !d_right || !P1 || !P2 || !d_kp || !d_desc || !d_n_kp || !d_matches || !d_n_matches ||
         !d_xyz || !d_flags)
         return VSLAM_E_INVALID;
@@ -352,6 +355,7 @@ extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, 
                                            const double* P1, const double* P2, const double* T_c_w,
                                            vslam_keypoint* kp, uint8_t* desc, int32_t* n_kp, vslam_dmatch* matches,
                                            int32_t* n_matches, float* xyz, uint8_t* flags) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !n_kp || !n_matches) return VSLAM_E_INVALID;
     if (!left || !right) return VSLAM_E_INVALID;  // reference: -1 "Could not open or find the image"
     if (!P1 || !P2 || !kp || !desc || !matches || !xyz || !flags) return VSLAM_E_INVALID;

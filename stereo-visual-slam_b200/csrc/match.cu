@@ -237,6 +237,7 @@ extern "C" int vslam_match_hamming_batch_dev(vslam_ctx* ctx, const uint8_t* d_qu
                                              int t_stride_rows, int batch, int max_rows, int cross_check,
                                              double gate_rel, double gate_abs, vslam_dmatch* d_out, int out_stride,
                                              int32_t* d_n_out) {
+    VslamDeviceGuard device_guard__(ctx);
     return vslam_match_enqueue(ctx, d_query, d_nq, q_stride_rows, d_train, d_nt, t_stride_rows, batch, max_rows,
                                cross_check, gate_rel, gate_abs, d_out, out_stride, d_n_out, 0);
 }
@@ -269,6 +270,7 @@ int vslam_match_enqueue(vslam_ctx* ctx, const uint8_t* d_query, const int32_t* d
 extern "C" int vslam_match_hamming(vslam_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt,
                                    int cross_check, double gate_rel, double gate_abs, vslam_dmatch* out,
                                    int* n_out) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !n_out || nq < 0 || nt < 0) return VSLAM_E_INVALID;
     *n_out = 0;
     if (nq == 0 || nt == 0) return VSLAM_OK;

@@ -1186,6 +1186,7 @@ extern "C" int vslam_orb_detect_compute_batch_dev(vslam_ctx* ctx, const uint8_t*
                                                   int height, int row_pitch, long long image_stride, int nfeatures,
                                                   int anms_keep, float anms_c, vslam_keypoint* d_kp, uint8_t* d_desc,
                                                   int32_t* d_n) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !d_images || !d_kp || !d_desc || !d_n) return VSLAM_E_INVALID;
     if (width <= 0 || height <= 0 || row_pitch < width) return VSLAM_E_INVALID;
     ImgSrc src;
@@ -1211,6 +1212,7 @@ int vslam_orb_check_flags(vslam_ctx* ctx, int n_img) {
 }
 
 extern "C" int vslam_orb_last_flags(vslam_ctx* ctx, int n_images) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !ctx->orb) return VSLAM_E_INVALID;
     return vslam_orb_check_flags(ctx, n_images);
 }
@@ -1219,6 +1221,7 @@ extern "C" int vslam_orb_detect_compute_batch(vslam_ctx* ctx, const uint8_t* ima
                                               int height, int row_pitch, long long image_stride, int nfeatures,
                                               int anms_keep, float anms_c, vslam_keypoint* kp_out, uint8_t* desc_out,
                                               int32_t* n_out) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !n_out) return VSLAM_E_INVALID;
     if (!images) return VSLAM_E_INVALID;  // reference: "Could not open or find the image" -> -1 (vo.cpp:73-77)
     if (!kp_out || !desc_out) return VSLAM_E_INVALID;
@@ -1261,6 +1264,7 @@ extern "C" int vslam_orb_detect_compute_batch(vslam_ctx* ctx, const uint8_t* ima
 extern "C" int vslam_orb_detect_compute(vslam_ctx* ctx, const uint8_t* image, int width, int height, int row_pitch,
                                         int nfeatures, int anms_keep, float anms_c, vslam_keypoint* kp_out,
                                         uint8_t* desc_out, int32_t* n_out) {
+    VslamDeviceGuard device_guard__(ctx);
     return vslam_orb_detect_compute_batch(ctx, image, 1, width, height, row_pitch, 0, nfeatures, anms_keep, anms_c,
                                           kp_out, desc_out, n_out);
 }
@@ -1268,6 +1272,7 @@ extern "C" int vslam_orb_detect_compute(vslam_ctx* ctx, const uint8_t* image, in
 // test/debug taps: copy intermediate device state of image `img` to host buffers (any may be NULL)
 extern "C" int vslam_orb_debug_read(vslam_ctx* ctx, int img, int level, uint8_t* level_pixels, uint8_t* blurred_pixels,
                                     int* w_out, int* h_out, uint32_t* cand_xy_score, int cand_cap, int* n_cand) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !ctx->orb || !ctx->orb->geom_valid) return VSLAM_E_INVALID;
     OrbState* o = ctx->orb;
     if (img < 0 || img >= o->max_images || level < 0 || level >= ORB_NL) return VSLAM_E_INVALID;

@@ -438,6 +438,7 @@ static void pnp_draw_samples(int n, int iters, int* out) {
 extern "C" int vslam_pnp_ransac(vslam_ctx* ctx, const float* xyz, const float* uv, int n, const double* Kmat, int iters,
                                 float reproj_err, double confidence, double* rvec, double* tvec, double* T_c_w,
                                 int32_t* inliers, int32_t* n_inliers) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !n_inliers || !Kmat || n < 0) return VSLAM_E_INVALID;
     *n_inliers = 0;
     // OpenCV asserts n >= 4 and switches to a P3P kernel for exactly 4 points; the reference rejects any frame with
@@ -499,6 +500,7 @@ extern "C" int vslam_pnp_ransac(vslam_ctx* ctx, const float* xyz, const float* u
 /* test tap: model (R row-major 9, t 3) and inlier count of RANSAC sample `it` of the last vslam_pnp_ransac call, and
  * the number of iterations OpenCV's loop would have executed */
 extern "C" int vslam_pnp_debug_read(vslam_ctx* ctx, int it, double* R_t12, int32_t* count, int32_t* executed) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !ctx->pnp || it < 0 || it >= PNP_MAX_HYP) return VSLAM_E_INVALID;
     PnpState* p = ctx->pnp;
     VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -510,6 +512,7 @@ extern "C" int vslam_pnp_debug_read(vslam_ctx* ctx, int it, double* R_t12, int32
 
 extern "C" int vslam_anms(vslam_ctx* ctx, const vslam_keypoint* keypoints, int n, int num, float c_robust,
                           int32_t* keep_idx, int32_t* n_keep) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !n_keep || n < 0) return VSLAM_E_INVALID;
     *n_keep = 0;
     if (n == 0) return VSLAM_OK;

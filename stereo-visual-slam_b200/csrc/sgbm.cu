@@ -1072,6 +1072,7 @@ static int sgbm_enqueue(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_
 extern "C" int vslam_sgbm_compute_dev(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_right, int n_pairs, int width,
                                       int height, int row_pitch, long long image_stride, const vslam_sgbm_params* params,
                                       int16_t* d_disp16, float* d_disp_f32) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !d_left || !d_right || n_pairs < 0 || row_pitch < width || (!d_disp16 && !d_disp_f32)) return VSLAM_E_INVALID;
     SgParams p;
     int st = sgbm_check(params, width, height, &p);
@@ -1113,6 +1114,7 @@ extern "C" int vslam_sgbm_compute_dev(vslam_ctx* ctx, const uint8_t* d_left, con
 extern "C" int vslam_sgbm_compute(vslam_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_pairs, int width, int height,
                                   int row_pitch, long long image_stride, const vslam_sgbm_params* params, int16_t* disp16,
                                   float* disp_f32) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !left || !right || n_pairs < 0 || row_pitch < width || (!disp16 && !disp_f32)) return VSLAM_E_INVALID;
     SgParams p;
     int st = sgbm_check(params, width, height, &p);
@@ -1148,6 +1150,7 @@ extern "C" int vslam_sgbm_compute(vslam_ctx* ctx, const uint8_t* left, const uin
 
 // test tap: stage 0 = C, 1..3 = path volumes (1 holds S4 after the horizontal sweep), 4 = raw disparity, 5 = median
 extern "C" int vslam_sgbm_debug_read(vslam_ctx* ctx, int pair, int stage, void* host_out, size_t bytes) {
+    VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !ctx->sgbm || !host_out || pair < 0 || pair >= ctx->sgbm->cap_pairs) return VSLAM_E_INVALID;
     SgbmState* s = ctx->sgbm;
     const size_t vol = (size_t)s->cap_h * (s->cap_w - SG_D) * SG_NDP * sizeof(uint32_t);
