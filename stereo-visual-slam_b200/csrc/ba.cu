@@ -1550,10 +1550,14 @@ __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
 }
 
 // Called by every thread after its peer stores of this exchange.  Returns when every rank's data of `epoch` is visible.
+// The grid barrier orders every thread's peer stores before the publishing threads (gpu scope); ONE fence.sys + release
+// store per peer then publishes them at system scope (cumulativity) -- a fence.sys in every thread costs ~100 us here.
 __device__ void ba_multi_signal_wait(const BaMulti& M, cg::grid_group& grid, unsigned epoch) {
-    __threadfence_system();  // this thread's peer stores are ordered before whatever follows the grid barrier
     grid.sync();
-    if (blockIdx.x == 0 && (int)threadIdx.x < M.world) st_release_sys_u32(M.flags[threadIdx.x] + M.rank, epoch);
+    if (blockIdx.x == 0 && (int)threadIdx.x < M.world) {
+        __threadfence_system();
+        st_release_sys_u32(M.flags[threadIdx.x] + M.rank, epoch);
+    }
     if ((int)threadIdx.x < M.world) {
         const unsigned* f = M.flags[M.rank] + threadIdx.x;
         const unsigned long long t0 = gtimer();
@@ -1602,16 +1606,15 @@ __device__ double ba_multi_exchange_system(const BaParams& P, const BaMulti& M, 
     return chi;
 }
 
-// small exchange: every rank publishes `len` doubles (taken from `src` in local global memory); afterwards slot g of the
-// returned area holds rank g's values.  Two parities so that two consecutive small exchanges never share a slot.
-__device__ const double* ba_multi_exchange_small(const BaMulti& M, cg::grid_group& grid, unsigned epoch, const double* src,
-                                                 int len, int gtid) {
+// small exchange: thread j < len of every rank publishes its value v (slot j of the rank's area on every device);
+// afterwards slot g of the returned area holds rank g's values.  Two parities so that two consecutive small exchanges
+// never share a slot.
+__device__ const double* ba_multi_exchange_small(const BaMulti& M, cg::grid_group& grid, unsigned epoch, double v, int len,
+                                                 int gtid) {
     const int par = epoch & 1;
     const size_t off = ((size_t)par * M.world + M.rank) * BA_XS;
-    if (gtid < len) {
-        const double v = src[gtid];
+    if (gtid < len)
         for (int g = 0; g < M.world; ++g) M.xsmall[g][off + gtid] = v;
-    }
     ba_multi_signal_wait(M, grid, epoch);
     return M.xsmall[M.rank] + (size_t)par * M.world * BA_XS;
 }
@@ -1622,7 +1625,6 @@ ba_lm_multi_kernel(const __grid_constant__ BaParams P, const __grid_constant__ B
     cg::grid_group grid = cg::this_grid();
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
     BaScalars* sc = P.sc;
-    double* stage = P.x + P.n + 3 * (size_t)P.L;  // n spare doubles behind the update vector: small-exchange staging
     unsigned epoch = M.epoch0;
     int cur = 0, trials = 0, accepted = 0, it = 0;
     double lambda = 0.0, ni = 2.0, chi_first = 0.0, chi_last = 0.0;
@@ -1641,10 +1643,9 @@ ba_lm_multi_kernel(const __grid_constant__ BaParams P, const __grid_constant__ B
         const double chi_local = sc->chi_cur;
         if (it == 0) {
             // computeLambdaInit: tau * max |diagonal| over the landmark blocks of all ranks and the SUMMED pose blocks
-            if (gtid < P.n) stage[gtid] = P.Hpp[(gtid / 6) * 36 + (gtid % 6) * 7];
-            if (gtid == 0) stage[P.n] = __longlong_as_double((long long)sc->maxdiag_bits);
-            grid.sync();
-            const double* rs = ba_multi_exchange_small(M, grid, ++epoch, stage, P.n + 1, gtid);
+            const double v0 = gtid < P.n ? P.Hpp[(gtid / 6) * 36 + (gtid % 6) * 7]
+                                         : gtid == P.n ? __longlong_as_double((long long)sc->maxdiag_bits) : 0.0;
+            const double* rs = ba_multi_exchange_small(M, grid, ++epoch, v0, P.n + 1, gtid);
             __shared__ double s_md;
             if (threadIdx.x == 0) {
                 double md = 0.0;
@@ -1681,14 +1682,8 @@ ba_lm_multi_kernel(const __grid_constant__ BaParams P, const __grid_constant__ B
             grid.sync();
             ba_phase_trial_err(P, cur, slot, gtid, gsize);
             grid.sync();
-            const int ok_local = sc->solve_ok[slot];
-            if (gtid == 0) {
-                stage[0] = sc->chi_trial[slot];
-                stage[1] = sc->scale[slot];
-                stage[2] = (double)ok_local;
-            }
-            grid.sync();
-            const double* rs = ba_multi_exchange_small(M, grid, ++epoch, stage, 3, gtid);
+            const double v3 = gtid == 0 ? sc->chi_trial[slot] : gtid == 1 ? sc->scale[slot] : gtid == 2 ? (double)sc->solve_ok[slot] : 0.0;
+            const double* rs = ba_multi_exchange_small(M, grid, ++epoch, v3, 3, gtid);
             double tchi = 0.0, tscale = 0.0, tok = 0.0;
             for (int g = 0; g < M.world; ++g) {
                 tchi += __ldcg(rs + (size_t)g * BA_XS);
@@ -1725,9 +1720,7 @@ ba_lm_multi_kernel(const __grid_constant__ BaParams P, const __grid_constant__ B
         grid.sync();
         ba_phase_build_edges(P, cur, gtid, gsize);
         grid.sync();
-        if (gtid == 0) stage[0] = sc->chi_cur;
-        grid.sync();
-        const double* rs = ba_multi_exchange_small(M, grid, ++epoch, stage, 1, gtid);
+        const double* rs = ba_multi_exchange_small(M, grid, ++epoch, gtid == 0 ? sc->chi_cur : 0.0, 1, gtid);
         double c = 0.0;
         for (int g = 0; g < M.world; ++g) c += __ldcg(rs + (size_t)g * BA_XS);
         chi_first = chi_last = c;
@@ -1736,9 +1729,7 @@ ba_lm_multi_kernel(const __grid_constant__ BaParams P, const __grid_constant__ B
     grid.sync();
     ba_phase_relabel_count(P, gtid, gsize);
     grid.sync();
-    if (gtid < 6) stage[gtid] = (double)sc->cnt_le[gtid];
-    grid.sync();
-    const double* rc = ba_multi_exchange_small(M, grid, ++epoch, stage, 6, gtid);
+    const double* rc = ba_multi_exchange_small(M, grid, ++epoch, gtid < 6 ? (double)sc->cnt_le[gtid] : 0.0, 6, gtid);
     int cnt[6];
     for (int r = 0; r < 6; ++r) {
         double c = 0.0;

@@ -2,6 +2,7 @@
 # Multi-GPU visit (gpurun --gpus N -- bash tools/gpu_multi.sh N): device-side multi-GPU BA tests + the N-rank bench line.
 N=${1:-2}
 mkdir -p gpurun_out
+[ -x tools/micro/minmax_pipes ] && tools/micro/minmax_pipes > gpurun_out/minmax_pipes.txt 2>&1; cat gpurun_out/minmax_pipes.txt
 nvidia-smi topo -m > gpurun_out/topo_${N}gpu.txt 2>&1
 timeout 900 python -m pytest tests/test_ba_multi_gpu.py tests/test_ba_sharded_gpu.py -x -q -m gpu > gpurun_out/pytest_multi_${N}gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_multi_${N}gpu.log
 tail -15 gpurun_out/pytest_multi_${N}gpu.log
