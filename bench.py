@@ -804,6 +804,7 @@ def bench_ba(ctx, pkg, args, torch, dev, dist, rank, world, stream):
                         "kernel_iters_per_s": rm["iterations"] / (kmax * 1e-3), "ms_per_iter_kernel": kmax / rm["iterations"],
                         "e2e_iters_per_s": rm["iterations"] / dtm, "exchanges": rm["exchanges"], "trials": rm["trials"],
                         "exchange_bytes_per_trial_per_gpu": 8 * ((6 * nk) ** 2 // 2 + 3 * 6 * nk) * world,
+                        "device_profile_us": ctx.ba_multi_last_profile_us(),
                         "speedup_vs_one_gpu_kernel": kms / kmax,
                         "pose_rel_diff_vs_single_gpu": float(np.abs(rm["poses"] - r["poses"]).max() / np.abs(r["poses"]).max())}
                     for cc in ctxs[1:]:

@@ -347,6 +347,11 @@ int vslam_ba_optimize_multi(vslam_ctx* const* ctxs, int n_dev, int n_poses, doub
                             const double* Kmat, const vslam_ba_options* opt, vslam_ba_result* res, double* chi2_per_obs,
                             uint8_t* point_inlier);
 
+/* device-side profile of the last vslam_ba_optimize_multi call as seen by rank 0 (ctxs[0]): nanoseconds (GPU
+ * globaltimer) [kernel start .. first exchange complete (includes the launch skew between the GPUs), first exchange
+ * complete .. end, inside the per-trial system exchanges, publish + wait for the slowest peer over all exchanges] */
+int vslam_ba_multi_last_profile_ns(vslam_ctx* ctx, uint64_t* ns4);
+
 /* Measurement probe (the north star's "tensor cores only for the dense J^T J camera-block GEMM"): after phase SCHUR of a
  * session that covers ALL landmarks, form the same product -(Hpl Hll^-1 Hpl^T) as ONE dense fp64 SYRK on the tensor
  * cores (DMMA m8n8k4) into d_S_dense (n x n device doubles, n = 6 * n_poses, upper triangle written) and report the

@@ -1107,6 +1107,7 @@ struct BaState {
     uint8_t* d_inlier;
     BaScalars* d_sc;
     BaScalars* h_sc;  // pinned
+    void* h_stage;    // pinned staging arena of the marshalled graph (ba_stage_bytes)
     // landmark-sharded session (multi-GPU): parameters of the open session, current buffer, trial counter
     BaParams* sess;
     int sess_open, sess_cur, sess_trials;
@@ -1122,6 +1123,8 @@ __global__ void ba_phase_kernel(const __grid_constant__ BaParams P, int phase, d
                                 double* r3);
 struct BaMulti;
 __global__ void ba_lm_multi_kernel(const __grid_constant__ BaParams P, const __grid_constant__ BaMulti M);
+
+static size_t ba_stage_bytes(size_t K, size_t L, size_t O);
 
 // shared memory of one CTA: max(pose partials K*42, per-CTA S n*n+n, in-shared-memory Cholesky n*n+n) doubles
 static int ba_smem_bytes(int K) {
@@ -1170,6 +1173,7 @@ int vslam_ba_init(vslam_ctx* ctx) {
     VSLAM_CUDA(ctx, cudaMalloc(&b->d_inlier, L));
     VSLAM_CUDA(ctx, cudaMalloc(&b->d_sc, sizeof(BaScalars)));
     VSLAM_CUDA(ctx, cudaMallocHost(&b->h_sc, sizeof(BaScalars)));
+    VSLAM_CUDA(ctx, cudaMallocHost(&b->h_stage, ba_stage_bytes(K, L, O)));
     // dynamic shared memory is sized per call from the actual K (ba_smem_bytes); opt in to the largest case here
     b->smem_bytes = 0;
     for (size_t k = 1; k <= K; ++k) {
@@ -1191,6 +1195,7 @@ void vslam_ba_free(vslam_ctx* ctx) {
     cudaFree(b->d_bs); cudaFree(b->d_x); cudaFree(b->d_dbl); cudaFree(b->d_U); cudaFree(b->d_block_flag); cudaFree(b->d_pose_start); cudaFree(b->d_pose_obs); cudaFree(b->d_obs_of); cudaFree(b->d_chi2); cudaFree(b->d_obs_pose);
     cudaFree(b->d_obs_point); cudaFree(b->d_obs_orig); cudaFree(b->d_lm_start); cudaFree(b->d_inlier); cudaFree(b->d_sc);
     cudaFreeHost(b->h_sc);
+    if (b->h_stage) cudaFreeHost(b->h_stage);
     if (b->d_dense) cudaFree(b->d_dense);
     if (b->x_big) { cudaFree(b->x_big); cudaFree(b->x_small); cudaFree(b->x_flags); cudaFree(b->d_bp_glob); }
     free(b->sess);
@@ -1202,19 +1207,38 @@ void vslam_ba_free(vslam_ctx* ctx) {
 // sorts of the edge list by landmark (the device order) and by pose (CSR over device indices), duplicate (pose,
 // landmark) detection -- once on the host -- then the uploads to one device.  Index bookkeeping only, no arithmetic on
 // the measurements.
-struct BaHostGraph {
+struct BaHostGraph {  // arrays live in the pinned staging arena of a context (BaState::h_stage)
     int K, n_points, n_obs, has_dup;
-    std::vector<int> lm_start, op, ol, oo, pose_start, pose_obs;
-    std::vector<double> uv;
+    int *lm_start, *op, *ol, *oo, *pose_start, *pose_obs;
+    double *uv, *poses, *points;
 };
 
-static int ba_prepare_host(BaHostGraph& g, int K, int n_points, int n_obs, const int32_t* obs_pose,
-                           const int32_t* obs_point, const double* obs_uv) {
-    const int L = n_points > 0 ? n_points : 1;
-    const int no = n_obs > 0 ? n_obs : 1;
+static size_t ba_stage_bytes(size_t K, size_t L, size_t O) {
+    return (L + 1 + K + 1 + 4 * O + 16) * sizeof(int) + (2 * O + 12 * K + 3 * L + 8) * sizeof(double);
+}
+
+static void ba_graph_bind(BaHostGraph& g, void* mem, int K, int n_points, int n_obs) {
+    const size_t L = n_points > 0 ? n_points : 1, O = n_obs > 0 ? n_obs : 1;
+    double* d = (double*)mem;  // doubles first: 8-byte alignment for free
+    g.uv = d; d += 2 * O;
+    g.poses = d; d += 12 * (size_t)K;
+    g.points = d; d += 3 * L;
+    int* q = (int*)d;
+    g.lm_start = q; q += L + 1;
+    g.pose_start = q; q += K + 1;
+    g.op = q; q += O;
+    g.ol = q; q += O;
+    g.oo = q; q += O;
+    g.pose_obs = q;
     g.K = K; g.n_points = n_points; g.n_obs = n_obs; g.has_dup = 0;
-    g.lm_start.assign(L + 1, 0); g.pose_start.assign(K + 1, 0);
-    g.op.resize(no); g.ol.resize(no); g.oo.resize(no); g.pose_obs.resize(no); g.uv.resize(2 * (size_t)no);
+}
+
+static int ba_prepare_host(BaHostGraph& g, const double* poses, const double* points, const int32_t* obs_pose,
+                           const int32_t* obs_point, const double* obs_uv) {
+    const int K = g.K, n_points = g.n_points, n_obs = g.n_obs;
+    const int L = n_points > 0 ? n_points : 1;
+    memset(g.lm_start, 0, (size_t)(L + 1) * sizeof(int));
+    memset(g.pose_start, 0, (size_t)(K + 1) * sizeof(int));
     for (int i = 0; i < n_obs; ++i) {
         if (obs_point[i] < 0 || obs_point[i] >= n_points || obs_pose[i] < 0 || obs_pose[i] >= K) return VSLAM_E_INVALID;
         g.lm_start[obs_point[i] + 1]++;
@@ -1223,7 +1247,7 @@ static int ba_prepare_host(BaHostGraph& g, int K, int n_points, int n_obs, const
     for (int l = 0; l < L; ++l) g.lm_start[l + 1] += g.lm_start[l];
     for (int k = 0; k < K; ++k) g.pose_start[k + 1] += g.pose_start[k];
     {
-        std::vector<int> fill(g.lm_start.begin(), g.lm_start.end() - 1);
+        std::vector<int> fill(g.lm_start, g.lm_start + L);
         for (int i = 0; i < n_obs; ++i) {
             const int d = fill[obs_point[i]]++;
             g.op[d] = obs_pose[i]; g.ol[d] = obs_point[i]; g.oo[d] = i;
@@ -1231,52 +1255,53 @@ static int ba_prepare_host(BaHostGraph& g, int K, int n_points, int n_obs, const
         }
     }
     {
-        std::vector<int> fill(g.pose_start.begin(), g.pose_start.end() - 1);
+        std::vector<int> fill(g.pose_start, g.pose_start + K);
         for (int d = 0; d < n_obs; ++d) g.pose_obs[fill[g.op[d]]++] = d;  // ascending device index within each pose
     }
     for (int l = 0; l < n_points && !g.has_dup; ++l)
         for (int i = g.lm_start[l]; i < g.lm_start[l + 1] && !g.has_dup; ++i)
             for (int j = i + 1; j < g.lm_start[l + 1]; ++j)
                 if (g.op[i] == g.op[j]) { g.has_dup = 1; break; }
+    memcpy(g.poses, poses, (size_t)K * 96);
+    if (n_points > 0) memcpy(g.points, points, (size_t)n_points * 24);
     return VSLAM_OK;
 }
 
-// uploads on the context stream of the CURRENT device; the caller synchronises before `g` goes out of scope
-static int ba_upload(vslam_ctx* ctx, BaState* b, const BaHostGraph& g, const double* poses, const double* points) {
+// uploads (from the pinned arena: truly asynchronous) on the context stream of the CURRENT device
+static int ba_upload(vslam_ctx* ctx, BaState* b, const BaHostGraph& g) {
     const int K = g.K, n_points = g.n_points, n_obs = g.n_obs;
     const int L = n_points > 0 ? n_points : 1;
     cudaStream_t s = ctx->stream;
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_poses, poses, (size_t)K * 96, cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_poses, g.poses, (size_t)K * 96, cudaMemcpyHostToDevice, s));
     if (n_points > 0) {
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_points, points, (size_t)n_points * 24, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_points, g.points, (size_t)n_points * 24, cudaMemcpyHostToDevice, s));
         // pose-only mode never writes the trial points: keep both buffers equal
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_points + (size_t)L * 3, points, (size_t)n_points * 24, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_points + (size_t)L * 3, b->d_points, (size_t)n_points * 24, cudaMemcpyDeviceToDevice, s));
     }
     if (n_obs > 0) {
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_pose, g.op.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_point, g.ol.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_orig, g.oo.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_pose_obs, g.pose_obs.data(), (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
-        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_uv, g.uv.data(), (size_t)n_obs * 16, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_pose, g.op, (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_point, g.ol, (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_obs_orig, g.oo, (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_pose_obs, g.pose_obs, (size_t)n_obs * 4, cudaMemcpyHostToDevice, s));
+        VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_uv, g.uv, (size_t)n_obs * 16, cudaMemcpyHostToDevice, s));
     }
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_lm_start, g.lm_start.data(), (size_t)(L + 1) * 4, cudaMemcpyHostToDevice, s));
-    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_pose_start, g.pose_start.data(), (size_t)(K + 1) * 4, cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_lm_start, g.lm_start, (size_t)(L + 1) * 4, cudaMemcpyHostToDevice, s));
+    VSLAM_CUDA(ctx, cudaMemcpyAsync(b->d_pose_start, g.pose_start, (size_t)(K + 1) * 4, cudaMemcpyHostToDevice, s));
     VSLAM_CUDA(ctx, cudaMemsetAsync(b->d_obs_of, 0xFF, (size_t)K * L * sizeof(int), s));
     VSLAM_CUDA(ctx, cudaMemsetAsync(b->d_block_flag, 0, (size_t)(K * (K + 1) / 2) * sizeof(int), s));
     return VSLAM_OK;
 }
 
+// the host-synchronous entry points finish (stream synchronised) before they return, so the arena is free again
 static int ba_marshal(vslam_ctx* ctx, BaState* b, int K, int n_points, int n_obs, const double* poses,
                       const double* points, const int32_t* obs_pose, const int32_t* obs_point, const double* obs_uv,
                       int* has_dup) {
     BaHostGraph g;
-    int st = ba_prepare_host(g, K, n_points, n_obs, obs_pose, obs_point, obs_uv);
+    ba_graph_bind(g, b->h_stage, K, n_points, n_obs);
+    int st = ba_prepare_host(g, poses, points, obs_pose, obs_point, obs_uv);
     if (st != VSLAM_OK) return st;
     *has_dup = g.has_dup;
-    st = ba_upload(ctx, b, g, poses, points);
-    if (st != VSLAM_OK) return st;
-    VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the staging vectors go out of scope
-    return VSLAM_OK;
+    return ba_upload(ctx, b, g);
 }
 
 static void ba_fill_params(BaParams& P, BaState* b, int K, int n_points, int n_obs, const vslam_ba_options* opt,
@@ -1456,6 +1481,7 @@ extern "C" int vslam_ba_session_begin(vslam_ctx* ctx, int n_poses, const double*
     P.S = d_r2; P.bs = d_r2 + (size_t)P.n * P.n;  // reduced camera system lives in r2
     b->sess_open = 1; b->sess_cur = 0; b->sess_trials = 0;
     b->sess_r1 = d_r1; b->sess_r2 = d_r2; b->sess_r3 = d_r3;
+    VSLAM_CUDA(ctx, cudaStreamSynchronize(s));  // the pinned staging arena is free again when this returns
     return VSLAM_OK;
 }
 
@@ -1552,8 +1578,9 @@ __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
 // Called by every thread after its peer stores of this exchange.  Returns when every rank's data of `epoch` is visible.
 // The grid barrier orders every thread's peer stores before the publishing threads (gpu scope); ONE fence.sys + release
 // store per peer then publishes them at system scope (cumulativity) -- a fence.sys in every thread costs ~100 us here.
-__device__ void ba_multi_signal_wait(const BaMulti& M, cg::grid_group& grid, unsigned epoch) {
+__device__ void ba_multi_signal_wait(const BaMulti& M, cg::grid_group& grid, unsigned epoch, unsigned long long* wait_ns) {
     grid.sync();
+    const unsigned long long t_pub = gtimer();
     if (blockIdx.x == 0 && (int)threadIdx.x < M.world) {
         __threadfence_system();
         st_release_sys_u32(M.flags[threadIdx.x] + M.rank, epoch);
@@ -1566,6 +1593,7 @@ __device__ void ba_multi_signal_wait(const BaMulti& M, cg::grid_group& grid, uns
         }
     }
     __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) *wait_ns += gtimer() - t_pub;  // publish + wait for the slowest peer
 }
 
 // big exchange + rank-ordered sum: S <- sum_g S_g + lambda I, bs <- sum_g bs_g, bp_glob <- sum_g bp_g; returns sum_g chi_g
@@ -1584,7 +1612,7 @@ __device__ double ba_multi_exchange_system(const BaParams& P, const BaMulti& M, 
         const double v = i < n ? P.bs[i] : i < 2 * n ? P.bp[i - n] : chi_local;
         for (int g = 0; g < M.world; ++g) M.xbig[g][slot + (size_t)n * n + i] = v;
     }
-    ba_multi_signal_wait(M, grid, epoch);
+    ba_multi_signal_wait(M, grid, epoch, &P.sc->phase_ns[11]);
     const double* rx = M.xbig[M.rank];
     for (int r = gw; r < n; r += nw) {
         const int c0 = 6 * (r / 6);
@@ -1610,12 +1638,12 @@ __device__ double ba_multi_exchange_system(const BaParams& P, const BaMulti& M, 
 // afterwards slot g of the returned area holds rank g's values.  Two parities so that two consecutive small exchanges
 // never share a slot.
 __device__ const double* ba_multi_exchange_small(const BaMulti& M, cg::grid_group& grid, unsigned epoch, double v, int len,
-                                                 int gtid) {
+                                                 int gtid, unsigned long long* wait_ns) {
     const int par = epoch & 1;
     const size_t off = ((size_t)par * M.world + M.rank) * BA_XS;
     if (gtid < len)
         for (int g = 0; g < M.world; ++g) M.xsmall[g][off + gtid] = v;
-    ba_multi_signal_wait(M, grid, epoch);
+    ba_multi_signal_wait(M, grid, epoch, wait_ns);
     return M.xsmall[M.rank] + (size_t)par * M.world * BA_XS;
 }
 
@@ -1628,8 +1656,14 @@ ba_lm_multi_kernel(const __grid_constant__ BaParams P, const __grid_constant__ B
     unsigned epoch = M.epoch0;
     int cur = 0, trials = 0, accepted = 0, it = 0;
     double lambda = 0.0, ni = 2.0, chi_first = 0.0, chi_last = 0.0;
-    if (gtid == 0)
+    // device-side profile (thread 0): [8] = start .. first exchange done (includes the launch skew between the GPUs),
+    // [9] = first exchange done .. end, [10] = time inside the big exchanges, [11] = publish + wait of all exchanges
+    unsigned long long t_start = 0, t_first = 0;
+    if (gtid == 0) {
         for (int r = 0; r < 6; ++r) sc->cnt_le[r] = 0;
+        for (int r = 0; r < 12; ++r) sc->phase_ns[r] = 0;
+        t_start = gtimer();
+    }
     for (it = 0; it < P.num_iterations; ++it) {
         ba_phase_zero(P, gtid, gsize);
         grid.sync();
@@ -1645,7 +1679,11 @@ ba_lm_multi_kernel(const __grid_constant__ BaParams P, const __grid_constant__ B
             // computeLambdaInit: tau * max |diagonal| over the landmark blocks of all ranks and the SUMMED pose blocks
             const double v0 = gtid < P.n ? P.Hpp[(gtid / 6) * 36 + (gtid % 6) * 7]
                                          : gtid == P.n ? __longlong_as_double((long long)sc->maxdiag_bits) : 0.0;
-            const double* rs = ba_multi_exchange_small(M, grid, ++epoch, v0, P.n + 1, gtid);
+            const double* rs = ba_multi_exchange_small(M, grid, ++epoch, v0, P.n + 1, gtid, &sc->phase_ns[11]);
+            if (gtid == 0) {
+                t_first = gtimer();
+                sc->phase_ns[11] = 0;  // the first wait is the launch skew, accounted in [8]
+            }
             __shared__ double s_md;
             if (threadIdx.x == 0) {
                 double md = 0.0;
@@ -1670,7 +1708,9 @@ ba_lm_multi_kernel(const __grid_constant__ BaParams P, const __grid_constant__ B
             if (P.has_dup) ba_phase_schur_atomic(P, gtid, gsize);
             else ba_phase_schur_blocks(P, smem);
             grid.sync();
+            const unsigned long long t_x0 = gtid == 0 ? gtimer() : 0ull;
             const double chi_sum = ba_multi_exchange_system(P, M, grid, ++epoch, lambda, chi_local, gtid, gsize);
+            if (gtid == 0) sc->phase_ns[10] += gtimer() - t_x0;
             if (qmax == 0) {
                 currentChi = chi_sum;
                 if (it == 0) chi_first = currentChi;
@@ -1683,7 +1723,7 @@ ba_lm_multi_kernel(const __grid_constant__ BaParams P, const __grid_constant__ B
             ba_phase_trial_err(P, cur, slot, gtid, gsize);
             grid.sync();
             const double v3 = gtid == 0 ? sc->chi_trial[slot] : gtid == 1 ? sc->scale[slot] : gtid == 2 ? (double)sc->solve_ok[slot] : 0.0;
-            const double* rs = ba_multi_exchange_small(M, grid, ++epoch, v3, 3, gtid);
+            const double* rs = ba_multi_exchange_small(M, grid, ++epoch, v3, 3, gtid, &sc->phase_ns[11]);
             double tchi = 0.0, tscale = 0.0, tok = 0.0;
             for (int g = 0; g < M.world; ++g) {
                 tchi += __ldcg(rs + (size_t)g * BA_XS);
@@ -1720,7 +1760,7 @@ ba_lm_multi_kernel(const __grid_constant__ BaParams P, const __grid_constant__ B
         grid.sync();
         ba_phase_build_edges(P, cur, gtid, gsize);
         grid.sync();
-        const double* rs = ba_multi_exchange_small(M, grid, ++epoch, gtid == 0 ? sc->chi_cur : 0.0, 1, gtid);
+        const double* rs = ba_multi_exchange_small(M, grid, ++epoch, gtid == 0 ? sc->chi_cur : 0.0, 1, gtid, &sc->phase_ns[11]);
         double c = 0.0;
         for (int g = 0; g < M.world; ++g) c += __ldcg(rs + (size_t)g * BA_XS);
         chi_first = chi_last = c;
@@ -1729,7 +1769,7 @@ ba_lm_multi_kernel(const __grid_constant__ BaParams P, const __grid_constant__ B
     grid.sync();
     ba_phase_relabel_count(P, gtid, gsize);
     grid.sync();
-    const double* rc = ba_multi_exchange_small(M, grid, ++epoch, gtid < 6 ? (double)sc->cnt_le[gtid] : 0.0, 6, gtid);
+    const double* rc = ba_multi_exchange_small(M, grid, ++epoch, gtid < 6 ? (double)sc->cnt_le[gtid] : 0.0, 6, gtid, &sc->phase_ns[11]);
     int cnt[6];
     for (int r = 0; r < 6; ++r) {
         double c = 0.0;
@@ -1759,6 +1799,10 @@ ba_lm_multi_kernel(const __grid_constant__ BaParams P, const __grid_constant__ B
         sc->n_inlier_obs = cnt[rr];
         sc->n_outlier_obs = P.n_obs - cnt[rr];
         sc->pad = (int)(epoch - M.epoch0);  // exchanges executed
+        const unsigned long long t_end = gtimer();
+        if (t_first == 0) t_first = t_start;
+        sc->phase_ns[8] = t_first - t_start;
+        sc->phase_ns[9] = t_end - t_first;
     }
 }
 
@@ -1799,7 +1843,8 @@ extern "C" int vslam_ba_optimize_multi(vslam_ctx* const* ctxs, int n_dev, int n_
     cudaGetDevice(&dev0);
     const int K = n_poses, n = 6 * K;
     BaHostGraph g;
-    int st = ba_prepare_host(g, K, n_points, n_obs, obs_pose, obs_point, obs_uv);
+    ba_graph_bind(g, ctxs[0]->ba->h_stage, K, n_points, n_obs);
+    int st = ba_prepare_host(g, poses, points, obs_pose, obs_point, obs_uv);
     if (st != VSLAM_OK) return st;
     int cuts[BA_MAX_DEV + 1];
     ba_landmark_shards(g, n_dev, cuts);
@@ -1850,7 +1895,7 @@ extern "C" int vslam_ba_optimize_multi(vslam_ctx* const* ctxs, int n_dev, int n_
             }
             MULTI_CUDA(d, cudaDeviceSynchronize());
         }
-        st = ba_upload(ctx, b, g, poses, points);
+        st = ba_upload(ctx, b, g);
         if (st != VSLAM_OK) { cudaSetDevice(dev0); return st; }
         MULTI_CUDA(d, cudaMemsetAsync(b->d_chi2, 0, (size_t)n_obs * 8, ctx->stream));
         if (point_inlier) MULTI_CUDA(d, cudaMemcpyAsync(b->d_inlier, point_inlier, (size_t)n_points, cudaMemcpyHostToDevice, ctx->stream));
@@ -2078,5 +2123,11 @@ extern "C" int vslam_ba_session_schur_dense(vslam_ctx* ctx, double* d_S_dense, f
 extern "C" int vslam_ba_last_phase_ns(vslam_ctx* ctx, uint64_t* ns8) {
     if (!ctx || !ctx->ba || !ctx->ba->h_sc || !ns8) return VSLAM_E_INVALID;
     for (int i = 0; i < 8; ++i) ns8[i] = ctx->ba->h_sc->phase_ns[i];
+    return VSLAM_OK;
+}
+
+extern "C" int vslam_ba_multi_last_profile_ns(vslam_ctx* ctx, uint64_t* ns4) {
+    if (!ctx || !ctx->ba || !ctx->ba->h_sc || !ns4) return VSLAM_E_INVALID;
+    for (int i = 0; i < 4; ++i) ns4[i] = ctx->ba->h_sc->phase_ns[8 + i];
     return VSLAM_OK;
 }

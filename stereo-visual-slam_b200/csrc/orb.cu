@@ -309,25 +309,21 @@ fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__
             d[11] = mid16x2(q[-2], q[-1]); d[5] = mid16x2(q[1], q[2]);
         }
         d[12] = mid16x2(c[-2], c[-1]); d[4] = mid16x2(c[1], c[2]);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) d[k] = __vadd2(d[k], nv);
-        uint32_t mn[16], mx[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            mn[k] = __vmins2(d[k], d[(k + 1) & 15]);
-            mx[k] = __vmaxs2(d[k], d[(k + 1) & 15]);
-        }
-        uint32_t mn2[16], mx2[16];
+        // The network runs on the RAW ring values: min / max commute with subtracting the centre, so
+        //   max_k min9_k(ring - c) = max_k min9_k(ring) - c   and   min_k max9_k(ring - c) = min_k max9_k(ring) - c,
+        // and a 9-window is three 3-windows: m3[k] = op3(d[k], d[k+1], d[k+2]), m9[k] = op3(m3[k], m3[k+3], m3[k+6])
+        // -- 32 three-input instructions per direction instead of 16 subtractions + 48.
+        uint32_t mn3[16], mx3[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            mn2[k] = __vmins2(mn[k], mn[(k + 2) & 15]);
-            mx2[k] = __vmaxs2(mx[k], mx[(k + 2) & 15]);
+            mn3[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+            mx3[k] = __vimax3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
         }
         uint32_t a[16], b[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            a[k] = __vimin3_s16x2(mn2[k], mn2[(k + 4) & 15], d[(k + 8) & 15]);
-            b[k] = __vimax3_s16x2(mx2[k], mx2[(k + 4) & 15], d[(k + 8) & 15]);
+            a[k] = __vimin3_s16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
+            b[k] = __vimax3_s16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
         }
         uint32_t besta = __vimax3_s16x2(a[0], a[1], a[2]), bmin = __vimin3_s16x2(b[0], b[1], b[2]);
 #pragma unroll
@@ -335,8 +331,8 @@ fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__
             besta = __vimax3_s16x2(besta, a[k], a[k + 1]);
             bmin = __vimin3_s16x2(bmin, b[k], b[k + 1]);
         }
-        besta = __vmaxs2(besta, a[15]);
-        bmin = __vmins2(bmin, b[15]);
+        besta = __vadd2(__vmaxs2(besta, a[15]), nv);  // brightest arc minus the centre
+        bmin = __vadd2(__vmins2(bmin, b[15]), nv);    // darkest arc minus the centre
         const uint32_t best = __vmaxs2(besta, neg16x2(bmin));
         // pixels closer than 3 to the image border have no full ring: not corners (h = FAST_T)
         const int gy = ty0 - 1 + r, gx = tx0 - 2 + 2 * j;

@@ -94,6 +94,7 @@ SIGNATURES = {
     "vslam_pnp_debug_read": (_i, [_vp, _i, _vp, _pi, _pi]),
     "vslam_anms": (_i, [_vp, _vp, _i, _i, _f, _vp, _pi]),
     "vslam_ba_last_phase_ns": (_i, [_vp, _vp]),
+    "vslam_ba_multi_last_profile_ns": (_i, [_vp, _vp]),
     "vslam_ba_reduce_sizes": (_i, [_i, _pi, _pi, _pi]),
     "vslam_ba_session_begin": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, C.POINTER(BaOptions), _i, _i, _vp,
                                     _vp, _vp]),
@@ -448,6 +449,12 @@ class Context:
         self.check(self.lib.vslam_ba_last_phase_ns(self.h, _ptr(ns)), "vslam_ba_last_phase_ns")
         names = ["zero", "build", "schur_init", "schur", "schur_reduce", "solve", "update", "trial_err"]
         return {k: float(v) / 1e3 for k, v in zip(names, ns)}
+
+    def ba_multi_last_profile_us(self) -> dict:
+        ns = np.zeros(4, dtype=np.uint64)
+        self.check(self.lib.vslam_ba_multi_last_profile_ns(self.h, _ptr(ns)), "vslam_ba_multi_last_profile_ns")
+        return {k: float(v) / 1e3 for k, v in zip(["start_to_first_exchange", "first_exchange_to_end", "system_exchanges",
+                                                   "publish_and_wait"], ns)}
 
     # ---- K17: landmark-sharded BA session (driver: sharding.ba_optimize_sharded) ------------
     def ba_session(self, problem, shard, r1, r2, r3, **opt):
