@@ -714,6 +714,7 @@ def bench_ba(ctx, pkg, args, torch, dev, dist, rank, world, stream):
     all ranks with one all-reduce of the reduced camera system per LM trial (strong scaling; at these window sizes a
     trial is shorter than its collectives)."""
     out = {}
+    cpu_group = dist.new_group(backend="gloo") if dist is not None else None
     for name, (seed, nk, nl, nobs, nit) in {"cfg3_K10_L5000": (42, 10, 5000, None, 10),
                                             "cfg5_K50_L20000_obs100k": (43, 50, 20000, 100000, 10)}.items():
         p = pkg.synth.synth_ba_problem(seed, nk, nl, n_obs_exact=nobs)
@@ -776,7 +777,10 @@ def bench_ba(ctx, pkg, args, torch, dev, dist, rank, world, stream):
             # strong scaling, device-side: ONE process (rank 0) drives all GPUs of the box through
             # vslam_ba_optimize_multi -- persistent LM kernel per GPU, partial systems exchanged by peer stores over
             # NVLink, no host or NCCL in the loop.  The other ranks idle at the barrier meanwhile.
-            dist.barrier()
+            # (the other ranks wait on a CPU-side gloo barrier: an NCCL barrier would park a spinning kernel on their GPU,
+            # which this rank is about to use)
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=cpu_group)
             if rank == 0:
                 try:
                     ctxs = [ctx] + [pkg.Context(device=dd, max_images=0, max_width=0, max_height=0, max_keypoints=1,
@@ -812,7 +816,7 @@ def bench_ba(ctx, pkg, args, torch, dev, dist, rank, world, stream):
                     ctx.set_stream(stream.cuda_stream)
                 except Exception as ex:
                     rec["multi_device"] = {"error": repr(ex)}
-            dist.barrier()
+            dist.barrier(group=cpu_group)
         if rank == 0:
             try:   # device-side phase profile of the last call and, for the large window, the dense DMMA Schur probe
                 tr = max(r["trials"], 1)

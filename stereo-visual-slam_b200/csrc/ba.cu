@@ -1095,6 +1095,434 @@ ba_lm_kernel(const __grid_constant__ BaParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Small windows (6K <= BA_SMALL_N, i.e. K <= 16: the reference's own window is 10 keyframes): the same LM loop with TWO
+// grid barriers per trial and one per outer iteration instead of five and three.
+//   * BUILD writes into one of two Hpp/bp/chi accumulators and clears the other (no separate ZERO phase), and takes the
+//     max |diag Hll| for lambda_0 in passing.
+//   * SCHUR recomputes Dinv = (Hll + lambda I)^-1 per use (45 flops) instead of a DINV phase, and accumulates
+//     -Hpl Dinv Hpl^T into one of two zero-initialised buffers; Hpp + lambda I is added when the system is loaded.
+//   * SOLVE + UPDATE + TRIAL_ERR are one phase: EVERY CTA factors the (identical) 6K x 6K system redundantly in its own
+//     shared memory -- so the update vector needs no broadcast -- computes all K trial poses into shared memory, then
+//     back-substitutes, updates and re-evaluates the edges of the landmarks it owns.
+// Same arithmetic per edge / per block as the general kernel; only summation order differs.
+// ---------------------------------------------------------------------------------------------------------------
+#define BA_SMALL_N 96
+
+__device__ __forceinline__ void inv3_sym_dev(const double* H, double lambda, double* d) {
+    const double m0 = H[0] + lambda, m1 = H[1], m2 = H[2], m4 = H[4] + lambda, m5 = H[5], m8 = H[8] + lambda;
+    const double c0 = m4 * m8 - m5 * m5, c1 = m5 * m2 - m1 * m8, c2 = m1 * m5 - m4 * m2;
+    const double id = 1.0 / (m0 * c0 + m1 * c1 + m2 * c2);
+    d[0] = c0 * id; d[1] = c1 * id; d[2] = c2 * id;
+    d[3] = d[1];    d[4] = (m0 * m8 - m2 * m2) * id; d[5] = (m2 * m1 - m0 * m5) * id;
+    d[6] = d[2];    d[7] = d[5];                     d[8] = (m0 * m4 - m1 * m1) * id;
+}
+
+// SCHUR blocks with Dinv recomputed per use; accumulates into S / bs (zero-initialised): S_ij -= sum Hpl_i Dinv Hpl_j^T
+__device__ void ba_small_schur(const BaParams& P, double lambda, double* __restrict__ S, double* __restrict__ bs, double* smem) {
+    const int n = P.n, K = P.K;
+    const int nb = K * (K + 1) / 2;
+    const int parts = max(1, (int)gridDim.x / nb);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int wi = blockIdx.x; wi < nb * parts; wi += gridDim.x) {
+        const int b = wi % nb, part = wi / nb;
+        if (!P.block_flag[b]) continue;
+        int ki = 0, rem = b;
+        while (rem >= K - ki) { rem -= K - ki; ++ki; }
+        const int kj = ki + rem;
+        double acc[42];
+#pragma unroll
+        for (int q = 0; q < 42; ++q) acc[q] = 0.0;
+        const int ps = P.pose_start[ki], pe = P.pose_start[ki + 1];
+        for (int t = ps + part * BA_THREADS + tid; t < pe; t += parts * BA_THREADS) {
+            const int i = P.pose_obs[t];
+            const int l = P.obs_point[i];
+            const int j = (ki == kj) ? i : P.obs_of[(size_t)kj * P.L + l];
+            if (j < 0) continue;
+            const double* Bi = P.Hpl + 18 * (size_t)i;
+            double d[9];
+            inv3_sym_dev(P.Hll + 9 * (size_t)l, lambda, d);
+            double BD[18];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                const double x0 = Bi[a * 3], x1 = Bi[a * 3 + 1], x2 = Bi[a * 3 + 2];
+                BD[a * 3] = x0 * d[0] + x1 * d[3] + x2 * d[6];
+                BD[a * 3 + 1] = x0 * d[1] + x1 * d[4] + x2 * d[7];
+                BD[a * 3 + 2] = x0 * d[2] + x1 * d[5] + x2 * d[8];
+            }
+            const double* Bj = P.Hpl + 18 * (size_t)j;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int c = 0; c < 6; ++c)
+                    acc[a * 6 + c] += BD[a * 3] * Bj[c * 3] + BD[a * 3 + 1] * Bj[c * 3 + 1] + BD[a * 3 + 2] * Bj[c * 3 + 2];
+            if (ki == kj) {
+                const double b0 = P.bl[3 * l], b1 = P.bl[3 * l + 1], b2 = P.bl[3 * l + 2];
+#pragma unroll
+                for (int a = 0; a < 6; ++a) acc[36 + a] += BD[a * 3] * b0 + BD[a * 3 + 1] * b1 + BD[a * 3 + 2] * b2;
+            }
+        }
+        __syncthreads();
+        const int nacc = (ki == kj) ? 42 : 36;
+#pragma unroll
+        for (int q = 0; q < 42; ++q) {
+            if (q < nacc) {
+                const double v = warp_sum(acc[q]);
+                if (lane == 0) smem[warp * 42 + q] = v;
+            }
+        }
+        __syncthreads();
+        if (tid < nacc) {
+            double v = 0.0;
+            for (int w8 = 0; w8 < BA_THREADS / 32; ++w8) v += smem[w8 * 42 + tid];
+            if (v != 0.0) {
+                if (tid < 36) atomicAdd(&S[(size_t)(6 * ki + tid / 6) * n + 6 * kj + tid % 6], -v);
+                else atomicAdd(&bs[6 * ki + tid - 36], -v);
+            }
+        }
+    }
+}
+
+// Every CTA: M = [S + Hpp + lambda I | bs + bp] into shared memory, blocked Cholesky + both substitutions; x -> xs (shared).
+// Returns false (uniformly over the grid: identical inputs) if the system is not positive definite.
+__device__ bool ba_small_solve(const BaParams& P, const double* S, const double* bs, const double* Hpp, const double* bp,
+                               double lambda, double* M, double* xs) {
+    const int n = P.n, ld = P.n + 1, tid = threadIdx.x, nt = blockDim.x;
+    __shared__ int s_fail;
+    __shared__ double s_rd[BA_SMALL_N];
+    if (tid == 0) s_fail = 0;
+    for (int i = tid; i < n * n; i += nt) {
+        const int r = i / n, c = i - r * n;
+        double v = __ldcg(S + i);
+        if (r / 6 == c / 6 && c >= r) v += __ldcg(Hpp + (r / 6) * 36 + (r % 6) * 6 + (c % 6));
+        if (r == c) v += lambda;
+        M[r * ld + c] = v;
+    }
+    for (int i = tid; i < n; i += nt) M[i * ld + n] = __ldcg(bs + i) + __ldcg(bp + i);
+    __syncthreads();
+    for (int j0 = 0; j0 < n; j0 += 6) {
+        {
+            double D[36];
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) D[r * 6 + c] = (c >= r) ? M[(j0 + r) * ld + j0 + c] : 0.0;
+            double rinv[6];
+            const bool ok = chol6_diag(D, 6, 0, rinv);
+            for (int c = j0 + 6 + tid; c <= n; c += nt) {
+                double v[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) v[r] = M[(j0 + r) * ld + c];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                    for (int p = 0; p < 6; ++p)
+                        if (p < r) v[r] -= D[p * 6 + r] * v[p];
+                    v[r] *= rinv[r];
+                }
+#pragma unroll
+                for (int r = 0; r < 6; ++r) M[(j0 + r) * ld + c] = v[r];
+            }
+            __syncthreads();
+            if (tid == 0) {
+                if (!ok) s_fail = 1;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c)
+                        if (c >= r) M[(j0 + r) * ld + j0 + c] = D[r * 6 + c];
+                    s_rd[j0 + r] = rinv[r];
+                }
+            }
+        }
+        const int m = n - j0 - 6;
+        for (int e = tid; e < m * (m + 1); e += nt) {
+            const int r = j0 + 6 + e / (m + 1), c = j0 + 6 + e % (m + 1);
+            if (c < r) continue;
+            double v = M[r * ld + c];
+#pragma unroll
+            for (int p = 0; p < 6; ++p) v -= M[(j0 + p) * ld + r] * M[(j0 + p) * ld + c];
+            M[r * ld + c] = v;
+        }
+        __syncthreads();
+        if (s_fail) break;
+    }
+    const bool fail = s_fail != 0;
+    if (!fail) {
+        for (int j0 = n - 6; j0 >= 0; j0 -= 6) {
+            double D[36], x[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) D[r * 6 + c] = (c >= r) ? M[(j0 + r) * ld + j0 + c] : 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) x[r] = M[(j0 + r) * ld + n];
+#pragma unroll
+            for (int r = 5; r >= 0; --r) {
+#pragma unroll
+                for (int p = 0; p < 6; ++p)
+                    if (p > r) x[r] -= D[r * 6 + p] * x[p];
+                x[r] *= s_rd[j0 + r];
+            }
+            __syncthreads();
+            for (int r = tid; r < j0; r += nt) {
+                double v = M[r * ld + n];
+#pragma unroll
+                for (int p = 0; p < 6; ++p) v -= M[r * ld + j0 + p] * x[p];
+                M[r * ld + n] = v;
+            }
+            if (tid < 6) M[(j0 + tid) * ld + n] = x[tid];
+            __syncthreads();
+        }
+        for (int i = tid; i < n; i += nt) xs[i] = M[i * ld + n];
+    }
+    __syncthreads();
+    return !fail;
+}
+
+__global__ void __launch_bounds__(BA_THREADS)
+ba_lm_small_kernel(const __grid_constant__ BaParams P) {
+    extern __shared__ double smem[];
+    cg::grid_group grid = cg::this_grid();
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    const int tid = threadIdx.x;
+    BaScalars* sc = P.sc;
+    const int n = P.n, K = P.K;
+    // shared memory: [0, n(n+1)) system / block-reduction scratch, then x [n], trial poses [12 K]
+    double* xs = smem + n * (n + 1);
+    double* tp = xs + n;
+    // double-buffered accumulators carved out of the (much larger) general-kernel buffers
+    double* HppB[2] = {P.Hpp, P.Hpp + 36 * K};
+    double* bpB[2] = {P.bp, P.bp + n};
+    double* SB[2] = {P.S, P.S + (size_t)n * n};
+    double* bsB[2] = {P.bs, P.bs + n};
+
+    int cur = 0, trials = 0, accepted = 0, it = 0;
+    double lambda = 0.0, ni = 2.0, chi_first = 0.0, chi_last = 0.0;
+    unsigned long long t_last = 0;
+    // prologue: clear accumulator set 0 and Schur buffer 0
+    for (int i = gtid; i < 36 * K; i += gsize) HppB[0][i] = 0.0;
+    for (int i = gtid; i < n; i += gsize) { bpB[0][i] = 0.0; bsB[0][i] = 0.0; }
+    for (int i = gtid; i < n * n; i += gsize) SB[0][i] = 0.0;
+    if (!P.pose_only) {
+        for (int i = P.shard_L0 * 9 + gtid; i < P.shard_L1 * 9; i += gsize) P.Hll[i] = 0.0;
+        for (int i = P.shard_L0 * 3 + gtid; i < P.shard_L1 * 3; i += gsize) P.bl[i] = 0.0;
+    }
+    if (gtid == 0) {
+        for (int r = 0; r < 6; ++r) sc->cnt_le[r] = 0;
+        for (int r = 0; r < 12; ++r) sc->phase_ns[r] = 0;
+        sc->chi_cur = 0.0;
+        sc->maxdiag_bits = 0ull;
+        sc->chi_trial[0] = sc->chi_trial[1] = 0.0;
+        sc->scale[0] = sc->scale[1] = 0.0;
+        t_last = gtimer();
+    }
+    grid.sync();
+    BA_TICK(0);
+    double chi_next = 0.0;  // chi at the linearisation point, carried from the accepted trial of the previous iteration
+    for (it = 0; it < P.num_iterations; ++it) {
+        const int hb = it & 1;
+        {   // BUILD into accumulator set hb; clear the other set for the next outer iteration
+            BaParams Q = P;
+            Q.Hpp = HppB[hb];
+            Q.bp = bpB[hb];
+            ba_phase_build_edges(Q, cur, gtid, gsize);
+            ba_phase_build_poses(Q, cur, smem);
+            for (int i = gtid; i < 36 * K; i += gsize) HppB[1 - hb][i] = 0.0;
+            for (int i = gtid; i < n; i += gsize) bpB[1 - hb][i] = 0.0;
+        }
+        if (it == 0) {
+            grid.sync();  // Hll complete (lambda_0 needs max |diag|); later iterations skip this
+            ba_phase_maxdiag(P, gtid, gsize);
+        }
+        grid.sync();
+        BA_TICK(1);
+        double currentChi = sc->chi_cur;
+        (void)chi_next;
+        if (it == 0) {
+            chi_first = currentChi;
+            __shared__ double s_md;
+            if (tid == 0) {
+                double md = __longlong_as_double((long long)sc->maxdiag_bits);
+                for (int i = 0; i < n; ++i) md = fmax(md, fabs(__ldcg(HppB[hb] + (i / 6) * 36 + (i % 6) * 7)));
+                s_md = md;
+            }
+            __syncthreads();
+            lambda = P.tau * s_md;
+            ni = 2.0;
+        }
+        double rho = 0.0;
+        int qmax = 0;
+        do {
+            const int tb = trials & 1;
+            if (!P.pose_only) {
+                ba_small_schur(P, lambda, SB[tb], bsB[tb], smem);
+                grid.sync();
+            }
+            BA_TICK(3);
+            // ---- every CTA: solve, then update + trial errors of its own landmarks --------------------------------
+            const bool ok = ba_small_solve(P, SB[tb], bsB[tb], HppB[hb], bpB[hb], lambda, smem, xs);
+            BA_TICK(5);
+            // clear the other Schur buffer and the other trial slot for the next trial; chi_cur for the next BUILD
+            for (int i = gtid; i < n * n; i += gsize) SB[1 - tb][i] = 0.0;
+            for (int i = gtid; i < n; i += gsize) bsB[1 - tb][i] = 0.0;
+            if (gtid == 0) {
+                sc->chi_trial[1 - tb] = 0.0;
+                sc->scale[1 - tb] = 0.0;
+                sc->chi_cur = 0.0;
+            }
+            double chi = 0.0, scale = 0.0;
+            if (ok) {
+                const double* poses = P.poses + (size_t)cur * K * 12;
+                double* tposes = P.poses + (size_t)(1 - cur) * K * 12;
+                if (tid < K) {  // trial poses, redundantly per CTA (CTA 0 publishes them)
+                    double dR[9], dt[3];
+                    se3_exp_dev(xs + 6 * tid, dR, dt);
+                    const double* T = poses + 12 * tid;
+                    double* Tn = tp + 12 * tid;
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) Tn[r * 4 + c] = dR[r * 3] * T[c] + dR[r * 3 + 1] * T[4 + c] + dR[r * 3 + 2] * T[8 + c];
+                        Tn[r * 4 + 3] = dR[r * 3] * T[3] + dR[r * 3 + 1] * T[7] + dR[r * 3 + 2] * T[11] + dt[r];
+                    }
+                    if (blockIdx.x == 0) {
+#pragma unroll
+                        for (int q = 0; q < 12; ++q) tposes[12 * tid + q] = Tn[q];
+                    }
+                }
+                if (gtid < K) {  // computeScale, pose part
+                    const double* xi = xs + 6 * gtid;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) scale += xi[a] * (lambda * xi[a] + __ldcg(bpB[hb] + 6 * gtid + a));
+                }
+                __syncthreads();
+                // landmarks: eight lanes per landmark, as in BUILD
+                const double* points = P.points + (size_t)cur * P.L * 3;
+                double* tpoints = P.points + (size_t)(1 - cur) * P.L * 3;
+                const int sub = gtid & (BA_LM_GROUP - 1), ngroups = gsize / BA_LM_GROUP;
+                const int nl = P.pose_only ? 0 : P.shard_L1 - P.shard_L0;
+                const int iters = (nl + ngroups - 1) / ngroups;
+                for (int itl = 0; itl < iters; ++itl) {
+                    const int l = P.shard_L0 + itl * ngroups + gtid / BA_LM_GROUP;
+                    const bool live = l < P.shard_L1;
+                    const int o0 = live ? P.lm_start[l] : 0, o1 = live ? P.lm_start[l + 1] : 0;
+                    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+                    for (int i = o0 + sub; i < o1; i += BA_LM_GROUP) {
+                        const double* Bi = P.Hpl + 18 * (size_t)i;
+                        const double* xp = xs + 6 * P.obs_pose[i];
+#pragma unroll
+                        for (int a = 0; a < 6; ++a) {
+                            c0 -= Bi[a * 3] * xp[a];
+                            c1 -= Bi[a * 3 + 1] * xp[a];
+                            c2 -= Bi[a * 3 + 2] * xp[a];
+                        }
+                    }
+#pragma unroll
+                    for (int o = BA_LM_GROUP / 2; o > 0; o >>= 1) {
+                        c0 += __shfl_xor_sync(0xFFFFFFFFu, c0, o);
+                        c1 += __shfl_xor_sync(0xFFFFFFFFu, c1, o);
+                        c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, o);
+                    }
+                    double pt[3] = {0.0, 0.0, 0.0};
+                    if (live && o1 > o0) {
+                        const double b0 = P.bl[3 * l], b1 = P.bl[3 * l + 1], b2 = P.bl[3 * l + 2];
+                        c0 += b0; c1 += b1; c2 += b2;
+                        double d[9];
+                        inv3_sym_dev(P.Hll + 9 * (size_t)l, lambda, d);
+                        const double x0 = d[0] * c0 + d[1] * c1 + d[2] * c2, x1 = d[3] * c0 + d[4] * c1 + d[5] * c2,
+                                     x2 = d[6] * c0 + d[7] * c1 + d[8] * c2;
+                        pt[0] = points[3 * l] + x0; pt[1] = points[3 * l + 1] + x1; pt[2] = points[3 * l + 2] + x2;
+                        if (sub == 0) {
+                            P.x[n + 3 * l] = x0; P.x[n + 3 * l + 1] = x1; P.x[n + 3 * l + 2] = x2;
+                            tpoints[3 * l] = pt[0]; tpoints[3 * l + 1] = pt[1]; tpoints[3 * l + 2] = pt[2];
+                            scale += x0 * (lambda * x0 + b0) + x1 * (lambda * x1 + b1) + x2 * (lambda * x2 + b2);
+                        }
+                    } else if (live && sub == 0) {  // landmark without edges: carried over unchanged
+                        tpoints[3 * l] = points[3 * l]; tpoints[3 * l + 1] = points[3 * l + 1]; tpoints[3 * l + 2] = points[3 * l + 2];
+                    }
+                    for (int i = o0 + sub; i < o1; i += BA_LM_GROUP) {  // computeActiveErrors at the trial estimate
+                        double pc[3], e0, e1, r0, w;
+                        residual_dev(tp + 12 * P.obs_pose[i], pt, P.Kc, P.obs_uv[2 * i], P.obs_uv[2 * i + 1], e0, e1, pc);
+                        P.err[2 * i] = e0;
+                        P.err[2 * i + 1] = e1;
+                        huber_dev(e0 * e0 + e1 * e1, P.delta, r0, w);
+                        chi += r0;
+                    }
+                }
+                if (P.pose_only) {  // points are fixed: every edge against the trial poses
+                    for (int i = gtid; i < P.n_obs; i += gsize) {
+                        double pc[3], e0, e1, r0, w;
+                        residual_dev(tp + 12 * P.obs_pose[i], points + 3 * P.obs_point[i], P.Kc, P.obs_uv[2 * i], P.obs_uv[2 * i + 1],
+                                     e0, e1, pc);
+                        P.err[2 * i] = e0;
+                        P.err[2 * i + 1] = e1;
+                        huber_dev(e0 * e0 + e1 * e1, P.delta, r0, w);
+                        chi += r0;
+                    }
+                }
+                chi = warp_sum(chi);
+                scale = warp_sum(scale);
+                if ((tid & 31) == 0) {
+                    if (chi != 0.0) atomicAdd(&sc->chi_trial[tb], chi);
+                    if (scale != 0.0) atomicAdd(&sc->scale[tb], scale);
+                }
+            }
+            grid.sync();
+            BA_TICK(6);
+            const double tempChi = ok ? sc->chi_trial[tb] : DBL_MAX;
+            const double scl = (ok ? sc->scale[tb] : 0.0) + 1e-3;
+            rho = (currentChi - tempChi) / scl;
+            if (rho > 0 && isfinite(tempChi)) {
+                double alpha = 1. - pow(2 * rho - 1, 3);
+                alpha = fmin(alpha, 2. / 3.);
+                lambda *= fmax(1. / 3., alpha);
+                ni = 2;
+                currentChi = tempChi;
+                cur = 1 - cur;
+                accepted++;
+            } else {
+                lambda *= ni;
+                ni *= 2;
+            }
+            qmax++;
+            trials++;
+        } while (rho < 0 && qmax < P.max_trials);
+        chi_last = currentChi;
+        if (qmax == P.max_trials || rho == 0) {
+            it++;
+            break;
+        }
+    }
+    if (P.num_iterations <= 0) {
+        ba_phase_build_edges(P, cur, gtid, gsize);
+        grid.sync();
+        chi_first = chi_last = sc->chi_cur;
+    }
+    grid.sync();
+    ba_phase_relabel_count(P, gtid, gsize);
+    grid.sync();
+    int n_in = 0;
+    const double th = ba_relabel_threshold(P, P.n_obs, &n_in);
+    ba_phase_relabel_apply(P, th, gtid, gsize);
+    if (cur == 1) {
+        for (int i = gtid; i < K * 12; i += gsize) P.poses[i] = P.poses[K * 12 + i];
+        if (!P.pose_only)
+            for (int i = gtid; i < P.L * 3; i += gsize) P.points[i] = P.points[(size_t)P.L * 3 + i];
+    }
+    if (gtid == 0) {
+        sc->iterations = it;
+        sc->trials = trials;
+        sc->accepted = accepted;
+        sc->chi2_initial = chi_first;
+        sc->chi2_final = chi_last;
+        sc->lambda_final = lambda;
+        sc->chi2_threshold = th;
+        sc->n_inlier_obs = n_in;
+        sc->n_outlier_obs = P.n_obs - n_in;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 struct BaState {
@@ -1125,6 +1553,12 @@ struct BaMulti;
 __global__ void ba_lm_multi_kernel(const __grid_constant__ BaParams P, const __grid_constant__ BaMulti M);
 
 static size_t ba_stage_bytes(size_t K, size_t L, size_t O);
+static size_t ba_small_smem_bytes(int K) {
+    const size_t n = 6 * (size_t)K;
+    size_t need = n * (n + 1) + n + 12 * (size_t)K;
+    if (need < (BA_THREADS / 32) * 42) need = (BA_THREADS / 32) * 42;
+    return need * sizeof(double);
+}
 
 // shared memory of one CTA: max(pose partials K*42, per-CTA S n*n+n, in-shared-memory Cholesky n*n+n) doubles
 static int ba_smem_bytes(int K) {
@@ -1184,6 +1618,8 @@ int vslam_ba_init(vslam_ctx* ctx) {
     VSLAM_CUDA(ctx, cudaFuncSetAttribute(ba_lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
     VSLAM_CUDA(ctx, cudaFuncSetAttribute(ba_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
     VSLAM_CUDA(ctx, cudaFuncSetAttribute(ba_lm_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
+    VSLAM_CUDA(ctx, cudaFuncSetAttribute(ba_lm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)ba_small_smem_bytes(BA_SMALL_N / 6)));
     return VSLAM_OK;
 }
 
@@ -1345,11 +1781,18 @@ extern "C" int vslam_ba_optimize(vslam_ctx* ctx, int n_poses, double* poses, int
     ba_fill_params(P, b, K, n_points, n_obs, opt, Kmat, has_dup);
 
     void* args[] = {(void*)&P};
+    static const bool force_general = getenv("VSLAM_BA_GENERAL") != nullptr;  // A/B switch for measurements
+    const bool small = P.n <= BA_SMALL_N && !has_dup && !force_general;
     vslam_time_begin(ctx, VK_BA_BUILD);
-    VSLAM_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)ba_lm_kernel, dim3(b->n_cta), dim3(BA_THREADS), args,
-                                                (size_t)ba_smem_bytes(K), s));
+    if (small) {
+        VSLAM_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)ba_lm_small_kernel, dim3(b->n_cta), dim3(BA_THREADS), args,
+                                                    ba_small_smem_bytes(K), s));
+    } else {
+        VSLAM_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)ba_lm_kernel, dim3(b->n_cta), dim3(BA_THREADS), args,
+                                                    (size_t)ba_smem_bytes(K), s));
+    }
     vslam_time_end(ctx);
-    VSLAM_LAUNCH_CHECK(ctx, "ba_lm_kernel");
+    VSLAM_LAUNCH_CHECK(ctx, small ? "ba_lm_small_kernel" : "ba_lm_kernel");
     VSLAM_CUDA(ctx, cudaMemcpyAsync(b->h_sc, b->d_sc, sizeof(BaScalars), cudaMemcpyDeviceToHost, s));
     VSLAM_CUDA(ctx, cudaMemcpyAsync(poses, b->d_poses, (size_t)K * 96, cudaMemcpyDeviceToHost, s));
     if (n_points > 0 && !P.pose_only)
@@ -1579,11 +2022,18 @@ __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
 // The grid barrier orders every thread's peer stores before the publishing threads (gpu scope); ONE fence.sys + release
 // store per peer then publishes them at system scope (cumulativity) -- a fence.sys in every thread costs ~100 us here.
 __device__ void ba_multi_signal_wait(const BaMulti& M, cg::grid_group& grid, unsigned epoch, unsigned long long* wait_ns) {
+    const bool prof = blockIdx.x == 0 && threadIdx.x == 0;
+    unsigned long long t_a = prof ? gtimer() : 0ull;
     grid.sync();
     const unsigned long long t_pub = gtimer();
+    if (prof) wait_ns[1 - 11] += t_pub - t_a;  // phase_ns[1]: grid barrier after the peer stores
     if (blockIdx.x == 0 && (int)threadIdx.x < M.world) {
         __threadfence_system();
         st_release_sys_u32(M.flags[threadIdx.x] + M.rank, epoch);
+    }
+    if (prof) {
+        const unsigned long long t_b = gtimer();
+        wait_ns[2 - 11] += t_b - t_pub;        // phase_ns[2]: fence.sys + release stores
     }
     if ((int)threadIdx.x < M.world) {
         const unsigned* f = M.flags[M.rank] + threadIdx.x;
@@ -1601,6 +2051,7 @@ __device__ double ba_multi_exchange_system(const BaParams& P, const BaMulti& M, 
                                            double lambda, double chi_local, int gtid, int gsize) {
     const int n = P.n, lane = threadIdx.x & 31, gw = gtid >> 5, nw = gsize >> 5;
     const size_t slot = (size_t)M.rank * M.xlen;
+    const unsigned long long t_w0 = gtid == 0 ? gtimer() : 0ull;
     for (int r = gw; r < n; r += nw) {  // one warp per row: the row segment right of (and including) the diagonal block
         const int c0 = 6 * (r / 6);
         for (int c = c0 + lane; c < n; c += 32) {
@@ -1612,7 +2063,9 @@ __device__ double ba_multi_exchange_system(const BaParams& P, const BaMulti& M, 
         const double v = i < n ? P.bs[i] : i < 2 * n ? P.bp[i - n] : chi_local;
         for (int g = 0; g < M.world; ++g) M.xbig[g][slot + (size_t)n * n + i] = v;
     }
+    if (gtid == 0) P.sc->phase_ns[0] += gtimer() - t_w0;  // this thread's share of the peer-store loops
     ba_multi_signal_wait(M, grid, epoch, &P.sc->phase_ns[11]);
+    const unsigned long long t_s0 = gtid == 0 ? gtimer() : 0ull;
     const double* rx = M.xbig[M.rank];
     for (int r = gw; r < n; r += nw) {
         const int c0 = 6 * (r / 6);
@@ -1631,6 +2084,7 @@ __device__ double ba_multi_exchange_system(const BaParams& P, const BaMulti& M, 
     double chi = 0.0;
     for (int g = 0; g < M.world; ++g) chi += __ldcg(rx + (size_t)g * M.xlen + (size_t)n * n + 2 * n);
     grid.sync();
+    if (gtid == 0) P.sc->phase_ns[4] += gtimer() - t_s0;  // rank-ordered sum + barrier
     return chi;
 }
 

@@ -453,8 +453,13 @@ class Context:
     def ba_multi_last_profile_us(self) -> dict:
         ns = np.zeros(4, dtype=np.uint64)
         self.check(self.lib.vslam_ba_multi_last_profile_ns(self.h, _ptr(ns)), "vslam_ba_multi_last_profile_ns")
-        return {k: float(v) / 1e3 for k, v in zip(["start_to_first_exchange", "first_exchange_to_end", "system_exchanges",
-                                                   "publish_and_wait"], ns)}
+        out = {k: float(v) / 1e3 for k, v in zip(["start_to_first_exchange", "first_exchange_to_end", "system_exchanges",
+                                                    "publish_and_wait"], ns)}
+        ns8 = np.zeros(8, dtype=np.uint64)
+        self.check(self.lib.vslam_ba_last_phase_ns(self.h, _ptr(ns8)), "vslam_ba_last_phase_ns")
+        out.update(peer_store_loops=float(ns8[0]) / 1e3, barrier_after_stores=float(ns8[1]) / 1e3,
+                   fence_and_flags=float(ns8[2]) / 1e3, sum_and_barrier=float(ns8[4]) / 1e3)
+        return out
 
     # ---- K17: landmark-sharded BA session (driver: sharding.ba_optimize_sharded) ------------
     def ba_session(self, problem, shard, r1, r2, r3, **opt):
