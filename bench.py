@@ -32,6 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W, H, NFEAT = 1241, 376, 2000
+PITCH = (W + 15) // 16 * 16   # device-resident images use a 16-byte aligned row pitch (the row_pitch argument of the C-ABI)
 WORKLOAD = ("configs[1] batched: 1241x376 synthetic stereo pairs, 2000 ORB kp, "
             "detect(L,R)+BF-Hamming cross-check match+DLT triangulate")
 METRIC = "stereo_frames_per_sec"
@@ -249,13 +250,20 @@ def pin_to_gpu_numa(index: int):
         return f"not pinned ({type(ex).__name__})"
 
 
+def to_pitched(torch, img_batch, dev):
+    """(B, H, W) uint8 numpy -> device tensor (B, H, PITCH), rows 16-byte aligned, padding zero"""
+    t = torch.zeros((img_batch.shape[0], H, PITCH), dtype=torch.uint8, device=dev)
+    t[:, :, :W] = torch.from_numpy(img_batch).to(dev)
+    return t
+
+
 def frontend_fps(pkg, torch, ctx, dev, stream, dist, world, B, nfeat, cap, steps, warmup, seed0):
     """Device-resident stereo frames/s of one workload (CUDA events on the launching stream, max over ranks)."""
     P1, P2 = pkg.synth.stereo_projection_matrices()
     sets = []
     for k in range(2):
         L, R = make_batch(pkg, B, seed0 + 17 * k)
-        sets.append((torch.from_numpy(L).to(dev), torch.from_numpy(R).to(dev)))
+        sets.append((to_pitched(torch, L, dev), to_pitched(torch, R, dev)))
     d_kp = torch.zeros((2 * B, cap, 7), dtype=torch.int32, device=dev)
     d_desc = torch.zeros((2 * B, cap, 32), dtype=torch.uint8, device=dev)
     d_nkp = torch.zeros(2 * B, dtype=torch.int32, device=dev)
@@ -267,7 +275,7 @@ def frontend_fps(pkg, torch, ctx, dev, stream, dist, world, B, nfeat, cap, steps
 
     def step(i):
         dl, dr = sets[i & 1]
-        ctx.stereo_frontend_dev(dl, dr, B, W, H, W, W * H, P1, P2, None, d_kp, d_desc, d_nkp, d_m, d_nm, d_xyz, d_fl,
+        ctx.stereo_frontend_dev(dl, dr, B, W, H, PITCH, PITCH * H, P1, P2, None, d_kp, d_desc, d_nkp, d_m, d_nm, d_xyz, d_fl,
                                 nfeatures=nfeat)
     with torch.cuda.stream(stream):
         for i in range(warmup):
@@ -326,7 +334,7 @@ def run_ours(args, rank, world, local_rank):
         L, R = make_batch(pkg, B, 100 * rank + 17 * k)
         hl = torch.from_numpy(L).pin_memory()
         hr = torch.from_numpy(R).pin_memory()
-        sets.append((hl, hr, hl.to(dev), hr.to(dev)))
+        sets.append((hl, hr, to_pitched(torch, L, dev), to_pitched(torch, R, dev)))
     d_kp = torch.zeros((2 * B, cap, 7), dtype=torch.int32, device=dev)
     d_desc = torch.zeros((2 * B, cap, 32), dtype=torch.uint8, device=dev)
     d_nkp = torch.zeros(2 * B, dtype=torch.int32, device=dev)
@@ -338,7 +346,7 @@ def run_ours(args, rank, world, local_rank):
 
     def step_dev(i):
         _, _, dl, dr = sets[i & 1]
-        ctx.stereo_frontend_dev(dl, dr, B, W, H, W, W * H, P1, P2, None, d_kp, d_desc, d_nkp, d_m, d_nm, d_xyz, d_fl,
+        ctx.stereo_frontend_dev(dl, dr, B, W, H, PITCH, PITCH * H, P1, P2, None, d_kp, d_desc, d_nkp, d_m, d_nm, d_xyz, d_fl,
                                 nfeatures=NFEAT)
 
     def barrier():
@@ -525,6 +533,7 @@ def run_ours(args, rank, world, local_rank):
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload,
                        "pairs_per_step_per_gpu": B, "nfeatures": NFEAT, "anms": "off (configs[1])", "host_affinity": numa,
+                       "device_row_pitch": PITCH,
                        "l2": "two alternating input sets + 256 MiB flush before the timed region; per-step working "
                              "set (inputs+pyramids+blurred) ~%.0f MB > 126 MB L2" % (2 * B * 3.7),
                        "mean_keypoints_per_image": n_kp_mean, "mean_matches_per_pair": n_m_mean,
@@ -650,14 +659,14 @@ def bench_sgbm(ctx, pkg, torch, dev, stream, dl, dr, hbm_peak):
     d16 = torch.empty((B, H, W), dtype=torch.int16, device=dev)
     with torch.cuda.stream(stream):
         for _ in range(2):
-            ctx.sgbm_compute_dev(dl, dr, B, W, H, W, W * H, d16)
+            ctx.sgbm_compute_dev(dl, dr, B, W, H, PITCH, PITCH * H, d16)
     torch.cuda.synchronize(dev)
     reps = 5
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):  # throughput: chunks interleaved on two streams (the library default)
         e0.record(stream)
         for _ in range(reps):
-            ctx.sgbm_compute_dev(dl, dr, B, W, H, W, W * H, d16)
+            ctx.sgbm_compute_dev(dl, dr, B, W, H, PITCH, PITCH * H, d16)
         e1.record(stream)
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / reps
@@ -666,7 +675,7 @@ def bench_sgbm(ctx, pkg, torch, dev, stream, dl, dr, hbm_peak):
     with torch.cuda.stream(stream):
         e0.record(stream)
         for _ in range(reps):
-            ctx.sgbm_compute_dev(dl, dr, B, W, H, W, W * H, d16)
+            ctx.sgbm_compute_dev(dl, dr, B, W, H, PITCH, PITCH * H, d16)
         e1.record(stream)
     torch.cuda.synchronize(dev)
     ms_serial = e0.elapsed_time(e1) / reps
@@ -684,7 +693,7 @@ def bench_sgbm(ctx, pkg, torch, dev, stream, dl, dr, hbm_peak):
         if k in alg:
             gbs = alg[k] * B / (per * 1e-3) / 1e9
             kern[k].update({"algorithmic_GBps": gbs, "hbm_frac": gbs / hbm_peak})
-    hl, hr = dl[0].cpu().numpy(), dr[0].cpu().numpy()
+    hl, hr = np.ascontiguousarray(dl[0, :, :W].cpu().numpy()), np.ascontiguousarray(dr[0, :, :W].cpu().numpy())
     ctx.sgbm_compute(hl, hr)
     t0 = time.perf_counter()
     for _ in range(5):

@@ -2306,6 +2306,7 @@ extern "C" int vslam_ba_optimize_multi(vslam_ctx* const* ctxs, int n_dev, int n_
         if (cuts[d + 1] <= cuts[d]) return VSLAM_E_INVALID;  // fewer landmarks than devices: use fewer devices
     const int xlen = n * n + 2 * n + 8;
     vslam_ctx* c0 = ctxs[0];
+    std::vector<int> shard_csr((size_t)n_dev * (K + 1 + n_obs));  // stays alive until the final stream synchronisations
 #define MULTI_CUDA(d, call)                                                            \
     do {                                                                               \
         cudaError_t e__ = (call);                                                      \
@@ -2351,6 +2352,20 @@ extern "C" int vslam_ba_optimize_multi(vslam_ctx* const* ctxs, int n_dev, int n_
         }
         st = ba_upload(ctx, b, g);
         if (st != VSLAM_OK) { cudaSetDevice(dev0); return st; }
+        {
+            // pose-major CSR restricted to this rank's edges: the per-pose and per-block phases then scan only owned edges
+            // instead of filtering the whole list (landmark-sorted edges of the shard are the contiguous range [e0, e1))
+            const int e0 = g.lm_start[cuts[d]], e1 = g.lm_start[cuts[d + 1]];
+            int* ps = shard_csr.data() + (size_t)d * (K + 1 + n_obs);
+            int* po = ps + K + 1;
+            for (int k = 0; k <= K; ++k) ps[k] = 0;
+            for (int e = e0; e < e1; ++e) ps[g.op[e] + 1]++;
+            for (int k = 0; k < K; ++k) ps[k + 1] += ps[k];
+            std::vector<int> fill(ps, ps + K);
+            for (int e = e0; e < e1; ++e) po[fill[g.op[e]]++] = e;
+            MULTI_CUDA(d, cudaMemcpyAsync(b->d_pose_start, ps, (size_t)(K + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+            if (e1 > e0) MULTI_CUDA(d, cudaMemcpyAsync(b->d_pose_obs, po, (size_t)(e1 - e0) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        }
         MULTI_CUDA(d, cudaMemsetAsync(b->d_chi2, 0, (size_t)n_obs * 8, ctx->stream));
         if (point_inlier) MULTI_CUDA(d, cudaMemcpyAsync(b->d_inlier, point_inlier, (size_t)n_points, cudaMemcpyHostToDevice, ctx->stream));
     }

@@ -217,30 +217,75 @@ fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__
     const int tid = threadIdx.x, lane = tid & 31;
     const int W = L.w, H = L.h;
 
-    // ---- load: 4 pixels per work item through aligned 32-bit global loads, widened to 2 x (2 pixels) ------------
-    for (int i = tid; i < FI_ROWS * FI_LOAD_WORDS; i += FAST_THREADS) {
-        const int r = i / FI_LOAD_WORDS, wj = i - r * FI_LOAD_WORDS;
-        const int gy = ty0 - 4 + r, gx = tx0 - 4 + 4 * wj;
-        uint32_t px = 0;
-        if (gy >= 0 && gy < H) {
-            const uint8_t* p = im + (size_t)gy * pitch + gx;
-            if (gx >= 0 && gx + 3 < W) {
-                const uint32_t a = (uint32_t)(uintptr_t)p & 3u;
-                const uint32_t* q = reinterpret_cast<const uint32_t*>(p - a);
-                px = __ldg(q);
-                if (a) px = __funnelshift_r(px, __ldg(q + 1), 8 * a);
-            } else {
+    // ---- load.  The stall profile of this kernel was dominated by the tile fill (one 32-bit load in flight per thread,
+    // three dependent rounds), so: when the level's rows are 16-byte aligned (every pyramid level, and level 0 whenever
+    // the caller's pitch and base allow it) ONE 128-bit load per thread fetches the whole 40 x 96-pixel window
+    // [tx0-16, tx0+80) -- 240 loads per tile, all in flight at once; otherwise the 32-bit path issues its three loads
+    // per thread back to back before touching any of them.  Pixels outside the image never reach a kept score (a
+    // corner's ring lies inside the image), so out-of-image lanes may hold anything that is safe to read.
+    const bool aligned16 = ((pitch & 15) == 0) && (((uintptr_t)im & 15) == 0);
+    if (aligned16) {
+        if (tid < FI_ROWS * 6) {
+            const int r = tid / 6, ch = tid - r * 6;
+            const int gy = ty0 - 4 + r, gx = tx0 - 16 + 16 * ch;
+            uint4 px = make_uint4(0, 0, 0, 0);
+            if (gy >= 0 && gy < H && gx >= 0 && gx < pitch) px = __ldg(reinterpret_cast<const uint4*>(im + (size_t)gy * pitch + gx));
+            // 16 pixels -> 8 words of two 16-bit pixels; word index in the row = (gx - (tx0 - 8)) / 2 = 8 * ch - 4
+            uint32_t w[8];
+            w[0] = __byte_perm(px.x, 0, 0x4140); w[1] = __byte_perm(px.x, 0, 0x4342);
+            w[2] = __byte_perm(px.y, 0, 0x4140); w[3] = __byte_perm(px.y, 0, 0x4342);
+            w[4] = __byte_perm(px.z, 0, 0x4140); w[5] = __byte_perm(px.z, 0, 0x4342);
+            w[6] = __byte_perm(px.w, 0, 0x4140); w[7] = __byte_perm(px.w, 0, 0x4342);
+            uint32_t* dst = &s_img[r * FI_WORDS + 8 * ch - 4];
+            if (ch > 0) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);          // words 8ch-4 .. 8ch-1
+            if (ch < 5) *reinterpret_cast<uint4*>(dst + 4) = make_uint4(w[4], w[5], w[6], w[7]);      // words 8ch .. 8ch+3
+        }
+    } else {
+        constexpr int ROUNDS = (FI_ROWS * FI_LOAD_WORDS + FAST_THREADS - 1) / FAST_THREADS;
+        uint32_t q0[ROUNDS], q1[ROUNDS];
+        int sh[ROUNDS];
+#pragma unroll
+        for (int k = 0; k < ROUNDS; ++k) {  // issue every load first
+            const int i = tid + k * FAST_THREADS;
+            const int r = i / FI_LOAD_WORDS, wj = i - r * FI_LOAD_WORDS;
+            const int gy = ty0 - 4 + r, gx = tx0 - 4 + 4 * wj;
+            q0[k] = q1[k] = 0;
+            sh[k] = -1;  // -1: nothing to fetch, -2: per-byte edge case
+            if (i < FI_ROWS * FI_LOAD_WORDS && gy >= 0 && gy < H) {
+                const uint8_t* p = im + (size_t)gy * pitch + gx;
+                if (gx >= 0 && gx + 3 < W) {
+                    const uint32_t a = (uint32_t)(uintptr_t)p & 3u;
+                    const uint32_t* q = reinterpret_cast<const uint32_t*>(p - a);
+                    q0[k] = __ldg(q);
+                    if (a) q1[k] = __ldg(q + 1);
+                    sh[k] = 8 * (int)a;
+                } else {
+                    sh[k] = -2;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < ROUNDS; ++k) {
+            const int i = tid + k * FAST_THREADS;
+            if (i >= FI_ROWS * FI_LOAD_WORDS) continue;
+            const int r = i / FI_LOAD_WORDS, wj = i - r * FI_LOAD_WORDS;
+            uint32_t px = 0;
+            if (sh[k] >= 0) {
+                px = __funnelshift_r(q0[k], q1[k], sh[k]);
+            } else if (sh[k] == -2) {
+                const int gy = ty0 - 4 + r, gx = tx0 - 4 + 4 * wj;
+                const uint8_t* p = im + (size_t)gy * pitch + gx;
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
                     if (gx + b >= 0 && gx + b < W) px |= (uint32_t)p[b] << (8 * b);
             }
+            uint2 v;
+            v.x = __byte_perm(px, 0, 0x4140);
+            v.y = __byte_perm(px, 0, 0x4342);
+            *reinterpret_cast<uint2*>(&s_img[r * FI_WORDS + 2 + 2 * wj]) = v;
         }
-        uint2 v;
-        v.x = __byte_perm(px, 0, 0x4140);
-        v.y = __byte_perm(px, 0, 0x4342);
-        *reinterpret_cast<uint2*>(&s_img[r * FI_WORDS + 2 + 2 * wj]) = v;
     }
-    if (tid < FI_ROWS * 4) {  // zero padding: words 0,1 and 38,39 of every row
+    if (!aligned16 && tid < FI_ROWS * 4) {  // zero padding: words 0,1 and 38,39 of every row (the 128-bit path fills them)
         const int r = tid >> 2, k = tid & 3;
         s_img[r * FI_WORDS + (k < 2 ? k : 36 + k)] = 0;
     }
