@@ -33,9 +33,6 @@
 #define HS_THREADS 1024
 #define DESC_WARPS 4
 #define DESC_KPW 8  // keypoints per warp (power of two <= 32)
-#define DP_R 19      // rBRIEF sampling radius: |pattern| <= 13 rotated -> ceil(13 * sqrt(2)) = 19
-#define DP_ROWS (2 * DP_R + 1)
-#define DP_WORDS 11  // aligned words covering 39 bytes at any byte offset: 3 + 39 <= 44
 
 struct OrbLevel {
     int w, h, pitch;
@@ -878,6 +875,9 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
+// (Measured and rejected, round 2: staging each keypoint's 39 x 39 blurred window in a double-buffered per-warp
+// shared-memory patch -- aligned, coalesced word copies, samples as shared-memory byte reads.  It copies 1.7 KB per
+// keypoint to serve 512 byte samples and needs 110 registers: 1.14 -> 1.94 ms per 512 images.  The direct gathers stay.)
 // One warp describes DESC_KPW keypoints: the intensity-centroid sums and the 256 tests of each keypoint are spread
 // over the 32 lanes, while the per-keypoint scalar work (fastAtan2, the double-precision cos/sin OpenCV uses, the
 // keypoint record) is done once with lane i owning keypoint i instead of 32 times redundantly.
@@ -962,38 +962,17 @@ describe_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const uint8_t* __re
     const float th = __fmul_rn(angle, 0x1.1df46ap-6f);  // (float)(CV_PI/180)
     const float my_a = (float)cos((double)th), my_b = (float)sin((double)th);
 
-    // rotated BRIEF on the blurred level (orb.cpp computeOrbDescriptors, WTA_K = 2); lane = output byte.
-    // The 512 samples of a keypoint fall inside a 39 x 39 window (|pattern| <= 13, rotated: <= 19): as scattered byte
-    // loads from global memory every one of the 16 warp-wide loads touches up to 32 different sectors and the kernel
-    // sits on L1/L2 gather latency.  The window's rows are instead copied as ALIGNED 32-bit words (11 per row, coalesced,
-    // all in flight at once) into a per-warp shared-memory patch -- two patches, so the copy of keypoint i + 1 overlaps
-    // the sampling of keypoint i -- and the samples are shared-memory byte reads.
-    __shared__ uint32_t s_patch[DESC_WARPS][2][DP_ROWS * DP_WORDS];
-    const int warp_in_cta = threadIdx.x >> 5;
+    // rotated BRIEF on the blurred level (orb.cpp computeOrbDescriptors, WTA_K = 2); lane = output byte
     const float4* pat = reinterpret_cast<const float4*>(pattern) + lane * 8;
     float4 pt[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) pt[t] = __ldg(&pat[t]);  // (x0, y0, x1, y1) of test 8*lane + t
-    auto stage = [&](int i, int buf) -> int {  // returns the byte offset of the window's column 0 inside its first word
+    for (int i = 0; i < nk; ++i) {
+        const float a = __shfl_sync(0xFFFFFFFFu, my_a, i), b = __shfl_sync(0xFFFFFFFFu, my_b, i);
         const int cx = __shfl_sync(0xFFFFFFFFu, my_cx, i), cy = __shfl_sync(0xFFFFFFFFu, my_cy, i);
         const int l = __shfl_sync(0xFFFFFFFFu, my_l, i);
         const int bp = g.lv[l].pitch;
-        const uint8_t* row0 = blur + (size_t)img * g.img_slab + g.lv[l].off + (size_t)(cy - DP_R) * bp + (cx - DP_R);
-        const int a = (int)((uintptr_t)row0 & 3u);  // pitches are multiples of 16: the same for every row
-        const uint32_t* base = reinterpret_cast<const uint32_t*>(row0 - a);
-        uint32_t* dst = s_patch[warp_in_cta][buf];
-        for (int e = lane; e < DP_ROWS * DP_WORDS; e += 32) {
-            const int r = e / DP_WORDS, wj = e - r * DP_WORDS;
-            dst[e] = __ldg(base + (size_t)r * (bp >> 2) + wj);
-        }
-        return a;
-    };
-    int a_cur = stage(0, 0);
-    for (int i = 0; i < nk; ++i) {
-        __syncwarp();
-        const int a_next = (i + 1 < nk) ? stage(i + 1, (i + 1) & 1) : 0;
-        const float a = __shfl_sync(0xFFFFFFFFu, my_a, i), b = __shfl_sync(0xFFFFFFFFu, my_b, i);
-        const uint8_t* center = reinterpret_cast<const uint8_t*>(s_patch[warp_in_cta][i & 1]) + DP_R * (DP_WORDS * 4) + DP_R + a_cur;
+        const uint8_t* center = blur + (size_t)img * g.img_slab + g.lv[l].off + (size_t)cy * bp + cx;
         uint32_t byte = 0;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
@@ -1005,12 +984,11 @@ describe_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const uint8_t* __re
             const float ry1 = __fadd_rn(__fadd_rn(__fmul_rn(p0.z, b), __fmul_rn(p0.w, a)), 12582912.f);
             const int ix0 = __float_as_int(rx0) - 0x4B400000, iy0 = __float_as_int(ry0) - 0x4B400000;
             const int ix1 = __float_as_int(rx1) - 0x4B400000, iy1 = __float_as_int(ry1) - 0x4B400000;
-            const int t0 = center[iy0 * (DP_WORDS * 4) + ix0];
-            const int t1 = center[iy1 * (DP_WORDS * 4) + ix1];
+            const int t0 = center[iy0 * bp + ix0];
+            const int t1 = center[iy1 * bp + ix1];
             byte |= (uint32_t)(t0 < t1) << t;
         }
         desc_out[((size_t)oslot * kp_cap + k0 + i) * 32 + lane] = (uint8_t)byte;
-        a_cur = a_next;
     }
 }
 
