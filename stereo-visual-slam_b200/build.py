@@ -78,13 +78,14 @@ RUN_VSLAM = os.path.join(HERE, "run_vslam")
 def build_host(force: bool = False) -> str:
     """C++ drop-in layer (VO, Map, optimize_*) + the run_vslam main loop, linked against libvslam_b200.so."""
     cxx = os.environ.get("CXX", "g++")
-    srcs = [os.path.join(HOST, f) for f in ("types_def.cpp", "map.cpp", "optimization.cpp", "visual_odometry.cpp")]
+    srcs = [os.path.join(HOST, f) for f in ("types_def.cpp", "map.cpp", "optimization.cpp", "visual_odometry.cpp",
+                                            "png_reader.cpp")]
     deps = srcs + [os.path.join(HOST, "run_vslam.cpp"), os.path.join(HOST, "compat", "vslam_compat.hpp"),
                    os.path.join(HERE, "..", "include", "vslam_b200.h")]
     deps += [os.path.join(HOST, "stereo_visual_slam_main", f) for f in os.listdir(os.path.join(HOST, "stereo_visual_slam_main"))]
     if force or not os.path.exists(HOST_LIB) or any(os.path.getmtime(d) > os.path.getmtime(HOST_LIB) for d in deps):
         cmd = [cxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-I", HOST, "-o", HOST_LIB, *srcs,
-               "-L", HERE, "-lvslam_b200", "-Wl,-rpath,$ORIGIN"]
+               "-L", HERE, "-lvslam_b200", "-lz", "-Wl,-rpath,$ORIGIN"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout)

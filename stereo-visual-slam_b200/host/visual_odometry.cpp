@@ -75,12 +75,26 @@ static bool read_pgm(const std::string& path, cv::Mat& img) {
     return (bool)f;
 }
 
+bool read_png_gray8(const std::string& path, std::vector<uint8_t>& grey, int& w, int& h);  // png_reader.cpp
+
+static bool read_png(const std::string& path, cv::Mat& img) {
+    std::vector<uint8_t> g;
+    int w = 0, h = 0;
+    if (!read_png_gray8(path, g, w, h)) return false;
+    img.create(h, w, cv::CV_8U);
+    std::memcpy(img.data, g.data(), g.size());
+    return true;
+}
+
+// image_0/%06d.png as the reference reads it (visual_odometry.cpp:42-51, cv::imread GRAYSCALE); binary PGM files of the
+// same name are accepted as well
+static bool read_gray(const std::string& stem, cv::Mat& img) { return read_png(stem + ".png", img) || read_pgm(stem + ".pgm", img); }
+
 int VO::read_img(int id, cv::Mat& left_img, cv::Mat& right_img) {
     if (image_source_) return image_source_(id, left_img, right_img);
     char name[16];
     std::snprintf(name, sizeof(name), "%06d", id);
-    const bool ok = read_pgm(dataset_ + "image_0/" + name + ".pgm", left_img) &&
-                    read_pgm(dataset_ + "image_1/" + name + ".pgm", right_img);
+    const bool ok = read_gray(dataset_ + "image_0/" + name, left_img) && read_gray(dataset_ + "image_1/" + name, right_img);
     if (!ok || !left_img.data) {
         std::cout << "Could not open or find the image" << std::endl;
         return -1;

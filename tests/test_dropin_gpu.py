@@ -99,3 +99,22 @@ def test_wider_window_and_landmark_write_back(sequence, tmp_path):
     err = np.abs(T[:, :, 3] - t[:n]).max(axis=1)
     assert err[:12].max() < 0.05 and err.max() < 0.5, err   # before the first BA: identical; after: gauge drift only
     assert (meta[1:, 0] >= 10).all()
+
+
+def test_png_sequence_like_kitti(pkg, sequence, tmp_path):
+    """image_0/%06d.png read by VO::read_img (the reference: cv::imread GRAYSCALE, visual_odometry.cpp:42-51):
+    the run on PNG files equals the run on the PGM files frame for frame"""
+    import cv2
+    seq_dir, n, t = sequence
+    d = tmp_path / "png"
+    os.makedirs(d / "image_0"); os.makedirs(d / "image_1")
+    for i in range(n):
+        for cam in ("image_0", "image_1"):
+            img = np.fromfile(os.path.join(seq_dir, cam, f"{i:06d}.pgm"), dtype=np.uint8)
+            img = img[-376 * 1241:].reshape(376, 1241)
+            cv2.imwrite(str(d / cam / f"{i:06d}.png"), img)
+    wa, wb = tmp_path / "a", tmp_path / "b"
+    os.makedirs(wa); os.makedirs(wb)
+    ids, T, meta, out = _run(str(d) + "/", n, wa, "--no-ba")
+    ids2, T2, meta2, out2 = _run(seq_dir, n, wb, "--no-ba")
+    assert len(ids) == n and np.array_equal(ids, ids2) and np.array_equal(meta, meta2) and np.array_equal(T, T2)
