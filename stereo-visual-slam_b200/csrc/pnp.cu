@@ -325,23 +325,35 @@ pnp_refine_kernel(const float* __restrict__ xyz, const float* __restrict__ uv, i
 // ----------------------------------------------------------------------------------------------------------------
 // K7 stand-alone: ANMS over a caller-supplied keypoint list (any order), one CTA.
 // ----------------------------------------------------------------------------------------------------------------
+// radius scan spread over the grid: one warp per keypoint i, lanes stride over all keypoints j with
+// response_j > response_i * c (any input order); min of the squared distances, one sqrt at the end (sqrt is monotone
+// and correctly rounded, so this equals the reference's min over sqrt bit for bit)
+__global__ void __launch_bounds__(256)
+anms_points_radius_kernel(const vslam_keypoint* __restrict__ kp, int n, float c_robust, double* __restrict__ rad) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+        const float thr = __fmul_rn(kp[i].response, c_robust);
+        const float xi = kp[i].x, yi = kp[i].y;
+        double best2 = 1.7976931348623157e308;
+        for (int j = lane; j < n; j += 32) {
+            if (!(kp[j].response > thr)) continue;
+            const float dx = __fsub_rn(xi, kp[j].x), dy = __fsub_rn(yi, kp[j].y);
+            best2 = fmin(best2, __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best2 = fmin(best2, __shfl_xor_sync(0xFFFFFFFFu, best2, o));
+        if (lane == 0) rad[i] = best2 < 1.7976931348623157e308 ? sqrt(best2) : best2;
+    }
+}
+
 __global__ void __launch_bounds__(1024)
 anms_points_kernel(const vslam_keypoint* __restrict__ kp, int n, int num, float c_robust, double* __restrict__ rad,
                    int* __restrict__ keep) {
     extern __shared__ unsigned long long s_sort[];
     __shared__ int s_base, s_warp[32];
     const int tid = threadIdx.x;
-    for (int i = tid; i < n; i += 1024) {
-        const float thr = __fmul_rn(kp[i].response, c_robust);
-        const float xi = kp[i].x, yi = kp[i].y;
-        double best = 1.7976931348623157e308;
-        for (int j = 0; j < n; ++j) {
-            if (!(kp[j].response > thr)) continue;
-            const float dx = __fsub_rn(xi, kp[j].x), dy = __fsub_rn(yi, kp[j].y);
-            best = fmin(best, sqrt(__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy))));
-        }
-        rad[i] = best;
-    }
+    (void)kp;
+    (void)c_robust;
     __syncthreads();
     int n2 = 1;
     while (n2 < n) n2 <<= 1;
@@ -530,6 +542,8 @@ extern "C" int vslam_anms(vslam_ctx* ctx, const vslam_keypoint* keypoints, int n
     cudaStream_t s = ctx->stream;
     VSLAM_CUDA(ctx, cudaMemcpyAsync(p->d_kp, keypoints, (size_t)n * sizeof(vslam_keypoint), cudaMemcpyHostToDevice, s));
     vslam_time_begin(ctx, VK_ANMS);
+    anms_points_radius_kernel<<<min(ceil_div(n, 8), 4 * ctx->num_sms), 256, 0, s>>>(p->d_kp, n, c_robust, p->d_rad);
+    VSLAM_LAUNCH_CHECK(ctx, "anms_points_radius_kernel");
     anms_points_kernel<<<1, 1024, (size_t)n2 * 8, s>>>(p->d_kp, n, num, c_robust, p->d_rad, p->d_keep);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "anms_points_kernel");
