@@ -367,7 +367,8 @@ extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, 
     cudaStream_t s = ctx->stream;
     // staging keeps the caller's row pitch when the batch is one contiguous block: 1-D DMAs instead of 2-D copies of
     // 1241-byte rows (the kernels read bytes, so the pitch need not be aligned)
-    const bool contiguous = image_stride == (long long)row_pitch * height && row_pitch <= f->pitch;
+    static const bool align_env = getenv("VSLAM_FRONT_ALIGN") != nullptr;  // experiment: always stage into 16-byte aligned rows
+    const bool contiguous = image_stride == (long long)row_pitch * height && row_pitch <= f->pitch && !(align_env && (row_pitch & 15));
     const int dpitch = contiguous ? row_pitch : f->pitch;
     const size_t dstride = (size_t)dpitch * height;
     uint8_t* dl = f->d_img;
