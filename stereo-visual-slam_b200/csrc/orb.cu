@@ -8,7 +8,7 @@
 //
 // Pipeline (every kernel covers ALL images of the batch; nothing returns to the host in between):
 //   resize_level_kernel x7   K1  INTER_LINEAR_EXACT chain, 8.8 fixed point, coefficient tables from the host
-//   fast_kernel              K2  FAST-9/16 (t=20) score + 3x3 NMS + 31-px border filter, tile = 64x32 in smem,
+//   fast_kernel              K2  FAST-9/16 (t=20) score + 3x3 NMS + 31-px border filter, tile = 60x30 in smem,
 //                                candidate list + per-(image,level) 256-bin score histogram
 //   harris_select_kernel     K3-K5 one CTA per (level,image): histogram cut (retainBest 2N, ties kept), Harris
 //                                response (7x7, no FMA), bitonic sort by (response desc, y, x), retainBest N
@@ -37,7 +37,8 @@
 struct OrbLevel {
     int w, h, pitch;
     int off;  // byte offset of the plane inside one image's slab (pyramid and blurred pyramid share the layout)
-    int tiles_x, tiles_y, tile_begin;
+    int tiles_x, tiles_y, tile_begin;  // blur tiling: TILE_W x TILE_H over the whole level
+    int ft_x, ft_y, ft_begin;          // FAST tiling: FT_W x FT_H over the frame the 31-px border filter keeps
     int cand_off, cand_cap;  // candidate-list region (entries) inside one image's candidate slab
     int xtab_off, ytab_off;  // resize coefficient tables (entries)
     float scale, inv_scale;
@@ -45,7 +46,7 @@ struct OrbLevel {
 
 struct OrbGeom {
     OrbLevel lv[ORB_NL];
-    int total_tiles;
+    int total_tiles, total_ft;
     int img_slab;   // bytes per image in the pyramid / blurred slabs
     int cand_slab;  // candidate entries per image
     int w, h;
@@ -176,22 +177,44 @@ resize_level_kernel(ImgSrc src, uint8_t* __restrict__ pyr, const uint32_t* __res
 // ------------------------------------------------------------------------------------------------------------
 // The tile's pixels are widened to 16 bits in shared memory so that one 32-bit word holds TWO horizontally adjacent
 // pixels; every step of the segment test / corner score then runs on a pixel pair with the native packed-16-bit
-// instructions of sm_100a (VIADD.16x2, VIMNMX.S16x2, VIMNMX3.S16x2).
-//   image tile : rows gy = ty0-4 .. ty0+35, columns gx = tx0-8 .. tx0+71 (gx < tx0-4 and gx > tx0+67 are zero padding)
-//   score tile : rows gy = ty0-1 .. ty0+32, columns gx = tx0-2 .. tx0+65, value h = max(corner score + 1, FAST_T)
-#define FI_ROWS (TILE_H + 8)
-#define FI_WORDS 40                 // words per image-tile row (80 pixels)
-#define FI_LOAD_WORDS 18            // 32-bit global words per row that carry pixels (72 pixels)
-#define FS_ROWS (TILE_H + 2)
-#define FS_WORDS 34                 // words (= pixel pairs) per score-tile row
-#define FAST_OUT_CAP 640
+// instructions of sm_100a (VIADD.16x2, VIMNMX.S16x2, VIMNMX3.S16x2 -- half-rate ALU instructions: 80 of them per pair
+// are the corner-score network, the floor of this kernel).
+//
+// Only pixels that survive ORB's 31-px border filter are ever used, and their 3x3 NMS neighbourhood and 16-px rings
+// lie >= 27 px inside the image, so the tile grid covers just the kept frame [30, W-31) x [31, H-31): no border
+// cases anywhere, and 20 % (level 0) to 65 % (level 7) fewer pixels than the whole level.
+//   output tile : FT_W x FT_H pixels at (tx0, ty0) = (30 + 60 i, 31 + 30 j)   (column 30 is dropped by the filter;
+//                 it keeps pixel pairs on even columns, i.e. on the byte pairs of the aligned global loads)
+//   score tile  : rows ty0-1 .. ty0+30, 32 pixel pairs from column tx0-2: one warp per row, one lane per pair
+//   image tile  : rows ty0-4 .. ty0+33, 96 pixels from gstart = (tx0-6) & ~15 (six aligned 128-bit loads per row)
+// Phases: (1) compass pre-test, every warp compacts the surviving pairs of its rows into its own list (ballot +
+// popc, no atomics, no block barrier); (2) full segment test + score on the list; (3) 3x3 NMS with a sliding
+// 3-row window in registers, border filter, ballot-compacted emit.
+#define FT_W 60
+#define FT_H 30
+#define FT_X0 30
+#define FT_Y0 ORB_EDGE
+#define FI_ROWS (FT_H + 8)
+#define FI_WORDS 48                 // words per image-tile row (96 pixels)
+#define FS_ROWS (FT_H + 2)
+#define FS_WORDS 32                 // words (= pixel pairs) per score-tile row
+#define FAST_WARPS (FAST_THREADS / 32)
+#define FAST_RPW (FS_ROWS / FAST_WARPS)   // score rows per warp
+#define FAST_OUT_CAP 480            // a 60x30 tile holds at most 30 x 15 strict 3x3 maxima
 #define FAST_TT ((uint32_t)FAST_T | ((uint32_t)FAST_T << 16))
+static_assert(FS_ROWS % FAST_WARPS == 0 && FS_WORDS == 32, "one warp per score row, one lane per pixel pair");
 
 __device__ __forceinline__ uint32_t neg16x2(uint32_t a) { return __vadd2(~a, 0x00010001u); }
 // two adjacent pixels starting at the odd pixel of word `lo` (upper half of lo, lower half of hi)
 __device__ __forceinline__ uint32_t mid16x2(uint32_t lo, uint32_t hi) { return __byte_perm(lo, hi, 0x5432); }
 __device__ __forceinline__ bool any_lane_gt_t(uint32_t e) {
-    return (int)(e << 16) > (FAST_T << 16) || (int)e > ((FAST_T << 16) | 0xFFFF);
+    return ((int)(e << 16) > (FAST_T << 16)) | ((int)e > ((FAST_T << 16) | 0xFFFF));
+}
+// shared-memory atomic add issued as written (nvcc otherwise wraps it in its own warp-aggregation sequence)
+__device__ __forceinline__ int atom_add_shared(int* p, int v) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+    return old;
 }
 
 __global__ void __launch_bounds__(FAST_THREADS)
@@ -199,138 +222,103 @@ fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__
             ImgCounters* __restrict__ cnt, uint32_t* __restrict__ sticky) {
     __shared__ __align__(16) uint32_t s_img[FI_ROWS * FI_WORDS];
     __shared__ uint32_t s_sc[FS_ROWS * FS_WORDS];
-    __shared__ uint16_t s_list[FS_ROWS * FS_WORDS];
+    __shared__ uint16_t s_list[FAST_WARPS][FAST_RPW * 32];
     __shared__ uint2 s_out[FAST_OUT_CAP];
     __shared__ uint32_t s_hist[256];
-    __shared__ int s_n1, s_nout, s_base;
+    __shared__ int s_nout, s_base;
 
     const int img = blockIdx.y;
     int l = 0;
 #pragma unroll
     for (int i = 1; i < ORB_NL; ++i)
-        if ((int)blockIdx.x >= g.lv[i].tile_begin) l = i;
+        if ((int)blockIdx.x >= g.lv[i].ft_begin) l = i;
     const OrbLevel& L = g.lv[l];
-    const int t = blockIdx.x - L.tile_begin;
-    const int tx0 = (t % L.tiles_x) * TILE_W, ty0 = (t / L.tiles_x) * TILE_H;
+    const int t = blockIdx.x - L.ft_begin;
+    const int tyi = t / L.ft_x;
+    const int tx0 = FT_X0 + (t - tyi * L.ft_x) * FT_W, ty0 = FT_Y0 + tyi * FT_H;
     int pitch;
     const uint8_t* im = level_ptr(src, pyr, g, img, l, pitch);
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int W = L.w, H = L.h;
+    const int gstart = (tx0 - 6) & ~15;
+    const int shift = (tx0 - 6 - gstart) >> 1;  // word offset of pixel tx0-6 inside an image-tile row (0, 2, 4 or 6)
+    // rows / pairs of the score tile that some kept pixel's NMS can read
+    const int n_srow = min(FS_ROWS, H - ORB_EDGE - ty0 + 2);       // score rows 0 .. n_srow-1 (gy <= H-31)
+    const int n_orow = min(FT_H, H - ORB_EDGE - ty0);              // output rows
+    const bool pair_live = tx0 - 2 + 2 * lane <= W - ORB_EDGE;     // this lane's score pair (gx <= W-31)
 
-    // ---- load.  The stall profile of this kernel was dominated by the tile fill (one 32-bit load in flight per thread,
-    // three dependent rounds), so: when the level's rows are 16-byte aligned (every pyramid level, and level 0 whenever
-    // the caller's pitch and base allow it) ONE 128-bit load per thread fetches the whole 40 x 96-pixel window
-    // [tx0-16, tx0+80) -- 240 loads per tile, all in flight at once; otherwise the 32-bit path issues its three loads
-    // per thread back to back before touching any of them.  Pixels outside the image never reach a kept score (a
-    // corner's ring lies inside the image), so out-of-image lanes may hold anything that is safe to read.
+    // ---- load: one 128-bit load per 16 pixels when the level's rows are 16-byte aligned (every pyramid level, and
+    // level 0 whenever the caller's pitch and base allow it); all loads of a thread are issued before any is used.
+    // Pixels beyond the image only feed scores of pixels the border filter drops; they read as zero.
     const bool aligned16 = ((pitch & 15) == 0) && (((uintptr_t)im & 15) == 0);
     if (aligned16) {
-        if (tid < FI_ROWS * 6) {
-            const int r = tid / 6, ch = tid - r * 6;
-            const int gy = ty0 - 4 + r, gx = tx0 - 16 + 16 * ch;
-            uint4 px = make_uint4(0, 0, 0, 0);
-            if (gy >= 0 && gy < H && gx >= 0 && gx < pitch) px = __ldg(reinterpret_cast<const uint4*>(im + (size_t)gy * pitch + gx));
-            // 16 pixels -> 8 words of two 16-bit pixels; word index in the row = (gx - (tx0 - 8)) / 2 = 8 * ch - 4
-            uint32_t w[8];
-            w[0] = __byte_perm(px.x, 0, 0x4140); w[1] = __byte_perm(px.x, 0, 0x4342);
-            w[2] = __byte_perm(px.y, 0, 0x4140); w[3] = __byte_perm(px.y, 0, 0x4342);
-            w[4] = __byte_perm(px.z, 0, 0x4140); w[5] = __byte_perm(px.z, 0, 0x4342);
-            w[6] = __byte_perm(px.w, 0, 0x4140); w[7] = __byte_perm(px.w, 0, 0x4342);
-            uint32_t* dst = &s_img[r * FI_WORDS + 8 * ch - 4];
-            if (ch > 0) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);          // words 8ch-4 .. 8ch-1
-            if (ch < 5) *reinterpret_cast<uint4*>(dst + 4) = make_uint4(w[4], w[5], w[6], w[7]);      // words 8ch .. 8ch+3
-        }
-    } else {
-        constexpr int ROUNDS = (FI_ROWS * FI_LOAD_WORDS + FAST_THREADS - 1) / FAST_THREADS;
-        uint32_t q0[ROUNDS], q1[ROUNDS];
-        int sh[ROUNDS];
+        constexpr int N = FI_ROWS * 6, ROUNDS = (N + FAST_THREADS - 1) / FAST_THREADS;
+        uint4 px[ROUNDS];
 #pragma unroll
-        for (int k = 0; k < ROUNDS; ++k) {  // issue every load first
+        for (int k = 0; k < ROUNDS; ++k) {
             const int i = tid + k * FAST_THREADS;
-            const int r = i / FI_LOAD_WORDS, wj = i - r * FI_LOAD_WORDS;
-            const int gy = ty0 - 4 + r, gx = tx0 - 4 + 4 * wj;
-            q0[k] = q1[k] = 0;
-            sh[k] = -1;  // -1: nothing to fetch, -2: per-byte edge case
-            if (i < FI_ROWS * FI_LOAD_WORDS && gy >= 0 && gy < H) {
-                const uint8_t* p = im + (size_t)gy * pitch + gx;
-                if (gx >= 0 && gx + 3 < W) {
-                    const uint32_t a = (uint32_t)(uintptr_t)p & 3u;
-                    const uint32_t* q = reinterpret_cast<const uint32_t*>(p - a);
-                    q0[k] = __ldg(q);
-                    if (a) q1[k] = __ldg(q + 1);
-                    sh[k] = 8 * (int)a;
-                } else {
-                    sh[k] = -2;
-                }
-            }
+            const int r = i / 6, ch = i - r * 6;
+            const int gy = ty0 - 4 + r, gx = gstart + 16 * ch;
+            px[k] = make_uint4(0, 0, 0, 0);
+            if (i < N && gy < H && gx < pitch) px[k] = __ldg(reinterpret_cast<const uint4*>(im + (size_t)gy * pitch + gx));
         }
 #pragma unroll
         for (int k = 0; k < ROUNDS; ++k) {
             const int i = tid + k * FAST_THREADS;
-            if (i >= FI_ROWS * FI_LOAD_WORDS) continue;
-            const int r = i / FI_LOAD_WORDS, wj = i - r * FI_LOAD_WORDS;
-            uint32_t px = 0;
-            if (sh[k] >= 0) {
-                px = __funnelshift_r(q0[k], q1[k], sh[k]);
-            } else if (sh[k] == -2) {
-                const int gy = ty0 - 4 + r, gx = tx0 - 4 + 4 * wj;
+            if (i >= N) continue;
+            uint4* dst = reinterpret_cast<uint4*>(&s_img[(i / 6) * FI_WORDS + 8 * (i % 6)]);
+            dst[0] = make_uint4(__byte_perm(px[k].x, 0, 0x4140), __byte_perm(px[k].x, 0, 0x4342),
+                                __byte_perm(px[k].y, 0, 0x4140), __byte_perm(px[k].y, 0, 0x4342));
+            dst[1] = make_uint4(__byte_perm(px[k].z, 0, 0x4140), __byte_perm(px[k].z, 0, 0x4342),
+                                __byte_perm(px[k].w, 0, 0x4140), __byte_perm(px[k].w, 0, 0x4342));
+        }
+    } else {  // any pitch / base: byte loads
+        for (int i = tid; i < FI_ROWS * FI_WORDS; i += FAST_THREADS) {
+            const int r = i / FI_WORDS, m = i - r * FI_WORDS;
+            const int gy = ty0 - 4 + r, gx = gstart + 2 * m;
+            uint32_t v = 0;
+            if (gy < H) {
                 const uint8_t* p = im + (size_t)gy * pitch + gx;
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (gx + b >= 0 && gx + b < W) px |= (uint32_t)p[b] << (8 * b);
+                if (gx < W) v = p[0];
+                if (gx + 1 < W) v |= (uint32_t)p[1] << 16;
             }
-            uint2 v;
-            v.x = __byte_perm(px, 0, 0x4140);
-            v.y = __byte_perm(px, 0, 0x4342);
-            *reinterpret_cast<uint2*>(&s_img[r * FI_WORDS + 2 + 2 * wj]) = v;
+            s_img[i] = v;
         }
     }
-    if (!aligned16 && tid < FI_ROWS * 4) {  // zero padding: words 0,1 and 38,39 of every row (the 128-bit path fills them)
-        const int r = tid >> 2, k = tid & 3;
-        s_img[r * FI_WORDS + (k < 2 ? k : 36 + k)] = 0;
-    }
     s_hist[tid] = 0;  // FAST_THREADS == 256
-    if (tid == 0) {
-        s_n1 = 0;
-        s_nout = 0;
-    }
+    if (tid == 0) s_nout = 0;
     __syncthreads();
 
     // ---- phase 1: compass pre-test on pixel pairs (any 9-arc contains two adjacent compass pixels) ---------------
-    for (int p0 = 0; p0 < FS_ROWS * FS_WORDS; p0 += FAST_THREADS) {
-        const int p = p0 + tid;
-        bool pass = false;
-        if (p < FS_ROWS * FS_WORDS) {
-            const int r = p / FS_WORDS, j = p - r * FS_WORDS;
-            const uint32_t* c = &s_img[(r + 3) * FI_WORDS + j + 3];
-            const uint32_t nv = neg16x2(c[0]);
-            const uint32_t d0 = __vadd2(c[3 * FI_WORDS], nv), d8 = __vadd2(c[-3 * FI_WORDS], nv);
-            const uint32_t d4 = __vadd2(mid16x2(c[1], c[2]), nv), d12 = __vadd2(mid16x2(c[-2], c[-1]), nv);
-            const uint32_t mb = __vmaxs2(__vimax3_s16x2(__vmins2(d0, d4), __vmins2(d4, d8), __vmins2(d8, d12)),
-                                         __vmins2(d12, d0));
-            const uint32_t md = __vmins2(__vimin3_s16x2(__vmaxs2(d0, d4), __vmaxs2(d4, d8), __vmaxs2(d8, d12)),
-                                         __vmaxs2(d12, d0));
-            pass = any_lane_gt_t(__vmaxs2(mb, neg16x2(md)));
-            if (!pass) s_sc[p] = FAST_TT;
-        }
+    const uint32_t* ctr = &s_img[3 * FI_WORDS + shift + 2 + lane];  // centre word of score pair (row 0, lane)
+    uint16_t* list = s_list[wid];
+    int n1 = 0;
+#pragma unroll
+    for (int k = 0; k < FAST_RPW; ++k) {
+        const int r = wid + k * FAST_WARPS;
+        const uint32_t* c = ctr + r * FI_WORDS;
+        // on the raw ring values (min / max commute with subtracting the centre)
+        const uint32_t cv = c[0];
+        const uint32_t d0 = c[3 * FI_WORDS], d8 = c[-3 * FI_WORDS];
+        const uint32_t d4 = mid16x2(c[1], c[2]), d12 = mid16x2(c[-2], c[-1]);
+        const uint32_t mb = __vmaxs2(__vimax3_s16x2(__vmins2(d0, d4), __vmins2(d4, d8), __vmins2(d8, d12)),
+                                     __vmins2(d12, d0));
+        const uint32_t md = __vmins2(__vimin3_s16x2(__vmaxs2(d0, d4), __vmaxs2(d4, d8), __vmaxs2(d8, d12)),
+                                     __vmaxs2(d12, d0));
+        const bool pass = pair_live & (r < n_srow) & any_lane_gt_t(__vmaxs2(__vsub2(mb, cv), __vsub2(cv, md)));
+        if (!pass) s_sc[r * FS_WORDS + lane] = FAST_TT;
         const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pass);
-        if (bal) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_n1, __popc(bal));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (pass) s_list[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)p;
-        }
+        if (pass) list[n1 + __popc(bal & ((1u << lane) - 1))] = (uint16_t)(r * FS_WORDS + lane);
+        n1 += __popc(bal);
     }
-    __syncthreads();
+    __syncwarp();
 
     // ---- phase 2: full segment test + corner score on the surviving pairs ----------------------------------------
     // score = max over the 16 arcs of max(min(d), -max(d)), d = centre - ring (sign-symmetric, so ring - centre is
-    // used); a pixel is a corner iff that exceeds FAST_T.  Sliding min / max over 9 = (pairs, quads, 4+4+1).
-    const int n1 = s_n1;
-    for (int e = tid; e < n1; e += FAST_THREADS) {
-        const int p = s_list[e];
-        const int r = p / FS_WORDS, j = p - r * FS_WORDS;
-        const uint32_t* c = &s_img[(r + 3) * FI_WORDS + j + 3];
+    // used); a pixel is a corner iff that exceeds FAST_T.
+    for (int e = lane; e < n1; e += 32) {
+        const int p = list[e];
+        const uint32_t* c = &s_img[3 * FI_WORDS + shift + 2] + (p >> 5) * FI_WORDS + (p & 31);
         const uint32_t nv = neg16x2(c[0]);
         uint32_t d[16];
         {
@@ -378,53 +366,64 @@ fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__
         }
         besta = __vadd2(__vmaxs2(besta, a[15]), nv);  // brightest arc minus the centre
         bmin = __vadd2(__vmins2(bmin, b[15]), nv);    // darkest arc minus the centre
-        const uint32_t best = __vmaxs2(besta, neg16x2(bmin));
-        // pixels closer than 3 to the image border have no full ring: not corners (h = FAST_T)
-        const int gy = ty0 - 1 + r, gx = tx0 - 2 + 2 * j;
-        const bool vy = gy >= 3 && gy < H - 3;
-        const uint32_t mask = ((vy && gx >= 3 && gx < W - 3) ? 0x00007FFFu : 0u) |
-                              ((vy && gx + 1 >= 3 && gx + 1 < W - 3) ? 0x7FFF0000u : 0u);
-        s_sc[p] = __vmaxs2(__vmins2(best, mask), FAST_TT);
+        // h = max(score, FAST_T): every pixel scored here has its whole ring inside the image
+        s_sc[p] = __vimax3_s16x2(besta, neg16x2(bmin), FAST_TT);
     }
     __syncthreads();
 
     // ---- phase 3: 3x3 NMS (strictly greater) on pixel pairs, border filter, emit ------------------------------------
-    for (int q0 = 0; q0 < TILE_W * TILE_H / 2; q0 += FAST_THREADS) {
-        const int q = q0 + tid;
-        const int r = q >> 5, j = q & 31;  // TILE_W / 2 == 32 pairs per row
-        const uint32_t* sc = &s_sc[(r + 1) * FS_WORDS + j + 1];
-        const uint32_t c0 = sc[0];
-        uint32_t m = __vimax3_s16x2(mid16x2(sc[-1], c0), mid16x2(c0, sc[1]), sc[-FS_WORDS]);
-        m = __vimax3_s16x2(m, mid16x2(sc[-FS_WORDS - 1], sc[-FS_WORDS]), mid16x2(sc[-FS_WORDS], sc[-FS_WORDS + 1]));
-        m = __vimax3_s16x2(m, mid16x2(sc[FS_WORDS - 1], sc[FS_WORDS]), mid16x2(sc[FS_WORDS], sc[FS_WORDS + 1]));
-        m = __vmaxs2(m, sc[FS_WORDS]);
-        const uint32_t x = __vmaxs2(c0, m) ^ m;  // lane != 0  <=>  centre strictly greater than its 8 neighbours
-        const int gy = ty0 + r, gx = tx0 + 2 * j;
-        const bool iny = gy >= ORB_EDGE && gy < H - ORB_EDGE;
-        const bool k0 = (x & 0xFFFFu) && iny && gx >= ORB_EDGE && gx < W - ORB_EDGE;
-        const bool k1 = (x >> 16) && iny && gx + 1 >= ORB_EDGE && gx + 1 < W - ORB_EDGE;
-        const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, k0), b1 = __ballot_sync(0xFFFFFFFFu, k1);
-        if (b0 | b1) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_nout, __popc(b0) + __popc(b1));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            const uint32_t lt = (1u << lane) - 1;
-            int pos = base + __popc(b0 & lt) + __popc(b1 & lt);
-            if (k0) {
-                const uint32_t s = (c0 & 0xFFFFu) - 1;
-                if (pos < FAST_OUT_CAP) s_out[pos] = make_uint2((uint32_t)gx | ((uint32_t)gy << 16), s);
-                atomicAdd(&s_hist[s], 1u);
-                ++pos;
+    // Warp w owns output rows 4w .. 4w+3 and slides down them: per score row `side` = max of the two horizontal
+    // neighbours, `full` = max(side, centre); the 8-neighbour maximum of row r is max3(full[r-1], side[r], full[r+1]).
+    {
+        constexpr int OPW = (FT_H + FAST_WARPS - 1) / FAST_WARPS;
+        const int ro0 = wid * OPW;
+        // lane <-> score word `lane`; output pairs are words 1..30 (pixels tx0 + 2 (lane-1))
+        const int gx = tx0 - 2 + 2 * lane;
+        const bool col0 = lane >= 1 && lane <= FT_W / 2 && gx >= ORB_EDGE && gx < W - ORB_EDGE;
+        const bool col1 = lane >= 1 && lane <= FT_W / 2 && gx + 1 < W - ORB_EDGE;
+        const int ll = max(lane - 1, 0), lr = min(lane + 1, 31);
+        uint32_t c_prev = 0, full_prev = 0, c_cur = 0, side_cur = 0, full_cur = 0;
+#pragma unroll
+        for (int k = 0; k < OPW + 2; ++k) {
+            const int sr = ro0 + k;  // score row (clamped: the rows past the tile only feed dead outputs)
+            const uint32_t* row = &s_sc[min(sr, FS_ROWS - 1) * FS_WORDS];
+            const uint32_t cw = row[lane];
+            const uint32_t side = __vmaxs2(mid16x2(row[ll], cw), mid16x2(cw, row[lr]));
+            const uint32_t full = __vmaxs2(side, cw);
+            if (k >= 2) {
+                const int ro = sr - 2;  // output row whose centre is score row sr-1 (= c_cur)
+                const uint32_t m = __vimax3_s16x2(full_prev, side_cur, full);
+                const uint32_t x = __vmaxs2(c_cur, m) ^ m;  // lane != 0  <=>  centre strictly greater than its 8 neighbours
+                const bool live = ro < n_orow;
+                const bool k0 = ((x & 0xFFFFu) != 0) & col0 & live, k1 = ((x >> 16) != 0) & col1 & live;
+                const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, k0), b1 = __ballot_sync(0xFFFFFFFFu, k1);
+                if (b0 | b1) {
+                    int base = 0;
+                    if (lane == 0) base = atom_add_shared(&s_nout, __popc(b0) + __popc(b1));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    const uint32_t lt = (1u << lane) - 1;
+                    int pos = base + __popc(b0 & lt) + __popc(b1 & lt);
+                    const uint32_t gy = (uint32_t)(ty0 + ro) << 16;
+                    if (k0) {
+                        const uint32_t sc = (c_cur & 0xFFFFu) - 1;
+                        if (pos < FAST_OUT_CAP) s_out[pos] = make_uint2((uint32_t)gx | gy, sc);
+                        atomicAdd(&s_hist[sc], 1u);
+                        ++pos;
+                    }
+                    if (k1) {
+                        const uint32_t sc = (c_cur >> 16) - 1;
+                        if (pos < FAST_OUT_CAP) s_out[pos] = make_uint2((uint32_t)(gx + 1) | gy, sc);
+                        atomicAdd(&s_hist[sc], 1u);
+                    }
+                }
             }
-            if (k1) {
-                const uint32_t s = (c0 >> 16) - 1;
-                if (pos < FAST_OUT_CAP) s_out[pos] = make_uint2((uint32_t)(gx + 1) | ((uint32_t)gy << 16), s);
-                atomicAdd(&s_hist[s], 1u);
-            }
+            c_prev = c_cur; full_prev = full_cur;
+            c_cur = cw; side_cur = side; full_cur = full;
+            (void)c_prev;
         }
     }
     __syncthreads();
-    const int nout = min(s_nout, FAST_OUT_CAP);  // a 64x32 tile holds at most 512 strict 3x3 maxima
+    const int nout = min(s_nout, FAST_OUT_CAP);
     if (nout == 0) return;
     ImgCounters* C = &cnt[img];
     if (tid == 0) s_base = (int)atomicAdd(&C->cand_cnt[l], (uint32_t)nout);
@@ -1035,7 +1034,7 @@ static int orb_set_geometry(vslam_ctx* ctx, int w, int h) {
     memset(&g, 0, sizeof(g));
     g.w = w;
     g.h = h;
-    int off = 0, tiles = 0, cand = 0, tab = 0;
+    int off = 0, tiles = 0, ft = 0, cand = 0, tab = 0;
     for (int l = 0; l < ORB_NL; ++l) {
         OrbLevel& L = g.lv[l];
         L.scale = h_scales[l];
@@ -1053,6 +1052,12 @@ static int orb_set_geometry(vslam_ctx* ctx, int w, int h) {
         L.tiles_y = ceil_div(L.h, TILE_H);
         L.tile_begin = tiles;
         tiles += L.tiles_x * L.tiles_y;
+        // kept frame: columns [FT_X0, w-31), rows [31, h-31); empty for a level narrower than the border allows
+        L.ft_x = L.w - ORB_EDGE > FT_X0 ? ceil_div(L.w - ORB_EDGE - FT_X0, FT_W) : 0;
+        L.ft_y = L.h - ORB_EDGE > FT_Y0 ? ceil_div(L.h - ORB_EDGE - FT_Y0, FT_H) : 0;
+        if (L.ft_x == 0 || L.ft_y == 0) L.ft_x = L.ft_y = 0;
+        L.ft_begin = ft;
+        ft += L.ft_x * L.ft_y;
         L.cand_off = cand;
         L.cand_cap = (L.w * L.h) / 12 + 64;
         cand += L.cand_cap;
@@ -1062,6 +1067,7 @@ static int orb_set_geometry(vslam_ctx* ctx, int w, int h) {
         tab += (L.h + 3) & ~3;
     }
     g.total_tiles = tiles;
+    g.total_ft = ft;
     g.img_slab = off;
     g.cand_slab = cand;
     if ((size_t)off > o->slab_cap || (size_t)cand > o->cand_cap_total || tab > o->tab_cap) return VSLAM_E_CAPACITY;
@@ -1187,7 +1193,7 @@ int vslam_orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h
         VSLAM_LAUNCH_CHECK(ctx, "resize_level_kernel");
     }
     vslam_time_begin(ctx, VK_FAST);
-    fast_kernel<<<dim3(g.total_tiles, n_img), FAST_THREADS, 0, s>>>(src, pyr, g, cand, cnt, o->d_sticky);
+    if (g.total_ft > 0) fast_kernel<<<dim3(g.total_ft, n_img), FAST_THREADS, 0, s>>>(src, pyr, g, cand, cnt, o->d_sticky);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "fast_kernel");
     vslam_time_begin(ctx, VK_HARRIS_SELECT);

@@ -62,14 +62,36 @@ def synth_canvas(seed: int, w: int = W + 200, h: int = H, n_rect: int = 400) -> 
     return canvas
 
 
-def synth_pair(seed: int, w: int = W, h: int = H):
+def synth_canvas_street(seed: int, w: int = W + 200, h: int = H) -> np.ndarray:
+    """Canvas with the corner statistics of a street scene: smooth shading, soft-edged flat objects, patches of fine
+    texture on a fraction of the area and a little sensor noise.  About 3 % of its pixels pass FAST-9/16 at t = 20
+    (KITTI frames: 1-3 %), against 17 % for `synth_canvas` -- ORB(2000) still fills its quota on it."""
+    rng = np.random.default_rng(seed)
+    base = _gauss_blur_sep(rng.integers(0, 256, size=(h, w), dtype=np.uint8), 12.0)
+    img = (base - base.min()) / (base.max() - base.min()) * 120.0 + 60.0
+    for _ in range(260):
+        rw = int(rng.integers(8, 90))
+        rh = int(rng.integers(8, 60))
+        x0 = int(rng.integers(0, w - rw))
+        y0 = int(rng.integers(0, h - rh))
+        img[y0:y0 + rh, x0:x0 + rw] = img[y0:y0 + rh, x0:x0 + rw] * 0.3 + float(rng.integers(20, 235)) * 0.7
+    fine = _gauss_blur_sep(rng.integers(0, 256, size=(h, w), dtype=np.uint8), 1.0)
+    fine = (fine - fine.mean()) / fine.std()
+    mask = _gauss_blur_sep((rng.random((h, w)) < 0.0008).astype(np.uint8) * 255, 10.0)
+    mask = np.clip(mask / mask.max() * 3.0, 0.0, 1.0)
+    img = _gauss_blur_sep(np.clip(img + fine * 22.0 * mask, 0, 255).astype(np.uint8), 0.7)
+    img = img + rng.normal(0.0, 1.5, size=img.shape)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def synth_pair(seed: int, w: int = W, h: int = H, texture: str = "dense"):
     """One rectified stereo pair (left, right, band_disparity[h]).
 
     left = canvas[:, 100:100+w]; right row y is the same canvas shifted by the
     disparity of y's horizontal band (8 bands, d in {4..80} px), i.e. a point at
     left column x appears at right column x - d.
     """
-    canvas = synth_canvas(seed, w + 200, h)
+    canvas = synth_canvas(seed, w + 200, h) if texture == "dense" else synth_canvas_street(seed, w + 200, h)
     rng = np.random.default_rng(seed + 1_000_003)
     left = np.ascontiguousarray(canvas[:, 100:100 + w])
     n_band = 8
