@@ -61,7 +61,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(f"[build] {f}\n{out}\n")
     if failed:
         raise RuntimeError("nvcc failed")
-    if force or procs or not os.path.exists(LIB):
+    if force or procs or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:

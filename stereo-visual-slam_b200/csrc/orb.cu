@@ -26,8 +26,6 @@
 #define ORB_NL VSLAM_NLEVELS
 #define ORB_EDGE 31
 #define FAST_T 20
-#define TILE_W 64
-#define TILE_H 32
 #define FAST_THREADS 256
 #define SORT_CAP 8192
 #define HS_THREADS 1024
@@ -37,7 +35,7 @@
 struct OrbLevel {
     int w, h, pitch;
     int off;  // byte offset of the plane inside one image's slab (pyramid and blurred pyramid share the layout)
-    int tiles_x, tiles_y, tile_begin;  // blur tiling: TILE_W x TILE_H over the whole level
+    int tiles_x, tiles_y, tile_begin;  // blur tiling: BL_W x BL_H over the whole level
     int ft_x, ft_y, ft_begin;          // FAST tiling: FT_W x FT_H over the frame the 31-px border filter keeps
     int cand_off, cand_cap;  // candidate-list region (entries) inside one image's candidate slab
     int xtab_off, ytab_off;  // resize coefficient tables (entries)
@@ -587,8 +585,17 @@ harris_select_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_c
 // ------------------------------------------------------------------------------------------------------------
 // K8  descriptor blur (see oracle/orb_restate.blur7 for how the op order was pinned against cv2)
 // ------------------------------------------------------------------------------------------------------------
-#define BL_ROWS (TILE_H + 6)  // input rows gy = ty0-3 .. ty0+34
-#define BL_WORDS 18           // input bytes gx = tx0-4 .. tx0+67 as 18 words per row
+// Tile = BL_W x BL_H pixels.  Thread (warp = strip of BL_SH rows, lane = quad of 4 columns) marches down its strip:
+// per input row one horizontal pass for its 4 columns (10 input bytes -> 4 floats), kept in a 7-row register window,
+// and from the 7th row on one vertical pass + rounding + one packed 32-bit store per row.  The float intermediate
+// never leaves registers; the horizontal pass is recomputed for the 6 halo rows of a strip (22 / 16).
+#define BL_W 128
+#define BL_H 128
+#define BL_SH 16                         // rows per strip
+#define BL_THREADS ((BL_W / 4) * (BL_H / BL_SH))
+#define BL_ROWS (BL_H + 6)               // input rows gy = ty0-3 .. ty0+BL_H+2
+#define BL_WORDS 40                      // input bytes gx = tx0-16 .. tx0+143 as 40 words per row (10 aligned 16-byte chunks)
+static_assert(BL_W == 128 && BL_THREADS == 256, "one lane per quad, one warp per strip");
 
 __device__ __forceinline__ int reflect101(int p, int n) {
     if (p < 0) p = -p;
@@ -602,10 +609,9 @@ __device__ __forceinline__ float byte_to_float(uint32_t w) {
     return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 | K)), 8388608.f);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(BL_THREADS)
 blur_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, const __grid_constant__ OrbGeom g) {
-    __shared__ uint32_t s_in[BL_ROWS * BL_WORDS];
-    __shared__ __align__(16) float s_row[BL_ROWS * TILE_W];
+    __shared__ __align__(16) uint32_t s_in[BL_ROWS * BL_WORDS];
     const float k0 = 0x1.1f5f62p-4f, k1 = 0x1.0c70fcp-3f, k2 = 0x1.869472p-3f, k3 = 0x1.ba95c0p-3f;
 
     const int img = blockIdx.y;
@@ -615,45 +621,70 @@ blur_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ b
         if ((int)blockIdx.x >= g.lv[i].tile_begin) l = i;
     const OrbLevel& L = g.lv[l];
     const int t = blockIdx.x - L.tile_begin;
-    const int tx0 = (t % L.tiles_x) * TILE_W, ty0 = (t / L.tiles_x) * TILE_H;
+    const int tyi = t / L.tiles_x;
+    const int tx0 = (t - tyi * L.tiles_x) * BL_W, ty0 = tyi * BL_H;
     int pitch;
     const uint8_t* im = level_ptr(src, pyr, g, img, l, pitch);
     const int tid = threadIdx.x;
     const int W = L.w, H = L.h;
+    const int n_rows = min(BL_H, H - ty0) + 6;  // input rows some output row of this tile reads
 
-    // load: 4 pixels per work item (aligned 32-bit global loads inside the image, BORDER_REFLECT_101 bytes outside)
-    for (int i = tid; i < BL_ROWS * BL_WORDS; i += 256) {
-        const int r = i / BL_WORDS, wj = i - r * BL_WORDS;
-        const int gy = ty0 - 3 + r, gx = tx0 - 4 + 4 * wj;
-        uint32_t px = 0;
-        if (gy >= 0 && gy < H && gx >= 0 && gx + 3 < W) {
-            const uint8_t* p = im + (size_t)gy * pitch + gx;
-            const uint32_t a = (uint32_t)(uintptr_t)p & 3u;
-            const uint32_t* q = reinterpret_cast<const uint32_t*>(p - a);
-            px = __ldg(q);
-            if (a) px = __funnelshift_r(px, __ldg(q + 1), 8 * a);
-        } else {
-            const uint8_t* row = im + (size_t)reflect101(min(gy, H + 2), H) * pitch;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) px |= (uint32_t)row[reflect101(min(gx + b, W + 2), W)] << (8 * b);
+    // load: BORDER_REFLECT_101.  Rows reflect through their index; columns are fetched as aligned 16-byte chunks
+    // (zero outside the pitch) and the three reflected bytes on either side of the image are patched in afterwards.
+    const bool aligned16 = ((pitch & 15) == 0) && (((uintptr_t)im & 15) == 0);
+    if (aligned16) {
+        for (int i = tid; i < n_rows * 10; i += BL_THREADS) {
+            const int r = i / 10, ch = i - r * 10;
+            const int gy = reflect101(min(ty0 - 3 + r, H + 2), H), gx = tx0 - 16 + 16 * ch;
+            uint4 px = make_uint4(0, 0, 0, 0);
+            if (gx >= 0 && gx < pitch) px = __ldg(reinterpret_cast<const uint4*>(im + (size_t)gy * pitch + gx));
+            *reinterpret_cast<uint4*>(&s_in[r * BL_WORDS + 4 * ch]) = px;
         }
-        s_in[i] = px;
+        __syncthreads();
+        uint8_t* s8 = reinterpret_cast<uint8_t*>(s_in);
+        const bool fix_l = tx0 == 0, fix_r = W < tx0 + BL_W + 3;
+        for (int r = tid; r < n_rows; r += BL_THREADS) {
+            uint8_t* row = s8 + r * (BL_WORDS * 4) + 16 - tx0;  // row[gx]
+            if (fix_r) {  // first: the left patch may read a byte this one writes when W is tiny
+#pragma unroll
+                for (int k = 0; k < 3; ++k) row[W + k] = row[W - 2 - k];
+            }
+            if (fix_l) {
+#pragma unroll
+                for (int k = 1; k <= 3; ++k) row[-k] = row[k];
+            }
+        }
+    } else {
+        for (int i = tid; i < n_rows * BL_WORDS; i += BL_THREADS) {
+            const int r = i / BL_WORDS, wj = i - r * BL_WORDS;
+            const uint8_t* row = im + (size_t)reflect101(min(ty0 - 3 + r, H + 2), H) * pitch;
+            const int gx = tx0 - 16 + 4 * wj;
+            uint32_t px = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) px |= (uint32_t)row[reflect101(min(max(gx + b, -3), W + 2), W)] << (8 * b);
+            s_in[i] = px;
+        }
     }
     __syncthreads();
 
-    // row pass: 4 outputs per work item from 10 input bytes.  cv2's AVX2 row filter: fused 32-wide body, unfused
-    // scalar tail (x >= 32 * (W / 32)); a quad never straddles the boundary.
-    const int tail = (W / 32) * 32;
-    for (int i = tid; i < BL_ROWS * (TILE_W / 4); i += 256) {
-        const int r = i >> 4, qi = i & 15;
-        const uint32_t* w = &s_in[r * BL_WORDS + qi];
-        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    const int q = tid & 31, strip = tid >> 5;
+    const int gx = tx0 + 4 * q, y0 = ty0 + strip * BL_SH;
+    if (gx >= W || y0 >= H) return;
+    // cv2's AVX2 row filter: fused 32-wide body, unfused scalar tail (x >= 32 * (W / 32)); a quad never straddles it
+    const bool fused = gx < (W / 32) * 32;
+    uint8_t* out = blur + (size_t)img * g.img_slab + L.off + (size_t)y0 * L.pitch + gx;
+    const uint32_t* in = &s_in[strip * BL_SH * BL_WORDS + 3 + q];
+    float win[7][4];
+#pragma unroll
+    for (int j = 0; j < BL_SH + 6; ++j) {
+        if (y0 + j - 6 >= H) break;  // warp-uniform: the rest of the strip lies below the image
+        const uint32_t w0 = in[j * BL_WORDS], w1 = in[j * BL_WORDS + 1], w2 = in[j * BL_WORDS + 2];
         float f[10];
         f[0] = byte_to_float<1>(w0); f[1] = byte_to_float<2>(w0); f[2] = byte_to_float<3>(w0);
         f[3] = byte_to_float<0>(w1); f[4] = byte_to_float<1>(w1); f[5] = byte_to_float<2>(w1); f[6] = byte_to_float<3>(w1);
         f[7] = byte_to_float<0>(w2); f[8] = byte_to_float<1>(w2); f[9] = byte_to_float<2>(w2);
         float o[4];
-        if (tx0 + 4 * qi < tail) {
+        if (fused) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 float acc = __fmul_rn(k0, f[k]);
@@ -676,37 +707,24 @@ blur_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ b
                 o[k] = __fadd_rn(acc, __fmul_rn(k0, f[k + 6]));
             }
         }
-        *reinterpret_cast<float4*>(&s_row[r * TILE_W + 4 * qi]) = make_float4(o[0], o[1], o[2], o[3]);
-    }
-    __syncthreads();
-
-    // column pass: 4 x 2 outputs per thread (symmetric pairing, fused), rounded once, packed 32-bit stores
-    {
-        const int qi = tid & 15, r0 = (tid >> 4) * 2;
-        const int gx = tx0 + 4 * qi;
-        if (gx >= W) return;
-        float4 p[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) p[k] = *reinterpret_cast<const float4*>(&s_row[(r0 + k) * TILE_W + 4 * qi]);
-        uint8_t* out = blur + (size_t)img * g.img_slab + L.off;
-#pragma unroll
-        for (int a = 0; a < 2; ++a) {
-            const int gy = ty0 + r0 + a;
-            if (gy >= H) break;
+        for (int k = 0; k < 4; ++k) win[j % 7][k] = o[k];
+        if (j >= 6) {
+            // column pass for output row y0 + j - 6: window rows (j-6 .. j) sit in slots (j-6) % 7 .. j % 7; symmetric
+            // pairing, fused, rounded once
             uint32_t packed = 0;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const float* pc = reinterpret_cast<const float*>(&p[0]) + c;  // element c of each float4 (stride 4)
-                float acc = __fmul_rn(k3, pc[4 * (a + 3)]);
-                acc = fmaf(__fadd_rn(pc[4 * (a + 4)], pc[4 * (a + 2)]), k2, acc);
-                acc = fmaf(__fadd_rn(pc[4 * (a + 5)], pc[4 * (a + 1)]), k1, acc);
-                acc = fmaf(__fadd_rn(pc[4 * (a + 6)], pc[4 * a]), k0, acc);
+                float acc = __fmul_rn(k3, win[(j - 3) % 7][c]);
+                acc = fmaf(__fadd_rn(win[(j - 2) % 7][c], win[(j - 4) % 7][c]), k2, acc);
+                acc = fmaf(__fadd_rn(win[(j - 1) % 7][c], win[(j - 5) % 7][c]), k1, acc);
+                acc = fmaf(__fadd_rn(win[j % 7][c], win[(j - 6) % 7][c]), k0, acc);
                 int v = __float2int_rn(acc);
                 v = max(0, min(255, v));
                 packed |= (uint32_t)v << (8 * c);
             }
             // gx is a multiple of 4 below W and the plane pitch is a multiple of 16: the word stays inside the row
-            *reinterpret_cast<uint32_t*>(&out[(size_t)gy * L.pitch + gx]) = packed;
+            *reinterpret_cast<uint32_t*>(out + (size_t)(j - 6) * L.pitch) = packed;
         }
     }
 }
@@ -1048,8 +1066,8 @@ static int orb_set_geometry(vslam_ctx* ctx, int w, int h) {
         L.off = off;
         off += L.pitch * L.h;
         off = (off + 255) & ~255;
-        L.tiles_x = ceil_div(L.w, TILE_W);
-        L.tiles_y = ceil_div(L.h, TILE_H);
+        L.tiles_x = ceil_div(L.w, BL_W);
+        L.tiles_y = ceil_div(L.h, BL_H);
         L.tile_begin = tiles;
         tiles += L.tiles_x * L.tiles_y;
         // kept frame: columns [FT_X0, w-31), rows [31, h-31); empty for a level narrower than the border allows
@@ -1202,7 +1220,7 @@ int vslam_orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "harris_select_kernel");
     vslam_time_begin(ctx, VK_BLUR);
-    blur_kernel<<<dim3(g.total_tiles, n_img), 256, 0, s>>>(src, pyr, blur, g);
+    blur_kernel<<<dim3(g.total_tiles, n_img), BL_THREADS, 0, s>>>(src, pyr, blur, g);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "blur_kernel");
     const int use_keep = anms_keep > 0 ? 1 : 0;
