@@ -168,7 +168,9 @@ def algorithmic_bytes(n_images: int, n_pairs: int, n_kp: float, n_match: float):
     return {
         # one launch per level l>=1: read level l-1, write level l  (sum over the 7 launches / 7 = per-launch average)
         "resize_level_kernel": n_images * (sum(px[:-1]) + sum(px[1:])) / 7.0,
-        "fast_kernel": n_images * tot,                      # every pyramid pixel read once (+ small candidate list)
+        # every pixel that can reach a kept keypoint, read once: the frame ORB's 31-px border filter keeps plus the
+        # 4-px ring of its NMS neighbours' segment tests (+ small candidate list); 1 065 395 of 1 444 097 pyramid pixels
+        "fast_kernel": n_images * sum((w - 54) * (h - 54) for w, h in lv),
         "blur_kernel": n_images * 2 * tot,                  # read + write every pyramid pixel
         "harris_select_kernel": n_images * (2 * n_kp * (81 + 8) + n_kp * 8),   # 9x9 patch per candidate + lists
         "describe_kernel": n_images * n_kp * (749 + 512 + 28 + 32),            # IC disc + 512 samples + outputs
@@ -503,6 +505,7 @@ def run_ours(args, rank, world, local_rank):
                           "note": "pipe utilisation (% of peak, sustained active) of the dominant kernel in that capture"},
             "algorithmic_bytes_per_launch": alg.get(top, 0.0),
             "kernel_time_share": {k: round(v / tot_k, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
+            "kernel_ms_per_step": {k: round(v[0] / min(args.steps, 5), 4) for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])},
             "note": "per-kernel CUDA-event times measured live in this run, right after the timed region, with every launch "
                     "alone on the stream (the timed region interleaves two half-batches on two streams); "
                     "see DESIGN.md §4 for the bytes"}

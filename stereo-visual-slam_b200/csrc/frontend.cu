@@ -19,6 +19,8 @@ struct FrontState {
     // host-buffer staging for vslam_stereo_frontend_batch / vslam_triangulate
     uint8_t* d_img;  // [2 * pairs][h][pitch] left images first, then right
     int pitch;
+    uint8_t* d_raw;  // host-buffer batches whose row pitch is not a multiple of 16 land here (1-D DMAs) and are re-pitched
+    size_t raw_cap;  //   into d_img on the device, so that every kernel reads level 0 with aligned 128-bit loads
     vslam_keypoint* d_kp;
     uint8_t* d_desc;
     int32_t* d_nkp;
@@ -160,6 +162,23 @@ triangulate_points_kernel(const float* __restrict__ xl, const float* __restrict_
     triangulate_one(xl[2 * i], xl[2 * i + 1], xr[2 * i], xr[2 * i + 1], cam.p, cam.p + 12, pose, xyz + 3 * i, flags + i);
 }
 
+// Copy n_img images of w x h bytes from an arbitrary row pitch to a 16-byte aligned one: 16 output bytes per thread
+// from five aligned source words.  HBM-trivial (2 x 467 KB per image) next to the 2-D DMA it replaces.
+__global__ void __launch_bounds__(128)
+repitch_kernel(const uint8_t* __restrict__ src, int spitch, long long sstride, uint8_t* __restrict__ dst, int dpitch,
+               long long dstride) {
+    const int x = (blockIdx.x * 128 + threadIdx.x) * 16;
+    if (x >= dpitch) return;
+    const uint8_t* p = src + blockIdx.z * sstride + (long long)blockIdx.y * spitch + x;
+    const uint32_t a = (uint32_t)(uintptr_t)p & 3u;
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p - a);
+    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3), w4 = a ? __ldg(q + 4) : 0u;
+    const uint32_t sh = 8 * a;
+    *reinterpret_cast<uint4*>(dst + blockIdx.z * dstride + (long long)blockIdx.y * dpitch + x) =
+        make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                   __funnelshift_r(w3, w4, sh));
+}
+
 int vslam_front_init(vslam_ctx* ctx) {
     FrontState* f = (FrontState*)calloc(1, sizeof(FrontState));
     if (!f) return VSLAM_E_INVALID;
@@ -197,6 +216,7 @@ void vslam_front_free(vslam_ctx* ctx) {
     FrontState* f = ctx->front;
     if (!f) return;
     cudaFree(f->d_img);
+    cudaFree(f->d_raw);
     cudaFree(f->d_kp);
     cudaFree(f->d_desc);
     cudaFree(f->d_nkp);
@@ -369,10 +389,27 @@ extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, 
     // 1241-byte rows (the kernels read bytes, so the pitch need not be aligned)
     static const bool align_env = getenv("VSLAM_FRONT_ALIGN") != nullptr;  // experiment: always stage into 16-byte aligned rows
     const bool contiguous = image_stride == (long long)row_pitch * height && row_pitch <= f->pitch && !(align_env && (row_pitch & 15));
-    const int dpitch = contiguous ? row_pitch : f->pitch;
+    // an unaligned pitch (1241-byte KITTI rows) still goes up as 1-D DMAs, into d_raw, and a device kernel re-pitches
+    // each chunk into d_img: level 0 then takes the aligned 128-bit paths of the FAST / blur / resize kernels
+    static const bool no_repitch = getenv("VSLAM_FRONT_NO_REPITCH") != nullptr;
+    const bool repitch = contiguous && (row_pitch & 15) && !no_repitch;
+    if (repitch) {
+        const size_t need = 2 * (size_t)n_pairs * image_stride + 64;  // + slack for the last aligned window
+        if (need > f->raw_cap) {
+            VSLAM_CUDA(ctx, cudaStreamSynchronize(s));
+            cudaFree(f->d_raw);
+            f->d_raw = nullptr;
+            f->raw_cap = 0;
+            VSLAM_CUDA(ctx, cudaMalloc(&f->d_raw, need));
+            f->raw_cap = need;
+        }
+    }
+    const int dpitch = contiguous && !repitch ? row_pitch : f->pitch;
     const size_t dstride = (size_t)dpitch * height;
     uint8_t* dl = f->d_img;
     uint8_t* dr = f->d_img + (size_t)n_pairs * dstride;
+    uint8_t* rawl = f->d_raw;
+    uint8_t* rawr = f->d_raw + (size_t)n_pairs * image_stride;
     const size_t cap = (size_t)f->kp_cap, np = (size_t)n_pairs;
     // chunk schedule: equal chunks.  Every chunk costs ~0.35 ms of launch tails on top of ~48 us per pair (measured with
     // VSLAM_FRONT_TRACE=1), so ramping the pipeline up with small chunks loses more than the exposed first upload costs.
@@ -400,7 +437,12 @@ extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, 
     if (T_c_w) VSLAM_CUDA(ctx, cudaMemcpyAsync(f->d_pose, T_c_w, np * 96, cudaMemcpyHostToDevice, f->s_in));
     for (int c = 0; c < n_chunks; ++c) {  // all uploads are queued up front; they run back to back on the H2D engine
         const int p0 = c_start[c], nc = c_start[c + 1] - p0;
-        if (contiguous) {
+        if (repitch) {
+            VSLAM_CUDA(ctx, cudaMemcpyAsync(rawl + (size_t)p0 * image_stride, left + (size_t)p0 * image_stride,
+                                            (size_t)image_stride * nc, cudaMemcpyHostToDevice, f->s_in));
+            VSLAM_CUDA(ctx, cudaMemcpyAsync(rawr + (size_t)p0 * image_stride, right + (size_t)p0 * image_stride,
+                                            (size_t)image_stride * nc, cudaMemcpyHostToDevice, f->s_in));
+        } else if (contiguous) {
             VSLAM_CUDA(ctx, cudaMemcpyAsync(dl + p0 * dstride, left + (size_t)p0 * image_stride, dstride * nc,
                                             cudaMemcpyHostToDevice, f->s_in));
             VSLAM_CUDA(ctx, cudaMemcpyAsync(dr + p0 * dstride, right + (size_t)p0 * image_stride, dstride * nc,
@@ -426,6 +468,14 @@ extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, 
         cudaStream_t sc = alt ? f->s_alt : s;
         VSLAM_CUDA(ctx, cudaStreamWaitEvent(sc, f->ev_in[c], 0));
         ctx->stream = sc;  // every enqueue below launches on the context's current stream
+        if (repitch) {
+            const dim3 grid(ceil_div(dpitch, 128 * 16), height, nc);
+            repitch_kernel<<<grid, 128, 0, sc>>>(rawl + (size_t)p0 * image_stride, row_pitch, image_stride, dl + p0 * dstride,
+                                                 dpitch, (long long)dstride);
+            repitch_kernel<<<grid, 128, 0, sc>>>(rawr + (size_t)p0 * image_stride, row_pitch, image_stride, dr + p0 * dstride,
+                                                 dpitch, (long long)dstride);
+            VSLAM_LAUNCH_CHECK(ctx, "repitch_kernel");
+        }
         int st = front_enqueue_chunk(ctx, dl + p0 * dstride, dr + p0 * dstride, n_pairs, p0, nc, width, height, dpitch,
                                      (long long)dstride, nfeatures, anms_keep, anms_c, gate_rel, gate_abs, P1, P2,
                                      T_c_w ? f->d_pose : nullptr, f->d_kp, f->d_desc, f->d_nkp, f->d_match,

@@ -31,6 +31,9 @@
 #define HS_THREADS 1024
 #define DESC_WARPS 4
 #define DESC_KPW 8  // keypoints per warp (power of two <= 32)
+#ifndef DESC_MIN_CTAS
+#define DESC_MIN_CTAS 8
+#endif
 
 struct OrbLevel {
     int w, h, pitch;
@@ -898,7 +901,7 @@ __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9
 // One warp describes DESC_KPW keypoints: the intensity-centroid sums and the 256 tests of each keypoint are spread
 // over the 32 lanes, while the per-keypoint scalar work (fastAtan2, the double-precision cos/sin OpenCV uses, the
 // keypoint record) is done once with lane i owning keypoint i instead of 32 times redundantly.
-__global__ void __launch_bounds__(DESC_WARPS * 32)
+__global__ void __launch_bounds__(DESC_WARPS * 32, DESC_MIN_CTAS)
 describe_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur, const __grid_constant__ OrbGeom g,
                 const uint2* __restrict__ sel, ImgCounters* __restrict__ cnt, const uint32_t* __restrict__ keep,
                 int use_keep, const float* __restrict__ pattern, int kp_cap, vslam_keypoint* __restrict__ kp_out,
@@ -936,6 +939,7 @@ describe_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const uint8_t* __re
     const int u = lane - 15;
     const int au = abs(u);
     int my_m10 = 0, my_m01 = 0;
+#pragma unroll 2
     for (int i = 0; i < nk; ++i) {
         const int x = __shfl_sync(0xFFFFFFFFu, my_x, i), y = __shfl_sync(0xFFFFFFFFu, my_y, i);
         const int l = __shfl_sync(0xFFFFFFFFu, my_l, i);
@@ -984,6 +988,7 @@ describe_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const uint8_t* __re
     float4 pt[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) pt[t] = __ldg(&pat[t]);  // (x0, y0, x1, y1) of test 8*lane + t
+#pragma unroll 2
     for (int i = 0; i < nk; ++i) {
         const float a = __shfl_sync(0xFFFFFFFFu, my_a, i), b = __shfl_sync(0xFFFFFFFFu, my_b, i);
         const int cx = __shfl_sync(0xFFFFFFFFu, my_cx, i), cy = __shfl_sync(0xFFFFFFFFu, my_cy, i);
