@@ -223,7 +223,7 @@ fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__
             ImgCounters* __restrict__ cnt, uint32_t* __restrict__ sticky) {
     __shared__ __align__(16) uint32_t s_img[FI_ROWS * FI_WORDS];
     __shared__ uint32_t s_sc[FS_ROWS * FS_WORDS];
-    __shared__ uint16_t s_list[FAST_WARPS][FAST_RPW * 32];
+    __shared__ uint16_t s_list[FAST_WARPS][2][FAST_RPW * 32];
     __shared__ uint2 s_out[FAST_OUT_CAP];
     __shared__ uint32_t s_hist[256];
     __shared__ int s_nout, s_base;
@@ -291,9 +291,13 @@ fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__
     __syncthreads();
 
     // ---- phase 1: compass pre-test on pixel pairs (any 9-arc contains two adjacent compass pixels) ---------------
+    // The brighter and the darker half are tested separately: a pixel whose brighter (darker) pre-test fails has a
+    // brighter- (darker-) arc score <= FAST_T, which the final max with FAST_T hides -- so each half of the score
+    // network only runs where its own pre-test passed (a pixel can never be a corner both ways).
     const uint32_t* ctr = &s_img[3 * FI_WORDS + shift + 2 + lane];  // centre word of score pair (row 0, lane)
-    uint16_t* list = s_list[wid];
-    int n1 = 0;
+    uint16_t* listb = s_list[wid][0];
+    uint16_t* listd = s_list[wid][1];
+    int nb = 0, nd = 0;
 #pragma unroll
     for (int k = 0; k < FAST_RPW; ++k) {
         const int r = wid + k * FAST_WARPS;
@@ -306,69 +310,79 @@ fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__
                                      __vmins2(d12, d0));
         const uint32_t md = __vmins2(__vimin3_s16x2(__vmaxs2(d0, d4), __vmaxs2(d4, d8), __vmaxs2(d8, d12)),
                                      __vmaxs2(d12, d0));
-        const bool pass = pair_live & (r < n_srow) & any_lane_gt_t(__vmaxs2(__vsub2(mb, cv), __vsub2(cv, md)));
-        if (!pass) s_sc[r * FS_WORDS + lane] = FAST_TT;
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, pass);
-        if (pass) list[n1 + __popc(bal & ((1u << lane) - 1))] = (uint16_t)(r * FS_WORDS + lane);
-        n1 += __popc(bal);
+        const bool live = pair_live & (r < n_srow);
+        const bool pb = live & any_lane_gt_t(__vsub2(mb, cv)), pd = live & any_lane_gt_t(__vsub2(cv, md));
+        s_sc[r * FS_WORDS + lane] = FAST_TT;
+        const uint32_t balb = __ballot_sync(0xFFFFFFFFu, pb), bald = __ballot_sync(0xFFFFFFFFu, pd);
+        const uint32_t lt = (1u << lane) - 1;
+        if (pb) listb[nb + __popc(balb & lt)] = (uint16_t)(r * FS_WORDS + lane);
+        if (pd) listd[nd + __popc(bald & lt)] = (uint16_t)(r * FS_WORDS + lane);
+        nb += __popc(balb);
+        nd += __popc(bald);
     }
     __syncwarp();
 
     // ---- phase 2: full segment test + corner score on the surviving pairs ----------------------------------------
-    // score = max over the 16 arcs of max(min(d), -max(d)), d = centre - ring (sign-symmetric, so ring - centre is
-    // used); a pixel is a corner iff that exceeds FAST_T.
-    for (int e = lane; e < n1; e += 32) {
-        const int p = list[e];
-        const uint32_t* c = &s_img[3 * FI_WORDS + shift + 2] + (p >> 5) * FI_WORDS + (p & 31);
-        const uint32_t nv = neg16x2(c[0]);
-        uint32_t d[16];
-        {
-            const uint32_t* q = c + 3 * FI_WORDS;
-            const uint32_t a = q[-1], b = q[0], cc = q[1];
-            d[15] = mid16x2(a, b); d[0] = b; d[1] = mid16x2(b, cc);
-        }
-        {
-            const uint32_t* q = c - 3 * FI_WORDS;
-            const uint32_t a = q[-1], b = q[0], cc = q[1];
-            d[9] = mid16x2(a, b); d[8] = b; d[7] = mid16x2(b, cc);
-        }
-        d[14] = c[2 * FI_WORDS - 1]; d[2] = c[2 * FI_WORDS + 1];
-        d[10] = c[-2 * FI_WORDS - 1]; d[6] = c[-2 * FI_WORDS + 1];
-        {
-            const uint32_t* q = c + FI_WORDS;
-            d[13] = mid16x2(q[-2], q[-1]); d[3] = mid16x2(q[1], q[2]);
-        }
-        {
-            const uint32_t* q = c - FI_WORDS;
-            d[11] = mid16x2(q[-2], q[-1]); d[5] = mid16x2(q[1], q[2]);
-        }
-        d[12] = mid16x2(c[-2], c[-1]); d[4] = mid16x2(c[1], c[2]);
-        // The network runs on the RAW ring values: min / max commute with subtracting the centre, so
-        //   max_k min9_k(ring - c) = max_k min9_k(ring) - c   and   min_k max9_k(ring - c) = min_k max9_k(ring) - c,
-        // and a 9-window is three 3-windows: m3[k] = op3(d[k], d[k+1], d[k+2]), m9[k] = op3(m3[k], m3[k+3], m3[k+6])
-        // -- 32 three-input instructions per direction instead of 16 subtractions + 48.
-        uint32_t mn3[16], mx3[16];
+    // score = max over the 16 arcs of max(min(d), -max(d)), d = ring - centre; a pixel is a corner iff that exceeds
+    // FAST_T.  The network runs on the RAW ring values: min / max commute with subtracting the centre, so
+    //   max_k min9_k(ring - c) = max_k min9_k(ring) - c   and   min_k max9_k(ring - c) = min_k max9_k(ring) - c,
+    // and a 9-window is three 3-windows: m3[k] = op3(d[k], d[k+1], d[k+2]), m9[k] = op3(m3[k], m3[k+3], m3[k+6])
+    // -- 32 three-input instructions per direction instead of 16 subtractions + 48.
+    // h = max(score, FAST_T): every pixel scored here has its whole ring inside the image.
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            mn3[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-            mx3[k] = __vimax3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-        }
-        uint32_t a[16], b[16];
+    for (int half = 0; half < 2; ++half) {
+        const uint16_t* list = half ? listd : listb;
+        const int n1 = half ? nd : nb;
+        for (int e = lane; e < n1; e += 32) {
+            const int p = list[e];
+            const uint32_t* c = &s_img[3 * FI_WORDS + shift + 2] + (p >> 5) * FI_WORDS + (p & 31);
+            const uint32_t cv = c[0];
+            uint32_t d[16];
+            {
+                const uint32_t* q = c + 3 * FI_WORDS;
+                const uint32_t a = q[-1], b = q[0], cc = q[1];
+                d[15] = mid16x2(a, b); d[0] = b; d[1] = mid16x2(b, cc);
+            }
+            {
+                const uint32_t* q = c - 3 * FI_WORDS;
+                const uint32_t a = q[-1], b = q[0], cc = q[1];
+                d[9] = mid16x2(a, b); d[8] = b; d[7] = mid16x2(b, cc);
+            }
+            d[14] = c[2 * FI_WORDS - 1]; d[2] = c[2 * FI_WORDS + 1];
+            d[10] = c[-2 * FI_WORDS - 1]; d[6] = c[-2 * FI_WORDS + 1];
+            {
+                const uint32_t* q = c + FI_WORDS;
+                d[13] = mid16x2(q[-2], q[-1]); d[3] = mid16x2(q[1], q[2]);
+            }
+            {
+                const uint32_t* q = c - FI_WORDS;
+                d[11] = mid16x2(q[-2], q[-1]); d[5] = mid16x2(q[1], q[2]);
+            }
+            d[12] = mid16x2(c[-2], c[-1]); d[4] = mid16x2(c[1], c[2]);
+            uint32_t m3[16], m9[16];
+            if (half == 0) {  // brightest arc: max over the arcs of the arc minimum
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            a[k] = __vimin3_s16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
-            b[k] = __vimax3_s16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
-        }
-        uint32_t besta = __vimax3_s16x2(a[0], a[1], a[2]), bmin = __vimin3_s16x2(b[0], b[1], b[2]);
+                for (int k = 0; k < 16; ++k) m3[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
 #pragma unroll
-        for (int k = 3; k < 15; k += 2) {
-            besta = __vimax3_s16x2(besta, a[k], a[k + 1]);
-            bmin = __vimin3_s16x2(bmin, b[k], b[k + 1]);
+                for (int k = 0; k < 16; ++k) m9[k] = __vimin3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+                uint32_t best = __vimax3_s16x2(m9[0], m9[1], m9[2]);
+#pragma unroll
+                for (int k = 3; k < 15; k += 2) best = __vimax3_s16x2(best, m9[k], m9[k + 1]);
+                best = __vsub2(__vmaxs2(best, m9[15]), cv);
+                s_sc[p] = __vmaxs2(best, FAST_TT);  // phase 1 left FAST_T here
+            } else {          // darkest arc: min over the arcs of the arc maximum
+#pragma unroll
+                for (int k = 0; k < 16; ++k) m3[k] = __vimax3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) m9[k] = __vimax3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+                uint32_t best = __vimin3_s16x2(m9[0], m9[1], m9[2]);
+#pragma unroll
+                for (int k = 3; k < 15; k += 2) best = __vimin3_s16x2(best, m9[k], m9[k + 1]);
+                best = __vsub2(cv, __vmins2(best, m9[15]));
+                s_sc[p] = __vmaxs2(best, s_sc[p]);  // on top of the brighter half's result (>= FAST_T)
+            }
         }
-        besta = __vadd2(__vmaxs2(besta, a[15]), nv);  // brightest arc minus the centre
-        bmin = __vadd2(__vmins2(bmin, b[15]), nv);    // darkest arc minus the centre
-        // h = max(score, FAST_T): every pixel scored here has its whole ring inside the image
-        s_sc[p] = __vimax3_s16x2(besta, neg16x2(bmin), FAST_TT);
+        __syncwarp();
     }
     __syncthreads();
 
