@@ -4,6 +4,9 @@
 #include <stereo_visual_slam_main/optimization.hpp>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <vector>
 #include <stdexcept>
@@ -73,8 +76,11 @@ void run(std::unordered_map<unsigned long, Frame>& keyframes, std::unordered_map
          const cv::Mat& K, bool pose_only, bool if_update_map, bool if_update_landmark, int num_ite) {
     vslam_ctx* g_opt_ctx = optimization_context();
     if (!g_opt_ctx) throw std::runtime_error("vslam::optimize_*: no library context (set_optimization_context)");
+    static const bool trace = std::getenv("VSLAM_VO_TRACE") != nullptr;  // per-stage wall clock on stderr
+    const auto t0 = std::chrono::steady_clock::now();
     Graph g = build_graph(keyframes, landmarks, !pose_only);
     if (g.kf_ids.empty()) return;
+    const auto t1 = std::chrono::steady_clock::now();
     double Kc[9];
     for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) Kc[r * 3 + c] = K.at<double>(r, c);
@@ -92,6 +98,7 @@ void run(std::unordered_map<unsigned long, Frame>& keyframes, std::unordered_map
                                      g.points.data(), (int)g.obs_pose.size(), g.obs_pose.data(), g.obs_point.data(),
                                      g.uv.data(), Kc, &opt, &res, nullptr, inlier.data());
     if (st != VSLAM_OK) throw std::runtime_error(std::string("vslam_ba_optimize: ") + vslam_status_string(st));
+    const auto t2 = std::chrono::steady_clock::now();
 
     // relabel: every landmark that contributed an edge gets the verdict of its last edge (optimization.cpp:254-266)
     for (size_t i = 0; i < g.lm_ids.size(); ++i) landmarks.at(g.lm_ids[i]).is_inlier = inlier[i] != 0;
@@ -107,6 +114,13 @@ void run(std::unordered_map<unsigned long, Frame>& keyframes, std::unordered_map
         if (if_update_landmark && !pose_only)
             for (size_t i = 0; i < g.lm_ids.size(); ++i)
                 landmarks.at(g.lm_ids[i]).pt_3d_ = cv::Point3f((float)g.points[3 * i], (float)g.points[3 * i + 1], (float)g.points[3 * i + 2]);
+    }
+    if (trace) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        std::fprintf(stderr, "[ba] %s K %zu L %zu obs %zu: graph %.3f optimize %.3f (%d iterations, %d trials) write-back %.3f ms\n",
+                     pose_only ? "pose-only" : "map", g.kf_ids.size(), g.lm_ids.size(), g.obs_pose.size(), ms(t0, t1), ms(t1, t2),
+                     res.iterations, res.trials, ms(t2, t3));
     }
 }
 
