@@ -175,3 +175,45 @@ def test_two_stream_chunking_equals_single_stream(pkg):
     finally:
         ctx.set_concurrency(True)
         ctx.close()
+
+
+def test_repitched_ramped_host_batch_equals_device_path_on_unaligned_rows(pkg):
+    """136 pairs with 641-byte rows through the host-buffer call -- re-pitched to 16-byte rows on the device
+    (repitch_kernel) and cut into ramped chunks (16 + 32 + 32 + 32 + 24 pairs) -- against the device-resident call on the
+    same images at their unaligned pitch (byte-load paths of the FAST / blur kernels): bit-identical results."""
+    import torch
+    n, nfeat, h, w = 136, 300, 200, 641
+    ctx = pkg.Context(device=0, max_images=2 * n, max_width=w, max_height=h, max_keypoints=384)
+    try:
+        P1, P2 = _cams(pkg)
+        base = [pkg.synth.synth_pair(200 + i) for i in range(6)]
+        L = np.stack([np.ascontiguousarray(base[i % 6][0][40:40 + h, 30 + i:30 + i + w]) for i in range(n)])
+        Rr = np.stack([np.ascontiguousarray(base[i % 6][1][40:40 + h, 30 + i:30 + i + w]) for i in range(n)])
+        a = ctx.stereo_frontend(L, Rr, P1, P2, nfeatures=nfeat)
+        a = {k: np.array(v, copy=True) for k, v in a.items() if isinstance(v, np.ndarray)}
+        assert a["n_kp"].min() > 100 and a["n_matches"].min() > 5
+        dev = torch.device("cuda:0")
+        dl, dr = torch.from_numpy(L).to(dev), torch.from_numpy(Rr).to(dev)
+        cap = ctx.kp_cap
+        d_kp = torch.zeros((2 * n, cap, 7), dtype=torch.int32, device=dev)
+        d_desc = torch.zeros((2 * n, cap, 32), dtype=torch.uint8, device=dev)
+        d_nkp = torch.zeros(2 * n, dtype=torch.int32, device=dev)
+        d_m = torch.zeros((n, cap, 4), dtype=torch.int32, device=dev)
+        d_nm = torch.zeros(n, dtype=torch.int32, device=dev)
+        d_xyz = torch.zeros((n, cap, 3), dtype=torch.float32, device=dev)
+        d_fl = torch.zeros((n, cap), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        ctx.stereo_frontend_dev(dl, dr, n, w, h, w, w * h, P1, P2, None, d_kp, d_desc, d_nkp, d_m, d_nm, d_xyz, d_fl,
+                                nfeatures=nfeat)
+        ctx.synchronize()
+        nkp, nm = d_nkp.cpu().numpy(), d_nm.cpu().numpy()
+        assert np.array_equal(nkp, a["n_kp"]) and np.array_equal(nm, a["n_matches"])
+        kp, desc, m, xyz = d_kp.cpu().numpy(), d_desc.cpu().numpy(), d_m.cpu().numpy(), d_xyz.cpu().numpy()
+        for i in range(2 * n):
+            k = nkp[i]
+            assert a["kp"][i, :k].tobytes() == kp[i, :k].tobytes() and np.array_equal(a["desc"][i, :k], desc[i, :k])
+        for i in range(n):
+            assert a["matches"][i, :nm[i]].tobytes() == m[i, :nm[i]].tobytes()
+            assert np.array_equal(a["xyz"][i, :nm[i]], xyz[i, :nm[i]])
+    finally:
+        ctx.close()
