@@ -474,6 +474,37 @@ def run_ours(args, rank, world, local_rank):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(t.item())
+    # the same through the streaming form of the call: two contexts alternate, so two batches are in flight and the first
+    # upload / last download of one batch hide behind the other's kernels (every step still uploads its 2 x B images
+    # from pinned host memory and downloads all its results inside the timed region)
+    e2e_stream_value = None
+    try:
+        ctx_b = pkg.Context(device=local_rank, max_images=2 * B, max_keypoints=cap, max_ba_poses=0, max_ba_points=0, max_ba_obs=0)
+        out_b = ctx_b.alloc_frontend_outputs(B)
+        for k, v in list(out_b.items()):
+            tt = torch.from_numpy(v.view(np.uint8).reshape(-1)).pin_memory()
+            keep_alive.append(tt)
+            out_b[k] = tt.numpy().view(v.dtype).reshape(v.shape)
+        cs, outs = (ctx, ctx_b), (out, out_b)
+        def stream_run(n):
+            cs[0].stereo_frontend_begin(sets[0][0], sets[0][1], P1, P2, outs[0], nfeatures=NFEAT)
+            for i in range(1, n):
+                cs[i & 1].stereo_frontend_begin(sets[i & 1][0], sets[i & 1][1], P1, P2, outs[i & 1], nfeatures=NFEAT)
+                cs[(i - 1) & 1].stereo_frontend_end()
+            cs[(n - 1) & 1].stereo_frontend_end()
+        stream_run(2)
+        barrier()
+        t0 = time.perf_counter()
+        stream_run(args.steps)
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_stream_value = world * B * args.steps / float(t.item())
+        ctx_b.close()
+    except Exception as ex:
+        e2e_stream_value = None
+        sys.stderr.write(f"[bench] streaming e2e leg failed: {ex!r}\n")
     # configs[1] read literally: ONE stereo pair per call through the host-buffer C-ABI (latency, not throughput)
     out1 = ctx.alloc_frontend_outputs(1)
     l1, r1 = sets[0][0][:1], sets[0][1][:1]
@@ -609,7 +640,11 @@ def run_ours(args, rank, world, local_rank):
                              "set (inputs+pyramids+blurred) ~%.0f MB > 126 MB L2" % (2 * B * 3.7),
                        "mean_keypoints_per_image": n_kp_mean, "mean_matches_per_pair": n_m_mean,
                        "parallelism": f"frames sharded over {world} GPU(s), no data-path collective"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": max(e2e_value, e2e_stream_value or 0.0), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h,
+                    "mode": ("vslam_stereo_frontend_batch_begin/_end, two contexts alternating = two batches in flight"
+                             if (e2e_stream_value or 0.0) > e2e_value else "vslam_stereo_frontend_batch, one call at a time"),
+                    "one_call_at_a_time": e2e_value, "two_batches_in_flight": e2e_stream_value,
                     "matches_per_step": matches_e2e, "usable_points_per_step": usable,
                     "single_pair_latency_ms": single_pair_ms},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof,

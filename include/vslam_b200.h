@@ -186,6 +186,17 @@ int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, const uint8
                                 float anms_c, double gate_rel, double gate_abs, const double* P1, const double* P2,
                                 const double* T_c_w, vslam_keypoint* kp, uint8_t* desc, int32_t* n_kp,
                                 vslam_dmatch* matches, int32_t* n_matches, float* xyz, uint8_t* flags);
+/* The host-buffer call in two halves: _begin enqueues uploads, kernels and downloads of the batch and returns, _end
+ * waits and returns VSLAM_OK / VSLAM_E_OVERFLOW.  One batch per context at a time; inputs and outputs must stay valid
+ * (and be pinned for the copies to be asynchronous) until _end.  Two contexts alternating keep two batches in flight
+ * -- the streaming form of the reference's frame loop (run_vslam.cpp:44-75 reads, processes and stores one frame after
+ * the other). */
+int vslam_stereo_frontend_batch_begin(vslam_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_pairs, int width,
+                                      int height, int row_pitch, long long image_stride, int nfeatures, int anms_keep,
+                                      float anms_c, double gate_rel, double gate_abs, const double* P1, const double* P2,
+                                      const double* T_c_w, vslam_keypoint* kp, uint8_t* desc, int32_t* n_kp,
+                                      vslam_dmatch* matches, int32_t* n_matches, float* xyz, uint8_t* flags);
+int vslam_stereo_frontend_batch_end(vslam_ctx* ctx);
 int vslam_stereo_frontend_batch_dev(vslam_ctx* ctx, const uint8_t* d_left, const uint8_t* d_right, int n_pairs,
                                     int width, int height, int row_pitch, long long image_stride, int nfeatures,
                                     int anms_keep, float anms_c, double gate_rel, double gate_abs, const double* P1,

@@ -38,6 +38,9 @@ struct FrontState {
     cudaStream_t s_alt;  // second compute stream: odd chunks run here so that one chunk's launch tails overlap the next
     cudaEvent_t ev_join;
     cudaEvent_t ev_in[FRONT_MAX_CHUNKS], ev_done[FRONT_MAX_CHUNKS], ev_start;
+    // a batch enqueued by vslam_stereo_frontend_batch_begin and not yet collected by _end
+    int inflight_pairs, inflight_chunks;
+    int inflight_c_start[FRONT_MAX_CHUNKS + 1];
 };
 
 struct Cam24 {
@@ -369,14 +372,20 @@ extern "C" int vslam_stereo_frontend_batch_dev(vslam_ctx* ctx, const uint8_t* d_
 // copies asynchronous DMA), results are copied back, one synchronisation at the end.  Outputs use the same strides as
 // the device form (cap = vslam_orb_keypoint_capacity(ctx)): kp [2*n_pairs][cap], desc [2*n_pairs][cap][32],
 // n_kp [2*n_pairs], matches [n_pairs][cap], n_matches [n_pairs], xyz [n_pairs][cap][3], flags [n_pairs][cap].
-extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_pairs,
-                                           int width, int height, int row_pitch, long long image_stride, int nfeatures,
-                                           int anms_keep, float anms_c, double gate_rel, double gate_abs,
-                                           const double* P1, const double* P2, const double* T_c_w,
-                                           vslam_keypoint* kp, uint8_t* desc, int32_t* n_kp, vslam_dmatch* matches,
-                                           int32_t* n_matches, float* xyz, uint8_t* flags) {
+//
+// _begin enqueues the whole batch (uploads, kernels, downloads) and returns; _end waits for it and reports the overflow
+// flags.  A caller that alternates two contexts keeps two batches in flight: the first upload and the last download of
+// one batch hide behind the other batch's kernels (bench.py's e2e loop; inputs and outputs must stay valid, and pinned
+// for the copies to be asynchronous, until _end).  vslam_stereo_frontend_batch = _begin + _end.
+extern "C" int vslam_stereo_frontend_batch_begin(vslam_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_pairs,
+                                                 int width, int height, int row_pitch, long long image_stride,
+                                                 int nfeatures, int anms_keep, float anms_c, double gate_rel,
+                                                 double gate_abs, const double* P1, const double* P2, const double* T_c_w,
+                                                 vslam_keypoint* kp, uint8_t* desc, int32_t* n_kp, vslam_dmatch* matches,
+                                                 int32_t* n_matches, float* xyz, uint8_t* flags) {
     VslamDeviceGuard device_guard__(ctx);
     if (!ctx || !n_kp || !n_matches) return VSLAM_E_INVALID;
+    if (ctx->front && ctx->front->inflight_pairs > 0) return VSLAM_E_INVALID;  // one batch per context at a time
     if (!left || !right) return VSLAM_E_INVALID;  // reference: -1 "Could not open or find the image"
     if (!P1 || !P2 || !kp || !desc || !matches || !xyz || !flags) return VSLAM_E_INVALID;
     FrontState* f = ctx->front;
@@ -512,6 +521,19 @@ extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, 
         VSLAM_CUDA(ctx, cudaEventRecord(f->ev_join, f->s_alt));
         VSLAM_CUDA(ctx, cudaStreamWaitEvent(s, f->ev_join, 0));
     }
+    f->inflight_pairs = n_pairs;
+    f->inflight_chunks = n_chunks;
+    memcpy(f->inflight_c_start, c_start, sizeof(int) * (n_chunks + 1));
+    return VSLAM_OK;
+}
+
+extern "C" int vslam_stereo_frontend_batch_end(vslam_ctx* ctx) {
+    VslamDeviceGuard device_guard__(ctx);
+    if (!ctx || !ctx->front || ctx->front->inflight_pairs <= 0) return VSLAM_E_INVALID;
+    FrontState* f = ctx->front;
+    const int n_pairs = f->inflight_pairs, n_chunks = f->inflight_chunks;
+    const int* c_start = f->inflight_c_start;
+    f->inflight_pairs = 0;
     const int st = vslam_orb_check_flags(ctx, 2 * n_pairs);  // synchronises the context stream
     VSLAM_CUDA(ctx, cudaStreamSynchronize(f->s_out));
     if (getenv("VSLAM_FRONT_TRACE")) {  // pipeline trace: when each chunk's upload and kernels finished, ms after the call began
@@ -523,4 +545,17 @@ extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, 
         }
     }
     return st;  // VSLAM_E_OVERFLOW if a work list overflowed
+}
+
+extern "C" int vslam_stereo_frontend_batch(vslam_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_pairs,
+                                           int width, int height, int row_pitch, long long image_stride, int nfeatures,
+                                           int anms_keep, float anms_c, double gate_rel, double gate_abs,
+                                           const double* P1, const double* P2, const double* T_c_w,
+                                           vslam_keypoint* kp, uint8_t* desc, int32_t* n_kp, vslam_dmatch* matches,
+                                           int32_t* n_matches, float* xyz, uint8_t* flags) {
+    const int st = vslam_stereo_frontend_batch_begin(ctx, left, right, n_pairs, width, height, row_pitch, image_stride,
+                                                     nfeatures, anms_keep, anms_c, gate_rel, gate_abs, P1, P2, T_c_w, kp,
+                                                     desc, n_kp, matches, n_matches, xyz, flags);
+    if (st != VSLAM_OK) return st;
+    return vslam_stereo_frontend_batch_end(ctx);
 }

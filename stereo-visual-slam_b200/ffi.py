@@ -84,6 +84,9 @@ SIGNATURES = {
     "vslam_triangulate_matches_batch_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "vslam_stereo_frontend_batch": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_longlong, _i, _i, _f, _d, _d, _vp, _vp, _vp,
                                          _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vslam_stereo_frontend_batch_begin": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_longlong, _i, _i, _f, _d, _d, _vp, _vp, _vp,
+                                               _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vslam_stereo_frontend_batch_end": (_i, [_vp]),
     "vslam_stereo_frontend_batch_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_longlong, _i, _i, _f, _d, _d, _vp, _vp,
                                              _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vslam_ba_optimize": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, C.POINTER(BaOptions),
@@ -278,7 +281,7 @@ class Context:
         return xyz[:n], fl[:n]
 
     def stereo_frontend(self, left, right, P1, P2, T_c_w=None, nfeatures=2000, anms_keep=0, anms_c=1.11,
-                        gate_rel=2.0, gate_abs=30.0, out=None):
+                        gate_rel=2.0, gate_abs=30.0, out=None, begin_only=False):
         """Host-buffer batched frontend.  left/right: [B,H,W] u8 numpy arrays or pinned torch tensors.
         Returns a dict of full-stride numpy arrays (see include/vslam_b200.h) plus per-pair views."""
         is_np = isinstance(left, np.ndarray)
@@ -292,12 +295,24 @@ class Context:
         P1 = np.ascontiguousarray(P1, dtype=np.float64).reshape(12)
         P2 = np.ascontiguousarray(P2, dtype=np.float64).reshape(12)
         T = None if T_c_w is None else np.ascontiguousarray(T_c_w, dtype=np.float64).reshape(b, 12)
-        st = self.lib.vslam_stereo_frontend_batch(
+        fn = self.lib.vslam_stereo_frontend_batch_begin if begin_only else self.lib.vslam_stereo_frontend_batch
+        st = fn(
             self.h, _ptr(left), _ptr(right), b, w, h, w, h * w, int(nfeatures), int(anms_keep), float(anms_c),
             float(gate_rel), float(gate_abs), _ptr(P1), _ptr(P2), _ptr(T), _ptr(out["kp"]), _ptr(out["desc"]),
             _ptr(out["n_kp"]), _ptr(out["matches"]), _ptr(out["n_matches"]), _ptr(out["xyz"]), _ptr(out["flags"]))
         self.check(st, "vslam_stereo_frontend_batch")
+        if begin_only:  # the arrays the enqueued copies read must outlive the call
+            self._front_keep = (left, right, P1, P2, T, out)
         return out
+
+    def stereo_frontend_begin(self, left, right, P1, P2, out, **kw):
+        """Enqueue a host-buffer batch and return (vslam_stereo_frontend_batch_begin); `out` (alloc_frontend_outputs,
+        ideally pinned) is filled when stereo_frontend_end() returns.  left/right should be pinned."""
+        return self.stereo_frontend(left, right, P1, P2, out=out, begin_only=True, **kw)
+
+    def stereo_frontend_end(self):
+        self.check(self.lib.vslam_stereo_frontend_batch_end(self.h), "vslam_stereo_frontend_batch_end")
+        self._front_keep = None
 
     def alloc_frontend_outputs(self, n_pairs: int):
         cap = self.kp_cap

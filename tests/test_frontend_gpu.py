@@ -217,3 +217,46 @@ def test_repitched_ramped_host_batch_equals_device_path_on_unaligned_rows(pkg):
             assert np.array_equal(a["xyz"][i, :nm[i]], xyz[i, :nm[i]])
     finally:
         ctx.close()
+
+
+def test_begin_end_on_two_contexts_equals_the_synchronous_call(pkg):
+    """vslam_stereo_frontend_batch_begin / _end with two contexts alternating (two batches in flight) returns what
+    vslam_stereo_frontend_batch returns; a second _begin on a busy context and an _end without a batch are refused."""
+    n, nfeat, h, w = 40, 300, 200, 640
+    P1, P2 = _cams(pkg)
+    base = [pkg.synth.synth_pair(300 + i) for i in range(4)]
+    batches = []
+    for k in range(3):
+        L = np.stack([np.ascontiguousarray(base[(i + k) % 4][0][30:30 + h, 20 + i:20 + i + w]) for i in range(n)])
+        Rr = np.stack([np.ascontiguousarray(base[(i + k) % 4][1][30:30 + h, 20 + i:20 + i + w]) for i in range(n)])
+        batches.append((L, Rr))
+    ctxs = [pkg.Context(device=0, max_images=2 * n, max_width=w, max_height=h, max_keypoints=384) for _ in range(2)]
+    try:
+        ref = []
+        for L, Rr in batches:
+            o = ctxs[0].stereo_frontend(L, Rr, P1, P2, nfeatures=nfeat)
+            ref.append({k: np.array(v, copy=True) for k, v in o.items()})
+        outs = [ctxs[i & 1].alloc_frontend_outputs(n) for i in range(3)]
+        ctxs[0].stereo_frontend_begin(batches[0][0], batches[0][1], P1, P2, outs[0], nfeatures=nfeat)
+        with pytest.raises(pkg.ffi.VslamError):
+            ctxs[0].stereo_frontend_begin(batches[1][0], batches[1][1], P1, P2, outs[1], nfeatures=nfeat)
+        ctxs[1].stereo_frontend_begin(batches[1][0], batches[1][1], P1, P2, outs[1], nfeatures=nfeat)
+        ctxs[0].stereo_frontend_end()
+        ctxs[0].stereo_frontend_begin(batches[2][0], batches[2][1], P1, P2, outs[2], nfeatures=nfeat)
+        ctxs[1].stereo_frontend_end()
+        ctxs[0].stereo_frontend_end()
+        with pytest.raises(pkg.ffi.VslamError):
+            ctxs[0].stereo_frontend_end()
+        for o, r in zip(outs, ref):
+            assert np.array_equal(o["n_kp"], r["n_kp"]) and np.array_equal(o["n_matches"], r["n_matches"])
+            assert r["n_kp"].min() > 100
+            for i in range(2 * n):
+                k = r["n_kp"][i]
+                assert o["kp"][i, :k].tobytes() == r["kp"][i, :k].tobytes() and np.array_equal(o["desc"][i, :k], r["desc"][i, :k])
+            for i in range(n):
+                m = r["n_matches"][i]
+                assert o["matches"][i, :m].tobytes() == r["matches"][i, :m].tobytes()
+                assert np.array_equal(o["xyz"][i, :m], r["xyz"][i, :m]) and np.array_equal(o["flags"][i, :m], r["flags"][i, :m])
+    finally:
+        for c in ctxs:
+            c.close()
