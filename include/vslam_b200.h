@@ -76,6 +76,14 @@ const char* vslam_last_error(const vslam_ctx* ctx);
 
 int vslam_ctx_create(const vslam_config* cfg, vslam_ctx** out);
 void vslam_ctx_destroy(vslam_ctx* ctx);
+
+/* Pinned (page-locked) host memory from a process-wide pool, for the image-sized buffers the reference keeps in
+ * cv::Mat -- the frames cv::imread returns (visual_odometry.cpp:42-51) and the disparity image (:163-168): uploads and
+ * downloads of such buffers are direct DMAs.  Freed blocks are recycled (a fresh cudaHostAlloc per frame would cost
+ * more than it saves).  vslam_host_alloc returns NULL when no CUDA device can pin memory; vslam_host_free ignores
+ * pointers it did not hand out. */
+void* vslam_host_alloc(size_t bytes);
+void vslam_host_free(void* p);
 /* run on a caller-owned stream (a cudaStream_t, e.g. torch's current stream); NULL = context's own */
 int vslam_ctx_set_stream(vslam_ctx* ctx, void* cuda_stream);
 int vslam_ctx_synchronize(vslam_ctx* ctx);

@@ -5,6 +5,47 @@
 
 extern "C" int vslam_abi_version(void) { return VSLAM_ABI_VERSION; }
 
+// ---- pinned host memory pool ------------------------------------------------------------------------------------
+// Image-sized host buffers of the drop-in layer (the cv::Mat behind cv::imread / the disparity image) come from here so
+// that the library's uploads and downloads are plain DMAs instead of copies staged through the driver's bounce buffer.
+// cudaHostAlloc costs far more than it saves per frame, so freed blocks are kept on per-size free lists and handed out
+// again; the pool is process-wide and is left to the OS at exit (the CUDA runtime may already be gone by then).
+#include <map>
+#include <mutex>
+#include <vector>
+static std::mutex g_pool_mu;
+static std::map<size_t, std::vector<void*>> g_pool_free;  // block size -> free blocks
+static std::map<void*, size_t> g_pool_size;              // every block ever allocated -> its size
+
+extern "C" void* vslam_host_alloc(size_t bytes) {
+    const size_t sz = (bytes + 65535) & ~(size_t)65535;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        auto it = g_pool_free.find(sz);
+        if (it != g_pool_free.end() && !it->second.empty()) {
+            void* p = it->second.back();
+            it->second.pop_back();
+            return p;
+        }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, sz, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool_size[p] = sz;
+    return p;
+}
+
+extern "C" void vslam_host_free(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_pool_size.find(p);
+    if (it == g_pool_size.end()) return;  // not ours
+    g_pool_free[it->second].push_back(p);
+}
+
 extern "C" const char* vslam_status_string(int status) {
     switch (status) {
         case VSLAM_OK: return "ok";

@@ -66,6 +66,8 @@ SIGNATURES = {
     "vslam_ctx_create": (_i, [C.POINTER(Config), C.POINTER(_vp)]),
     "vslam_ctx_destroy": (None, [_vp]),
     "vslam_ctx_set_stream": (_i, [_vp, _vp]),
+    "vslam_host_alloc": (_vp, [C.c_size_t]),
+    "vslam_host_free": (None, [_vp]),
     "vslam_ctx_synchronize": (_i, [_vp]),
     "vslam_ctx_set_concurrency": (_i, [_vp, _i]),
     "vslam_ctx_launch_count": (_i64, [_vp]),

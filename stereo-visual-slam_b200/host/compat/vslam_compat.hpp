@@ -213,9 +213,24 @@ public:
         type_ = type;
         rows = r; cols = c;
         step = (size_t)c * elemSize();
-        buf_ = std::shared_ptr<uint8_t>(new uint8_t[std::max<size_t>(step * r, 1)], std::default_delete<uint8_t[]>());
+        const size_t bytes = std::max<size_t>(step * r, 1);
+        // image-sized buffers come from the library's pinned pool when the drop-in layer installed it (VO's
+        // constructor): frames and disparity images then move over PCIe as plain DMAs
+        uint8_t* pinned = (bytes >= kPinnedMin && allocator().alloc) ? static_cast<uint8_t*>(allocator().alloc(bytes)) : nullptr;
+        if (pinned) {
+            void (*fr)(void*) = allocator().free;
+            buf_ = std::shared_ptr<uint8_t>(pinned, [fr](uint8_t* p) { fr(p); });
+        } else {
+            buf_ = std::shared_ptr<uint8_t>(new uint8_t[bytes], std::default_delete<uint8_t[]>());
+        }
         data = buf_.get();
     }
+    struct Allocator {
+        void* (*alloc)(size_t) = nullptr;
+        void (*free)(void*) = nullptr;
+    };
+    static Allocator& allocator() { static Allocator a; return a; }
+    static constexpr size_t kPinnedMin = 256 * 1024;
     int type() const { return type_; }
     size_t elemSize() const { return type_ == CV_8U ? 1 : type_ == CV_32F ? 4 : 8; }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }

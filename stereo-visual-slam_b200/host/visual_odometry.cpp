@@ -39,6 +39,10 @@ void VO::create_context() {
     cfg.max_ba_obs = 262144;
     check(vslam_ctx_create(&cfg, &ctx_), "vslam_ctx_create");  // throws without a B200: there is no CPU path
     set_optimization_context(ctx_);
+    if (!std::getenv("VSLAM_NO_PINNED_MAT")) {  // image-sized cv::Mat buffers from the library's pinned pool
+        cv::Mat::allocator().alloc = vslam_host_alloc;
+        cv::Mat::allocator().free = vslam_host_free;
+    }
     // runtime knobs for callers that cannot reach the members (the reference's unmodified main, run_vslam.cpp:17-92)
     if (const char* e = std::getenv("VSLAM_NFEATURES")) detector_nfeatures_ = std::atoi(e);
     if (const char* e = std::getenv("VSLAM_ANMS_KEEP")) anms_keep_ = std::atoi(e);
