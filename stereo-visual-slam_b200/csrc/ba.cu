@@ -1182,15 +1182,209 @@ __device__ void ba_small_schur(const BaParams& P, double lambda, double* __restr
     }
 }
 
-// Every CTA: M = [S + Hpp + lambda I | bs + bp] into shared memory, blocked Cholesky + both substitutions; x -> xs (shared).
-// Returns false (uniformly over the grid: identical inputs) if the system is not positive definite.
-__device__ bool ba_small_solve(const BaParams& P, const double* S, const double* bs, const double* Hpp, const double* bp,
-                               double lambda, double* M, double* xs) {
+// branch-free reciprocal and reciprocal square root for well-scaled positive doubles (Hessian pivots): hardware seed
+// (about 20 bits) + two Newton steps to full precision.  Unlike 1.0 / d and rsqrt(d) they carry no special-case branch,
+// so independent ones interleave in the instruction stream.
+__device__ __forceinline__ double rcp_pos(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double rsqrt_pos(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double h = 0.5 * d;
+    y = y * fma(-h * y, y, 1.5);
+    return y * fma(-h * y, y, 1.5);
+}
+
+// Root-free factorisation of a 6x6 diagonal block with the square roots OFF the dependency chain: on return D holds the
+// unnormalised rows u'[r][c] (u'[r][r] = d_r), G[p][r] = u'[p][r] / d_p and rs[r] = 1 / sqrt(d_r); the Cholesky factor is
+// U = diag(rs) u'.  The chain per row is one reciprocal, one multiply and one DFMA; the six rs[] are independent of it.
+__device__ __forceinline__ bool ldl6_diag(double* D, double* rs, double* G) {
+    bool ok = true;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const double d = D[r * 6 + r];
+        if (!(d > 0.0) || !isfinite(d)) ok = false;
+        const double inv = rcp_pos(d);
+        rs[r] = rsqrt_pos(d);
+#pragma unroll
+        for (int r2 = 0; r2 < 6; ++r2) {
+            if (r2 > r) {
+                const double g = D[r * 6 + r2] * inv;
+                G[r * 6 + r2] = g;
+#pragma unroll
+                for (int c = 0; c < 6; ++c)
+                    if (c >= r2) D[r2 * 6 + c] -= g * D[r * 6 + c];
+            }
+        }
+    }
+    return ok;
+}
+
+// Every CTA: solve [S + Hpp + lambda I] x = bs + bp by a 6x6-blocked Cholesky factorisation; x -> xs (shared).  Returns
+// false (uniformly over the grid: identical inputs) if the system is not positive definite.
+//
+// Measured with tools/micro/solve_probe2.cu (n = 60: 42.3 k -> 31.7 k cycles stand-alone, profiles/r02_v3_fp64_latency.txt):
+//   * the rank-6 trailing update is SHARED-MEMORY-BANDWIDTH bound when the trailing matrix lives in shared memory (every
+//     element read and written once per block step), so it lives in REGISTERS instead, 2-D cyclic (warp w owns the rows
+//     r = w mod 8, lane l the columns c = l mod 32, SB_A x SB_B entries per thread, loaded straight from global memory);
+//     shared memory only ever holds finished factor rows.  Entries below the diagonal are updated with whatever they
+//     hold and never published: the update carries no per-entry predicates;
+//   * per block step: the six pivot rows are published (each lives in one warp), every thread factors the 6x6 diagonal
+//     block redundantly in registers (root-free, branch-free reciprocals: the dependency chain of the step), one thread
+//     per column forward-substitutes the panel and the right-hand side (column n), then the trailing rows are updated
+//     from the panel: two block barriers per block step;
+//   * the backward substitution reads the factor rows from shared memory, blocked the same way.
+template <int SB_A, int SB_B>
+__device__ bool ba_small_solve_t(const BaParams& P, const double* S, const double* bs, const double* Hpp, const double* bp,
+                                 double lambda, double* M, double* xs) {
     const int n = P.n, ld = P.n + 1, tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    static_assert(BA_THREADS == 256, "8 warps: row residues mod 8");
     __shared__ int s_fail;
     __shared__ double s_rd[BA_SMALL_N];
     if (tid == 0) s_fail = 0;
+    double v[SB_A][SB_B];
+#pragma unroll
+    for (int a = 0; a < SB_A; ++a) {
+        const int r = warp + 8 * a;
+        const int hb = (r / 6) * 36 + (r % 6) * 6 - (r / 6) * 6;  // Hpp offset of (r, c) inside r's diagonal block: hb + c
+#pragma unroll
+        for (int b = 0; b < SB_B; ++b) {
+            const int c = lane + 32 * b;
+            double x = 0.0;
+            if (r < n && c >= r && c < n) {
+                x = __ldcg(S + r * n + c);
+                if (c < (r / 6) * 6 + 6) x += __ldcg(Hpp + hb + c);
+                if (c == r) x += lambda;
+            }
+            if (r < n && c == n) x = __ldcg(bs + r) + __ldcg(bp + r);
+            v[a][b] = x;
+        }
+    }
+    __syncthreads();  // s_fail cleared; M free (the caller's previous phase used it as scratch)
+    for (int j0 = 0; j0 < n; j0 += 6) {
+        // (1) publish the six pivot rows
+#pragma unroll
+        for (int a = 0; a < SB_A; ++a) {
+            const int r = warp + 8 * a;
+            if (r >= j0 && r < j0 + 6) {  // warp-uniform
+#pragma unroll
+                for (int b = 0; b < SB_B; ++b) {
+                    const int c = lane + 32 * b;
+                    if (c >= r && c <= n) M[r * ld + c] = v[a][b];
+                }
+            }
+        }
+        __syncthreads();
+        // (2) diagonal block by every thread, panel columns (and the right-hand side) by one thread each
+        {
+            double D[36], rs[6], G[36];
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) D[r * 6 + c] = (c >= r) ? M[(j0 + r) * ld + j0 + c] : 0.0;
+            const bool ok = ldl6_diag(D, rs, G);
+            for (int c = j0 + 6 + tid; c <= n; c += nt) {
+                double w[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) w[r] = M[(j0 + r) * ld + c];
+#pragma unroll
+                for (int r = 0; r < 6; ++r)
+#pragma unroll
+                    for (int p = 0; p < 6; ++p)
+                        if (p < r) w[r] -= G[p * 6 + r] * w[p];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) M[(j0 + r) * ld + c] = w[r] * rs[r];
+            }
+            if (tid == 0 && !ok) s_fail = 1;
+            __syncthreads();  // panel done; everyone has read the un-factored diagonal block
+            if (tid == nt - 1) {  // the factored diagonal block and its reciprocals: only the backward substitution reads them
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c)
+                        if (c >= r) M[(j0 + r) * ld + j0 + c] = D[r * 6 + c] * rs[r];
+                    s_rd[j0 + r] = rs[r];
+                }
+            }
+        }
+        if (s_fail) break;
+        // (3) rank-6 update of the register-resident trailing rows
+        {
+            const double* W = M + j0 * ld;
+            double wc[SB_B][6];
+#pragma unroll
+            for (int b = 0; b < SB_B; ++b) {
+                const int c = min(lane + 32 * b, n);
+#pragma unroll
+                for (int p = 0; p < 6; ++p) wc[b][p] = W[p * ld + c];
+            }
+            const int a1 = (j0 + 6 - warp + 7) >> 3;  // first row slot of this warp below the panel
+#pragma unroll
+            for (int a = 0; a < SB_A; ++a) {
+                const int r = warp + 8 * a;
+                if (a >= a1 && r < n) {  // warp-uniform
+                    double wr[6];
+#pragma unroll
+                    for (int p = 0; p < 6; ++p) wr[p] = W[p * ld + r];
+#pragma unroll
+                    for (int p = 0; p < 6; ++p)
+#pragma unroll
+                        for (int b = 0; b < SB_B; ++b) v[a][b] -= wr[p] * wc[b][p];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const bool fail = s_fail != 0;
+    if (!fail) {
+        for (int j0 = n - 6; j0 >= 0; j0 -= 6) {
+            double D[36], x[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) D[r * 6 + c] = (c >= r) ? M[(j0 + r) * ld + j0 + c] : 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) x[r] = M[(j0 + r) * ld + n];
+#pragma unroll
+            for (int r = 5; r >= 0; --r) {
+#pragma unroll
+                for (int p = 0; p < 6; ++p)
+                    if (p > r) x[r] -= D[r * 6 + p] * x[p];
+                x[r] *= s_rd[j0 + r];
+            }
+            __syncthreads();
+            for (int r = tid; r < j0; r += nt) {
+                double y = M[r * ld + n];
+#pragma unroll
+                for (int p = 0; p < 6; ++p) y -= M[r * ld + j0 + p] * x[p];
+                M[r * ld + n] = y;
+            }
+            if (tid == 0) {
+#pragma unroll
+                for (int r = 0; r < 6; ++r) M[(j0 + r) * ld + n] = x[r];
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < n; i += nt) xs[i] = M[i * ld + n];
+    }
+    __syncthreads();
+    return !fail;
+}
+
+__device__ bool ba_small_solve(const BaParams& P, const double* S, const double* bs, const double* Hpp, const double* bp,
+                               double lambda, double* M, double* xs) {
+    const int n = P.n, tid = threadIdx.x;
     if (P.pose_only) {
+        __shared__ int s_fail;
+        if (tid == 0) s_fail = 0;
+
         // No landmark vertices: the system is block diagonal (K independent 6x6 blocks Hpp_k + lambda I, right-hand
         // side bp_k; S and bs stay zero), one thread per pose.  The same arithmetic as the dense factorisation applied
         // to a block-diagonal matrix -- the off-diagonal zeros only ever contribute exact zeros -- without its 2 K
@@ -1228,93 +1422,8 @@ __device__ bool ba_small_solve(const BaParams& P, const double* S, const double*
         __syncthreads();
         return s_fail == 0;
     }
-    for (int i = tid; i < n * n; i += nt) {
-        const int r = i / n, c = i - r * n;
-        double v = __ldcg(S + i);
-        if (r / 6 == c / 6 && c >= r) v += __ldcg(Hpp + (r / 6) * 36 + (r % 6) * 6 + (c % 6));
-        if (r == c) v += lambda;
-        M[r * ld + c] = v;
-    }
-    for (int i = tid; i < n; i += nt) M[i * ld + n] = __ldcg(bs + i) + __ldcg(bp + i);
-    __syncthreads();
-    for (int j0 = 0; j0 < n; j0 += 6) {
-        {
-            double D[36];
-#pragma unroll
-            for (int r = 0; r < 6; ++r)
-#pragma unroll
-                for (int c = 0; c < 6; ++c) D[r * 6 + c] = (c >= r) ? M[(j0 + r) * ld + j0 + c] : 0.0;
-            double rinv[6];
-            const bool ok = chol6_diag(D, 6, 0, rinv);
-            for (int c = j0 + 6 + tid; c <= n; c += nt) {
-                double v[6];
-#pragma unroll
-                for (int r = 0; r < 6; ++r) v[r] = M[(j0 + r) * ld + c];
-#pragma unroll
-                for (int r = 0; r < 6; ++r) {
-#pragma unroll
-                    for (int p = 0; p < 6; ++p)
-                        if (p < r) v[r] -= D[p * 6 + r] * v[p];
-                    v[r] *= rinv[r];
-                }
-#pragma unroll
-                for (int r = 0; r < 6; ++r) M[(j0 + r) * ld + c] = v[r];
-            }
-            __syncthreads();
-            if (tid == 0) {
-                if (!ok) s_fail = 1;
-#pragma unroll
-                for (int r = 0; r < 6; ++r) {
-#pragma unroll
-                    for (int c = 0; c < 6; ++c)
-                        if (c >= r) M[(j0 + r) * ld + j0 + c] = D[r * 6 + c];
-                    s_rd[j0 + r] = rinv[r];
-                }
-            }
-        }
-        const int m = n - j0 - 6;
-        for (int e = tid; e < m * (m + 1); e += nt) {
-            const int r = j0 + 6 + e / (m + 1), c = j0 + 6 + e % (m + 1);
-            if (c < r) continue;
-            double v = M[r * ld + c];
-#pragma unroll
-            for (int p = 0; p < 6; ++p) v -= M[(j0 + p) * ld + r] * M[(j0 + p) * ld + c];
-            M[r * ld + c] = v;
-        }
-        __syncthreads();
-        if (s_fail) break;
-    }
-    const bool fail = s_fail != 0;
-    if (!fail) {
-        for (int j0 = n - 6; j0 >= 0; j0 -= 6) {
-            double D[36], x[6];
-#pragma unroll
-            for (int r = 0; r < 6; ++r)
-#pragma unroll
-                for (int c = 0; c < 6; ++c) D[r * 6 + c] = (c >= r) ? M[(j0 + r) * ld + j0 + c] : 0.0;
-#pragma unroll
-            for (int r = 0; r < 6; ++r) x[r] = M[(j0 + r) * ld + n];
-#pragma unroll
-            for (int r = 5; r >= 0; --r) {
-#pragma unroll
-                for (int p = 0; p < 6; ++p)
-                    if (p > r) x[r] -= D[r * 6 + p] * x[p];
-                x[r] *= s_rd[j0 + r];
-            }
-            __syncthreads();
-            for (int r = tid; r < j0; r += nt) {
-                double v = M[r * ld + n];
-#pragma unroll
-                for (int p = 0; p < 6; ++p) v -= M[r * ld + j0 + p] * x[p];
-                M[r * ld + n] = v;
-            }
-            if (tid < 6) M[(j0 + tid) * ld + n] = x[tid];
-            __syncthreads();
-        }
-        for (int i = tid; i < n; i += nt) xs[i] = M[i * ld + n];
-    }
-    __syncthreads();
-    return !fail;
+    if (n <= 63) return ba_small_solve_t<8, 2>(P, S, bs, Hpp, bp, lambda, M, xs);
+    return ba_small_solve_t<BA_SMALL_N / 8, (BA_SMALL_N + 32) / 32>(P, S, bs, Hpp, bp, lambda, M, xs);
 }
 
 __global__ void __launch_bounds__(BA_THREADS)
