@@ -116,9 +116,11 @@ __device__ __forceinline__ const uint8_t* level_ptr(const ImgSrc& src, const uin
 // ------------------------------------------------------------------------------------------------------------
 // K1  resize INTER_LINEAR_EXACT: out = (c0y*(c0x*s00 + c1x*s01) + c1y*(c0x*s10 + c1x*s11) + 32768) >> 16
 // ------------------------------------------------------------------------------------------------------------
-// One thread produces 4 horizontally adjacent output pixels and stores them as one word.  Their source bytes span at
-// most 6 columns (scale 1.2), fetched per source row as up to three aligned words and shifted into place; the
-// horizontal pass of each pixel is one byte permute + one 16x8-bit dot product (IDP.2A).
+// One thread produces 8 horizontally adjacent output pixels (two quads) and stores them as one 64-bit word.  A quad's
+// source bytes span at most 6 columns (scale 1.2), fetched per source row as up to three aligned words and shifted
+// into place; the horizontal pass of each pixel is one byte permute + one 16x8-bit dot product (IDP.2A).  Everything
+// that depends only on the output column -- first source column of the quad, last needed byte, the four byte selectors
+// and the four coefficient pairs -- comes precomputed from the host as 8 words per quad (two 128-bit loads).
 __device__ __forceinline__ void load_window(const uint8_t* p, int last_byte, uint32_t& v0, uint32_t& v1) {
     const uint32_t a = (uint32_t)(uintptr_t)p & 3u;
     const uint32_t* q = reinterpret_cast<const uint32_t*>(p - a);
@@ -134,43 +136,40 @@ __global__ void __launch_bounds__(256)
 resize_level_kernel(ImgSrc src, uint8_t* __restrict__ pyr, const uint32_t* __restrict__ tab, const __grid_constant__ OrbGeom g, int l) {
     const int img = blockIdx.z;
     const OrbLevel& L = g.lv[l];
-    const int x = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int x = (blockIdx.x * 32 + threadIdx.x) * 8;
     const int y = blockIdx.y * 8 + threadIdx.y;
     if (x >= L.w || y >= L.h) return;
     int sp;
     const uint8_t* s = level_ptr(src, pyr, g, img, l - 1, sp);
-    const int sw = g.lv[l - 1].w, sh = g.lv[l - 1].h;
-    const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(&tab[L.xtab_off + x]));  // table regions are 16-byte aligned
-    uint32_t tx[4] = {t4.x, t4.y, t4.z, t4.w};
-#pragma unroll
-    for (int k = 1; k < 4; ++k)
-        if (x + k >= L.w) tx[k] = tx[0];  // columns in the row padding: any in-range value
+    const int sh = g.lv[l - 1].h;
     const uint32_t ty = __ldg(&tab[L.ytab_off + y]);
     const int oy = ty >> 16, c1y = ty & 0xFFFF, c0y = 256 - c1y;
-    const int oy1 = min(oy + 1, sh - 1);
-    const int ox0 = tx[0] >> 16;
-    uint32_t sel[4], coef[4];
-    int last = 0;
+    const uint8_t* r0 = s + (size_t)oy * sp;
+    const uint8_t* r1 = s + (size_t)min(oy + 1, sh - 1) * sp;
+    const uint4* qt = reinterpret_cast<const uint4*>(&tab[L.xtab_off]) + (x >> 2) * 2;  // 8 words per quad
+    uint32_t out[2] = {0u, 0u};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int ox = tx[k] >> 16, c1x = tx[k] & 0xFFFF;
-        const int d0 = ox - ox0, d1 = min(ox + 1, sw - 1) - ox0;
-        sel[k] = (uint32_t)d0 | ((uint32_t)d1 << 4);
-        coef[k] = (uint32_t)(256 - c1x) | ((uint32_t)c1x << 16);
-        last = max(last, d1);
-    }
-    uint32_t a0, a1, b0, b1;
-    load_window(s + (size_t)oy * sp + ox0, last, a0, a1);
-    load_window(s + (size_t)oy1 * sp + ox0, last, b0, b1);
-    uint32_t packed = 0;
+    for (int h = 0; h < 2; ++h) {
+        if (x + 4 * h >= L.w) break;  // the second quad lies in the row padding
+        const uint4 qa = __ldg(qt + 2 * h), coef = __ldg(qt + 2 * h + 1);
+        const int ox0 = qa.x & 0xFFFF, last = qa.x >> 16;
+        uint32_t a0, a1, b0, b1;
+        load_window(r0 + ox0, last, a0, a1);
+        load_window(r1 + ox0, last, b0, b1);
+        const uint32_t cf[4] = {coef.x, coef.y, coef.z, coef.w};
+        uint32_t packed = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t h0 = __dp2a_lo(coef[k], __byte_perm(a0, a1, sel[k]), 0u);
-        const uint32_t h1 = __dp2a_lo(coef[k], __byte_perm(b0, b1, sel[k]), 0u);
-        const uint32_t v = ((uint32_t)c0y * h0 + (uint32_t)c1y * h1 + 32768u) >> 16;
-        packed |= v << (8 * k);
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t sel = (qa.y >> (8 * k)) & 0xFFu;
+            const uint32_t h0 = __dp2a_lo(cf[k], __byte_perm(a0, a1, sel), 0u);
+            const uint32_t h1 = __dp2a_lo(cf[k], __byte_perm(b0, b1, sel), 0u);
+            const uint32_t v = ((uint32_t)c0y * h0 + (uint32_t)c1y * h1 + 32768u) >> 16;
+            packed |= v << (8 * k);
+        }
+        out[h] = packed;
     }
-    *reinterpret_cast<uint32_t*>(&pyr[(size_t)img * g.img_slab + L.off + (size_t)y * L.pitch + x]) = packed;
+    // x is a multiple of 8 and the plane pitch a multiple of 16: the 8 bytes stay inside the (padded) row
+    *reinterpret_cast<uint2*>(&pyr[(size_t)img * g.img_slab + L.off + (size_t)y * L.pitch + x]) = make_uint2(out[0], out[1]);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1063,6 +1062,33 @@ static void resize_table(int dst, int srcn, uint32_t* out) {
     }
 }
 
+// The x table in the form resize_level_kernel consumes: 8 words per quad of output columns --
+//   [0] first source column of the quad | last needed byte (relative) << 16
+//   [1] four byte selectors (d0 | d1 << 4: the two source bytes of pixel k relative to the first column), one per byte
+//   [2], [3] unused     [4..7] coefficient pairs (256 - c1) | c1 << 16 of the four pixels
+// Columns past dst (row padding) repeat the quad's first column.
+static void resize_quad_table(int dst, int srcn, uint32_t* out) {
+    std::vector<uint32_t> t((size_t)dst);
+    resize_table(dst, srcn, t.data());
+    for (int q = 0; 4 * q < dst; ++q) {
+        uint32_t* o = out + 8 * (size_t)q;
+        const int ox0 = (int)(t[4 * q] >> 16);
+        int last = 0;
+        uint32_t sel = 0;
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t e = 4 * q + k < dst ? t[4 * q + k] : t[4 * q];
+            const int ox = (int)(e >> 16), c1 = (int)(e & 0xFFFF);
+            const int d0 = ox - ox0, d1 = (ox + 1 < srcn ? ox + 1 : srcn - 1) - ox0;
+            sel |= (uint32_t)(d0 | (d1 << 4)) << (8 * k);
+            o[4 + k] = (uint32_t)(256 - c1) | ((uint32_t)c1 << 16);
+            if (d1 > last) last = d1;
+        }
+        o[0] = (uint32_t)ox0 | ((uint32_t)last << 16);
+        o[1] = sel;
+        o[2] = o[3] = 0;
+    }
+}
+
 static int orb_set_geometry(vslam_ctx* ctx, int w, int h) {
     OrbState* o = ctx->orb;
     if (o->geom_valid && o->geom.w == w && o->geom.h == h) return VSLAM_OK;
@@ -1097,8 +1123,8 @@ static int orb_set_geometry(vslam_ctx* ctx, int w, int h) {
         L.cand_off = cand;
         L.cand_cap = (L.w * L.h) / 12 + 64;
         cand += L.cand_cap;
-        L.xtab_off = tab;  // 16-byte aligned regions, zero-padded to a multiple of 4 entries (uint4 loads)
-        tab += (L.w + 3) & ~3;
+        L.xtab_off = tab;  // 16-byte aligned regions; x: 8 words per quad of columns (resize_quad_table)
+        tab += 8 * ((L.w + 3) / 4);
         L.ytab_off = tab;
         tab += (L.h + 3) & ~3;
     }
@@ -1109,7 +1135,7 @@ static int orb_set_geometry(vslam_ctx* ctx, int w, int h) {
     if ((size_t)off > o->slab_cap || (size_t)cand > o->cand_cap_total || tab > o->tab_cap) return VSLAM_E_CAPACITY;
     std::vector<uint32_t> t((size_t)tab, 0);
     for (int l = 1; l < ORB_NL; ++l) {
-        resize_table(g.lv[l].w, g.lv[l - 1].w, &t[g.lv[l].xtab_off]);
+        resize_quad_table(g.lv[l].w, g.lv[l - 1].w, &t[g.lv[l].xtab_off]);
         resize_table(g.lv[l].h, g.lv[l - 1].h, &t[g.lv[l].ytab_off]);
     }
     VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1131,7 +1157,7 @@ int vslam_orb_init(vslam_ctx* ctx) {
     const size_t wh = (size_t)((c.max_width + 15) & ~15) * c.max_height;
     o->slab_cap = (size_t)(wh * 3.4) + 8 * 256 + 4096;
     o->cand_cap_total = (size_t)(wh * 3.4 / 12) + 8 * 64 + 1024;
-    o->tab_cap = (int)((c.max_width + c.max_height) * 6.2) + 64;
+    o->tab_cap = (int)(c.max_width * 9.6 + c.max_height * 4.8) + 512;  // x: 2 words per column and level, y: 1
     o->in_pitch = (c.max_width + 15) & ~15;
     const size_t ni = (size_t)c.max_images;
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_pyr, ni * o->slab_cap));
@@ -1222,7 +1248,7 @@ int vslam_orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h
     double* rad = o->d_rad + (size_t)scratch0 * o->kp_cap;
     VSLAM_CUDA(ctx, cudaMemsetAsync(cnt, 0, (size_t)n_img * sizeof(ImgCounters), s));
     for (int l = 1; l < ORB_NL; ++l) {
-        dim3 grid(ceil_div(ceil_div(g.lv[l].w, 4), 32), ceil_div(g.lv[l].h, 8), n_img);
+        dim3 grid(ceil_div(ceil_div(g.lv[l].w, 8), 32), ceil_div(g.lv[l].h, 8), n_img);
         vslam_time_begin(ctx, VK_RESIZE);
         resize_level_kernel<<<grid, dim3(32, 8), 0, s>>>(src, pyr, o->d_tab, g, l);
         vslam_time_end(ctx);
