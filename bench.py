@@ -60,6 +60,7 @@ class ClockSampler:
         self.nvml = None
         self.stop_flag = False
         self.sm, self.mx, self.reasons = [], [], set()
+        self.err = None
 
     def start(self):
         try:
@@ -101,8 +102,9 @@ class ClockSampler:
                 for name, bit in bits.items():
                     if r & bit:
                         self.reasons.add(name)
-            except Exception:
-                pass
+            except Exception as ex:
+                if not self.err:
+                    self.err = repr(ex)
             time.sleep(0.005)
 
     def _read(self):
@@ -111,10 +113,16 @@ class ClockSampler:
 
     def stop(self):
         if self.nvml is not None:
+            try:  # one sample from the calling thread (the GPU is still busy when the timed region has just ended), in
+                # case the polling thread never got the interpreter during a very short region
+                self.sm.append(float(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM)))
+            except Exception:
+                pass
             self.stop_flag = True
             self.t.join(timeout=1.0)
             return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
-                    "samples": len(self.sm), "reasons": sorted(self.reasons), "source": "nvml, 5 ms"}
+                    "samples": len(self.sm), "reasons": sorted(self.reasons), "source": "nvml, 5 ms",
+                    **({"error": self.err} if self.err else {})}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)

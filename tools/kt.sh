@@ -5,5 +5,5 @@ python - <<EOF
 import json
 d=json.load(open("gpurun_out/bench_kt.json"))
 print("value", round(d["value"]), "e2e", d["e2e"].get("one_call_at_a_time"), d["e2e"].get("two_batches_in_flight"), "ms/step", round(d["ms_per_step"],3))
-print(d["roofline"]["kernel_ms_per_step"])
+print(d["roofline"]["kernel_ms_per_step"]); print(d["clocks"])
 EOF
