@@ -15,8 +15,10 @@
 #include <cuda_pipeline.h>
 
 #define MT_THREADS 128
-#define MT_QPT 2                        // queries per thread
-#define MT_TILE_Q (MT_THREADS * MT_QPT) // 256 queries per CTA
+#ifndef MT_QPT
+#define MT_QPT 4                        // queries per thread (2 -> 4: the per-train overhead -- two broadcast loads, the
+#endif                                  // warp minimum, the shared-memory atomic -- is shared by twice the distances)
+#define MT_TILE_Q (MT_THREADS * MT_QPT) // queries per CTA
 #define MT_TILE_T 128                   // trains per CTA
 #define CC_THREADS 1024
 
@@ -32,21 +34,35 @@ struct MatchState {
     int32_t* h_cnt;       // pinned
 };
 
-// 256-bit Hamming distance.  POPC issues on the quarter-rate XU pipe, which bounds this kernel; three carry-save
-// adders (2 LOP3 each, full-rate ALU pipe) compress 7 of the 8 XOR words into one "ones" and three "twos" words, so a
-// distance costs 5 POPC instead of 8 and the two pipes are balanced:
-//   d = popc(s3) + popc(x7) + 2 * (popc(c1) + popc(c2) + popc(c3))
+// 256-bit Hamming distance.  POPC issues on the quarter-rate XU pipe, everything else on the integer ALU pipe, which binds
+// (ncu: alu 87 %, xu 62 % with three carry-save adders).  A carry-save adder (2 LOP3) turns three words into a "ones"
+// and a "twos" word and saves one POPC; MT_CSA of them balance the two pipes.  Measured per 256 pairs x 2000^2 distances:
+// 3 adders / 5 POPC 1.67 ms, 2 adders / 6 POPC 1.55 ms (the default), 1 adder / 7 POPC 1.67 ms, plain 8 POPC 1.88 ms.
+#ifndef MT_CSA
+#define MT_CSA 2
+#endif
 __device__ __forceinline__ uint32_t csa_sum(uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; }
 __device__ __forceinline__ uint32_t csa_carry(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
 
 __device__ __forceinline__ uint32_t hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
     const uint32_t x0 = a0.x ^ b0.x, x1 = a0.y ^ b0.y, x2 = a0.z ^ b0.z, x3 = a0.w ^ b0.w;
     const uint32_t x4 = a1.x ^ b1.x, x5 = a1.y ^ b1.y, x6 = a1.z ^ b1.z, x7 = a1.w ^ b1.w;
+#if MT_CSA == 0
+    return __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3) + __popc(x4) + __popc(x5) + __popc(x6) + __popc(x7);
+#elif MT_CSA == 1
+    const uint32_t s1 = csa_sum(x0, x1, x2), c1 = csa_carry(x0, x1, x2);
+    return __popc(s1) + __popc(x3) + __popc(x4) + __popc(x5) + __popc(x6) + __popc(x7) + 2 * __popc(c1);
+#elif MT_CSA == 2
+    const uint32_t s1 = csa_sum(x0, x1, x2), c1 = csa_carry(x0, x1, x2);
+    const uint32_t s2 = csa_sum(x3, x4, x5), c2 = csa_carry(x3, x4, x5);
+    return __popc(s1) + __popc(s2) + __popc(x6) + __popc(x7) + 2 * (__popc(c1) + __popc(c2));
+#else
     const uint32_t s1 = csa_sum(x0, x1, x2), c1 = csa_carry(x0, x1, x2);
     const uint32_t s2 = csa_sum(x3, x4, x5), c2 = csa_carry(x3, x4, x5);
     const uint32_t s3 = csa_sum(s1, s2, x6), c3 = csa_carry(s1, s2, x6);
     const uint32_t twos = __popc(c1) + __popc(c2) + __popc(c3);
     return __popc(s3) + __popc(x7) + 2 * twos;
+#endif
 }
 
 __global__ void __launch_bounds__(MT_THREADS)
@@ -111,7 +127,9 @@ hamming_argmin_kernel(const uint8_t* __restrict__ query, const int32_t* __restri
             kb = min(kb, kq);
         }
         kb = __reduce_min_sync(0xFFFFFFFFu, kb);
-        if (lane == 0) atomicMin(&s_bw[j], kb);
+        // issued as written: nvcc otherwise wraps a shared-memory atomic in its own warp-aggregation sequence
+        if (lane == 0)
+            asm volatile("red.shared.min.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_bw[j])), "r"(kb) : "memory");
     }
     __syncthreads();
 
