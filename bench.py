@@ -597,8 +597,8 @@ def run_ours(args, rank, world, local_rank):
         hk = (ncu or {}).get("kernels", {}).get("hamming_argmin_kernel")
         roof["hamming"] = {"hbm_GBps": alg["hamming_argmin_kernel"] / (hm * 1e-3) / 1e9,
                            "hbm_frac": alg["hamming_argmin_kernel"] / (hm * 1e-3) / 1e9 / peak,
-                           # 256-bit distance = 8 XOR words, carry-save compressed to 5 POPC (match.cu)
-                           "popc_issued_Tops": B * n_kp_mean * n_kp_mean * 5 / (hm * 1e-3) / 1e12,
+                           # 256-bit distance = 8 XOR words, two carry-save adders -> 6 POPC (match.cu, MT_CSA = 2)
+                           "popc_issued_Tops": B * n_kp_mean * n_kp_mean * 6 / (hm * 1e-3) / 1e12,
                            "popc_pipe_peak_Tops": 148 * 16 * (clk["sm_mhz"] or 1965.0) * 1e6 / 1e12,
                            "ncu_pipes": hk["pipes"] if hk else None,
                            "bound": "integer ALU (LOP3 carry-save + min/compare) with the POPC (XU) pipe second; HBM "

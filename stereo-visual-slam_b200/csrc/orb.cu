@@ -72,6 +72,8 @@ struct OrbState {
     uint8_t* d_pyr;
     uint8_t* d_blur;
     uint32_t* d_tab;      // resize tables
+    uint32_t* d_ftab;     // FAST tile table: level | tile column << 4 | tile row << 16, one entry per tile of an image
+    int ftab_cap;
     uint2* d_cand;        // {x | y << 16, score}
     uint2* d_sel;         // [img][level][SORT_CAP] {x | y << 16, response bits}
     ImgCounters* d_cnt;
@@ -189,7 +191,8 @@ resize_level_kernel(ImgSrc src, uint8_t* __restrict__ pyr, const uint32_t* __res
 //   image tile  : rows ty0-4 .. ty0+33, 96 pixels from gstart = (tx0-6) & ~15 (six aligned 128-bit loads per row)
 // Phases: (1) compass pre-test, every warp compacts the surviving pairs of its rows into its own list (ballot +
 // popc, no atomics, no block barrier); (2) full segment test + score on the list; (3) 3x3 NMS with a sliding
-// 3-row window in registers, border filter, ballot-compacted emit.
+// 3-row window in registers, border filter, emit into the warp's own output segment (positions from ballots).
+// The tile -> (level, column, row) mapping comes from a table built with the geometry (one broadcast load).
 #define FT_W 60
 #define FT_H 30
 #define FT_X0 30
@@ -200,7 +203,7 @@ resize_level_kernel(ImgSrc src, uint8_t* __restrict__ pyr, const uint32_t* __res
 #define FS_WORDS 32                 // words (= pixel pairs) per score-tile row
 #define FAST_WARPS (FAST_THREADS / 32)
 #define FAST_RPW (FS_ROWS / FAST_WARPS)   // score rows per warp
-#define FAST_OUT_CAP 480            // a 60x30 tile holds at most 30 x 15 strict 3x3 maxima
+#define FAST_WOUT 64                // candidates one warp can emit: its 4 output rows hold at most 2 x 15 strict 3x3 maxima
 #define FAST_TT ((uint32_t)FAST_T | ((uint32_t)FAST_T << 16))
 static_assert(FS_ROWS % FAST_WARPS == 0 && FS_WORDS == 32, "one warp per score row, one lane per pixel pair");
 
@@ -210,32 +213,24 @@ __device__ __forceinline__ uint32_t mid16x2(uint32_t lo, uint32_t hi) { return _
 __device__ __forceinline__ bool any_lane_gt_t(uint32_t e) {
     return ((int)(e << 16) > (FAST_T << 16)) | ((int)e > ((FAST_T << 16) | 0xFFFF));
 }
-// shared-memory atomic add issued as written (nvcc otherwise wraps it in its own warp-aggregation sequence)
-__device__ __forceinline__ int atom_add_shared(int* p, int v) {
-    int old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
-    return old;
-}
-
 __global__ void __launch_bounds__(FAST_THREADS)
-fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g, uint2* __restrict__ cand,
-            ImgCounters* __restrict__ cnt, uint32_t* __restrict__ sticky) {
+fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g, const uint32_t* __restrict__ tile_tab,
+            uint2* __restrict__ cand, ImgCounters* __restrict__ cnt, uint32_t* __restrict__ sticky) {
     __shared__ __align__(16) uint32_t s_img[FI_ROWS * FI_WORDS];
     __shared__ uint32_t s_sc[FS_ROWS * FS_WORDS];
     __shared__ uint16_t s_list[FAST_WARPS][2][FAST_RPW * 32];
-    __shared__ uint2 s_out[FAST_OUT_CAP];
+    __shared__ uint2 s_out[FAST_WARPS][FAST_WOUT];
     __shared__ uint32_t s_hist[256];
-    __shared__ int s_nout, s_base;
+    __shared__ int s_wcnt[FAST_WARPS];
+    __shared__ int s_base;
 
     const int img = blockIdx.y;
-    int l = 0;
-#pragma unroll
-    for (int i = 1; i < ORB_NL; ++i)
-        if ((int)blockIdx.x >= g.lv[i].ft_begin) l = i;
+    // tile -> (level, tile column, tile row) from a table the host built with the geometry: one broadcast load
+    // instead of a level search and an integer division in every thread
+    const uint32_t te = __ldg(&tile_tab[blockIdx.x]);
+    const int l = te & 15;
     const OrbLevel& L = g.lv[l];
-    const int t = blockIdx.x - L.ft_begin;
-    const int tyi = t / L.ft_x;
-    const int tx0 = FT_X0 + (t - tyi * L.ft_x) * FT_W, ty0 = FT_Y0 + tyi * FT_H;
+    const int tx0 = FT_X0 + (int)((te >> 4) & 0xFFFu) * FT_W, ty0 = FT_Y0 + (int)(te >> 16) * FT_H;
     int pitch;
     const uint8_t* im = level_ptr(src, pyr, g, img, l, pitch);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -286,7 +281,6 @@ fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__
         }
     }
     s_hist[tid] = 0;  // FAST_THREADS == 256
-    if (tid == 0) s_nout = 0;
     __syncthreads();
 
     // ---- phase 1: compass pre-test on pixel pairs (any 9-arc contains two adjacent compass pixels) ---------------
@@ -385,6 +379,7 @@ fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__
     }
     __syncthreads();
 
+    int n_wout = 0;  // candidates this warp has emitted
     // ---- phase 3: 3x3 NMS (strictly greater) on pixel pairs, border filter, emit ------------------------------------
     // Warp w owns output rows 4w .. 4w+3 and slides down them: per score row `side` = max of the two horizontal
     // neighbours, `full` = max(side, centre); the 8-neighbour maximum of row r is max3(full[r-1], side[r], full[r+1]).
@@ -397,6 +392,8 @@ fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__
         const bool col1 = lane >= 1 && lane <= FT_W / 2 && gx + 1 < W - ORB_EDGE;
         const int ll = max(lane - 1, 0), lr = min(lane + 1, 31);
         uint32_t full_prev = 0, c_cur = 0, side_cur = 0, full_cur = 0;
+        uint2* wout = s_out[wid];  // this warp's own output segment: positions from ballots, no atomics
+        const uint32_t lt = (1u << lane) - 1;
 #pragma unroll
         for (int k = 0; k < OPW + 2; ++k) {
             const int sr = ro0 + k;  // score row (clamped: the rows past the tile only feed dead outputs)
@@ -412,41 +409,45 @@ fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__
                 const bool k0 = ((x & 0xFFFFu) != 0) & col0 & live, k1 = ((x >> 16) != 0) & col1 & live;
                 const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, k0), b1 = __ballot_sync(0xFFFFFFFFu, k1);
                 if (b0 | b1) {
-                    int base = 0;
-                    if (lane == 0) base = atom_add_shared(&s_nout, __popc(b0) + __popc(b1));
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    const uint32_t lt = (1u << lane) - 1;
-                    int pos = base + __popc(b0 & lt) + __popc(b1 & lt);
+                    int pos = n_wout + __popc(b0 & lt) + __popc(b1 & lt);
                     const uint32_t gy = (uint32_t)(ty0 + ro) << 16;
                     if (k0) {
                         const uint32_t sc = (c_cur & 0xFFFFu) - 1;
-                        if (pos < FAST_OUT_CAP) s_out[pos] = make_uint2((uint32_t)gx | gy, sc);
+                        if (pos < FAST_WOUT) wout[pos] = make_uint2((uint32_t)gx | gy, sc);
                         atomicAdd(&s_hist[sc], 1u);
                         ++pos;
                     }
                     if (k1) {
                         const uint32_t sc = (c_cur >> 16) - 1;
-                        if (pos < FAST_OUT_CAP) s_out[pos] = make_uint2((uint32_t)(gx + 1) | gy, sc);
+                        if (pos < FAST_WOUT) wout[pos] = make_uint2((uint32_t)(gx + 1) | gy, sc);
                         atomicAdd(&s_hist[sc], 1u);
                     }
+                    n_wout += __popc(b0) + __popc(b1);
                 }
             }
             full_prev = full_cur;
             c_cur = cw; side_cur = side; full_cur = full;
         }
     }
+    if (lane == 0) s_wcnt[wid] = min(n_wout, FAST_WOUT);
     __syncthreads();
-    const int nout = min(s_nout, FAST_OUT_CAP);
+    int nout = 0, my_off = 0;
+#pragma unroll
+    for (int w = 0; w < FAST_WARPS; ++w) {
+        const int c = s_wcnt[w];
+        if (w < wid) my_off += c;
+        nout += c;
+    }
     if (nout == 0) return;
     ImgCounters* C = &cnt[img];
     if (tid == 0) s_base = (int)atomicAdd(&C->cand_cnt[l], (uint32_t)nout);
     __syncthreads();
-    const int base = s_base;
+    const int base = s_base + my_off;
     uint2* dst = cand + (size_t)img * g.cand_slab + L.cand_off;
-    for (int i = tid; i < nout; i += FAST_THREADS) {
-        if (base + i < L.cand_cap) dst[base + i] = s_out[i];
+    for (int i = lane; i < s_wcnt[wid]; i += 32) {
+        if (base + i < L.cand_cap) dst[base + i] = s_out[wid][i];
     }
-    if (tid == 0 && base + nout > L.cand_cap) {
+    if (tid == 0 && s_base + nout > L.cand_cap) {
         atomicOr(&C->flags, 1u);
         atomicOr(sticky, 1u);
     }
@@ -1140,6 +1141,15 @@ static int orb_set_geometry(vslam_ctx* ctx, int w, int h) {
     }
     VSLAM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     VSLAM_CUDA(ctx, cudaMemcpy(o->d_tab, t.data(), (size_t)tab * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (ft > o->ftab_cap) return VSLAM_E_CAPACITY;
+    {
+        std::vector<uint32_t> ftab((size_t)(ft > 0 ? ft : 1), 0u);
+        for (int l = 0; l < ORB_NL; ++l)
+            for (int ty = 0; ty < g.lv[l].ft_y; ++ty)
+                for (int tx = 0; tx < g.lv[l].ft_x; ++tx)
+                    ftab[(size_t)g.lv[l].ft_begin + ty * g.lv[l].ft_x + tx] = (uint32_t)l | ((uint32_t)tx << 4) | ((uint32_t)ty << 16);
+        VSLAM_CUDA(ctx, cudaMemcpy(o->d_ftab, ftab.data(), ftab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
     o->geom = g;
     o->geom_valid = true;
     return VSLAM_OK;
@@ -1163,6 +1173,8 @@ int vslam_orb_init(vslam_ctx* ctx) {
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_pyr, ni * o->slab_cap));
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_blur, ni * o->slab_cap));
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_tab, (size_t)o->tab_cap * sizeof(uint32_t)));
+    o->ftab_cap = (int)((c.max_width / FT_W + 2) * (c.max_height / FT_H + 2) * 3.4) + ORB_NL * 4;  // sum over the levels < 3.28 x level 0
+    VSLAM_CUDA(ctx, cudaMalloc(&o->d_ftab, (size_t)o->ftab_cap * sizeof(uint32_t)));
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_cand, ni * o->cand_cap_total * sizeof(uint2)));
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_sel, ni * ORB_NL * SORT_CAP * sizeof(uint2)));
     VSLAM_CUDA(ctx, cudaMalloc(&o->d_cnt, ni * sizeof(ImgCounters)));
@@ -1196,6 +1208,7 @@ void vslam_orb_free(vslam_ctx* ctx) {
     cudaFree(o->d_pyr);
     cudaFree(o->d_blur);
     cudaFree(o->d_tab);
+    cudaFree(o->d_ftab);
     cudaFree(o->d_cand);
     cudaFree(o->d_sel);
     cudaFree(o->d_cnt);
@@ -1255,7 +1268,7 @@ int vslam_orb_enqueue(vslam_ctx* ctx, const ImgSrc& src, int n_img, int w, int h
         VSLAM_LAUNCH_CHECK(ctx, "resize_level_kernel");
     }
     vslam_time_begin(ctx, VK_FAST);
-    if (g.total_ft > 0) fast_kernel<<<dim3(g.total_ft, n_img), FAST_THREADS, 0, s>>>(src, pyr, g, cand, cnt, o->d_sticky);
+    if (g.total_ft > 0) fast_kernel<<<dim3(g.total_ft, n_img), FAST_THREADS, 0, s>>>(src, pyr, g, o->d_ftab, cand, cnt, o->d_sticky);
     vslam_time_end(ctx);
     VSLAM_LAUNCH_CHECK(ctx, "fast_kernel");
     vslam_time_begin(ctx, VK_HARRIS_SELECT);
