@@ -1465,7 +1465,6 @@ ba_lm_small_kernel(const __grid_constant__ BaParams P) {
     }
     grid.sync();
     BA_TICK(0);
-    double chi_next = 0.0;  // chi at the linearisation point, carried from the accepted trial of the previous iteration
     for (it = 0; it < P.num_iterations; ++it) {
         const int hb = it & 1;
         {   // BUILD into accumulator set hb; clear the other set for the next outer iteration
@@ -1484,7 +1483,6 @@ ba_lm_small_kernel(const __grid_constant__ BaParams P) {
         grid.sync();
         BA_TICK(1);
         double currentChi = sc->chi_cur;
-        (void)chi_next;
         if (it == 0) {
             chi_first = currentChi;
             __shared__ double s_md;
