@@ -1,5 +1,6 @@
 #!/bin/bash
-# quick per-kernel times of the headline workload (bench.py without its secondary blocks)
+# quick per-kernel times of the headline workload (bench.py without its secondary blocks):
+#   gpurun -- bash tools/quick_kernel_times.sh
 timeout 500 python bench.py --steps 10 --warmup 3 --no-ba --no-sgbm --no-cfg3 --no-street --cpu-seconds 1 > gpurun_out/bench_kt.json 2> gpurun_out/bench_kt.err; tail -3 gpurun_out/bench_kt.err
 python - <<EOF
 import json
