@@ -210,9 +210,6 @@ static_assert(FS_ROWS % FAST_WARPS == 0 && FS_WORDS == 32, "one warp per score r
 __device__ __forceinline__ uint32_t neg16x2(uint32_t a) { return __vadd2(~a, 0x00010001u); }
 // two adjacent pixels starting at the odd pixel of word `lo` (upper half of lo, lower half of hi)
 __device__ __forceinline__ uint32_t mid16x2(uint32_t lo, uint32_t hi) { return __byte_perm(lo, hi, 0x5432); }
-__device__ __forceinline__ bool any_lane_gt_t(uint32_t e) {
-    return ((int)(e << 16) > (FAST_T << 16)) | ((int)e > ((FAST_T << 16) | 0xFFFF));
-}
 __global__ void __launch_bounds__(FAST_THREADS)
 fast_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_constant__ OrbGeom g, const uint32_t* __restrict__ tile_tab,
             uint2* __restrict__ cand, ImgCounters* __restrict__ cnt, uint32_t* __restrict__ sticky) {
