@@ -18,6 +18,7 @@
 // This file is compiled with -fmad=false; fused operations are explicit fmaf() where cv2's AVX2 path fuses.
 #include "common.cuh"
 
+#include <cuda_pipeline.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -34,6 +35,9 @@
 #ifndef DESC_MIN_CTAS
 #define DESC_MIN_CTAS 8
 #endif
+#define DESC_PH 19   // half height of the staged rBRIEF window: |rotated pattern coordinate| <= 13 sqrt(2) + rounding < 19
+#define DESC_PR (2 * DESC_PH + 1)  // rows
+#define DESC_PW 64   // bytes per row: the window starts at the 16-byte boundary left of cx - 19, 39 + 15 <= 64
 
 struct OrbLevel {
     int w, h, pitch;
@@ -906,9 +910,8 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
-// (Measured and rejected, round 2: staging each keypoint's 39 x 39 blurred window in a double-buffered per-warp
-// shared-memory patch -- aligned, coalesced word copies, samples as shared-memory byte reads.  It copies 1.7 KB per
-// keypoint to serve 512 byte samples and needs 110 registers: 1.14 -> 1.94 ms per 512 images.  The direct gathers stay.)
+// (A first version of the shared-memory window staged it through registers -- word loads, word stores, 110 registers --
+// and was slower than the direct gathers, 1.14 -> 1.94 ms per 512 images; the cp.async form below needs none.)
 // One warp describes DESC_KPW keypoints: the intensity-centroid sums and the 256 tests of each keypoint are spread
 // over the 32 lanes, while the per-keypoint scalar work (fastAtan2, the double-precision cos/sin OpenCV uses, the
 // keypoint record) is done once with lane i owning keypoint i instead of 32 times redundantly.
@@ -946,9 +949,26 @@ describe_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const uint8_t* __re
     const uint2 my_e = sel[((size_t)img * ORB_NL + my_l) * SORT_CAP + j];
     const int my_x = my_e.x & 0xFFFF, my_y = my_e.x >> 16;
 
-    // intensity centroid over the radius-15 disc (orb.cpp ICAngles); lanes run along u, rows along v
-    const int u = lane - 15;
-    const int au = abs(u);
+    // intensity centroid over the radius-15 disc (orb.cpp ICAngles).  Lane (g, q) = (lane >> 3, lane & 7) reads the four
+    // pixels u = -16 + 4q .. -13 + 4q of row v = -15 + 4t + g in step t: eight steps cover the 31 rows, the disc is a byte
+    // mask per (step, lane) built once per warp, and both moments are byte dot products (DP4A): m10 += sum u * I,
+    // m01 += v * sum I.  Integer sums: the order does not matter.
+    __shared__ uint32_t s_icm[DESC_WARPS][8][32];
+    const int wq = threadIdx.x >> 5;
+    const int ig = lane >> 3, iq = lane & 7, u0 = -16 + 4 * iq;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int v = -15 + 4 * t + ig;
+        const int um = v <= 15 ? c_umax[v < 0 ? -v : v] : -1;
+        uint32_t m = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (abs(u0 + k) <= um) m |= 0xFFu << (8 * k);
+        s_icm[wq][t][lane] = m;
+    }
+    __syncwarp();
+    const uint32_t uw = (uint32_t)(u0 & 0xFF) | ((uint32_t)((u0 + 1) & 0xFF) << 8) | ((uint32_t)((u0 + 2) & 0xFF) << 16) |
+                        ((uint32_t)((u0 + 3) & 0xFF) << 24);
     int my_m10 = 0, my_m01 = 0;
 #pragma unroll 2
     for (int i = 0; i < nk; ++i) {
@@ -956,17 +976,17 @@ describe_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const uint8_t* __re
         const int l = __shfl_sync(0xFFFFFFFFu, my_l, i);
         int pitch;
         const uint8_t* im = level_ptr(src, pyr, g, img, l, pitch);
+        const uint8_t* rowp = im + (size_t)(y - 15 + ig) * pitch + (x + u0);
         int m10 = 0, m01 = 0;
-        if (lane < 31) {
-            const uint8_t* c = im + (size_t)y * pitch + x + u;
 #pragma unroll
-            for (int v = -15; v <= 15; ++v) {
-                if (au <= c_umax[v < 0 ? -v : v]) {
-                    const int val = c[v * pitch];
-                    m10 += u * val;
-                    m01 += v * val;
-                }
-            }
+        for (int t = 0; t < 8; ++t) {
+            const uint8_t* p = rowp + (size_t)(4 * t) * pitch;
+            const uint32_t a = (uint32_t)(uintptr_t)p & 3u;
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(p - a);
+            const uint32_t word = __funnelshift_r(__ldg(q), __ldg(q + 1), 8 * a) & s_icm[wq][t][lane];
+            const uint32_t vw = (uint32_t)((-15 + 4 * t + ig) & 0xFF) * 0x01010101u;
+            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m10) : "r"(word), "r"(uw));
+            asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(m01) : "r"(word), "r"(vw));
         }
         m10 = __reduce_add_sync(0xFFFFFFFFu, m10);
         m01 = __reduce_add_sync(0xFFFFFFFFu, m01);
@@ -994,18 +1014,44 @@ describe_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const uint8_t* __re
     const float th = __fmul_rn(angle, 0x1.1df46ap-6f);  // (float)(CV_PI/180)
     const float my_a = (float)cos((double)th), my_b = (float)sin((double)th);
 
-    // rotated BRIEF on the blurred level (orb.cpp computeOrbDescriptors, WTA_K = 2); lane = output byte
+    // rotated BRIEF on the blurred level (orb.cpp computeOrbDescriptors, WTA_K = 2); lane = output byte.
+    // The 512 samples of a keypoint are byte gathers scattered over a 37 x 37 window: straight from global memory a
+    // warp-wide gather touches up to 32 cache lines, and the kernel was bound by exactly those L1 wavefronts.  The window
+    // (39 rows x 64 bytes from the 16-byte boundary left of it) is therefore staged into a per-warp shared-memory patch
+    // with cp.async -- no registers in between, the next keypoint's window in flight while this one is sampled.
     const float4* pat = reinterpret_cast<const float4*>(pattern) + lane * 8;
     float4 pt[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) pt[t] = __ldg(&pat[t]);  // (x0, y0, x1, y1) of test 8*lane + t
-#pragma unroll 2
-    for (int i = 0; i < nk; ++i) {
-        const float a = __shfl_sync(0xFFFFFFFFu, my_a, i), b = __shfl_sync(0xFFFFFFFFu, my_b, i);
+    __shared__ __align__(16) uint8_t s_patch[DESC_WARPS][2][DESC_PR * DESC_PW];
+    const int wib = threadIdx.x >> 5;
+    const uint8_t* bplane = blur + (size_t)img * g.img_slab;
+    auto stage = [&](int i, int buf) {
         const int cx = __shfl_sync(0xFFFFFFFFu, my_cx, i), cy = __shfl_sync(0xFFFFFFFFu, my_cy, i);
         const int l = __shfl_sync(0xFFFFFFFFu, my_l, i);
         const int bp = g.lv[l].pitch;
-        const uint8_t* center = blur + (size_t)img * g.img_slab + g.lv[l].off + (size_t)cy * bp + cx;
+        const uint8_t* srcp = bplane + g.lv[l].off + (size_t)(cy - DESC_PH) * bp + ((cx - DESC_PH) & ~15);
+        uint8_t* dstp = s_patch[wib][buf];
+#pragma unroll
+        for (int q0 = 0; q0 < DESC_PR * (DESC_PW / 16); q0 += 32) {
+            const int q = q0 + lane;
+            if (q < DESC_PR * (DESC_PW / 16)) {
+                const int row = q / (DESC_PW / 16), ch = q % (DESC_PW / 16);
+                __pipeline_memcpy_async(dstp + row * DESC_PW + 16 * ch, srcp + (size_t)row * bp + 16 * ch, 16);
+            }
+        }
+        __pipeline_commit();
+    };
+    stage(0, 0);
+    for (int i = 0; i < nk; ++i) {
+        if (i + 1 < nk) stage(i + 1, (i + 1) & 1);  // warp-uniform
+        else __pipeline_commit();                    // keep one group per iteration so that wait_prior(1) means "patch i landed"
+        __pipeline_wait_prior(1);
+        __syncwarp();
+        const float a = __shfl_sync(0xFFFFFFFFu, my_a, i), b = __shfl_sync(0xFFFFFFFFu, my_b, i);
+        const int cx = __shfl_sync(0xFFFFFFFFu, my_cx, i);
+        // sample (ix, iy) lives at row iy + DESC_PH, column ix + (cx - window start)
+        const uint8_t* center = s_patch[wib][i & 1] + DESC_PH * DESC_PW + (cx - ((cx - DESC_PH) & ~15));
         uint32_t byte = 0;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
@@ -1017,12 +1063,14 @@ describe_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const uint8_t* __re
             const float ry1 = __fadd_rn(__fadd_rn(__fmul_rn(p0.z, b), __fmul_rn(p0.w, a)), 12582912.f);
             const int ix0 = __float_as_int(rx0) - 0x4B400000, iy0 = __float_as_int(ry0) - 0x4B400000;
             const int ix1 = __float_as_int(rx1) - 0x4B400000, iy1 = __float_as_int(ry1) - 0x4B400000;
-            const int t0 = center[iy0 * bp + ix0];
-            const int t1 = center[iy1 * bp + ix1];
+            const int t0 = center[iy0 * DESC_PW + ix0];
+            const int t1 = center[iy1 * DESC_PW + ix1];
             byte |= (uint32_t)(t0 < t1) << t;
         }
         desc_out[((size_t)oslot * kp_cap + k0 + i) * 32 + lane] = (uint8_t)byte;
+        __syncwarp();  // everyone has sampled buffer i & 1 before the next iteration's copies overwrite it
     }
+    __pipeline_wait_prior(0);
 }
 
 // ------------------------------------------------------------------------------------------------------------
