@@ -471,7 +471,7 @@ harris_select_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_c
                      uint32_t* __restrict__ sticky) {
     extern __shared__ unsigned long long s_key[];  // SORT_CAP
     __shared__ uint32_t s_h[256];
-    __shared__ uint8_t s_patch[HS_THREADS / 32][96];
+    __shared__ __align__(16) uint8_t s_patch[HS_THREADS / 32][112];  // 9 rows x 3 words
     __shared__ int s_cut, s_n, s_kept;
 
     const int l = blockIdx.x, img = blockIdx.y;
@@ -522,24 +522,45 @@ harris_select_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, const __grid_c
     // Harris response, one warp per candidate (orb.cpp HarrisResponses: blockSize 7, k = 0.04)
     int pitch;
     const uint8_t* im = level_ptr(src, pyr, g, img, l, pitch);
+    // The 9 x 9 patch is fetched as 9 rows x 3 aligned words (27 lanes, one word each) and the two 3 x 3 derivative
+    // kernels of a position become byte dot products (DP4A) on its three 3-byte row windows:
+    //   ix = [-1 0 1; -2 0 2; -1 0 1] . patch,  iy = [-1 -2 -1; 0 0 0; 1 2 1] . patch     (integer sums, order-free)
     for (int e = warp; e < n; e += HS_THREADS / 32) {
         const uint32_t xy = (uint32_t)s_key[e];
         const int x = xy & 0xFFFF, y = xy >> 16;
-        uint8_t* P = s_patch[warp];
-        for (int i = lane; i < 81; i += 32) {
-            const int r = i / 9, c = i - r * 9;
-            P[i] = im[(size_t)(y - 4 + r) * pitch + (x - 4 + c)];
+        uint32_t* P = reinterpret_cast<uint32_t*>(s_patch[warp]);  // [9][3] words; row r starts at the word boundary left of x-4
+        const uint8_t* p0 = im + (size_t)(y - 4) * pitch + (x - 4);
+        if (lane < 27) {
+            const int r = lane / 3, wj = lane - r * 3;
+            const uint8_t* pr = p0 + (size_t)r * pitch;
+            const uint32_t al = (uint32_t)(uintptr_t)pr & 3u;
+            P[lane] = __ldg(reinterpret_cast<const uint32_t*>(pr - al) + wj);
         }
         __syncwarp();
         int a = 0, b = 0, c = 0;
-        for (int i = lane; i < 49; i += 32) {
-            const int r = i / 7, q = i - r * 7;
-            const uint8_t* p = &P[(r + 1) * 9 + q + 1];
-            const int ix = ((int)p[1] - (int)p[-1]) * 2 + ((int)p[-9 + 1] - (int)p[-9 - 1]) + ((int)p[9 + 1] - (int)p[9 - 1]);
-            const int iy = ((int)p[9] - (int)p[-9]) * 2 + ((int)p[9 - 1] - (int)p[-9 - 1]) + ((int)p[9 + 1] - (int)p[-9 + 1]);
-            a += ix * ix;
-            b += iy * iy;
-            c += ix * iy;
+#pragma unroll
+        for (int rnd = 0; rnd < 2; ++rnd) {
+            const int i = lane + 32 * rnd;
+            if (i < 49) {
+                const int r = i / 7, q = i - r * 7;
+                uint32_t w3[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {  // bytes q .. q+2 of patch row r + k
+                    const uint32_t al = (uint32_t)(uintptr_t)(p0 + (size_t)(r + k) * pitch) & 3u;
+                    const uint32_t o = al + (uint32_t)q;
+                    const uint32_t* pw = P + 3 * (r + k) + (o >> 2);
+                    w3[k] = __funnelshift_r(pw[0], (o >> 2) < 2 ? pw[1] : 0u, 8 * (o & 3u));
+                }
+                int ix = 0, iy = 0;
+                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(ix) : "r"(w3[0]), "r"(0x0001'00FFu));  // (-1, 0, 1, 0)
+                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(ix) : "r"(w3[1]), "r"(0x0002'00FEu));  // (-2, 0, 2, 0)
+                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(ix) : "r"(w3[2]), "r"(0x0001'00FFu));
+                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(iy) : "r"(w3[0]), "r"(0x00FF'FEFFu));  // (-1, -2, -1, 0)
+                asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(iy) : "r"(w3[2]), "r"(0x0001'0201u));  // ( 1,  2,  1, 0)
+                a += ix * ix;
+                b += iy * iy;
+                c += ix * iy;
+            }
         }
         a = __reduce_add_sync(0xFFFFFFFFu, a);
         b = __reduce_add_sync(0xFFFFFFFFu, b);
