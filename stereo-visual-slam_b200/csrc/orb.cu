@@ -672,13 +672,15 @@ blur_kernel(ImgSrc src, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ b
     // (zero outside the pitch) and the three reflected bytes on either side of the image are patched in afterwards.
     const bool aligned16 = ((pitch & 15) == 0) && (((uintptr_t)im & 15) == 0);
     if (aligned16) {
-        for (int i = tid; i < n_rows * 10; i += BL_THREADS) {
+        for (int i = tid; i < n_rows * 10; i += BL_THREADS) {  // cp.async: the bytes are consumed as they lie
             const int r = i / 10, ch = i - r * 10;
             const int gy = reflect101(min(ty0 - 3 + r, H + 2), H), gx = tx0 - 16 + 16 * ch;
-            uint4 px = make_uint4(0, 0, 0, 0);
-            if (gx >= 0 && gx < pitch) px = __ldg(reinterpret_cast<const uint4*>(im + (size_t)gy * pitch + gx));
-            *reinterpret_cast<uint4*>(&s_in[r * BL_WORDS + 4 * ch]) = px;
+            uint32_t* dst = &s_in[r * BL_WORDS + 4 * ch];
+            if (gx >= 0 && gx < pitch) __pipeline_memcpy_async(dst, im + (size_t)gy * pitch + gx, 16);
+            else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
         }
+        __pipeline_commit();
+        __pipeline_wait_prior(0);
         __syncthreads();
         uint8_t* s8 = reinterpret_cast<uint8_t*>(s_in);
         const bool fix_l = tx0 == 0, fix_r = W < tx0 + BL_W + 3;
