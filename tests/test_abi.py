@@ -65,3 +65,20 @@ def test_product_path_never_touches_the_oracle():
             if re.search(r"oracle/_build|oracle/_ref|libba_oracle", txt):
                 offenders.append((os.path.relpath(os.path.join(dirpath, f), ROOT), "links the oracle library"))
     assert not offenders, offenders
+
+
+def test_host_pool_without_a_device_and_foreign_pointers(pkg):
+    """vslam_host_alloc hands out pinned blocks or NULL (no device: this container), never throws; vslam_host_free
+    ignores NULL and pointers the pool did not hand out; a freed block is handed out again for the same size."""
+    import ctypes as C
+    lib = pkg.ffi.load_library()
+    lib.vslam_host_free(None)
+    foreign = C.create_string_buffer(64)
+    lib.vslam_host_free(C.cast(foreign, C.c_void_p))  # not ours: ignored
+    p = lib.vslam_host_alloc(1 << 20)
+    if p:  # a CUDA device is present
+        C.memset(p, 0x5A, 1 << 20)
+        lib.vslam_host_free(p)
+        q = lib.vslam_host_alloc((1 << 20) - 100)  # same 64 KiB size class: the block comes back
+        assert q == p
+        lib.vslam_host_free(q)
