@@ -543,6 +543,50 @@ __device__ __forceinline__ bool chol6_diag(double* M, int ld, int j0, double* ri
     return ok;
 }
 
+// branch-free reciprocal and reciprocal square root for well-scaled positive doubles (Hessian pivots): hardware seed
+// (about 20 bits) + two Newton steps to full precision.  Unlike 1.0 / d and rsqrt(d) they carry no special-case branch,
+// so independent ones interleave in the instruction stream.
+__device__ __forceinline__ double rcp_pos(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double rsqrt_pos(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double h = 0.5 * d;
+    y = y * fma(-h * y, y, 1.5);
+    return y * fma(-h * y, y, 1.5);
+}
+
+// Root-free factorisation of a 6x6 diagonal block with the square roots OFF the dependency chain: on return D holds the
+// unnormalised rows u'[r][c] (u'[r][r] = d_r), G[p][r] = u'[p][r] / d_p and rs[r] = 1 / sqrt(d_r); the Cholesky factor is
+// U = diag(rs) u'.  The chain per row is one reciprocal, one multiply and one DFMA; the six rs[] are independent of it.
+__device__ __forceinline__ bool ldl6_diag(double* D, double* rs, double* G) {
+    bool ok = true;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const double d = D[r * 6 + r];
+        if (!(d > 0.0) || !isfinite(d)) ok = false;
+        const double inv = rcp_pos(d);
+        rs[r] = rsqrt_pos(d);
+#pragma unroll
+        for (int r2 = 0; r2 < 6; ++r2) {
+            if (r2 > r) {
+                const double g = D[r * 6 + r2] * inv;
+                G[r * 6 + r2] = g;
+#pragma unroll
+                for (int c = 0; c < 6; ++c)
+                    if (c >= r2) D[r2 * 6 + c] -= g * D[r * 6 + c];
+            }
+        }
+    }
+    return ok;
+}
+
 // small systems (6K <= 160): everything in the shared memory of CTA 0.  The right-hand side rides along as column n of
 // the augmented matrix [S | bs] (so the forward substitution happens inside the factorisation), every thread factors
 // the 6x6 diagonal block redundantly in registers (no serial single-thread stage), and the backward substitution is
@@ -576,21 +620,19 @@ __device__ void ba_phase_solve_cta(const BaParams& P, int slot, double* smem) {
             for (int r = 0; r < 6; ++r)
 #pragma unroll
                 for (int c = 0; c < 6; ++c) D[r * 6 + c] = (c >= r) ? M[(j0 + r) * ld + j0 + c] : 0.0;
-            double rinv[6];
-            const bool ok = chol6_diag(D, 6, 0, rinv);
+            double rinv[6], G[36];
+            const bool ok = ldl6_diag(D, rinv, G);  // root-free, branch-free reciprocals (see ba_small_solve_t)
             for (int c = j0 + 6 + tid; c <= n; c += nt) {  // panel (and the rhs column c == n)
                 double v[6];
 #pragma unroll
                 for (int r = 0; r < 6; ++r) v[r] = M[(j0 + r) * ld + c];
 #pragma unroll
-                for (int r = 0; r < 6; ++r) {
+                for (int r = 0; r < 6; ++r)
 #pragma unroll
                     for (int p = 0; p < 6; ++p)
-                        if (p < r) v[r] -= D[p * 6 + r] * v[p];
-                    v[r] *= rinv[r];
-                }
+                        if (p < r) v[r] -= G[p * 6 + r] * v[p];
 #pragma unroll
-                for (int r = 0; r < 6; ++r) M[(j0 + r) * ld + c] = v[r];
+                for (int r = 0; r < 6; ++r) M[(j0 + r) * ld + c] = v[r] * rinv[r];
             }
             __syncthreads();  // block row done; everyone has read the un-factored diagonal block
             if (tid == 0) {   // nobody reads this diagonal block again before the backward substitution
@@ -599,7 +641,7 @@ __device__ void ba_phase_solve_cta(const BaParams& P, int slot, double* smem) {
                 for (int r = 0; r < 6; ++r) {
 #pragma unroll
                     for (int c = 0; c < 6; ++c)
-                        if (c >= r) M[(j0 + r) * ld + j0 + c] = D[r * 6 + c];
+                        if (c >= r) M[(j0 + r) * ld + j0 + c] = D[r * 6 + c] * rinv[r];
                     s_rd[j0 + r] = rinv[r];
                 }
             }
@@ -683,25 +725,23 @@ __device__ void ba_phase_solve_grid(const BaParams& P, int slot, cg::grid_group&
         const int cend = J0 + nb;  // first column right of the diagonal block
         for (int j = 0; j < nb; j += 6) {
             const int c0 = J0 + j;  // column of this 6x6 block
-            double Dr[36], rinv[6];
+            double Dr[36], rinv[6], G[36];
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
                 for (int c = 0; c < 6; ++c) Dr[r * 6 + c] = (c >= r) ? Pn[(j + r) * ld + c0 + c] : 0.0;
-            const bool ok = chol6_diag(Dr, 6, 0, rinv);  // every thread, in registers
+            const bool ok = ldl6_diag(Dr, rinv, G);  // every thread, in registers; root-free, branch-free reciprocals
             for (int c = c0 + 6 + tid; c < cend; c += nt) {
                 double v[6];
 #pragma unroll
                 for (int r = 0; r < 6; ++r) v[r] = Pn[(j + r) * ld + c];
 #pragma unroll
-                for (int r = 0; r < 6; ++r) {
+                for (int r = 0; r < 6; ++r)
 #pragma unroll
                     for (int q = 0; q < 6; ++q)
-                        if (q < r) v[r] -= Dr[q * 6 + r] * v[q];
-                    v[r] *= rinv[r];
-                }
+                        if (q < r) v[r] -= G[q * 6 + r] * v[q];
 #pragma unroll
-                for (int r = 0; r < 6; ++r) Pn[(j + r) * ld + c] = v[r];
+                for (int r = 0; r < 6; ++r) Pn[(j + r) * ld + c] = v[r] * rinv[r];
             }
             __syncthreads();  // block row done; everyone has read the un-factored 6x6 block
             if (tid == 0) {
@@ -710,7 +750,7 @@ __device__ void ba_phase_solve_grid(const BaParams& P, int slot, cg::grid_group&
                 for (int r = 0; r < 6; ++r) {
 #pragma unroll
                     for (int c = 0; c < 6; ++c)
-                        if (c >= r) Pn[(j + r) * ld + c0 + c] = Dr[r * 6 + c];
+                        if (c >= r) Pn[(j + r) * ld + c0 + c] = Dr[r * 6 + c] * rinv[r];
                     s_rinv[j + r] = rinv[r];
                 }
             }
@@ -1180,50 +1220,6 @@ __device__ void ba_small_schur(const BaParams& P, double lambda, double* __restr
             }
         }
     }
-}
-
-// branch-free reciprocal and reciprocal square root for well-scaled positive doubles (Hessian pivots): hardware seed
-// (about 20 bits) + two Newton steps to full precision.  Unlike 1.0 / d and rsqrt(d) they carry no special-case branch,
-// so independent ones interleave in the instruction stream.
-__device__ __forceinline__ double rcp_pos(double d) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-    double e = fma(-d, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-d, y, 1.0);
-    return fma(y, e, y);
-}
-__device__ __forceinline__ double rsqrt_pos(double d) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-    const double h = 0.5 * d;
-    y = y * fma(-h * y, y, 1.5);
-    return y * fma(-h * y, y, 1.5);
-}
-
-// Root-free factorisation of a 6x6 diagonal block with the square roots OFF the dependency chain: on return D holds the
-// unnormalised rows u'[r][c] (u'[r][r] = d_r), G[p][r] = u'[p][r] / d_p and rs[r] = 1 / sqrt(d_r); the Cholesky factor is
-// U = diag(rs) u'.  The chain per row is one reciprocal, one multiply and one DFMA; the six rs[] are independent of it.
-__device__ __forceinline__ bool ldl6_diag(double* D, double* rs, double* G) {
-    bool ok = true;
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-        const double d = D[r * 6 + r];
-        if (!(d > 0.0) || !isfinite(d)) ok = false;
-        const double inv = rcp_pos(d);
-        rs[r] = rsqrt_pos(d);
-#pragma unroll
-        for (int r2 = 0; r2 < 6; ++r2) {
-            if (r2 > r) {
-                const double g = D[r * 6 + r2] * inv;
-                G[r * 6 + r2] = g;
-#pragma unroll
-                for (int c = 0; c < 6; ++c)
-                    if (c >= r2) D[r2 * 6 + c] -= g * D[r * 6 + c];
-            }
-        }
-    }
-    return ok;
 }
 
 // Every CTA: solve [S + Hpp + lambda I] x = bs + bp by a 6x6-blocked Cholesky factorisation; x -> xs (shared).  Returns
