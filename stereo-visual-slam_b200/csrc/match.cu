@@ -113,23 +113,42 @@ hamming_argmin_kernel(const uint8_t* __restrict__ query, const int32_t* __restri
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
+    if (q0 + MT_TILE_Q <= nq) {
+        // every query of the tile exists (3 of 4 tiles at 2000 keypoints): no validity selects in the loop
 #pragma unroll 4
-    for (int j = 0; j < tile_n; ++j) {
-        const uint4 b0 = s_t[2 * j];
-        const uint4 b1 = s_t[2 * j + 1];
-        uint32_t kb = 0xFFFFFFFFu;
+        for (int j = 0; j < tile_n; ++j) {
+            const uint4 b0 = s_t[2 * j];
+            const uint4 b1 = s_t[2 * j + 1];
+            uint32_t kb = 0xFFFFFFFFu;
 #pragma unroll
-        for (int r = 0; r < MT_QPT; ++r) {
-            const uint32_t d = hamming256(qa[r][0], qa[r][1], b0, b1);
-            const uint32_t kf = (d << 16) | (uint32_t)(t0 + j);
-            best[r] = min(best[r], qv[r] ? kf : 0xFFFFFFFFu);
-            const uint32_t kq = qv[r] ? ((d << 16) | (uint32_t)qi[r]) : 0xFFFFFFFFu;
-            kb = min(kb, kq);
+            for (int r = 0; r < MT_QPT; ++r) {
+                const uint32_t d16 = hamming256(qa[r][0], qa[r][1], b0, b1) << 16;
+                best[r] = min(best[r], d16 | (uint32_t)(t0 + j));
+                kb = min(kb, d16 | (uint32_t)qi[r]);
+            }
+            kb = __reduce_min_sync(0xFFFFFFFFu, kb);
+            if (lane == 0)
+                asm volatile("red.shared.min.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_bw[j])), "r"(kb) : "memory");
         }
-        kb = __reduce_min_sync(0xFFFFFFFFu, kb);
-        // issued as written: nvcc otherwise wraps a shared-memory atomic in its own warp-aggregation sequence
-        if (lane == 0)
-            asm volatile("red.shared.min.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_bw[j])), "r"(kb) : "memory");
+    } else {
+#pragma unroll 4
+        for (int j = 0; j < tile_n; ++j) {
+            const uint4 b0 = s_t[2 * j];
+            const uint4 b1 = s_t[2 * j + 1];
+            uint32_t kb = 0xFFFFFFFFu;
+#pragma unroll
+            for (int r = 0; r < MT_QPT; ++r) {
+                const uint32_t d = hamming256(qa[r][0], qa[r][1], b0, b1);
+                const uint32_t kf = (d << 16) | (uint32_t)(t0 + j);
+                best[r] = min(best[r], qv[r] ? kf : 0xFFFFFFFFu);
+                const uint32_t kq = qv[r] ? ((d << 16) | (uint32_t)qi[r]) : 0xFFFFFFFFu;
+                kb = min(kb, kq);
+            }
+            kb = __reduce_min_sync(0xFFFFFFFFu, kb);
+            // issued as written: nvcc otherwise wraps a shared-memory atomic in its own warp-aggregation sequence
+            if (lane == 0)
+                asm volatile("red.shared.min.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_bw[j])), "r"(kb) : "memory");
+        }
     }
     __syncthreads();
 
